@@ -1,0 +1,180 @@
+/* jcvi_b200 -- C ABI of the B200-native MCscan anchor-detection hot path.
+ *
+ * Drop-in boundary for tanghaibao/jcvi's
+ *     jcvi.compara.blastfilter  ->  jcvi.compara.synteny scan  ->  jcvi.compara.synteny liftover
+ * The reference has no FFI for this path (it is plain Python + one Cython class); the entry
+ * points below are what a maintainer would bind with ctypes/cffi from the reference's own
+ * modules (INTEGRATION.md shows the stubs).  Each entry point cites the reference code it
+ * replaces, file:line relative to the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures;
+ *   - every function returns 0 on success, a negative JX_E* code on failure;
+ *     jx_last_error(ctx) then holds a message (valid until the next call on ctx);
+ *   - input buffers are caller-owned; `*_on_device != 0` means the pointer is a CUDA device
+ *     pointer on the context's device (16-byte aligned), otherwise host memory
+ *     (pinned memory gives full PCIe speed);
+ *   - result structs hold library-owned host arrays, released with jx_*_result_free;
+ *   - one context per GPU; a context is not thread-safe; calls release nothing of the GIL's
+ *     business (ctypes drops the GIL around each call).
+ *   - gene "ranks" are indices into the BED sorted by (natsort_key(seqid), start, accn)
+ *     exactly as src/jcvi/formats/bed.py:147,166-167,196-198 defines Bed.order.
+ */
+#ifndef JCVI_B200_H
+#define JCVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jx_ctx jx_ctx;
+
+enum {
+  JX_OK = 0,
+  JX_ECUDA = -1,        /* CUDA runtime failure (no device, OOM, launch error)              */
+  JX_EARG = -2,         /* bad argument                                                     */
+  JX_EZERODIV = -3,     /* blastfilter.py:235 ZeroDivisionError (score <= 0 with cscore on) */
+  JX_EUNSUPPORTED = -4, /* input outside what the device tokenizer converts exactly
+                           (inf/nan/hex floats, >19 significant digits, names >= 128 bytes) */
+  JX_EDUPANCHOR = -5,   /* synteny.py:397 AssertionError: duplicate (qi,si) anchors         */
+  JX_EINTERNAL = -6
+};
+
+/* ---- context -------------------------------------------------------------------------- */
+int jx_ctx_create(int device, jx_ctx** out);
+void jx_ctx_destroy(jx_ctx* ctx);
+const char* jx_last_error(jx_ctx* ctx);
+const char* jx_version(void);
+/* number of kernels this library launched on ctx since creation (bench.py "gpu_launches") */
+int64_t jx_launch_count(jx_ctx* ctx);
+/* the context's CUDA stream as an integer handle (for event timing on the launching stream) */
+uint64_t jx_stream_handle(jx_ctx* ctx);
+/* accumulated device time (ms, CUDA events on the context's stream) of the K1/K2 tokenizer
+ * launches since the last call with reset != 0, and the number of launches / bytes they read */
+int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes);
+
+/* ---- BED side tables -------------------------------------------------------------------
+ * Replaces the name -> (rank, BedLine) dicts of Bed.order (formats/bed.py:196-198) and the
+ * per-gene attributes the path reads (seqid, start, end, accn).  All arrays are in rank order.
+ */
+typedef struct {
+  int64_t n_genes;
+  const char* names;            /* concatenated accn bytes                                      */
+  const uint32_t* name_off;     /* n_genes + 1 offsets into names                               */
+  const uint8_t* indexable;     /* 1 iff Bed.order[accn] == this rank (later duplicate wins)    */
+  const int32_t* chr_lex;       /* byte-order rank of the gene's seqid among this BED's seqids  */
+  const int32_t* chr_begin;     /* first rank of the gene's seqid run                           */
+  const int32_t* chr_end;       /* one past the last rank of the run                            */
+  const int32_t* length;        /* abs(end - start), start = col2 + 1 (blastfilter.py:171)      */
+  const uint32_t* accn_lexrank; /* rank of accn in byte-order sort of this BED's accns          */
+  const uint32_t* name_id;      /* id of accn in the union of both BEDs' accns (filter_cscore's
+                                   single dict keyed by name, blastfilter.py:227-232)          */
+  int32_t n_chr;
+} jx_bed;
+
+/* side: 0 = query (--qbed), 1 = subject (--sbed) */
+int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed);
+/* is_self: qbed and sbed are the same file (synteny.py:494); q_same_s[qi] = subject rank whose
+ * accn equals the query gene's accn, or -1 (filter_tandem's `b.query == b.subject`,
+ * blastfilter.py:253); n_name_ids = size of the union namespace */
+int jx_pair_setup(jx_ctx* ctx, int is_self, const int32_t* q_same_s, uint32_t n_name_ids);
+
+/* ---- stage 1: blastfilter  (src/jcvi/compara/blastfilter.py:35-161) -------------------- */
+typedef struct {
+  int32_t strip_names;          /* set_stripnames(): gene_name() on both names (cbook.py:308)   */
+  double cscore;                /* --cscore, 0 disables (blastfilter.py:105)                    */
+  int32_t tandem_nmax;          /* --tandem_Nmax, 0 disables (blastfilter.py:113)               */
+  const uint64_t* exclude_keys; /* sorted (qi << 32 | si) pairs of --exclude (205-222), or NULL */
+  int64_t n_exclude;
+  int32_t want_text;            /* also produce the `.filtered` text (write_new_blast 200-202)  */
+  int32_t want_mothers;         /* also return the tandem mother maps (write_localdups 164-185) */
+} jx_filter_opts;
+
+typedef struct {
+  int64_t n;                    /* surviving hits, in output order (score desc, file order)     */
+  int32_t* q_rank;              /* after tandem substitution                                    */
+  int32_t* s_rank;
+  float* score;                 /* float32 as parsed (cblast.pyx:88)                            */
+  uint64_t* line_off;           /* byte offset of the hit's line in the input text              */
+  char* text;                   /* `.filtered` bytes when want_text                             */
+  int64_t text_len;
+  int32_t* q_mother;            /* [n_genes(q)] when want_mothers: mother rank of every gene    */
+  int32_t* s_mother;            /* [n_genes(s)]                                                 */
+  /* counters: 0 lines (non-'#'), 1 mapped records, 2 unmapped names ("not in bed" warnings),
+   * 3 after exclude, 4 after cscore (pre-dedupe), 5 after dedupe, 6 after tandem, 7 '#' lines */
+  int64_t stats[8];
+} jx_filter_result;
+
+int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device,
+                   const jx_filter_opts* opts, jx_filter_result* out);
+void jx_filter_result_free(jx_filter_result* r);
+
+/* ---- stage 2: synteny scan  (src/jcvi/compara/synteny.py:1849-1904) -------------------- */
+typedef struct {
+  int32_t xdist, ydist;         /* --dist (add_arguments, synteny.py:506-523)                   */
+  int32_t min_size;             /* -n / --min_size (_score >= N, synteny.py:432)                */
+  int32_t intrabound;           /* --intrabound, self comparison only (synteny.py:422-427)      */
+} jx_scan_opts;
+
+typedef struct {
+  int64_t n_anchors;
+  int64_t n_blocks;
+  int32_t* q_rank;              /* members, cluster by cluster, each cluster ascending          */
+  int32_t* s_rank;
+  float* score;
+  int64_t* block_start;         /* n_blocks + 1 offsets                                         */
+  int64_t* index;               /* scan_points only: input index of every member                */
+  /* 0 lines, 1 hits imported (read_blast), 2 points in clusters before min_size, 3 '#' lines */
+  int64_t stats[8];
+} jx_scan_result;
+
+/* read_blast (synteny.py:255-297) + batch_scan (437-452) on the text of a `.filtered` file */
+int jx_scan_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
+                 const jx_scan_opts* opts, jx_scan_result* out);
+/* batch_scan / synteny_scan (synteny.py:402-452) on caller-supplied points; group[] is the
+ * chromosome-pair id of each point (ascending id == sorted(chr_pair) order); is_self as in
+ * synteny_scan's argument.  Points must be distinct within a group. */
+int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const float* score,
+                   const int64_t* group, int64_t n, int is_self, const jx_scan_opts* opts,
+                   jx_scan_result* out);
+/* the in-memory hand-over of a blastfilter result to scan: equivalent to writing `.filtered`
+ * with "%.3g" scores (cblast.pyx:17) and reading it back with read_blast */
+int jx_scan_filtered(jx_ctx* ctx, const jx_filter_result* filtered, const jx_scan_opts* opts,
+                     jx_scan_result* out);
+void jx_scan_result_free(jx_scan_result* r);
+
+/* ---- stage 3: synteny liftover  (src/jcvi/compara/synteny.py:1919-1971) ---------------- */
+typedef struct {
+  int64_t n_lifted;             /* new pairs, ordered by (block, sorted chr pair, file order)   */
+  int32_t* q_rank;
+  int32_t* s_rank;
+  float* score;                 /* raw float32 score; the writer prints str(int(score)) + "L"   */
+  int32_t* block;
+  /* per input anchor line (AnchorFile.filter_blocks, compara/base.py:52-83) */
+  uint8_t* accepted;            /* 1 iff the (qi,si) pair is among the de-duplicated raw hits   */
+  float* raw_score;             /* its raw score when accepted                                  */
+  /* 0 lines, 1 hits imported (process_blast_for_liftover), 2 anchors in BED, 3 lifted,
+   * 4 hits resolved by the KD-tree walk (cross-block ties), 5 '#' lines */
+  int64_t stats[8];
+} jx_liftover_result;
+
+/* a_qi/a_si: ranks of every anchor line in file order (-1 when the name is not in the BED);
+ * a_block: its block index (AnchorFile.iter_pairs, compara/base.py:21-27) */
+int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device,
+                     int strip_names, int dist, const int32_t* a_qi, const int32_t* a_si,
+                     const int32_t* a_block, int64_t n_anchor_lines, jx_liftover_result* out);
+void jx_liftover_result_free(jx_liftover_result* r);
+
+/* synteny_liftover (synteny.py:455-473) on caller-supplied integer points: nearest[i] = index
+ * of the anchor cKDTree(anchors, leafsize=16).query(p=1, distance_upper_bound=dist) returns for
+ * point i, or n_anchors when none is strictly closer than dist; dist_out[i] its L1 distance. */
+int jx_nearest_anchor(jx_ctx* ctx, const int64_t* points_xy, int64_t n_points,
+                      const int64_t* anchors_xy, int64_t n_anchors, int dist, int64_t* nearest,
+                      int64_t* dist_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JCVI_B200_H */

@@ -1,0 +1,34 @@
+"""jcvi_b200 -- B200-native (sm_100a) MCscan anchor detection: a drop-in for
+jcvi.compara.blastfilter -> jcvi.compara.synteny scan -> jcvi.compara.synteny liftover.
+
+    from jcvi_b200.compara import blastfilter, synteny
+    blastfilter.main(["A.B.last", "--cscore=0.7"])
+    synteny.scan(["A.B.last.filtered", "A.B.anchors", "--liftover=A.B.last"])
+
+`install()` rebinds the same names inside an importable `jcvi` so that callers such as
+`jcvi.compara.catalog.ortholog` pick up the GPU path unchanged.
+"""
+__version__ = "0.1.0"
+
+
+def install():
+    """Rebind blastfilter.main / synteny.scan / synteny.liftover (and the names catalog imported
+    with `from ... import`, catalog.py:21,23) inside the reference package."""
+    import importlib
+    from .compara import blastfilter as bf, synteny as syn
+
+    jbf = importlib.import_module("jcvi.compara.blastfilter")
+    jsyn = importlib.import_module("jcvi.compara.synteny")
+    jbf.main = bf.main
+    jbf.blastfilter_main = bf.blastfilter_main
+    for name in ("scan", "liftover", "batch_scan", "synteny_scan", "synteny_liftover"):
+        setattr(jsyn, name, getattr(syn, name))
+    try:
+        jcat = importlib.import_module("jcvi.compara.catalog")
+        if hasattr(jcat, "blastfilter_main"):
+            jcat.blastfilter_main = bf.main
+        for name in ("scan", "liftover"):
+            if hasattr(jcat, name):
+                setattr(jcat, name, getattr(syn, name))
+    except ImportError:
+        pass

@@ -1,0 +1,120 @@
+"""ctypes binding of libjcvi_b200.so (C ABI declared in include/jcvi_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a
+context without a CUDA device, raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjcvi_b200.so")
+
+JX_OK, JX_ECUDA, JX_EARG, JX_EZERODIV, JX_EUNSUPPORTED, JX_EDUPANCHOR, JX_EINTERNAL = 0, -1, -2, -3, -4, -5, -6
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_u64p = ctypes.POINTER(ctypes.c_uint64)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class JxBed(ctypes.Structure):
+    _fields_ = [("n_genes", ctypes.c_int64), ("names", ctypes.c_void_p), ("name_off", ctypes.c_void_p),
+                ("indexable", ctypes.c_void_p), ("chr_lex", ctypes.c_void_p), ("chr_begin", ctypes.c_void_p),
+                ("chr_end", ctypes.c_void_p), ("length", ctypes.c_void_p), ("accn_lexrank", ctypes.c_void_p),
+                ("name_id", ctypes.c_void_p), ("n_chr", ctypes.c_int32)]
+
+
+class JxFilterOpts(ctypes.Structure):
+    _fields_ = [("strip_names", ctypes.c_int32), ("cscore", ctypes.c_double), ("tandem_nmax", ctypes.c_int32),
+                ("exclude_keys", ctypes.c_void_p), ("n_exclude", ctypes.c_int64), ("want_text", ctypes.c_int32),
+                ("want_mothers", ctypes.c_int32)]
+
+
+class JxFilterResult(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("q_rank", c_i32p), ("s_rank", c_i32p), ("score", c_f32p),
+                ("line_off", c_u64p), ("text", ctypes.c_void_p), ("text_len", ctypes.c_int64),
+                ("q_mother", c_i32p), ("s_mother", c_i32p), ("stats", ctypes.c_int64 * 8)]
+
+
+class JxScanOpts(ctypes.Structure):
+    _fields_ = [("xdist", ctypes.c_int32), ("ydist", ctypes.c_int32), ("min_size", ctypes.c_int32),
+                ("intrabound", ctypes.c_int32)]
+
+
+class JxScanResult(ctypes.Structure):
+    _fields_ = [("n_anchors", ctypes.c_int64), ("n_blocks", ctypes.c_int64), ("q_rank", c_i32p), ("s_rank", c_i32p),
+                ("score", c_f32p), ("block_start", c_i64p), ("index", c_i64p), ("stats", ctypes.c_int64 * 8)]
+
+
+class JxLiftoverResult(ctypes.Structure):
+    _fields_ = [("n_lifted", ctypes.c_int64), ("q_rank", c_i32p), ("s_rank", c_i32p), ("score", c_f32p),
+                ("block", c_i32p), ("accepted", c_u8p), ("raw_score", c_f32p), ("stats", ctypes.c_int64 * 8)]
+
+
+EXPORTS = [
+    "jx_ctx_create", "jx_ctx_destroy", "jx_last_error", "jx_version", "jx_launch_count", "jx_stream_handle",
+    "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
+    "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
+    "jx_liftover_result_free", "jx_nearest_anchor",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "jcvi_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.jx_last_error.restype = ctypes.c_char_p
+        L.jx_last_error.argtypes = [ctypes.c_void_p]
+        L.jx_version.restype = ctypes.c_char_p
+        L.jx_launch_count.restype = ctypes.c_int64
+        L.jx_launch_count.argtypes = [ctypes.c_void_p]
+        L.jx_stream_handle.restype = ctypes.c_uint64
+        L.jx_stream_handle.argtypes = [ctypes.c_void_p]
+        L.jx_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.jx_ctx_destroy.argtypes = [ctypes.c_void_p]
+        L.jx_ctx_destroy.restype = None
+        L.jx_tokenizer_timing.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_i64p, c_i64p]
+        L.jx_bed_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(JxBed)]
+        L.jx_pair_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32]
+        L.jx_blastfilter.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                     ctypes.POINTER(JxFilterOpts), ctypes.POINTER(JxFilterResult)]
+        L.jx_filter_result_free.argtypes = [ctypes.POINTER(JxFilterResult)]
+        L.jx_filter_result_free.restype = None
+        L.jx_scan_text.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                   ctypes.POINTER(JxScanOpts), ctypes.POINTER(JxScanResult)]
+        L.jx_scan_points.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_int, ctypes.POINTER(JxScanOpts), ctypes.POINTER(JxScanResult)]
+        L.jx_scan_filtered.argtypes = [ctypes.c_void_p, ctypes.POINTER(JxFilterResult), ctypes.POINTER(JxScanOpts),
+                                       ctypes.POINTER(JxScanResult)]
+        L.jx_scan_result_free.argtypes = [ctypes.POINTER(JxScanResult)]
+        L.jx_scan_result_free.restype = None
+        L.jx_liftover_text.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.POINTER(JxLiftoverResult)]
+        L.jx_liftover_result_free.argtypes = [ctypes.POINTER(JxLiftoverResult)]
+        L.jx_liftover_result_free.restype = None
+        L.jx_nearest_anchor.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def as_np(p, n, dtype):
+    """Copy a library-owned array into numpy."""
+    if n == 0 or not p:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(p, shape=(n,)).astype(dtype, copy=True)

@@ -1,0 +1,279 @@
+"""B200-native drop-in for the hot subset of `jcvi.compara.synteny`
+(src/jcvi/compara/synteny.py): `scan`, `liftover`, `batch_scan`, `synteny_scan`,
+`synteny_liftover`, `check_beds`, `get_bed_filenames`, `summary` -- same argv, same return
+values, same `.anchors` / `.lifted.anchors` bytes, same exceptions.  Per-hit work runs in
+libjcvi_b200.so (jx_scan_text, jx_liftover_text, jx_scan_points, jx_nearest_anchor).
+"""
+import os.path as op
+import sys
+from collections.abc import Iterable
+
+import numpy as np
+
+from ..apps_base import OptionParser, logger, read_text_file
+from ..engine import get_engine
+from ..formats.bed import Bed
+from .base import AnchorFile
+
+
+def _score(cluster):
+    """synteny.py:214-219"""
+    x, y = list(zip(*cluster))[:2]
+    return min(len(set(x)), len(set(y)))
+
+
+def get_bed_filenames(hintfile, p, opts):
+    """synteny.py:476-488"""
+    wd, hintfile = op.split(hintfile)
+    if not (opts.qbed and opts.sbed):
+        try:
+            q, s = hintfile.split(".", 2)[:2]
+            opts.qbed = op.join(wd, q + ".bed")
+            opts.sbed = op.join(wd, s + ".bed")
+            logger.debug("Assuming --qbed={0} --sbed={1}".format(opts.qbed, opts.sbed))
+        except:  # noqa: E722  (mirrors the reference)
+            print("Options --qbed and --sbed are required", file=sys.stderr)
+            sys.exit(not p.print_help())
+    return opts.qbed, opts.sbed
+
+
+_BED_CACHE = {}
+
+
+def _load_bed(path):
+    import os
+    st = os.stat(path)
+    key = (op.abspath(path), st.st_mtime_ns, st.st_size)
+    b = _BED_CACHE.get(key)
+    if b is None:
+        if len(_BED_CACHE) > 8:
+            _BED_CACHE.clear()
+        b = _BED_CACHE[key] = Bed(path)
+    return b
+
+
+def check_beds(hintfile, p, opts, sorted=True):
+    """synteny.py:491-503"""
+    qbed_file, sbed_file = get_bed_filenames(hintfile, p, opts)
+    is_self = qbed_file == sbed_file
+    if is_self:
+        logger.debug("Looks like self-self comparison.")
+    qbed = _load_bed(opts.qbed)
+    sbed = qbed if is_self else _load_bed(opts.sbed)
+    return qbed, sbed, qbed.order, sbed.order, is_self
+
+
+def add_arguments(p, args, dist=10):
+    """synteny.py:506-523"""
+    p.set_beds()
+    p.add_argument("--dist", default=dist, type=int, help="Extent of flanking regions to search")
+    opts, args = p.parse_args(args)
+    if len(args) != 2:
+        sys.exit(not p.print_help())
+    blast_file, anchor_file = args
+    return blast_file, anchor_file, opts.dist, opts
+
+
+# ---- library API on points ------------------------------------------------------------------
+def _points_to_arrays(points):
+    qi = np.fromiter((p[0] for p in points), dtype=np.int64, count=len(points))
+    si = np.fromiter((p[1] for p in points), dtype=np.int64, count=len(points))
+    return qi, si
+
+
+def synteny_scan(points, xdist, ydist, N, is_self=False, intrabound=300):
+    """synteny.py:402-434: single linkage on one chromosome pair; returns clusters of the input
+    tuples, each sorted, in the reference's (Grouper insertion) order."""
+    if not points:
+        return []
+    qi, si = _points_to_arrays(points)
+    sc = np.zeros(len(points), dtype=np.float32)
+    res = get_engine().scan_points(qi, si, sc, None, xdist=xdist, ydist=ydist, N=N, is_self=is_self,
+                                   intrabound=intrabound)
+    bs = res.block_start
+    return [sorted(points[j] for j in res.index[bs[b]:bs[b + 1]]) for b in range(res.n_blocks)]
+
+
+def batch_scan(points, xdist=20, ydist=20, N=5, is_self=False, intrabound=300):
+    """synteny.py:437-452: accepts hit objects (.qseqid/.sseqid/.qi/.si/.score) or 3-tuples."""
+    if not points:
+        return []
+    if isinstance(points[0], Iterable) and len(points[0]) == 3:
+        return synteny_scan(list(points), xdist, ydist, N, is_self=is_self, intrabound=intrabound)
+    pairs = sorted(set((b.qseqid, b.sseqid) for b in points))
+    gid = {cp: i for i, cp in enumerate(pairs)}
+    tup = [(b.qi, b.si, b.score) for b in points]
+    qi, si = _points_to_arrays(tup)
+    sc = np.fromiter((t[2] for t in tup), dtype=np.float32, count=len(tup))
+    grp = np.fromiter((gid[(b.qseqid, b.sseqid)] for b in points), dtype=np.int64, count=len(points))
+    res = get_engine().scan_points(qi, si, sc, grp, xdist=xdist, ydist=ydist, N=N, is_self=is_self,
+                                   intrabound=intrabound)
+    bs = res.block_start
+    return [sorted(tup[j] for j in res.index[bs[b]:bs[b + 1]]) for b in range(res.n_blocks)]
+
+
+def synteny_liftover(points, anchors, dist):
+    """synteny.py:455-473: yields (point, nearest anchor) for points with 0 < L1 distance < dist,
+    the nearest anchor being cKDTree's choice among equidistant ones."""
+    points = np.array(points, dtype=int)
+    ppoints = points[:, :2] if points.shape[1] > 2 else points
+    anchors = np.asarray(anchors)
+    near, dd = get_engine().nearest_anchor(ppoints, anchors, dist)
+    n = len(anchors)
+    for point, d, idx in zip(points, dd, near):
+        if idx == n:
+            continue
+        if d == 0:
+            continue
+        yield point, tuple(anchors[idx])
+
+
+# ---- actions -------------------------------------------------------------------------------------
+def summary(args):
+    """synteny.py:1445-1484 (stderr statistics; ValueError when no anchor was found)."""
+    p = OptionParser(summary.__doc__)
+    p.add_argument("--prefix", help="Generate per block stats")
+    opts, args = p.parse_args(args)
+    if len(args) != 1:
+        sys.exit(not p.print_help())
+    (anchorfile,) = args
+    ac = AnchorFile(anchorfile)
+    clusters = ac.blocks
+    if clusters == [[]]:
+        logger.debug("A total of 0 anchor was found. Aborted.")
+        raise ValueError("A total of 0 anchor was found. Aborted.")
+    nclusters = len(clusters)
+    nanchors = [len(c) for c in clusters]
+    nranchors = [_score(c) for c in clusters]
+    print("A total of {0} (NR:{1}) anchors found in {2} clusters.".format(sum(nanchors), sum(nranchors), nclusters),
+          file=sys.stderr)
+
+    def stats(a):
+        a = np.array(a)
+        return "Min={} Max={} N={} Mean={:.2f} SD={:.2f} Median={} Sum={}".format(
+            a.min(), a.max(), a.size, np.mean(a), np.std(a), np.median(a), a.sum())
+
+    print("Stats:", stats(nanchors), file=sys.stderr)
+    print("NR stats:", stats(nranchors), file=sys.stderr)
+    if opts.prefix:
+        pad = len(str(nclusters))
+        for i, c in enumerate(clusters):
+            print("\t".join(("{0}{1:0{2}d}".format(opts.prefix, i + 1, pad), str(len(c)))))
+
+
+def _int_str(x):
+    return str(int(x))
+
+
+def write_anchors(res, qbed, sbed, anchor_file):
+    """scan's writer (synteny.py:1897-1903)."""
+    qa = qbed.tables()["accns"]
+    sa = sbed.tables()["accns"]
+    out = []
+    bs = res.block_start
+    q, s, sc = res.q_rank.tolist(), res.s_rank.tolist(), res.score.astype(np.float64).tolist()
+    for b in range(res.n_blocks):
+        out.append("###\n")
+        for t in range(bs[b], bs[b + 1]):
+            out.append("%s\t%s\t%s\n" % (qa[q[t]], sa[s[t]], _int_str(sc[t])))
+    with open(anchor_file, "w") as fw:
+        fw.write("".join(out))
+
+
+def scan(args):
+    """
+    %prog scan blastfile anchor_file [options]
+
+    pull out syntenic anchors from blastfile based on single-linkage algorithm
+    """
+    p = OptionParser(scan.__doc__)
+    p.add_argument("-n", "--min_size", dest="n", type=int, default=4, help="minimum number of anchors in a cluster")
+    p.add_argument("--intrabound", default=300, type=int,
+                   help="Lower bound of intra-chromosomal blocks (only for self comparison)")
+    p.add_argument("--liftover", help="Scan BLAST file to find extra anchors")
+    p.add_argument("--liftover_dist", type=int, help="Distance to extend from liftover. Defaults to half of --dist")
+    p.set_stripnames()
+
+    blast_file, anchor_file, dist, opts = add_arguments(p, args, dist=20)
+    qbed, sbed, qorder, sorder, is_self = check_beds(blast_file, p, opts)
+    eng = get_engine()
+    eng.load_pair(qbed, sbed, is_self)
+    logger.debug("Chaining distance = {0}".format(dist))
+    res = eng.scan_text(read_text_file(blast_file), strip_names=False, xdist=dist, ydist=dist, N=opts.n,
+                        intrabound=opts.intrabound)
+    logger.debug("A total of %d BLAST imported from `%s`.", res.stats["hits"], blast_file)
+    write_anchors(res, qbed, sbed, anchor_file)
+    summary([anchor_file])
+
+    lo = opts.liftover
+    if not lo:
+        return anchor_file
+    dargs = ["--qbed=" + opts.qbed, "--sbed=" + opts.sbed]
+    if not opts.strip_names:
+        dargs += ["--no_strip_names"]
+    liftover_dist = opts.liftover_dist or dist // 2
+    dargs += ["--dist={}".format(liftover_dist)]
+    return liftover([lo, anchor_file] + dargs)
+
+
+def liftover(args):
+    """
+    %prog liftover blastfile anchorfile [options]
+
+    Typical use for this program is given a list of anchors (syntennic
+    genes), choose from the blastfile the pairs that are close to the anchors.
+    """
+    p = OptionParser(liftover.__doc__)
+    p.set_stripnames()
+    p.set_outfile(outfile=None)
+
+    blast_file, anchor_file, dist, opts = add_arguments(p, args)
+    qbed, sbed, qorder, sorder, is_self = check_beds(blast_file, p, opts)
+    eng = get_engine()
+    eng.load_pair(qbed, sbed, is_self)
+
+    ac = AnchorFile(anchor_file)
+    lines = [(row, bi) for bi, block in enumerate(ac.blocks) for row in block]
+    a_qi = np.fromiter((qorder[r[0]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
+                       dtype=np.int32, count=len(lines))
+    a_si = np.fromiter((sorder[r[1]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
+                       dtype=np.int32, count=len(lines))
+    a_block = np.fromiter((bi for _, bi in lines), dtype=np.int32, count=len(lines))
+    logger.debug("A total of {0} anchors imported.".format(int((a_qi >= 0).sum())))
+
+    res = eng.liftover_text(read_text_file(blast_file), a_qi, a_si, a_block, strip_names=opts.strip_names, dist=dist)
+    logger.debug("A total of %d BLAST imported from `%s`.", res.stats["hits"], blast_file)
+
+    qa = qbed.tables()["accns"]
+    sa = sbed.tables()["accns"]
+    for q, s, sc, b in zip(res.q_rank.tolist(), res.s_rank.tolist(), res.score.astype(np.float64).tolist(),
+                           res.block.tolist()):
+        ac.blocks[b].append((qa[q], sa[s], _int_str(sc) + "L"))
+    logger.debug("%d new pairs found (dist=%d).", res.n_lifted, dist)
+    newanchorfile = opts.outfile or anchor_file.rsplit(".", 1)[0] + ".lifted.anchors"
+    if res.stats["hits"]:
+        # AnchorFile.filter_blocks (compara/base.py:52-83) with `accepted` restricted to the
+        # pairs the anchors file mentions (the device did the lookups)
+        accepted = {}
+        acc, raw = res.accepted.tolist(), res.raw_score.astype(np.float64).tolist()
+        for (row, _), ok, sc in zip(lines, acc, raw):
+            if ok:
+                accepted[(row[0], row[1])] = _int_str(sc)
+        for q, s, sc in zip(res.q_rank.tolist(), res.s_rank.tolist(), res.score.astype(np.float64).tolist()):
+            accepted[(qa[q], sa[s])] = _int_str(sc)
+        ac.filter_blocks(accepted)
+    ac.print_to_file(filename=newanchorfile)
+    summary([newanchorfile])
+    return newanchorfile
+
+
+def main():
+    actions = {"scan": scan, "liftover": liftover, "summary": summary}
+    if len(sys.argv) < 2 or sys.argv[1] not in actions:
+        print("usage: python -m jcvi_b200.compara.synteny {scan,liftover,summary} ...", file=sys.stderr)
+        sys.exit(1)
+    actions[sys.argv[1]](sys.argv[2:])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+// Context, BED side tables and the sort/scan library primitives of libjcvi_b200.so.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "jx_internal.cuh"
+
+namespace {
+struct HostReader {
+  const unsigned char* p;
+  __host__ __device__ inline uint32_t operator()(int i) const { return p[i]; }
+};
+template <class T>
+int upload(jx_ctx* ctx, T** dst, const T* src, size_t n) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  JX_CK(cudaMalloc((void**)dst, (n ? n : 1) * sizeof(T)));
+  if (n) JX_CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return JX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* jx_version(void) { return "jcvi_b200 0.1 (sm_100a)"; }
+
+int jx_ctx_create(int device, jx_ctx** out) {
+  if (!out) return JX_EARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return JX_ECUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return JX_ECUDA;
+  jx_ctx* ctx = new jx_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return JX_ECUDA;
+  }
+  // keep freed scratch memory in the stream-ordered pool between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return JX_OK;
+}
+
+void jx_ctx_destroy(jx_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < 2; ++s) {
+    SideDev& d = ctx->side[s];
+    cudaFree(d.table); cudaFree(d.names); cudaFree(d.name_off); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
+    cudaFree(d.chr_end); cudaFree(d.length); cudaFree(d.lexrank); cudaFree(d.name_id);
+  }
+  cudaFree(ctx->q_same_s);
+  for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* jx_last_error(jx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t jx_launch_count(jx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t jx_stream_handle(jx_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes) {
+  if (!ctx) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  for (auto& ev : ctx->tok_events) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) { ctx->tok_ms_acc += t; ++ctx->tok_launches_acc; }
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  ctx->tok_events.clear();
+  if (ms) *ms = ctx->tok_ms_acc;
+  if (launches) *launches = ctx->tok_launches_acc;
+  if (bytes) *bytes = ctx->tok_bytes;
+  if (reset) { ctx->tok_ms_acc = 0; ctx->tok_launches_acc = 0; ctx->tok_bytes = 0; }
+  return JX_OK;
+}
+
+int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
+  if (!ctx || !bed || side < 0 || side > 1 || bed->n_genes < 0) return JX_EARG;
+  if (bed->n_genes >= (1ll << 31) - 2) { ctx->err = "too many genes"; return JX_EARG; }
+  cudaSetDevice(ctx->device);
+  SideDev& d = ctx->side[side];
+  const int64_t G = bed->n_genes;
+  d.G = G;
+  d.n_chr = bed->n_chr;
+  const size_t blob = G ? bed->name_off[G] : 0;
+  d.h_names.assign(bed->names, bed->names + blob);
+  d.h_off.assign(bed->name_off, bed->name_off + G + 1);
+  d.h_chr_lex.assign(bed->chr_lex, bed->chr_lex + G);
+  // open-addressing table at load factor <= 0.5, built on the host with the same hash the
+  // kernels use (jx_parse.cuh name_hash)
+  uint32_t cap = 16;
+  while ((int64_t)cap < 2 * G + 2) cap <<= 1;
+  std::vector<uint64_t> tab(cap, 0);
+  HostReader rd{(const unsigned char*)bed->names};
+  for (int64_t r = 0; r < G; ++r) {
+    if (bed->indexable && !bed->indexable[r]) continue;
+    uint32_t a = bed->name_off[r], b = bed->name_off[r + 1];
+    if (b - a >= 128u) continue;   // can never match: BLAST names of 128+ bytes are rejected
+    uint64_t h = jx::name_hash(rd, (int)a, (int)b);
+    uint32_t idx = (uint32_t)h & (cap - 1);
+    while (tab[idx]) idx = (idx + 1) & (cap - 1);
+    tab[idx] = (h & 0xFFFFFFFF00000000ull) | (uint64_t)(r + 1);
+  }
+  d.tmask = cap - 1;
+  int rc;
+  if ((rc = upload(ctx, &d.table, tab.data(), tab.size()))) return rc;
+  if ((rc = upload(ctx, &d.names, bed->names, blob))) return rc;
+  if ((rc = upload(ctx, &d.name_off, bed->name_off, (size_t)G + 1))) return rc;
+  if ((rc = upload(ctx, &d.chr_lex, bed->chr_lex, (size_t)G))) return rc;
+  if ((rc = upload(ctx, &d.chr_begin, bed->chr_begin, (size_t)G))) return rc;
+  if ((rc = upload(ctx, &d.chr_end, bed->chr_end, (size_t)G))) return rc;
+  if ((rc = upload(ctx, &d.length, bed->length, (size_t)G))) return rc;
+  if ((rc = upload(ctx, &d.lexrank, bed->accn_lexrank, (size_t)G))) return rc;
+  if ((rc = upload(ctx, &d.name_id, bed->name_id, (size_t)G))) return rc;
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  d.loaded = true;
+  ctx->pair_ready = false;
+  return JX_OK;
+}
+
+int jx_pair_setup(jx_ctx* ctx, int is_self, const int32_t* q_same_s, uint32_t n_name_ids) {
+  if (!ctx || !q_same_s) return JX_EARG;
+  if (!ctx->side[0].loaded || !ctx->side[1].loaded) { ctx->err = "jx_bed_load both sides first"; return JX_EARG; }
+  cudaSetDevice(ctx->device);
+  ctx->is_self = is_self != 0;
+  ctx->n_name_ids = n_name_ids;
+  int rc;
+  if ((rc = upload(ctx, &ctx->q_same_s, q_same_s, (size_t)ctx->side[0].G))) return rc;
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  ctx->pair_ready = true;
+  return JX_OK;
+}
+
+}  // extern "C"
+
+// ---- CUB-backed primitives -------------------------------------------------------------------
+int jx_sort_pairs(jx_ctx* ctx, Arena& arena, uint64_t*& keys, uint32_t*& vals, size_t n, int begin_bit, int end_bit) {
+  if (n == 0) return JX_OK;
+  if (n >= (1ull << 31)) { ctx->err = "sort of >= 2^31 items"; return JX_EARG; }
+  JX_ALLOC(k2, uint64_t, n, false);
+  JX_ALLOC(v2, uint32_t, n, false);
+  cub::DoubleBuffer<uint64_t> dk(keys, k2);
+  cub::DoubleBuffer<uint32_t> dv(vals, v2);
+  size_t tmp = 0;
+  JX_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, begin_bit, end_bit, ctx->stream));
+  JX_ALLOC(t, uint8_t, tmp, false);
+  JX_CK(cub::DeviceRadixSort::SortPairs(t, tmp, dk, dv, (int)n, begin_bit, end_bit, ctx->stream));
+  ++ctx->launches;
+  keys = dk.Current();
+  vals = dv.Current();
+  return JX_OK;
+}
+
+int jx_sort_keys(jx_ctx* ctx, Arena& arena, uint64_t*& keys, size_t n, int begin_bit, int end_bit) {
+  if (n == 0) return JX_OK;
+  if (n >= (1ull << 31)) { ctx->err = "sort of >= 2^31 items"; return JX_EARG; }
+  JX_ALLOC(k2, uint64_t, n, false);
+  cub::DoubleBuffer<uint64_t> dk(keys, k2);
+  size_t tmp = 0;
+  JX_CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)n, begin_bit, end_bit, ctx->stream));
+  JX_ALLOC(t, uint8_t, tmp, false);
+  JX_CK(cub::DeviceRadixSort::SortKeys(t, tmp, dk, (int)n, begin_bit, end_bit, ctx->stream));
+  ++ctx->launches;
+  keys = dk.Current();
+  return JX_OK;
+}
+
+int jx_exclusive_sum(jx_ctx* ctx, Arena& arena, const uint32_t* in, uint32_t* out, size_t n) {
+  if (n == 0) return JX_OK;
+  size_t tmp = 0;
+  JX_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)n, ctx->stream));
+  JX_ALLOC(t, uint8_t, tmp, false);
+  JX_CK(cub::DeviceScan::ExclusiveSum(t, tmp, in, out, (int)n, ctx->stream));
+  ++ctx->launches;
+  return JX_OK;
+}

@@ -1,0 +1,471 @@
+// Stage 1: blastfilter on the GPU (K3-K8 of SURVEY.md section 2).
+//
+// Replaces src/jcvi/compara/blastfilter.py:
+//   49,86-89   stable score-descending sort + first-seen set  -> per (qi,si) run: max score, min line
+//   225-237    filter_cscore (float64 division, strict >)      -> k_select (fused with compaction)
+//   262-284    tandem_grouper                                  -> sort + adjacent-rank unions (lock-free union-find)
+//   164-185    write_localdups (mother = longest, then accn)   -> atomicMax of (length, ~lexrank) per root
+//   240-259    filter_tandem                                   -> mother substitution + second run-best
+//   158-161    write_new_blast                                 -> order by (score desc, line asc), host "%.3g" writer
+// The C-score predicate is applied BEFORE the pair de-duplication: the reference keeps the
+// best-scoring record of each pair and the predicate is monotone in the score for fixed genes,
+// so the surviving record of every pair is the same, while the sort that de-duplicates only
+// sees the ~5-10 % of records that pass.
+#include <thread>
+
+#include "jx_internal.cuh"
+
+namespace {
+
+__global__ void k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ best,
+                         const uint32_t* __restrict__ qnid, const uint32_t* __restrict__ snid, double cscore,
+                         int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
+                         uint32_t* errflag) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    bool keep = false;
+    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
+    if (i < n) {
+      r = __ldcs(recs + i);
+      keep = r.x != JX_NOREC;
+      if (keep && use_cscore) {
+        double bq = (double)__uint_as_float(__ldg(best + __ldg(qnid + r.x)));
+        double bs = (double)__uint_as_float(__ldg(best + __ldg(snid + r.y)));
+        double den = bq > bs ? bq : bs;                       // max(best_score[q], best_score[s])
+        if (den == 0.0) { atomicExch(errflag, 1u); keep = false; }
+        else keep = ((double)__uint_as_float(r.z) / den) > cscore;   // IEEE float64 division, strict >
+      }
+    }
+    uint32_t slot = warp_append(keep, counter);
+    if (keep) { out[slot] = r; out_idx[slot] = i; }
+  }
+}
+
+__global__ void k_make_keys(const uint4* __restrict__ C, uint32_t n, int sb, uint64_t* keys, uint32_t* vals) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint4 r = C[j];
+  keys[j] = ((uint64_t)r.x << sb) | r.y;
+  vals[j] = j;
+}
+
+// per run of equal keys: pick the preferred record. mode 0: (score desc, line asc); mode 1: line asc
+__global__ void k_run_best(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                           const uint4* __restrict__ C, const uint32_t* __restrict__ Cidx, uint32_t n, int mode,
+                           uint32_t* flag, uint32_t* pick) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint64_t k = keys[t];
+  const bool head = (t == 0) || keys[t - 1] != k;
+  flag[t] = head;
+  if (!head) return;
+  uint32_t bj = vals[t];
+  uint32_t bs = mode == 0 ? score_ord(C[bj].z) : 0u, bi = Cidx[bj];
+  for (uint32_t u = t + 1; u < n && keys[u] == k; ++u) {
+    uint32_t j = vals[u];
+    uint32_t s = mode == 0 ? score_ord(C[j].z) : 0u, i = Cidx[j];
+    if (s > bs || (s == bs && i < bi)) { bj = j; bs = s; bi = i; }
+  }
+  pick[t] = bj;
+}
+
+__global__ void k_scatter_pairs(const uint64_t* keys, const uint32_t* vals, const uint32_t* flag, const uint32_t* pos,
+                                uint32_t n, uint64_t* okeys, uint32_t* ovals) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || !flag[t]) return;
+  okeys[pos[t]] = keys[t];
+  if (ovals) ovals[pos[t]] = vals[t];
+}
+
+__global__ void k_eflags(const uint32_t* Kj, const uint4* C, uint32_t n, uint32_t* flag) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) flag[t] = C[Kj[t]].w & 1u;
+}
+
+__global__ void k_swap_keys(const uint64_t* in, uint32_t n, int sb, int qb, uint64_t* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint64_t k = in[t];
+  uint64_t qi = k >> sb, si = k & ((1ull << sb) - 1);
+  out[t] = (si << qb) | qi;
+}
+
+// tandem_grouper: consecutive hits of one gene (sorted by partner rank) on the same seqid and
+// within Nmax ranks are joined
+__global__ void k_tandem_adj(const uint64_t* __restrict__ keys, uint32_t n, int lowbits, const int32_t* __restrict__ chr,
+                             int nmax, uint32_t* parent) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 || t >= n) return;
+  uint64_t a = keys[t - 1], b = keys[t];
+  if ((a >> lowbits) != (b >> lowbits)) return;
+  uint32_t ra = (uint32_t)(a & ((1ull << lowbits) - 1)), rb = (uint32_t)(b & ((1ull << lowbits) - 1));
+  if (chr[ra] == chr[rb] && (int64_t)rb - (int64_t)ra <= nmax) uf_union(parent, ra, rb);
+}
+
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+__global__ void k_flatten(uint32_t* parent, uint32_t n, uint32_t* root) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) root[i] = uf_find(parent, i);
+}
+__device__ __forceinline__ unsigned long long mother_key(int32_t len, uint32_t lexrank) {
+  return ((unsigned long long)(uint32_t)len << 32) | (0xFFFFFFFFu - lexrank);
+}
+__global__ void k_mother1(const uint32_t* root, const int32_t* len, const uint32_t* lex, uint32_t n, unsigned long long* bestkey) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) atomicMax(bestkey + root[g], mother_key(len[g], lex[g]));
+}
+__global__ void k_mother2(const uint32_t* root, const int32_t* len, const uint32_t* lex, uint32_t n,
+                          const unsigned long long* bestkey, uint32_t* mroot) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n && bestkey[root[g]] == mother_key(len[g], lex[g])) mroot[root[g]] = g;
+}
+__global__ void k_mother3(const uint32_t* root, const uint32_t* mroot, uint32_t n, int32_t* mother) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) mother[g] = (int32_t)mroot[root[g]];
+}
+
+__global__ void k_collapse(const uint64_t* Kkey, uint32_t n, int sb, const int32_t* mq, const int32_t* ms,
+                           const int32_t* q_same_s, uint64_t* key2, uint32_t* flag) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint64_t k = Kkey[t];
+  uint32_t qi = (uint32_t)(k >> sb), si = (uint32_t)(k & ((1ull << sb) - 1));
+  int32_t a = mq[qi], b = ms[si];
+  key2[t] = ((uint64_t)(uint32_t)a << sb) | (uint32_t)b;
+  flag[t] = q_same_s[a] != b;          // filter_tandem: `if b.query == b.subject: continue`
+}
+
+__global__ void k_order_keys(const uint32_t* Fj, const uint4* C, const uint32_t* Cidx, uint32_t n, uint64_t* keys) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t j = Fj[t];
+  keys[t] = ((uint64_t)(~score_ord(C[j].z)) << 32) | Cidx[j];
+}
+
+__global__ void k_gather_out(const uint32_t* Fj, uint32_t n, const uint4* C, const uint32_t* Cidx, const int32_t* mq,
+                             const int32_t* ms, const uint64_t* desc, int64_t ntiles, int32_t* oq, int32_t* os,
+                             float* oscore, uint64_t* ooff) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t j = Fj[t];
+  uint4 r = C[j];
+  oq[t] = mq ? mq[r.x] : (int32_t)r.x;
+  os[t] = ms ? ms[r.y] : (int32_t)r.y;
+  oscore[t] = __uint_as_float(r.z);
+  // tile of line i: first tile whose inclusive line count exceeds i
+  const uint64_t i = Cidx[j];
+  int64_t lo = 0, hi = ntiles - 1;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((desc[mid] & ((1ull << 62) - 1)) > i) hi = mid; else lo = mid + 1;
+  }
+  ooff[t] = (uint64_t)lo * JX_TILE + (r.w >> 1);
+}
+
+__global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, uint32_t cnt, uint32_t* len) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  int64_t p = (int64_t)off[t], e = p;
+  while (e < n && !jx::is_term(text[e])) ++e;
+  len[t] = (uint32_t)(e - p) + 1;      // + '\n'
+}
+__global__ void k_copy_lines(const uint8_t* text, const uint64_t* off, const uint32_t* len, const uint32_t* pos,
+                             uint32_t cnt, uint8_t* out) {
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= cnt) return;
+  const uint8_t* src = text + off[w];
+  uint8_t* dst = out + pos[w];
+  uint32_t L = len[w] - 1;
+  for (uint32_t i = lane; i < L; i += 32) dst[i] = src[i];
+  if (lane == 0) dst[L] = '\n';
+}
+
+inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+// flags -> exclusive positions + count (one small D2H)
+int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n, uint32_t*& pos, uint32_t& count) {
+  count = 0;
+  pos = nullptr;
+  if (!n) return JX_OK;
+  JX_ALLOC(p, uint32_t, n, false);
+  int rc = jx_exclusive_sum(ctx, arena, flag, p, n);
+  if (rc) return rc;
+  uint32_t last[2];
+  JX_CK(cudaMemcpyAsync(&last[0], p + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&last[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  count = last[0] + last[1];
+  pos = p;
+  return JX_OK;
+}
+
+// sort (key, j) and keep one record per key; output stays sorted by key
+int dedupe(jx_ctx* ctx, Arena& arena, uint64_t* keys, uint32_t* vals, size_t n, int keybits, const uint4* C,
+           const uint32_t* Cidx, int mode, uint64_t*& Kkey, uint32_t*& Kj, uint32_t& nK) {
+  Kkey = nullptr; Kj = nullptr; nK = 0;
+  if (!n) return JX_OK;
+  int rc = jx_sort_pairs(ctx, arena, keys, vals, n, 0, keybits);
+  if (rc) return rc;
+  JX_ALLOC(flag, uint32_t, n, false);
+  JX_ALLOC(pick, uint32_t, n, false);
+  JX_LAUNCH(k_run_best, nblk(n), 256, 0, keys, vals, C, Cidx, (uint32_t)n, mode, flag, pick);
+  uint32_t* pos;
+  if ((rc = compact_positions(ctx, arena, flag, n, pos, nK))) return rc;
+  JX_ALLOC(ok, uint64_t, nK, false);
+  JX_ALLOC(oj, uint32_t, nK, false);
+  JX_LAUNCH(k_scatter_pairs, nblk(n), 256, 0, keys, pick, flag, pos, (uint32_t)n, ok, oj);
+  Kkey = ok; Kj = oj;
+  return JX_OK;
+}
+
+// the reference's own formatting of one survivor: sscanf with cblast.pyx:15, start/stop
+// normalisation (cblast.pyx:115-120), sprintf with cblast.pyx:17 and the substituted names
+void format_range(const char* lines, const uint32_t* pos, const uint32_t* len, const int32_t* q, const int32_t* s,
+                  size_t lo, size_t hi, const SideDev& Q, const SideDev& S, std::string& out) {
+  char qn[160], sn[160], buf[1024];
+  std::string line;
+  for (size_t t = lo; t < hi; ++t) {
+    line.assign(lines + pos[t], len[t]);
+    float pct = 0, score = 0; double ev = 0; int v[7] = {0, 0, 0, 0, 0, 0, 0};
+    qn[0] = sn[0] = 0;
+    sscanf(line.c_str(), "%127s\t%127s\t%f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lf\t%f", qn, sn, &pct, &v[0], &v[1], &v[2],
+           &v[3], &v[4], &v[5], &v[6], &ev, &score);
+    if (v[3] > v[4]) std::swap(v[3], v[4]);
+    if (v[5] > v[6]) std::swap(v[5], v[6]);
+    const uint32_t qa = Q.h_off[(size_t)q[t]], qb = Q.h_off[(size_t)q[t] + 1];
+    const uint32_t sa = S.h_off[(size_t)s[t]], sb = S.h_off[(size_t)s[t] + 1];
+    out.append(Q.h_names.data() + qa, qb - qa);
+    out.push_back('\t');
+    out.append(S.h_names.data() + sa, sb - sa);
+    int w = snprintf(buf, sizeof buf, "\t%.2f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.2g\t%.3g\n", pct, v[0], v[1], v[2], v[3],
+                     v[4], v[5], v[6], ev, score);
+    out.append(buf, (size_t)w);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void jx_filter_result_free(jx_filter_result* r) {
+  if (!r) return;
+  free(r->q_rank); free(r->s_rank); free(r->score); free(r->line_off); free(r->text); free(r->q_mother); free(r->s_mother);
+  memset(r, 0, sizeof *r);
+}
+
+int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, const jx_filter_opts* opts,
+                   jx_filter_result* out) {
+  if (!ctx || !opts || !out) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  const bool use_cscore = opts->cscore != 0.0;
+  const bool use_tandem = opts->tandem_nmax != 0;
+  int rc;
+
+  // ---- K1/K2 (+ K4 fused): text -> records, per-name best score -------------------------------
+  TokMode mode;
+  mode.strip = opts->strip_names;
+  JX_ALLOC(d_excl, uint64_t, (size_t)std::max<int64_t>(opts->n_exclude, 1), false);
+  if (opts->n_exclude > 0) {
+    JX_CK(cudaMemcpyAsync(d_excl, opts->exclude_keys, (size_t)opts->n_exclude * 8, cudaMemcpyHostToDevice, ctx->stream));
+    mode.excl = d_excl; mode.n_excl = opts->n_exclude;
+  }
+  uint32_t* d_best = nullptr;
+  if (use_cscore) {
+    JX_ALLOC(b, uint32_t, (size_t)ctx->n_name_ids + 1, true);
+    d_best = b; mode.best = b;
+  }
+  TokOut tok;
+  if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+  out->stats[0] = (int64_t)(tok.stats[0] - tok.stats[1]);
+  out->stats[7] = (int64_t)tok.stats[1];
+  out->stats[2] = (int64_t)tok.stats[3];
+  out->stats[1] = (int64_t)(tok.stats[2] + tok.stats[8]);
+  out->stats[3] = (int64_t)tok.stats[2];
+  const uint32_t nrec = tok.n_lines;
+
+  // ---- K5: C-score predicate fused with compaction -------------------------------------------------
+  const size_t capC = (size_t)tok.stats[2] + 1;
+  JX_ALLOC(C, uint4, capC, false);
+  JX_ALLOC(Cidx, uint32_t, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 2, true);
+  if (nrec) {
+    unsigned grid = std::min<unsigned>(nblk(nrec), 148u * 16u);
+    JX_LAUNCH(k_select, grid, 256, 0, tok.recs, nrec, d_best, Q.name_id, S.name_id, opts->cscore, use_cscore ? 1 : 0, C,
+              Cidx, d_cnt, d_cnt + 1);
+  }
+  uint32_t h_cnt[2] = {0, 0};
+  JX_CK(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (h_cnt[1]) { ctx->err = "float division by zero"; return JX_EZERODIV; }
+  const uint32_t nC = h_cnt[0];
+  out->stats[4] = nC;
+
+  // ---- K3: per-pair best record (sorted by (qi, si)) ----------------------------------------------------
+  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+  uint64_t* Kkey = nullptr; uint32_t* Kj = nullptr; uint32_t nK = 0;
+  {
+    JX_ALLOC(keys, uint64_t, nC, false);
+    JX_ALLOC(vals, uint32_t, nC, false);
+    if (nC) JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
+    if ((rc = dedupe(ctx, arena, keys, vals, nC, sb + qb, C, Cidx, 0, Kkey, Kj, nK))) return rc;
+  }
+  out->stats[5] = nK;
+
+  // ---- K6: tandem families + mothers -----------------------------------------------------------------------
+  int32_t *d_mq = nullptr, *d_ms = nullptr;
+  uint32_t* Fj = Kj; uint32_t nF = nK;
+  if (use_tandem) {
+    const uint32_t Gq = (uint32_t)Q.G, Gs = (uint32_t)S.G;
+    JX_ALLOC(parent_q, uint32_t, Gq, false);
+    uint32_t* parent_s = parent_q;
+    JX_LAUNCH(k_iota, nblk(std::max(Gq, 1u)), 256, 0, parent_q, Gq);
+    if (!ctx->is_self) {
+      JX_ALLOC(ps, uint32_t, Gs, false);
+      parent_s = ps;
+      JX_LAUNCH(k_iota, nblk(std::max(Gs, 1u)), 256, 0, parent_s, Gs);
+    }
+    if (nK) {
+      JX_ALLOC(ef, uint32_t, nK, false);
+      JX_LAUNCH(k_eflags, nblk(nK), 256, 0, Kj, C, nK, ef);
+      uint32_t* pos; uint32_t nT;
+      if ((rc = compact_positions(ctx, arena, ef, nK, pos, nT))) return rc;
+      if (nT) {
+        JX_ALLOC(Tk, uint64_t, nT, false);
+        JX_LAUNCH(k_scatter_pairs, nblk(nK), 256, 0, Kkey, (const uint32_t*)nullptr, ef, pos, nK, Tk, (uint32_t*)nullptr);
+        // flip=False: per query, subject ranks ascending -> subject families
+        JX_LAUNCH(k_tandem_adj, nblk(nT), 256, 0, Tk, nT, sb, S.chr_lex, opts->tandem_nmax, parent_s);
+        // flip=True: per subject, query ranks ascending -> query families
+        JX_ALLOC(Tk2, uint64_t, nT, false);
+        JX_LAUNCH(k_swap_keys, nblk(nT), 256, 0, Tk, nT, sb, qb, Tk2);
+        uint64_t* Tk2s = Tk2;
+        if ((rc = jx_sort_keys(ctx, arena, Tk2s, nT, 0, sb + qb))) return rc;
+        JX_LAUNCH(k_tandem_adj, nblk(nT), 256, 0, Tk2s, nT, qb, Q.chr_lex, opts->tandem_nmax, parent_q);
+      }
+    }
+    auto mothers = [&](uint32_t* parent, const SideDev& D, int32_t*& d_m) -> int {
+      const uint32_t G = (uint32_t)D.G;
+      JX_ALLOC(root, uint32_t, G, false);
+      JX_ALLOC(bk, unsigned long long, G, true);
+      JX_ALLOC(mroot, uint32_t, G, false);
+      JX_ALLOC(m, int32_t, G, false);
+      if (G) {
+        JX_LAUNCH(k_flatten, nblk(G), 256, 0, parent, G, root);
+        JX_LAUNCH(k_mother1, nblk(G), 256, 0, root, D.length, D.lexrank, G, bk);
+        JX_LAUNCH(k_mother2, nblk(G), 256, 0, root, D.length, D.lexrank, G, bk, mroot);
+        JX_LAUNCH(k_mother3, nblk(G), 256, 0, root, mroot, G, m);
+      }
+      d_m = m;
+      return JX_OK;
+    };
+    if ((rc = mothers(parent_q, Q, d_mq))) return rc;
+    if (ctx->is_self) d_ms = d_mq;
+    else if ((rc = mothers(parent_s, S, d_ms))) return rc;
+
+    // ---- K7: substitute mothers, drop q == s, second per-pair best --------------------------------------
+    nF = 0; Fj = nullptr;
+    if (nK) {
+      JX_ALLOC(key2, uint64_t, nK, false);
+      JX_ALLOC(fl, uint32_t, nK, false);
+      JX_LAUNCH(k_collapse, nblk(nK), 256, 0, Kkey, nK, sb, d_mq, d_ms, ctx->q_same_s, key2, fl);
+      uint32_t* pos; uint32_t nM;
+      if ((rc = compact_positions(ctx, arena, fl, nK, pos, nM))) return rc;
+      JX_ALLOC(k3, uint64_t, nM, false);
+      JX_ALLOC(v3, uint32_t, nM, false);
+      if (nM) JX_LAUNCH(k_scatter_pairs, nblk(nK), 256, 0, key2, Kj, fl, pos, nK, k3, v3);
+      uint64_t* Fkey;
+      if ((rc = dedupe(ctx, arena, k3, v3, nM, sb + qb, C, Cidx, 0, Fkey, Fj, nF))) return rc;
+    }
+  }
+  out->stats[6] = nF;
+
+  // ---- K8: output order (score desc, line asc) and gather ----------------------------------------------------
+  out->n = nF;
+  out->q_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
+  out->s_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
+  out->score = (float*)malloc(sizeof(float) * (nF + 1));
+  out->line_off = (uint64_t*)malloc(sizeof(uint64_t) * (nF + 1));
+  if (nF) {
+    JX_ALLOC(okeys, uint64_t, nF, false);
+    JX_LAUNCH(k_order_keys, nblk(nF), 256, 0, Fj, C, Cidx, nF, okeys);
+    uint64_t* ok = okeys; uint32_t* ov = Fj;
+    {  // sort needs a private copy of the values
+      JX_ALLOC(vcopy, uint32_t, nF, false);
+      JX_CK(cudaMemcpyAsync(vcopy, Fj, nF * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      ov = vcopy;
+    }
+    if ((rc = jx_sort_pairs(ctx, arena, ok, ov, nF, 0, 64))) return rc;
+    JX_ALLOC(oq, int32_t, nF, false);
+    JX_ALLOC(os, int32_t, nF, false);
+    JX_ALLOC(osc, float, nF, false);
+    JX_ALLOC(ooff, uint64_t, nF, false);
+    JX_LAUNCH(k_gather_out, nblk(nF), 256, 0, ov, nF, C, Cidx, d_mq, d_ms, tok.desc, tok.ntiles, oq, os, osc, ooff);
+    JX_CK(cudaMemcpyAsync(out->q_rank, oq, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->s_rank, os, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->score, osc, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->line_off, ooff, nF * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (opts->want_text) {
+      // gather the surviving lines on the device, format on the host with the reference's own
+      // sscanf/sprintf pair (cblast.pyx:15,17)
+      JX_ALLOC(len, uint32_t, nF, false);
+      JX_ALLOC(pos, uint32_t, nF, false);
+      JX_LAUNCH(k_line_len, nblk(nF), 256, 0, tok.d_text, tok.nbytes, ooff, nF, len);
+      if ((rc = jx_exclusive_sum(ctx, arena, len, pos, nF))) return rc;
+      std::vector<uint32_t> hlen(nF), hpos(nF);
+      JX_CK(cudaMemcpyAsync(hlen.data(), len, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(hpos.data(), pos, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaStreamSynchronize(ctx->stream));
+      const uint64_t total = (uint64_t)hpos[nF - 1] + hlen[nF - 1];
+      if (total >= 0xFFFFFFFFull) { ctx->err = "surviving lines exceed 4 GiB"; return JX_EUNSUPPORTED; }
+      JX_ALLOC(packed, uint8_t, (size_t)total, false);
+      JX_LAUNCH(k_copy_lines, nblk((size_t)nF * 32), 256, 0, tok.d_text, ooff, len, pos, nF, packed);
+      std::vector<char> hl((size_t)total);
+      JX_CK(cudaMemcpyAsync(hl.data(), packed, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaStreamSynchronize(ctx->stream));
+      unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      if (nF < 4096) nt = 1;
+      std::vector<std::string> parts(nt);
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) {
+        size_t lo = (size_t)nF * t / nt, hi = (size_t)nF * (t + 1) / nt;
+        th.emplace_back([&, t, lo, hi]() {
+          format_range(hl.data(), hpos.data(), hlen.data(), out->q_rank, out->s_rank, lo, hi, Q, S, parts[t]);
+        });
+      }
+      for (auto& x : th) x.join();
+      size_t tl = 0;
+      for (auto& p : parts) tl += p.size();
+      out->text = (char*)malloc(tl + 1);
+      out->text_len = (int64_t)tl;
+      size_t o = 0;
+      for (auto& p : parts) { memcpy(out->text + o, p.data(), p.size()); o += p.size(); }
+      out->text[tl] = 0;
+    }
+  } else if (opts->want_text) {
+    out->text = (char*)calloc(1, 1);
+    out->text_len = 0;
+  }
+  if (opts->want_mothers) {
+    out->q_mother = (int32_t*)malloc(sizeof(int32_t) * (size_t)(Q.G + 1));
+    out->s_mother = (int32_t*)malloc(sizeof(int32_t) * (size_t)(S.G + 1));
+    if (use_tandem) {
+      if (Q.G) JX_CK(cudaMemcpyAsync(out->q_mother, d_mq, (size_t)Q.G * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      if (S.G) JX_CK(cudaMemcpyAsync(out->s_mother, d_ms, (size_t)S.G * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      for (int64_t g = 0; g < Q.G; ++g) out->q_mother[g] = (int32_t)g;
+      for (int64_t g = 0; g < S.G; ++g) out->s_mother[g] = (int32_t)g;
+    }
+  }
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  JX_CK(cudaGetLastError());
+  return JX_OK;
+}
+
+}  // extern "C"

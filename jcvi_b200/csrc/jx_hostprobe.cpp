@@ -1,0 +1,83 @@
+// Test tooling: exposes the host build of jx_parse.cuh so that the CPU test-suite can check
+// the tokenizer arithmetic against glibc (strtof / strtod / sscanf / printf) without a GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "jx_parse.cuh"
+
+namespace {
+struct PtrReader { const unsigned char* p; inline uint32_t operator()(int i) const { return p[i]; } };
+}
+
+extern "C" {
+
+// returns 1 ok / 0 hard / -1 no conversion; *consumed = chars consumed
+int probe_f32(const char* s, float* out, int* consumed) {
+  PtrReader rd{(const unsigned char*)s};
+  jx::Dec d;
+  int e = (int)strlen(s);
+  int q = jx::scan_decimal(rd, 0, e, d);
+  *consumed = q;
+  if (d.special) return 0;
+  if (!d.ok) return -1;
+  return jx::dec_to_f32(d, *out) ? 1 : 0;
+}
+
+// returns 1/0 for (strtod(s) < 1e-10), -1 hard, -2 no conversion
+int probe_lt1e10(const char* s) {
+  PtrReader rd{(const unsigned char*)s};
+  jx::Dec d;
+  jx::scan_decimal(rd, 0, (int)strlen(s), d);
+  if (d.special) return -1;
+  if (!d.ok) return -2;
+  return jx::dec_lt_1e10(d);
+}
+
+int probe_round3g(float x, float* out) { return jx::round3g_f32(x, *out) ? 1 : 0; }
+
+// bulk check of round3g against glibc for every float32 with bit patterns in [lo, hi) step
+// returns number of mismatches; first mismatching bit pattern in *bad
+long probe_round3g_range(unsigned lo, unsigned hi, unsigned step, unsigned* bad, long* unsupported) {
+  long mism = 0; *unsupported = 0;
+  char buf[64];
+  for (unsigned long u = lo; u < hi; u += step) {
+    float x = jx::bits_to_float((uint32_t)u), got;
+    if (!jx::round3g_f32(x, got)) { ++*unsupported; continue; }
+    snprintf(buf, sizeof buf, "%.3g", (double)x);
+    float want = strtof(buf, nullptr);
+    if (jx::float_to_bits(want) != jx::float_to_bits(got)) { if (!mism) *bad = (unsigned)u; ++mism; }
+  }
+  return mism;
+}
+
+unsigned long long probe_hash(const char* s, int n) {
+  PtrReader rd{(const unsigned char*)s};
+  return jx::name_hash(rd, 0, n);
+}
+
+int probe_strip(const char* s, int n) {
+  PtrReader rd{(const unsigned char*)s};
+  int b = n;
+  jx::strip_isoform(rd, 0, b);
+  return b;
+}
+
+// tokenize one line (no terminator needed); outputs spans/score/nconv/eflag/flags
+int probe_line(const char* s, int n, int* spans, float* score, int* nconv, int* eflag) {
+  PtrReader rd{(const unsigned char*)s};
+  jx::LineTok t;
+  jx::tokenize_line(rd, 0, n, t);
+  spans[0] = t.qa; spans[1] = t.qb; spans[2] = t.sa; spans[3] = t.sb;
+  *score = t.score; *nconv = t.nconv; *eflag = t.eflag;
+  return (t.hard ? 1 : 0) | (t.longname ? 2 : 0);
+}
+
+// the reference's own parse of the same line, via glibc sscanf with the cblast.pyx:15 format
+int probe_line_glibc(const char* s, char* q, char* sb, float* score, double* evalue, int* ints) {
+  float pct = 0; *score = 0; *evalue = 0; q[0] = sb[0] = 0;
+  for (int i = 0; i < 7; ++i) ints[i] = 0;
+  return sscanf(s, "%127s\t%127s\t%f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lf\t%f", q, sb, &pct, ints, ints + 1, ints + 2,
+                ints + 3, ints + 4, ints + 5, ints + 6, evalue, score);
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Internal declarations shared by the translation units of libjcvi_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jcvi_b200.h"
+#include "jx_parse.cuh"
+
+// ---- records ---------------------------------------------------------------------------------
+// One 16-byte record per input line, indexed by the line's ordinal in the text (so the record
+// index IS the file order the reference's first-seen / stable-sort rules refer to).
+//   x = query rank  (0xFFFFFFFF: no record -- '#' line, unmapped name, dropped self hit ...)
+//   y = subject rank
+//   z = float32 score bits (cblast.pyx:88)
+//   w = (byte offset of the line inside its 8 KiB tile << 1) | (evalue < 1e-10)
+#define JX_NOREC 0xFFFFFFFFu
+
+constexpr int JX_TOK_THREADS = 256;
+constexpr int JX_SEG = 32;                               // bytes of the tile owned by one thread
+constexpr int JX_TILE = JX_TOK_THREADS * JX_SEG;         // 8192
+constexpr int JX_OVER = 1024;                            // look-ahead staged in shared memory
+constexpr int JX_WIN = JX_TILE + JX_OVER;
+
+struct SideDev {
+  int64_t G = 0;
+  int32_t n_chr = 0;
+  uint64_t* table = nullptr;   // open addressing: (tag32 << 32) | (rank + 1), 0 = empty
+  uint32_t tmask = 0;
+  char* names = nullptr;
+  uint32_t* name_off = nullptr;
+  int32_t *chr_lex = nullptr, *chr_begin = nullptr, *chr_end = nullptr, *length = nullptr;
+  uint32_t *lexrank = nullptr, *name_id = nullptr;
+  std::vector<char> h_names;
+  std::vector<uint32_t> h_off;
+  std::vector<int32_t> h_chr_lex;
+  bool loaded = false;
+};
+
+struct jx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  SideDev side[2];
+  bool is_self = false;
+  bool pair_ready = false;
+  int32_t* q_same_s = nullptr;
+  uint32_t n_name_ids = 0;
+  std::string err;
+  int64_t launches = 0;
+  // tokenizer timing (CUDA events on `stream`)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
+  int64_t tok_bytes = 0;
+  double tok_ms_acc = 0;
+  int64_t tok_launches_acc = 0;
+};
+
+#define JX_CK(call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      return JX_ECUDA;                                                                      \
+    }                                                                                       \
+  } while (0)
+
+#define JX_LAUNCH(kernel, grid, block, smem, ...)                                           \
+  do {                                                                                      \
+    kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                          \
+    ++ctx->launches;                                                                        \
+  } while (0)
+
+// stream-ordered scratch allocations, released when the Arena goes out of scope
+struct Arena {
+  jx_ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit Arena(jx_ctx* c) : ctx(c) {}
+  ~Arena() {
+    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+  }
+  template <class T>
+  T* alloc(size_t n, bool zero = false) {
+    void* p = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    return (T*)p;
+  }
+};
+
+#define JX_ALLOC(var, T, n, zero)                                                           \
+  T* var = arena.alloc<T>((n), (zero));                                                     \
+  if (!var) {                                                                               \
+    ctx->err = "device allocation failed: " #var;                                           \
+    return JX_ECUDA;                                                                        \
+  }
+
+// ---- library primitives (jx_core.cu; CUB) ---------------------------------------------------
+// LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit); stable.  keys/vals are
+// updated to point at the sorted buffers (which live in the arena).
+int jx_sort_pairs(jx_ctx* ctx, Arena& arena, uint64_t*& keys, uint32_t*& vals, size_t n, int begin_bit, int end_bit);
+int jx_sort_keys(jx_ctx* ctx, Arena& arena, uint64_t*& keys, size_t n, int begin_bit, int end_bit);
+int jx_exclusive_sum(jx_ctx* ctx, Arena& arena, const uint32_t* in, uint32_t* out, size_t n);
+inline int jx_bits(uint64_t maxval) { int b = 1; while (b < 64 && (maxval >> b)) ++b; return b; }
+
+// ---- tokenizer (jx_tokenize.cu) -----------------------------------------------------------------
+struct TokMode {
+  int strip = 1;
+  int neardiag = 0;            // self comparison: drop same-seqid hits with si - qi < 40 (synteny.py:280)
+  uint32_t* best = nullptr;    // per name-id best score bits (filter_cscore pass 1) or null
+  const uint64_t* excl = nullptr;
+  int64_t n_excl = 0;
+};
+struct TokOut {
+  uint4* recs = nullptr;       // [n_lines]
+  uint64_t* desc = nullptr;    // per tile: (2 << 62) | inclusive line count
+  int64_t ntiles = 0;
+  const uint8_t* d_text = nullptr;
+  int64_t nbytes = 0;
+  uint32_t n_lines = 0;
+  // 0 lines 1 comment 2 mapped 3 unmapped 4 hard 5 longname 6 overflow 7 first bad offset+1
+  // 8 excluded 9 self/near-diagonal drops
+  unsigned long long stats[12] = {0};
+};
+int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
+                     const TokMode& mode, TokOut& out);
+
+// ---- shared device helpers ---------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t score_ord(uint32_t bits) {   // monotone float32 -> uint32
+  return bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
+  for (;;) {
+    uint32_t p = __ldcg(parent + x);
+    if (p == x) return x;
+    uint32_t gp = __ldcg(parent + p);
+    if (gp != p) parent[x] = gp;   // path halving: benign race (any ancestor is valid)
+    x = p;
+  }
+}
+// lock-free union: hook the larger root under the smaller one, so root == min member index
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { uint32_t t = a; a = b; b = t; }
+    if (atomicCAS(parent + b, b, a) == b) return;
+  }
+}
+// append `pred` items of a warp to a global list; returns the slot (valid when pred)
+__device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* counter) {
+  unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+  if (!m) return 0;
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  return base + __popc(m & ((1u << lane) - 1));
+}
+#endif

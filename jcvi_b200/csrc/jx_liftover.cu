@@ -1,0 +1,600 @@
+// Stage 3: synteny liftover on the GPU (K11 of SURVEY.md section 2).
+//
+// Replaces src/jcvi/compara/synteny.py:
+//   300-374  process_blast_for_liftover  file-order first-seen de-duplication of the raw hits
+//   377-399  read_anchors                (qi,si) -> block, duplicate check
+//   455-473  synteny_liftover            scipy cKDTree(anchors, leafsize=16).query(p=1, distance_upper_bound=dist)
+//   1946-1962 append lifted pairs to the nearest anchor's block, per sorted chromosome pair, in file order
+// and the lookup half of AnchorFile.filter_blocks (compara/base.py:52-83).
+//
+// Nearest anchor.  Anchors are sorted by (qi, si) with a row pointer per query rank, so the
+// candidates of a hit are one contiguous slice (rows qi-dist+1 .. qi+dist-1, clipped to the
+// hit's chromosome); the kernel takes the exact minimum L1 distance.  Which BLOCK the hit joins
+// only depends on cKDTree's traversal order when several anchors at that minimum distance
+// belong to different blocks; exactly those hits are re-run through a bit-exact emulation of
+// scipy's tree (host build with std::nth_element -- its permutation defines the leaf order --
+// and a device walk with scipy's near-first descent and binary-heap tie rules).
+#include <algorithm>
+#include <map>
+
+#include "jx_internal.cuh"
+
+namespace {
+
+inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+__global__ void k_select_valid(const uint4* __restrict__ recs, uint32_t n, uint4* out, uint32_t* out_idx, uint32_t* counter) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
+    if (i < n) r = __ldcs(recs + i);
+    bool keep = r.x != JX_NOREC;
+    uint32_t slot = warp_append(keep, counter);
+    if (keep) { out[slot] = r; out_idx[slot] = i; }
+  }
+}
+__global__ void k_make_keys(const uint4* __restrict__ C, uint32_t n, int sb, uint64_t* keys, uint32_t* vals) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint4 r = C[j];
+  keys[j] = ((uint64_t)r.x << sb) | r.y;
+  vals[j] = j;
+}
+__global__ void k_run_first(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                            const uint32_t* __restrict__ Cidx, uint32_t n, uint32_t* flag, uint32_t* pick) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint64_t k = keys[t];
+  const bool head = (t == 0) || keys[t - 1] != k;
+  flag[t] = head;
+  if (!head) return;
+  uint32_t bj = vals[t], bi = Cidx[bj];
+  for (uint32_t u = t + 1; u < n && keys[u] == k; ++u) {
+    uint32_t j = vals[u], i = Cidx[j];
+    if (i < bi) { bj = j; bi = i; }
+  }
+  pick[t] = bj;
+}
+// unique hits sorted by (qi, si): key, score, line ordinal
+__global__ void k_scatter_hits(const uint64_t* keys, const uint32_t* pick, const uint32_t* flag, const uint32_t* pos,
+                               uint32_t n, const uint4* C, const uint32_t* Cidx, uint64_t* hkey, float* hsc, uint32_t* hline) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || !flag[t]) return;
+  uint32_t o = pos[t], j = pick[t];
+  hkey[o] = keys[t];
+  hsc[o] = __uint_as_float(C[j].z);
+  hline[o] = Cidx[j];
+}
+
+// accepted[(query, subject)] lookup for every anchor line
+__global__ void k_lookup(const uint64_t* hkey, const float* hsc, uint32_t nh, const int32_t* aq, const int32_t* as_,
+                         uint32_t na, int sb, uint8_t* acc, float* raw) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= na) return;
+  acc[t] = 0; raw[t] = 0.f;
+  if (aq[t] < 0 || as_[t] < 0) return;
+  uint64_t key = ((uint64_t)(uint32_t)aq[t] << sb) | (uint32_t)as_[t];
+  uint32_t lo = 0, hi = nh;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (hkey[mid] < key) lo = mid + 1; else hi = mid; }
+  if (lo < nh && hkey[lo] == key) { acc[t] = 1; raw[t] = hsc[lo]; }
+}
+
+__global__ void k_rowptr(const uint64_t* akey, uint32_t na, int sb, uint32_t G, uint32_t* rowptr) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  uint64_t key = (uint64_t)g << sb;
+  uint32_t lo = 0, hi = na;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (akey[mid] < key) lo = mid + 1; else hi = mid; }
+  rowptr[g] = lo;
+}
+
+// exact minimum L1 distance (< dist) to the anchors of the same chromosome pair
+__global__ void k_nearest(const uint64_t* __restrict__ hkey, uint32_t nh, int sb, const uint64_t* __restrict__ akey,
+                          const uint32_t* __restrict__ ablock, const uint32_t* __restrict__ rowptr,
+                          const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
+                          const int32_t* __restrict__ schr, int dist, uint32_t* best_a, uint8_t* state) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nh) return;
+  const uint64_t k = hkey[t];
+  const uint64_t smask = (1ull << sb) - 1;
+  const int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & smask);
+  const int32_t lo = max(x - (dist - 1), qbeg[x]), hi = min(x + dist - 1, qend[x] - 1);
+  const uint32_t t0 = rowptr[lo], t1 = rowptr[hi + 1];
+  const int32_t cy = schr[y];
+  int best = dist; uint32_t bt = 0xFFFFFFFFu, bblk = 0; bool amb = false;
+  for (uint32_t u = t0; u < t1; ++u) {
+    const uint64_t a = akey[u];
+    const int32_t ax = (int32_t)(a >> sb), ay = (int32_t)(a & smask);
+    const int d = abs(ax - x) + abs(ay - y);
+    if (d > best) continue;
+    if (schr[ay] != cy) continue;
+    if (d < best) { best = d; bt = u; bblk = ablock[u]; amb = false; }
+    else if (bt != 0xFFFFFFFFu && ablock[u] != bblk) amb = true;
+  }
+  // state: 0 none within dist / is an anchor itself, 1 lifted (unambiguous), 2 needs the tree walk
+  uint8_t st = 0;
+  if (bt != 0xFFFFFFFFu && best > 0) st = amb ? 2 : 1;
+  state[t] = st;
+  best_a[t] = bt;
+}
+
+// ---- scipy cKDTree emulation ------------------------------------------------------------------
+struct KNode { long long split; int split_dim, lesser, greater, start, end, pad; };
+
+struct HostTrees {
+  std::vector<KNode> nodes;
+  std::vector<int> indices;           // per tree: permutation of local point ids, global offset applied
+  std::vector<long long> px, py;      // concatenated points (tree-local order = input order)
+  std::vector<int> root, ptbase;
+  std::vector<long long> bounds;      // mins0, mins1, maxes0, maxes1 per tree
+
+  int build(int base, int start, int end) {      // [start, end) are global positions in `indices`
+    int me = (int)nodes.size();
+    nodes.push_back(KNode{0, -1, -1, -1, start, end, 0});
+    if (end - start <= 16) return me;
+    auto cx = [&](int id, int d) { return d == 0 ? px[(size_t)base + id] : py[(size_t)base + id]; };
+    long long mx[2], mn[2];
+    for (int d = 0; d < 2; ++d) mx[d] = mn[d] = cx(indices[(size_t)start], d);
+    for (int i = start + 1; i < end; ++i)
+      for (int d = 0; d < 2; ++d) { long long v = cx(indices[(size_t)i], d); if (v > mx[d]) mx[d] = v; if (v < mn[d]) mn[d] = v; }
+    int d = 0; long long size = 0;
+    for (int i = 0; i < 2; ++i) if (mx[i] - mn[i] > size) { d = i; size = mx[i] - mn[i]; }
+    if (mx[d] == mn[d]) return me;
+    const int npts = end - start;
+    std::nth_element(indices.begin() + start, indices.begin() + start + npts / 2, indices.begin() + end,
+                     [&](int a, int b) { return cx(a, d) < cx(b, d); });
+    long long split = cx(indices[(size_t)(start + npts / 2)], d);
+    int p = start, q = end - 1;
+    while (p <= q) {
+      if (cx(indices[(size_t)p], d) < split) ++p;
+      else if (cx(indices[(size_t)q], d) >= split) --q;
+      else { std::swap(indices[(size_t)p], indices[(size_t)q]); ++p; --q; }
+    }
+    if (p == start) {
+      int j = start; split = cx(indices[(size_t)j], d);
+      for (int i = start + 1; i < end; ++i) if (cx(indices[(size_t)i], d) < split) { j = i; split = cx(indices[(size_t)j], d); }
+      std::swap(indices[(size_t)start], indices[(size_t)j]);
+      p = start + 1;
+    } else if (p == end) {
+      int j = end - 1; split = cx(indices[(size_t)j], d);
+      for (int i = start; i < end - 1; ++i) if (cx(indices[(size_t)i], d) > split) { j = i; split = cx(indices[(size_t)j], d); }
+      std::swap(indices[(size_t)(end - 1)], indices[(size_t)j]);
+      p = end - 1;
+    }
+    nodes[(size_t)me].split_dim = d;
+    nodes[(size_t)me].split = split;
+    int l = build(base, start, p);
+    int g = build(base, p, end);
+    nodes[(size_t)me].lesser = l;
+    nodes[(size_t)me].greater = g;
+    return me;
+  }
+  // points of one tree in input order; returns the tree id
+  int add_tree(const std::vector<std::pair<long long, long long>>& pts) {
+    const int base = (int)px.size(), n = (int)pts.size();
+    long long mn0 = 0, mn1 = 0, mx0 = 0, mx1 = 0;
+    for (int i = 0; i < n; ++i) {
+      px.push_back(pts[(size_t)i].first); py.push_back(pts[(size_t)i].second);
+      indices.push_back(i);
+      if (i == 0) { mn0 = mx0 = pts[0].first; mn1 = mx1 = pts[0].second; }
+      mn0 = std::min(mn0, pts[(size_t)i].first); mx0 = std::max(mx0, pts[(size_t)i].first);
+      mn1 = std::min(mn1, pts[(size_t)i].second); mx1 = std::max(mx1, pts[(size_t)i].second);
+    }
+    ptbase.push_back(base);
+    bounds.push_back(mn0); bounds.push_back(mn1); bounds.push_back(mx0); bounds.push_back(mx1);
+    root.push_back(n ? build(base, base, base + n) : -1);
+    return (int)root.size() - 1;
+  }
+};
+
+constexpr int HEAP_CAP = 96;
+
+// k = 1, p = 1, eps = 0 query of one point against its tree; all quantities are integers, so
+// int64 arithmetic reproduces scipy's float64 arithmetic exactly.
+__global__ void k_kdwalk(const long long* __restrict__ qx, const long long* __restrict__ qy, const int* __restrict__ qtree,
+                         uint32_t n, const KNode* __restrict__ nodes, const int* __restrict__ indices,
+                         const long long* __restrict__ px, const long long* __restrict__ py, const int* __restrict__ root,
+                         const int* __restrict__ ptbase, const long long* __restrict__ bounds, long long bound,
+                         int* out_local, long long* out_dist, uint32_t* overflow) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int tr = qtree[t];
+  const long long x[2] = {qx[t], qy[t]};
+  long long best = bound; int besti = -1;
+  int cur = root[tr];
+  if (cur < 0) { out_local[t] = -1; out_dist[t] = -1; return; }
+  const int base = ptbase[tr];
+  long long hp[HEAP_CAP], hs0[HEAP_CAP], hs1[HEAP_CAP]; int hn[HEAP_CAP];
+  int hsize = 0;
+  long long sd[2], prio = 0;
+  for (int d = 0; d < 2; ++d) {
+    long long mn = bounds[tr * 4 + d], mx = bounds[tr * 4 + 2 + d];
+    long long s = max(0ll, max(mn - x[d], x[d] - mx));
+    sd[d] = s; prio += s;
+  }
+  for (;;) {
+    const KNode nd = nodes[cur];
+    if (nd.split_dim == -1) {
+      for (int i = nd.start; i < nd.end; ++i) {
+        int id = indices[i];
+        long long dd = llabs(px[base + id] - x[0]) + llabs(py[base + id] - x[1]);
+        if (dd < best) { best = dd; besti = id; }
+      }
+      if (hsize == 0) break;
+      // pop: move last to the root, sift down (swap only when the parent is strictly larger)
+      cur = hn[0]; prio = hp[0]; sd[0] = hs0[0]; sd[1] = hs1[0];
+      --hsize;
+      hp[0] = hp[hsize]; hn[0] = hn[hsize]; hs0[0] = hs0[hsize]; hs1[0] = hs1[hsize];
+      int i = 0;
+      for (;;) {
+        int j = 2 * i + 1, k = 2 * i + 2, l = i;
+        if (j < hsize && hp[i] > hp[j]) l = j;
+        if (k < hsize && hp[l] > hp[k]) l = k;
+        if (l == i) break;
+        long long tp = hp[i]; hp[i] = hp[l]; hp[l] = tp;
+        int tn = hn[i]; hn[i] = hn[l]; hn[l] = tn;
+        long long a0 = hs0[i]; hs0[i] = hs0[l]; hs0[l] = a0;
+        long long a1 = hs1[i]; hs1[i] = hs1[l]; hs1[l] = a1;
+        i = l;
+      }
+    } else {
+      if (prio > best) break;
+      const int d = nd.split_dim;
+      int nearn, farn;
+      if (x[d] < nd.split) { nearn = nd.lesser; farn = nd.greater; } else { nearn = nd.greater; farn = nd.lesser; }
+      const long long nsd = llabs(nd.split - x[d]);
+      const long long fprio = prio + nsd - sd[d];
+      if (fprio <= best) {
+        if (hsize >= HEAP_CAP) { atomicExch(overflow, 1u); }
+        else {
+          int i = hsize++;
+          hp[i] = fprio; hn[i] = farn; hs0[i] = d == 0 ? nsd : sd[0]; hs1[i] = d == 1 ? nsd : sd[1];
+          while (i > 0) {
+            int par = (i - 1) / 2;
+            if (hp[i] < hp[par]) {
+              long long tp = hp[i]; hp[i] = hp[par]; hp[par] = tp;
+              int tn = hn[i]; hn[i] = hn[par]; hn[par] = tn;
+              long long a0 = hs0[i]; hs0[i] = hs0[par]; hs0[par] = a0;
+              long long a1 = hs1[i]; hs1[i] = hs1[par]; hs1[par] = a1;
+              i = par;
+            } else break;
+          }
+        }
+      }
+      cur = nearn;
+    }
+  }
+  out_local[t] = besti;
+  out_dist[t] = besti < 0 ? -1 : best;
+}
+
+int run_walk(jx_ctx* ctx, Arena& arena, const HostTrees& T, const std::vector<long long>& qx, const std::vector<long long>& qy,
+             const std::vector<int>& qtree, long long bound, std::vector<int>& local, std::vector<long long>& dist) {
+  const uint32_t n = (uint32_t)qx.size();
+  local.assign(n, -1); dist.assign(n, -1);
+  if (!n) return JX_OK;
+  JX_ALLOC(dqx, long long, n, false);
+  JX_ALLOC(dqy, long long, n, false);
+  JX_ALLOC(dqt, int, n, false);
+  JX_ALLOC(dnodes, KNode, T.nodes.size(), false);
+  JX_ALLOC(dind, int, T.indices.size(), false);
+  JX_ALLOC(dpx, long long, T.px.size(), false);
+  JX_ALLOC(dpy, long long, T.py.size(), false);
+  JX_ALLOC(droot, int, T.root.size(), false);
+  JX_ALLOC(dbase, int, T.ptbase.size(), false);
+  JX_ALLOC(dbounds, long long, T.bounds.size(), false);
+  JX_ALLOC(dol, int, n, false);
+  JX_ALLOC(dod, long long, n, false);
+  JX_ALLOC(dovf, uint32_t, 1, true);
+#define UP(dst, src) if (!(src).empty()) JX_CK(cudaMemcpyAsync(dst, (src).data(), (src).size() * sizeof((src)[0]), cudaMemcpyHostToDevice, ctx->stream))
+  UP(dqx, qx); UP(dqy, qy); UP(dqt, qtree); UP(dnodes, T.nodes); UP(dind, T.indices); UP(dpx, T.px); UP(dpy, T.py);
+  UP(droot, T.root); UP(dbase, T.ptbase); UP(dbounds, T.bounds);
+#undef UP
+  JX_LAUNCH(k_kdwalk, nblk(n, 64), 64, 0, dqx, dqy, dqt, n, dnodes, dind, dpx, dpy, droot, dbase, dbounds, bound, dol, dod, dovf);
+  uint32_t ovf = 0;
+  JX_CK(cudaMemcpyAsync(local.data(), dol, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(dist.data(), dod, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&ovf, dovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (ovf) { ctx->err = "KD-tree walk heap overflow"; return JX_EINTERNAL; }
+  return JX_OK;
+}
+
+__global__ void k_lift_flags(const uint8_t* state, uint32_t n, uint32_t* f1, uint32_t* f2) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  f1[t] = state[t] != 0;
+  f2[t] = state[t] == 2;
+}
+__global__ void k_gather_amb(const uint8_t* state, const uint32_t* pos2, uint32_t n, uint32_t* amb_hit) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && state[t] == 2) amb_hit[pos2[t]] = t;
+}
+__global__ void k_patch_amb(const uint32_t* amb_hit, const uint32_t* amb_block, uint32_t n, uint32_t* hit_block) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) hit_block[amb_hit[t]] = amb_block[t];
+}
+__global__ void k_hit_block(const uint8_t* state, const uint32_t* best_a, const uint32_t* ablock, uint32_t n, uint32_t* hit_block) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) hit_block[t] = state[t] == 1 ? ablock[best_a[t]] : 0u;
+}
+// sort keys of the lifted hits: pass 1 (cp << 32 | line), pass 2 block
+__global__ void k_lift_keys(const uint8_t* state, const uint32_t* pos1, const uint64_t* hkey, const uint32_t* hline, int sb,
+                            const int32_t* qchr, const int32_t* schr, uint64_t nschr, uint32_t n, uint64_t* k1, uint32_t* v1) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || state[t] == 0) return;
+  uint64_t k = hkey[t];
+  int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & ((1ull << sb) - 1));
+  uint64_t cp = (uint64_t)qchr[x] * nschr + (uint64_t)schr[y];
+  k1[pos1[t]] = (cp << 32) | hline[t];
+  v1[pos1[t]] = t;
+}
+__global__ void k_block_keys(const uint32_t* v, const uint32_t* hit_block, uint32_t n, uint64_t* k2) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) k2[t] = hit_block[v[t]];
+}
+__global__ void k_emit_lifted(const uint32_t* v, uint32_t n, const uint64_t* hkey, const float* hsc, const uint32_t* hit_block,
+                              int sb, int32_t* oq, int32_t* os, float* osc, int32_t* ob) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t h = v[t];
+  uint64_t k = hkey[h];
+  oq[t] = (int32_t)(k >> sb); os[t] = (int32_t)(k & ((1ull << sb) - 1));
+  osc[t] = hsc[h]; ob[t] = (int32_t)hit_block[h];
+}
+
+int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n, uint32_t*& pos, uint32_t& count) {
+  count = 0; pos = nullptr;
+  if (!n) return JX_OK;
+  JX_ALLOC(p, uint32_t, n, false);
+  int rc = jx_exclusive_sum(ctx, arena, flag, p, n);
+  if (rc) return rc;
+  uint32_t last[2];
+  JX_CK(cudaMemcpyAsync(&last[0], p + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&last[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  count = last[0] + last[1];
+  pos = p;
+  return JX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void jx_liftover_result_free(jx_liftover_result* r) {
+  if (!r) return;
+  free(r->q_rank); free(r->s_rank); free(r->score); free(r->block); free(r->accepted); free(r->raw_score);
+  memset(r, 0, sizeof *r);
+}
+
+int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                     const int32_t* a_qi, const int32_t* a_si, const int32_t* a_block, int64_t n_lines64,
+                     jx_liftover_result* out) {
+  if (!ctx || !out || n_lines64 < 0 || n_lines64 >= (1ll << 31) || dist < 0) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  const uint32_t nal = (uint32_t)n_lines64;
+  int rc;
+
+  // ---- raw hits: tokenizer -> unique (qi,si), first occurrence -----------------------------------
+  TokMode mode;
+  mode.strip = strip_names;
+  mode.neardiag = ctx->is_self ? 1 : 0;
+  TokOut tok;
+  if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+  out->stats[0] = (int64_t)(tok.stats[0] - tok.stats[1]);
+  out->stats[5] = (int64_t)tok.stats[1];
+  const size_t capC = (size_t)tok.stats[2] + 1;
+  JX_ALLOC(C, uint4, capC, false);
+  JX_ALLOC(Cidx, uint32_t, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 1, true);
+  if (tok.n_lines) {
+    unsigned grid = std::min<unsigned>(nblk(tok.n_lines), 148u * 16u);
+    JX_LAUNCH(k_select_valid, grid, 256, 0, tok.recs, tok.n_lines, C, Cidx, d_cnt);
+  }
+  uint32_t nC = 0;
+  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+  uint32_t nh = 0;
+  uint64_t* hkey = nullptr; float* hsc = nullptr; uint32_t* hline = nullptr;
+  if (nC) {
+    JX_ALLOC(keys, uint64_t, nC, false);
+    JX_ALLOC(vals, uint32_t, nC, false);
+    JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
+    uint64_t* ks = keys; uint32_t* vs = vals;
+    if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
+    JX_ALLOC(flag, uint32_t, nC, false);
+    JX_ALLOC(pick, uint32_t, nC, false);
+    JX_LAUNCH(k_run_first, nblk(nC), 256, 0, ks, vs, Cidx, nC, flag, pick);
+    uint32_t* pos;
+    if ((rc = compact_positions(ctx, arena, flag, nC, pos, nh))) return rc;
+    JX_ALLOC(hk, uint64_t, nh, false);
+    JX_ALLOC(hs, float, nh, false);
+    JX_ALLOC(hl, uint32_t, nh, false);
+    JX_LAUNCH(k_scatter_hits, nblk(nC), 256, 0, ks, pick, flag, pos, nC, C, Cidx, hk, hs, hl);
+    hkey = hk; hsc = hs; hline = hl;
+  }
+  out->stats[1] = nh;
+
+  // ---- anchors ------------------------------------------------------------------------------------------
+  out->accepted = (uint8_t*)calloc((size_t)nal + 1, 1);
+  out->raw_score = (float*)calloc((size_t)nal + 1, sizeof(float));
+  std::vector<uint64_t> akeys_h; std::vector<uint32_t> aline_h;
+  akeys_h.reserve(nal); aline_h.reserve(nal);
+  for (uint32_t t = 0; t < nal; ++t) {
+    if (a_qi[t] < 0 || a_si[t] < 0) continue;
+    if (a_qi[t] >= Q.G || a_si[t] >= S.G) { ctx->err = "anchor rank out of range"; return JX_EARG; }
+    akeys_h.push_back(((uint64_t)(uint32_t)a_qi[t] << sb) | (uint32_t)a_si[t]);
+    aline_h.push_back(t);
+  }
+  const uint32_t na = (uint32_t)akeys_h.size();
+  out->stats[2] = na;
+  JX_ALLOC(daq, int32_t, nal, false);
+  JX_ALLOC(das, int32_t, nal, false);
+  JX_ALLOC(dacc, uint8_t, nal, false);
+  JX_ALLOC(draw, float, nal, false);
+  if (nal) {
+    JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_LAUNCH(k_lookup, nblk(nal), 256, 0, hkey, hsc, nh, daq, das, nal, sb, dacc, draw);
+    JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  auto alloc_out = [&](uint32_t n) {
+    out->q_rank = (int32_t*)malloc(4 * ((size_t)n + 1)); out->s_rank = (int32_t*)malloc(4 * ((size_t)n + 1));
+    out->score = (float*)malloc(4 * ((size_t)n + 1)); out->block = (int32_t*)malloc(4 * ((size_t)n + 1));
+    out->n_lifted = n;
+  };
+  if (!na || !nh) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
+
+  // sort anchors by (qi, si) on the device; detect duplicates (read_anchors' assert)
+  JX_ALLOC(akey, uint64_t, na, false);
+  JX_ALLOC(aord, uint32_t, na, false);
+  std::vector<uint32_t> ablock_h(na);
+  for (uint32_t i = 0; i < na; ++i) ablock_h[i] = (uint32_t)a_block[aline_h[i]];
+  JX_CK(cudaMemcpyAsync(akey, akeys_h.data(), (size_t)na * 8, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    std::vector<uint32_t> iota(na);
+    for (uint32_t i = 0; i < na; ++i) iota[i] = i;
+    JX_CK(cudaMemcpyAsync(aord, iota.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+  }
+  uint64_t* aks = akey; uint32_t* aos = aord;
+  if ((rc = jx_sort_pairs(ctx, arena, aks, aos, na, 0, sb + qb))) return rc;
+  std::vector<uint64_t> aks_h(na); std::vector<uint32_t> aos_h(na);
+  JX_CK(cudaMemcpyAsync(aks_h.data(), aks, (size_t)na * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(aos_h.data(), aos, (size_t)na * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t i = 1; i < na; ++i)
+    if (aks_h[i] == aks_h[i - 1]) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
+  std::vector<uint32_t> ablock_sorted(na);
+  for (uint32_t i = 0; i < na; ++i) ablock_sorted[i] = ablock_h[aos_h[i]];
+  JX_ALLOC(dablock, uint32_t, na, false);
+  JX_CK(cudaMemcpyAsync(dablock, ablock_sorted.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
+  JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
+
+  // ---- nearest anchor per hit -------------------------------------------------------------------------------
+  JX_ALLOC(best_a, uint32_t, nh, false);
+  JX_ALLOC(state, uint8_t, nh, false);
+  JX_LAUNCH(k_nearest, nblk(nh, 128), 128, 0, hkey, nh, sb, aks, dablock, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist,
+            best_a, state);
+  JX_ALLOC(f1, uint32_t, nh, false);
+  JX_ALLOC(f2, uint32_t, nh, false);
+  JX_LAUNCH(k_lift_flags, nblk(nh), 256, 0, state, nh, f1, f2);
+  uint32_t *pos1, *pos2; uint32_t nlift, namb;
+  if ((rc = compact_positions(ctx, arena, f1, nh, pos1, nlift))) return rc;
+  if ((rc = compact_positions(ctx, arena, f2, nh, pos2, namb))) return rc;
+  out->stats[3] = nlift;
+  out->stats[4] = namb;
+  JX_ALLOC(hit_block, uint32_t, nh, false);
+  JX_LAUNCH(k_hit_block, nblk(nh), 256, 0, state, best_a, dablock, nh, hit_block);
+
+  // ---- cross-block ties: exact cKDTree emulation ---------------------------------------------------------------
+  if (namb) {
+    JX_ALLOC(amb_hit, uint32_t, namb, false);
+    JX_LAUNCH(k_gather_amb, nblk(nh), 256, 0, state, pos2, nh, amb_hit);
+    std::vector<uint32_t> amb_h(namb);
+    std::vector<uint64_t> hk_h(nh);
+    JX_CK(cudaMemcpyAsync(amb_h.data(), amb_hit, (size_t)namb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(hk_h.data(), hkey, (size_t)nh * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t smask = (1ull << sb) - 1;
+    auto cp_of = [&](uint64_t key) {
+      return (uint64_t)Q.h_chr_lex[(size_t)(key >> sb)] * (uint64_t)S.n_chr + (uint64_t)S.h_chr_lex[(size_t)(key & smask)];
+    };
+    std::map<uint64_t, int> tree_of;          // chromosome pair -> tree id
+    std::vector<long long> qx(namb), qy(namb); std::vector<int> qtree(namb);
+    for (uint32_t i = 0; i < namb; ++i) {
+      uint64_t key = hk_h[amb_h[i]];
+      qx[i] = (long long)(key >> sb); qy[i] = (long long)(key & smask);
+      tree_of.emplace(cp_of(key), -1);
+    }
+    // anchors of those chromosome pairs, in file order (all_anchors[chr_pair], synteny.py:392)
+    std::map<uint64_t, std::vector<uint32_t>> members;
+    for (uint32_t i = 0; i < na; ++i) {
+      uint64_t cp = cp_of(akeys_h[i]);
+      if (tree_of.count(cp)) members[cp].push_back(i);
+    }
+    HostTrees T;
+    std::vector<const std::vector<uint32_t>*> tree_members;
+    for (auto& kv : members) {
+      std::vector<std::pair<long long, long long>> pts;
+      pts.reserve(kv.second.size());
+      for (uint32_t i : kv.second) pts.emplace_back((long long)(akeys_h[i] >> sb), (long long)(akeys_h[i] & smask));
+      tree_of[kv.first] = T.add_tree(pts);
+      tree_members.push_back(&kv.second);
+    }
+    for (uint32_t i = 0; i < namb; ++i) qtree[i] = tree_of[cp_of(hk_h[amb_h[i]])];
+    std::vector<int> local; std::vector<long long> dd;
+    if ((rc = run_walk(ctx, arena, T, qx, qy, qtree, (long long)dist, local, dd))) return rc;
+    std::vector<uint32_t> amb_block(namb);
+    for (uint32_t i = 0; i < namb; ++i) {
+      if (local[i] < 0) { ctx->err = "KD-tree walk found no anchor for a flagged hit"; return JX_EINTERNAL; }
+      uint32_t ai = (*tree_members[(size_t)qtree[i]])[(size_t)local[i]];
+      amb_block[i] = ablock_h[ai];
+    }
+    JX_ALLOC(d_ab, uint32_t, namb, false);
+    JX_CK(cudaMemcpyAsync(d_ab, amb_block.data(), (size_t)namb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_LAUNCH(k_patch_amb, nblk(namb), 256, 0, amb_hit, d_ab, namb, hit_block);
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+  }
+
+  // ---- order: (block, sorted chromosome pair, file order) ------------------------------------------------------------
+  alloc_out(nlift);
+  if (nlift) {
+    JX_ALLOC(k1, uint64_t, nlift, false);
+    JX_ALLOC(v1, uint32_t, nlift, false);
+    JX_LAUNCH(k_lift_keys, nblk(nh), 256, 0, state, pos1, hkey, hline, sb, Q.chr_lex, S.chr_lex, (uint64_t)S.n_chr, nh, k1, v1);
+    uint64_t* k1s = k1; uint32_t* v1s = v1;
+    const uint64_t maxcp = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
+    if (maxcp >= (1ull << 32)) { ctx->err = "too many chromosome pairs"; return JX_EUNSUPPORTED; }
+    if ((rc = jx_sort_pairs(ctx, arena, k1s, v1s, nlift, 0, 32 + jx_bits(maxcp)))) return rc;
+    JX_ALLOC(k2, uint64_t, nlift, false);
+    JX_LAUNCH(k_block_keys, nblk(nlift), 256, 0, v1s, hit_block, nlift, k2);
+    uint64_t* k2s = k2;
+    if ((rc = jx_sort_pairs(ctx, arena, k2s, v1s, nlift, 0, 32))) return rc;
+    JX_ALLOC(oq, int32_t, nlift, false);
+    JX_ALLOC(os, int32_t, nlift, false);
+    JX_ALLOC(osc, float, nlift, false);
+    JX_ALLOC(ob, int32_t, nlift, false);
+    JX_LAUNCH(k_emit_lifted, nblk(nlift), 256, 0, v1s, nlift, hkey, hsc, hit_block, sb, oq, os, osc, ob);
+    JX_CK(cudaMemcpyAsync(out->q_rank, oq, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->s_rank, os, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->score, osc, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->block, ob, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  JX_CK(cudaGetLastError());
+  return JX_OK;
+}
+
+int jx_nearest_anchor(jx_ctx* ctx, const int64_t* points_xy, int64_t n_points, const int64_t* anchors_xy,
+                      int64_t n_anchors, int dist, int64_t* nearest, int64_t* dist_out) {
+  if (!ctx || n_points < 0 || n_anchors < 0 || n_points >= (1ll << 31) || n_anchors >= (1ll << 31)) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  HostTrees T;
+  std::vector<std::pair<long long, long long>> pts((size_t)n_anchors);
+  for (int64_t i = 0; i < n_anchors; ++i) pts[(size_t)i] = {(long long)anchors_xy[2 * i], (long long)anchors_xy[2 * i + 1]};
+  T.add_tree(pts);
+  std::vector<long long> qx((size_t)n_points), qy((size_t)n_points);
+  std::vector<int> qtree((size_t)n_points, 0);
+  for (int64_t i = 0; i < n_points; ++i) { qx[(size_t)i] = points_xy[2 * i]; qy[(size_t)i] = points_xy[2 * i + 1]; }
+  std::vector<int> local; std::vector<long long> dd;
+  int rc = run_walk(ctx, arena, T, qx, qy, qtree, (long long)dist, local, dd);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n_points; ++i) {
+    nearest[i] = local[(size_t)i] < 0 ? n_anchors : local[(size_t)i];
+    if (dist_out) dist_out[i] = dd[(size_t)i];
+  }
+  return JX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+// Host+device text primitives of the BLAST tab12 tokenizer (K1/K2).
+//
+// Replaces, per line, what the reference does with glibc `sscanf` in
+// src/jcvi/formats/cblast.pyx:106-112 (format string cblast.pyx:15) and with
+// `gene_name` in src/jcvi/utils/cbook.py:308-329.  Everything here is
+// `__host__ __device__` so that the exact same code is unit-tested on the CPU against
+// glibc strtof/strtod/sscanf (tests/test_parse_host.py) and runs inside the CUDA kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JX_HD __host__ __device__ __forceinline__
+#else
+#define JX_HD inline
+#endif
+
+namespace jx {
+
+// ---- byte classes ------------------------------------------------------------------
+// sscanf's isspace() in the C locale; '\n' and '\r' never occur inside a line because the
+// line splitter treats both as terminators (Python universal newlines, formats/base.py
+// must_open -> open()).
+JX_HD bool is_space(uint32_t c) { return c == ' ' || (c - 9u) <= 4u; }
+JX_HD bool is_digit(uint32_t c) { return (c - (uint32_t)'0') <= 9u; }
+JX_HD bool is_term(uint32_t c) { return c == '\n' || c == '\r'; }
+
+// ---- decimal scanner -------------------------------------------------------------------
+struct Dec {
+  uint64_t m;     // up to 19 significant digits
+  int32_t e10;    // value = m * 10^e10  (ignoring dropped digits)
+  bool neg;
+  bool ok;        // a conversion happened (at least one digit)
+  bool dropped;   // non-zero digits beyond the 19th were dropped
+  bool special;   // inf / nan / hex float / dangling exponent: not supported on device
+};
+
+// Scans the longest prefix matching  [+-]? (d+ [. d*]? | . d+) ([eE] [+-]? d+)?  starting at p
+// (no leading whitespace), never reading at or beyond `e`.  Returns the position after the
+// prefix (p itself when nothing matched).  `rd(pos)` yields the byte at pos.
+template <class R>
+JX_HD int scan_decimal(R& rd, int p, int e, Dec& d) {
+  d.m = 0; d.e10 = 0; d.neg = false; d.ok = false; d.dropped = false; d.special = false;
+  int q = p;
+  if (q < e) { uint32_t c = rd(q); if (c == '-') { d.neg = true; ++q; } else if (c == '+') { ++q; } }
+  if (q < e) {
+    uint32_t c = rd(q) | 0x20u;
+    if ((c == 'i' || c == 'n') && q + 2 < e) {
+      uint32_t c1 = rd(q + 1) | 0x20u, c2 = rd(q + 2) | 0x20u;
+      if ((c == 'i' && c1 == 'n' && c2 == 'f') || (c == 'n' && c1 == 'a' && c2 == 'n')) { d.special = true; return p; }
+    }
+    if (c == '0' && q + 1 < e && (rd(q + 1) | 0x20u) == 'x') { d.special = true; return p; }
+  }
+  int nd = 0;          // significant digits accumulated
+  bool any = false;
+  while (q < e) {
+    uint32_t c = rd(q);
+    if (!is_digit(c)) break;
+    any = true;
+    uint32_t v = c - '0';
+    if (nd < 19) { if (nd > 0 || v) { d.m = d.m * 10u + v; ++nd; } }
+    else { ++d.e10; if (v) d.dropped = true; }
+    ++q;
+  }
+  if (q < e && rd(q) == '.') {
+    int q2 = q + 1;
+    bool anyf = false;
+    while (q2 < e) {
+      uint32_t c = rd(q2);
+      if (!is_digit(c)) break;
+      anyf = true;
+      uint32_t v = c - '0';
+      if (nd < 19) { if (nd > 0 || v) { d.m = d.m * 10u + v; ++nd; } --d.e10; }
+      else if (v) d.dropped = true;
+      ++q2;
+    }
+    if (any || anyf) { q = q2; any = true; }
+  }
+  if (!any) return p;
+  d.ok = true;
+  if (q < e && (rd(q) | 0x20u) == 'e') {
+    int q2 = q + 1;
+    bool eneg = false;
+    if (q2 < e) { uint32_t c = rd(q2); if (c == '-') { eneg = true; ++q2; } else if (c == '+') { ++q2; } }
+    if (q2 < e && is_digit(rd(q2))) {
+      int ex = 0;
+      while (q2 < e) {
+        uint32_t c = rd(q2);
+        if (!is_digit(c)) break;
+        if (ex < 100000) ex = ex * 10 + (int)(c - '0');
+        ++q2;
+      }
+      d.e10 += eneg ? -ex : ex;
+      q = q2;
+    } else {
+      // "1e", "1e+": glibc scanf treats this as a matching failure while strtod would stop
+      // before the 'e'; refuse instead of guessing.
+      d.special = true;
+    }
+  }
+  if (d.m == 0) d.e10 = 0;
+  return q;
+}
+
+// [+-]? d+   (scanf %d).  Returns position after the prefix, p when nothing matched.
+template <class R>
+JX_HD int scan_int(R& rd, int p, int e) {
+  int q = p;
+  if (q < e) { uint32_t c = rd(q); if (c == '-' || c == '+') ++q; }
+  int q0 = q;
+  while (q < e && is_digit(rd(q))) ++q;
+  return q == q0 ? p : q;
+}
+
+// ---- decimal -> binary ---------------------------------------------------------------
+JX_HD double pow10_exact(int k) {  // 10^k, exact in double for 0 <= k <= 22
+  const double t[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                        1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  return t[k];
+}
+JX_HD uint64_t pow10_u64(int k) {  // 0 <= k <= 19
+  const uint64_t t[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
+                          100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull,
+                          10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull,
+                          100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull};
+  return t[k];
+}
+
+JX_HD void mul64x64(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo) {
+#if defined(__CUDA_ARCH__)
+  lo = a * b; hi = __umul64hi(a, b);
+#else
+  unsigned __int128 p = (unsigned __int128)a * b; lo = (uint64_t)p; hi = (uint64_t)(p >> 64);
+#endif
+}
+JX_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+JX_HD float bits_to_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { uint32_t u; float f; } x; x.u = u; return x.f;
+#endif
+}
+JX_HD uint32_t float_to_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  union { uint32_t u; float f; } x; x.f = f; return x.u;
+#endif
+}
+
+// exact round-to-nearest-even of the 128-bit integer (hi:lo) to float32
+JX_HD float u128_to_f32(uint64_t hi, uint64_t lo) {
+  if (!hi && !lo) return 0.f;
+  int top = hi ? 127 - clz64(hi) : 63 - clz64(lo);   // index of the top set bit
+  if (top < 24) return (float)(uint32_t)lo;          // exact
+  int sh = top - 23;                                 // bits to drop
+  // mant = (N >> sh), rem = N & ((1<<sh)-1)
+  uint64_t mant, rem_hi, rem_lo, half_hi, half_lo;
+  if (sh >= 64) {
+    mant = hi >> (sh - 64);
+    rem_hi = (sh - 64) ? (hi & ((1ull << (sh - 64)) - 1)) : 0; rem_lo = lo;
+    half_hi = (sh - 64) ? (1ull << (sh - 65)) : 0; half_lo = (sh - 64) ? 0 : (1ull << 63);
+  } else {
+    mant = (lo >> sh) | (hi ? (hi << (64 - sh)) : 0);
+    rem_hi = 0; rem_lo = lo & ((1ull << sh) - 1);
+    half_hi = 0; half_lo = 1ull << (sh - 1);
+  }
+  mant &= 0xFFFFFFull;
+  bool gt = rem_hi > half_hi || (rem_hi == half_hi && rem_lo > half_lo);
+  bool eq = rem_hi == half_hi && rem_lo == half_lo;
+  uint32_t m = (uint32_t)mant;
+  int ex = top;
+  if (gt || (eq && (m & 1u))) { ++m; if (m == 0x1000000u) { m >>= 1; ++ex; } }
+  if (ex > 127) return bits_to_float(0x7F800000u);
+  return bits_to_float(((uint32_t)(ex + 127) << 23) | (m & 0x7FFFFFu));
+}
+
+// Correctly rounded float32 (== glibc strtof) for the decimals this path sees; returns
+// false ("hard") when the cheap exact routes do not apply -- the caller then reports the line
+// instead of guessing.  Routes and why they are exact:
+//   e10 >= 0 (<= 19): m*10^e10 as an exact 128-bit integer, one rounding.
+//   e10 <  0 (>= -12), m < 2^53: one correctly rounded double division followed by the
+//        double->float rounding; a float32 midpoint cannot sit within 2^-53 (relative) of
+//        m/10^k unless it equals it, because 5^k * 2^25 < 2^53 for k <= 12.
+JX_HD bool dec_to_f32(const Dec& d, float& out) {
+  if (d.m == 0) { out = d.neg ? -0.f : 0.f; return !d.dropped; }
+  if (d.dropped) return false;
+  float r;
+  if (d.e10 >= 0) {
+    if (d.e10 > 19) {
+      if (d.e10 > 60) { r = bits_to_float(0x7F800000u); }
+      else return false;
+    } else {
+      uint64_t hi, lo;
+      mul64x64(d.m, pow10_u64(d.e10), hi, lo);
+      r = u128_to_f32(hi, lo);
+    }
+  } else {
+    uint64_t m = d.m; int k = -d.e10;
+    if (k > 12 || m >= (1ull << 53)) {           // "54.000000000000000" style: strip zeros first
+      while (k > 0 && m % 10u == 0) { m /= 10u; --k; }
+    }
+    if (k == 0) r = u128_to_f32(0, m);
+    else if (k <= 12 && m < (1ull << 53)) r = (float)((double)m / pow10_exact(k));
+    else return false;
+  }
+  out = d.neg ? -r : r;
+  return true;
+}
+
+// Decides  strtod(text) < 1e-10  (tandem_grouper, blastfilter.py:265-271) exactly.
+// Returns 1 / 0, or -1 when the value is within 1e-6 (relative) of the threshold and the
+// exact route (m < 2^53, |e10| <= 22: single correctly rounded double op) does not apply.
+JX_HD int dec_lt_1e10(const Dec& d) {
+  if (d.m == 0) return 1;
+  if (d.neg) return 1;
+  if (!d.dropped && d.m < (1ull << 53) && d.e10 >= -22 && d.e10 <= 22) {
+    double v = d.e10 < 0 ? (double)d.m / pow10_exact(-d.e10) : (double)d.m * pow10_exact(d.e10);
+    return v < 1e-10 ? 1 : 0;
+  }
+  // magnitude route: log10(value) = log10(m) + e10; m has at most 19 digits
+  int nd = 1; { uint64_t t = d.m; while (t >= 10u) { t /= 10u; ++nd; } }
+  int mag = nd - 1 + d.e10;          // value in [10^mag, 10^(mag+1))
+  if (mag <= -12) return 1;
+  if (mag >= -9) return 0;
+  // mag in {-11, -10}: compare leading digits exactly.  value < 1e-10  <=>  mag == -11 unless
+  // the digits are 999.. close to rolling over; value >= 1e-10 when mag == -10.  The rounded
+  // double can only cross the threshold when the decimal is within 1 ulp (2^-53) of 1e-10.
+  if (mag == -11) {
+    // value = 0.d1d2..dn * 1e-10 ; within 1e-6 of threshold iff leading digits are 999999..
+    uint64_t lead = d.m; int n = nd; while (n > 7) { lead /= 10u; --n; }
+    uint64_t all9 = pow10_u64(n) - 1;
+    if (n >= 7 && lead == all9) return -1;
+    return 1;
+  }
+  // mag == -10: value in [1e-10, 1e-9).  RN(1e-10) is the double nearest to 1e-10; any decimal
+  // >= 1e-10 rounds to a double >= RN(1e-10), hence not "<".
+  return 0;
+}
+
+// ---- %.3g round trip -------------------------------------------------------------------------
+// strtof(sprintf("%.3g", (double)x)) for finite x: what `synteny scan` sees after
+// `blastfilter` printed the score with "%.3g" (cblast.pyx:17) -- exact integer arithmetic,
+// round-half-even on the exact binary value like glibc printf.  Returns false when the
+// magnitude is outside the exactly handled range (caller falls back to text round trip).
+JX_HD bool round3g_f32(float x, float& out) {
+  uint32_t u = float_to_bits(x);
+  bool neg = u >> 31;
+  uint32_t ex = (u >> 23) & 0xFFu, fr = u & 0x7FFFFFu;
+  if (ex == 0xFFu) return false;
+  if (ex == 0 && fr == 0) { out = x; return true; }
+  if (ex == 0) return false;                 // subnormal: not a score
+  const uint64_t M = fr | 0x800000u;         // |x| = M * 2^E, 2^23 <= M < 2^24
+  const int E = (int)ex - 150;
+  uint64_t q; int p;                         // |x| ~ q * 10^(p-2), 100 <= q <= 999
+  uint64_t rem, den;                         // exact remainder / denominator of the cut
+  if (E >= 0) {
+    if (E > 39) return false;                // >= 2^63
+    const uint64_t N = M << E;               // exact integer
+    p = 0; while (p < 19 && N >= pow10_u64(p + 1)) ++p;
+    if (p <= 2) { q = N * pow10_u64(2 - p); rem = 0; den = 1; }
+    else { const uint64_t D = pow10_u64(p - 2); q = N / D; rem = N % D; den = D; }
+  } else {
+    const int s = -E;                        // |x| = M / 2^s
+    if (s > 60) return false;
+    const uint64_t I = s < 24 ? (M >> s) : 0;
+    if (I >= 1000) {
+      p = 3; while (I >= pow10_u64(p + 1)) ++p;
+      const uint64_t D = pow10_u64(p - 2) << s;   // <= M, fits
+      q = M / D; rem = M % D; den = D;
+    } else {
+      p = 2;
+      for (; p >= -10; --p) {
+        bool ge;
+        if (p >= 0) ge = (s < 40) && ((pow10_u64(p) << s) <= M);
+        else ge = ((M * pow10_u64(-p)) >> s) >= 1;
+        if (ge) break;
+      }
+      if (p < -10) return false;
+      const uint64_t N = M * pow10_u64(2 - p);     // < 2^24 * 10^12 < 2^64
+      q = N >> s; rem = N & ((1ull << s) - 1); den = 1ull << s;
+    }
+  }
+  // round half to even on the exact value (glibc printf)
+  const uint64_t twice = rem << 1;            // rem < den <= 2^61: no overflow
+  if (twice > den || (twice == den && (q & 1u))) ++q;
+  if (q >= 1000) { q = 100; ++p; }
+  Dec d; d.m = q; d.e10 = p - 2; d.neg = neg; d.ok = true; d.dropped = false; d.special = false;
+  return dec_to_f32(d, out);
+}
+
+// ---- names -------------------------------------------------------------------------------
+// gene_name (cbook.py:308-329): cut at the first '|'; unless the name starts with "ev", drop
+// a trailing ".x" whose suffix is exactly one character.  Adjusts b.
+template <class R>
+JX_HD void strip_isoform(R& rd, int a, int& b) {
+  bool ev = (b - a >= 2) && rd(a) == 'e' && rd(a + 1) == 'v';
+  int dot = -1, end = b;
+  for (int p = a; p < b; ++p) {
+    uint32_t c = rd(p);
+    if (c == '|') { end = p; break; }
+    if (c == '.') dot = p;
+  }
+  if (!ev && dot >= 0 && end - dot - 1 == 1) end = dot;
+  b = end;
+}
+
+// 64-bit hash of the bytes [a,b): two independent 32-bit FNV-style lanes + avalanche.
+// Host (BED table build) and device (probe) must agree, hence JX_HD.
+JX_HD uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+template <class R>
+JX_HD uint64_t name_hash(R& rd, int a, int b) {
+  uint32_t h1 = 0x811C9DC5u, h2 = 0x9747B28Cu;
+  for (int p = a; p < b; ++p) {
+    uint32_t c = rd(p);
+    h1 = (h1 ^ c) * 16777619u;
+    h2 = (h2 + c) * 0x9E3779B1u; h2 = (h2 << 13) | (h2 >> 19);
+  }
+  h1 = fmix32(h1 ^ (uint32_t)(b - a));
+  h2 = fmix32(h2 + h1);
+  return ((uint64_t)h1 << 32) | h2;
+}
+
+// ---- one line --------------------------------------------------------------------------------
+struct LineTok {
+  int qa, qb, sa, sb;   // raw name spans
+  float score;
+  int nconv;            // number of successful sscanf conversions (0..12)
+  int eflag;            // evalue < 1e-10 : 1 / 0
+  bool hard;            // a needed numeric field could not be converted exactly on device
+  bool longname;        // a name of >= 128 bytes (cblast.pyx char[128] overflow)
+};
+
+// sscanf(line, "%s\t%s\t%f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lf\t%f") over [s,e) (e = terminator).
+// Fields that are not converted keep the zero initialisation of the Cython object.
+template <class R>
+JX_HD void tokenize_line(R& rd, int s, int e, LineTok& t) {
+  t.qa = t.qb = t.sa = t.sb = s; t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false;
+  int p = s;
+  while (p < e && is_space(rd(p))) ++p;
+  t.qa = p; while (p < e && !is_space(rd(p))) ++p; t.qb = p;
+  if (t.qb == t.qa) return;
+  t.nconv = 1;
+  while (p < e && is_space(rd(p))) ++p;
+  t.sa = p; while (p < e && !is_space(rd(p))) ++p; t.sb = p;
+  if (t.sb == t.sa) return;
+  t.nconv = 2;
+  if (t.qb - t.qa >= 128 || t.sb - t.sa >= 128) t.longname = true;
+  Dec d;
+  while (p < e && is_space(rd(p))) ++p;
+  int p2 = scan_decimal(rd, p, e, d);            // %f pctid (value not needed here)
+  if (d.special) { t.hard = true; return; }
+  if (!d.ok) return;
+  p = p2; t.nconv = 3;
+  for (int k = 0; k < 7; ++k) {                   // 7 x %d
+    while (p < e && is_space(rd(p))) ++p;
+    p2 = scan_int(rd, p, e);
+    if (p2 == p) return;
+    p = p2; ++t.nconv;
+  }
+  while (p < e && is_space(rd(p))) ++p;
+  p2 = scan_decimal(rd, p, e, d);                 // %lf evalue
+  if (d.special) { t.hard = true; return; }
+  if (!d.ok) return;
+  p = p2; t.nconv = 11;
+  int lt = dec_lt_1e10(d);
+  if (lt < 0) { t.hard = true; return; }
+  t.eflag = lt;
+  while (p < e && is_space(rd(p))) ++p;
+  p2 = scan_decimal(rd, p, e, d);                 // %f score
+  if (d.special) { t.hard = true; return; }
+  if (!d.ok) return;
+  t.nconv = 12;
+  if (!dec_to_f32(d, t.score)) t.hard = true;
+}
+
+}  // namespace jx

@@ -1,0 +1,426 @@
+// Stage 2: synteny scan on the GPU (K9/K10 of SURVEY.md section 2).
+//
+// Replaces src/jcvi/compara/synteny.py:
+//   255-297  read_blast   file-order first-seen de-duplication        -> sort by (qi,si), min line per run
+//   239-252  group_hits / 437-452 batch_scan  per chromosome pair      -> stable sort by chromosome-pair id
+//   402-434  synteny_scan single linkage (Grouper.join)                -> window neighbour search + lock-free union-find
+//   214-219  _score        min(#distinct qi, #distinct si) >= N        -> per-component counters
+//   utils/grouper.py:73-81 iteration order (dict insertion)            -> "birth" = smallest sorted index that has an
+//                                                                        earlier neighbour; components ordered by birth
+#include "jx_internal.cuh"
+
+namespace {
+
+inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+__global__ void k_select_valid(const uint4* __restrict__ recs, uint32_t n, uint4* out, uint32_t* out_idx, uint32_t* counter) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
+    if (i < n) r = __ldcs(recs + i);
+    bool keep = r.x != JX_NOREC;
+    uint32_t slot = warp_append(keep, counter);
+    if (keep) { out[slot] = r; out_idx[slot] = i; }
+  }
+}
+
+__global__ void k_make_keys(const uint4* __restrict__ C, uint32_t n, int sb, uint64_t* keys, uint32_t* vals) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint4 r = C[j];
+  keys[j] = ((uint64_t)r.x << sb) | r.y;
+  vals[j] = j;
+}
+
+// first occurrence in file order within each run of equal (qi,si)
+__global__ void k_run_first(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                            const uint32_t* __restrict__ Cidx, uint32_t n, uint32_t* flag, uint32_t* pick) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint64_t k = keys[t];
+  const bool head = (t == 0) || keys[t - 1] != k;
+  flag[t] = head;
+  if (!head) return;
+  uint32_t bj = vals[t], bi = Cidx[bj];
+  for (uint32_t u = t + 1; u < n && keys[u] == k; ++u) {
+    uint32_t j = vals[u], i = Cidx[j];
+    if (i < bi) { bj = j; bi = i; }
+  }
+  pick[t] = bj;
+}
+
+__global__ void k_scatter_pts(const uint64_t* keys, const uint32_t* pick, const uint32_t* flag, const uint32_t* pos,
+                              uint32_t n, int sb, const uint4* C, const int32_t* qchr, const int32_t* schr, int64_t nschr,
+                              int32_t* px, int32_t* py, float* psc, uint64_t* cpkey, uint32_t* ident) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n || !flag[t]) return;
+  uint32_t o = pos[t];
+  uint64_t k = keys[t];
+  int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & ((1ull << sb) - 1));
+  px[o] = x; py[o] = y;
+  psc[o] = __uint_as_float(C[pick[t]].z);
+  cpkey[o] = (uint64_t)qchr[x] * (uint64_t)nschr + (uint64_t)schr[y];
+  ident[o] = o;
+}
+
+template <class T>
+__global__ void k_permute(const T* in, const uint32_t* perm, uint32_t n, T* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = in[perm[t]];
+}
+
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+// synteny_scan inner loops: for point i walk back while x_i - x_j <= xdist (same chromosome pair)
+__global__ void k_link(const int32_t* __restrict__ px, const int32_t* __restrict__ py, const uint64_t* __restrict__ cp,
+                       uint32_t n, int xdist, int ydist, int is_self, int intrabound, uint32_t* parent, uint8_t* hasprev) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t xi = px[i], yi = py[i];
+  const uint64_t ci = cp[i];
+  const int di = abs(xi - yi);
+  bool any = false;
+  for (int64_t j = (int64_t)i - 1; j >= 0; --j) {
+    if (cp[j] != ci) break;
+    const int32_t xj = px[j];
+    if (xi - xj > xdist) break;
+    const int32_t yj = py[j];
+    if (abs(yi - yj) > ydist) continue;
+    if (is_self) {
+      int dj = abs(xj - yj);
+      if ((di < dj ? di : dj) < intrabound) continue;
+    }
+    uf_union(parent, i, (uint32_t)j);
+    any = true;
+  }
+  hasprev[i] = any;
+}
+
+__global__ void k_label(uint32_t* parent, const uint8_t* hasprev, uint32_t n, uint32_t* label, uint32_t* birth) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r = uf_find(parent, i);
+  label[i] = r;
+  if (hasprev[i]) atomicMin(birth + r, i);
+}
+
+// #distinct qi per component: point i counts iff no earlier point of its row (same cp, same x)
+// carries the same label
+__global__ void k_count_x(const int32_t* px, const uint64_t* cp, const uint32_t* label, uint32_t n, uint32_t* nx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t l = label[i];
+  for (int64_t j = (int64_t)i - 1; j >= 0 && cp[j] == cp[i] && px[j] == px[i]; --j)
+    if (label[j] == l) return;
+  atomicAdd(nx + l, 1u);
+}
+__global__ void k_label_y_keys(const uint32_t* label, const int32_t* py, uint32_t n, uint64_t* keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = ((uint64_t)label[i] << 32) | (uint32_t)py[i];
+}
+__global__ void k_count_unique(const uint64_t* keys, uint32_t n, uint32_t* ny) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (t == 0 || keys[t] != keys[t - 1]) atomicAdd(ny + (uint32_t)(keys[t] >> 32), 1u);
+}
+
+__global__ void k_pass_flags(const uint32_t* label, const uint32_t* birth, const uint32_t* nx, const uint32_t* ny,
+                             uint32_t n, int N, uint32_t* flag, uint32_t* inclus) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t l = label[i];
+  bool clustered = birth[l] != 0xFFFFFFFFu;        // isolated points never enter the Grouper
+  uint32_t s = nx[l] < ny[l] ? nx[l] : ny[l];
+  flag[i] = clustered && (int)s >= N;
+  if (clustered) atomicAdd(inclus, 1u);
+}
+__global__ void k_out_keys(const uint32_t* flag, const uint32_t* pos, const uint32_t* label, const uint32_t* birth,
+                           uint32_t n, uint64_t* keys, uint32_t* vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  keys[pos[i]] = ((uint64_t)birth[label[i]] << 32) | i;
+  vals[pos[i]] = i;
+}
+__global__ void k_emit(const uint64_t* keys, const uint32_t* vals, uint32_t n, const int32_t* px, const int32_t* py,
+                       const float* psc, const uint32_t* pidx, int32_t* oq, int32_t* os, float* osc, uint32_t* oidx,
+                       uint32_t* head) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t i = vals[t];
+  oq[t] = px[i]; os[t] = py[i]; osc[t] = psc[i];
+  if (oidx) oidx[t] = pidx ? pidx[i] : i;
+  head[t] = (t == 0) || (keys[t] >> 32) != (keys[t - 1] >> 32);
+}
+
+int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n, uint32_t*& pos, uint32_t& count) {
+  count = 0; pos = nullptr;
+  if (!n) return JX_OK;
+  JX_ALLOC(p, uint32_t, n, false);
+  int rc = jx_exclusive_sum(ctx, arena, flag, p, n);
+  if (rc) return rc;
+  uint32_t last[2];
+  JX_CK(cudaMemcpyAsync(&last[0], p + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&last[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  count = last[0] + last[1];
+  pos = p;
+  return JX_OK;
+}
+
+// Core: points already sorted by (chromosome pair, qi, si) on the device.
+int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32_t* py, const float* psc,
+                       const uint64_t* cp, const uint32_t* pidx, uint32_t n, int is_self, const jx_scan_opts* o,
+                       jx_scan_result* out) {
+  out->n_anchors = 0; out->n_blocks = 0;
+  out->block_start = (int64_t*)calloc(1, sizeof(int64_t));
+  if (!n) {
+    out->q_rank = (int32_t*)malloc(4); out->s_rank = (int32_t*)malloc(4); out->score = (float*)malloc(4);
+    out->index = (int64_t*)malloc(8);
+    return JX_OK;
+  }
+  JX_ALLOC(parent, uint32_t, n, false);
+  JX_ALLOC(hasprev, uint8_t, n, false);
+  JX_ALLOC(label, uint32_t, n, false);
+  JX_ALLOC(birth, uint32_t, n, false);
+  JX_ALLOC(nx, uint32_t, n, true);
+  JX_ALLOC(ny, uint32_t, n, true);
+  JX_ALLOC(d_in, uint32_t, 1, true);
+  JX_CK(cudaMemsetAsync(birth, 0xFF, (size_t)n * 4, ctx->stream));
+  JX_LAUNCH(k_iota, nblk(n), 256, 0, parent, n);
+  JX_LAUNCH(k_link, nblk(n, 128), 128, 0, px, py, cp, n, o->xdist, o->ydist, is_self, o->intrabound, parent, hasprev);
+  JX_LAUNCH(k_label, nblk(n), 256, 0, parent, hasprev, n, label, birth);
+  JX_LAUNCH(k_count_x, nblk(n), 256, 0, px, cp, label, n, nx);
+  {
+    JX_ALLOC(yk, uint64_t, n, false);
+    JX_LAUNCH(k_label_y_keys, nblk(n), 256, 0, label, py, n, yk);
+    uint64_t* yks = yk;
+    int rc = jx_sort_keys(ctx, arena, yks, n, 0, 64);
+    if (rc) return rc;
+    JX_LAUNCH(k_count_unique, nblk(n), 256, 0, yks, n, ny);
+  }
+  JX_ALLOC(flag, uint32_t, n, false);
+  JX_LAUNCH(k_pass_flags, nblk(n), 256, 0, label, birth, nx, ny, n, o->min_size, flag, d_in);
+  uint32_t* pos; uint32_t m;
+  int rc = compact_positions(ctx, arena, flag, n, pos, m);
+  if (rc) return rc;
+  uint32_t h_in = 0;
+  JX_CK(cudaMemcpyAsync(&h_in, d_in, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  out->q_rank = (int32_t*)malloc(4 * ((size_t)m + 1));
+  out->s_rank = (int32_t*)malloc(4 * ((size_t)m + 1));
+  out->score = (float*)malloc(4 * ((size_t)m + 1));
+  out->index = (int64_t*)malloc(8 * ((size_t)m + 1));
+  out->n_anchors = m;
+  if (m) {
+    JX_ALLOC(okeys, uint64_t, m, false);
+    JX_ALLOC(ovals, uint32_t, m, false);
+    JX_LAUNCH(k_out_keys, nblk(n), 256, 0, flag, pos, label, birth, n, okeys, ovals);
+    uint64_t* ok = okeys; uint32_t* ov = ovals;
+    if ((rc = jx_sort_pairs(ctx, arena, ok, ov, m, 0, 64))) return rc;
+    JX_ALLOC(oq, int32_t, m, false);
+    JX_ALLOC(os, int32_t, m, false);
+    JX_ALLOC(osc, float, m, false);
+    JX_ALLOC(oidx, uint32_t, m, false);
+    JX_ALLOC(head, uint32_t, m, false);
+    JX_LAUNCH(k_emit, nblk(m), 256, 0, ok, ov, m, px, py, psc, pidx, oq, os, osc, oidx, head);
+    std::vector<uint32_t> hhead(m), hidx(m);
+    JX_CK(cudaMemcpyAsync(out->q_rank, oq, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->s_rank, os, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->score, osc, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(hhead.data(), head, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(hidx.data(), oidx, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    int64_t nb = 0;
+    for (uint32_t t = 0; t < m; ++t) nb += hhead[t];
+    free(out->block_start);
+    out->block_start = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nb + 1));
+    int64_t b = 0;
+    for (uint32_t t = 0; t < m; ++t) {
+      if (hhead[t]) out->block_start[b++] = t;
+      out->index[t] = hidx[t];
+    }
+    out->block_start[nb] = m;
+    out->n_blocks = nb;
+  }
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  out->stats[2] = h_in;
+  JX_CK(cudaGetLastError());
+  return JX_OK;
+}
+
+// records (file order, holes marked JX_NOREC) -> scan
+int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, size_t nvalid_hint, const jx_scan_opts* o,
+                 jx_scan_result* out) {
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  int rc;
+  JX_ALLOC(C, uint4, nvalid_hint + 1, false);
+  JX_ALLOC(Cidx, uint32_t, nvalid_hint + 1, false);
+  JX_ALLOC(d_cnt, uint32_t, 1, true);
+  if (nrec) {
+    unsigned grid = std::min<unsigned>(nblk(nrec), 148u * 16u);
+    JX_LAUNCH(k_select_valid, grid, 256, 0, recs, nrec, C, Cidx, d_cnt);
+  }
+  uint32_t nC = 0;
+  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+  uint32_t n = 0;
+  int32_t *px = nullptr, *py = nullptr; float* psc = nullptr; uint64_t* cp = nullptr;
+  if (nC) {
+    JX_ALLOC(keys, uint64_t, nC, false);
+    JX_ALLOC(vals, uint32_t, nC, false);
+    JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
+    uint64_t* ks = keys; uint32_t* vs = vals;
+    if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
+    JX_ALLOC(flag, uint32_t, nC, false);
+    JX_ALLOC(pick, uint32_t, nC, false);
+    JX_LAUNCH(k_run_first, nblk(nC), 256, 0, ks, vs, Cidx, nC, flag, pick);
+    uint32_t* pos;
+    if ((rc = compact_positions(ctx, arena, flag, nC, pos, n))) return rc;
+    JX_ALLOC(x0, int32_t, n, false);
+    JX_ALLOC(y0, int32_t, n, false);
+    JX_ALLOC(s0, float, n, false);
+    JX_ALLOC(c0, uint64_t, n, false);
+    JX_ALLOC(id0, uint32_t, n, false);
+    JX_LAUNCH(k_scatter_pts, nblk(nC), 256, 0, ks, pick, flag, pos, nC, sb, C, Q.chr_lex, S.chr_lex, (int64_t)S.n_chr, x0, y0,
+              s0, c0, id0);
+    // stable sort by chromosome-pair id keeps (qi, si) order inside each pair
+    uint64_t* cs = c0; uint32_t* perm = id0;
+    const uint64_t maxcp = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
+    if ((rc = jx_sort_pairs(ctx, arena, cs, perm, n, 0, jx_bits(maxcp)))) return rc;
+    JX_ALLOC(x1, int32_t, n, false);
+    JX_ALLOC(y1, int32_t, n, false);
+    JX_ALLOC(s1, float, n, false);
+    JX_LAUNCH(k_permute<int32_t>, nblk(n), 256, 0, x0, perm, n, x1);
+    JX_LAUNCH(k_permute<int32_t>, nblk(n), 256, 0, y0, perm, n, y1);
+    JX_LAUNCH(k_permute<float>, nblk(n), 256, 0, s0, perm, n, s1);
+    px = x1; py = y1; psc = s1; cp = cs;
+  }
+  out->stats[1] = n;
+  return scan_sorted_points(ctx, arena, px, py, psc, cp, nullptr, n, ctx->is_self ? 1 : 0, o, out);
+}
+
+__global__ void k_filtered_to_recs(const int32_t* q, const int32_t* s, const float* score, uint32_t n, int is_self,
+                                   const int32_t* qchr, const int32_t* schr, uint4* recs, uint32_t* bad) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int32_t qi = q[t], si = s[t];
+  float r;
+  if (!jx::round3g_f32(score[t], r)) { atomicExch(bad, 1u); r = score[t]; }   // "%.3g" text round trip
+  uint4 rec = make_uint4((uint32_t)qi, (uint32_t)si, __float_as_uint(r), 0u);
+  if (is_self) {                                   // read_blast, synteny.py:274-283
+    if (qi > si) { rec.x = (uint32_t)si; rec.y = (uint32_t)qi; int32_t tmp = qi; qi = si; si = tmp; }
+    if (qchr[qi] == schr[si] && si - qi < 40) rec.x = JX_NOREC;
+  }
+  recs[t] = rec;
+}
+
+}  // namespace
+
+extern "C" {
+
+void jx_scan_result_free(jx_scan_result* r) {
+  if (!r) return;
+  free(r->q_rank); free(r->s_rank); free(r->score); free(r->block_start); free(r->index);
+  memset(r, 0, sizeof *r);
+}
+
+int jx_scan_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
+                 const jx_scan_opts* opts, jx_scan_result* out) {
+  if (!ctx || !opts || !out) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  TokMode mode;
+  mode.strip = strip_names;
+  mode.neardiag = ctx->is_self ? 1 : 0;
+  TokOut tok;
+  int rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok);
+  if (rc) return rc;
+  out->stats[0] = (int64_t)(tok.stats[0] - tok.stats[1]);
+  out->stats[3] = (int64_t)tok.stats[1];
+  return scan_records(ctx, arena, tok.recs, tok.n_lines, (size_t)tok.stats[2], opts, out);
+}
+
+int jx_scan_filtered(jx_ctx* ctx, const jx_filter_result* f, const jx_scan_opts* opts, jx_scan_result* out) {
+  if (!ctx || !f || !opts || !out) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  if (!ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const uint32_t n = (uint32_t)f->n;
+  JX_ALLOC(dq, int32_t, n, false);
+  JX_ALLOC(ds, int32_t, n, false);
+  JX_ALLOC(dsc, float, n, false);
+  JX_ALLOC(recs, uint4, n, false);
+  JX_ALLOC(bad, uint32_t, 1, true);
+  if (n) {
+    JX_CK(cudaMemcpyAsync(dq, f->q_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(ds, f->s_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dsc, f->score, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_LAUNCH(k_filtered_to_recs, nblk(n), 256, 0, dq, ds, dsc, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
+              ctx->side[1].chr_lex, recs, bad);
+  }
+  uint32_t hbad = 0;
+  JX_CK(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (hbad) { ctx->err = "score outside the exactly handled %.3g range"; return JX_EUNSUPPORTED; }
+  out->stats[0] = n;
+  return scan_records(ctx, arena, recs, n, n, opts, out);
+}
+
+int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const float* score, const int64_t* group,
+                   int64_t n64, int is_self, const jx_scan_opts* opts, jx_scan_result* out) {
+  if (!ctx || !opts || !out || n64 < 0 || n64 >= (1ll << 31)) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const uint32_t n = (uint32_t)n64;
+  int rc;
+  // host-side key build is avoided: sort by (qi,si) then stably by group on the device
+  std::vector<uint64_t> hk(n), hg(n);
+  int64_t maxq = 0, maxs = 0, maxg = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (qi[i] < 0 || si[i] < 0 || (group && group[i] < 0)) { ctx->err = "negative coordinate or group"; return JX_EARG; }
+    maxq = std::max<int64_t>(maxq, qi[i]); maxs = std::max<int64_t>(maxs, si[i]);
+    if (group) maxg = std::max<int64_t>(maxg, group[i]);
+  }
+  const int sb = jx_bits((uint64_t)maxs + 1), qb = jx_bits((uint64_t)maxq + 1);
+  for (uint32_t i = 0; i < n; ++i) { hk[i] = ((uint64_t)qi[i] << sb) | (uint32_t)si[i]; hg[i] = group ? (uint64_t)group[i] : 0; }
+  JX_ALLOC(keys, uint64_t, n, false);
+  JX_ALLOC(vals, uint32_t, n, false);
+  JX_ALLOC(g0, uint64_t, n, false);
+  JX_ALLOC(dx, int32_t, n, false);
+  JX_ALLOC(dy, int32_t, n, false);
+  JX_ALLOC(dsc, float, n, false);
+  int32_t *px = nullptr, *py = nullptr; float* psc = nullptr; uint64_t* cp = nullptr; uint32_t* pidx = nullptr;
+  if (n) {
+    JX_CK(cudaMemcpyAsync(keys, hk.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(g0, hg.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dx, qi, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dy, si, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dsc, score, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_LAUNCH(k_iota, nblk(n), 256, 0, vals, n);
+    uint64_t* ks = keys; uint32_t* vs = vals;
+    if ((rc = jx_sort_pairs(ctx, arena, ks, vs, n, 0, sb + qb))) return rc;
+    JX_ALLOC(g1, uint64_t, n, false);
+    JX_LAUNCH(k_permute<uint64_t>, nblk(n), 256, 0, g0, vs, n, g1);
+    uint64_t* gs = g1; uint32_t* perm = vs;
+    if ((rc = jx_sort_pairs(ctx, arena, gs, perm, n, 0, jx_bits((uint64_t)maxg + 1)))) return rc;
+    JX_ALLOC(x1, int32_t, n, false);
+    JX_ALLOC(y1, int32_t, n, false);
+    JX_ALLOC(s1, float, n, false);
+    JX_LAUNCH(k_permute<int32_t>, nblk(n), 256, 0, dx, perm, n, x1);
+    JX_LAUNCH(k_permute<int32_t>, nblk(n), 256, 0, dy, perm, n, y1);
+    JX_LAUNCH(k_permute<float>, nblk(n), 256, 0, dsc, perm, n, s1);
+    px = x1; py = y1; psc = s1; cp = gs; pidx = perm;
+  }
+  out->stats[1] = n;
+  return scan_sorted_points(ctx, arena, px, py, psc, cp, pidx, n, is_self, opts, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// K1 + K2: BLAST tab12 text -> one 16-byte record per line (gene ranks, float32 score, flags).
+//
+// Replaces the reference's per-line Python loop:
+//   Blast.__iter__            src/jcvi/formats/blast.py:90-95   (skip '#', one BlastLine per row)
+//   BlastLine.__init__        src/jcvi/formats/cblast.pyx:106-120 (sscanf of 12 fields)
+//   gene_name                 src/jcvi/utils/cbook.py:308-329
+//   qorder[query]/sorder[..]  src/jcvi/compara/blastfilter.py:56-84, synteny.py:261-283, 339-357
+//   filter_cscore pass 1      src/jcvi/compara/blastfilter.py:227-232 (optional, fused)
+//
+// Layout.  The text is cut into 8 KiB tiles; one CTA of 256 threads stages a tile (+1 KiB of
+// look-ahead) in shared memory with coalesced 16-byte loads, builds a bit mask of line
+// terminators with SIMD-in-word compares, numbers the lines that START in the tile with a
+// block scan, and publishes the tile's line count to a decoupled look-back chain so that every
+// line learns its global ordinal in the same pass (no separate newline-count pass over the
+// text).  Lines are then parsed one per thread straight out of shared memory and the record is
+// written at recs[ordinal] -- 16-byte stores, consecutive threads -> consecutive addresses.
+// HBM traffic per line: the line's bytes once + 16 bytes of record.
+#include "jx_internal.cuh"
+
+namespace {
+
+struct TokArgs {
+  const uint8_t* text;
+  int64_t n;                 // total bytes of text
+  uint64_t* desc;            // decoupled look-back descriptors, one per tile of the whole text
+  uint32_t* ticket;          // global tile ticket (monotone across launches)
+  uint4* recs;
+  uint32_t rec_cap;
+  const uint64_t* qtab; uint32_t qmask; const char* qnames; const uint32_t* qoff;
+  const uint64_t* stab; uint32_t smask; const char* snames; const uint32_t* soff;
+  const int32_t* qchr; const int32_t* schr;   // chr_lex per gene (near-diagonal rule)
+  const uint32_t* qnid; const uint32_t* snid;
+  uint32_t* best;
+  const uint64_t* excl; int64_t n_excl;
+  int strip, is_self, neardiag;
+  unsigned long long* stats;
+};
+
+#define FLAG_AGG (1ull << 62)
+#define FLAG_INC (2ull << 62)
+#define VAL_MASK ((1ull << 62) - 1)
+
+struct WinReader {
+  const uint8_t* sm;
+  const uint8_t* g;
+  int64_t base, n;
+  __device__ __forceinline__ uint32_t operator()(int p) const {
+    if (p < JX_WIN) return sm[p];
+    int64_t gp = base + p;
+    return gp < n ? g[gp] : (uint32_t)'\n';
+  }
+};
+
+template <class R>
+__device__ __forceinline__ int table_lookup(R& rd, int a, int b, const uint64_t* tab, uint32_t mask,
+                                            const char* names, const uint32_t* off) {
+  if (b <= a) return -1;
+  uint64_t h = jx::name_hash(rd, a, b);
+  uint32_t tag = (uint32_t)(h >> 32), idx = (uint32_t)h & mask;
+  for (;;) {
+    uint64_t slot = __ldg(tab + idx);
+    if (!slot) return -1;
+    if ((uint32_t)(slot >> 32) == tag) {
+      uint32_t r = (uint32_t)slot - 1u;
+      uint32_t o = __ldg(off + r), len = __ldg(off + r + 1) - o;
+      if (len == (uint32_t)(b - a)) {
+        bool eq = true;
+        for (uint32_t i = 0; i < len; ++i)
+          if ((uint32_t)(uint8_t)__ldg(names + o + i) != rd(a + (int)i)) { eq = false; break; }
+        if (eq) return (int)r;
+      }
+    }
+    idx = (idx + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ uint32_t term_bits(uint32_t w) {   // 4 bytes -> 4 terminator bits
+  uint32_t m = (__vcmpeq4(w, 0x0A0A0A0Au) | __vcmpeq4(w, 0x0D0D0D0Du)) & 0x01010101u;
+  return ((m * 0x00204081u) >> 21) & 0xFu;
+}
+
+__global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
+  __shared__ __align__(16) uint8_t sm[JX_WIN];
+  __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
+  __shared__ uint32_t s_start[JX_TOK_THREADS];  // line-start bit per byte of the tile
+  __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per segment
+  __shared__ uint32_t s_warp[JX_TOK_THREADS / 32];
+  __shared__ uint32_t s_tile, s_nlines;
+  __shared__ unsigned long long s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t base = (int64_t)tile * JX_TILE;
+
+  // ---- stage the window: coalesced 16-byte loads, '\n' beyond the end of the text ------------
+  for (int v = tid; v < JX_WIN / 16; v += JX_TOK_THREADS) {
+    int64_t gp = base + (int64_t)v * 16;
+    uint4 val;
+    if (gp + 16 <= a.n) {
+      val = __ldcs(reinterpret_cast<const uint4*>(a.text + gp));
+    } else {
+      uint8_t tmp[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tmp[i] = (gp + i < a.n) ? a.text[gp + i] : (uint8_t)'\n';
+      val = *reinterpret_cast<uint4*>(tmp);
+    }
+    reinterpret_cast<uint4*>(sm)[v] = val;
+  }
+  __syncthreads();
+
+  // ---- terminator masks for the whole window ---------------------------------------------------
+  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) {
+    const uint4* p = reinterpret_cast<const uint4*>(sm + seg * 32);
+    uint4 x = p[0], y = p[1];
+    uint32_t m = term_bits(x.x) | (term_bits(x.y) << 4) | (term_bits(x.z) << 8) | (term_bits(x.w) << 12) |
+                 (term_bits(y.x) << 16) | (term_bits(y.y) << 20) | (term_bits(y.z) << 24) | (term_bits(y.w) << 28);
+    s_term[seg] = m;
+  }
+  __syncthreads();
+
+  // ---- line starts inside the tile + block scan ---------------------------------------------------
+  uint32_t prevbit;
+  if (tid == 0) prevbit = (base == 0) ? 1u : (uint32_t)jx::is_term(a.text[base - 1]);
+  else prevbit = s_term[tid - 1] >> 31;
+  uint32_t starts = (s_term[tid] << 1) | prevbit;
+  {  // only positions that exist in the text can start a line
+    int64_t remain = a.n - (base + (int64_t)tid * JX_SEG);
+    if (remain <= 0) starts = 0;
+    else if (remain < 32) starts &= (1u << remain) - 1u;
+  }
+  s_start[tid] = starts;
+  uint32_t cnt = __popc(starts), inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < JX_TOK_THREADS / 32 ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += t; }
+    if (lane < JX_TOK_THREADS / 32) s_warp[lane] = wi - w;
+    if (lane == JX_TOK_THREADS / 32 - 1) s_nlines = wi;
+  }
+  __syncthreads();
+  s_pref[tid] = s_warp[warp] + inc - cnt;
+  const uint32_t nlines = s_nlines;
+
+  // ---- decoupled look-back: global ordinal of the tile's first line ---------------------------------
+  if (warp == 0) {
+    if (lane == 0) {
+      uint64_t d = (tile == 0 ? FLAG_INC : FLAG_AGG) | (uint64_t)nlines;
+      atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)d);
+    }
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      int64_t j = (int64_t)tile - 1;
+      for (;;) {
+        int64_t idx = j - lane;
+        uint64_t d = idx >= 0 ? *((volatile uint64_t*)(a.desc + idx)) : FLAG_INC;
+        uint32_t flag = (uint32_t)(d >> 62);
+        unsigned notready = __ballot_sync(0xFFFFFFFFu, flag == 0);
+        unsigned isinc = __ballot_sync(0xFFFFFFFFu, flag == 2);
+        int first = isinc ? __ffs(isinc) - 1 : 32;
+        unsigned upto = first < 31 ? ((2u << first) - 1u) : 0xFFFFFFFFu;
+        if (notready & upto) continue;   // spin until every needed predecessor has published
+        unsigned long long v = ((upto >> lane) & 1u) ? (d & VAL_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        excl += v;
+        if (first < 32) break;
+        j -= 32;
+      }
+      if (lane == 0) atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)(FLAG_INC | (excl + nlines)));
+    }
+    if (lane == 0) s_base = excl;
+  }
+  __syncthreads();
+  const unsigned long long line_base = s_base;
+
+  // ---- parse: one line per thread -----------------------------------------------------------------
+  WinReader rd{sm, a.text, base, a.n};
+  unsigned long long c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
+  unsigned long long first_bad = 0;
+  for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
+    const uint32_t k = k0 + tid;
+    if (k >= nlines) break;
+    // segment holding line k: last t with s_pref[t] <= k
+    int lo = 0, hi = JX_TOK_THREADS - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= k) lo = mid; else hi = mid - 1; }
+    // among equal prefixes pick the segment that actually contains the line
+    const int seg = lo;
+    const int bit = __fns(s_start[seg], 0, (int)(k - s_pref[seg]) + 1);
+    const int s = seg * JX_SEG + bit;
+    // end of line: next terminator at or after s
+    int e;
+    {
+      int w = s >> 5;
+      uint32_t m = s_term[w] & (0xFFFFFFFFu << (s & 31));
+      while (!m && ++w < JX_WIN / 32) m = s_term[w];
+      if (m) e = w * 32 + __ffs(m) - 1;
+      else { e = JX_WIN; while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e; }
+    }
+    uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+    if (s < e && sm[s] == '#') {
+      ++c_comment;
+    } else {
+      jx::LineTok t;
+      jx::tokenize_line(rd, s, e, t);
+      bool bad = false;
+      int qi = -1, si = -1;
+      bool selfhit = false;
+      if (t.nconv >= 2) {
+        if (t.longname) { bad = true; ++c_long; }
+        int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
+        if (a.is_self && (qb - qa) == (sb - sa)) {      // `is_self and query == subject` on raw names
+          selfhit = true;
+          for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
+        }
+        if (!selfhit && !bad) {
+          if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
+          qi = table_lookup(rd, qa, qb, a.qtab, a.qmask, a.qnames, a.qoff);
+          if (qi >= 0) si = table_lookup(rd, sa, sb, a.stab, a.smask, a.snames, a.soff);
+        }
+      }
+      if (selfhit) ++c_self;
+      else if (bad) { if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+      else if (qi < 0 || si < 0) ++c_unmapped;
+      else if (t.hard) { ++c_hard; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+      else {
+        if (a.is_self && qi > si) { int tmp = qi; qi = si; si = tmp; }
+        bool keep = true;
+        if (a.neardiag && a.qchr[qi] == a.schr[si] && si - qi < 40) { keep = false; ++c_self; }
+        if (keep && a.n_excl) {
+          uint64_t key = ((uint64_t)(uint32_t)qi << 32) | (uint32_t)si;
+          int64_t l = 0, h = a.n_excl;
+          while (l < h) { int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+          if (l < a.n_excl && a.excl[l] == key) { keep = false; ++c_excl; }
+        }
+        if (keep) {
+          ++c_mapped;
+          const uint32_t sbits = __float_as_uint(t.score);
+          rec = make_uint4((uint32_t)qi, (uint32_t)si, sbits, ((uint32_t)s << 1) | (uint32_t)t.eflag);
+          if (a.best && t.score > 0.f) {            // best_score[name] = max(score), starting at 0.0
+            uint32_t* bq = a.best + a.qnid[qi];
+            uint32_t* bs = a.best + a.snid[si];
+            if (__ldcg(bq) < sbits) atomicMax(bq, sbits);
+            if (__ldcg(bs) < sbits) atomicMax(bs, sbits);
+          }
+        }
+      }
+    }
+    const unsigned long long ord = line_base + k;
+    if (ord < a.rec_cap) a.recs[ord] = rec;
+  }
+
+  // ---- counters ---------------------------------------------------------------------------------------
+  unsigned long long vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    unsigned long long v = vals[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    vals[i] = v;
+  }
+  if (lane == 0) {
+    if (vals[0]) atomicAdd(a.stats + 1, vals[0]);
+    if (vals[1]) atomicAdd(a.stats + 2, vals[1]);
+    if (vals[2]) atomicAdd(a.stats + 3, vals[2]);
+    if (vals[3]) atomicAdd(a.stats + 4, vals[3]);
+    if (vals[4]) atomicAdd(a.stats + 5, vals[4]);
+    if (vals[5]) atomicAdd(a.stats + 8, vals[5]);
+    if (vals[6]) atomicAdd(a.stats + 9, vals[6]);
+  }
+  if (first_bad) atomicMin(a.stats + 7, first_bad);
+  if (tid == 0) {
+    atomicAdd(a.stats + 0, (unsigned long long)nlines);
+    if (line_base + nlines > a.rec_cap) atomicExch(a.stats + 6, 1ull);
+  }
+}
+
+}  // namespace
+
+int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
+                     const TokMode& mode, TokOut& out) {
+  if (!ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
+  if (nbytes < 0 || (nbytes && !text)) return JX_EARG;
+  const int64_t ntiles = (nbytes + JX_TILE - 1) / JX_TILE;
+  out.ntiles = ntiles;
+  out.nbytes = nbytes;
+  const uint8_t* d_text = nullptr;
+  constexpr int64_t CHUNK = 64ll << 20;   // H2D pipelining granule (multiple of the tile size)
+  const int64_t nchunks = (nbytes + CHUNK - 1) / CHUNK;
+  std::vector<cudaEvent_t> copied;
+  if (on_device) {
+    if (((uintptr_t)text & 15u) != 0) { ctx->err = "device text must be 16-byte aligned"; return JX_EARG; }
+    d_text = (const uint8_t*)text;
+  } else {
+    JX_ALLOC(buf, uint8_t, (size_t)nbytes + 16, false);
+    d_text = buf;
+    // the copy stream must not run ahead of the allocation on the compute stream
+    cudaEvent_t ready;
+    JX_CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    JX_CK(cudaEventRecord(ready, ctx->stream));
+    JX_CK(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+    cudaEventDestroy(ready);
+    for (int64_t c = 0; c < nchunks; ++c) {
+      int64_t off = c * CHUNK, len = std::min(CHUNK, nbytes - off);
+      JX_CK(cudaMemcpyAsync(buf + off, text + off, (size_t)len, cudaMemcpyHostToDevice, ctx->copy_stream));
+      cudaEvent_t ev;
+      JX_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      JX_CK(cudaEventRecord(ev, ctx->copy_stream));
+      copied.push_back(ev);
+    }
+  }
+  out.d_text = d_text;
+
+  // record capacity: lines are >= 24 bytes in any real table; retry with the exact worst case
+  // (every byte a line) only if that guess overflows.
+  JX_ALLOC(d_stats, unsigned long long, 12, true);
+  JX_ALLOC(d_ticket, uint32_t, 1, true);
+  JX_ALLOC(d_desc, uint64_t, (size_t)ntiles, true);
+  out.desc = d_desc;
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    uint64_t cap64 = attempt == 0 ? (uint64_t)(nbytes / 20 + 1024) : (uint64_t)nbytes + 1;
+    if (cap64 > 0xFFFFFFF0ull) { ctx->err = "more than 2^32 lines in one text"; return JX_EARG; }
+    JX_ALLOC(recs, uint4, (size_t)cap64, false);
+    out.recs = recs;
+    if (attempt) {
+      JX_CK(cudaMemsetAsync(d_stats, 0, 12 * sizeof(unsigned long long), ctx->stream));
+      JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), ctx->stream));
+      JX_CK(cudaMemsetAsync(d_desc, 0, (size_t)ntiles * sizeof(uint64_t), ctx->stream));
+      if (mode.best) JX_CK(cudaMemsetAsync(mode.best, 0, (size_t)ctx->n_name_ids * sizeof(uint32_t), ctx->stream));
+    }
+    {
+      unsigned long long init = ~0ull;
+      JX_CK(cudaMemcpyAsync(d_stats + 7, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TokArgs a;
+    a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.recs = recs; a.rec_cap = (uint32_t)cap64;
+    a.qtab = Q.table; a.qmask = Q.tmask; a.qnames = Q.names; a.qoff = Q.name_off;
+    a.stab = S.table; a.smask = S.tmask; a.snames = S.names; a.soff = S.name_off;
+    a.qchr = Q.chr_lex; a.schr = S.chr_lex; a.qnid = Q.name_id; a.snid = S.name_id;
+    a.best = mode.best; a.excl = mode.excl; a.n_excl = mode.n_excl;
+    a.strip = mode.strip; a.is_self = ctx->is_self ? 1 : 0; a.neardiag = mode.neardiag;
+    a.stats = d_stats;
+    const int64_t tiles_per_chunk = CHUNK / JX_TILE;
+    for (int64_t c = 0; c < std::max<int64_t>(nchunks, 0); ++c) {
+      int64_t t0 = c * tiles_per_chunk, t1 = std::min(ntiles, t0 + tiles_per_chunk);
+      if (!on_device && attempt == 0) {
+        // a tile's look-ahead may reach into the next chunk: wait for that copy too
+        JX_CK(cudaStreamWaitEvent(ctx->stream, copied[(size_t)std::min(c + 1, nchunks - 1)], 0));
+      }
+      cudaEvent_t e0, e1;
+      JX_CK(cudaEventCreate(&e0));
+      JX_CK(cudaEventCreate(&e1));
+      JX_CK(cudaEventRecord(e0, ctx->stream));
+      JX_LAUNCH(k_tokenize, (unsigned)(t1 - t0), JX_TOK_THREADS, 0, a);
+      JX_CK(cudaEventRecord(e1, ctx->stream));
+      ctx->tok_events.emplace_back(e0, e1);
+    }
+    ctx->tok_bytes += nbytes;
+    JX_CK(cudaGetLastError());
+    JX_CK(cudaMemcpyAsync(out.stats, d_stats, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    if (!out.stats[6]) break;
+    if (attempt == 1) { ctx->err = "record buffer overflow"; return JX_EINTERNAL; }
+  }
+  for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
+  out.n_lines = (uint32_t)out.stats[0];
+  if (out.stats[5]) {
+    ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +
+               " (overflows cblast.pyx's char[128]; undefined behaviour in the reference)";
+    return JX_EUNSUPPORTED;
+  }
+  if (out.stats[4]) {
+    ctx->err = "numeric field the device tokenizer cannot convert exactly (inf/nan/hex float, >19 significant "
+               "digits or dangling exponent) near byte offset " + std::to_string(out.stats[7] - 1);
+    return JX_EUNSUPPORTED;
+  }
+  return JX_OK;
+}

@@ -1,0 +1,252 @@
+"""Per-GPU engine: owns one jx_ctx (include/jcvi_b200.h) and the BED pair loaded on it."""
+import ctypes
+
+import numpy as np
+
+from . import _cabi as C
+
+_ERR = {
+    C.JX_ECUDA: RuntimeError,
+    C.JX_EARG: ValueError,
+    C.JX_EZERODIV: ZeroDivisionError,      # blastfilter.py:235
+    C.JX_EUNSUPPORTED: NotImplementedError,
+    C.JX_EDUPANCHOR: AssertionError,       # synteny.py:397
+    C.JX_EINTERNAL: RuntimeError,
+}
+
+
+def _text_ptr(text):
+    """-> (pointer, nbytes, on_device, keepalive)."""
+    if hasattr(text, "data_ptr") and hasattr(text, "is_cuda"):          # torch tensor
+        t = text.contiguous()
+        return t.data_ptr(), t.numel() * t.element_size(), int(t.is_cuda), t
+    if hasattr(text, "__cuda_array_interface__"):
+        cai = text.__cuda_array_interface__
+        n = int(np.prod(cai["shape"])) * np.dtype(cai["typestr"]).itemsize
+        return cai["data"][0], n, 1, text
+    if isinstance(text, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(text, dtype=np.uint8)
+        return a.ctypes.data, a.size, 0, a
+    a = np.ascontiguousarray(text).view(np.uint8).reshape(-1)
+    return a.ctypes.data, a.size, 0, a
+
+
+class FilterResult(object):
+    def __init__(self, r, lib, Gq, Gs, want_mothers):
+        n = r.n
+        self.n = n
+        self.q_rank = C.as_np(r.q_rank, n, np.int32)
+        self.s_rank = C.as_np(r.s_rank, n, np.int32)
+        self.score = C.as_np(r.score, n, np.float32)
+        self.line_off = C.as_np(r.line_off, n, np.uint64)
+        self.text = ctypes.string_at(r.text, r.text_len) if r.text else None
+        self.q_mother = C.as_np(r.q_mother, Gq, np.int32) if want_mothers else None
+        self.s_mother = C.as_np(r.s_mother, Gs, np.int32) if want_mothers else None
+        self.stats = dict(zip(("lines", "mapped", "unmapped", "after_exclude", "after_cscore", "after_dedupe",
+                               "after_tandem", "comments"), list(r.stats)))
+
+
+class ScanResult(object):
+    def __init__(self, r, with_index=False):
+        n, nb = r.n_anchors, r.n_blocks
+        self.n_anchors, self.n_blocks = n, nb
+        self.q_rank = C.as_np(r.q_rank, n, np.int32)
+        self.s_rank = C.as_np(r.s_rank, n, np.int32)
+        self.score = C.as_np(r.score, n, np.float32)
+        self.block_start = C.as_np(r.block_start, nb + 1, np.int64)
+        self.index = C.as_np(r.index, n, np.int64) if with_index else None
+        self.stats = dict(zip(("lines", "hits", "clustered", "comments"), list(r.stats)[:4]))
+
+
+class LiftoverResult(object):
+    def __init__(self, r, n_lines):
+        n = r.n_lifted
+        self.n_lifted = n
+        self.q_rank = C.as_np(r.q_rank, n, np.int32)
+        self.s_rank = C.as_np(r.s_rank, n, np.int32)
+        self.score = C.as_np(r.score, n, np.float32)
+        self.block = C.as_np(r.block, n, np.int32)
+        self.accepted = C.as_np(r.accepted, n_lines, np.uint8)
+        self.raw_score = C.as_np(r.raw_score, n_lines, np.float32)
+        self.stats = dict(zip(("lines", "hits", "anchors", "lifted", "tree_walked", "comments"), list(r.stats)[:6]))
+
+
+class Engine(object):
+    """One per GPU.  Not thread-safe (like a jx_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = C.lib()
+        ctx = ctypes.c_void_p()
+        rc = self.lib.jx_ctx_create(int(device), ctypes.byref(ctx))
+        if rc != 0:
+            raise RuntimeError("jcvi_b200: no usable CUDA device %d (jx_ctx_create -> %d); there is no CPU fallback"
+                               % (device, rc))
+        self.ctx = ctx
+        self.device = device
+        self._pair = None
+        self.Gq = self.Gs = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.jx_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.jx_last_error(self.ctx).decode()
+            raise _ERR.get(rc, RuntimeError)(msg)
+
+    # ---- BED pair -----------------------------------------------------------------------------
+    def load_pair(self, qbed, sbed, is_self):
+        key = (id(qbed), id(sbed), bool(is_self))
+        if self._pair == key:
+            return
+        tq = qbed.tables()
+        ts = tq if (is_self or sbed is qbed) else sbed.tables()
+        ids = {}
+        for a in tq["accns"]:
+            ids.setdefault(a, len(ids))
+        for a in ts["accns"]:
+            ids.setdefault(a, len(ids))
+        nid_q = np.fromiter((ids[a] for a in tq["accns"]), dtype=np.uint32, count=tq["G"])
+        nid_s = np.fromiter((ids[a] for a in ts["accns"]), dtype=np.uint32, count=ts["G"])
+        slast = ts["last"]
+        same = np.fromiter((slast.get(a, -1) for a in tq["accns"]), dtype=np.int32, count=tq["G"])
+        keep = []
+        for side, t, nid in ((0, tq, nid_q), (1, ts, nid_s)):
+            b = C.JxBed()
+            b.n_genes = t["G"]
+            arrs = [t["names"], t["name_off"], t["indexable"], t["chr_lex"], t["chr_begin"], t["chr_end"], t["length"],
+                    t["accn_lexrank"], nid]
+            keep += arrs
+            (b.names, b.name_off, b.indexable, b.chr_lex, b.chr_begin, b.chr_end, b.length, b.accn_lexrank,
+             b.name_id) = [C.ptr(a) for a in arrs]
+            b.n_chr = t["n_chr"]
+            self._check(self.lib.jx_bed_load(self.ctx, side, ctypes.byref(b)))
+        self._check(self.lib.jx_pair_setup(self.ctx, int(bool(is_self)), C.ptr(same), len(ids)))
+        self._pair = key
+        self._beds = (qbed, sbed)          # keep alive: the cache key uses id()
+        self.Gq, self.Gs = tq["G"], ts["G"]
+
+    # ---- stages ---------------------------------------------------------------------------------
+    def blastfilter(self, text, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None, want_text=True,
+                    want_mothers=False, raw=False):
+        p, n, dev, keep = _text_ptr(text)
+        o = C.JxFilterOpts()
+        o.strip_names = int(bool(strip_names))
+        o.cscore = float(cscore or 0.0)
+        o.tandem_nmax = int(tandem_Nmax or 0)
+        ek = None
+        if exclude_keys is not None and len(exclude_keys):
+            ek = np.unique(np.asarray(exclude_keys, dtype=np.uint64))
+            o.exclude_keys = C.ptr(ek)
+            o.n_exclude = len(ek)
+        o.want_text = int(bool(want_text))
+        o.want_mothers = int(bool(want_mothers))
+        r = C.JxFilterResult()
+        rc = self.lib.jx_blastfilter(self.ctx, p, n, dev, ctypes.byref(o), ctypes.byref(r))
+        if rc != 0:
+            self.lib.jx_filter_result_free(ctypes.byref(r))
+            self._check(rc)
+        if raw:
+            return r          # caller frees with free_filter()
+        try:
+            return FilterResult(r, self.lib, self.Gq, self.Gs, want_mothers)
+        finally:
+            self.lib.jx_filter_result_free(ctypes.byref(r))
+
+    def free_filter(self, r):
+        self.lib.jx_filter_result_free(ctypes.byref(r))
+
+    def _scan_opts(self, xdist, ydist, N, intrabound):
+        o = C.JxScanOpts()
+        o.xdist, o.ydist, o.min_size, o.intrabound = int(xdist), int(ydist), int(N), int(intrabound)
+        return o
+
+    def scan_text(self, text, strip_names=False, xdist=20, ydist=20, N=4, intrabound=300):
+        p, n, dev, keep = _text_ptr(text)
+        o = self._scan_opts(xdist, ydist, N, intrabound)
+        r = C.JxScanResult()
+        rc = self.lib.jx_scan_text(self.ctx, p, n, dev, int(bool(strip_names)), ctypes.byref(o), ctypes.byref(r))
+        try:
+            self._check(rc)
+            return ScanResult(r)
+        finally:
+            self.lib.jx_scan_result_free(ctypes.byref(r))
+
+    def scan_filtered(self, raw_filter_result, xdist=20, ydist=20, N=4, intrabound=300):
+        o = self._scan_opts(xdist, ydist, N, intrabound)
+        r = C.JxScanResult()
+        rc = self.lib.jx_scan_filtered(self.ctx, ctypes.byref(raw_filter_result), ctypes.byref(o), ctypes.byref(r))
+        try:
+            self._check(rc)
+            return ScanResult(r)
+        finally:
+            self.lib.jx_scan_result_free(ctypes.byref(r))
+
+    def scan_points(self, qi, si, score, group=None, xdist=20, ydist=20, N=4, is_self=False, intrabound=300):
+        qi = np.ascontiguousarray(qi, dtype=np.int32)
+        si = np.ascontiguousarray(si, dtype=np.int32)
+        score = np.ascontiguousarray(score, dtype=np.float32)
+        g = None if group is None else np.ascontiguousarray(group, dtype=np.int64)
+        o = self._scan_opts(xdist, ydist, N, intrabound)
+        r = C.JxScanResult()
+        rc = self.lib.jx_scan_points(self.ctx, C.ptr(qi), C.ptr(si), C.ptr(score), C.ptr(g), len(qi), int(bool(is_self)),
+                                     ctypes.byref(o), ctypes.byref(r))
+        try:
+            self._check(rc)
+            return ScanResult(r, with_index=True)
+        finally:
+            self.lib.jx_scan_result_free(ctypes.byref(r))
+
+    def liftover_text(self, text, a_qi, a_si, a_block, strip_names=True, dist=10):
+        p, n, dev, keep = _text_ptr(text)
+        a_qi = np.ascontiguousarray(a_qi, dtype=np.int32)
+        a_si = np.ascontiguousarray(a_si, dtype=np.int32)
+        a_block = np.ascontiguousarray(a_block, dtype=np.int32)
+        r = C.JxLiftoverResult()
+        rc = self.lib.jx_liftover_text(self.ctx, p, n, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si),
+                                       C.ptr(a_block), len(a_qi), ctypes.byref(r))
+        try:
+            self._check(rc)
+            return LiftoverResult(r, len(a_qi))
+        finally:
+            self.lib.jx_liftover_result_free(ctypes.byref(r))
+
+    def nearest_anchor(self, points, anchors, dist):
+        pts = np.ascontiguousarray(points, dtype=np.int64).reshape(-1, 2)
+        anc = np.ascontiguousarray(anchors, dtype=np.int64).reshape(-1, 2)
+        near = np.zeros(len(pts), dtype=np.int64)
+        dd = np.zeros(len(pts), dtype=np.int64)
+        self._check(self.lib.jx_nearest_anchor(self.ctx, C.ptr(pts), len(pts), C.ptr(anc), len(anc), int(dist),
+                                               C.ptr(near), C.ptr(dd)))
+        return near, dd
+
+    # ---- instrumentation ----------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.jx_launch_count(self.ctx))
+
+    def tokenizer_timing(self, reset=True):
+        ms = ctypes.c_double(); n = ctypes.c_int64(); b = ctypes.c_int64()
+        self._check(self.lib.jx_tokenizer_timing(self.ctx, int(reset), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b)))
+        return ms.value, n.value, b.value
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine for `device` (default: LOCAL_RANK or 0)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("JCVI_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    e = _ENGINES.get(device)
+    if e is None:
+        e = _ENGINES[device] = Engine(device)
+    return e

@@ -1,0 +1,139 @@
+"""Host-side BED handling of the hot path (kept on the host: it is O(genes), not O(hits)).
+
+Mirrors the part of the reference that DEFINES gene ranks:
+  BedLine  src/jcvi/formats/bed.py:40-73     (start = col2 + 1, accn = col4)
+  Bed      src/jcvi/formats/bed.py:141-198   (skip blank/#/browser/track; sort by
+           (natsort_key(seqid), start, accn); order[accn] = (rank, BedLine), later duplicate wins)
+natsort is an unpinned third-party dependency of the reference (pyproject.toml:49) that is
+not installed here; `natsort_key` restates its default algorithm (split on runs of decimal
+digits, ints for digit runs, leading "" when the first chunk is numeric).
+"""
+import re
+
+import numpy as np
+
+_num = re.compile(r"([0-9]+)")
+
+
+def natsort_key(s):
+    parts = [p for p in _num.split(s) if p != ""]
+    out = [int(p) if (p[0] in "0123456789" and p.isascii() and p.isdigit()) else p for p in parts]
+    if out and isinstance(out[0], int):
+        out.insert(0, "")
+    return tuple(out)
+
+
+class BedLine(object):
+    __slots__ = ("seqid", "start", "end", "accn", "extra", "score", "strand", "args", "nargs")
+
+    def __init__(self, sline):
+        args = sline.strip().split("\t")
+        self.nargs = nargs = len(args)
+        self.seqid = args[0]
+        self.start = int(args[1]) + 1
+        self.end = int(args[2])
+        assert self.start <= self.end, "start={0} end={1}".format(self.start, self.end)
+        self.extra = self.accn = self.score = self.strand = None
+        if nargs > 3:
+            self.accn = args[3]
+        if nargs > 4:
+            self.score = args[4]
+        if nargs > 5:
+            self.strand = args[5]
+        if nargs > 6:
+            self.extra = args[6:]
+        self.args = args
+
+    def __str__(self):
+        args = [self.seqid, self.start - 1, self.end]
+        for x in (self.accn, self.score, self.strand):
+            if x is not None:
+                args.append(x)
+        if self.extra is not None:
+            args += self.extra
+        return "\t".join(str(x) for x in args)
+
+    __repr__ = __str__
+
+    def __getitem__(self, key):
+        return getattr(self, key)
+
+
+class Bed(list):
+    def __init__(self, filename=None, key=None, sorted=True):
+        super().__init__()
+        self.filename = filename
+        self.nullkey = lambda x: (natsort_key(x.seqid), x.start, x.accn)
+        self.key = key or self.nullkey
+        self._tables = None
+        if not filename:
+            return
+        with open(filename) as fp:
+            for line in fp:
+                if line.strip() == "" or line[0] == "#" or line.startswith("browser ") or line.startswith("track name"):
+                    continue
+                self.append(BedLine(line))
+        if sorted:
+            self.sort(key=self.key)
+
+    @property
+    def order(self):
+        return dict((f.accn, (i, f)) for (i, f) in enumerate(self))
+
+    @property
+    def seqids(self):
+        seen = {}
+        for b in self:
+            seen.setdefault(b.seqid, None)
+        return sorted(seen, key=natsort_key)
+
+    # ---- device tables ---------------------------------------------------------------------
+    def tables(self):
+        """Arrays in rank order for jx_bed_load (see include/jcvi_b200.h, struct jx_bed)."""
+        if getattr(self, "_tables", None) is not None:
+            return self._tables
+        G = len(self)
+        accns = [b.accn for b in self]
+        if any(a is None for a in accns):
+            raise AssertionError("BED needs >= 4 columns")
+        enc = [a.encode() for a in accns]
+        lens = np.fromiter((len(e) for e in enc), dtype=np.int64, count=G)
+        off = np.zeros(G + 1, dtype=np.uint32)
+        np.cumsum(lens, out=off[1:])
+        blob = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if G else np.zeros(0, dtype=np.uint8)
+        last = {}
+        for i, a in enumerate(accns):
+            last[a] = i
+        indexable = np.zeros(G, dtype=np.uint8)
+        indexable[list(last.values())] = 1
+        # seqid runs; ranks of one seqid must be contiguous (equal natsort keys of distinct
+        # seqids, e.g. chr1 / chr01, would interleave them)
+        seqid_of = [b.seqid for b in self]
+        chr_begin = np.zeros(G, dtype=np.int32)
+        chr_end = np.zeros(G, dtype=np.int32)
+        runs = []
+        i = 0
+        while i < G:
+            j = i
+            while j < G and seqid_of[j] == seqid_of[i]:
+                j += 1
+            runs.append((seqid_of[i], i, j))
+            chr_begin[i:j] = i
+            chr_end[i:j] = j
+            i = j
+        names = [r[0] for r in runs]
+        if len(set(names)) != len(names):
+            raise NotImplementedError(
+                "seqids with equal natural-sort keys interleave in the BED order (%s); not supported" % self.filename)
+        lex = {s: k for k, s in enumerate(sorted(names, key=lambda s: s.encode()))}
+        chr_lex = np.zeros(G, dtype=np.int32)
+        for s, a, b in runs:
+            chr_lex[a:b] = lex[s]
+        length = np.fromiter((abs(b.end - b.start) for b in self), dtype=np.int64, count=G).astype(np.int32)
+        order = sorted(range(G), key=lambda i: (enc[i], i))
+        lexrank = np.zeros(G, dtype=np.uint32)
+        lexrank[order] = np.arange(G, dtype=np.uint32)
+        self._tables = dict(G=G, names=blob, name_off=off, indexable=indexable, chr_lex=chr_lex, chr_begin=chr_begin,
+                            chr_end=chr_end, length=length, accn_lexrank=lexrank, n_chr=len(runs), accns=accns,
+                            seqids=names, last=last)
+        return self._tables

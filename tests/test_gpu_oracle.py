@@ -1,0 +1,166 @@
+"""GPU parity against the CPU oracle on seeded synthetic tables (sizes the oracle finishes in
+seconds), plus API-level checks of the point interfaces."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import read
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from jcvi_b200.compara import blastfilter, synteny
+    return blastfilter, synteny
+
+
+def _pipeline(tmp, mods, seed, Gq, Gs, n, self_mode=False, bf_args=(), scan_args=(), lift_args=(), **kw):
+    import oracle
+    from jcvi_b200 import synth
+    bf, syn = mods
+    d = str(tmp)
+    q, s = ("A", "A") if self_mode else ("A", "B")
+    qbed, sbed, last = synth.write_dataset(d, q, s, seed, Gq, Gs, n, self_mode=self_mode, **kw)
+    if self_mode:
+        sbed = qbed
+    beds = ["--qbed=" + qbed, "--sbed=" + sbed]
+
+    def opt(args, name, default, cast):
+        for a in args:
+            if a.startswith("--" + name + "="):
+                return cast(a.split("=", 1)[1])
+        return default
+
+    ost = oracle.blastfilter(last, qbed, sbed, out_path=last + ".orc.filtered",
+                             strip_names="--no_strip_names" not in bf_args, cscore=opt(bf_args, "cscore", 0.7, float),
+                             tandem_Nmax=opt(bf_args, "tandem_Nmax", 10, int))
+    bf.main([last] + beds + list(bf_args))
+    assert read(last + ".filtered") == read(last + ".orc.filtered")
+    oracle.scan(last + ".filtered", last + ".orc.anchors", qbed, sbed, dist=opt(scan_args, "dist", 20, int),
+                min_size=opt(scan_args, "min_size", 4, int), intrabound=opt(scan_args, "intrabound", 300, int))
+    syn.scan([last + ".filtered", last + ".gpu.anchors"] + beds + list(scan_args))
+    assert read(last + ".gpu.anchors") == read(last + ".orc.anchors")
+    oracle.liftover(last, last + ".orc.anchors", qbed, sbed, out_path=last + ".orc.lifted",
+                    strip_names="--no_strip_names" not in lift_args, dist=opt(lift_args, "dist", 10, int))
+    syn.liftover([last, last + ".gpu.anchors"] + beds + ["--outfile=" + last + ".gpu.lifted"] + list(lift_args))
+    assert read(last + ".gpu.lifted") == read(last + ".orc.lifted")
+    return ost
+
+
+def test_pair_300k(tmp_path, mods):
+    st = _pipeline(tmp_path, mods, seed=21, Gq=8000, Gs=7500, n=300000, Kq=13, Ks=12)
+    assert st["after_tandem"] > 1000
+
+
+def test_pair_2m_lastlike_scores(tmp_path, mods):
+    _pipeline(tmp_path, mods, seed=22, Gq=30000, Gs=30000, n=2000000, Kq=12, Ks=12, score_style=1)
+
+
+def test_pair_polyploid_shape(tmp_path, mods):
+    # 3 sub-genomes vs a diploid (C3 shape), looser C-score, small clusters, wide liftover
+    _pipeline(tmp_path, mods, seed=23, Gq=9000, Gs=3000, n=250000, Kq=21, Ks=7, bf_args=["--cscore=0.5"],
+              scan_args=["--min_size=3", "--dist=10"], lift_args=["--dist=15"])
+
+
+def test_self_comparison(tmp_path, mods):
+    _pipeline(tmp_path, mods, seed=24, Gq=6000, Gs=6000, n=120000, Kq=5, Ks=5, self_mode=True,
+              bf_args=["--cscore=0.4"], scan_args=["--intrabound=150"])
+
+
+def test_tie_heavy_liftover(tmp_path, mods):
+    # many tiny adjacent blocks + wide rescue radius: cross-block ties decided by cKDTree order
+    _pipeline(tmp_path, mods, seed=25, Gq=3000, Gs=3000, n=150000, Kq=3, Ks=3, bf_args=["--cscore=0.2"],
+              scan_args=["--min_size=2", "--dist=2"], lift_args=["--dist=14"])
+
+
+def test_empty_and_comment_only(tmp_path, mods):
+    bf, syn = mods
+    from jcvi_b200 import synth
+    d = str(tmp_path)
+    qbed, sbed, last = synth.write_dataset(d, "A", "B", 1, 200, 200, 500, Kq=2, Ks=2)
+    for body in (b"", b"# only a comment\n", b"\n\n\n"):
+        with open(last, "wb") as fw:
+            fw.write(body)
+        bf.main([last])
+        assert read(last + ".filtered") == b""
+        with pytest.raises(ValueError, match="A total of 0 anchor was found"):
+            syn.scan([last + ".filtered", last + ".anchors"])
+        assert read(last + ".anchors") == b""
+
+
+def test_zero_division_and_unsupported(tmp_path, mods):
+    bf, _ = mods
+    from jcvi_b200 import synth
+    d = str(tmp_path)
+    qbed, sbed, last = synth.write_dataset(d, "A", "B", 2, 200, 200, 500, Kq=2, Ks=2)
+    with open(last, "w") as fw:
+        fw.write("Ag000001.1\tBg000002.1\t90.0\t10\t0\t0\t1\t10\t1\t10\t1e-5\t0\n")
+    with pytest.raises(ZeroDivisionError):                        # blastfilter.py:235
+        bf.main([last])
+    with open(last, "w") as fw:
+        fw.write("Ag000001.1\tBg000002.1\t90.0\t10\t0\t0\t1\t10\t1\t10\t1e-5\tinf\n")
+    with pytest.raises(NotImplementedError):
+        bf.main([last])
+
+
+def test_synteny_scan_points_api(mods):
+    """synteny_scan / batch_scan on plain tuples (synteny.py:402-452), checked against a direct
+    restatement of the reference loop with its Grouper."""
+    _, syn = mods
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        n = int(rng.integers(50, 3000))
+        span = int(rng.integers(60, 1500))
+        pts = set()
+        while len(pts) < n:
+            x = int(rng.integers(0, span)); y = x + int(rng.integers(-40, 41)) if rng.random() < 0.7 else int(rng.integers(0, span))
+            pts.add((x, max(y, 0)))
+        pts = [(x, y, float(rng.integers(1, 999))) for x, y in pts]
+        rng.shuffle(pts)
+        xd, yd, N = int(rng.integers(2, 25)), int(rng.integers(2, 25)), int(rng.integers(1, 6))
+        got = syn.synteny_scan(list(pts), xd, yd, N)
+        # reference algorithm
+        mapping = {}
+        P = sorted(pts)
+        for i in range(len(P)):
+            for j in range(i - 1, -1, -1):
+                if P[i][0] - P[j][0] > xd:
+                    break
+                if abs(P[i][1] - P[j][1]) > yd:
+                    continue
+                a, b = P[i], P[j]
+                sa = mapping.setdefault(a, [a])
+                sb = mapping.get(b)
+                if sb is None:
+                    sa.append(b); mapping[b] = sa
+                elif sb is not sa:
+                    if len(sb) > len(sa):
+                        sa, sb = sb, sa
+                    sa.extend(sb)
+                    for e in sb:
+                        mapping[e] = sa
+        seen, want = set(), []
+        for e, g in mapping.items():
+            if e not in seen:
+                seen.update(g)
+                if min(len(set(p[0] for p in g)), len(set(p[1] for p in g))) >= N:
+                    want.append(sorted(g))
+        assert got == want, trial
+
+
+def test_nearest_anchor_matches_scipy(mods):
+    _, syn = mods
+    spatial = pytest.importorskip("scipy.spatial")
+    rng = np.random.default_rng(9)
+    for n in (1, 5, 17, 200, 5000):
+        x = rng.integers(0, max(4, n // 2), size=n)
+        a = np.unique(np.stack([x, x + rng.integers(-3, 4, size=n)], 1), axis=0)
+        a = a[rng.permutation(len(a))]
+        q = rng.integers(a.min() - 12, a.max() + 13, size=(4000, 2))
+        for dist in (5, 10, 20):
+            d, i = spatial.cKDTree(a, leafsize=16).query(q, p=1, distance_upper_bound=dist)
+            want = [(tuple(p), tuple(a[k])) for p, dd, k in zip(q, d, i) if k != len(a) and dd != 0]
+            got = [(tuple(p), nn) for p, nn in syn.synteny_liftover(q, a, dist)]
+            assert got == want, (n, dist)

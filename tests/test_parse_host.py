@@ -1,0 +1,164 @@
+"""CPU checks of the tokenizer arithmetic (jcvi_b200/csrc/jx_parse.cuh, host build) against
+glibc -- the very functions the reference calls through cblast.pyx (sscanf "%f"/"%lf",
+sprintf "%.3g")."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "jcvi_b200", "csrc")
+SO = os.path.join(ROOT, "jcvi_b200", "libjx_hostprobe.so")
+libc = ctypes.CDLL("libc.so.6")
+libc.strtof.restype = ctypes.c_float
+libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+libc.strtod.restype = ctypes.c_double
+libc.strtod.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+
+
+@pytest.fixture(scope="module")
+def probe():
+    srcs = [os.path.join(CSRC, f) for f in ("jx_hostprobe.cpp", "jx_parse.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(SO) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
+                               srcs[0], "-o", SO])
+    L = ctypes.CDLL(SO)
+    L.probe_round3g_range.restype = ctypes.c_long
+    L.probe_hash.restype = ctypes.c_ulonglong
+    return L
+
+
+def f32bits(x):
+    return np.float32(x).view(np.uint32)
+
+
+def _decimals(rng, n):
+    out = []
+    for _ in range(n):
+        kind = rng.integers(0, 8)
+        if kind == 0:
+            out.append("%d" % rng.integers(0, 10**6))
+        elif kind == 1:
+            out.append("%.1f" % rng.uniform(0, 5000))
+        elif kind == 2:
+            out.append("%.2f" % rng.uniform(0, 100))
+        elif kind == 3:
+            out.append("%.3g" % rng.uniform(0.5, 2e6))
+        elif kind == 4:
+            out.append("%.*e" % (int(rng.integers(0, 10)), rng.uniform(1e-3, 1e7)))
+        elif kind == 5:
+            # near float32 midpoints: take a float, move half an ulp, print with few digits
+            f = np.float32(rng.uniform(1, 4096))
+            nxt = np.nextafter(f, np.float32(np.inf))
+            mid = (float(f) + float(nxt)) / 2
+            out.append("%.*f" % (int(rng.integers(4, 12)), mid))
+        elif kind == 6:
+            out.append("%.*f" % (int(rng.integers(0, 12)), rng.uniform(0, 3000)))
+        else:
+            out.append("%se%+d" % (rng.integers(1, 99999), rng.integers(-6, 6)))
+    return out
+
+
+def test_float32_parse_matches_strtof(probe):
+    rng = np.random.default_rng(1)
+    n_ok = n_hard = 0
+    for s in _decimals(rng, 200000) + ["0", "0.0", "-0", "54.0", "1.06e+03", "1e+05", "100", "+7.5", ".5", "5.",
+                                      "16777217", "33554433", "1e38", "3.5e38", "1234.5678", "0.1", "99999",
+                                      "54.000000000000000"]:
+        out = ctypes.c_float()
+        used = ctypes.c_int()
+        rc = probe.probe_f32(s.encode(), ctypes.byref(out), ctypes.byref(used))
+        assert rc in (0, 1), s
+        if rc == 0:
+            n_hard += 1
+            continue
+        n_ok += 1
+        assert used.value == len(s), s
+        want = libc.strtof(s.encode(), None)
+        assert f32bits(out.value) == f32bits(want), (s, out.value, want)
+    assert n_hard < 0.01 * n_ok      # the exact routes cover (nearly) everything that occurs
+
+
+def test_float_prefix_and_failures(probe):
+    out = ctypes.c_float(); used = ctypes.c_int()
+    assert probe.probe_f32(b"54.0abc", ctypes.byref(out), ctypes.byref(used)) == 1 and used.value == 4
+    assert probe.probe_f32(b"abc", ctypes.byref(out), ctypes.byref(used)) == -1
+    assert probe.probe_f32(b"-", ctypes.byref(out), ctypes.byref(used)) == -1
+    assert probe.probe_f32(b".", ctypes.byref(out), ctypes.byref(used)) == -1
+    assert probe.probe_f32(b"none", ctypes.byref(out), ctypes.byref(used)) == -1
+    for bad in (b"nan", b"inf", b"-Infinity", b"0x1p3", b"1e", b"1e+"):
+        assert probe.probe_f32(bad, ctypes.byref(out), ctypes.byref(used)) == 0, bad
+
+
+def test_evalue_threshold_matches_strtod(probe):
+    rng = np.random.default_rng(2)
+    cases = ["1e-10", "1.0e-10", "9.9e-11", "9.99999e-11", "1.00001e-10", "0", "0.0", "1e-400", "1e-50", "2.5e-180",
+             "1e400", "5", "0.001", "1e-9", "1e-11", "100e-12", "10e-11", "0.0000000001", "0.00000000009",
+             "1234567890123456789012e-32", "1000000000000e-22", "999999999999e-22"]
+    for _ in range(100000):
+        cases.append("%.*e" % (int(rng.integers(0, 6)), 10.0 ** rng.uniform(-200, 3)))
+    for _ in range(20000):
+        cases.append("%.*e" % (int(rng.integers(0, 8)), 1e-10 * rng.uniform(0.9, 1.1)))
+    hard = 0
+    for s in cases:
+        rc = probe.probe_lt1e10(s.encode())
+        if rc == -1:
+            hard += 1
+            continue
+        want = 1 if libc.strtod(s.encode(), None) < 1e-10 else 0
+        assert rc == want, s
+    assert hard == 0
+
+
+def test_round3g_matches_printf_strtof(probe):
+    bad = ctypes.c_uint(); unsup = ctypes.c_long()
+    # every 97th float32 between 1e-3 and 1e12, plus dense sweeps where scores live
+    lo, hi = int(f32bits(1e-3)), int(f32bits(1e12))
+    assert probe.probe_round3g_range(lo, hi, 97, ctypes.byref(bad), ctypes.byref(unsup)) == 0, hex(bad.value)
+    assert unsup.value == 0
+    lo, hi = int(f32bits(30.0)), int(f32bits(3000.0))
+    assert probe.probe_round3g_range(lo, hi, 1, ctypes.byref(bad), ctypes.byref(unsup)) == 0, hex(bad.value)
+    assert unsup.value == 0
+
+
+def test_strip_isoform_matches_oracle(probe):
+    import oracle
+    for s in ["Ag000123.1", "Ag000123.12", "evm.model.x.5", "a.b.c|x.1", "abc", "abc.", ".1", "a|b", "a.1|b.2",
+              "ev.1", "e.1", "x..2", "AT1G01010.1", "gene|", "|x"]:
+        b = probe.probe_strip(s.encode(), len(s))
+        assert s[:b] == oracle.gene_name(s), s
+
+
+def test_tokenize_line_matches_sscanf(probe):
+    rng = np.random.default_rng(3)
+    base = "Ag000791.3\tBg002441.1\t75.72\t1173\t284\t18\t1402\t2575\t1556\t2729\t6.5e-21\t161.5"
+    lines = [base, base.replace("\t", " "), "  " + base, base + "\textra\tcols", "\t".join(base.split("\t")[:8]),
+             "a b", "a", "", "   ", base.replace("1173", "x1173"), base + "abc", base.replace("6.5e-21", "1e-10"),
+             base.replace("161.5", "1.06e+03"), base.replace("75.72", "abc"), base.replace("\t284\t", "\t-284\t"),
+             base.replace("\t18\t", "\t+18\t"), base.replace("\t18\t", "\t1.8\t"), "a\tb\t1\t2"]
+    for ln in lines:
+        spans = (ctypes.c_int * 4)(); score = ctypes.c_float(); nconv = ctypes.c_int(); eflag = ctypes.c_int()
+        fl = probe.probe_line(ln.encode(), len(ln), spans, ctypes.byref(score), ctypes.byref(nconv), ctypes.byref(eflag))
+        q = ctypes.create_string_buffer(256); s = ctypes.create_string_buffer(256)
+        gs = ctypes.c_float(); ge = ctypes.c_double(); ints = (ctypes.c_int * 7)()
+        n = probe.probe_line_glibc((ln + "\n").encode(), q, s, ctypes.byref(gs), ctypes.byref(ge), ints)
+        n = max(n, 0)
+        assert fl == 0, ln
+        assert nconv.value == n, (ln, nconv.value, n)
+        assert ln[spans[0]:spans[1]] == q.value.decode()
+        assert ln[spans[2]:spans[3]] == s.value.decode()
+        assert f32bits(score.value) == f32bits(gs.value), ln
+        if n >= 11:
+            assert eflag.value == (1 if ge.value < 1e-10 else 0)
+        else:
+            assert eflag.value == 1      # evalue stays 0.0 in the Cython object
+
+
+def test_hash_is_stable(probe):
+    # host table build and device probe share this function; pin a few values against drift
+    h1 = probe.probe_hash(b"Ag000123", 8)
+    h2 = probe.probe_hash(b"Ag000124", 8)
+    assert h1 != h2 and probe.probe_hash(b"Ag000123x", 8) == h1
