@@ -112,17 +112,31 @@ JX_HD int scan_int(R& rd, int p, int e) {
 }
 
 // ---- decimal -> binary ---------------------------------------------------------------
+#define JX_POW10D {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11, \
+                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22}
+#define JX_POW10U {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, \
+                   1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, \
+                   100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull, \
+                   1000000000000000000ull, 10000000000000000000ull}
+static const double kPow10dHost[23] = JX_POW10D;
+static const uint64_t kPow10uHost[20] = JX_POW10U;
+#if defined(__CUDACC__)
+static __device__ const double kPow10dDev[23] = JX_POW10D;
+static __device__ const uint64_t kPow10uDev[20] = JX_POW10U;
+#endif
 JX_HD double pow10_exact(int k) {  // 10^k, exact in double for 0 <= k <= 22
-  const double t[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                        1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
-  return t[k];
+#if defined(__CUDA_ARCH__)
+  return kPow10dDev[k];
+#else
+  return kPow10dHost[k];
+#endif
 }
 JX_HD uint64_t pow10_u64(int k) {  // 0 <= k <= 19
-  const uint64_t t[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
-                          100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull,
-                          10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull,
-                          100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull};
-  return t[k];
+#if defined(__CUDA_ARCH__)
+  return kPow10uDev[k];
+#else
+  return kPow10uHost[k];
+#endif
 }
 
 JX_HD void mul64x64(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo) {

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
     unsigned long long excl = 0;
     if (tile > 0) {
       int64_t j = (int64_t)tile - 1;
+      uint32_t spins = 0;
       for (;;) {
         int64_t idx = j - lane;
         uint64_t d = idx >= 0 ? *((volatile uint64_t*)(a.desc + idx)) : FLAG_INC;
@@ -164,7 +165,10 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
         unsigned isinc = __ballot_sync(0xFFFFFFFFu, flag == 2);
         int first = isinc ? __ffs(isinc) - 1 : 32;
         unsigned upto = first < 31 ? ((2u << first) - 1u) : 0xFFFFFFFFu;
-        if (notready & upto) continue;   // spin until every needed predecessor has published
+        if (notready & upto) {             // spin until every needed predecessor has published
+          if (++spins > (1u << 24)) { if (lane == 0) atomicExch(a.stats + 10, 1ull); break; }   // never hang the GPU
+          continue;
+        }
         unsigned long long v = ((upto >> lane) & 1u) ? (d & VAL_MASK) : 0ull;
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -371,6 +375,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   }
   for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
   out.n_lines = (uint32_t)out.stats[0];
+  if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
   if (out.stats[5]) {
     ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +
                " (overflows cblast.pyx's char[128]; undefined behaviour in the reference)";
