@@ -52,8 +52,9 @@ int64_t jx_launch_count(jx_ctx* ctx);
 /* the context's CUDA stream as an integer handle (for event timing on the launching stream) */
 uint64_t jx_stream_handle(jx_ctx* ctx);
 /* accumulated device time (ms, CUDA events on the context's stream) of the K1/K2 tokenizer
- * launches since the last call with reset != 0, and the number of launches / bytes they read */
-int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes);
+ * launches since the last call with reset != 0, the number of launches, the text bytes they read
+ * and the lines (16-byte records) they wrote */
+int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes, int64_t* lines);
 
 /* ---- BED side tables -------------------------------------------------------------------
  * Replaces the name -> (rank, BedLine) dicts of Bed.order (formats/bed.py:196-198) and the

@@ -83,7 +83,7 @@ def lib():
         L.jx_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
         L.jx_ctx_destroy.argtypes = [ctypes.c_void_p]
         L.jx_ctx_destroy.restype = None
-        L.jx_tokenizer_timing.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_i64p, c_i64p]
+        L.jx_tokenizer_timing.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_i64p, c_i64p, c_i64p]
         L.jx_bed_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(JxBed)]
         L.jx_pair_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32]
         L.jx_blastfilter.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,

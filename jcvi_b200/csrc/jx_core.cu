@@ -65,7 +65,7 @@ const char* jx_last_error(jx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null c
 int64_t jx_launch_count(jx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t jx_stream_handle(jx_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 
-int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes) {
+int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes, int64_t* lines) {
   if (!ctx) return JX_EARG;
   cudaSetDevice(ctx->device);
   JX_CK(cudaStreamSynchronize(ctx->stream));
@@ -78,7 +78,8 @@ int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, i
   if (ms) *ms = ctx->tok_ms_acc;
   if (launches) *launches = ctx->tok_launches_acc;
   if (bytes) *bytes = ctx->tok_bytes;
-  if (reset) { ctx->tok_ms_acc = 0; ctx->tok_launches_acc = 0; ctx->tok_bytes = 0; }
+  if (lines) *lines = ctx->tok_lines;
+  if (reset) { ctx->tok_ms_acc = 0; ctx->tok_launches_acc = 0; ctx->tok_bytes = 0; ctx->tok_lines = 0; }
   return JX_OK;
 }
 

@@ -55,6 +55,7 @@ struct jx_ctx {
   // tokenizer timing (CUDA events on `stream`)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
   int64_t tok_bytes = 0;
+  int64_t tok_lines = 0;
   double tok_ms_acc = 0;
   int64_t tok_launches_acc = 0;
 };

@@ -375,6 +375,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   }
   for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
   out.n_lines = (uint32_t)out.stats[0];
+  ctx->tok_lines += (int64_t)out.stats[0];
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
   if (out.stats[5]) {
     ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +

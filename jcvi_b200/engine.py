@@ -233,9 +233,10 @@ class Engine(object):
         return int(self.lib.jx_launch_count(self.ctx))
 
     def tokenizer_timing(self, reset=True):
-        ms = ctypes.c_double(); n = ctypes.c_int64(); b = ctypes.c_int64()
-        self._check(self.lib.jx_tokenizer_timing(self.ctx, int(reset), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b)))
-        return ms.value, n.value, b.value
+        ms = ctypes.c_double(); n = ctypes.c_int64(); b = ctypes.c_int64(); ln = ctypes.c_int64()
+        self._check(self.lib.jx_tokenizer_timing(self.ctx, int(reset), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b),
+                                                 ctypes.byref(ln)))
+        return ms.value, n.value, b.value, ln.value
 
 
 _ENGINES = {}
