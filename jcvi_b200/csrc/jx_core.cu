@@ -51,7 +51,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int s = 0; s < 2; ++s) {
     SideDev& d = ctx->side[s];
-    cudaFree(d.table); cudaFree(d.names); cudaFree(d.name_off); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
+    cudaFree(d.table); cudaFree(d.blobw); cudaFree(d.name_meta); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
     cudaFree(d.chr_end); cudaFree(d.length); cudaFree(d.lexrank); cudaFree(d.name_id);
   }
   cudaFree(ctx->q_same_s);
@@ -113,8 +113,26 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
   d.tmask = cap - 1;
   int rc;
   if ((rc = upload(ctx, &d.table, tab.data(), tab.size()))) return rc;
-  if ((rc = upload(ctx, &d.names, bed->names, blob))) return rc;
-  if ((rc = upload(ctx, &d.name_off, bed->name_off, (size_t)G + 1))) return rc;
+  {
+    // word-aligned, zero-padded copy of the names so that the kernel verifies a probe with
+    // 32-bit compares against shared-memory words
+    std::vector<uint32_t> meta((size_t)G), words;
+    words.reserve(blob / 4 + (size_t)G + 4);
+    for (int64_t r = 0; r < G; ++r) {
+      uint32_t a = bed->name_off[r], b = bed->name_off[r + 1], len = b - a;
+      if (len >= 128u) { meta[(size_t)r] = 0; continue; }
+      if (words.size() >= (1u << 25)) { ctx->err = "BED names exceed 128 MiB"; return JX_EARG; }
+      meta[(size_t)r] = ((uint32_t)words.size() << 7) | len;
+      for (uint32_t i = 0; i < len; i += 4) {
+        uint32_t w = 0;
+        for (uint32_t k = 0; k < 4 && i + k < len; ++k) w |= (uint32_t)(unsigned char)bed->names[a + i + k] << (8 * k);
+        words.push_back(w);
+      }
+    }
+    words.push_back(0);
+    if ((rc = upload(ctx, &d.blobw, words.data(), words.size()))) return rc;
+    if ((rc = upload(ctx, &d.name_meta, meta.data(), meta.size()))) return rc;
+  }
   if ((rc = upload(ctx, &d.chr_lex, bed->chr_lex, (size_t)G))) return rc;
   if ((rc = upload(ctx, &d.chr_begin, bed->chr_begin, (size_t)G))) return rc;
   if ((rc = upload(ctx, &d.chr_end, bed->chr_end, (size_t)G))) return rc;

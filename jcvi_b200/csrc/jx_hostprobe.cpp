@@ -80,4 +80,22 @@ int probe_line_glibc(const char* s, char* q, char* sb, float* score, double* eva
                 ints + 3, ints + 4, ints + 5, ints + 6, evalue, score);
 }
 
+
+// fast path vs generic scanner on one line; buffer must be padded (16 readable bytes past n)
+namespace { struct WordRd { const unsigned char* p; inline uint32_t operator()(int i) const { uint32_t w; memcpy(&w, p + 4 * i, 4); return w; } }; }
+int probe_fast_line(const char* buf, int s, int n, int* spans, float* score, int* eflag, int* strip_ends,
+                    unsigned long long* hashes) {
+  WordRd wr{(const unsigned char*)buf};
+  jx::LineTok t;
+  if (!jx::fast_line(wr, s, n, t)) return 0;
+  spans[0] = t.qa; spans[1] = t.qb; spans[2] = t.sa; spans[3] = t.sb;
+  *score = t.score; *eflag = t.eflag;
+  jx::WordBytes<WordRd> B(wr);
+  strip_ends[0] = jx::fast_strip(B, t.qa, t.qb, t.qbar);
+  strip_ends[1] = jx::fast_strip(B, t.sa, t.sb, t.sbar);
+  hashes[0] = jx::fast_hash(B, t.qa, strip_ends[0]);
+  hashes[1] = jx::fast_hash(B, t.sa, strip_ends[1]);
+  return 1;
+}
+
 }  // extern "C"

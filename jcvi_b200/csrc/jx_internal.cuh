@@ -21,8 +21,8 @@
 //   w = (byte offset of the line inside its 8 KiB tile << 1) | (evalue < 1e-10)
 #define JX_NOREC 0xFFFFFFFFu
 
-constexpr int JX_TOK_THREADS = 256;
-constexpr int JX_SEG = 32;                               // bytes of the tile owned by one thread
+constexpr int JX_TOK_THREADS = 128;
+constexpr int JX_SEG = 64;                               // bytes of the tile owned by one thread
 constexpr int JX_TILE = JX_TOK_THREADS * JX_SEG;         // 8192
 constexpr int JX_OVER = 1024;                            // look-ahead staged in shared memory
 constexpr int JX_WIN = JX_TILE + JX_OVER;
@@ -32,8 +32,8 @@ struct SideDev {
   int32_t n_chr = 0;
   uint64_t* table = nullptr;   // open addressing: (tag32 << 32) | (rank + 1), 0 = empty
   uint32_t tmask = 0;
-  char* names = nullptr;
-  uint32_t* name_off = nullptr;
+  uint32_t* blobw = nullptr;     // accn bytes, each name padded with zeros to a 4-byte boundary
+  uint32_t* name_meta = nullptr; // per rank: (word offset into blobw << 7) | byte length (< 128)
   int32_t *chr_lex = nullptr, *chr_begin = nullptr, *chr_end = nullptr, *length = nullptr;
   uint32_t *lexrank = nullptr, *name_id = nullptr;
   std::vector<char> h_names;

@@ -325,28 +325,44 @@ JX_HD void strip_isoform(R& rd, int a, int& b) {
   b = end;
 }
 
-// 64-bit hash of the bytes [a,b): two independent 32-bit FNV-style lanes + avalanche.
-// Host (BED table build) and device (probe) must agree, hence JX_HD.
+// 64-bit hash of the bytes [a,b), defined on little-endian 32-bit words (last word zero padded)
+// so that the kernel can hash straight from shared-memory words.  Host (BED table build) and
+// device (probe) must agree, hence JX_HD.
 JX_HD uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
+JX_HD uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+struct NameHash {
+  uint32_t h1, h2;
+  JX_HD void init() { h1 = 0x2F0B4A87u; h2 = 0x9747B28Cu; }
+  JX_HD void word(uint32_t w) {
+    uint32_t k = w * 0xCC9E2D51u; k = rotl32(k, 15); k *= 0x1B873593u;
+    h1 ^= k; h1 = rotl32(h1, 13); h1 = h1 * 5u + 0xE6546B64u;
+    h2 = (h2 + w) * 0x9E3779B1u;
+  }
+  JX_HD uint64_t finish(uint32_t len) {
+    uint32_t a = fmix32(h1 ^ len), b = fmix32(h2 ^ (a + len));
+    return ((uint64_t)a << 32) | b;
+  }
+};
 template <class R>
 JX_HD uint64_t name_hash(R& rd, int a, int b) {
-  uint32_t h1 = 0x811C9DC5u, h2 = 0x9747B28Cu;
-  for (int p = a; p < b; ++p) {
-    uint32_t c = rd(p);
-    h1 = (h1 ^ c) * 16777619u;
-    h2 = (h2 + c) * 0x9E3779B1u; h2 = (h2 << 13) | (h2 >> 19);
+  NameHash h; h.init();
+  for (int p = a; p < b; p += 4) {
+    uint32_t w = rd(p);
+    if (p + 1 < b) w |= rd(p + 1) << 8;
+    if (p + 2 < b) w |= rd(p + 2) << 16;
+    if (p + 3 < b) w |= rd(p + 3) << 24;
+    h.word(w);
   }
-  h1 = fmix32(h1 ^ (uint32_t)(b - a));
-  h2 = fmix32(h2 + h1);
-  return ((uint64_t)h1 << 32) | h2;
+  return h.finish((uint32_t)(b - a));
 }
 
 // ---- one line --------------------------------------------------------------------------------
 struct LineTok {
   int qa, qb, sa, sb;   // raw name spans
+  int qbar, sbar;       // position of the first '|' in each name, -1 none, -2 not searched
   float score;
   int nconv;            // number of successful sscanf conversions (0..12)
   int eflag;            // evalue < 1e-10 : 1 / 0
@@ -359,6 +375,7 @@ struct LineTok {
 template <class R>
 JX_HD void tokenize_line(R& rd, int s, int e, LineTok& t) {
   t.qa = t.qb = t.sa = t.sb = s; t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false;
+  t.qbar = t.sbar = -2;
   int p = s;
   while (p < e && is_space(rd(p))) ++p;
   t.qa = p; while (p < e && !is_space(rd(p))) ++p; t.qb = p;
@@ -395,6 +412,144 @@ JX_HD void tokenize_line(R& rd, int s, int e, LineTok& t) {
   if (!d.ok) return;
   t.nconv = 12;
   if (!dec_to_f32(d, t.score)) t.hard = true;
+}
+
+
+// ---- fast path -------------------------------------------------------------------------------
+// Word-at-a-time (SWAR) parse of a REGULAR line: 12+ fields separated by single tabs, names made
+// of bytes > 0x20, pctid = digits with at most one '.', seven all-digit integers, evalue/score
+// plain decimals.  Returns false for anything else; the caller then runs tokenize_line(), the
+// generic sscanf-faithful scanner, so the fast path only has to be exact on what it accepts.
+// `W` yields aligned 32-bit little-endian words of the buffer: w(i) = bytes [4i, 4i+4).
+template <class W>
+struct WordBytes {                       // byte/unaligned views on top of a word reader
+  const W& w;
+  JX_HD explicit WordBytes(const W& w_) : w(w_) {}
+  JX_HD uint32_t operator()(int p) const { return (w(p >> 2) >> ((p & 3) * 8)) & 0xFFu; }
+  JX_HD uint32_t load32(int p) const {   // bytes [p, p+4)
+    const int i = p >> 2, sh = (p & 3) * 8;
+    uint32_t lo = w(i);
+    if (!sh) return lo;
+    return (lo >> sh) | (w(i + 1) << (32 - sh));
+  }
+};
+
+JX_HD uint32_t swar_le20(uint32_t x) {   // 0x80 in every byte that is <= 0x20 (and < 0x80)
+  uint32_t t = (x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu;      // bit7 set iff low7 >= 0x21
+  return ~(t | x) & 0x80808080u;
+}
+JX_HD uint32_t swar_eq(uint32_t x, uint32_t pat) {   // 0x80 in every byte equal to pat's byte
+  uint32_t y = x ^ pat;
+  uint32_t t = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  return ~(t | y) & 0x80808080u;
+}
+JX_HD uint32_t swar_nondigit(uint32_t x) {           // 0x80 in every byte that is not '0'..'9'
+  uint32_t a = x & 0x7F7F7F7Fu;
+  uint32_t ge0 = a + 0x50505050u;                    // bit7 iff low7 >= 0x30
+  uint32_t gt9 = a + 0x46464646u;                    // bit7 iff low7 >= 0x3A
+  return ~(ge0 & ~gt9 & ~x) & 0x80808080u;
+}
+JX_HD int first_flag(uint32_t f) {                   // byte index (0..3) of the lowest 0x80 flag
+#if defined(__CUDA_ARCH__)
+  return (__ffs((int)f) - 1) >> 3;
+#else
+  return (__builtin_ctz(f)) >> 3;
+#endif
+}
+
+// end of the name starting at p: first byte <= 0x20 must be a tab.  Returns the tab position or
+// -1 (irregular / beyond limit).  *bar receives the position of the first '|' (or -1).
+template <class W>
+JX_HD int fast_name_end(const WordBytes<W>& B, int p, int limit, int* bar) {
+  *bar = -1;
+  for (int q = p; q < limit; q += 4) {
+    const uint32_t x = B.load32(q);
+    if (*bar < 0) { uint32_t f = swar_eq(x, 0x7C7C7C7Cu); if (f) *bar = q + first_flag(f); }
+    const uint32_t lo = swar_le20(x);
+    if (lo) {
+      const int k = first_flag(lo), t = q + k;
+      if (((x >> (8 * k)) & 0xFFu) != '\t' || t >= limit) return -1;
+      if (*bar >= t) *bar = -1;
+      return t;
+    }
+  }
+  return -1;
+}
+
+template <class W>
+JX_HD bool fast_line(const W& wr, int s, int e, LineTok& t) {
+  const WordBytes<W> B(wr);
+  t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false;
+  if (e - s < 23) return false;
+  const int t1 = fast_name_end(B, s, e, &t.qbar);
+  if (t1 <= s || t1 - s >= 128) return false;
+  t.qa = s; t.qb = t1;
+  const int t2 = fast_name_end(B, t1 + 1, e, &t.sbar);
+  if (t2 <= t1 + 1 || t2 - t1 - 1 >= 128) return false;
+  t.sa = t1 + 1; t.sb = t2;
+  // fields 3..10: non-digit bytes must be exactly: at most one '.' inside field 3, then 8 tabs,
+  // no empty field
+  int p = t2 + 1;               // start of the current field
+  int ntab = 0, ndot = 0, prev = t2, t10 = -1;
+  {
+    int q = p & ~3;
+    uint32_t nd = swar_nondigit(wr(q >> 2));
+    nd &= 0xFFFFFFFFu << ((p & 3) * 8);     // ignore bytes before p
+    for (;;) {
+      while (!nd) { q += 4; if (q >= e) return false; nd = swar_nondigit(wr(q >> 2)); }
+      const int pos = q + first_flag(nd);
+      nd &= nd - 1;
+      if (pos >= e) return false;
+      const uint32_t c = B(pos);
+      if (c == '\t') {
+        const int ndig = pos - prev - 1 - (ntab == 0 ? ndot : 0);
+        if (ndig < 1) return false;          // empty field (or a lone '.')
+        prev = pos;
+        if (++ntab == 8) { t10 = pos; break; }
+      } else if (c == '.' && ntab == 0 && ndot == 0) {
+        ndot = 1;
+      } else {
+        return false;
+      }
+    }
+  }
+  // field 11 (evalue) and field 12 (score): short decimals, scanned bytewise
+  Dec d;
+  p = t10 + 1;
+  int p2 = scan_decimal(B, p, e, d);
+  if (d.special || !d.ok || p2 >= e || B(p2) != '\t') return false;
+  const int lt = dec_lt_1e10(d);
+  if (lt < 0) return false;
+  t.eflag = lt;
+  p = p2 + 1;
+  p2 = scan_decimal(B, p, e, d);
+  if (d.special || !d.ok) return false;
+  // whatever follows the score's numeric prefix is ignored by sscanf (last conversion)
+  if (!dec_to_f32(d, t.score)) return false;
+  t.nconv = 12;
+  return true;
+}
+
+// gene_name with the first '|' already located (bar = its position or -1)
+template <class W>
+JX_HD int fast_strip(const WordBytes<W>& B, int a, int b, int bar) {
+  const bool ev = (b - a >= 2) && B(a) == 'e' && B(a + 1) == 'v';
+  int end = bar >= 0 ? bar : b;
+  // rsplit('.', 1) leaves a one-character suffix iff the last '.' sits at end-2
+  if (!ev && end - a >= 2 && B(end - 2) == '.' && B(end - 1) != '.') end -= 2;
+  return end;
+}
+
+template <class W>
+JX_HD uint64_t fast_hash(const WordBytes<W>& B, int a, int b) {
+  NameHash h; h.init();
+  for (int p = a; p < b; p += 4) {
+    uint32_t w = B.load32(p);
+    const int rem = b - p;
+    if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+    h.word(w);
+  }
+  return h.finish((uint32_t)(b - a));
 }
 
 }  // namespace jx

@@ -26,8 +26,8 @@ struct TokArgs {
   uint32_t* ticket;          // global tile ticket (monotone across launches)
   uint4* recs;
   uint32_t rec_cap;
-  const uint64_t* qtab; uint32_t qmask; const char* qnames; const uint32_t* qoff;
-  const uint64_t* stab; uint32_t smask; const char* snames; const uint32_t* soff;
+  const uint64_t* qtab; uint32_t qmask; const uint32_t* qmeta; const uint32_t* qblob;
+  const uint64_t* stab; uint32_t smask; const uint32_t* smeta; const uint32_t* sblob;
   const int32_t* qchr; const int32_t* schr;   // chr_lex per gene (near-diagonal rule)
   const uint32_t* qnid; const uint32_t* snid;
   uint32_t* best;
@@ -40,7 +40,9 @@ struct TokArgs {
 #define FLAG_INC (2ull << 62)
 #define VAL_MASK ((1ull << 62) - 1)
 
-struct WinReader {
+constexpr int LCAP = 1024;     // line starts of a tile kept in shared memory (more -> search path)
+
+struct WinReader {             // byte view: shared-memory window, global memory beyond it
   const uint8_t* sm;
   const uint8_t* g;
   int64_t base, n;
@@ -50,23 +52,29 @@ struct WinReader {
     return gp < n ? g[gp] : (uint32_t)'\n';
   }
 };
+struct SmemWords {             // aligned 32-bit words of the window
+  const uint32_t* w;
+  __device__ __forceinline__ uint32_t operator()(int i) const { return w[i]; }
+};
 
+// generic (byte reader) probe: assembles words to match the word-based hash / blob layout
 template <class R>
-__device__ __forceinline__ int table_lookup(R& rd, int a, int b, const uint64_t* tab, uint32_t mask,
-                                            const char* names, const uint32_t* off) {
-  if (b <= a) return -1;
-  uint64_t h = jx::name_hash(rd, a, b);
-  uint32_t tag = (uint32_t)(h >> 32), idx = (uint32_t)h & mask;
+__device__ int table_lookup_bytes(R& rd, int a, int b, const uint64_t* tab, uint32_t mask, const uint32_t* meta,
+                                  const uint32_t* blob) {
+  if (b <= a || b - a >= 128) return -1;
+  const uint64_t h = jx::name_hash(rd, a, b);
+  const uint32_t tag = (uint32_t)(h >> 32);
+  uint32_t idx = (uint32_t)h & mask;
   for (;;) {
-    uint64_t slot = __ldg(tab + idx);
+    const uint64_t slot = __ldg(tab + idx);
     if (!slot) return -1;
     if ((uint32_t)(slot >> 32) == tag) {
-      uint32_t r = (uint32_t)slot - 1u;
-      uint32_t o = __ldg(off + r), len = __ldg(off + r + 1) - o;
+      const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r), len = m & 127u;
       if (len == (uint32_t)(b - a)) {
+        const uint32_t* bw = blob + (m >> 7);
         bool eq = true;
-        for (uint32_t i = 0; i < len; ++i)
-          if ((uint32_t)(uint8_t)__ldg(names + o + i) != rd(a + (int)i)) { eq = false; break; }
+        for (uint32_t i = 0; i < len && eq; ++i)
+          eq = ((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) == rd(a + (int)i);
         if (eq) return (int)r;
       }
     }
@@ -74,19 +82,55 @@ __device__ __forceinline__ int table_lookup(R& rd, int a, int b, const uint64_t*
   }
 }
 
-__device__ __forceinline__ uint32_t term_bits(uint32_t w) {   // 4 bytes -> 4 terminator bits
-  uint32_t m = (__vcmpeq4(w, 0x0A0A0A0Au) | __vcmpeq4(w, 0x0D0D0D0Du)) & 0x01010101u;
-  return ((m * 0x00204081u) >> 21) & 0xFu;
+// fast probe: hash and verify with 32-bit words straight from shared memory
+__device__ __forceinline__ int table_lookup_words(const jx::WordBytes<SmemWords>& B, int a, int b, const uint64_t* tab,
+                                                  uint32_t mask, const uint32_t* meta, const uint32_t* blob) {
+  if (b <= a) return -1;
+  const uint64_t h = jx::fast_hash(B, a, b);
+  const uint32_t tag = (uint32_t)(h >> 32), len = (uint32_t)(b - a);
+  uint32_t idx = (uint32_t)h & mask;
+  for (;;) {
+    const uint64_t slot = __ldg(tab + idx);
+    if (!slot) return -1;
+    if ((uint32_t)(slot >> 32) == tag) {
+      const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r);
+      if ((m & 127u) == len) {
+        const uint32_t* bw = blob + (m >> 7);
+        bool eq = true;
+        for (uint32_t i = 0; i < len; i += 4) {
+          uint32_t w = B.load32(a + (int)i);
+          const uint32_t rem = len - i;
+          if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+          if (w != __ldg(bw + (i >> 2))) { eq = false; break; }
+        }
+        if (eq) return (int)r;
+      }
+    }
+    idx = (idx + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ uint32_t term_nibble(uint32_t x) {   // 4 bytes -> 4 terminator bits
+  const uint32_t f = jx::swar_eq(x, 0x0A0A0A0Au) | jx::swar_eq(x, 0x0D0D0D0Du);
+  return (((f >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+__device__ __forceinline__ uint32_t term_mask32(const uint32_t* w) {   // 8 words -> 32 bits
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m |= term_nibble(w[k]) << (4 * k);
+  return m;
 }
 
 __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
-  __shared__ __align__(16) uint8_t sm[JX_WIN];
+  __shared__ __align__(16) uint32_t smw[JX_WIN / 4 + 8];
   __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
-  __shared__ uint32_t s_start[JX_TOK_THREADS];  // line-start bit per byte of the tile
-  __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per segment
+  __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per 64-byte segment
+  __shared__ unsigned long long s_start[JX_TOK_THREADS];
+  __shared__ uint16_t s_lpos[LCAP];             // start offset of every line of the tile
   __shared__ uint32_t s_warp[JX_TOK_THREADS / 32];
   __shared__ uint32_t s_tile, s_nlines;
   __shared__ unsigned long long s_base;
+  const uint8_t* sm = reinterpret_cast<const uint8_t*>(smw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
@@ -95,8 +139,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
   const int64_t base = (int64_t)tile * JX_TILE;
 
   // ---- stage the window: coalesced 16-byte loads, '\n' beyond the end of the text ------------
-  for (int v = tid; v < JX_WIN / 16; v += JX_TOK_THREADS) {
-    int64_t gp = base + (int64_t)v * 16;
+  for (int v = tid; v < JX_WIN / 16 + 2; v += JX_TOK_THREADS) {
+    const int64_t gp = base + (int64_t)v * 16;
     uint4 val;
     if (gp + 16 <= a.n) {
       val = __ldcs(reinterpret_cast<const uint4*>(a.text + gp));
@@ -106,46 +150,46 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
       for (int i = 0; i < 16; ++i) tmp[i] = (gp + i < a.n) ? a.text[gp + i] : (uint8_t)'\n';
       val = *reinterpret_cast<uint4*>(tmp);
     }
-    reinterpret_cast<uint4*>(sm)[v] = val;
+    reinterpret_cast<uint4*>(smw)[v] = val;
   }
   __syncthreads();
 
-  // ---- terminator masks for the whole window ---------------------------------------------------
-  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) {
-    const uint4* p = reinterpret_cast<const uint4*>(sm + seg * 32);
-    uint4 x = p[0], y = p[1];
-    uint32_t m = term_bits(x.x) | (term_bits(x.y) << 4) | (term_bits(x.z) << 8) | (term_bits(x.w) << 12) |
-                 (term_bits(y.x) << 16) | (term_bits(y.y) << 20) | (term_bits(y.z) << 24) | (term_bits(y.w) << 28);
-    s_term[seg] = m;
-  }
+  // ---- terminator masks (SWAR, 32 bytes per mask word) ---------------------------------------------
+  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) s_term[seg] = term_mask32(smw + seg * 8);
   __syncthreads();
 
-  // ---- line starts inside the tile + block scan ---------------------------------------------------
-  uint32_t prevbit;
-  if (tid == 0) prevbit = (base == 0) ? 1u : (uint32_t)jx::is_term(a.text[base - 1]);
-  else prevbit = s_term[tid - 1] >> 31;
-  uint32_t starts = (s_term[tid] << 1) | prevbit;
-  {  // only positions that exist in the text can start a line
-    int64_t remain = a.n - (base + (int64_t)tid * JX_SEG);
+  // ---- line starts inside the tile (64 bytes per thread) + block scan ----------------------------------
+  unsigned long long starts;
+  {
+    const unsigned long long term = (unsigned long long)s_term[2 * tid] | ((unsigned long long)s_term[2 * tid + 1] << 32);
+    uint32_t prevbit;
+    if (tid == 0) prevbit = (base == 0) ? 1u : (uint32_t)jx::is_term(a.text[base - 1]);
+    else prevbit = s_term[2 * tid - 1] >> 31;
+    starts = (term << 1) | prevbit;
+    const int64_t remain = a.n - (base + (int64_t)tid * JX_SEG);   // only positions that exist can start a line
     if (remain <= 0) starts = 0;
-    else if (remain < 32) starts &= (1u << remain) - 1u;
+    else if (remain < 64) starts &= (1ull << remain) - 1ull;
   }
-  s_start[tid] = starts;
-  uint32_t cnt = __popc(starts), inc = cnt;
+  const uint32_t cnt = __popcll(starts);
+  uint32_t inc = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < JX_TOK_THREADS / 32 ? s_warp[lane] : 0, wi = w;
+  uint32_t wbase = 0, nlines = 0;
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += t; }
-    if (lane < JX_TOK_THREADS / 32) s_warp[lane] = wi - w;
-    if (lane == JX_TOK_THREADS / 32 - 1) s_nlines = wi;
+  for (int w = 0; w < JX_TOK_THREADS / 32; ++w) { const uint32_t v = s_warp[w]; if (w < warp) wbase += v; nlines += v; }
+  const uint32_t mypref = wbase + inc - cnt;
+  s_pref[tid] = mypref;
+  s_start[tid] = starts;
+  {
+    unsigned long long m = starts;
+    uint32_t o = mypref;
+    while (m && o < LCAP) {
+      s_lpos[o++] = (uint16_t)(tid * JX_SEG + __ffsll((long long)m) - 1);
+      m &= m - 1;
+    }
   }
-  __syncthreads();
-  s_pref[tid] = s_warp[warp] + inc - cnt;
-  const uint32_t nlines = s_nlines;
 
   // ---- decoupled look-back: global ordinal of the tile's first line ---------------------------------
   if (warp == 0) {
@@ -185,21 +229,25 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
 
   // ---- parse: one line per thread -----------------------------------------------------------------
   WinReader rd{sm, a.text, base, a.n};
-  unsigned long long c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
+  const SmemWords wr{smw};
+  const jx::WordBytes<SmemWords> B(wr);
+  uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
   unsigned long long first_bad = 0;
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
     const uint32_t k = k0 + tid;
     if (k >= nlines) break;
-    // segment holding line k: last t with s_pref[t] <= k
-    int lo = 0, hi = JX_TOK_THREADS - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= k) lo = mid; else hi = mid - 1; }
-    // among equal prefixes pick the segment that actually contains the line
-    const int seg = lo;
-    const int bit = __fns(s_start[seg], 0, (int)(k - s_pref[seg]) + 1);
-    const int s = seg * JX_SEG + bit;
-    // end of line: next terminator at or after s
-    int e;
-    {
+    int s;
+    if (k < LCAP) s = s_lpos[k];
+    else {   // overfull tile (average line < 8 bytes): locate the line through the prefix array
+      int lo = 0, hi = JX_TOK_THREADS - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= k) lo = mid; else hi = mid - 1; }
+      unsigned long long m = s_start[lo];
+      for (uint32_t r = k - s_pref[lo]; r; --r) m &= m - 1;
+      s = lo * JX_SEG + __ffsll((long long)m) - 1;
+    }
+    int e;   // end of line: next terminator at or after s
+    if (k + 1 < nlines && k + 1 < LCAP) e = (int)s_lpos[k + 1] - 1;
+    else {
       int w = s >> 5;
       uint32_t m = s_term[w] & (0xFFFFFFFFu << (s & 31));
       while (!m && ++w < JX_WIN / 32) m = s_term[w];
@@ -209,12 +257,12 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
     uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
     if (s < e && sm[s] == '#') {
       ++c_comment;
-    } else {
+    } else if (s < e) {
       jx::LineTok t;
-      jx::tokenize_line(rd, s, e, t);
-      bool bad = false;
+      const bool fast = (e + 8 <= JX_WIN) && jx::fast_line(wr, s, e, t);
+      if (!fast) jx::tokenize_line(rd, s, e, t);
+      bool bad = false, selfhit = false;
       int qi = -1, si = -1;
-      bool selfhit = false;
       if (t.nconv >= 2) {
         if (t.longname) { bad = true; ++c_long; }
         int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
@@ -223,9 +271,15 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
           for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
         }
         if (!selfhit && !bad) {
-          if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
-          qi = table_lookup(rd, qa, qb, a.qtab, a.qmask, a.qnames, a.qoff);
-          if (qi >= 0) si = table_lookup(rd, sa, sb, a.stab, a.smask, a.snames, a.soff);
+          if (fast) {
+            if (a.strip) { qb = jx::fast_strip(B, qa, qb, t.qbar); sb = jx::fast_strip(B, sa, sb, t.sbar); }
+            qi = table_lookup_words(B, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
+            if (qi >= 0) si = table_lookup_words(B, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
+          } else {
+            if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
+            qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
+            if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
+          }
         }
       }
       if (selfhit) ++c_self;
@@ -254,28 +308,30 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
           }
         }
       }
+    } else {
+      ++c_unmapped;   // empty line: a BlastLine with empty names, never in the BED
     }
     const unsigned long long ord = line_base + k;
     if (ord < a.rec_cap) a.recs[ord] = rec;
   }
 
   // ---- counters ---------------------------------------------------------------------------------------
-  unsigned long long vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
+  uint32_t vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    unsigned long long v = vals[i];
+    uint32_t v = vals[i];
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     vals[i] = v;
   }
   if (lane == 0) {
-    if (vals[0]) atomicAdd(a.stats + 1, vals[0]);
-    if (vals[1]) atomicAdd(a.stats + 2, vals[1]);
-    if (vals[2]) atomicAdd(a.stats + 3, vals[2]);
-    if (vals[3]) atomicAdd(a.stats + 4, vals[3]);
-    if (vals[4]) atomicAdd(a.stats + 5, vals[4]);
-    if (vals[5]) atomicAdd(a.stats + 8, vals[5]);
-    if (vals[6]) atomicAdd(a.stats + 9, vals[6]);
+    if (vals[0]) atomicAdd(a.stats + 1, (unsigned long long)vals[0]);
+    if (vals[1]) atomicAdd(a.stats + 2, (unsigned long long)vals[1]);
+    if (vals[2]) atomicAdd(a.stats + 3, (unsigned long long)vals[2]);
+    if (vals[3]) atomicAdd(a.stats + 4, (unsigned long long)vals[3]);
+    if (vals[4]) atomicAdd(a.stats + 5, (unsigned long long)vals[4]);
+    if (vals[5]) atomicAdd(a.stats + 8, (unsigned long long)vals[5]);
+    if (vals[6]) atomicAdd(a.stats + 9, (unsigned long long)vals[6]);
   }
   if (first_bad) atomicMin(a.stats + 7, first_bad);
   if (tid == 0) {
@@ -345,8 +401,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     }
     TokArgs a;
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.recs = recs; a.rec_cap = (uint32_t)cap64;
-    a.qtab = Q.table; a.qmask = Q.tmask; a.qnames = Q.names; a.qoff = Q.name_off;
-    a.stab = S.table; a.smask = S.tmask; a.snames = S.names; a.soff = S.name_off;
+    a.qtab = Q.table; a.qmask = Q.tmask; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
+    a.stab = S.table; a.smask = S.tmask; a.smeta = S.name_meta; a.sblob = S.blobw;
     a.qchr = Q.chr_lex; a.schr = S.chr_lex; a.qnid = Q.name_id; a.snid = S.name_id;
     a.best = mode.best; a.excl = mode.excl; a.n_excl = mode.n_excl;
     a.strip = mode.strip; a.is_self = ctx->is_self ? 1 : 0; a.neardiag = mode.neardiag;

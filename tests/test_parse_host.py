@@ -162,3 +162,60 @@ def test_hash_is_stable(probe):
     h1 = probe.probe_hash(b"Ag000123", 8)
     h2 = probe.probe_hash(b"Ag000124", 8)
     assert h1 != h2 and probe.probe_hash(b"Ag000123x", 8) == h1
+
+
+def test_fast_line_agrees_with_generic_scanner(probe):
+    """The SWAR fast path (jx::fast_line) must either refuse a line or produce exactly what the
+    generic sscanf-faithful scanner produces (spans, score bits, evalue flag, stripped name,
+    hash of the stripped name)."""
+    rng = np.random.default_rng(4)
+    base = "Ag000791.3\tBg002441.1\t75.72\t1173\t284\t18\t1402\t2575\t1556\t2729\t6.5e-21\t161.5"
+    lines = [base]
+    names = ["Ag1.1", "evm.model.000021F_np12.565", "mrna.AA565170.t1", "AT1G01010.1|x", "a|b.1", "g.12", "x", "ev.1",
+             "Os09g11510", "a.b.c", "averyveryveryverylongnamethatkeepsgoing_0123456789.2", "n..1", "p.1.", ".1"]
+    nums = ["161.5", "54.0", "1386", "1.06e+03", "1e+05", "0", "99999", "3.5", ".5", "5.", "12345678.125", "1e-3"]
+    evs = ["6.5e-21", "0.0", "0", "1e-10", "9.9e-11", "2.5e-180", "0.001", "3", "1e-400", "1.0e-10", "5e-11"]
+    pcts = ["75.72", "100", "100.00", "99.", ".5", "7"]
+    for _ in range(4000):
+        f = [names[rng.integers(len(names))], names[rng.integers(len(names))], pcts[rng.integers(len(pcts))]]
+        f += [str(rng.integers(0, 10 ** int(rng.integers(1, 7)))) for _ in range(7)]
+        f += [evs[rng.integers(len(evs))], nums[rng.integers(len(nums))]]
+        ln = "\t".join(f)
+        r = rng.integers(0, 14)
+        if r == 0: ln = ln.replace("\t", " ", 1)
+        elif r == 1: ln = ln + "\textra"
+        elif r == 2: ln = "\t".join(f[:9])
+        elif r == 3: ln = ln.replace("\t", "\t\t", 1)
+        elif r == 4: f[5] = "-" + f[5]; ln = "\t".join(f)
+        elif r == 5: f[4] = "1.5"; ln = "\t".join(f)
+        elif r == 6: ln = ln + "abc"
+        elif r == 7: f[0] = "a b"; ln = "\t".join(f)
+        elif r == 8: f[2] = "1.2.3"; ln = "\t".join(f)
+        elif r == 9: f[10] = "1e"; ln = "\t".join(f)
+        elif r == 10: f[11] = "nan"; ln = "\t".join(f)
+        elif r == 11: ln = " " + ln
+        lines.append(ln)
+    nfast = 0
+    for ln in lines:
+        for pad in (0, 1, 2, 3):          # every alignment of the line start
+            raw = (b"#" * pad) + ln.encode()
+            buf = raw + b"\n" + b"\0" * 24
+            s, n = pad, len(raw)
+            spans = (ctypes.c_int * 4)(); score = ctypes.c_float(); eflag = ctypes.c_int()
+            ends = (ctypes.c_int * 2)(); hs = (ctypes.c_ulonglong * 2)()
+            ok = probe.probe_fast_line(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
+            gsp = (ctypes.c_int * 4)(); gsc = ctypes.c_float(); gnc = ctypes.c_int(); gef = ctypes.c_int()
+            fl = probe.probe_line(ln.encode(), len(ln), gsp, ctypes.byref(gsc), ctypes.byref(gnc), ctypes.byref(gef))
+            if not ok:
+                continue
+            nfast += 1
+            assert fl == 0 and gnc.value == 12, ln
+            assert [x - pad for x in spans] == list(gsp), ln
+            assert f32bits(score.value) == f32bits(gsc.value), ln
+            assert eflag.value == gef.value, ln
+            for k in (0, 1):
+                name = ln[gsp[2 * k]:gsp[2 * k + 1]]
+                b = probe.probe_strip(name.encode(), len(name))
+                assert ends[k] - pad - gsp[2 * k] == b, (ln, k)
+                assert hs[k] == probe.probe_hash(name[:b].encode(), b), (ln, k)
+    assert nfast > 0.2 * 4 * len(lines)
