@@ -98,4 +98,21 @@ int probe_fast_line(const char* buf, int s, int n, int* spans, float* score, int
   return 1;
 }
 
+
+int probe_fast_line3(const char* buf, int s, int limit, int* spans, float* score, int* eflag, int* strip_ends,
+                     unsigned long long* hashes) {
+  WordRd wr{(const unsigned char*)buf};
+  jx::LineTok t;
+  unsigned short sep[12];
+  if (!jx::fast_line3(wr, s, limit, sep, 1, t)) return 0;
+  spans[0] = t.qa; spans[1] = t.qb; spans[2] = t.sa; spans[3] = t.sb;
+  *score = t.score; *eflag = t.eflag;
+  jx::WordBytes<WordRd> B(wr);
+  uint64_t h0, h1;
+  strip_ends[0] = jx::fast_strip_hash(B, t.qa, t.qb, true, h0);
+  strip_ends[1] = jx::fast_strip_hash(B, t.sa, t.sb, true, h1);
+  hashes[0] = h0; hashes[1] = h1;
+  return 1;
+}
+
 }  // extern "C"

@@ -552,4 +552,215 @@ JX_HD uint64_t fast_hash(const WordBytes<W>& B, int a, int b) {
   return h.finish((uint32_t)(b - a));
 }
 
+
+// ---- fast path, version 3 ---------------------------------------------------------------------
+// One pass over the line's words finds the bytes <= 0x20 (separators): a regular line has exactly
+// 11 tabs followed by the terminator (or a 12th tab / CR LF).  Everything else is validated with
+// population counts of SWAR flags, so the instruction stream is nearly identical for all lanes.
+// `sep` is a 12-entry scratch array addressed as sep[j * stride].
+
+JX_HD uint32_t range_mask(int q, int a, int b) {    // 0x80 flags of the bytes of word [q,q+4) inside [a,b)
+  int lo = a - q; if (lo < 0) lo = 0;
+  int hi = b - q; if (hi > 4) hi = 4;
+  if (hi <= lo) return 0u;
+  uint32_t m = 0xFFFFFFFFu << (8 * lo);
+  if (hi < 4) m &= 0xFFFFFFFFu >> (8 * (4 - hi));
+  return m & 0x80808080u;
+}
+JX_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+// number of flagged bytes in [a,b), b > a: edge words masked once, interior words unmasked
+template <class W, class F>
+JX_HD int count_flags(const W& wr, int a, int b, F fl) {
+  const int q0 = a >> 2, q1 = (b - 1) >> 2;
+  const uint32_t first = 0x80808080u & (0xFFFFFFFFu << (8 * (a & 3)));
+  const uint32_t last = 0x80808080u & (0xFFFFFFFFu >> (8 * (3 - ((b - 1) & 3))));
+  if (q0 == q1) return popc32(fl(wr(q0)) & first & last);
+  int c = popc32(fl(wr(q0)) & first) + popc32(fl(wr(q1)) & last);
+  for (int q = q0 + 1; q < q1; ++q) c += popc32(fl(wr(q)));
+  return c;
+}
+struct FlNonDigit { JX_HD uint32_t operator()(uint32_t x) const { return swar_nondigit(x); } };
+struct FlDot { JX_HD uint32_t operator()(uint32_t x) const { return swar_eq(x, 0x2E2E2E2Eu); } };
+template <class W>
+JX_HD int count_nondigit(const W& wr, int a, int b) { return b > a ? count_flags(wr, a, b, FlNonDigit()) : 0; }
+template <class W>
+JX_HD int count_eq(const W& wr, int a, int b, uint32_t) { return b > a ? count_flags(wr, a, b, FlDot()) : 0; }
+JX_HD float pow10f_exact(int k) {   // 10^k exact in float for 0 <= k <= 10
+  const uint32_t bits = k == 0 ? 0x3F800000u : k == 1 ? 0x41200000u : k == 2 ? 0x42C80000u : k == 3 ? 0x447A0000u
+                      : k == 4 ? 0x461C4000u : k == 5 ? 0x47C35000u : k == 6 ? 0x49742400u : k == 7 ? 0x4B189680u
+                      : k == 8 ? 0x4CBEBC20u : k == 9 ? 0x4E6E6B28u : 0x501502F9u;
+  return bits_to_float(bits);
+}
+
+// evalue field [a,b): decides (value < 1e-10) for the shapes BLAST/LAST print; false = not handled.
+// One uniform loop over the characters with a 4-state machine (lanes stay converged).
+template <class BR>
+JX_HD bool fast_evalue(const BR& B, int a, int b, int& flag) {
+  if (b - a > 14 || b <= a) return false;
+  const uint32_t first = B(a);
+  if (!is_digit(first)) return false;
+  int st = 0, nint = 0, nfrac = 0, X = 0, nexp = 0;
+  bool nz = false, neg = false, ok = true;
+  for (int p = a; p < b; ++p) {
+    const uint32_t c = B(p);
+    const uint32_t d = c - '0';
+    const bool isd = d <= 9u, ise = (c | 0x20u) == 'e';
+    if (st == 0) {
+      if (isd) { ++nint; nz |= (d != 0); } else if (c == '.') st = 1; else if (ise) st = 2; else ok = false;
+    } else if (st == 1) {
+      if (isd) { ++nfrac; nz |= (d != 0); } else if (ise) st = 2; else ok = false;
+    } else if (st == 2) {
+      if (isd) { X = (int)d; nexp = 1; } else if (c == '-' || c == '+') neg = (c == '-'); else ok = false;
+      st = 3;
+    } else {
+      if (isd) { X = X * 10 + (int)d; ++nexp; } else ok = false;
+    }
+  }
+  const bool has_exp = st >= 2;
+  if (!ok || (has_exp && (nexp == 0 || nexp > 3))) return false;
+  if (neg) X = -X;
+  if (!nz) { flag = 1; return true; }                    // 0, 0.0, 0e-5 ...
+  if (nint + nfrac > 8) return false;
+  if (first == '0') {                                    // "0.ddd": >= 10^-nfrac >= 1e-8
+    if (nint == 1 && !has_exp) { flag = 0; return true; }
+    return false;
+  }
+  // value in [10^(nint-1+X), 10^(nint+X)); with <= 8 digits it stays >= 1e-8 (relative) away
+  // from 1e-10 unless it is >= 1e-10 exactly, so the rounded double compares the same way
+  flag = (nint + X <= -10) ? 1 : 0;
+  return true;
+}
+
+// score field starting at a (field ends before b): digits [. digits], <= 9 digits, no exponent;
+// anything after the numeric prefix is ignored (last sscanf conversion)
+template <class BR>
+JX_HD bool fast_score(const BR& B, int a, int b, float& score) {
+  int st = 0, cnt = 0, k = 0;
+  uint32_t m = 0;
+  bool expo = false;
+  const int bb = b - a > 12 ? a + 12 : b;               // longer fields go to the generic scanner
+  if (bb != b) return false;
+  for (int p = a; p < b; ++p) {
+    const uint32_t c = B(p);
+    const uint32_t d = c - '0';
+    const bool isd = d <= 9u;
+    if (st == 0) {
+      if (isd) { m = m * 10u + d; ++cnt; } else if (c == '.') st = 1; else { expo = (c | 0x20u) == 'e'; st = 2; }
+    } else if (st == 1) {
+      if (isd) { m = m * 10u + d; ++cnt; ++k; } else { expo = (c | 0x20u) == 'e'; st = 2; }
+    }
+  }
+  if (cnt == 0 || cnt > 9 || expo) return false;
+  if (m >= (1u << 24)) return false;
+  // both operands exact in float -> one correctly rounded division == strtof
+#if defined(__CUDA_ARCH__)
+  score = k ? __fdiv_rn((float)m, pow10f_exact(k)) : (float)m;
+#else
+  score = k ? (float)m / pow10f_exact(k) : (float)m;
+#endif
+  return true;
+}
+
+template <class W, class S>
+JX_HD bool fast_line3(const W& wr, int s, int limit, S* sep, int stride, LineTok& t) {
+  const WordBytes<W> B(wr);
+  t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false; t.qbar = t.sbar = -2;
+  // ---- separators: all lanes advance one word per iteration ------------------------------------
+  int nsep = 0, end12 = -1;
+  {
+    uint32_t keep = 0xFFFFFFFFu << (8 * (s & 3));
+    bool bad = false;
+    for (int q = s & ~3; end12 < 0 && !bad; q += 4) {
+      if (q + 8 > limit) { bad = true; break; }
+      const uint32_t x = wr(q >> 2);
+      uint32_t f = swar_le20(x) & keep;
+      keep = 0xFFFFFFFFu;
+      while (f) {
+        const int j = first_flag(f);
+        f &= f - 1;
+        const uint32_t c = (x >> (8 * j)) & 0xFFu;
+        const int pos = q + j;
+        if (c == '\t' && nsep < 11) {
+          sep[nsep * stride] = (S)pos;
+          ++nsep;
+        } else {
+          if (c == '\t' || c == '\n' || (c == '\r' && B(pos + 1) == '\n')) end12 = pos; else bad = true;
+          break;
+        }
+      }
+    }
+    if (bad) return false;
+  }
+  if (nsep != 11) return false;
+  int prev = s - 1;
+  bool ok = true;
+  for (int j = 0; j < 11; ++j) { const int tj = sep[j * stride]; ok &= (tj - prev >= 2); prev = tj; }
+  ok &= (end12 - prev >= 2);
+  const int t1 = sep[0], t2 = sep[stride], t3 = sep[2 * stride], t10 = sep[9 * stride], t11 = sep[10 * stride];
+  ok &= (t1 - s < 128) & (t2 - t1 - 1 < 128);
+  if (!ok) return false;
+  t.qa = s; t.qb = t1; t.sa = t1 + 1; t.sb = t2;
+  // ---- pctid: digits with at most one '.' ---------------------------------------------------------
+  {
+    const int nnd = count_nondigit(wr, t2 + 1, t3);
+    if (nnd > 1) return false;
+    if (nnd == 1 && (count_eq(wr, t2 + 1, t3, 0x2E2E2E2Eu) != 1 || t3 - t2 - 1 < 2)) return false;
+  }
+  // ---- seven integers: the only non-digits between t3 and t10 are the six tabs ------------------
+  if (count_nondigit(wr, t3 + 1, t10) != 6) return false;
+  // ---- evalue, score ----------------------------------------------------------------------------------
+  int flag;
+  if (!fast_evalue(B, t10 + 1, t11, flag)) {
+    Dec d;
+    const int p2 = scan_decimal(B, t10 + 1, t11, d);
+    if (d.special || !d.ok || p2 != t11) return false;
+    flag = dec_lt_1e10(d);
+    if (flag < 0) return false;
+  }
+  t.eflag = flag;
+  if (!fast_score(B, t11 + 1, end12, t.score)) {
+    Dec d;
+    scan_decimal(B, t11 + 1, end12, d);
+    if (d.special || !d.ok) return false;
+    if (!dec_to_f32(d, t.score)) return false;
+  }
+  t.nconv = 12;
+  return true;
+}
+
+// gene_name + hash in one go: returns the stripped end, sets h.  '|' is searched while hashing;
+// when one turns up the (rare) cut is applied and the hash recomputed.
+template <class W>
+JX_HD int fast_strip_hash(const WordBytes<W>& B, int a, int b, bool strip, uint64_t& h) {
+  int end = b;
+  if (strip) {
+    const bool ev = (b - a >= 2) && B(a) == 'e' && B(a + 1) == 'v';
+    if (!ev && b - a >= 2 && B(b - 2) == '.' && B(b - 1) != '.') end = b - 2;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    NameHash nh; nh.init();
+    int bar = -1;
+    for (int p = a; p < end; p += 4) {
+      uint32_t w = B.load32(p);
+      const int rem = end - p;
+      if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+      if (strip && bar < 0) { const uint32_t f = swar_eq(w, 0x7C7C7C7Cu); if (f) bar = p + first_flag(f); }
+      nh.word(w);
+    }
+    if (bar < 0 || pass == 1) { h = nh.finish((uint32_t)(end - a)); return end; }
+    // a '|' inside: gene_name cuts there first, then looks for the one-character suffix
+    end = bar;
+    const bool ev = (b - a >= 2) && B(a) == 'e' && B(a + 1) == 'v';
+    if (!ev && end - a >= 2 && B(end - 2) == '.' && B(end - 1) != '.') end -= 2;
+    strip = false;   // second pass: plain hash of [a, end)
+  }
+  return end;
+}
+
 }  // namespace jx

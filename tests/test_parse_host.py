@@ -164,7 +164,8 @@ def test_hash_is_stable(probe):
     assert h1 != h2 and probe.probe_hash(b"Ag000123x", 8) == h1
 
 
-def test_fast_line_agrees_with_generic_scanner(probe):
+@pytest.mark.parametrize("version", [2, 3])
+def test_fast_line_agrees_with_generic_scanner(probe, version):
     """The SWAR fast path (jx::fast_line) must either refuse a line or produce exactly what the
     generic sscanf-faithful scanner produces (spans, score bits, evalue flag, stripped name,
     hash of the stripped name)."""
@@ -172,9 +173,12 @@ def test_fast_line_agrees_with_generic_scanner(probe):
     base = "Ag000791.3\tBg002441.1\t75.72\t1173\t284\t18\t1402\t2575\t1556\t2729\t6.5e-21\t161.5"
     lines = [base]
     names = ["Ag1.1", "evm.model.000021F_np12.565", "mrna.AA565170.t1", "AT1G01010.1|x", "a|b.1", "g.12", "x", "ev.1",
-             "Os09g11510", "a.b.c", "averyveryveryverylongnamethatkeepsgoing_0123456789.2", "n..1", "p.1.", ".1"]
+             "Os09g11510", "a.b.c", "averyveryveryverylongnamethatkeepsgoing_0123456789.2", "n..1", "p.1.", ".1",
+             "evx|y.1", "ab.1|cd", "abcd|efgh.2", "abc.1|", "|abc"]
     nums = ["161.5", "54.0", "1386", "1.06e+03", "1e+05", "0", "99999", "3.5", ".5", "5.", "12345678.125", "1e-3"]
-    evs = ["6.5e-21", "0.0", "0", "1e-10", "9.9e-11", "2.5e-180", "0.001", "3", "1e-400", "1.0e-10", "5e-11"]
+    evs = ["6.5e-21", "0.0", "0", "1e-10", "9.9e-11", "2.5e-180", "0.001", "3", "1e-400", "1.0e-10", "5e-11", "10e-11",
+           "100e-12", "0.5e-10", "12.5e-12", "9.9999999e-11", "99999999e-18", "1E-11", "1e+2", "1e-09", "0.00000000001",
+           "0.31", "007e-12", "1.e-11", "5e-010"]
     pcts = ["75.72", "100", "100.00", "99.", ".5", "7"]
     for _ in range(4000):
         f = [names[rng.integers(len(names))], names[rng.integers(len(names))], pcts[rng.integers(len(pcts))]]
@@ -194,6 +198,7 @@ def test_fast_line_agrees_with_generic_scanner(probe):
         elif r == 9: f[10] = "1e"; ln = "\t".join(f)
         elif r == 10: f[11] = "nan"; ln = "\t".join(f)
         elif r == 11: ln = " " + ln
+        elif r == 12: ln = ln + "\r"
         lines.append(ln)
     nfast = 0
     for ln in lines:
@@ -203,7 +208,10 @@ def test_fast_line_agrees_with_generic_scanner(probe):
             s, n = pad, len(raw)
             spans = (ctypes.c_int * 4)(); score = ctypes.c_float(); eflag = ctypes.c_int()
             ends = (ctypes.c_int * 2)(); hs = (ctypes.c_ulonglong * 2)()
-            ok = probe.probe_fast_line(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
+            if version == 2:
+                ok = probe.probe_fast_line(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
+            else:
+                ok = probe.probe_fast_line3(buf, s, len(buf), spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
             gsp = (ctypes.c_int * 4)(); gsc = ctypes.c_float(); gnc = ctypes.c_int(); gef = ctypes.c_int()
             fl = probe.probe_line(ln.encode(), len(ln), gsp, ctypes.byref(gsc), ctypes.byref(gnc), ctypes.byref(gef))
             if not ok:
