@@ -82,34 +82,6 @@ __device__ int table_lookup_bytes(R& rd, int a, int b, const uint64_t* tab, uint
   }
 }
 
-// fast probe: hash and verify with 32-bit words straight from shared memory
-__device__ __forceinline__ int table_lookup_words(const jx::WordBytes<SmemWords>& B, int a, int b, const uint64_t* tab,
-                                                  uint32_t mask, const uint32_t* meta, const uint32_t* blob) {
-  if (b <= a) return -1;
-  const uint64_t h = jx::fast_hash(B, a, b);
-  const uint32_t tag = (uint32_t)(h >> 32), len = (uint32_t)(b - a);
-  uint32_t idx = (uint32_t)h & mask;
-  for (;;) {
-    const uint64_t slot = __ldg(tab + idx);
-    if (!slot) return -1;
-    if ((uint32_t)(slot >> 32) == tag) {
-      const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r);
-      if ((m & 127u) == len) {
-        const uint32_t* bw = blob + (m >> 7);
-        bool eq = true;
-        for (uint32_t i = 0; i < len; i += 4) {
-          uint32_t w = B.load32(a + (int)i);
-          const uint32_t rem = len - i;
-          if (rem < 4) w &= (1u << (8 * rem)) - 1u;
-          if (w != __ldg(bw + (i >> 2))) { eq = false; break; }
-        }
-        if (eq) return (int)r;
-      }
-    }
-    idx = (idx + 1) & mask;
-  }
-}
-
 // fast probe with a precomputed hash and the first slot already loaded (so that the query and
 // subject probes are in flight together); single-exit loops keep the warp converged
 __device__ __forceinline__ int table_probe_words(const jx::WordBytes<SmemWords>& B, int a, int b, uint64_t h,
@@ -142,12 +114,25 @@ __device__ __forceinline__ int table_probe_words(const jx::WordBytes<SmemWords>&
   return res;
 }
 
+__device__ __forceinline__ uint32_t term_nibble(uint32_t x) {   // 4 bytes -> 4 terminator bits
+  const uint32_t f = jx::swar_eq(x, 0x0A0A0A0Au) | jx::swar_eq(x, 0x0D0D0D0Du);
+  return (((f >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+__device__ __forceinline__ uint32_t term_mask32(const uint32_t* w) {   // 8 words -> 32 bits
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m |= term_nibble(w[k]) << (4 * k);
+  return m;
+}
+
 __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
   __shared__ __align__(16) uint32_t smw[JX_WIN / 4 + 8];
-  __shared__ uint16_t s_lpos[LCAP];                    // start offset of the lines of the current chunk
-  __shared__ uint16_t s_sep[12 * JX_TOK_THREADS];      // per-thread tab positions, [j][tid]
+  __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
+  __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per 64-byte segment
+  __shared__ unsigned long long s_start[JX_TOK_THREADS];
+  __shared__ uint16_t s_lpos[LCAP];             // start offset of every line of the tile
   __shared__ uint32_t s_warp[JX_TOK_THREADS / 32];
-  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_tile, s_nlines;
   __shared__ unsigned long long s_base;
   const uint8_t* sm = reinterpret_cast<const uint8_t*>(smw);
 
@@ -173,22 +158,23 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
   }
   __syncthreads();
 
-  // ---- count the lines that start in my 64 bytes: a line starts after every '\n' ----------------
-  // (valid starts: inside the tile and inside the text)
-  const int seg0 = tid * JX_SEG;
-  int64_t lim64 = a.n - base;                 // first offset that is not text
-  const int lim = (int)(lim64 < JX_TILE ? lim64 : JX_TILE);   // a start p must satisfy p < lim
-  uint32_t cnt = 0, wmask = 0;
-  const bool seg_full = seg0 + JX_SEG <= lim - 1;      // every '\n' of my segment starts a line of this tile
-#pragma unroll
-  for (int w = 0; w < JX_SEG / 4; ++w) {
-    uint32_t f = jx::swar_eq(smw[seg0 / 4 + w], 0x0A0A0A0Au);
-    // start = pos + 1 < lim  <=>  pos < lim - 1
-    if (!seg_full) f &= jx::range_mask(seg0 + 4 * w, 0, lim - 1);
-    cnt += __popc(f);
-    wmask |= (f ? 1u : 0u) << w;
+  // ---- terminator masks (SWAR, 32 bytes per mask word) ---------------------------------------------
+  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) s_term[seg] = term_mask32(smw + seg * 8);
+  __syncthreads();
+
+  // ---- line starts inside the tile (64 bytes per thread) + block scan ----------------------------------
+  unsigned long long starts;
+  {
+    const unsigned long long term = (unsigned long long)s_term[2 * tid] | ((unsigned long long)s_term[2 * tid + 1] << 32);
+    uint32_t prevbit;
+    if (tid == 0) prevbit = (base == 0) ? 1u : (uint32_t)jx::is_term(a.text[base - 1]);
+    else prevbit = s_term[2 * tid - 1] >> 31;
+    starts = (term << 1) | prevbit;
+    const int64_t remain = a.n - (base + (int64_t)tid * JX_SEG);   // only positions that exist can start a line
+    if (remain <= 0) starts = 0;
+    else if (remain < 64) starts &= (1ull << remain) - 1ull;
   }
-  if (tid == 0 && lim > 0 && (base == 0 || a.text[base - 1] == '\n')) ++cnt;
+  const uint32_t cnt = __popcll(starts);
   uint32_t inc = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
@@ -198,6 +184,16 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
 #pragma unroll
   for (int w = 0; w < JX_TOK_THREADS / 32; ++w) { const uint32_t v = s_warp[w]; if (w < warp) wbase += v; nlines += v; }
   const uint32_t mypref = wbase + inc - cnt;
+  s_pref[tid] = mypref;
+  s_start[tid] = starts;
+  {
+    unsigned long long m = starts;
+    uint32_t o = mypref;
+    while (m && o < LCAP) {
+      s_lpos[o++] = (uint16_t)(tid * JX_SEG + __ffsll((long long)m) - 1);
+      m &= m - 1;
+    }
+  }
 
   // ---- decoupled look-back: global ordinal of the tile's first line ---------------------------------
   if (warp == 0) {
@@ -232,123 +228,104 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
     }
     if (lane == 0) s_base = excl;
   }
+  __syncthreads();
+  const unsigned long long line_base = s_base;
 
+  // ---- parse: one line per thread -----------------------------------------------------------------
   WinReader rd{sm, a.text, base, a.n};
   const SmemWords wr{smw};
   const jx::WordBytes<SmemWords> B(wr);
-  uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0, c_cr = 0;
+  uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
   unsigned long long first_bad = 0;
-
-  // ---- lines, LCAP at a time (one chunk unless the average line is shorter than 8 bytes) -------------
-  for (uint32_t c0 = 0; c0 < nlines; c0 += LCAP) {
-    if (c0) __syncthreads();
-    {   // publish the start offsets of the lines [c0, c0 + LCAP)
-      uint32_t o = mypref;
-      if (tid == 0 && lim > 0 && (base == 0 || a.text[base - 1] == '\n')) {
-        if (o >= c0 && o < c0 + LCAP) s_lpos[o - c0] = 0;
-        ++o;
-      }
-      if (o < c0 + LCAP && mypref + cnt > c0) {
-        uint32_t wm = wmask;
-        while (wm) {                       // only the (one or two) words that hold a '\n'
-          const int w = __ffs((int)wm) - 1;
-          wm &= wm - 1;
-          uint32_t f = jx::swar_eq(smw[seg0 / 4 + w], 0x0A0A0A0Au);
-          if (!seg_full) f &= jx::range_mask(seg0 + 4 * w, 0, lim - 1);
-          while (f) {
-            const int pos = seg0 + 4 * w + jx::first_flag(f);
-            f &= f - 1;
-            if (o >= c0 && o < c0 + LCAP) s_lpos[o - c0] = (uint16_t)(pos + 1);
-            ++o;
-          }
-        }
-      }
+  for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
+    const uint32_t k = k0 + tid;
+    if (k >= nlines) break;
+    int s;
+    if (k < LCAP) s = s_lpos[k];
+    else {   // overfull tile (average line < 8 bytes): locate the line through the prefix array
+      int lo = 0, hi = JX_TOK_THREADS - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= k) lo = mid; else hi = mid - 1; }
+      unsigned long long m = s_start[lo];
+      for (uint32_t r = k - s_pref[lo]; r; --r) m &= m - 1;
+      s = lo * JX_SEG + __ffsll((long long)m) - 1;
     }
-    __syncthreads();
-    const unsigned long long line_base = s_base;
-    const uint32_t nchunk = min(nlines - c0, (uint32_t)LCAP);
-    for (uint32_t k0 = 0; k0 < nchunk; k0 += JX_TOK_THREADS) {
-      const uint32_t k = k0 + tid;
-      if (k >= nchunk) break;
-      const int s = s_lpos[k];
-      uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
-      if (sm[s] == '#') {
-        ++c_comment;
-      } else {
-        jx::LineTok t;
-        const bool fast = jx::fast_line3(wr, s, JX_WIN, s_sep + tid, JX_TOK_THREADS, t);
-        if (!fast) {
-          int e = s;
-          for (;;) {
-            const uint32_t c = rd(e);
-            if (c == '\n') break;
-            if (c == '\r' && rd(e + 1) != '\n') ++c_cr;     // classic-Mac line ending: not supported
-            ++e;
-          }
-          jx::tokenize_line(rd, s, e, t);
+    int e;   // end of line: next terminator at or after s
+    if (k + 1 < nlines && k + 1 < LCAP) e = (int)s_lpos[k + 1] - 1;
+    else {
+      int w = s >> 5;
+      uint32_t m = s_term[w] & (0xFFFFFFFFu << (s & 31));
+      while (!m && ++w < JX_WIN / 32) m = s_term[w];
+      if (m) e = w * 32 + __ffs(m) - 1;
+      else { e = JX_WIN; while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e; }
+    }
+    uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+    if (s < e && sm[s] == '#') {
+      ++c_comment;
+    } else if (s < e) {
+      jx::LineTok t;
+      const bool fast = (e + 8 <= JX_WIN) && jx::fast_line(wr, s, e, t);
+      if (!fast) jx::tokenize_line(rd, s, e, t);
+      bool bad = false, selfhit = false;
+      int qi = -1, si = -1;
+      if (t.nconv >= 2) {
+        if (t.longname) { bad = true; ++c_long; }
+        int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
+        if (a.is_self && (qb - qa) == (sb - sa)) {      // `is_self and query == subject` on raw names
+          selfhit = true;
+          for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
         }
-        bool bad = false, selfhit = false;
-        int qi = -1, si = -1;
-        if (t.nconv >= 2) {
-          if (t.longname) { bad = true; ++c_long; }
-          int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
-          if (a.is_self && (qb - qa) == (sb - sa)) {      // `is_self and query == subject` on raw names
-            selfhit = true;
-            for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
-          }
-          if (!selfhit && !bad) {
-            if (fast) {
-              uint64_t hq, hs;
-              qb = jx::fast_strip_hash(B, qa, qb, a.strip != 0, hq);
-              sb = jx::fast_strip_hash(B, sa, sb, a.strip != 0, hs);
-              const uint64_t slot_q = __ldg(a.qtab + ((uint32_t)hq & a.qmask));
-              const uint64_t slot_s = __ldg(a.stab + ((uint32_t)hs & a.smask));
-              qi = table_probe_words(B, qa, qb, hq, slot_q, a.qtab, a.qmask, a.qmeta, a.qblob);
-              si = table_probe_words(B, sa, sb, hs, slot_s, a.stab, a.smask, a.smeta, a.sblob);
-            } else {
-              if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
-              qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
-              if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
-            }
-          }
-        }
-        if (selfhit) ++c_self;
-        else if (bad) { if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
-        else if (qi < 0 || si < 0) ++c_unmapped;
-        else if (t.hard) { ++c_hard; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
-        else {
-          if (a.is_self && qi > si) { int tmp = qi; qi = si; si = tmp; }
-          bool keep = true;
-          if (a.neardiag && a.qchr[qi] == a.schr[si] && si - qi < 40) { keep = false; ++c_self; }
-          if (keep && a.n_excl) {
-            uint64_t key = ((uint64_t)(uint32_t)qi << 32) | (uint32_t)si;
-            int64_t l = 0, h = a.n_excl;
-            while (l < h) { int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
-            if (l < a.n_excl && a.excl[l] == key) { keep = false; ++c_excl; }
-          }
-          if (keep) {
-            ++c_mapped;
-            const uint32_t sbits = __float_as_uint(t.score);
-            rec = make_uint4((uint32_t)qi, (uint32_t)si, sbits, ((uint32_t)s << 1) | (uint32_t)t.eflag);
-            if (a.best && t.score > 0.f) {            // best_score[name] = max(score), starting at 0.0
-              uint32_t* bq = a.best + a.qnid[qi];
-              uint32_t* bs = a.best + a.snid[si];
-              if (__ldcg(bq) < sbits) atomicMax(bq, sbits);
-              if (__ldcg(bs) < sbits) atomicMax(bs, sbits);
-            }
+        if (!selfhit && !bad) {
+          if (fast) {
+            if (a.strip) { qb = jx::fast_strip(B, qa, qb, t.qbar); sb = jx::fast_strip(B, sa, sb, t.sbar); }
+            const uint64_t hq = jx::fast_hash(B, qa, qb), hs = jx::fast_hash(B, sa, sb);
+            const uint64_t slot_q = __ldg(a.qtab + ((uint32_t)hq & a.qmask));
+            const uint64_t slot_s = __ldg(a.stab + ((uint32_t)hs & a.smask));
+            qi = table_probe_words(B, qa, qb, hq, slot_q, a.qtab, a.qmask, a.qmeta, a.qblob);
+            si = table_probe_words(B, sa, sb, hs, slot_s, a.stab, a.smask, a.smeta, a.sblob);
+          } else {
+            if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
+            qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
+            if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
           }
         }
       }
-      const unsigned long long ord = line_base + c0 + k;
-      if (ord < a.rec_cap) a.recs[ord] = rec;
+      if (selfhit) ++c_self;
+      else if (bad) { if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+      else if (qi < 0 || si < 0) ++c_unmapped;
+      else if (t.hard) { ++c_hard; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+      else {
+        if (a.is_self && qi > si) { int tmp = qi; qi = si; si = tmp; }
+        bool keep = true;
+        if (a.neardiag && a.qchr[qi] == a.schr[si] && si - qi < 40) { keep = false; ++c_self; }
+        if (keep && a.n_excl) {
+          uint64_t key = ((uint64_t)(uint32_t)qi << 32) | (uint32_t)si;
+          int64_t l = 0, h = a.n_excl;
+          while (l < h) { int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+          if (l < a.n_excl && a.excl[l] == key) { keep = false; ++c_excl; }
+        }
+        if (keep) {
+          ++c_mapped;
+          const uint32_t sbits = __float_as_uint(t.score);
+          rec = make_uint4((uint32_t)qi, (uint32_t)si, sbits, ((uint32_t)s << 1) | (uint32_t)t.eflag);
+          if (a.best && t.score > 0.f) {            // best_score[name] = max(score), starting at 0.0
+            uint32_t* bq = a.best + a.qnid[qi];
+            uint32_t* bs = a.best + a.snid[si];
+            if (__ldcg(bq) < sbits) atomicMax(bq, sbits);
+            if (__ldcg(bs) < sbits) atomicMax(bs, sbits);
+          }
+        }
+      }
+    } else {
+      ++c_unmapped;   // empty line: a BlastLine with empty names, never in the BED
     }
+    const unsigned long long ord = line_base + k;
+    if (ord < a.rec_cap) a.recs[ord] = rec;
   }
-  if (nlines == 0) __syncthreads();   // pair with the barrier the loop would have executed
 
   // ---- counters ---------------------------------------------------------------------------------------
-  uint32_t vals[8] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self, c_cr};
+  uint32_t vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 7; ++i) {
     uint32_t v = vals[i];
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -362,12 +339,11 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
     if (vals[4]) atomicAdd(a.stats + 5, (unsigned long long)vals[4]);
     if (vals[5]) atomicAdd(a.stats + 8, (unsigned long long)vals[5]);
     if (vals[6]) atomicAdd(a.stats + 9, (unsigned long long)vals[6]);
-    if (vals[7]) atomicAdd(a.stats + 11, (unsigned long long)vals[7]);
   }
   if (first_bad) atomicMin(a.stats + 7, first_bad);
   if (tid == 0) {
     atomicAdd(a.stats + 0, (unsigned long long)nlines);
-    if (s_base + nlines > a.rec_cap) atomicExch(a.stats + 6, 1ull);
+    if (line_base + nlines > a.rec_cap) atomicExch(a.stats + 6, 1ull);
   }
 }
 
@@ -464,11 +440,6 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   out.n_lines = (uint32_t)out.stats[0];
   ctx->tok_lines += (int64_t)out.stats[0];
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
-  if (out.stats[11]) {
-    ctx->err = "the text contains '\\r' line terminators that are not followed by '\\n' (classic Mac line endings); "
-               "not supported";
-    return JX_EUNSUPPORTED;
-  }
   if (out.stats[5]) {
     ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +
                " (overflows cblast.pyx's char[128]; undefined behaviour in the reference)";
