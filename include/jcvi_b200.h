@@ -56,6 +56,15 @@ uint64_t jx_stream_handle(jx_ctx* ctx);
  * and the lines (16-byte records) they wrote */
 int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, int64_t* bytes, int64_t* lines);
 
+/* ---- text residency ------------------------------------------------------------------------
+ * blastfilter and liftover both read the raw hit table (blastfilter.py:48, synteny.py:1939);
+ * upload it once: the copy runs asynchronously in 64 MiB chunks and the stage calls that are
+ * handed the returned device pointer (text_on_device = 1, same nbytes) start tokenizing each
+ * chunk as soon as it has landed.  One held text per context; released by the next upload,
+ * jx_text_release or jx_ctx_destroy.  Pinned host memory gives full PCIe speed. */
+int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t* device_ptr);
+int jx_text_release(jx_ctx* ctx);
+
 /* ---- BED side tables -------------------------------------------------------------------
  * Replaces the name -> (rank, BedLine) dicts of Bed.order (formats/bed.py:196-198) and the
  * per-gene attributes the path reads (seqid, start, end, accn).  All arrays are in rank order.
@@ -99,13 +108,16 @@ typedef struct {
   int32_t* s_rank;
   float* score;                 /* float32 as parsed (cblast.pyx:88)                            */
   uint64_t* line_off;           /* byte offset of the hit's line in the input text              */
-  char* text;                   /* `.filtered` bytes when want_text                             */
+  char* text;                   /* `.filtered` bytes when want_text; when text_pinned != 0 they
+                                   live in the context's pinned staging buffer and stay valid
+                                   until the next jx_blastfilter call on the same context       */
   int64_t text_len;
   int32_t* q_mother;            /* [n_genes(q)] when want_mothers: mother rank of every gene    */
   int32_t* s_mother;            /* [n_genes(s)]                                                 */
   /* counters: 0 lines (non-'#'), 1 mapped records, 2 unmapped names ("not in bed" warnings),
    * 3 after exclude, 4 after cscore (pre-dedupe), 5 after dedupe, 6 after tandem, 7 '#' lines */
   int64_t stats[8];
+  int32_t text_pinned;          /* 0: malloc'ed, owned by the result; 2: context-owned (see text) */
 } jx_filter_result;
 
 int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device,

@@ -37,7 +37,8 @@ class JxFilterOpts(ctypes.Structure):
 class JxFilterResult(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int64), ("q_rank", c_i32p), ("s_rank", c_i32p), ("score", c_f32p),
                 ("line_off", c_u64p), ("text", ctypes.c_void_p), ("text_len", ctypes.c_int64),
-                ("q_mother", c_i32p), ("s_mother", c_i32p), ("stats", ctypes.c_int64 * 8)]
+                ("q_mother", c_i32p), ("s_mother", c_i32p), ("stats", ctypes.c_int64 * 8),
+                ("text_pinned", ctypes.c_int32)]
 
 
 class JxScanOpts(ctypes.Structure):
@@ -59,7 +60,7 @@ EXPORTS = [
     "jx_ctx_create", "jx_ctx_destroy", "jx_last_error", "jx_version", "jx_launch_count", "jx_stream_handle",
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
-    "jx_liftover_result_free", "jx_nearest_anchor",
+    "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release",
 ]
 
 _lib = None
@@ -105,6 +106,8 @@ def lib():
         L.jx_liftover_result_free.restype = None
         L.jx_nearest_anchor.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.jx_text_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64)]
+        L.jx_text_release.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 

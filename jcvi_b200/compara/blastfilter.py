@@ -88,7 +88,7 @@ def blastfilter_main(blast_file, p, opts):
                 sd = write_localdups(res.s_mother, sbed, fh)
             write_new_bed(sbed, sd)
     with open(blast_file + ".filtered", "wb") as fw:
-        fw.write(res.text)
+        fw.write(memoryview(res.text))
     return res
 
 

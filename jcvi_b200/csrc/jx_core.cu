@@ -55,6 +55,10 @@ void jx_ctx_destroy(jx_ctx* ctx) {
     cudaFree(d.chr_end); cudaFree(d.length); cudaFree(d.lexrank); cudaFree(d.name_id);
   }
   cudaFree(ctx->q_same_s);
+  cudaStreamSynchronize(ctx->copy_stream);
+  for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
+  cudaFree(ctx->held_text);
+  if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);

@@ -13,6 +13,7 @@
 // sees the ~5-10 % of records that pass.
 #include <thread>
 
+#include "jx_format.cuh"
 #include "jx_internal.cuh"
 
 namespace {
@@ -166,22 +167,67 @@ __global__ void k_gather_out(const uint32_t* Fj, uint32_t n, const uint4* C, con
   ooff[t] = (uint64_t)lo * JX_TILE + (r.w >> 1);
 }
 
-__global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, uint32_t cnt, uint32_t* len) {
+__global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, const uint32_t* idx, uint32_t cnt, uint32_t* len) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt) return;
-  int64_t p = (int64_t)off[t], e = p;
+  int64_t p = (int64_t)off[idx ? idx[t] : t], e = p;
   while (e < n && !jx::is_term(text[e])) ++e;
   len[t] = (uint32_t)(e - p) + 1;      // + '\n'
 }
-__global__ void k_copy_lines(const uint8_t* text, const uint64_t* off, const uint32_t* len, const uint32_t* pos,
-                             uint32_t cnt, uint8_t* out) {
+__global__ void k_copy_lines(const uint8_t* text, const uint64_t* off, const uint32_t* idx, const uint32_t* len,
+                             const uint32_t* pos, uint32_t cnt, uint8_t* out) {
   uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= cnt) return;
-  const uint8_t* src = text + off[w];
+  const uint8_t* src = text + off[idx ? idx[w] : w];
   uint8_t* dst = out + pos[w];
   uint32_t L = len[w] - 1;
   for (uint32_t i = lane; i < L; i += 32) dst[i] = src[i];
   if (lane == 0) dst[L] = '\n';
+}
+
+// ---- K12: exact `.filtered` writer on the device ------------------------------------------------
+struct TextReader {            // bytes of one line in global memory, relative to its start
+  const uint8_t* t;
+  int64_t remain;
+  __device__ __forceinline__ uint32_t operator()(int p) const { return p < remain ? t[p] : (uint32_t)'\n'; }
+};
+
+// formats the numeric tail of survivor t into `tail` (<= 160 bytes); returns false -> glibc
+__device__ bool format_tail(const uint8_t* text, int64_t n, uint64_t off, char* tail, int& tail_len) {
+  TextReader rd{text + off, n - (int64_t)off};
+  int e = 0;
+  while (!jx::is_term(rd(e))) ++e;
+  jx::LineFields f;
+  jx::scan_fields(rd, 0, e, f);
+  return jx::fmt_numeric_tail(tail, tail_len, f);
+}
+
+__global__ void k_format_len(const uint8_t* text, int64_t n, const uint64_t* off, const int32_t* q, const int32_t* s,
+                             const uint32_t* qmeta, const uint32_t* smeta, uint32_t cnt, uint32_t* len, uint32_t* fallback) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  char tail[160];
+  int tl = 0;
+  if (!format_tail(text, n, off[t], tail, tl)) { atomicAdd(fallback, 1u); len[t] = 0; return; }   // declined: host formats it
+  len[t] = (qmeta[q[t]] & 127u) + 1u + (smeta[s[t]] & 127u) + (uint32_t)tl;
+}
+
+__global__ void k_format_write(const uint8_t* text, int64_t n, const uint64_t* off, const int32_t* q, const int32_t* s,
+                               const uint32_t* qmeta, const uint32_t* qblob, const uint32_t* smeta, const uint32_t* sblob,
+                               uint32_t cnt, const uint32_t* pos, char* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  char tail[160];
+  int tl = 0;
+  if (!format_tail(text, n, off[t], tail, tl)) return;
+  char* o = out + pos[t];
+  uint32_t m = qmeta[q[t]], l = m & 127u;
+  const uint32_t* w = qblob + (m >> 7);
+  for (uint32_t i = 0; i < l; ++i) *o++ = (char)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+  *o++ = '\t';
+  m = smeta[s[t]]; l = m & 127u; w = sblob + (m >> 7);
+  for (uint32_t i = 0; i < l; ++i) *o++ = (char)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+  for (int i = 0; i < tl; ++i) *o++ = tail[i];
 }
 
 inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
@@ -224,11 +270,13 @@ int dedupe(jx_ctx* ctx, Arena& arena, uint64_t* keys, uint32_t* vals, size_t n, 
 
 // the reference's own formatting of one survivor: sscanf with cblast.pyx:15, start/stop
 // normalisation (cblast.pyx:115-120), sprintf with cblast.pyx:17 and the substituted names
-void format_range(const char* lines, const uint32_t* pos, const uint32_t* len, const int32_t* q, const int32_t* s,
-                  size_t lo, size_t hi, const SideDev& Q, const SideDev& S, std::string& out) {
+void format_range(const char* lines, const uint32_t* pos, const uint32_t* len, const int32_t* q_all, const int32_t* s_all,
+                  const uint32_t* idx, size_t lo, size_t hi, const SideDev& Q, const SideDev& S, std::string& out) {
   char qn[160], sn[160], buf[1024];
   std::string line;
   for (size_t t = lo; t < hi; ++t) {
+    const int32_t* q = q_all + (idx ? idx[t] : t) - t;   // q[t] / s[t] below address the survivor
+    const int32_t* s = s_all + (idx ? idx[t] : t) - t;
     line.assign(lines + pos[t], len[t]);
     float pct = 0, score = 0; double ev = 0; int v[7] = {0, 0, 0, 0, 0, 0, 0};
     qn[0] = sn[0] = 0;
@@ -253,7 +301,8 @@ extern "C" {
 
 void jx_filter_result_free(jx_filter_result* r) {
   if (!r) return;
-  free(r->q_rank); free(r->s_rank); free(r->score); free(r->line_off); free(r->text); free(r->q_mother); free(r->s_mother);
+  free(r->q_rank); free(r->s_rank); free(r->score); free(r->line_off); free(r->q_mother); free(r->s_mother);
+  if (!r->text_pinned) free(r->text);   // pinned text belongs to the context
   memset(r, 0, sizeof *r);
 }
 
@@ -412,41 +461,107 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     JX_CK(cudaMemcpyAsync(out->score, osc, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaMemcpyAsync(out->line_off, ooff, nF * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (opts->want_text) {
-      // gather the surviving lines on the device, format on the host with the reference's own
-      // sscanf/sprintf pair (cblast.pyx:15,17)
-      JX_ALLOC(len, uint32_t, nF, false);
-      JX_ALLOC(pos, uint32_t, nF, false);
-      JX_LAUNCH(k_line_len, nblk(nF), 256, 0, tok.d_text, tok.nbytes, ooff, nF, len);
-      if ((rc = jx_exclusive_sum(ctx, arena, len, pos, nF))) return rc;
-      std::vector<uint32_t> hlen(nF), hpos(nF);
-      JX_CK(cudaMemcpyAsync(hlen.data(), len, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      JX_CK(cudaMemcpyAsync(hpos.data(), pos, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      // K12: format on the device (exact re-implementation of the "%.2f/%.2g/%.3g" conversions);
+      // anything it declines (inf/nan, >int32 integers, decimal rounding ties in the evalue ...)
+      // sends the whole output through the host's glibc instead.
+      JX_ALLOC(flen, uint32_t, nF, false);
+      JX_ALLOC(fpos, uint32_t, nF, false);
+      JX_ALLOC(ffb, uint32_t, 1, true);
+      JX_LAUNCH(k_format_len, nblk(nF, 128), 128, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, S.name_meta, nF, flen, ffb);
+      if ((rc = jx_exclusive_sum(ctx, arena, flen, fpos, nF))) return rc;
+      uint32_t h[3] = {0, 0, 0};
+      JX_CK(cudaMemcpyAsync(&h[0], ffb, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(&h[1], fpos + nF - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(&h[2], flen + nF - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
       JX_CK(cudaStreamSynchronize(ctx->stream));
-      const uint64_t total = (uint64_t)hpos[nF - 1] + hlen[nF - 1];
-      if (total >= 0xFFFFFFFFull) { ctx->err = "surviving lines exceed 4 GiB"; return JX_EUNSUPPORTED; }
-      JX_ALLOC(packed, uint8_t, (size_t)total, false);
-      JX_LAUNCH(k_copy_lines, nblk((size_t)nF * 32), 256, 0, tok.d_text, ooff, len, pos, nF, packed);
-      std::vector<char> hl((size_t)total);
-      JX_CK(cudaMemcpyAsync(hl.data(), packed, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-      JX_CK(cudaStreamSynchronize(ctx->stream));
-      unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-      if (nF < 4096) nt = 1;
-      std::vector<std::string> parts(nt);
-      std::vector<std::thread> th;
-      for (unsigned t = 0; t < nt; ++t) {
-        size_t lo = (size_t)nF * t / nt, hi = (size_t)nF * (t + 1) / nt;
-        th.emplace_back([&, t, lo, hi]() {
-          format_range(hl.data(), hpos.data(), hlen.data(), out->q_rank, out->s_rank, lo, hi, Q, S, parts[t]);
-        });
+      const uint32_t ndecl = h[0];
+      const uint64_t total = (uint64_t)h[1] + h[2];
+      if (total >= 0xFFFFFFF0ull) { ctx->err = "`.filtered` text exceeds 4 GiB"; return JX_EUNSUPPORTED; }
+      JX_ALLOC(dtext, char, (size_t)total + 1, false);
+      JX_LAUNCH(k_format_write, nblk(nF, 128), 128, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, Q.blobw,
+                S.name_meta, S.blobw, nF, fpos, dtext);
+      if (ctx->pin_cap < total + 1) {               // grow-only pinned staging owned by the context
+        if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+        ctx->pin_buf = nullptr; ctx->pin_cap = 0;
+        const size_t cap = (size_t)(total + 1) + (size_t)(total >> 2) + (1u << 20);
+        JX_CK(cudaMallocHost((void**)&ctx->pin_buf, cap));
+        ctx->pin_cap = cap;
       }
-      for (auto& x : th) x.join();
-      size_t tl = 0;
-      for (auto& p : parts) tl += p.size();
-      out->text = (char*)malloc(tl + 1);
-      out->text_len = (int64_t)tl;
-      size_t o = 0;
-      for (auto& p : parts) { memcpy(out->text + o, p.data(), p.size()); o += p.size(); }
-      out->text[tl] = 0;
+      char* host = ctx->pin_buf;
+      JX_CK(cudaMemcpyAsync(host, dtext, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+      if (!ndecl) {
+        JX_CK(cudaStreamSynchronize(ctx->stream));
+        host[total] = 0;
+        out->text = host;
+        out->text_pinned = 2;                        // context-owned: valid until the next jx_blastfilter on ctx
+        out->text_len = (int64_t)total;
+      } else {
+        // a few lines were declined by the device writer: format exactly those with the host's
+        // glibc (the reference's own sscanf/sprintf pair, cblast.pyx:15,17) and splice them in
+        std::vector<uint32_t> hlen_all(nF), hpos_all(nF);
+        JX_CK(cudaMemcpyAsync(hlen_all.data(), flen, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaMemcpyAsync(hpos_all.data(), fpos, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<uint32_t> didx;
+        didx.reserve(ndecl);
+        for (uint32_t t = 0; t < nF; ++t) if (!hlen_all[t]) didx.push_back(t);
+        const uint32_t nd = (uint32_t)didx.size();
+        JX_ALLOC(d_idx, uint32_t, nd, false);
+        JX_ALLOC(len, uint32_t, nd, false);
+        JX_ALLOC(pos, uint32_t, nd, false);
+        JX_CK(cudaMemcpyAsync(d_idx, didx.data(), (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->stream));
+        JX_LAUNCH(k_line_len, nblk(nd), 256, 0, tok.d_text, tok.nbytes, ooff, d_idx, nd, len);
+        if ((rc = jx_exclusive_sum(ctx, arena, len, pos, nd))) return rc;
+        std::vector<uint32_t> hlen(nd), hpos(nd);
+        JX_CK(cudaMemcpyAsync(hlen.data(), len, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaMemcpyAsync(hpos.data(), pos, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaStreamSynchronize(ctx->stream));
+        const uint64_t ltotal = (uint64_t)hpos[nd - 1] + hlen[nd - 1];
+        if (ltotal >= 0xFFFFFFFFull) { ctx->err = "declined lines exceed 4 GiB"; return JX_EUNSUPPORTED; }
+        JX_ALLOC(packed, uint8_t, (size_t)ltotal, false);
+        JX_LAUNCH(k_copy_lines, nblk((size_t)nd * 32), 256, 0, tok.d_text, ooff, d_idx, len, pos, nd, packed);
+        std::vector<char> hl((size_t)ltotal);
+        JX_CK(cudaMemcpyAsync(hl.data(), packed, (size_t)ltotal, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaStreamSynchronize(ctx->stream));
+        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (nd < 4096) nt = 1;
+        std::vector<std::string> parts(nt);
+        std::vector<size_t> part_lo(nt + 1, 0);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) {
+          size_t lo = (size_t)nd * t / nt, hi = (size_t)nd * (t + 1) / nt;
+          part_lo[t] = lo; part_lo[t + 1] = hi;
+          th.emplace_back([&, t, lo, hi]() {
+            format_range(hl.data(), hpos.data(), hlen.data(), out->q_rank, out->s_rank, didx.data(), lo, hi, Q, S, parts[t]);
+          });
+        }
+        for (auto& x : th) x.join();
+        std::string merged;
+        size_t extra = 0;
+        for (auto& p : parts) extra += p.size();
+        merged.reserve((size_t)total + extra + 1);
+        // every host-formatted line ends with '\n': walk the parts line by line while copying the
+        // device-formatted runs in between
+        unsigned pi = 0; size_t po = 0;
+        uint64_t copied_to = 0;                       // device text consumed so far
+        for (uint32_t k = 0; k < nd; ++k) {
+          const uint32_t t = didx[k];
+          const uint64_t upto = hpos_all[t];          // device bytes that precede survivor t
+          merged.append(host + copied_to, (size_t)(upto - copied_to));
+          copied_to = upto;
+          while (pi < nt && k >= part_lo[pi + 1]) { ++pi; po = 0; }
+          const std::string& P = parts[pi];
+          const size_t nl = P.find('\n', po);
+          merged.append(P, po, nl - po + 1);
+          po = nl + 1;
+        }
+        merged.append(host + copied_to, (size_t)(total - copied_to));
+        out->text = (char*)malloc(merged.size() + 1);
+        memcpy(out->text, merged.data(), merged.size());
+        out->text[merged.size()] = 0;
+        out->text_len = (int64_t)merged.size();
+        out->text_pinned = 0;
+      }
     }
   } else if (opts->want_text) {
     out->text = (char*)calloc(1, 1);

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "jx_parse.cuh"
+#include "jx_format.cuh"
 
 namespace {
 struct PtrReader { const unsigned char* p; inline uint32_t operator()(int i) const { return p[i]; } };
@@ -113,6 +114,48 @@ int probe_fast_line3(const char* buf, int s, int limit, int* spans, float* score
   strip_ends[1] = jx::fast_strip_hash(B, t.sa, t.sb, true, h1);
   hashes[0] = h0; hashes[1] = h1;
   return 1;
+}
+
+
+int probe_fmt_2f(float x, char* out) { int n; if (!jx::fmt_f32_2f(out, n, x)) return -1; out[n] = 0; return n; }
+int probe_fmt_3g(float x, char* out) { int n; if (!jx::fmt_f32_3g(out, n, x)) return -1; out[n] = 0; return n; }
+int probe_fmt_2g_text(const char* s, char* out) {
+  PtrReader rd{(const unsigned char*)s};
+  jx::Dec d;
+  jx::scan_decimal(rd, 0, (int)strlen(s), d);
+  if (d.special || !d.ok) return -2;
+  int n; if (!jx::fmt_dec_2g(out, n, d)) return -1; out[n] = 0; return n;
+}
+// exhaustive-ish sweeps against glibc; return mismatches
+long probe_fmt_3g_range(unsigned lo, unsigned hi, unsigned step, unsigned* bad, long* unsupported) {
+  long mism = 0; *unsupported = 0; char a[64], b[64];
+  for (unsigned long u = lo; u < hi; u += step) {
+    float x = jx::bits_to_float((uint32_t)u); int n;
+    if (!jx::fmt_f32_3g(a, n, x)) { ++*unsupported; continue; }
+    a[n] = 0; snprintf(b, sizeof b, "%.3g", (double)x);
+    if (strcmp(a, b)) { if (!mism) *bad = (unsigned)u; ++mism; }
+  }
+  return mism;
+}
+long probe_fmt_2f_range(unsigned lo, unsigned hi, unsigned step, unsigned* bad, long* unsupported) {
+  long mism = 0; *unsupported = 0; char a[64], b[64];
+  for (unsigned long u = lo; u < hi; u += step) {
+    float x = jx::bits_to_float((uint32_t)u); int n;
+    if (!jx::fmt_f32_2f(a, n, x)) { ++*unsupported; continue; }
+    a[n] = 0; snprintf(b, sizeof b, "%.2f", (double)x);
+    if (strcmp(a, b)) { if (!mism) *bad = (unsigned)u; ++mism; }
+  }
+  return mism;
+}
+// whole line: returns length of the numeric tail or -1 (leave to glibc)
+int probe_fmt_line(const char* line, int n, char* out) {
+  PtrReader rd{(const unsigned char*)line};
+  jx::LineFields f;
+  jx::scan_fields(rd, 0, n, f);
+  int k;
+  if (!jx::fmt_numeric_tail(out, k, f)) return -1;
+  out[k] = 0;
+  return k;
 }
 
 }  // extern "C"

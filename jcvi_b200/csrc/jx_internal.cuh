@@ -55,6 +55,12 @@ struct jx_ctx {
   // tokenizer timing (CUDA events on `stream`)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
   int64_t tok_bytes = 0;
+  // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
+  char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text
+  size_t pin_cap = 0;
+  uint8_t* held_text = nullptr;
+  int64_t held_n = 0;
+  std::vector<cudaEvent_t> held_events;
   int64_t tok_lines = 0;
   double tok_ms_acc = 0;
   int64_t tok_launches_acc = 0;

@@ -263,12 +263,14 @@ JX_HD int dec_lt_1e10(const Dec& d) {
 // `blastfilter` printed the score with "%.3g" (cblast.pyx:17) -- exact integer arithmetic,
 // round-half-even on the exact binary value like glibc printf.  Returns false when the
 // magnitude is outside the exactly handled range (caller falls back to text round trip).
-JX_HD bool round3g_f32(float x, float& out) {
+// |x| rounded to three significant digits exactly like glibc's "%.3g": |x| ~ q * 10^(p-2), 100 <= q <= 999
+JX_HD bool round3_digits(float x, uint32_t& q_out, int& p_out, bool& neg_out, bool& zero_out) {
   uint32_t u = float_to_bits(x);
   bool neg = u >> 31;
   uint32_t ex = (u >> 23) & 0xFFu, fr = u & 0x7FFFFFu;
   if (ex == 0xFFu) return false;
-  if (ex == 0 && fr == 0) { out = x; return true; }
+  neg_out = neg; zero_out = false;
+  if (ex == 0 && fr == 0) { zero_out = true; q_out = 0; p_out = 0; return true; }
   if (ex == 0) return false;                 // subnormal: not a score
   const uint64_t M = fr | 0x800000u;         // |x| = M * 2^E, 2^23 <= M < 2^24
   const int E = (int)ex - 150;
@@ -305,6 +307,13 @@ JX_HD bool round3g_f32(float x, float& out) {
   const uint64_t twice = rem << 1;            // rem < den <= 2^61: no overflow
   if (twice > den || (twice == den && (q & 1u))) ++q;
   if (q >= 1000) { q = 100; ++p; }
+  q_out = (uint32_t)q; p_out = p;
+  return true;
+}
+JX_HD bool round3g_f32(float x, float& out) {
+  uint32_t q; int p; bool neg, zero;
+  if (!round3_digits(x, q, p, neg, zero)) return false;
+  if (zero) { out = x; return true; }
   Dec d; d.m = q; d.e10 = p - 2; d.neg = neg; d.ok = true; d.dropped = false; d.special = false;
   return dec_to_f32(d, out);
 }

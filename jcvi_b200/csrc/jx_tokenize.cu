@@ -360,9 +360,13 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   constexpr int64_t CHUNK = 64ll << 20;   // H2D pipelining granule (multiple of the tile size)
   const int64_t nchunks = (nbytes + CHUNK - 1) / CHUNK;
   std::vector<cudaEvent_t> copied;
+  bool held = false;
   if (on_device) {
     if (((uintptr_t)text & 15u) != 0) { ctx->err = "device text must be 16-byte aligned"; return JX_EARG; }
     d_text = (const uint8_t*)text;
+    // text uploaded by jx_text_upload: its chunk copies may still be in flight on the copy stream
+    held = ctx->held_text && d_text == ctx->held_text && nbytes == ctx->held_n;
+    if (held) copied = ctx->held_events;
   } else {
     JX_ALLOC(buf, uint8_t, (size_t)nbytes + 16, false);
     d_text = buf;
@@ -417,7 +421,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     const int64_t tiles_per_chunk = CHUNK / JX_TILE;
     for (int64_t c = 0; c < std::max<int64_t>(nchunks, 0); ++c) {
       int64_t t0 = c * tiles_per_chunk, t1 = std::min(ntiles, t0 + tiles_per_chunk);
-      if (!on_device && attempt == 0) {
+      if ((!on_device || held) && attempt == 0 && !copied.empty()) {
         // a tile's look-ahead may reach into the next chunk: wait for that copy too
         JX_CK(cudaStreamWaitEvent(ctx->stream, copied[(size_t)std::min(c + 1, nchunks - 1)], 0));
       }
@@ -436,7 +440,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     if (!out.stats[6]) break;
     if (attempt == 1) { ctx->err = "record buffer overflow"; return JX_EINTERNAL; }
   }
-  for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
+  if (!held) for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
   out.n_lines = (uint32_t)out.stats[0];
   ctx->tok_lines += (int64_t)out.stats[0];
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
@@ -452,3 +456,43 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   }
   return JX_OK;
 }
+
+extern "C" {
+
+int jx_text_release(jx_ctx* ctx) {
+  if (!ctx) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->held_text) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
+    ctx->held_events.clear();
+    cudaFree(ctx->held_text);
+    ctx->held_text = nullptr;
+    ctx->held_n = 0;
+  }
+  return JX_OK;
+}
+
+int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t* device_ptr) {
+  if (!ctx || !device_ptr || nbytes < 0 || (nbytes && !host_text)) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  jx_text_release(ctx);
+  constexpr int64_t CHUNK = 64ll << 20;
+  uint8_t* buf = nullptr;
+  JX_CK(cudaMalloc((void**)&buf, (size_t)nbytes + 16));
+  for (int64_t off = 0; off < nbytes; off += CHUNK) {
+    const int64_t len = std::min(CHUNK, nbytes - off);
+    JX_CK(cudaMemcpyAsync(buf + off, host_text + off, (size_t)len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    cudaEvent_t ev;
+    JX_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    JX_CK(cudaEventRecord(ev, ctx->copy_stream));
+    ctx->held_events.push_back(ev);
+  }
+  ctx->held_text = buf;
+  ctx->held_n = nbytes;
+  *device_ptr = (uint64_t)(uintptr_t)buf;
+  return JX_OK;
+}
+
+}  // extern "C"

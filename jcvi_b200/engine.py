@@ -15,8 +15,17 @@ _ERR = {
 }
 
 
+class DeviceText(object):
+    """Text held on the device by Engine.upload (jx_text_upload)."""
+
+    def __init__(self, ptr, nbytes, keep):
+        self.ptr, self.nbytes, self._keep = ptr, nbytes, keep
+
+
 def _text_ptr(text):
     """-> (pointer, nbytes, on_device, keepalive)."""
+    if isinstance(text, DeviceText):
+        return text.ptr, text.nbytes, 1, text
     if hasattr(text, "data_ptr") and hasattr(text, "is_cuda"):          # torch tensor
         t = text.contiguous()
         return t.data_ptr(), t.numel() * t.element_size(), int(t.is_cuda), t
@@ -39,11 +48,22 @@ class FilterResult(object):
         self.s_rank = C.as_np(r.s_rank, n, np.int32)
         self.score = C.as_np(r.score, n, np.float32)
         self.line_off = C.as_np(r.line_off, n, np.uint64)
-        self.text = ctypes.string_at(r.text, r.text_len) if r.text else None
+        # zero-copy view of the library-owned `.filtered` bytes; freed with this object
+        self._raw, self._lib = r, lib
+        self.text = (np.ctypeslib.as_array(ctypes.cast(r.text, C.c_u8p), shape=(max(r.text_len, 1),))[: r.text_len]
+                     if r.text else None)
         self.q_mother = C.as_np(r.q_mother, Gq, np.int32) if want_mothers else None
         self.s_mother = C.as_np(r.s_mother, Gs, np.int32) if want_mothers else None
         self.stats = dict(zip(("lines", "mapped", "unmapped", "after_exclude", "after_cscore", "after_dedupe",
                                "after_tandem", "comments"), list(r.stats)))
+
+
+    def __del__(self):
+        raw = getattr(self, "_raw", None)
+        if raw is not None:
+            self.text = None
+            self._lib.jx_filter_result_free(ctypes.byref(raw))
+            self._raw = None
 
 
 class ScanResult(object):
@@ -134,6 +154,19 @@ class Engine(object):
         self._beds = (qbed, sbed)          # keep alive: the cache key uses id()
         self.Gq, self.Gs = tq["G"], ts["G"]
 
+    def upload(self, text):
+        """Start the asynchronous upload of a host text; the returned DeviceText can be handed to
+        blastfilter / scan_text / liftover_text, which overlap tokenizing with the copy."""
+        p, n, dev, keep = _text_ptr(text)
+        if dev:
+            raise ValueError("text is already on the device")
+        out = ctypes.c_uint64()
+        self._check(self.lib.jx_text_upload(self.ctx, p, n, ctypes.byref(out)))
+        return DeviceText(out.value, n, keep)
+
+    def release_text(self):
+        self._check(self.lib.jx_text_release(self.ctx))
+
     # ---- stages ---------------------------------------------------------------------------------
     def blastfilter(self, text, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None, want_text=True,
                     want_mothers=False, raw=False):
@@ -156,10 +189,7 @@ class Engine(object):
             self._check(rc)
         if raw:
             return r          # caller frees with free_filter()
-        try:
-            return FilterResult(r, self.lib, self.Gq, self.Gs, want_mothers)
-        finally:
-            self.lib.jx_filter_result_free(ctypes.byref(r))
+        return FilterResult(r, self.lib, self.Gq, self.Gs, want_mothers)   # owns and frees `r`
 
     def free_filter(self, r):
         self.lib.jx_filter_result_free(ctypes.byref(r))

@@ -75,6 +75,34 @@ def test_tie_heavy_liftover(tmp_path, mods):
               scan_args=["--min_size=2", "--dist=2"], lift_args=["--dist=14"])
 
 
+def test_writer_declined_lines_are_spliced(tmp_path, mods):
+    """Lines the device writer declines (decimal rounding ties in the evalue, integers beyond
+    int32, 17-digit percent identities) are formatted by the host's glibc and spliced in place."""
+    import oracle
+    from jcvi_b200 import synth
+    bf, _ = mods
+    d = str(tmp_path)
+    qbed, sbed, last = synth.write_dataset(d, "A", "B", 31, 3000, 3000, 60000, Kq=4, Ks=4)
+    lines = open(last).read().split("\n")
+    out = []
+    for i, ln in enumerate(lines):
+        f = ln.split("\t")
+        if len(f) == 12:
+            if i % 5 == 0:
+                f[10] = "1.25e-%02d" % (12 + i % 40)          # tie at two significant digits
+            elif i % 5 == 1:
+                f[3] = "123456789012"                         # %d of a value beyond int32
+            elif i % 5 == 2:
+                f[10] = "3.45e-%02d" % (11 + i % 30)          # tie again, other parity
+        out.append("\t".join(f))
+    open(last, "w").write("\n".join(out))
+    oracle.blastfilter(last, qbed, sbed, out_path=last + ".orc", cscore=0.5)
+    bf.main([last, "--cscore=0.5"])
+    got, want = read(last + ".filtered"), read(last + ".orc")
+    assert got.count(b"1.2e-") + got.count(b"1.3e-") > 50       # the declined lines really survive the filters
+    assert got == want
+
+
 def test_empty_and_comment_only(tmp_path, mods):
     bf, syn = mods
     from jcvi_b200 import synth
