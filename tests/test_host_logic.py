@@ -1,0 +1,155 @@
+"""CPU tests of the host side: the C ABI library loads and exports what include/jcvi_b200.h
+declares, BED ranks agree with the oracle's restatement, AnchorFile/read_block semantics, argv
+handling, and the multi-rank sharding (gloo, world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_header_symbols():
+    import ctypes
+    from jcvi_b200 import _cabi
+    L = _cabi.lib()
+    header = open(os.path.join(ROOT, "include", "jcvi_b200.h")).read()
+    declared = set(re.findall(r"\b(jx_[a-z_0-9]+)\s*\(", header))
+    assert {"jx_ctx_create", "jx_blastfilter", "jx_scan_text", "jx_liftover_text", "jx_text_upload"} <= declared
+    for name in declared:
+        assert hasattr(L, name), "libjcvi_b200.so does not export %s" % name
+    assert set(_cabi.EXPORTS) == declared
+    assert b"sm_100a" in L.jx_version()
+    # struct layouts the Python side mirrors (sizes as the C compiler sees them)
+    assert ctypes.sizeof(_cabi.JxScanOpts) == 16
+    assert ctypes.sizeof(_cabi.JxFilterResult) == 8 * 9 + 64 + 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from jcvi_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(0)
+
+
+def test_bed_ranks_match_oracle(tmp_path):
+    import oracle
+    from jcvi_b200.formats.bed import Bed, natsort_key
+    p = tmp_path / "x.bed"
+    rng = np.random.default_rng(3)
+    rows = []
+    for k, seqid in enumerate(["chr10", "chr2", "chr1", "scaffold_9", "scaffold_10", "1", "02", "X", "chrUn.3"]):
+        pos = 0
+        for g in range(40):
+            pos += int(rng.integers(1, 500))
+            rows.append("%s\t%d\t%d\tg%02d_%03d\t0\t+" % (seqid, pos, pos + int(rng.integers(1, 900)), k, g))
+    rows.append("chr2\t5\t50\tdup_name\t0\t+")
+    rows.append("chr10\t7\t70\tdup_name\t0\t-")
+    rng.shuffle(rows)
+    p.write_text("# header\ntrack name=foo\n\n" + "\n".join(rows) + "\n")
+    bed = Bed(str(p))
+    out = tmp_path / "order.txt"
+    oracle.bed_order(str(p), str(out))
+    assert [b.accn for b in bed] == out.read_text().split()
+    assert natsort_key("chr10") > natsort_key("chr2") and natsort_key("1") < natsort_key("02") < natsort_key("X")
+    t = bed.tables()
+    assert t["G"] == len(rows) and t["n_chr"] == 9
+    assert t["indexable"].sum() == len(rows) - 1            # later duplicate wins (bed.py:196-198)
+    assert bed.order["dup_name"][0] == t["last"]["dup_name"]
+    # chr_lex is the byte order of the seqids (sorted(chr_pair) in batch_scan, synteny.py:444)
+    lex_of = {b.seqid: int(t["chr_lex"][i]) for i, b in enumerate(bed)}
+    assert [s_ for s_, _ in sorted(lex_of.items(), key=lambda kv: kv[1])] == sorted(lex_of, key=lambda s_: s_.encode())
+    assert (np.diff(t["chr_begin"]) >= 0).all()
+
+
+def test_bed_with_colliding_natsort_keys_is_refused(tmp_path):
+    from jcvi_b200.formats.bed import Bed
+    p = tmp_path / "y.bed"
+    p.write_text("chr1\t10\t20\ta\nchr01\t15\t25\tb\nchr1\t30\t40\tc\n")
+    with pytest.raises(NotImplementedError):
+        Bed(str(p)).tables()
+
+
+def test_anchorfile_matches_reference_fixture(golden):
+    # tests/compara/test_base.py:7-14 of the reference: 3 blocks, 14 pairs
+    from jcvi_b200.compara.base import AnchorFile
+    d, _ = golden("ref_fixtures")
+    ac = AnchorFile(os.path.join(d, "anchorfile_test.anchors"))
+    assert len(ac.blocks) == 3
+    assert len(list(ac.iter_pairs())) == 14
+    sizes = [len(b) for b in ac.blocks]
+    assert len(list(ac.iter_pairs(minsize=5))) == sum(n for n in sizes if n >= 5)
+
+
+def test_read_block_quirks(tmp_path):
+    from jcvi_b200.compara.base import AnchorFile
+    p = tmp_path / "q.anchors"
+    p.write_text("###\n###\na\tb\t1\n# note\nc\td\t2\n")
+    assert AnchorFile(str(p)).blocks == [[], [["a", "b", "1"]], [["c", "d", "2"]]]
+    p.write_text("a\tb\t1\nc\td\t2\n")                    # no header at all: one block
+    assert AnchorFile(str(p)).blocks == [[["a", "b", "1"], ["c", "d", "2"]]]
+    p.write_text("")
+    assert AnchorFile(str(p)).blocks == [[]]
+
+
+def test_get_bed_filenames_inference():
+    # tests/compara/test_synteny.py:23-40 of the reference
+    from argparse import Namespace
+    from jcvi_b200.compara.synteny import get_bed_filenames
+    o = Namespace(qbed=None, sbed=None)
+    assert get_bed_filenames("dir/grape.peach.last", None, o) == ("dir/grape.bed", "dir/peach.bed")
+    o = Namespace(qbed="x.bed", sbed="y.bed")
+    assert get_bed_filenames("a.b.last", None, o) == ("x.bed", "y.bed")
+
+
+def test_cli_misuse_exits_like_the_reference():
+    from jcvi_b200.compara import blastfilter, synteny
+    with pytest.raises(SystemExit):
+        blastfilter.main([])
+    with pytest.raises(SystemExit):
+        synteny.scan(["only_one_arg"])
+
+
+def test_assign_pairs_is_a_balanced_partition():
+    from jcvi_b200.parallel import assign_pairs
+    sizes = [90, 10, 50, 50, 40, 5, 5, 70, 30, 1]
+    for world in (1, 2, 4, 8):
+        parts = assign_pairs(sizes, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(sizes)))
+        loads = [sum(sizes[i] for i in p) for p in parts]
+        assert max(loads) <= sum(sizes) / world + max(sizes)
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from jcvi_b200.parallel import assign_pairs, max_over_ranks, rank_world
+dist.init_process_group("gloo")
+rank, world = rank_world()
+sizes = [90, 10, 50, 50, 40, 5, 5, 70, 30, 1]
+mine = assign_pairs(sizes, world)[rank]
+t = max_over_ranks(1.0 + rank)
+got = [None] * world
+dist.all_gather_object(got, mine)
+if rank == 0:
+    assert sorted(i for p in got for i in p) == list(range(len(sizes))), got
+    assert t == float(world), t
+    print("GLOO_OK", got)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout

@@ -65,7 +65,7 @@ def _decimals(rng, n):
 def test_float32_parse_matches_strtof(probe):
     rng = np.random.default_rng(1)
     n_ok = n_hard = 0
-    for s in _decimals(rng, 200000) + ["0", "0.0", "-0", "54.0", "1.06e+03", "1e+05", "100", "+7.5", ".5", "5.",
+    for s in _decimals(rng, 80000) + ["0", "0.0", "-0", "54.0", "1.06e+03", "1e+05", "100", "+7.5", ".5", "5.",
                                       "16777217", "33554433", "1e38", "3.5e38", "1234.5678", "0.1", "99999",
                                       "54.000000000000000"]:
         out = ctypes.c_float()
@@ -98,7 +98,7 @@ def test_evalue_threshold_matches_strtod(probe):
     cases = ["1e-10", "1.0e-10", "9.9e-11", "9.99999e-11", "1.00001e-10", "0", "0.0", "1e-400", "1e-50", "2.5e-180",
              "1e400", "5", "0.001", "1e-9", "1e-11", "100e-12", "10e-11", "0.0000000001", "0.00000000009",
              "1234567890123456789012e-32", "1000000000000e-22", "999999999999e-22"]
-    for _ in range(100000):
+    for _ in range(40000):
         cases.append("%.*e" % (int(rng.integers(0, 6)), 10.0 ** rng.uniform(-200, 3)))
     for _ in range(20000):
         cases.append("%.*e" % (int(rng.integers(0, 8)), 1e-10 * rng.uniform(0.9, 1.1)))
