@@ -59,6 +59,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
   cudaFree(ctx->held_text);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+  cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc);
   for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
@@ -146,6 +147,7 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
   JX_CK(cudaStreamSynchronize(ctx->stream));
   d.loaded = true;
   ctx->pair_ready = false;
+  ctx->cache.valid = false;
   return JX_OK;
 }
 

@@ -56,10 +56,20 @@ struct jx_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
+  // records of the last jx_blastfilter pass over the held text, for jx_liftover_text
+  struct RecCache {
+    uint4* recs = nullptr; size_t recs_cap = 0;       // context-owned, grow-only
+    uint64_t* desc = nullptr; size_t desc_cap = 0;
+    bool valid = false;
+    const uint8_t* text = nullptr; int64_t nbytes = 0; int strip = 0;
+    int64_t ntiles = 0; uint32_t n_lines = 0;
+    unsigned long long stats[12] = {0};
+  } cache;
   char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text
   size_t pin_cap = 0;
   uint8_t* held_text = nullptr;
   int64_t held_n = 0;
+  int64_t held_cap = 0;
   std::vector<cudaEvent_t> held_events;
   int64_t tok_lines = 0;
   double tok_ms_acc = 0;
@@ -122,6 +132,7 @@ struct TokMode {
   uint32_t* best = nullptr;    // per name-id best score bits (filter_cscore pass 1) or null
   const uint64_t* excl = nullptr;
   int64_t n_excl = 0;
+  bool fill_cache = false;     // keep records/descriptors in ctx->cache (held text only)
 };
 struct TokOut {
   uint4* recs = nullptr;       // [n_lines]

@@ -89,6 +89,67 @@ __global__ void k_rowptr(const uint64_t* akey, uint32_t na, int sb, uint32_t G, 
   rowptr[g] = lo;
 }
 
+// occupancy bitmap over (q cell, s cell): a set bit means "an anchor may be within dist"
+__global__ void k_mark_cells(const uint64_t* akey, uint32_t na, int sb, int dist, int cshift, uint32_t nsc, uint32_t nqc,
+                             uint32_t* bitmap) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= na) return;
+  const uint64_t a = akey[t];
+  const int32_t x = (int32_t)(a >> sb), y = (int32_t)(a & ((1ull << sb) - 1));
+  const int32_t x0 = max(x - dist, 0) >> cshift, x1 = min((uint32_t)((x + dist) >> cshift), nqc - 1);
+  const int32_t y0 = max(y - dist, 0) >> cshift, y1 = min((uint32_t)((y + dist) >> cshift), nsc - 1);
+  for (int32_t cx = x0; cx <= x1; ++cx)
+    for (int32_t cy = y0; cy <= y1; ++cy) {
+      const uint64_t bit = (uint64_t)cx * nsc + (uint64_t)cy;
+      atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+    }
+}
+
+// is some anchor of the same chromosome pair at L1 distance < dist (0 included)?
+__device__ __forceinline__ bool anchor_within(int32_t x, int32_t y, int sb, const uint64_t* __restrict__ akey,
+                                              const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ qbeg,
+                                              const int32_t* __restrict__ qend, const int32_t* __restrict__ schr, int dist) {
+  const uint64_t smask = (1ull << sb) - 1;
+  const int32_t lo = max(x - (dist - 1), qbeg[x]), hi = min(x + dist - 1, qend[x] - 1);
+  if (hi < lo) return false;
+  const uint32_t t0 = rowptr[lo], t1 = rowptr[hi + 1];
+  const int32_t cy = schr[y];
+  for (uint32_t u = t0; u < t1; ++u) {
+    const uint64_t a = akey[u];
+    const int32_t ax = (int32_t)(a >> sb), ay = (int32_t)(a & smask);
+    if (abs(ax - x) + abs(ay - y) < dist && schr[ay] == cy) return true;
+  }
+  return false;
+}
+
+// raw records -> the few that can matter to liftover: hits within dist of an anchor (the
+// anchors themselves included: AnchorFile.filter_blocks needs their raw scores)
+__global__ void k_select_near(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bitmap, int cshift,
+                              uint32_t nsc, int sb, const uint64_t* __restrict__ akey, const uint32_t* __restrict__ rowptr,
+                              const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
+                              const int32_t* __restrict__ schr, int dist, uint4* out, uint32_t* out_idx, uint32_t* counter,
+                              unsigned long long* nvalid) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t nround = (n + 31u) & ~31u;
+  uint32_t valid = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
+    if (i < n) r = __ldcs(recs + i);
+    bool keep = r.x != JX_NOREC;
+    if (keep) {
+      ++valid;
+      const uint64_t bit = (uint64_t)(r.x >> cshift) * nsc + (uint64_t)(r.y >> cshift);
+      keep = (__ldg(bitmap + (bit >> 5)) >> (bit & 31)) & 1u;
+      if (keep) keep = anchor_within((int32_t)r.x, (int32_t)r.y, sb, akey, rowptr, qbeg, qend, schr, dist);
+    }
+    uint32_t slot = warp_append(keep, counter);
+    if (keep) { out[slot] = r; out_idx[slot] = i; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xFFFFFFFFu, valid, o);
+  if ((threadIdx.x & 31) == 0 && valid) atomicAdd(nvalid, (unsigned long long)valid);
+}
+
 // exact minimum L1 distance (< dist) to the anchors of the same chromosome pair
 __global__ void k_nearest(const uint64_t* __restrict__ hkey, uint32_t nh, int sb, const uint64_t* __restrict__ akey,
                           const uint32_t* __restrict__ ablock, const uint32_t* __restrict__ rowptr,
@@ -381,46 +442,32 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   const uint32_t nal = (uint32_t)n_lines64;
   int rc;
 
-  // ---- raw hits: tokenizer -> unique (qi,si), first occurrence -----------------------------------
-  TokMode mode;
-  mode.strip = strip_names;
-  mode.neardiag = ctx->is_self ? 1 : 0;
-  TokOut tok;
-  if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
-  out->stats[0] = (int64_t)(tok.stats[0] - tok.stats[1]);
-  out->stats[5] = (int64_t)tok.stats[1];
-  const size_t capC = (size_t)tok.stats[2] + 1;
-  JX_ALLOC(C, uint4, capC, false);
-  JX_ALLOC(Cidx, uint32_t, capC, false);
-  JX_ALLOC(d_cnt, uint32_t, 1, true);
-  if (tok.n_lines) {
-    unsigned grid = std::min<unsigned>(nblk(tok.n_lines), 148u * 16u);
-    JX_LAUNCH(k_select_valid, grid, 256, 0, tok.recs, tok.n_lines, C, Cidx, d_cnt);
-  }
-  uint32_t nC = 0;
-  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
   const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
-  uint32_t nh = 0;
-  uint64_t* hkey = nullptr; float* hsc = nullptr; uint32_t* hline = nullptr;
-  if (nC) {
-    JX_ALLOC(keys, uint64_t, nC, false);
-    JX_ALLOC(vals, uint32_t, nC, false);
-    JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
-    uint64_t* ks = keys; uint32_t* vs = vals;
-    if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
-    JX_ALLOC(flag, uint32_t, nC, false);
-    JX_ALLOC(pick, uint32_t, nC, false);
-    JX_LAUNCH(k_run_first, nblk(nC), 256, 0, ks, vs, Cidx, nC, flag, pick);
-    uint32_t* pos;
-    if ((rc = compact_positions(ctx, arena, flag, nC, pos, nh))) return rc;
-    JX_ALLOC(hk, uint64_t, nh, false);
-    JX_ALLOC(hs, float, nh, false);
-    JX_ALLOC(hl, uint32_t, nh, false);
-    JX_LAUNCH(k_scatter_hits, nblk(nC), 256, 0, ks, pick, flag, pos, nC, C, Cidx, hk, hs, hl);
-    hkey = hk; hsc = hs; hline = hl;
+
+  // ---- raw records: reuse the ones jx_blastfilter just produced from the same held text (the
+  // reference parses the raw table twice: blastfilter.py:48 and synteny.py:1939), else tokenize
+  const uint4* recs = nullptr; uint32_t n_lines = 0;
+  unsigned long long tstats[12];
+  {
+    auto& c = ctx->cache;
+    if (c.valid && text_on_device && (const uint8_t*)text == c.text && nbytes == c.nbytes && (strip_names != 0) == (c.strip != 0) &&
+        !ctx->is_self) {
+      recs = c.recs; n_lines = c.n_lines;
+      memcpy(tstats, c.stats, sizeof tstats);
+      c.valid = false;                      // one-shot: the next pipeline pass tokenizes again
+    } else {
+      TokMode mode;
+      mode.strip = strip_names;
+      mode.neardiag = ctx->is_self ? 1 : 0;
+      TokOut tok;
+      if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+      recs = tok.recs; n_lines = tok.n_lines;
+      memcpy(tstats, tok.stats, sizeof tstats);
+    }
   }
-  out->stats[1] = nh;
+  out->stats[0] = (int64_t)(tstats[0] - tstats[1]);
+  out->stats[5] = (int64_t)tstats[1];
+  out->stats[1] = (int64_t)tstats[2];        // mapped raw records (before pair de-duplication)
 
   // ---- anchors ------------------------------------------------------------------------------------------
   out->accepted = (uint8_t*)calloc((size_t)nal + 1, 1);
@@ -435,23 +482,12 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   }
   const uint32_t na = (uint32_t)akeys_h.size();
   out->stats[2] = na;
-  JX_ALLOC(daq, int32_t, nal, false);
-  JX_ALLOC(das, int32_t, nal, false);
-  JX_ALLOC(dacc, uint8_t, nal, false);
-  JX_ALLOC(draw, float, nal, false);
-  if (nal) {
-    JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_LAUNCH(k_lookup, nblk(nal), 256, 0, hkey, hsc, nh, daq, das, nal, sb, dacc, draw);
-    JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  }
   auto alloc_out = [&](uint32_t n) {
     out->q_rank = (int32_t*)malloc(4 * ((size_t)n + 1)); out->s_rank = (int32_t*)malloc(4 * ((size_t)n + 1));
     out->score = (float*)malloc(4 * ((size_t)n + 1)); out->block = (int32_t*)malloc(4 * ((size_t)n + 1));
     out->n_lifted = n;
   };
-  if (!na || !nh) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
+  if (!na || !tstats[2]) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
 
   // sort anchors by (qi, si) on the device; detect duplicates (read_anchors' assert)
   JX_ALLOC(akey, uint64_t, na, false);
@@ -479,6 +515,60 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_CK(cudaMemcpyAsync(dablock, ablock_sorted.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
   JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
   JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
+
+  // ---- raw records -> candidates near an anchor -> unique (qi,si), first occurrence ------------------------
+  int cshift = 5;                                          // 32 x 32 rank cells, coarser for huge genomes
+  while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
+  const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
+  const size_t nwords = (size_t)(((uint64_t)nqc * nsc + 31) >> 5);
+  JX_ALLOC(bitmap, uint32_t, nwords, true);
+  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist, cshift, nsc, nqc, bitmap);
+  const size_t capC = (size_t)tstats[2] + 1;
+  JX_ALLOC(C, uint4, capC, false);
+  JX_ALLOC(Cidx, uint32_t, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 1, true);
+  JX_ALLOC(d_nvalid, unsigned long long, 1, true);
+  if (n_lines) {
+    unsigned grid = std::min<unsigned>(nblk(n_lines), 148u * 16u);
+    JX_LAUNCH(k_select_near, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex,
+              dist, C, Cidx, d_cnt, d_nvalid);
+  }
+  uint32_t nC = 0;
+  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  uint32_t nh = 0;
+  uint64_t* hkey = nullptr; float* hsc = nullptr; uint32_t* hline = nullptr;
+  if (nC) {
+    JX_ALLOC(keys, uint64_t, nC, false);
+    JX_ALLOC(vals, uint32_t, nC, false);
+    JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
+    uint64_t* ks = keys; uint32_t* vs = vals;
+    if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
+    JX_ALLOC(flag, uint32_t, nC, false);
+    JX_ALLOC(pick, uint32_t, nC, false);
+    JX_LAUNCH(k_run_first, nblk(nC), 256, 0, ks, vs, Cidx, nC, flag, pick);
+    uint32_t* pos;
+    if ((rc = compact_positions(ctx, arena, flag, nC, pos, nh))) return rc;
+    JX_ALLOC(hk, uint64_t, nh, false);
+    JX_ALLOC(hs, float, nh, false);
+    JX_ALLOC(hl, uint32_t, nh, false);
+    JX_LAUNCH(k_scatter_hits, nblk(nC), 256, 0, ks, pick, flag, pos, nC, C, Cidx, hk, hs, hl);
+    hkey = hk; hsc = hs; hline = hl;
+  }
+
+  // accepted[(query, subject)] for every anchor line
+  JX_ALLOC(daq, int32_t, nal, false);
+  JX_ALLOC(das, int32_t, nal, false);
+  JX_ALLOC(dacc, uint8_t, nal, false);
+  JX_ALLOC(draw, float, nal, false);
+  if (nal) {
+    JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_LAUNCH(k_lookup, nblk(nal), 256, 0, hkey, hsc, nh, daq, das, nal, sb, dacc, draw);
+    JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (!nh) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
 
   // ---- nearest anchor per hit -------------------------------------------------------------------------------
   JX_ALLOC(best_a, uint32_t, nh, false);

@@ -391,14 +391,41 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   // (every byte a line) only if that guess overflows.
   JX_ALLOC(d_stats, unsigned long long, 12, true);
   JX_ALLOC(d_ticket, uint32_t, 1, true);
-  JX_ALLOC(d_desc, uint64_t, (size_t)ntiles, true);
+  const bool to_cache = mode.fill_cache && held && !ctx->is_self && mode.n_excl == 0 && !mode.neardiag;
+  ctx->cache.valid = false;
+  uint64_t* d_desc = nullptr;
+  if (to_cache) {
+    if (ctx->cache.desc_cap < (size_t)ntiles + 1) {
+      if (ctx->cache.desc) cudaFree(ctx->cache.desc);
+      ctx->cache.desc = nullptr; ctx->cache.desc_cap = 0;
+      JX_CK(cudaMalloc((void**)&ctx->cache.desc, ((size_t)ntiles + 1) * sizeof(uint64_t)));
+      ctx->cache.desc_cap = (size_t)ntiles + 1;
+    }
+    d_desc = ctx->cache.desc;
+    JX_CK(cudaMemsetAsync(d_desc, 0, ((size_t)ntiles + 1) * sizeof(uint64_t), ctx->stream));
+  } else {
+    JX_ALLOC(dd, uint64_t, (size_t)ntiles, true);
+    d_desc = dd;
+  }
   out.desc = d_desc;
   const SideDev& Q = ctx->side[0];
   const SideDev& S = ctx->side[1];
   for (int attempt = 0; attempt < 2; ++attempt) {
     uint64_t cap64 = attempt == 0 ? (uint64_t)(nbytes / 20 + 1024) : (uint64_t)nbytes + 1;
     if (cap64 > 0xFFFFFFF0ull) { ctx->err = "more than 2^32 lines in one text"; return JX_EARG; }
-    JX_ALLOC(recs, uint4, (size_t)cap64, false);
+    uint4* recs = nullptr;
+    if (to_cache) {
+      if (ctx->cache.recs_cap < (size_t)cap64) {
+        if (ctx->cache.recs) cudaFree(ctx->cache.recs);
+        ctx->cache.recs = nullptr; ctx->cache.recs_cap = 0;
+        JX_CK(cudaMalloc((void**)&ctx->cache.recs, (size_t)cap64 * sizeof(uint4)));
+        ctx->cache.recs_cap = (size_t)cap64;
+      }
+      recs = ctx->cache.recs;
+    } else {
+      JX_ALLOC(rr, uint4, (size_t)cap64, false);
+      recs = rr;
+    }
     out.recs = recs;
     if (attempt) {
       JX_CK(cudaMemsetAsync(d_stats, 0, 12 * sizeof(unsigned long long), ctx->stream));
@@ -443,6 +470,11 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   if (!held) for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
   out.n_lines = (uint32_t)out.stats[0];
   ctx->tok_lines += (int64_t)out.stats[0];
+  if (to_cache && !out.stats[4] && !out.stats[5] && !out.stats[10] && !out.stats[11]) {
+    auto& c = ctx->cache;
+    c.valid = true; c.text = d_text; c.nbytes = nbytes; c.strip = mode.strip; c.ntiles = ntiles; c.n_lines = out.n_lines;
+    memcpy(c.stats, out.stats, sizeof c.stats);
+  }
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
   if (out.stats[5]) {
     ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +
@@ -462,6 +494,7 @@ extern "C" {
 int jx_text_release(jx_ctx* ctx) {
   if (!ctx) return JX_EARG;
   cudaSetDevice(ctx->device);
+  ctx->cache.valid = false;
   if (ctx->held_text) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
@@ -470,6 +503,7 @@ int jx_text_release(jx_ctx* ctx) {
     cudaFree(ctx->held_text);
     ctx->held_text = nullptr;
     ctx->held_n = 0;
+    ctx->held_cap = 0;
   }
   return JX_OK;
 }
@@ -477,10 +511,22 @@ int jx_text_release(jx_ctx* ctx) {
 int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t* device_ptr) {
   if (!ctx || !device_ptr || nbytes < 0 || (nbytes && !host_text)) return JX_EARG;
   cudaSetDevice(ctx->device);
-  jx_text_release(ctx);
+  ctx->cache.valid = false;
   constexpr int64_t CHUNK = 64ll << 20;
-  uint8_t* buf = nullptr;
-  JX_CK(cudaMalloc((void**)&buf, (size_t)nbytes + 16));
+  if (ctx->held_text && ctx->held_cap >= nbytes + 16) {
+    // reuse the allocation: earlier work on it must have finished before it is overwritten
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->copy_stream));
+    for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
+    ctx->held_events.clear();
+  } else {
+    jx_text_release(ctx);
+    uint8_t* buf = nullptr;
+    JX_CK(cudaMalloc((void**)&buf, (size_t)nbytes + 16));
+    ctx->held_text = buf;
+    ctx->held_cap = nbytes + 16;
+  }
+  uint8_t* buf = ctx->held_text;
   for (int64_t off = 0; off < nbytes; off += CHUNK) {
     const int64_t len = std::min(CHUNK, nbytes - off);
     JX_CK(cudaMemcpyAsync(buf + off, host_text + off, (size_t)len, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -489,7 +535,6 @@ int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t*
     JX_CK(cudaEventRecord(ev, ctx->copy_stream));
     ctx->held_events.push_back(ev);
   }
-  ctx->held_text = buf;
   ctx->held_n = nbytes;
   *device_ptr = (uint64_t)(uintptr_t)buf;
   return JX_OK;
