@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjcvi_b200.so")
+LIB_PATH = os.environ.get("JCVI_B200_LIB") or os.path.join(_HERE, "libjcvi_b200.so")
 
 JX_OK, JX_ECUDA, JX_EARG, JX_EZERODIV, JX_EUNSUPPORTED, JX_EDUPANCHOR, JX_EINTERNAL = 0, -1, -2, -3, -4, -5, -6
 

@@ -158,4 +158,22 @@ int probe_fmt_line(const char* line, int n, char* out) {
   return k;
 }
 
+
+int probe_fast_line4(const char* buf, int s, int e, int* spans, float* score, int* eflag, int* strip_ends,
+                     unsigned long long* hashes) {
+  WordRd wr{(const unsigned char*)buf};
+  jx::LineTok t;
+  if (!jx::fast_line4(wr, s, e, t)) return 0;
+  spans[0] = t.qa; spans[1] = t.qb; spans[2] = t.sa; spans[3] = t.sb;
+  *score = t.score; *eflag = t.eflag;
+  jx::WordBytes<WordRd> B(wr);
+  for (int k = 0; k < 2; ++k) {
+    const int a = k ? t.sa : t.qa, b = k ? t.sb : t.qb;
+    jx::NameRegs nr; uint64_t h;
+    if (jx::name_to_regs(B, a, b, true, nr, h)) { strip_ends[k] = a + nr.len; hashes[k] = h; }
+    else { uint64_t h2; strip_ends[k] = jx::fast_strip_hash(B, a, b, true, h2); hashes[k] = h2; }
+  }
+  return 1;
+}
+
 }  // extern "C"

@@ -21,6 +21,9 @@
 //   w = (byte offset of the line inside its 8 KiB tile << 1) | (evalue < 1e-10)
 #define JX_NOREC 0xFFFFFFFFu
 
+#ifndef JX_TOK_MINBLOCKS
+#define JX_TOK_MINBLOCKS 8
+#endif
 constexpr int JX_TOK_THREADS = 128;
 constexpr int JX_SEG = 64;                               // bytes of the tile owned by one thread
 constexpr int JX_TILE = JX_TOK_THREADS * JX_SEG;         // 8192

@@ -13,6 +13,14 @@
 #else
 #define JX_HD inline
 #endif
+// Reconvergence point for code that the kernel runs with ALL 32 lanes of a warp (fast_line4 and
+// its helpers): after a data-dependent loop the lanes are brought back together explicitly,
+// because independent thread scheduling does not guarantee it.
+#if defined(__CUDA_ARCH__)
+#define JX_CONVERGE() __syncwarp()
+#else
+#define JX_CONVERGE() ((void)0)
+#endif
 
 namespace jx {
 
@@ -168,6 +176,13 @@ JX_HD uint32_t float_to_bits(float f) {
 #endif
 }
 
+JX_HD float pow10f_exact(int k) {   // 10^k exact in float for 0 <= k <= 10
+  const uint32_t bits = k == 0 ? 0x3F800000u : k == 1 ? 0x41200000u : k == 2 ? 0x42C80000u : k == 3 ? 0x447A0000u
+                      : k == 4 ? 0x461C4000u : k == 5 ? 0x47C35000u : k == 6 ? 0x49742400u : k == 7 ? 0x4B189680u
+                      : k == 8 ? 0x4CBEBC20u : k == 9 ? 0x4E6E6B28u : 0x501502F9u;
+  return bits_to_float(bits);
+}
+
 // exact round-to-nearest-even of the 128-bit integer (hi:lo) to float32
 JX_HD float u128_to_f32(uint64_t hi, uint64_t lo) {
   if (!hi && !lo) return 0.f;
@@ -206,7 +221,18 @@ JX_HD bool dec_to_f32(const Dec& d, float& out) {
   if (d.m == 0) { out = d.neg ? -0.f : 0.f; return !d.dropped; }
   if (d.dropped) return false;
   float r;
-  if (d.e10 >= 0) {
+  if (d.m < (1u << 24) && d.e10 <= 0 && d.e10 >= -10) {
+    // both operands exact in float32: one correctly rounded operation == strtof
+    const float fm = (float)(uint32_t)d.m;
+    if (d.e10 == 0) r = fm;
+    else {
+#if defined(__CUDA_ARCH__)
+      r = __fdiv_rn(fm, pow10f_exact(-d.e10));
+#else
+      r = fm / pow10f_exact(-d.e10);
+#endif
+    }
+  } else if (d.e10 >= 0) {
     if (d.e10 > 19) {
       if (d.e10 > 60) { r = bits_to_float(0x7F800000u); }
       else return false;
@@ -234,6 +260,15 @@ JX_HD bool dec_to_f32(const Dec& d, float& out) {
 JX_HD int dec_lt_1e10(const Dec& d) {
   if (d.m == 0) return 1;
   if (d.neg) return 1;
+  if (!d.dropped && d.m < 1000000000000000ull) {
+    // <= 15 significant digits: the decimal is at least 1e-15 (relative) away from 1e-10 unless it
+    // is >= 1e-10, so the comparison of the rounded doubles equals the comparison of the decimals:
+    // m * 10^e10 < 10^-10  <=>  m < 10^(-10 - e10)
+    const int k = -10 - d.e10;
+    if (k <= 0) return 0;
+    if (k >= 16) return 1;
+    return d.m < pow10_u64(k) ? 1 : 0;
+  }
   if (!d.dropped && d.m < (1ull << 53) && d.e10 >= -22 && d.e10 <= 22) {
     double v = d.e10 < 0 ? (double)d.m / pow10_exact(-d.e10) : (double)d.m * pow10_exact(d.e10);
     return v < 1e-10 ? 1 : 0;
@@ -346,9 +381,8 @@ struct NameHash {
   uint32_t h1, h2;
   JX_HD void init() { h1 = 0x2F0B4A87u; h2 = 0x9747B28Cu; }
   JX_HD void word(uint32_t w) {
-    uint32_t k = w * 0xCC9E2D51u; k = rotl32(k, 15); k *= 0x1B873593u;
-    h1 ^= k; h1 = rotl32(h1, 13); h1 = h1 * 5u + 0xE6546B64u;
-    h2 = (h2 + w) * 0x9E3779B1u;
+    h1 = (h1 ^ w) * 0x9E3779B1u;
+    h2 = (h2 + w) * 0x85EBCA77u; h2 ^= h2 >> 15;
   }
   JX_HD uint64_t finish(uint32_t len) {
     uint32_t a = fmix32(h1 ^ len), b = fmix32(h2 ^ (a + len));
@@ -459,11 +493,12 @@ JX_HD uint32_t swar_nondigit(uint32_t x) {           // 0x80 in every byte that 
   return ~(ge0 & ~gt9 & ~x) & 0x80808080u;
 }
 JX_HD int first_flag(uint32_t f) {                   // byte index (0..3) of the lowest 0x80 flag
-#if defined(__CUDA_ARCH__)
-  return (__ffs((int)f) - 1) >> 3;
-#else
-  return (__builtin_ctz(f)) >> 3;
-#endif
+  // ALU/FMA only: isolate the lowest flag, move it to bit 0 of its byte, table-by-multiply
+  const uint32_t x = (f & (0u - f)) >> 7;            // 1, 2^8, 2^16 or 2^24
+  return (int)((x * 0x00010203u) >> 24);
+}
+JX_HD int count_flags4(uint32_t f) {                 // number of 0x80 flags in the word (0..4)
+  return (int)((((f >> 7) & 0x01010101u) * 0x01010101u) >> 24);
 }
 
 // end of the name starting at p: first byte <= 0x20 must be a tab.  Returns the tab position or
@@ -596,16 +631,11 @@ JX_HD int count_flags(const W& wr, int a, int b, F fl) {
 }
 struct FlNonDigit { JX_HD uint32_t operator()(uint32_t x) const { return swar_nondigit(x); } };
 struct FlDot { JX_HD uint32_t operator()(uint32_t x) const { return swar_eq(x, 0x2E2E2E2Eu); } };
+struct FlCR { JX_HD uint32_t operator()(uint32_t x) const { return swar_eq(x, 0x0D0D0D0Du); } };
 template <class W>
 JX_HD int count_nondigit(const W& wr, int a, int b) { return b > a ? count_flags(wr, a, b, FlNonDigit()) : 0; }
 template <class W>
 JX_HD int count_eq(const W& wr, int a, int b, uint32_t) { return b > a ? count_flags(wr, a, b, FlDot()) : 0; }
-JX_HD float pow10f_exact(int k) {   // 10^k exact in float for 0 <= k <= 10
-  const uint32_t bits = k == 0 ? 0x3F800000u : k == 1 ? 0x41200000u : k == 2 ? 0x42C80000u : k == 3 ? 0x447A0000u
-                      : k == 4 ? 0x461C4000u : k == 5 ? 0x47C35000u : k == 6 ? 0x49742400u : k == 7 ? 0x4B189680u
-                      : k == 8 ? 0x4CBEBC20u : k == 9 ? 0x4E6E6B28u : 0x501502F9u;
-  return bits_to_float(bits);
-}
 
 // evalue field [a,b): decides (value < 1e-10) for the shapes BLAST/LAST print; false = not handled.
 // One uniform loop over the characters with a 4-state machine (lanes stay converged).
@@ -770,6 +800,210 @@ JX_HD int fast_strip_hash(const WordBytes<W>& B, int a, int b, bool strip, uint6
     strip = false;   // second pass: plain hash of [a, end)
   }
   return end;
+}
+
+
+// ---- fast path, version 4 ---------------------------------------------------------------------
+// Five events instead of twelve: the two name ends and the end of pctid are found walking
+// forward, the last two tabs walking backward from the end of the line; the seven integer fields
+// in between are validated by counting (every non-digit byte must be a tab, six of them, never
+// adjacent), which is one uniform loop over ~8 words.
+JX_HD int last_flag(uint32_t f) {                    // byte index (0..3) of the highest 0x80 flag
+  return (f & 0x80000000u) ? 3 : (f & 0x00800000u) ? 2 : (f & 0x00008000u) ? 1 : 0;
+}
+// NOTE on control flow: every loop below has a single exit and the function has a single return.
+// With independent thread scheduling a `return`/`break` out of a loop leaves the lanes of a warp
+// diverged for the rest of the line (measured: 13 active lanes instead of 25), so validity is
+// accumulated in `ok` and all reads are clamped to the line instead of bailing out early.
+
+// last tab in [lo, hi), -1 if none
+template <class W>
+JX_HD int prev_tab(const W& wr, int hi, int lo) {
+  int res = -2;
+  uint32_t keep = 0x80808080u & (0xFFFFFFFFu >> (8 * (3 - ((hi - 1) & 3))));
+  for (int q = (hi - 1) & ~3; q + 4 > lo && res == -2; q -= 4) {
+    const uint32_t f = swar_eq(wr(q >> 2), 0x09090909u) & keep;
+    keep = 0x80808080u;
+    if (f) { const int pos = q + last_flag(f); res = pos >= lo ? pos : -1; }
+  }
+  JX_CONVERGE();
+  return res == -2 ? -1 : res;
+}
+// first byte <= 0x20 in [lo, hi): position, or hi when none
+template <class W>
+JX_HD int next_low(const W& wr, int lo, int hi) {
+  int res = -1;
+  uint32_t keep = 0x80808080u & (0xFFFFFFFFu << (8 * (lo & 3)));
+  for (int q = lo & ~3; q < hi && res < 0; q += 4) {
+    const uint32_t f = swar_le20(wr(q >> 2)) & keep;
+    keep = 0x80808080u;
+    if (f) { const int pos = q + first_flag(f); res = pos < hi ? pos : hi; }
+  }
+  JX_CONVERGE();
+  return res < 0 ? hi : res;
+}
+
+#if defined(__CUDACC__)
+#define JX_COLD __host__ __device__ __noinline__
+#else
+#define JX_COLD
+#endif
+// rare: the uniform state machines declined; generic scanner, kept out of line
+template <class BR>
+JX_COLD bool slow_evalue(const BR& B, int ea, int eb, int& flag) {
+  Dec d;
+  const int p2 = scan_decimal(B, ea, eb, d);
+  const int lt = dec_lt_1e10(d);
+  flag = lt;
+  return !d.special && d.ok && p2 == eb && lt >= 0;
+}
+template <class BR>
+JX_COLD bool slow_score(const BR& B, int sa, int e1, float& score) {
+  Dec d;
+  scan_decimal(B, sa, e1, d);
+  return !d.special && d.ok && dec_to_f32(d, score);
+}
+
+// s = first byte of the line, e = position of its '\n' (e > s).  All words up to (e + 4) must be
+// readable.
+template <class W>
+JX_HD bool fast_line4(const W& wr, int s, int e, LineTok& t) {
+  const WordBytes<W> B(wr);
+  t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false; t.qbar = t.sbar = -2;
+  if (e > s && B(e - 1) == '\r') --e;                // CR LF: the CR is trailing whitespace
+  bool ok = e - s >= 23;
+  const int e1 = ok ? e : s + 1;                     // keep every position inside the line when !ok
+  // ---- forward: the two names and pctid ---------------------------------------------------------
+  const int t1 = next_low(wr, s, e1);
+  ok &= (t1 > s) & (t1 < e1) & (t1 - s < 128);
+  const int a2 = t1 + 1 < e1 ? t1 + 1 : e1 - 1;
+  const int t2 = next_low(wr, a2, e1);
+  ok &= (t2 > a2) & (t2 < e1) & (t2 - a2 < 128);
+  const int a3 = t2 + 1 < e1 ? t2 + 1 : e1 - 1;
+  const int t3 = next_low(wr, a3, e1);
+  ok &= (t3 > a3) & (t3 < e1);
+  ok &= (B(t1 < e1 ? t1 : s) == '\t') & (B(t2 < e1 ? t2 : s) == '\t') & (B(t3 < e1 ? t3 : s) == '\t');
+  // ---- backward: score and evalue ------------------------------------------------------------------
+  const int lo = t3 + 1 < e1 ? t3 + 1 : e1 - 1;
+  int t11 = prev_tab(wr, e1, lo);
+  ok &= t11 >= 0;
+  if (t11 < 0) t11 = e1 - 1;
+  int t10 = prev_tab(wr, t11 > lo ? t11 : lo + 1, lo);
+  ok &= t10 >= 0;
+  if (t10 < 0) t10 = lo;
+  ok &= (t11 - t10 >= 2) & (e1 - t11 >= 2);
+  // ---- pctid [a3, t3): digits with at most one '.' ------------------------------------------------
+  {
+    const int a = a3, b = t3 > a3 ? t3 : a3 + 1;
+    const int q0 = a >> 2, q1 = (b - 1) >> 2;
+    const uint32_t first = 0x80808080u & (0xFFFFFFFFu << (8 * (a & 3)));
+    const uint32_t last = 0x80808080u & (0xFFFFFFFFu >> (8 * (3 - ((b - 1) & 3))));
+    int nnd = 0; uint32_t bad = 0;
+    for (int q = q0; q <= q1; ++q) {
+      const uint32_t x = wr(q);
+      uint32_t m = 0x80808080u;
+      if (q == q0) m &= first;
+      if (q == q1) m &= last;
+      const uint32_t nd = swar_nondigit(x) & m;
+      bad |= nd ^ (swar_eq(x, 0x2E2E2E2Eu) & m);      // a non-digit that is not '.'
+      nnd += count_flags4(nd);
+    }
+    JX_CONVERGE();
+    ok &= (bad == 0) & (nnd <= 1) & (b - a - nnd >= 1);
+  }
+  // ---- the seven integers [t3+1, t10): non-digits == tabs, six of them, none adjacent ----------------
+  {
+    const int a = lo, b = t10 > lo ? t10 : lo + 1;
+    ok &= b - a >= 13;
+    const int q0 = a >> 2, q1 = (b - 1) >> 2;
+    const uint32_t first = 0x80808080u & (0xFFFFFFFFu << (8 * (a & 3)));
+    const uint32_t last = 0x80808080u & (0xFFFFFFFFu >> (8 * (3 - ((b - 1) & 3))));
+    int ntab = 0; uint32_t bad = 0, carry = 0;
+    // the byte before `a` is the tab t3: as the "previous byte" of a it sits in the carry (a at a
+    // word start) or one byte below a inside the first word
+    const uint32_t prevflag = (a & 3) ? (0x80u << (8 * ((a & 3) - 1))) : 0u;
+    carry = (a & 3) ? 0u : 0x80u;
+    for (int q = q0; q <= q1; ++q) {
+      const uint32_t x = wr(q);
+      uint32_t m = 0x80808080u;
+      if (q == q0) m &= first;
+      if (q == q1) m &= last;
+      const uint32_t nd = swar_nondigit(x) & m;
+      const uint32_t tb = swar_eq(x, 0x09090909u) & m;
+      const uint32_t tbp = (q == q0) ? (tb | prevflag) : tb;
+      bad |= nd ^ tb;                                 // a non-digit that is not a tab
+      bad |= ((tbp << 8) & tb) | (tb & carry);        // adjacent tabs inside / across words
+      carry = tb >> 24;
+      ntab += count_flags4(tb);
+    }
+    JX_CONVERGE();
+    ok &= (bad == 0) & (ntab == 6) & (B(b - 1) != '\t');
+  }
+  t.qa = s; t.qb = t1; t.sa = a2; t.sb = t2;
+  // ---- evalue, score (uniform state machines; the generic scanner only when they decline) ------------
+  {
+    const int ea = t10 + 1, eb = t11 > t10 + 1 ? t11 : t10 + 2;
+    int flag = 1;
+    bool done = fast_evalue(B, ea, eb, flag);
+    JX_CONVERGE();
+    if (ok && !done) done = slow_evalue(B, ea, eb, flag);
+    ok &= done;
+    t.eflag = flag;
+    const int sa = t11 + 1 < e1 ? t11 + 1 : e1 - 1;
+    JX_CONVERGE();
+    done = fast_score(B, sa, e1, t.score);
+    JX_CONVERGE();
+    if (ok && !done) done = slow_score(B, sa, e1, t.score);
+    ok &= done;
+    // junk after the score is ignored by sscanf, but a '\r' in it would be a line break for Python
+    JX_CONVERGE();
+    ok &= count_flags(wr, sa, e1, FlCR()) == 0;
+    JX_CONVERGE();
+  }
+  t.nconv = ok ? 12 : 0;
+  return ok;
+}
+
+// A name of <= 16 bytes held in four registers: strip, hash and (later) verify without touching
+// shared memory again.  Longer names use fast_strip_hash + the generic probe.
+struct NameRegs { uint32_t w[4]; int len; };
+
+template <class W>
+JX_HD bool name_to_regs(const WordBytes<W>& B, int a, int b, bool strip, NameRegs& n, uint64_t& h) {
+  if (b - a > 16 || b <= a) return false;
+  uint32_t w0 = B.load32(a), w1 = 0, w2 = 0, w3 = 0;
+  int len = b - a;
+  if (len > 4) w1 = B.load32(a + 4);
+  if (len > 8) w2 = B.load32(a + 8);
+  if (len > 12) w3 = B.load32(a + 12);
+  if (strip) {
+    // gene_name: cut at the first '|', then drop ".x" unless the name starts with "ev"
+    const uint32_t f0 = swar_eq(w0, 0x7C7C7C7Cu), f1 = swar_eq(w1, 0x7C7C7C7Cu), f2 = swar_eq(w2, 0x7C7C7C7Cu),
+                   f3 = swar_eq(w3, 0x7C7C7C7Cu);
+    int bar = f0 ? first_flag(f0) : f1 ? 4 + first_flag(f1) : f2 ? 8 + first_flag(f2) : f3 ? 12 + first_flag(f3) : 99;
+    if (bar < len) len = bar;
+    const bool ev = (b - a >= 2) && (w0 & 0xFFFFu) == 0x7665u;    // "ev"
+    if (!ev && len >= 2) {
+      const int i2 = len - 2;                                    // bytes len-2, len-1
+      const uint32_t wa = i2 < 4 ? w0 : i2 < 8 ? w1 : i2 < 12 ? w2 : w3;
+      const uint32_t wb = (i2 + 1) < 4 ? w0 : (i2 + 1) < 8 ? w1 : (i2 + 1) < 12 ? w2 : w3;
+      const uint32_t c2 = (wa >> (8 * (i2 & 3))) & 0xFFu, c1 = (wb >> (8 * ((i2 + 1) & 3))) & 0xFFu;
+      if (c2 == '.' && c1 != '.') len -= 2;
+    }
+  }
+  // zero the bytes beyond len
+  const uint32_t k0 = len >= 4 ? 0xFFFFFFFFu : (len <= 0 ? 0u : (1u << (8 * len)) - 1u);
+  const uint32_t k1 = len >= 8 ? 0xFFFFFFFFu : (len <= 4 ? 0u : (1u << (8 * (len - 4))) - 1u);
+  const uint32_t k2 = len >= 12 ? 0xFFFFFFFFu : (len <= 8 ? 0u : (1u << (8 * (len - 8))) - 1u);
+  const uint32_t k3 = len >= 16 ? 0xFFFFFFFFu : (len <= 12 ? 0u : (1u << (8 * (len - 12))) - 1u);
+  n.w[0] = w0 & k0; n.w[1] = w1 & k1; n.w[2] = w2 & k2; n.w[3] = w3 & k3; n.len = len;
+  NameHash nh; nh.init();
+  if (len > 0) nh.word(n.w[0]);
+  if (len > 4) nh.word(n.w[1]);
+  if (len > 8) nh.word(n.w[2]);
+  if (len > 12) nh.word(n.w[3]);
+  h = nh.finish((uint32_t)len);
+  return true;
 }
 
 }  // namespace jx

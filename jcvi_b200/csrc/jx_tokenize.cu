@@ -125,7 +125,7 @@ __device__ __forceinline__ uint32_t term_mask32(const uint32_t* w) {   // 8 word
   return m;
 }
 
-__global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(TokArgs a) {
+__global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   __shared__ __align__(16) uint32_t smw[JX_WIN / 4 + 8];
   __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
   __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per 64-byte segment
@@ -476,6 +476,11 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     memcpy(c.stats, out.stats, sizeof c.stats);
   }
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
+  if (out.stats[11]) {
+    ctx->err = "the text contains '\\r' line terminators that are not followed by '\\n' (classic Mac line endings); "
+               "not supported";
+    return JX_EUNSUPPORTED;
+  }
   if (out.stats[5]) {
     ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +
                " (overflows cblast.pyx's char[128]; undefined behaviour in the reference)";

@@ -164,7 +164,7 @@ def test_hash_is_stable(probe):
     assert h1 != h2 and probe.probe_hash(b"Ag000123x", 8) == h1
 
 
-@pytest.mark.parametrize("version", [2, 3])
+@pytest.mark.parametrize("version", [2, 3, 4])
 def test_fast_line_agrees_with_generic_scanner(probe, version):
     """The SWAR fast path (jx::fast_line) must either refuse a line or produce exactly what the
     generic sscanf-faithful scanner produces (spans, score bits, evalue flag, stripped name,
@@ -210,8 +210,10 @@ def test_fast_line_agrees_with_generic_scanner(probe, version):
             ends = (ctypes.c_int * 2)(); hs = (ctypes.c_ulonglong * 2)()
             if version == 2:
                 ok = probe.probe_fast_line(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
-            else:
+            elif version == 3:
                 ok = probe.probe_fast_line3(buf, s, len(buf), spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
+            else:
+                ok = probe.probe_fast_line4(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
             gsp = (ctypes.c_int * 4)(); gsc = ctypes.c_float(); gnc = ctypes.c_int(); gef = ctypes.c_int()
             fl = probe.probe_line(ln.encode(), len(ln), gsp, ctypes.byref(gsc), ctypes.byref(gnc), ctypes.byref(gef))
             if not ok:
