@@ -187,6 +187,30 @@ int jx_nearest_anchor(jx_ctx* ctx, const int64_t* points_xy, int64_t n_points,
                       const int64_t* anchors_xy, int64_t n_anchors, int dist, int64_t* nearest,
                       int64_t* dist_out);
 
+/* ---- one genome pair sharded over several GPUs ---------------------------------
+ * Every rank owns a slice of the raw table cut at line boundaries.  The only value blastfilter
+ * needs globally is filter_cscore's per-name best score (blastfilter.py:227-232):
+ *   1. jx_cscore_begin   tokenizes the slice and accumulates the rank-local best table; it returns
+ *                        the DEVICE address of that table (n_name_ids float32 values >= 0 stored
+ *                        as their bit patterns, which order like integers);
+ *   2. the caller max-reduces the tables in place across ranks (ncclAllReduce(ncclMax) on int32 /
+ *      torch.distributed.all_reduce(MAX) over NVLink);
+ *   3. jx_cscore_finish  applies the C-score predicate with the global table and returns the raw
+ *                        text lines of the slice that pass, in file order.
+ * Concatenating the returned lines in rank order and running jx_blastfilter on them with
+ * cscore = 0 gives exactly the unsharded `.filtered` (the later stages only see survivors).
+ * jx_near_lines is the same idea for liftover: the lines of a slice whose hit lies within `dist`
+ * (L1, same chromosome pair) of an anchor, anchors included; jx_liftover_text on the concatenation
+ * equals jx_liftover_text on the whole table.  Returned buffers are released with jx_free. */
+int jx_cscore_begin(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
+                    const uint64_t* exclude_keys, int64_t n_exclude, uint64_t* best_table_device_ptr,
+                    uint32_t* n_name_ids);
+int jx_cscore_finish(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_len, int64_t* n_lines);
+int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                  const int32_t* a_qi, const int32_t* a_si, int64_t n_anchor_lines, char** lines,
+                  int64_t* lines_len, int64_t* n_lines);
+void jx_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

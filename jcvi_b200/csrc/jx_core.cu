@@ -20,6 +20,8 @@ int upload(jx_ctx* ctx, T** dst, const T* src, size_t n) {
 
 extern "C" {
 
+void jx_free(void* p) { free(p); }
+
 const char* jx_version(void) { return "jcvi_b200 0.1 (sm_100a)"; }
 
 int jx_ctx_create(int device, jx_ctx** out) {
@@ -59,7 +61,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
   cudaFree(ctx->held_text);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
-  cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc);
+  cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);
   for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);

@@ -297,7 +297,144 @@ void format_range(const char* lines, const uint32_t* pos, const uint32_t* len, c
 
 }  // namespace
 
+namespace {
+__global__ void k_cscore_flags(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ best,
+                               const uint32_t* __restrict__ qnid, const uint32_t* __restrict__ snid, double cscore,
+                               int use_cscore, uint32_t* flags, uint32_t* errflag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 r = __ldcs(recs + i);
+  bool keep = r.x != JX_NOREC;
+  if (keep && use_cscore) {
+    double bq = (double)__uint_as_float(__ldg(best + __ldg(qnid + r.x)));
+    double bs = (double)__uint_as_float(__ldg(best + __ldg(snid + r.y)));
+    double den = bq > bs ? bq : bs;
+    if (den == 0.0) { atomicExch(errflag, 1u); keep = false; }
+    else keep = ((double)__uint_as_float(r.z) / den) > cscore;
+  }
+  flags[i] = keep;
+}
+__global__ void k_compact_idx(const uint32_t* flags, const uint32_t* pos, uint32_t n, uint32_t* idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) idx[pos[i]] = i;
+}
+__global__ void k_line_off(const uint32_t* idx, uint32_t cnt, const uint4* recs, const uint64_t* desc, int64_t ntiles, uint64_t* off) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  const uint64_t i = idx[t];
+  int64_t lo = 0, hi = ntiles - 1;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((desc[mid] & ((1ull << 62) - 1)) > i) hi = mid; else lo = mid + 1;
+  }
+  off[t] = (uint64_t)lo * JX_TILE + (recs[i].w >> 1);
+}
+}  // namespace
+
+int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
+                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len) {
+  *out = nullptr; *out_len = 0;
+  if (!cnt) { *out = (char*)calloc(1, 1); return JX_OK; }
+  int rc;
+  JX_ALLOC(off, uint64_t, cnt, false);
+  JX_ALLOC(len, uint32_t, cnt, false);
+  JX_ALLOC(pos, uint32_t, cnt, false);
+  JX_LAUNCH(k_line_off, nblk(cnt), 256, 0, rec_idx, cnt, recs, desc, ntiles, off);
+  JX_LAUNCH(k_line_len, nblk(cnt), 256, 0, d_text, nbytes, off, (const uint32_t*)nullptr, cnt, len);
+  if ((rc = jx_exclusive_sum(ctx, arena, len, pos, cnt))) return rc;
+  uint32_t h[2];
+  JX_CK(cudaMemcpyAsync(&h[0], pos + cnt - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&h[1], len + cnt - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  const uint64_t total = (uint64_t)h[0] + h[1];
+  if (total >= 0xFFFFFFF0ull) { ctx->err = "gathered lines exceed 4 GiB; use more ranks"; return JX_EUNSUPPORTED; }
+  JX_ALLOC(packed, uint8_t, (size_t)total, false);
+  JX_LAUNCH(k_copy_lines, nblk((size_t)cnt * 32), 256, 0, d_text, off, (const uint32_t*)nullptr, len, pos, cnt, packed);
+  char* host = (char*)malloc((size_t)total + 1);
+  JX_CK(cudaMemcpyAsync(host, packed, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  host[total] = 0;
+  *out = host; *out_len = (int64_t)total;
+  return JX_OK;
+}
+
 extern "C" {
+
+int jx_cscore_begin(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
+                    const uint64_t* exclude_keys, int64_t n_exclude, uint64_t* best_ptr, uint32_t* n_ids) {
+  if (!ctx || !best_ptr || !n_ids) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  ctx->sess_open = false;
+  int rc;
+  // the slice must outlive this call: hold it on the device (jx_text_upload) unless it already is
+  uint64_t dptr = 0;
+  if (!text_on_device) {
+    if ((rc = jx_text_upload(ctx, text, nbytes, &dptr))) return rc;
+  } else if (!(ctx->held_text && (const uint8_t*)text == ctx->held_text && nbytes == ctx->held_n)) {
+    ctx->err = "jx_cscore_begin: device text must come from jx_text_upload"; return JX_EARG;
+  } else dptr = (uint64_t)(uintptr_t)text;
+  Arena arena(ctx);
+  if (ctx->sess_best_cap < (size_t)ctx->n_name_ids + 1) {
+    cudaFree(ctx->sess_best); ctx->sess_best = nullptr; ctx->sess_best_cap = 0;
+    JX_CK(cudaMalloc((void**)&ctx->sess_best, ((size_t)ctx->n_name_ids + 1) * 4));
+    ctx->sess_best_cap = (size_t)ctx->n_name_ids + 1;
+  }
+  JX_CK(cudaMemsetAsync(ctx->sess_best, 0, ((size_t)ctx->n_name_ids + 1) * 4, ctx->stream));
+  TokMode mode;
+  mode.strip = strip_names;
+  mode.best = ctx->sess_best;
+  mode.persist = true;
+  JX_ALLOC(d_excl, uint64_t, (size_t)std::max<int64_t>(n_exclude, 1), false);
+  if (n_exclude > 0) {
+    JX_CK(cudaMemcpyAsync(d_excl, exclude_keys, (size_t)n_exclude * 8, cudaMemcpyHostToDevice, ctx->stream));
+    mode.excl = d_excl; mode.n_excl = n_exclude;
+  }
+  TokOut tok;
+  if ((rc = jx_run_tokenizer(ctx, arena, (const char*)(uintptr_t)dptr, nbytes, 1, mode, tok))) return rc;
+  if (!ctx->cache.valid) { ctx->err = "jx_cscore_begin: records were not retained"; return JX_EINTERNAL; }
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  ctx->sess_open = true;
+  *best_ptr = (uint64_t)(uintptr_t)ctx->sess_best;
+  *n_ids = ctx->n_name_ids;
+  return JX_OK;
+}
+
+int jx_cscore_finish(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_len, int64_t* n_lines) {
+  if (!ctx || !lines || !lines_len || !n_lines) return JX_EARG;
+  if (!ctx->sess_open || !ctx->cache.valid) { ctx->err = "jx_cscore_finish without jx_cscore_begin"; return JX_EARG; }
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  auto& c = ctx->cache;
+  const uint32_t n = c.n_lines;
+  *lines = nullptr; *lines_len = 0; *n_lines = 0;
+  int rc;
+  uint32_t cnt = 0;
+  uint32_t* idx = nullptr;
+  if (n) {
+    JX_ALLOC(flags, uint32_t, n, false);
+    JX_ALLOC(pos, uint32_t, n, false);
+    JX_ALLOC(err, uint32_t, 1, true);
+    JX_LAUNCH(k_cscore_flags, nblk(n), 256, 0, c.recs, n, ctx->sess_best, ctx->side[0].name_id, ctx->side[1].name_id, cscore,
+              cscore != 0.0 ? 1 : 0, flags, err);
+    if ((rc = jx_exclusive_sum(ctx, arena, flags, pos, n))) return rc;
+    uint32_t h[3];
+    JX_CK(cudaMemcpyAsync(&h[0], pos + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(&h[1], flags + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(&h[2], err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    if (h[2]) { ctx->err = "float division by zero"; return JX_EZERODIV; }
+    cnt = h[0] + h[1];
+    JX_ALLOC(ix, uint32_t, cnt, false);
+    if (cnt) JX_LAUNCH(k_compact_idx, nblk(n), 256, 0, flags, pos, n, ix);
+    idx = ix;
+  }
+  rc = jx_gather_lines(ctx, arena, c.text, c.nbytes, c.desc, c.ntiles, c.recs, idx, cnt, lines, lines_len);
+  if (rc) return rc;
+  *n_lines = cnt;
+  ctx->sess_open = false;
+  c.valid = false;
+  return JX_OK;
+}
 
 void jx_filter_result_free(jx_filter_result* r) {
   if (!r) return;

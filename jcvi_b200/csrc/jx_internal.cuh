@@ -68,6 +68,8 @@ struct jx_ctx {
     int64_t ntiles = 0; uint32_t n_lines = 0;
     unsigned long long stats[12] = {0};
   } cache;
+  uint32_t* sess_best = nullptr; size_t sess_best_cap = 0;   // jx_cscore_begin/finish session
+  bool sess_open = false;
   char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text
   size_t pin_cap = 0;
   uint8_t* held_text = nullptr;
@@ -136,6 +138,7 @@ struct TokMode {
   const uint64_t* excl = nullptr;
   int64_t n_excl = 0;
   bool fill_cache = false;     // keep records/descriptors in ctx->cache (held text only)
+  bool persist = false;        // like fill_cache but also for self comparisons / exclusions (sharded session)
 };
 struct TokOut {
   uint4* recs = nullptr;       // [n_lines]
@@ -150,6 +153,10 @@ struct TokOut {
 };
 int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
                      const TokMode& mode, TokOut& out);
+
+// raw text lines of the records rec_idx[0..cnt) (device array, file order) -> malloc'ed host buffer
+int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
+                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len);
 
 // ---- shared device helpers ---------------------------------------------------------------------
 #if defined(__CUDACC__)

@@ -665,6 +665,75 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   return JX_OK;
 }
 
+namespace {
+__global__ void k_widen_idx(const uint32_t* in, uint32_t n, uint64_t* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = in[t];
+}
+__global__ void k_narrow_idx(const uint64_t* in, uint32_t n, uint32_t* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (uint32_t)in[t];
+}
+}  // namespace
+
+int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                  const int32_t* a_qi, const int32_t* a_si, int64_t n_lines64, char** lines, int64_t* lines_len,
+                  int64_t* n_out) {
+  if (!ctx || !lines || !lines_len || !n_out || n_lines64 < 0 || n_lines64 >= (1ll << 31) || dist < 0) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  *lines = nullptr; *lines_len = 0; *n_out = 0;
+  int rc;
+  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+  TokMode mode;
+  mode.strip = strip_names;
+  mode.neardiag = ctx->is_self ? 1 : 0;
+  TokOut tok;
+  if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+  std::vector<uint64_t> akeys_h;
+  for (int64_t t = 0; t < n_lines64; ++t)
+    if (a_qi[t] >= 0 && a_si[t] >= 0 && a_qi[t] < Q.G && a_si[t] < S.G)
+      akeys_h.push_back(((uint64_t)(uint32_t)a_qi[t] << sb) | (uint32_t)a_si[t]);
+  const uint32_t na = (uint32_t)akeys_h.size();
+  if (!na || !tok.stats[2]) { *lines = (char*)calloc(1, 1); return JX_OK; }
+  JX_ALLOC(akey, uint64_t, na, false);
+  JX_CK(cudaMemcpyAsync(akey, akeys_h.data(), (size_t)na * 8, cudaMemcpyHostToDevice, ctx->stream));
+  uint64_t* aks = akey;
+  if ((rc = jx_sort_keys(ctx, arena, aks, na, 0, sb + qb))) return rc;
+  JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
+  JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
+  int cshift = 5;
+  while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
+  const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
+  JX_ALLOC(bitmap, uint32_t, (size_t)(((uint64_t)nqc * nsc + 31) >> 5), true);
+  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist, cshift, nsc, nqc, bitmap);
+  const size_t capC = (size_t)tok.stats[2] + 1;
+  JX_ALLOC(C, uint4, capC, false);
+  JX_ALLOC(Cidx, uint32_t, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 1, true);
+  JX_ALLOC(d_nvalid, unsigned long long, 1, true);
+  unsigned grid = std::min<unsigned>(nblk(tok.n_lines), 148u * 16u);
+  JX_LAUNCH(k_select_near, grid, 256, 0, tok.recs, tok.n_lines, bitmap, cshift, nsc, sb, aks, rowptr, Q.chr_begin, Q.chr_end,
+            S.chr_lex, dist, C, Cidx, d_cnt, d_nvalid);
+  uint32_t nC = 0;
+  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  // back to file order
+  JX_ALLOC(k64, uint64_t, nC, false);
+  JX_ALLOC(idx, uint32_t, nC, false);
+  if (nC) {
+    JX_LAUNCH(k_widen_idx, nblk(nC), 256, 0, Cidx, nC, k64);
+    uint64_t* ks = k64;
+    if ((rc = jx_sort_keys(ctx, arena, ks, nC, 0, 32))) return rc;
+    JX_LAUNCH(k_narrow_idx, nblk(nC), 256, 0, ks, nC, idx);
+  }
+  if ((rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, idx, nC, lines, lines_len))) return rc;
+  *n_out = nC;
+  return JX_OK;
+}
+
 int jx_nearest_anchor(jx_ctx* ctx, const int64_t* points_xy, int64_t n_points, const int64_t* anchors_xy,
                       int64_t n_anchors, int dist, int64_t* nearest, int64_t* dist_out) {
   if (!ctx || n_points < 0 || n_anchors < 0 || n_points >= (1ll << 31) || n_anchors >= (1ll << 31)) return JX_EARG;

@@ -258,6 +258,51 @@ class Engine(object):
                                                C.ptr(near), C.ptr(dd)))
         return near, dd
 
+    # ---- one genome pair sharded over ranks (see jcvi_b200/sharded.py) --------------------------------
+    def cscore_begin(self, text, strip_names=True, exclude_keys=None):
+        """Tokenize this rank's slice, accumulate the local per-name best scores.  Returns
+        (device pointer of the table, number of entries): int32-orderable float bits."""
+        p, n, dev, keep = _text_ptr(text)
+        ek = None
+        if exclude_keys is not None and len(exclude_keys):
+            ek = np.unique(np.asarray(exclude_keys, dtype=np.uint64))
+        ptr = ctypes.c_uint64(); nids = ctypes.c_uint32()
+        self._check(self.lib.jx_cscore_begin(self.ctx, p, n, dev, int(bool(strip_names)), C.ptr(ek), 0 if ek is None else len(ek),
+                                             ctypes.byref(ptr), ctypes.byref(nids)))
+        return ptr.value, nids.value
+
+    def best_table_tensor(self, ptr, n):
+        """torch int32 view of the device table (positive float bit patterns order like ints)."""
+        import torch
+
+        class _Dev(object):
+            pass
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(d, device="cuda:%d" % self.device)
+
+    def _take_lines(self, buf, ln):
+        try:
+            return np.ctypeslib.as_array(ctypes.cast(buf, C.c_u8p), shape=(max(ln.value, 1),))[: ln.value].copy()
+        finally:
+            self.lib.jx_free(buf)
+
+    def cscore_finish(self, cscore):
+        """-> (uint8 array of the slice's raw lines that pass the C-score filter, file order; count)."""
+        buf = ctypes.c_void_p(); ln = ctypes.c_int64(); cnt = ctypes.c_int64()
+        self._check(self.lib.jx_cscore_finish(self.ctx, float(cscore or 0.0), ctypes.byref(buf), ctypes.byref(ln), ctypes.byref(cnt)))
+        return self._take_lines(buf, ln), cnt.value
+
+    def near_lines(self, text, a_qi, a_si, strip_names=True, dist=10):
+        """-> (uint8 array of the raw lines whose hit lies within `dist` of an anchor; count)."""
+        p, n, dev, keep = _text_ptr(text)
+        a_qi = np.ascontiguousarray(a_qi, dtype=np.int32)
+        a_si = np.ascontiguousarray(a_si, dtype=np.int32)
+        buf = ctypes.c_void_p(); ln = ctypes.c_int64(); cnt = ctypes.c_int64()
+        self._check(self.lib.jx_near_lines(self.ctx, p, n, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si),
+                                           len(a_qi), ctypes.byref(buf), ctypes.byref(ln), ctypes.byref(cnt)))
+        return self._take_lines(buf, ln), cnt.value
+
     # ---- instrumentation ----------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.jx_launch_count(self.ctx))

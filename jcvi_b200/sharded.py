@@ -1,0 +1,83 @@
+"""One genome pair sharded over several GPUs (BASELINE config C3).
+
+Every rank tokenizes a byte range of the raw table cut at line boundaries.  blastfilter needs one
+global quantity, filter_cscore's per-name best score (src/jcvi/compara/blastfilter.py:227-232):
+the rank-local tables are max-reduced in place with an NCCL all-reduce over NVLink.  Each rank then
+keeps the lines of its slice that pass the C-score filter (~5 % of the table); their concatenation
+in rank order is in file order, and the remaining stages (pair de-duplication, tandem collapse,
+ordering, writer) on rank 0 see exactly what they would have seen unsharded.  liftover is sharded
+the same way with the "within dist of an anchor" predicate.  Outputs are byte-identical to the
+single-GPU path (tests/test_gpu_sharded.py; tools/check_sharded.py on 2 GPUs).
+"""
+import numpy as np
+
+from .engine import get_engine
+from .parallel import rank_world
+
+
+def slice_bounds(text, rank, world):
+    """[lo, hi) of rank's slice; cuts fall just after a '\\n' (lines never straddle ranks)."""
+    n = len(text)
+
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        p = n * r // world
+        nl = np.flatnonzero(text[p:p + (1 << 20)] == 10)
+        while len(nl) == 0 and p + (1 << 20) < n:
+            p += 1 << 20
+            nl = np.flatnonzero(text[p:p + (1 << 20)] == 10)
+        return n if len(nl) == 0 else p + int(nl[0]) + 1
+
+    return cut(rank), cut(rank + 1)
+
+
+def _gather_bytes(arr, dst=0):
+    import torch.distributed as dist
+    rank, world = rank_world()
+    if world == 1 or not dist.is_initialized():
+        return [arr]
+    out = [None] * world if rank == dst else None
+    dist.gather_object(arr, out, dst=dst)
+    return out
+
+
+def blastfilter_sharded(text, qbed, sbed, is_self, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None,
+                        want_text=True, engine=None):
+    """Collective over all ranks; returns the FilterResult on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = rank_world()
+    eng = engine or get_engine()
+    eng.load_pair(qbed, sbed, is_self)
+    text = np.asarray(text).view(np.uint8).reshape(-1)
+    lo, hi = slice_bounds(text, rank, world)
+    ptr, n = eng.cscore_begin(text[lo:hi], strip_names=strip_names, exclude_keys=exclude_keys)
+    if world > 1 and dist.is_initialized():
+        best = eng.best_table_tensor(ptr, n)
+        dist.all_reduce(best, op=dist.ReduceOp.MAX)          # ncclAllReduce(max) over NVLink, in place
+        torch.cuda.synchronize(eng.device)
+    lines, cnt = eng.cscore_finish(cscore)
+    parts = _gather_bytes(lines)
+    if rank != 0:
+        return None
+    merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    # survivors only: the C-score filter is done, exclusions were applied while tokenizing
+    return eng.blastfilter(merged, strip_names=strip_names, cscore=0, tandem_Nmax=tandem_Nmax, want_text=want_text)
+
+
+def liftover_sharded(text, a_qi, a_si, a_block, qbed, sbed, is_self, strip_names=True, dist=10, engine=None):
+    """Collective; LiftoverResult on rank 0 (None elsewhere)."""
+    rank, world = rank_world()
+    eng = engine or get_engine()
+    eng.load_pair(qbed, sbed, is_self)
+    text = np.asarray(text).view(np.uint8).reshape(-1)
+    lo, hi = slice_bounds(text, rank, world)
+    lines, cnt = eng.near_lines(text[lo:hi], a_qi, a_si, strip_names=strip_names, dist=dist)
+    parts = _gather_bytes(lines)
+    if rank != 0:
+        return None
+    merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    return eng.liftover_text(merged, a_qi, a_si, a_block, strip_names=strip_names, dist=dist)

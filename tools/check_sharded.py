@@ -1,0 +1,42 @@
+"""torchrun --nproc-per-node N tools/check_sharded.py : sharded blastfilter/liftover over N GPUs
+(NCCL all-reduce of the best-score table) must reproduce the single-GPU bytes."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from jcvi_b200 import synth
+from jcvi_b200.engine import get_engine
+from jcvi_b200.formats.bed import Bed
+from jcvi_b200.sharded import blastfilter_sharded, liftover_sharded
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+hits = int(os.environ.get("HITS", "4000000"))
+d = "/tmp/jx_sharded_%d" % rank
+qbed_p, sbed_p, last = synth.write_dataset(d, "A", "B", 77, 40000, 40000, hits, Kq=12, Ks=12)   # same seed on every rank
+qbed, sbed = Bed(qbed_p), Bed(sbed_p)
+text = np.fromfile(last, dtype=np.uint8)
+eng = get_engine(local)
+for it in range(3):
+    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = blastfilter_sharded(text, qbed, sbed, False, cscore=0.7)
+    torch.cuda.synchronize(); dist.barrier(); t1 = time.perf_counter()
+if rank == 0:
+    eng.load_pair(qbed, sbed, False)
+    whole = eng.blastfilter(text, cscore=0.7)
+    ok = bytes(memoryview(whole.text)) == bytes(memoryview(res.text))
+    sc = eng.scan_text(res.text)
+    blk = np.repeat(np.arange(sc.n_blocks, dtype=np.int32), np.diff(sc.block_start))
+    a = [sc.q_rank, sc.s_rank, blk]
+else:
+    a = [None, None, None]
+dist.broadcast_object_list(a, src=0)
+lf = liftover_sharded(text, a[0], a[1], a[2], qbed, sbed, False, dist=10)
+if rank == 0:
+    full = eng.liftover_text(text, a[0], a[1], a[2], dist=10)
+    ok2 = all(np.array_equal(getattr(full, k), getattr(lf, k)) for k in ("q_rank", "s_rank", "block", "accepted", "score"))
+    print("SHARDED world=%d hits=%d filtered=%d identical_filtered=%s identical_lifted=%s (%d lifted) sharded_blastfilter_s=%.4f"
+          % (world, hits, res.n, ok, ok2, lf.n_lifted, t1 - t0), flush=True)
+dist.barrier()
+dist.destroy_process_group()
