@@ -187,7 +187,7 @@ def impl_ours(args):
         return s.q_rank, s.s_rank, blk
 
     def step_device():
-        r = eng.blastfilter(dev_text, want_text=False, raw=True)
+        r = eng.blastfilter(dev_text, want_text=False, raw=True, skip_arrays=True)   # survivors stay on the device
         try:
             s = eng.scan_filtered(r)
         finally:
@@ -201,7 +201,7 @@ def impl_ours(args):
     def step_e2e():
         t0 = time.perf_counter()
         dt = eng.upload(pin_text)                      # one asynchronous H2D of the raw table ...
-        f = eng.blastfilter(dt, want_text=True)        # ... overlapped with tokenizing; `.filtered` text comes back
+        f = eng.blastfilter(dt, want_text=True, skip_arrays=True)   # ... overlapped with tokenizing; `.filtered` text comes back
         t1 = time.perf_counter()
         s = eng.scan_text(f.text)                      # the `.filtered` bytes, as a host buffer
         t2 = time.perf_counter()
@@ -210,7 +210,7 @@ def impl_ours(args):
         t3 = time.perf_counter()
         e2e_log.append((t1 - t0, t2 - t1, t3 - t2))
         h2d = len(text) + len(f.text) + 3 * 4 * len(aq)
-        d2h = (len(f.text) + 20 * f.n + 12 * s.n_anchors + 16 * l.n_lifted + 5 * len(aq))
+        d2h = (len(f.text) + 12 * s.n_anchors + 16 * l.n_lifted + 5 * len(aq))
         return s, l, f, h2d, d2h
 
     def barrier():
@@ -275,12 +275,19 @@ def impl_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:   # DRAM bytes per 64 MiB launch from the committed `ncu --set full` capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_tokenize_traffic.json")))
+            traffic = float(tj["dram_bytes_per_launch"])
+        except Exception:
+            pass
         alg_bytes = tok_bytes + 16 * tok_lines
         achieved = alg_bytes / (tok_ms / 1000.0) / 1e9 if tok_ms > 0 else 0.0
         roof = {"bound": "hbm", "kernel": "k_tokenize (K1 tokenizer + K2 hash join, fused K4 best-score)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback",
-                "traffic": None, "launches": tok_launches, "avg_launch_ms": tok_ms / max(tok_launches, 1),
+                "traffic": traffic, "traffic_note": "dram__bytes_read+write of one full 64 MiB launch (67.1 MB text + 15.1 MB records algorithmic), profiles/r1_tokenize_traffic.json",
+                "launches": tok_launches, "avg_launch_ms": tok_ms / max(tok_launches, 1),
                 "algorithmic_bytes_per_launch": alg_bytes / max(tok_launches, 1),
                 "share_of_step": tok_ms / dev_ms if dev_ms else None}
         # CPU baseline: bounded sample of the same table, + parity of the GPU path on that sample

@@ -47,6 +47,9 @@ int jx_ctx_create(int device, jx_ctx** out);
 void jx_ctx_destroy(jx_ctx* ctx);
 const char* jx_last_error(jx_ctx* ctx);
 const char* jx_version(void);
+/* sizeof() of jx_bed, jx_filter_opts, jx_filter_result, jx_scan_opts, jx_scan_result,
+ * jx_liftover_result as this library was compiled (binding self-check) */
+void jx_abi_sizes(int32_t out[6]);
 /* number of kernels this library launched on ctx since creation (bench.py "gpu_launches") */
 int64_t jx_launch_count(jx_ctx* ctx);
 /* the context's CUDA stream as an integer handle (for event timing on the launching stream) */
@@ -100,6 +103,8 @@ typedef struct {
   int64_t n_exclude;
   int32_t want_text;            /* also produce the `.filtered` text (write_new_blast 200-202)  */
   int32_t want_mothers;         /* also return the tandem mother maps (write_localdups 164-185) */
+  int32_t skip_arrays;          /* do not copy q_rank/s_rank/score/line_off to the host (they stay NULL);
+                                   the survivors remain on the device for jx_scan_filtered            */
 } jx_filter_opts;
 
 typedef struct {
@@ -118,6 +123,8 @@ typedef struct {
    * 3 after exclude, 4 after cscore (pre-dedupe), 5 after dedupe, 6 after tandem, 7 '#' lines */
   int64_t stats[8];
   int32_t text_pinned;          /* 0: malloc'ed, owned by the result; 2: context-owned (see text) */
+  int64_t device_token;         /* identifies the device-resident copy of the survivors kept by the
+                                   context (valid until the next jx_blastfilter on it)               */
 } jx_filter_result;
 
 int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device,

@@ -31,14 +31,14 @@ class JxBed(ctypes.Structure):
 class JxFilterOpts(ctypes.Structure):
     _fields_ = [("strip_names", ctypes.c_int32), ("cscore", ctypes.c_double), ("tandem_nmax", ctypes.c_int32),
                 ("exclude_keys", ctypes.c_void_p), ("n_exclude", ctypes.c_int64), ("want_text", ctypes.c_int32),
-                ("want_mothers", ctypes.c_int32)]
+                ("want_mothers", ctypes.c_int32), ("skip_arrays", ctypes.c_int32)]
 
 
 class JxFilterResult(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int64), ("q_rank", c_i32p), ("s_rank", c_i32p), ("score", c_f32p),
                 ("line_off", c_u64p), ("text", ctypes.c_void_p), ("text_len", ctypes.c_int64),
                 ("q_mother", c_i32p), ("s_mother", c_i32p), ("stats", ctypes.c_int64 * 8),
-                ("text_pinned", ctypes.c_int32)]
+                ("text_pinned", ctypes.c_int32), ("device_token", ctypes.c_int64)]
 
 
 class JxScanOpts(ctypes.Structure):
@@ -61,7 +61,7 @@ EXPORTS = [
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
     "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release",
-    "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_free",
+    "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_free", "jx_abi_sizes",
 ]
 
 _lib = None
@@ -116,6 +116,11 @@ def lib():
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), c_i64p, c_i64p]
         L.jx_free.argtypes = [ctypes.c_void_p]
         L.jx_free.restype = None
+        sizes = (ctypes.c_int32 * 6)()
+        L.jx_abi_sizes(sizes)
+        mine = [ctypes.sizeof(x) for x in (JxBed, JxFilterOpts, JxFilterResult, JxScanOpts, JxScanResult, JxLiftoverResult)]
+        if list(sizes) != mine:
+            raise ImportError("jcvi_b200: struct layout mismatch between _cabi.py %s and libjcvi_b200.so %s" % (mine, list(sizes)))
         _lib = L
     return _lib
 

@@ -22,6 +22,11 @@ extern "C" {
 
 void jx_free(void* p) { free(p); }
 
+void jx_abi_sizes(int32_t out[6]) {
+  out[0] = (int32_t)sizeof(jx_bed); out[1] = (int32_t)sizeof(jx_filter_opts); out[2] = (int32_t)sizeof(jx_filter_result);
+  out[3] = (int32_t)sizeof(jx_scan_opts); out[4] = (int32_t)sizeof(jx_scan_result); out[5] = (int32_t)sizeof(jx_liftover_result);
+}
+
 const char* jx_version(void) { return "jcvi_b200 0.1 (sm_100a)"; }
 
 int jx_ctx_create(int device, jx_ctx** out) {
@@ -62,6 +67,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaFree(ctx->held_text);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);
+  cudaFree(ctx->lastf.q); cudaFree(ctx->lastf.s); cudaFree(ctx->lastf.score);
   for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);

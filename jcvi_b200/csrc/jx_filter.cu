@@ -575,10 +575,14 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
 
   // ---- K8: output order (score desc, line asc) and gather ----------------------------------------------------
   out->n = nF;
-  out->q_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
-  out->s_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
-  out->score = (float*)malloc(sizeof(float) * (nF + 1));
-  out->line_off = (uint64_t*)malloc(sizeof(uint64_t) * (nF + 1));
+  const bool host_arrays = !opts->skip_arrays;
+  if (host_arrays) {
+    out->q_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
+    out->s_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
+    out->score = (float*)malloc(sizeof(float) * (nF + 1));
+    out->line_off = (uint64_t*)malloc(sizeof(uint64_t) * (nF + 1));
+  }
+  ctx->lastf.n = 0; ctx->lastf.token = 0;
   if (nF) {
     JX_ALLOC(okeys, uint64_t, nF, false);
     JX_LAUNCH(k_order_keys, nblk(nF), 256, 0, Fj, C, Cidx, nF, okeys);
@@ -594,10 +598,29 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     JX_ALLOC(osc, float, nF, false);
     JX_ALLOC(ooff, uint64_t, nF, false);
     JX_LAUNCH(k_gather_out, nblk(nF), 256, 0, ov, nF, C, Cidx, d_mq, d_ms, tok.desc, tok.ntiles, oq, os, osc, ooff);
-    JX_CK(cudaMemcpyAsync(out->q_rank, oq, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->s_rank, os, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->score, osc, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->line_off, ooff, nF * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_arrays) {
+      JX_CK(cudaMemcpyAsync(out->q_rank, oq, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(out->s_rank, os, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(out->score, osc, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(out->line_off, ooff, nF * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    {   // keep the survivors on the device for jx_scan_filtered
+      auto& L = ctx->lastf;
+      if (L.cap < nF) {
+        cudaFree(L.q); cudaFree(L.s); cudaFree(L.score);
+        L.q = nullptr; L.s = nullptr; L.score = nullptr; L.cap = 0;
+        const size_t cap = (size_t)nF + (nF >> 2) + 1024;
+        JX_CK(cudaMalloc((void**)&L.q, cap * 4));
+        JX_CK(cudaMalloc((void**)&L.s, cap * 4));
+        JX_CK(cudaMalloc((void**)&L.score, cap * 4));
+        L.cap = cap;
+      }
+      JX_CK(cudaMemcpyAsync(L.q, oq, (size_t)nF * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      JX_CK(cudaMemcpyAsync(L.s, os, (size_t)nF * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      JX_CK(cudaMemcpyAsync(L.score, osc, (size_t)nF * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      L.n = nF; L.token = ++ctx->token_counter;
+      out->device_token = L.token;
+    }
     if (opts->want_text) {
       // K12: format on the device (exact re-implementation of the "%.2f/%.2g/%.3g" conversions);
       // anything it declines (inf/nan, >int32 integers, decimal rounding ties in the evalue ...)
@@ -640,6 +663,15 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
         JX_CK(cudaMemcpyAsync(hlen_all.data(), flen, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
         JX_CK(cudaMemcpyAsync(hpos_all.data(), fpos, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
         JX_CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int32_t> tmpq, tmps;
+        const int32_t* hq = out->q_rank; const int32_t* hs = out->s_rank;
+        if (!host_arrays) {
+          tmpq.resize(nF); tmps.resize(nF);
+          JX_CK(cudaMemcpyAsync(tmpq.data(), oq, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+          JX_CK(cudaMemcpyAsync(tmps.data(), os, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+          JX_CK(cudaStreamSynchronize(ctx->stream));
+          hq = tmpq.data(); hs = tmps.data();
+        }
         std::vector<uint32_t> didx;
         didx.reserve(ndecl);
         for (uint32_t t = 0; t < nF; ++t) if (!hlen_all[t]) didx.push_back(t);
@@ -670,7 +702,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
           size_t lo = (size_t)nd * t / nt, hi = (size_t)nd * (t + 1) / nt;
           part_lo[t] = lo; part_lo[t + 1] = hi;
           th.emplace_back([&, t, lo, hi]() {
-            format_range(hl.data(), hpos.data(), hlen.data(), out->q_rank, out->s_rank, didx.data(), lo, hi, Q, S, parts[t]);
+            format_range(hl.data(), hpos.data(), hlen.data(), hq, hs, didx.data(), lo, hi, Q, S, parts[t]);
           });
         }
         for (auto& x : th) x.join();

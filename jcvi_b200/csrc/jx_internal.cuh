@@ -68,6 +68,9 @@ struct jx_ctx {
     int64_t ntiles = 0; uint32_t n_lines = 0;
     unsigned long long stats[12] = {0};
   } cache;
+  // device-resident survivors of the last jx_blastfilter (for jx_scan_filtered)
+  struct LastFilter { int32_t* q = nullptr; int32_t* s = nullptr; float* score = nullptr; size_t cap = 0; int64_t n = 0; int64_t token = 0; } lastf;
+  int64_t token_counter = 0;
   uint32_t* sess_best = nullptr; size_t sess_best_cap = 0;   // jx_cscore_begin/finish session
   bool sess_open = false;
   char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text

@@ -359,10 +359,16 @@ int jx_scan_filtered(jx_ctx* ctx, const jx_filter_result* f, const jx_scan_opts*
   JX_ALLOC(recs, uint4, n, false);
   JX_ALLOC(bad, uint32_t, 1, true);
   if (n) {
-    JX_CK(cudaMemcpyAsync(dq, f->q_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_CK(cudaMemcpyAsync(ds, f->s_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_CK(cudaMemcpyAsync(dsc, f->score, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_LAUNCH(k_filtered_to_recs, nblk(n), 256, 0, dq, ds, dsc, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
+    const int32_t* srcq = dq; const int32_t* srcs = ds; const float* srcsc = dsc;
+    if (f->device_token && f->device_token == ctx->lastf.token && (int64_t)n == ctx->lastf.n) {
+      srcq = ctx->lastf.q; srcs = ctx->lastf.s; srcsc = ctx->lastf.score;      // still resident: no round trip
+    } else {
+      if (!f->q_rank || !f->s_rank || !f->score) { ctx->err = "filter result has no host arrays and is no longer resident"; return JX_EARG; }
+      JX_CK(cudaMemcpyAsync(dq, f->q_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+      JX_CK(cudaMemcpyAsync(ds, f->s_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+      JX_CK(cudaMemcpyAsync(dsc, f->score, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    JX_LAUNCH(k_filtered_to_recs, nblk(n), 256, 0, srcq, srcs, srcsc, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
               ctx->side[1].chr_lex, recs, bad);
   }
   uint32_t hbad = 0;

@@ -392,7 +392,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   JX_ALLOC(d_stats, unsigned long long, 12, true);
   JX_ALLOC(d_ticket, uint32_t, 1, true);
   const bool to_cache = held && ((mode.fill_cache && !ctx->is_self && mode.n_excl == 0 && !mode.neardiag) || mode.persist);
-  ctx->cache.valid = false;
+  if (to_cache) ctx->cache.valid = false;    // about to overwrite the retained records
   uint64_t* d_desc = nullptr;
   if (to_cache) {
     if (ctx->cache.desc_cap < (size_t)ntiles + 1) {

@@ -44,10 +44,10 @@ class FilterResult(object):
     def __init__(self, r, lib, Gq, Gs, want_mothers):
         n = r.n
         self.n = n
-        self.q_rank = C.as_np(r.q_rank, n, np.int32)
-        self.s_rank = C.as_np(r.s_rank, n, np.int32)
-        self.score = C.as_np(r.score, n, np.float32)
-        self.line_off = C.as_np(r.line_off, n, np.uint64)
+        self.q_rank = C.as_np(r.q_rank, n, np.int32) if r.q_rank else None
+        self.s_rank = C.as_np(r.s_rank, n, np.int32) if r.s_rank else None
+        self.score = C.as_np(r.score, n, np.float32) if r.score else None
+        self.line_off = C.as_np(r.line_off, n, np.uint64) if r.line_off else None
         # zero-copy view of the library-owned `.filtered` bytes; freed with this object
         self._raw, self._lib = r, lib
         self.text = (np.ctypeslib.as_array(ctypes.cast(r.text, C.c_u8p), shape=(max(r.text_len, 1),))[: r.text_len]
@@ -169,7 +169,7 @@ class Engine(object):
 
     # ---- stages ---------------------------------------------------------------------------------
     def blastfilter(self, text, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None, want_text=True,
-                    want_mothers=False, raw=False):
+                    want_mothers=False, raw=False, skip_arrays=False):
         p, n, dev, keep = _text_ptr(text)
         o = C.JxFilterOpts()
         o.strip_names = int(bool(strip_names))
@@ -182,6 +182,7 @@ class Engine(object):
             o.n_exclude = len(ek)
         o.want_text = int(bool(want_text))
         o.want_mothers = int(bool(want_mothers))
+        o.skip_arrays = int(bool(skip_arrays))
         r = C.JxFilterResult()
         rc = self.lib.jx_blastfilter(self.ctx, p, n, dev, ctypes.byref(o), ctypes.byref(r))
         if rc != 0:

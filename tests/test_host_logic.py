@@ -25,7 +25,10 @@ def test_cabi_library_loads_and_exports_header_symbols():
     assert b"sm_100a" in L.jx_version()
     # struct layouts the Python side mirrors (sizes as the C compiler sees them)
     assert ctypes.sizeof(_cabi.JxScanOpts) == 16
-    assert ctypes.sizeof(_cabi.JxFilterResult) == 8 * 9 + 64 + 8
+    sizes = (ctypes.c_int32 * 6)()
+    L.jx_abi_sizes(sizes)
+    assert list(sizes) == [ctypes.sizeof(x) for x in (_cabi.JxBed, _cabi.JxFilterOpts, _cabi.JxFilterResult, _cabi.JxScanOpts,
+                                                     _cabi.JxScanResult, _cabi.JxLiftoverResult)]
 
 
 def test_no_cpu_fallback_without_gpu():
