@@ -1,0 +1,126 @@
+"""Tokenizer edge cases against the CPU oracle: rare paths of k_tokenize (lines longer than the
+shared-memory window, tiles holding more than 1024 line starts, 127-byte names, line starts on
+tile boundaries, CR LF and lone-CR terminators, no trailing newline)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import read
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from jcvi_b200.compara import blastfilter, synteny
+    return blastfilter, synteny
+
+
+def _beds(d, names_q, names_s):
+    qbed, sbed = os.path.join(d, "A.bed"), os.path.join(d, "B.bed")
+    with open(qbed, "w") as fw:
+        for i, n in enumerate(names_q):
+            fw.write("Achr%d\t%d\t%d\t%s\n" % (1 + i // 400, 1000 * i, 1000 * i + 500 + i % 7, n))
+    with open(sbed, "w") as fw:
+        for i, n in enumerate(names_s):
+            fw.write("Bchr%d\t%d\t%d\t%s\n" % (1 + i // 400, 1000 * i, 1000 * i + 400 + i % 5, n))
+    return qbed, sbed
+
+
+def _check_all(d, mods, last, qbed, sbed, cscore=0.3, lift_dist=10):
+    import oracle
+    bf, syn = mods
+    beds = ["--qbed=" + qbed, "--sbed=" + sbed]
+    oracle.blastfilter(last, qbed, sbed, out_path=last + ".orc", cscore=cscore)
+    bf.main([last] + beds + ["--cscore=%g" % cscore])
+    assert read(last + ".filtered") == read(last + ".orc")
+    try:
+        oracle.scan(last + ".filtered", last + ".orc.anchors", qbed, sbed, min_size=2)
+        err = None
+    except oracle.ZeroAnchors as e:
+        err = str(e)
+    try:
+        syn.scan([last + ".filtered", last + ".anchors"] + beds + ["--min_size=2"])
+        gerr = None
+    except ValueError as e:
+        gerr = str(e)
+    assert gerr == err
+    assert read(last + ".anchors") == read(last + ".orc.anchors")
+    if err is None:
+        oracle.liftover(last, last + ".orc.anchors", qbed, sbed, out_path=last + ".orc.lifted", dist=lift_dist)
+        syn.liftover([last, last + ".anchors"] + beds + ["--dist=%d" % lift_dist, "--outfile=" + last + ".lifted"])
+        assert read(last + ".lifted") == read(last + ".orc.lifted")
+
+
+def _lines(rng, nq, ns, n, qname, sname):
+    out = []
+    for _ in range(n):
+        q = int(rng.integers(0, nq)); s = min(ns - 1, max(0, q + int(rng.integers(-3, 4)))) if rng.random() < 0.7 else int(rng.integers(0, ns))
+        sc = "%.1f" % rng.uniform(50, 900)
+        out.append("%s\t%s\t%.2f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.1e\t%s" % (
+            qname(q), sname(s), rng.uniform(30, 100), rng.integers(50, 900), rng.integers(0, 90), rng.integers(0, 9),
+            rng.integers(1, 900), rng.integers(900, 1800), rng.integers(1, 900), rng.integers(900, 1800),
+            10.0 ** -rng.uniform(3, 60), sc))
+    return out
+
+
+def test_long_names_and_long_lines(tmp_path, mods):
+    """127-byte names (the cblast char[128] limit) and lines of 1.5-9 KB (longer than the 1 KiB
+    look-ahead, some longer than a whole 8 KiB tile) mixed into ordinary lines."""
+    rng = np.random.default_rng(51)
+    nq = ns = 1200
+    qn = lambda i: ("Q%05d_" % i).ljust(125, "x") + ".1" if i % 3 == 0 else "Ag%06d.1" % i
+    sn = lambda i: ("S%05d_" % i).ljust(127, "y") if i % 4 == 0 else "Bg%06d.1" % i
+    d = str(tmp_path)
+    qbed, sbed = _beds(d, [qn(i)[:-2] if qn(i).endswith(".1") else qn(i) for i in range(nq)],
+                       [sn(i)[:-2] if sn(i).endswith(".1") else sn(i) for i in range(ns)])
+    lines = _lines(rng, nq, ns, 30000, qn, sn)
+    for k in range(0, len(lines), 137):
+        lines[k] = lines[k] + "\t" + "z" * int(rng.integers(1500, 9000))      # extra columns: ignored by sscanf
+    for k in range(50, len(lines), 301):
+        f = lines[k].split("\t"); f[11] = f[11] + "0" * 1200; lines[k] = "\t".join(f)   # >19 digits but trailing zeros only
+    last = os.path.join(d, "A.B.last")
+    open(last, "w").write("\n".join(lines) + "\n")
+    _check_all(d, mods, last, qbed, sbed)
+
+
+def test_many_short_lines_and_boundaries(tmp_path, mods):
+    """Runs of blank / 2-byte lines put > 1024 line starts into one 8 KiB tile (chunked line table),
+    and padding comments move real line starts onto every offset around the tile boundaries."""
+    rng = np.random.default_rng(52)
+    nq = ns = 900
+    qn = lambda i: "Ag%06d.1" % i
+    sn = lambda i: "Bg%06d.1" % i
+    d = str(tmp_path)
+    qbed, sbed = _beds(d, ["Ag%06d" % i for i in range(nq)], ["Bg%06d" % i for i in range(ns)])
+    lines = _lines(rng, nq, ns, 20000, qn, sn)
+    out = []
+    for k, ln in enumerate(lines):
+        out.append(ln)
+        if k % 1000 == 500:
+            out.extend([""] * 6000)                      # 6000 empty lines: ~0.7 tiles of pure '\n'
+        if k % 1000 == 700:
+            out.extend(["x"] * 3000)                     # 2-byte lines
+        if k % 97 == 0:
+            out.append("#" + "p" * int(rng.integers(0, 64)))   # jitter the alignment of what follows
+    last = os.path.join(d, "A.B.last")
+    open(last, "w").write("\n".join(out))               # no trailing newline
+    _check_all(d, mods, last, qbed, sbed)
+
+
+def test_crlf_and_lone_cr(tmp_path, mods):
+    """Python universal newlines: CR LF and a lone CR both end a line."""
+    rng = np.random.default_rng(53)
+    nq = ns = 700
+    qn = lambda i: "Ag%06d.1" % i
+    sn = lambda i: "Bg%06d.1" % i
+    d = str(tmp_path)
+    qbed, sbed = _beds(d, ["Ag%06d" % i for i in range(nq)], ["Bg%06d" % i for i in range(ns)])
+    lines = _lines(rng, nq, ns, 12000, qn, sn)
+    body = ""
+    for k, ln in enumerate(lines):
+        body += ln + ("\r\n" if k % 3 == 0 else "\r" if k % 3 == 1 else "\n")
+    last = os.path.join(d, "A.B.last")
+    open(last, "w", newline="").write(body)
+    _check_all(d, mods, last, qbed, sbed)
