@@ -75,23 +75,51 @@ def head_lines(text, nlines):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region: NVML (same counters nvidia-smi prints
+    as clocks.sm / clocks_event_reasons.*) every 5 ms, nvidia-smi as a fallback."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = threading.Event()
 
     def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                     getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                     getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                     getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                r = int(get_reasons(h))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                self.stop_flag.wait(0.005)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                for i in range(4):
+                    if r[2 + i].lower().startswith("active"):
+                        self.reasons.add(names[i])
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
@@ -99,12 +127,8 @@ class ClockSampler(threading.Thread):
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def run_cpu_oracle(w, sample_text, steps, warmup):
@@ -252,11 +276,11 @@ def impl_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     dev_ms, wall_ms = timed(step_device, args.steps)
-    clocks = sampler.summary()
     launches = eng.launch_count() - l0n
     tok_ms, tok_launches, tok_bytes, tok_lines = eng.tokenizer_timing(reset=True)
     # ---- timed: end to end with host buffers --------------------------------------------------------------
     e2e_ms, e2e_wall = timed(lambda: step_e2e(), args.steps)
+    clocks = sampler.summary()          # sampled across both timed regions
     log("[rank %d] e2e sub-steps (s) blastfilter+upload / scan_text / liftover: %s" % (
         rank, ["%.4f %.4f %.4f" % x for x in e2e_log[-args.steps:]]))
 

@@ -35,7 +35,14 @@ __global__ void k_select(const uint4* __restrict__ recs, uint32_t n, const uint3
         double bs = (double)__uint_as_float(__ldg(best + __ldg(snid + r.y)));
         double den = bq > bs ? bq : bs;                       // max(best_score[q], best_score[s])
         if (den == 0.0) { atomicExch(errflag, 1u); keep = false; }
-        else keep = ((double)__uint_as_float(r.z) / den) > cscore;   // IEEE float64 division, strict >
+        else {
+          // the reference's test is the IEEE quotient score / den > cscore (strict).  One multiply
+          // settles all but the hair-thin band around the threshold; only there is the division done.
+          const double sc = (double)__uint_as_float(r.z), th = den * cscore;
+          if (sc < th * (1.0 - 1e-12)) keep = false;
+          else if (sc > th * (1.0 + 1e-12)) keep = true;
+          else keep = (sc / den) > cscore;
+        }
       }
     }
     uint32_t slot = warp_append(keep, counter);
