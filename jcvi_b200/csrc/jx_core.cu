@@ -37,6 +37,7 @@ int jx_ctx_create(int device, jx_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return JX_ECUDA;
   jx_ctx* ctx = new jx_ctx();
   ctx->device = device;
+  ctx->trace = getenv("JX_TRACE") ? atoi(getenv("JX_TRACE")) : 0;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;

@@ -18,35 +18,57 @@
 
 namespace {
 
-__global__ void k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ best,
+// 4 records per thread and iteration: the four 16-byte loads and the eight table gathers are all
+// in flight before anything is consumed (the first version was latency bound: long-scoreboard
+// stalls 84 warps per issue, 11 % issue utilisation)
+__global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ best,
                          const uint32_t* __restrict__ qnid, const uint32_t* __restrict__ snid, double cscore,
                          int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
                          uint32_t* errflag) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t nround = (n + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-    bool keep = false;
-    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
-    if (i < n) {
-      r = __ldcs(recs + i);
-      keep = r.x != JX_NOREC;
-      if (keep && use_cscore) {
-        double bq = (double)__uint_as_float(__ldg(best + __ldg(qnid + r.x)));
-        double bs = (double)__uint_as_float(__ldg(best + __ldg(snid + r.y)));
-        double den = bq > bs ? bq : bs;                       // max(best_score[q], best_score[s])
-        if (den == 0.0) { atomicExch(errflag, 1u); keep = false; }
+  constexpr int U = 4;
+  const uint32_t stride = gridDim.x * blockDim.x * U;
+  const uint32_t nround = (n + (32u * U - 1)) / (32u * U) * (32u * U);
+  const uint32_t lane = threadIdx.x & 31u, wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U;
+  for (uint32_t i0 = wbase; i0 < nround; i0 += stride) {
+    uint4 r[U]; uint32_t iq[U], is[U]; bool keep[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      r[u] = i < n ? __ldcs(recs + i) : make_uint4(JX_NOREC, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      keep[u] = r[u].x != JX_NOREC;
+      iq[u] = keep[u] && use_cscore ? __ldg(qnid + r[u].x) : 0u;
+      is[u] = keep[u] && use_cscore ? __ldg(snid + r[u].y) : 0u;
+    }
+    uint32_t bq[U], bs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bq[u] = keep[u] && use_cscore ? __ldg(best + iq[u]) : 0u;
+      bs[u] = keep[u] && use_cscore ? __ldg(best + is[u]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (keep[u] && use_cscore) {
+        const double a = (double)__uint_as_float(bq[u]), b = (double)__uint_as_float(bs[u]);
+        const double den = a > b ? a : b;                     // max(best_score[q], best_score[s])
+        if (den == 0.0) { atomicExch(errflag, 1u); keep[u] = false; }
         else {
           // the reference's test is the IEEE quotient score / den > cscore (strict).  One multiply
           // settles all but the hair-thin band around the threshold; only there is the division done.
-          const double sc = (double)__uint_as_float(r.z), th = den * cscore;
-          if (sc < th * (1.0 - 1e-12)) keep = false;
-          else if (sc > th * (1.0 + 1e-12)) keep = true;
-          else keep = (sc / den) > cscore;
+          const double sc = (double)__uint_as_float(r[u].z), th = den * cscore;
+          if (sc < th * (1.0 - 1e-12)) keep[u] = false;
+          else if (sc > th * (1.0 + 1e-12)) keep[u] = true;
+          else keep[u] = (sc / den) > cscore;
         }
       }
     }
-    uint32_t slot = warp_append(keep, counter);
-    if (keep) { out[slot] = r; out_idx[slot] = i; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t slot = warp_append(keep[u], counter);
+      if (keep[u]) { out[slot] = r[u]; out_idx[slot] = i0 + u * 32u + lane; }
+    }
   }
 }
 
@@ -462,6 +484,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   const bool use_tandem = opts->tandem_nmax != 0;
   int rc;
 
+  JX_TRACE("bf: enter");
   // ---- K1/K2 (+ K4 fused): text -> records, per-name best score -------------------------------
   TokMode mode;
   mode.strip = opts->strip_names;
@@ -484,6 +507,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   out->stats[1] = (int64_t)(tok.stats[2] + tok.stats[8]);
   out->stats[3] = (int64_t)tok.stats[2];
   const uint32_t nrec = tok.n_lines;
+  JX_TRACE("bf: tokenized");
 
   // ---- K5: C-score predicate fused with compaction -------------------------------------------------
   const size_t capC = (size_t)tok.stats[2] + 1;
@@ -491,7 +515,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   JX_ALLOC(Cidx, uint32_t, capC, false);
   JX_ALLOC(d_cnt, uint32_t, 2, true);
   if (nrec) {
-    unsigned grid = std::min<unsigned>(nblk(nrec), 148u * 16u);
+    unsigned grid = std::min<unsigned>(nblk((nrec + 3) / 4), 148u * 8u);
     JX_LAUNCH(k_select, grid, 256, 0, tok.recs, nrec, d_best, Q.name_id, S.name_id, opts->cscore, use_cscore ? 1 : 0, C,
               Cidx, d_cnt, d_cnt + 1);
   }
@@ -501,6 +525,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   if (h_cnt[1]) { ctx->err = "float division by zero"; return JX_EZERODIV; }
   const uint32_t nC = h_cnt[0];
   out->stats[4] = nC;
+  JX_TRACE("bf: k_select");
 
   // ---- K3: per-pair best record (sorted by (qi, si)) ----------------------------------------------------
   const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
@@ -512,6 +537,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     if ((rc = dedupe(ctx, arena, keys, vals, nC, sb + qb, C, Cidx, 0, Kkey, Kj, nK))) return rc;
   }
   out->stats[5] = nK;
+  JX_TRACE("bf: dedupe1");
 
   // ---- K6: tandem families + mothers -----------------------------------------------------------------------
   int32_t *d_mq = nullptr, *d_ms = nullptr;
@@ -579,6 +605,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     }
   }
   out->stats[6] = nF;
+  JX_TRACE("bf: tandem+dedupe2");
 
   // ---- K8: output order (score desc, line asc) and gather ----------------------------------------------------
   out->n = nF;
@@ -744,6 +771,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     out->text = (char*)calloc(1, 1);
     out->text_len = 0;
   }
+  JX_TRACE("bf: order+gather+text");
   if (opts->want_mothers) {
     out->q_mother = (int32_t*)malloc(sizeof(int32_t) * (size_t)(Q.G + 1));
     out->s_mother = (int32_t*)malloc(sizeof(int32_t) * (size_t)(S.G + 1));

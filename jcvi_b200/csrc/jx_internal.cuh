@@ -54,6 +54,8 @@ struct jx_ctx {
   int32_t* q_same_s = nullptr;
   uint32_t n_name_ids = 0;
   std::string err;
+  int trace = 0;                 // JX_TRACE=1: print phase timings (synchronising; debugging aid)
+  double trace_t0 = 0;
   int64_t launches = 0;
   // tokenizer timing (CUDA events on `stream`)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
@@ -92,6 +94,16 @@ struct jx_ctx {
       return JX_ECUDA;                                                                      \
     }                                                                                       \
   } while (0)
+
+#include <chrono>
+inline void jx_trace_point(jx_ctx* ctx, const char* label) {
+  if (!ctx->trace) return;
+  cudaStreamSynchronize(ctx->stream);
+  const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  fprintf(stderr, "[jx trace] %-28s +%.3f ms\n", label, ctx->trace_t0 ? t - ctx->trace_t0 : 0.0);
+  ctx->trace_t0 = t;
+}
+#define JX_TRACE(label) jx_trace_point(ctx, label)
 
 #define JX_LAUNCH(kernel, grid, block, smem, ...)                                           \
   do {                                                                                      \

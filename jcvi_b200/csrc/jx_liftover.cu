@@ -123,31 +123,52 @@ __device__ __forceinline__ bool anchor_within(int32_t x, int32_t y, int sb, cons
 }
 
 // raw records -> the few that can matter to liftover: hits within dist of an anchor (the
-// anchors themselves included: AnchorFile.filter_blocks needs their raw scores)
-__global__ void k_select_near(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bitmap, int cshift,
-                              uint32_t nsc, int sb, const uint64_t* __restrict__ akey, const uint32_t* __restrict__ rowptr,
-                              const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
-                              const int32_t* __restrict__ schr, int dist, uint4* out, uint32_t* out_idx, uint32_t* counter,
-                              unsigned long long* nvalid) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t nround = (n + 31u) & ~31u;
-  uint32_t valid = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
-    if (i < n) r = __ldcs(recs + i);
-    bool keep = r.x != JX_NOREC;
-    if (keep) {
-      ++valid;
-      const uint64_t bit = (uint64_t)(r.x >> cshift) * nsc + (uint64_t)(r.y >> cshift);
-      keep = (__ldg(bitmap + (bit >> 5)) >> (bit & 31)) & 1u;
-      if (keep) keep = anchor_within((int32_t)r.x, (int32_t)r.y, sb, akey, rowptr, qbeg, qend, schr, dist);
-    }
-    uint32_t slot = warp_append(keep, counter);
-    if (keep) { out[slot] = r; out_idx[slot] = i; }
-  }
+// anchors themselves included: AnchorFile.filter_blocks needs their raw scores).
+// Pass 1 (k_select_cell) only tests the occupancy bitmap -- uniform work, 4 records in flight per
+// thread; pass 2 (k_keep_near) runs the exact window test on the compacted candidates so that its
+// loop executes with full warps (one fused kernel ran with 5 of 32 lanes active).
+__global__ void __launch_bounds__(256) k_select_cell(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bitmap,
+                                                     int cshift, uint32_t nsc, uint4* out, uint32_t* out_idx, uint32_t* counter) {
+  constexpr int U = 4;
+  const uint32_t stride = gridDim.x * blockDim.x * U;
+  const uint32_t nround = (n + (32u * U - 1)) / (32u * U) * (32u * U);
+  const uint32_t lane = threadIdx.x & 31u, wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U;
+  for (uint32_t i0 = wbase; i0 < nround; i0 += stride) {
+    uint4 r[U]; bool keep[U]; uint32_t w[U];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xFFFFFFFFu, valid, o);
-  if ((threadIdx.x & 31) == 0 && valid) atomicAdd(nvalid, (unsigned long long)valid);
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      r[u] = i < n ? __ldcs(recs + i) : make_uint4(JX_NOREC, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      keep[u] = r[u].x != JX_NOREC;
+      const uint64_t bit = (uint64_t)(r[u].x >> cshift) * nsc + (uint64_t)(r[u].y >> cshift);
+      w[u] = keep[u] ? __ldg(bitmap + (bit >> 5)) >> (bit & 31) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      keep[u] = keep[u] && (w[u] & 1u);
+      const uint32_t slot = warp_append(keep[u], counter);
+      if (keep[u]) { out[slot] = r[u]; out_idx[slot] = i0 + u * 32u + lane; }
+    }
+  }
+}
+__global__ void k_keep_near(const uint4* __restrict__ cand, const uint32_t* __restrict__ cand_idx, uint32_t n, int sb,
+                            const uint64_t* __restrict__ akey, const uint32_t* __restrict__ rowptr,
+                            const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
+                            const int32_t* __restrict__ schr, int dist, uint4* out, uint32_t* out_idx, uint32_t* counter) {
+  const uint32_t nround = (n + 31u) & ~31u;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nround) return;
+  uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
+  bool keep = false;
+  if (t < n) {
+    r = cand[t];
+    keep = anchor_within((int32_t)r.x, (int32_t)r.y, sb, akey, rowptr, qbeg, qend, schr, dist);
+  }
+  const uint32_t slot = warp_append(keep, counter);
+  if (keep) { out[slot] = r; out_idx[slot] = cand_idx[t]; }
 }
 
 // exact minimum L1 distance (< dist) to the anchors of the same chromosome pair
@@ -517,24 +538,29 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
 
   // ---- raw records -> candidates near an anchor -> unique (qi,si), first occurrence ------------------------
-  int cshift = 5;                                          // 32 x 32 rank cells, coarser for huge genomes
+  int cshift = 4;                                          // 16 x 16 rank cells, coarser for huge genomes
   while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
   const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
   const size_t nwords = (size_t)(((uint64_t)nqc * nsc + 31) >> 5);
   JX_ALLOC(bitmap, uint32_t, nwords, true);
   JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist, cshift, nsc, nqc, bitmap);
   const size_t capC = (size_t)tstats[2] + 1;
-  JX_ALLOC(C, uint4, capC, false);
-  JX_ALLOC(Cidx, uint32_t, capC, false);
-  JX_ALLOC(d_cnt, uint32_t, 1, true);
-  JX_ALLOC(d_nvalid, unsigned long long, 1, true);
+  JX_ALLOC(C0, uint4, capC, false);
+  JX_ALLOC(C0idx, uint32_t, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 2, true);
   if (n_lines) {
-    unsigned grid = std::min<unsigned>(nblk(n_lines), 148u * 16u);
-    JX_LAUNCH(k_select_near, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex,
-              dist, C, Cidx, d_cnt, d_nvalid);
+    unsigned grid = std::min<unsigned>(nblk((n_lines + 3) / 4), 148u * 8u);
+    JX_LAUNCH(k_select_cell, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, C0, C0idx, d_cnt);
   }
+  uint32_t nC0 = 0;
+  JX_CK(cudaMemcpyAsync(&nC0, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
+  JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
+  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist, C, Cidx,
+                     d_cnt + 1);
   uint32_t nC = 0;
-  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&nC, d_cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
   JX_CK(cudaStreamSynchronize(ctx->stream));
   uint32_t nh = 0;
   uint64_t* hkey = nullptr; float* hsc = nullptr; uint32_t* hline = nullptr;
@@ -704,21 +730,26 @@ int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_dev
   if ((rc = jx_sort_keys(ctx, arena, aks, na, 0, sb + qb))) return rc;
   JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
   JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
-  int cshift = 5;
+  int cshift = 4;
   while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
   const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
   JX_ALLOC(bitmap, uint32_t, (size_t)(((uint64_t)nqc * nsc + 31) >> 5), true);
   JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist, cshift, nsc, nqc, bitmap);
   const size_t capC = (size_t)tok.stats[2] + 1;
-  JX_ALLOC(C, uint4, capC, false);
-  JX_ALLOC(Cidx, uint32_t, capC, false);
-  JX_ALLOC(d_cnt, uint32_t, 1, true);
-  JX_ALLOC(d_nvalid, unsigned long long, 1, true);
-  unsigned grid = std::min<unsigned>(nblk(tok.n_lines), 148u * 16u);
-  JX_LAUNCH(k_select_near, grid, 256, 0, tok.recs, tok.n_lines, bitmap, cshift, nsc, sb, aks, rowptr, Q.chr_begin, Q.chr_end,
-            S.chr_lex, dist, C, Cidx, d_cnt, d_nvalid);
+  JX_ALLOC(C0, uint4, capC, false);
+  JX_ALLOC(C0idx, uint32_t, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 2, true);
+  unsigned grid = std::min<unsigned>(nblk((tok.n_lines + 3) / 4), 148u * 8u);
+  JX_LAUNCH(k_select_cell, grid, 256, 0, tok.recs, tok.n_lines, bitmap, cshift, nsc, C0, C0idx, d_cnt);
+  uint32_t nC0 = 0;
+  JX_CK(cudaMemcpyAsync(&nC0, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
+  JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
+  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist, C, Cidx,
+                     d_cnt + 1);
   uint32_t nC = 0;
-  JX_CK(cudaMemcpyAsync(&nC, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&nC, d_cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
   JX_CK(cudaStreamSynchronize(ctx->stream));
   // back to file order
   JX_ALLOC(k64, uint64_t, nC, false);

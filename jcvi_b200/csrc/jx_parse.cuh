@@ -520,8 +520,11 @@ JX_HD int fast_name_end(const WordBytes<W>& B, int p, int limit, int* bar) {
   return -1;
 }
 
+// The fast path in two halves so that the kernel can start the two table probes (long-latency
+// loads) as soon as the names are known and overlap them with the validation of the numeric
+// fields:  fast_line_names  ->  [hash, issue probes]  ->  fast_line_rest.
 template <class W>
-JX_HD bool fast_line(const W& wr, int s, int e, LineTok& t) {
+JX_HD bool fast_line_names(const W& wr, int s, int e, LineTok& t) {
   const WordBytes<W> B(wr);
   t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false;
   if (e - s < 23) return false;
@@ -531,6 +534,12 @@ JX_HD bool fast_line(const W& wr, int s, int e, LineTok& t) {
   const int t2 = fast_name_end(B, t1 + 1, e, &t.sbar);
   if (t2 <= t1 + 1 || t2 - t1 - 1 >= 128) return false;
   t.sa = t1 + 1; t.sb = t2;
+  return true;
+}
+template <class W>
+JX_HD bool fast_line_rest(const W& wr, int e, LineTok& t) {
+  const WordBytes<W> B(wr);
+  const int t2 = t.sb;
   // fields 3..10: non-digit bytes must be exactly: at most one '.' inside field 3, then 8 tabs,
   // no empty field
   int p = t2 + 1;               // start of the current field
@@ -572,6 +581,10 @@ JX_HD bool fast_line(const W& wr, int s, int e, LineTok& t) {
   if (!dec_to_f32(d, t.score)) return false;
   t.nconv = 12;
   return true;
+}
+template <class W>
+JX_HD bool fast_line(const W& wr, int s, int e, LineTok& t) {
+  return fast_line_names(wr, s, e, t) && fast_line_rest(wr, e, t);
 }
 
 // gene_name with the first '|' already located (bar = its position or -1)

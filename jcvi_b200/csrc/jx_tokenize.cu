@@ -386,6 +386,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     }
   }
   out.d_text = d_text;
+  JX_TRACE("tok: text ready");
 
   // record capacity: lines are >= 24 bytes in any real table; retry with the exact worst case
   // (every byte a line) only if that guess overflows.
@@ -437,6 +438,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       unsigned long long init = ~0ull;
       JX_CK(cudaMemcpyAsync(d_stats + 7, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     }
+    JX_TRACE("tok: allocs");
     TokArgs a;
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.recs = recs; a.rec_cap = (uint32_t)cap64;
     a.qtab = Q.table; a.qmask = Q.tmask; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
@@ -460,6 +462,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
     }
+    JX_TRACE("tok: launched+done");
     ctx->tok_bytes += nbytes;
     JX_CK(cudaGetLastError());
     JX_CK(cudaMemcpyAsync(out.stats, d_stats, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));

@@ -156,3 +156,32 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
+    """jcvi_b200.install() against a stand-in `jcvi` package with the import shape of
+    compara/catalog.py:21,23 (`from ..compara.blastfilter import main as blastfilter_main`,
+    `from ..compara.synteny import liftover, mcscan, scan`)."""
+    import importlib
+    pkg = tmp_path / "jcvi" / "compara"
+    pkg.mkdir(parents=True)
+    (tmp_path / "jcvi" / "__init__.py").write_text("")
+    (pkg / "__init__.py").write_text("")
+    (pkg / "blastfilter.py").write_text("def main(args):\n    return 'ref'\ndef blastfilter_main(a, b, c):\n    return 'ref'\n")
+    (pkg / "synteny.py").write_text("def scan(a):\n    return 'ref'\ndef liftover(a):\n    return 'ref'\ndef mcscan(a):\n    return 'ref'\n"
+                                    "def batch_scan(*a, **k):\n    return 'ref'\ndef synteny_scan(*a, **k):\n    return 'ref'\n"
+                                    "def synteny_liftover(*a, **k):\n    return 'ref'\n")
+    (pkg / "catalog.py").write_text("from ..compara.blastfilter import main as blastfilter_main\n"
+                                    "from ..compara.synteny import liftover, mcscan, scan\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for m in [k for k in sys.modules if k == "jcvi" or k.startswith("jcvi.")]:
+        monkeypatch.delitem(sys.modules, m)
+    import jcvi_b200
+    from jcvi_b200.compara import blastfilter as gbf, synteny as gsyn
+    jcvi_b200.install()
+    cat = importlib.import_module("jcvi.compara.catalog")
+    assert cat.blastfilter_main is gbf.main and cat.scan is gsyn.scan and cat.liftover is gsyn.liftover
+    assert cat.mcscan(None) == "ref"                                   # untouched
+    assert importlib.import_module("jcvi.compara.synteny").batch_scan is gsyn.batch_scan
+    for m in [k for k in sys.modules if k == "jcvi" or k.startswith("jcvi.")]:
+        monkeypatch.delitem(sys.modules, m)
