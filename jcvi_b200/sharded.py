@@ -34,14 +34,47 @@ def slice_bounds(text, rank, world):
     return cut(rank), cut(rank + 1)
 
 
-def _gather_bytes(arr, dst=0):
+def _gather_bytes(arr, dst=0, device=None):
+    """Gather variable-length uint8 arrays on rank `dst` (list in rank order; None elsewhere).
+    With the NCCL backend the payload travels GPU to GPU over NVLink."""
+    import torch
     import torch.distributed as dist
     rank, world = rank_world()
     if world == 1 or not dist.is_initialized():
         return [arr]
-    out = [None] * world if rank == dst else None
-    dist.gather_object(arr, out, dst=dst)
-    return out
+    if dist.get_backend() != "nccl":
+        out = [None] * world if rank == dst else None
+        dist.gather_object(arr, out, dst=dst)
+        return out
+    dev = torch.device("cuda", device if device is not None else torch.cuda.current_device())
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = len(arr)
+    dist.all_reduce(sizes)
+    sizes = sizes.tolist()
+    pad = max(max(sizes), 1)
+    mine = torch.zeros(pad, dtype=torch.uint8, device=dev)
+    if len(arr):
+        mine[: len(arr)] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev, non_blocking=True)
+    bufs = [torch.empty(pad, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return [bufs[r][: sizes[r]].cpu().numpy() for r in range(world)]
+
+
+def _as_u8(text):
+    """numpy view of the text; torch CPU tensors (pinned or not) are viewed without a copy."""
+    if hasattr(text, "numpy") and hasattr(text, "is_cuda") and not text.is_cuda:
+        return text.numpy().view(np.uint8).reshape(-1), text
+    return np.asarray(text).view(np.uint8).reshape(-1), None
+
+
+def _slice_for_engine(text_np, owner, lo, hi):
+    """The rank's slice as something Engine accepts; a slice of a pinned torch tensor stays pinned
+    (full PCIe speed for jx_text_upload)."""
+    if owner is not None:
+        return owner.view(-1)[lo:hi] if owner.dtype == __import__("torch").uint8 else text_np[lo:hi]
+    return text_np[lo:hi]
 
 
 def blastfilter_sharded(text, qbed, sbed, is_self, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None,
@@ -52,15 +85,15 @@ def blastfilter_sharded(text, qbed, sbed, is_self, strip_names=True, cscore=0.7,
     rank, world = rank_world()
     eng = engine or get_engine()
     eng.load_pair(qbed, sbed, is_self)
-    text = np.asarray(text).view(np.uint8).reshape(-1)
+    text, owner = _as_u8(text)
     lo, hi = slice_bounds(text, rank, world)
-    ptr, n = eng.cscore_begin(text[lo:hi], strip_names=strip_names, exclude_keys=exclude_keys)
+    ptr, n = eng.cscore_begin(_slice_for_engine(text, owner, lo, hi), strip_names=strip_names, exclude_keys=exclude_keys)
     if world > 1 and dist.is_initialized():
         best = eng.best_table_tensor(ptr, n)
         dist.all_reduce(best, op=dist.ReduceOp.MAX)          # ncclAllReduce(max) over NVLink, in place
         torch.cuda.synchronize(eng.device)
     lines, cnt = eng.cscore_finish(cscore)
-    parts = _gather_bytes(lines)
+    parts = _gather_bytes(lines, device=eng.device)
     if rank != 0:
         return None
     merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
@@ -73,10 +106,10 @@ def liftover_sharded(text, a_qi, a_si, a_block, qbed, sbed, is_self, strip_names
     rank, world = rank_world()
     eng = engine or get_engine()
     eng.load_pair(qbed, sbed, is_self)
-    text = np.asarray(text).view(np.uint8).reshape(-1)
+    text, owner = _as_u8(text)
     lo, hi = slice_bounds(text, rank, world)
-    lines, cnt = eng.near_lines(text[lo:hi], a_qi, a_si, strip_names=strip_names, dist=dist)
-    parts = _gather_bytes(lines)
+    lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist)
+    parts = _gather_bytes(lines, device=eng.device)
     if rank != 0:
         return None
     merged = np.concatenate(parts) if len(parts) > 1 else parts[0]

@@ -17,14 +17,22 @@ d = "/tmp/jx_sharded_%d" % rank
 qbed_p, sbed_p, last = synth.write_dataset(d, "A", "B", 77, 40000, 40000, hits, Kq=12, Ks=12)   # same seed on every rank
 qbed, sbed = Bed(qbed_p), Bed(sbed_p)
 text = np.fromfile(last, dtype=np.uint8)
+pin = torch.from_numpy(text).pin_memory()          # each rank only uploads ITS slice, over its own PCIe link
 eng = get_engine(local)
-for it in range(3):
+best = 1e9
+for it in range(5):
     dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = blastfilter_sharded(text, qbed, sbed, False, cscore=0.7)
+    res = blastfilter_sharded(pin, qbed, sbed, False, cscore=0.7)
     torch.cuda.synchronize(); dist.barrier(); t1 = time.perf_counter()
+    best = min(best, t1 - t0)
+t0, t1 = 0.0, best
 if rank == 0:
     eng.load_pair(qbed, sbed, False)
-    whole = eng.blastfilter(text, cscore=0.7)
+    single = 1e9
+    for it in range(3):
+        torch.cuda.synchronize(); ts = time.perf_counter()
+        whole = eng.blastfilter(eng.upload(pin), cscore=0.7)
+        torch.cuda.synchronize(); single = min(single, time.perf_counter() - ts)
     ok = bytes(memoryview(whole.text)) == bytes(memoryview(res.text))
     sc = eng.scan_text(res.text)
     blk = np.repeat(np.arange(sc.n_blocks, dtype=np.int32), np.diff(sc.block_start))
@@ -36,7 +44,7 @@ lf = liftover_sharded(text, a[0], a[1], a[2], qbed, sbed, False, dist=10)
 if rank == 0:
     full = eng.liftover_text(text, a[0], a[1], a[2], dist=10)
     ok2 = all(np.array_equal(getattr(full, k), getattr(lf, k)) for k in ("q_rank", "s_rank", "block", "accepted", "score"))
-    print("SHARDED world=%d hits=%d filtered=%d identical_filtered=%s identical_lifted=%s (%d lifted) sharded_blastfilter_s=%.4f"
-          % (world, hits, res.n, ok, ok2, lf.n_lifted, t1 - t0), flush=True)
+    print("SHARDED world=%d hits=%d filtered=%d identical_filtered=%s identical_lifted=%s (%d lifted) sharded_blastfilter_host_to_host_s=%.4f single_gpu_s=%.4f"
+          % (world, hits, res.n, ok, ok2, lf.n_lifted, t1 - t0, single), flush=True)
 dist.barrier()
 dist.destroy_process_group()
