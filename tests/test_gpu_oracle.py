@@ -192,3 +192,57 @@ def test_nearest_anchor_matches_scipy(mods):
             want = [(tuple(p), tuple(a[k])) for p, dd, k in zip(q, d, i) if k != len(a) and dd != 0]
             got = [(tuple(p), nn) for p, nn in syn.synteny_liftover(q, a, dist)]
             assert got == want, (n, dist)
+
+
+def test_tandems_only_side_outputs(tmp_path, mods):
+    """--tandems_only: `.localdups` and `.nolocaldups.bed` (write_localdups / write_new_bed,
+    blastfilter.py:164-197) from the device's mother maps, against the oracle."""
+    import oracle
+    from jcvi_b200 import synth
+    bf, _ = mods
+    for self_mode in (False, True):
+        d = str(tmp_path / ("self" if self_mode else "pair"))
+        q, s = ("A", "A") if self_mode else ("A", "B")
+        qbed, sbed, last = synth.write_dataset(d, q, s, 61, 4000, 4000, 120000, Kq=5, Ks=5, self_mode=self_mode, p_tandem=0.25)
+        if self_mode:
+            sbed = qbed
+        o = lambda f: os.path.join(d, "orc." + f)
+        oracle.blastfilter(last, qbed, sbed, out_path=o("filtered"), cscore=0.5, qdups=o("q.localdups"),
+                           sdups=None if self_mode else o("s.localdups"), qnewbed=o("q.nolocaldups.bed"),
+                           snewbed=None if self_mode else o("s.nolocaldups.bed"))
+        bf.main([last, "--qbed=" + qbed, "--sbed=" + sbed, "--cscore=0.5", "--tandems_only"])
+        assert read(last + ".filtered") == read(o("filtered"))
+        assert read(os.path.splitext(qbed)[0] + ".localdups") == read(o("q.localdups"))
+        assert read(os.path.splitext(qbed)[0] + ".nolocaldups.bed") == read(o("q.nolocaldups.bed"))
+        assert len(read(o("q.localdups"))) > 100
+        if not self_mode:
+            assert read(os.path.splitext(sbed)[0] + ".localdups") == read(o("s.localdups"))
+            assert read(os.path.splitext(sbed)[0] + ".nolocaldups.bed") == read(o("s.nolocaldups.bed"))
+
+
+def test_batch_scan_on_hit_objects(mods):
+    """batch_scan with objects carrying qseqid/sseqid/qi/si/score (synteny.py:239-252,437-452):
+    groups are scanned in sorted chromosome-pair order."""
+    _, syn = mods
+
+    class Hit(object):
+        def __init__(self, qseqid, sseqid, qi, si, score):
+            self.qseqid, self.sseqid, self.qi, self.si, self.score = qseqid, sseqid, qi, si, score
+
+    rng = np.random.default_rng(11)
+    hits, seen = [], set()
+    for cp in [("chr2", "c1"), ("chr10", "c1"), ("chr1", "c2"), ("chr1", "c10")]:
+        base = int(rng.integers(0, 1000))
+        for k in range(400):
+            x = base + int(rng.integers(0, 300)); y = x + int(rng.integers(-15, 16)) if rng.random() < 0.8 else int(rng.integers(0, 2000))
+            if (cp, x, y) in seen or y < 0:
+                continue
+            seen.add((cp, x, y))
+            hits.append(Hit(cp[0], cp[1], x, y, float(rng.integers(10, 500))))
+    rng.shuffle(hits)
+    got = syn.batch_scan(hits, xdist=12, ydist=12, N=3)
+    want = []
+    for cp in sorted(set((h.qseqid, h.sseqid) for h in hits)):
+        pts = [(h.qi, h.si, h.score) for h in hits if (h.qseqid, h.sseqid) == cp]
+        want.extend(syn.synteny_scan(pts, 12, 12, 3))
+    assert got == want and len(got) >= 4
