@@ -27,38 +27,38 @@ def _exclude_keys(exclude, qorder, sorder):
     return np.array(keys, dtype=np.uint64)
 
 
+def tandem_families(mother, bed):
+    """Families of local duplicates from the device's mother map, each ordered like the reference
+    orders them (longest gene first, then accn: write_localdups, blastfilter.py:164-175); the
+    first member is the family's mother."""
+    members = {}
+    for gene, m in enumerate(mother):
+        if m != gene:
+            members.setdefault(int(m), {int(m)}).add(gene)
+    fams = []
+    for ranks in members.values():
+        feats = sorted((bed[i] for i in ranks), key=lambda f: (-abs(f.end - f.start), f.accn))
+        fams.append([f.accn for f in feats])
+    fams.sort()
+    return fams
+
+
 def write_localdups(mother, bed, dups_fh=None):
-    """write_localdups (blastfilter.py:164-185) from the device's mother map."""
-    groups = {}
-    for g, m in enumerate(mother):
-        if m != g:
-            groups.setdefault(int(m), [int(m)]).append(g)
-    tandem_groups = []
-    for m, members in groups.items():
-        rows = [bed[i] for i in members]
-        rows.sort(key=lambda a: (-abs(a.end - a.start), a.accn))
-        tandem_groups.append([x.accn for x in rows])
-    dups_to_mother = {}
-    n = 1
-    for accns in sorted(tandem_groups):
-        if dups_fh:
-            print("\t".join(accns), file=dups_fh)
-            if n:
-                n -= 1
-                logger.debug("write local dups to file {}".format(dups_fh.name))
-        for dup in accns[1:]:
-            dups_to_mother[dup] = accns[0]
-    return dups_to_mother
+    """-> {duplicate accn: mother accn}; one tab-separated family per line into dups_fh."""
+    fams = tandem_families(mother, bed)
+    if dups_fh and fams:
+        logger.debug("write local dups to file {}".format(dups_fh.name))
+        dups_fh.write("".join("\t".join(f) + "\n" for f in fams))
+    return {dup: f[0] for f in fams for dup in f[1:]}
 
 
 def write_new_bed(bed, children):
-    out_name = "%s.nolocaldups%s" % op.splitext(bed.filename)
+    """<bed>.nolocaldups.bed: the annotation without the collapsed duplicates (blastfilter.py:188-197)."""
+    stem, ext = op.splitext(bed.filename)
+    out_name = stem + ".nolocaldups" + ext
     logger.debug("write tandem-filtered bed file %s" % out_name)
     with open(out_name, "w") as fh:
-        for row in bed:
-            if row["accn"] in children:
-                continue
-            print(row, file=fh)
+        fh.write("".join(str(row) + "\n" for row in bed if row.accn not in children))
 
 
 def blastfilter_main(blast_file, p, opts):
@@ -92,22 +92,26 @@ def blastfilter_main(blast_file, p, opts):
     return res
 
 
+_OPTIONS = (
+    (("--tandems_only",), dict(dest="tandems_only", action="store_true", default=False,
+                               help="also write <bed>.localdups and <bed>.nolocaldups.bed")),
+    (("--tandem_Nmax",), dict(type=int, default=10, help="collapse tandem copies at most this many genes apart")),
+    (("--cscore",), dict(type=float, default=0.7,
+                         help="keep a hit when score / max(best score of either gene) exceeds this; 0 disables")),
+    (("--exclude",), dict(help="anchors file whose pairs are dropped (either orientation)")),
+)
+
+
 def main(args):
     p = OptionParser(__doc__)
     p.set_beds()
     p.set_stripnames()
-    p.add_argument("--tandems_only", dest="tandems_only", action="store_true", default=False,
-                   help="only calculate tandems, write .localdup file and exit.")
-    p.add_argument("--tandem_Nmax", type=int, default=10, help="merge tandem genes within distance")
-    p.add_argument("--cscore", type=float, default=0.7,
-                   help="retain hits that have good bitscore. a value of 0.5 means keep all values that are 50%% "
-                        "or greater of the best hit. higher is more stringent")
-    p.add_argument("--exclude", help="Remove anchors from a previous run")
+    for flags, kw in _OPTIONS:
+        p.add_argument(*flags, **kw)
     opts, args = p.parse_args(args)
     if len(args) != 1:
         sys.exit(not p.print_help())
-    (blastfile,) = args
-    blastfilter_main(blastfile, p, opts)
+    blastfilter_main(args[0], p, opts)
 
 
 if __name__ == "__main__":

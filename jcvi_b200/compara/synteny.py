@@ -23,17 +23,17 @@ def _score(cluster):
 
 
 def get_bed_filenames(hintfile, p, opts):
-    """synteny.py:476-488"""
-    wd, hintfile = op.split(hintfile)
-    if not (opts.qbed and opts.sbed):
-        try:
-            q, s = hintfile.split(".", 2)[:2]
-            opts.qbed = op.join(wd, q + ".bed")
-            opts.sbed = op.join(wd, s + ".bed")
-            logger.debug("Assuming --qbed={0} --sbed={1}".format(opts.qbed, opts.sbed))
-        except:  # noqa: E722  (mirrors the reference)
-            print("Options --qbed and --sbed are required", file=sys.stderr)
-            sys.exit(not p.print_help())
+    """--qbed/--sbed, or <dir>/<X>.bed and <dir>/<Y>.bed inferred from a file called X.Y.*
+    (synteny.py:476-488)."""
+    if opts.qbed and opts.sbed:
+        return opts.qbed, opts.sbed
+    folder, base = op.split(hintfile)
+    stems = base.split(".")
+    if len(stems) < 2:
+        print("Options --qbed and --sbed are required", file=sys.stderr)
+        sys.exit(not p.print_help())
+    opts.qbed, opts.sbed = (op.join(folder, x + ".bed") for x in stems[:2])
+    logger.debug("Assuming --qbed={0} --sbed={1}".format(opts.qbed, opts.sbed))
     return opts.qbed, opts.sbed
 
 
@@ -129,36 +129,33 @@ def synteny_liftover(points, anchors, dist):
 
 
 # ---- actions -------------------------------------------------------------------------------------
+def _describe(values):
+    v = np.array(values)
+    return "Min={} Max={} N={} Mean={:.2f} SD={:.2f} Median={} Sum={}".format(
+        v.min(), v.max(), v.size, np.mean(v), np.std(v), np.median(v), v.sum())
+
+
 def summary(args):
-    """synteny.py:1445-1484 (stderr statistics; ValueError when no anchor was found)."""
+    """Block statistics on stderr; ValueError when the file holds no anchor (synteny.py:1445-1484)."""
     p = OptionParser(summary.__doc__)
     p.add_argument("--prefix", help="Generate per block stats")
     opts, args = p.parse_args(args)
     if len(args) != 1:
         sys.exit(not p.print_help())
-    (anchorfile,) = args
-    ac = AnchorFile(anchorfile)
-    clusters = ac.blocks
-    if clusters == [[]]:
+    blocks = AnchorFile(args[0]).blocks
+    if blocks == [[]]:
         logger.debug("A total of 0 anchor was found. Aborted.")
         raise ValueError("A total of 0 anchor was found. Aborted.")
-    nclusters = len(clusters)
-    nanchors = [len(c) for c in clusters]
-    nranchors = [_score(c) for c in clusters]
-    print("A total of {0} (NR:{1}) anchors found in {2} clusters.".format(sum(nanchors), sum(nranchors), nclusters),
-          file=sys.stderr)
-
-    def stats(a):
-        a = np.array(a)
-        return "Min={} Max={} N={} Mean={:.2f} SD={:.2f} Median={} Sum={}".format(
-            a.min(), a.max(), a.size, np.mean(a), np.std(a), np.median(a), a.sum())
-
-    print("Stats:", stats(nanchors), file=sys.stderr)
-    print("NR stats:", stats(nranchors), file=sys.stderr)
+    sizes = [len(b) for b in blocks]
+    nr_sizes = [_score(b) for b in blocks]          # non-redundant: min(#distinct a, #distinct b)
+    err = sys.stderr
+    print("A total of {0} (NR:{1}) anchors found in {2} clusters.".format(sum(sizes), sum(nr_sizes), len(blocks)), file=err)
+    print("Stats:", _describe(sizes), file=err)
+    print("NR stats:", _describe(nr_sizes), file=err)
     if opts.prefix:
-        pad = len(str(nclusters))
-        for i, c in enumerate(clusters):
-            print("\t".join(("{0}{1:0{2}d}".format(opts.prefix, i + 1, pad), str(len(c)))))
+        width = len(str(len(blocks)))
+        for i, n in enumerate(sizes, 1):
+            print("{0}{1:0{2}d}\t{3}".format(opts.prefix, i, width, n))
 
 
 def _int_str(x):

@@ -24,34 +24,28 @@ def natsort_key(s):
 
 
 class BedLine(object):
+    """One BED feature with the attribute names the reference's callers use (formats/bed.py:40-73):
+    `start` is 1-based (column 2 + 1), `accn` is column 4, optional score / strand / extra."""
+
     __slots__ = ("seqid", "start", "end", "accn", "extra", "score", "strand", "args", "nargs")
 
     def __init__(self, sline):
-        args = sline.strip().split("\t")
-        self.nargs = nargs = len(args)
-        self.seqid = args[0]
-        self.start = int(args[1]) + 1
-        self.end = int(args[2])
+        cols = sline.strip().split("\t")
+        n = len(cols)
+        self.args, self.nargs = cols, n
+        self.seqid = cols[0]
+        self.start, self.end = int(cols[1]) + 1, int(cols[2])
         assert self.start <= self.end, "start={0} end={1}".format(self.start, self.end)
-        self.extra = self.accn = self.score = self.strand = None
-        if nargs > 3:
-            self.accn = args[3]
-        if nargs > 4:
-            self.score = args[4]
-        if nargs > 5:
-            self.strand = args[5]
-        if nargs > 6:
-            self.extra = args[6:]
-        self.args = args
+        self.accn = cols[3] if n > 3 else None
+        self.score = cols[4] if n > 4 else None
+        self.strand = cols[5] if n > 5 else None
+        self.extra = cols[6:] if n > 6 else None
 
     def __str__(self):
-        args = [self.seqid, self.start - 1, self.end]
-        for x in (self.accn, self.score, self.strand):
-            if x is not None:
-                args.append(x)
-        if self.extra is not None:
-            args += self.extra
-        return "\t".join(str(x) for x in args)
+        out = [self.seqid, str(self.start - 1), str(self.end)]
+        out += [x for x in (self.accn, self.score, self.strand) if x is not None]
+        out += [str(x) for x in (self.extra or [])]
+        return "\t".join(out)
 
     __repr__ = __str__
 
@@ -59,7 +53,16 @@ class BedLine(object):
         return getattr(self, key)
 
 
+def _is_feature_line(line):
+    """Bed.__init__ (formats/bed.py:154-160) skips blank lines, '#' comments and browser / track
+    declarations."""
+    return bool(line.strip()) and line[0] != "#" and not line.startswith(("browser ", "track name"))
+
+
 class Bed(list):
+    """Features sorted by (natural-sort key of seqid, start, accn): the index in this list is the
+    gene RANK every kernel works with (formats/bed.py:147,166-167,196-198)."""
+
     def __init__(self, filename=None, key=None, sorted=True):
         super().__init__()
         self.filename = filename
@@ -69,23 +72,19 @@ class Bed(list):
         if not filename:
             return
         with open(filename) as fp:
-            for line in fp:
-                if line.strip() == "" or line[0] == "#" or line.startswith("browser ") or line.startswith("track name"):
-                    continue
-                self.append(BedLine(line))
+            self.extend(BedLine(line) for line in fp if _is_feature_line(line))
         if sorted:
             self.sort(key=self.key)
 
     @property
     def order(self):
-        return dict((f.accn, (i, f)) for (i, f) in enumerate(self))
+        """accn -> (rank, BedLine); for duplicated accns the later rank wins, like the reference's
+        dict comprehension."""
+        return {f.accn: (i, f) for i, f in enumerate(self)}
 
     @property
     def seqids(self):
-        seen = {}
-        for b in self:
-            seen.setdefault(b.seqid, None)
-        return sorted(seen, key=natsort_key)
+        return sorted({b.seqid for b in self}, key=natsort_key)
 
     # ---- device tables ---------------------------------------------------------------------
     def tables(self):
