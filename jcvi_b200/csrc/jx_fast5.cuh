@@ -1,0 +1,322 @@
+// Tokenizer fast path, version 5: byte classes are computed ONCE per tile, cooperatively and
+// branch-free (every lane does the same work), and kept as two bit-per-byte masks in shared
+// memory:
+//     W  : byte <= 0x20          (tab, the terminators, space and the other control bytes)
+//     N  : byte is neither a decimal digit nor a tab
+// With them the per-line parse of a REGULAR line (12 fields, 11 single tabs, <= 128 bytes; what
+// LAST / BLAST+ / DIAMOND / MMseqs2 write) needs no loop over the text at all: field boundaries
+// are the set bits of W, "all digits" is "no bit of N", and the numeric fields are converted with
+// word arithmetic.  The instruction stream is the same for every lane of a warp, which is what
+// the previous (byte- and word-scanning) versions lacked.  Anything irregular is refused here and
+// goes to jx::tokenize_line, the generic sscanf-faithful scanner, so this path only has to be
+// exact on what it accepts (tests/test_parse_host.py checks the two against each other).
+//
+// Reference semantics being reproduced: src/jcvi/formats/cblast.pyx:15,106-112 (sscanf of the 12
+// fields), src/jcvi/utils/cbook.py:308-329 (gene_name).
+#pragma once
+#include "jx_parse.cuh"
+
+namespace jx {
+
+// ---- phase A: classification -------------------------------------------------------------------
+// 4 text bytes -> 0x80 flags per byte.  `hi` accumulates bit 7 of (low7 + 4): set when a byte's low
+// seven bits are >= 0x7C, i.e. the tile may contain a '|' (gene_name cuts there).
+JX_HD void classify4(uint32_t x, uint32_t& wf, uint32_t& nf, uint32_t& hi) {
+  const uint32_t a = x & 0x7F7F7F7Fu;
+  wf = ~((a + 0x5F5F5F5Fu) | x) & 0x80808080u;                  // low7 < 0x21 and bit7 clear
+  const uint32_t dig = (a + 0x50505050u) & ~(a + 0x46464646u);   // bit7: 0x30 <= low7 <= 0x39
+  const uint32_t tab = (a + 0x77777777u) & ~(a + 0x76767676u);   // bit7: low7 == 0x09
+  nf = ~((dig | tab) & ~x) & 0x80808080u;
+  hi |= a + 0x04040404u;
+}
+// flags of 8 consecutive bytes (two words) -> 8 mask bits in text order
+JX_HD uint32_t gather8(uint32_t f0, uint32_t f1) { return (((f0 >> 4) | f1) * 0x00204081u) >> 24; }
+
+// 32 text bytes (8 aligned words) -> one word of each mask
+JX_HD void classify32(const uint32_t* w, uint32_t& wmask, uint32_t& nmask, uint32_t& hi) {
+  uint32_t wm = 0, nm = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    uint32_t w0, n0, w1, n1;
+    classify4(w[2 * k], w0, n0, hi);
+    classify4(w[2 * k + 1], w1, n1, hi);
+    wm |= gather8(w0, w1) << (8 * k);
+    nm |= gather8(n0, n1) << (8 * k);
+  }
+  wmask = wm; nmask = nm;
+}
+
+// ---- small bit helpers ----------------------------------------------------------------------------
+JX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {      // low word of (hi:lo) >> sh, 0 <= sh < 32
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, (uint32_t)sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+JX_HD int ctz32(uint32_t x) {                                    // x != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+JX_HD int ctz64(uint64_t x) {                                    // x != 0
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+JX_HD int hibit32(uint32_t x) {                                  // x != 0
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)x);
+#else
+  return 31 - __builtin_clz(x);
+#endif
+}
+JX_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+JX_HD uint32_t below32(int k) { return k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u); }   // bits < k, 0 <= k
+JX_HD uint64_t below64(int k) { return k >= 64 ? ~0ull : ((1ull << k) - 1ull); }      // bits < k, 0 <= k
+
+// `M` yields mask words: m(i) covers bytes [32 i, 32 i + 32) of the buffer
+template <class M>
+JX_HD uint32_t bits32(const M& m, int pos) {                     // mask bits of bytes [pos, pos + 32)
+  const int i = pos >> 5;
+  return funnel_r(m(i), m(i + 1), pos & 31);
+}
+template <class M>
+JX_HD uint64_t bits64(const M& m, int pos) {                     // mask bits of bytes [pos, pos + 64)
+  const int i = pos >> 5, sh = pos & 31;
+  const uint32_t x0 = m(i), x1 = m(i + 1), x2 = m(i + 2);
+  return (uint64_t)funnel_r(x0, x1, sh) | ((uint64_t)funnel_r(x1, x2, sh) << 32);
+}
+
+// ---- numeric fields from words ------------------------------------------------------------------------
+// four ASCII-minus-'0' digits d0 d1 d2 d3 (d0 in the low byte) -> d0 d1 d2 d3 as a number
+JX_HD uint32_t digits4(uint32_t w) {
+  const uint32_t t = w * 10u + (w >> 8);              // byte0 = 10 d0 + d1, byte2 = 10 d2 + d3 (no carries: <= 99)
+  return (t & 0xFFu) * 100u + ((t >> 16) & 0xFFu);
+}
+// The first `n` (1..8) bytes of (w1:w0) are text; bytes [0,n) except an optional '.' at index `dot`
+// (-1: none) are decimal digits.  Returns the digits as an integer (< 10^8).
+JX_HD uint32_t digits_upto8(uint32_t w0, uint32_t w1, int n, int dot) {
+  uint64_t v = (uint64_t)w0 | ((uint64_t)w1 << 32);
+  int nd = n;
+  if (dot >= 0) {                                      // close the gap left by the '.'
+    const uint64_t lowm = (1ull << (8 * dot)) - 1ull;
+    v = (v & lowm) | ((v >> 8) & ~lowm);
+    --nd;
+  }
+  v = (v - 0x3030303030303030ull) << (8 * (8 - nd));   // right-justify: leading bytes become 0
+  return digits4((uint32_t)v) * 10000u + digits4((uint32_t)(v >> 32));
+}
+
+#define JX_POW10U32 {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u}
+#define JX_POW10F32 {1e0f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f}   /* all exact in float32 */
+static const uint32_t kPow10u32Host[10] = JX_POW10U32;
+static const float kPow10f32Host[11] = JX_POW10F32;
+#if defined(__CUDACC__)
+static __constant__ uint32_t kPow10u32Dev[10] = JX_POW10U32;
+static __constant__ float kPow10f32Dev[11] = JX_POW10F32;
+#endif
+JX_HD uint32_t pow10_u32(int k) {                      // 0 <= k <= 9
+#if defined(__CUDA_ARCH__)
+  return kPow10u32Dev[k];
+#else
+  return kPow10u32Host[k];
+#endif
+}
+JX_HD float pow10_f32(int k) {                         // 0 <= k <= 10
+#if defined(__CUDA_ARCH__)
+  return kPow10f32Dev[k];
+#else
+  return kPow10f32Host[k];
+#endif
+}
+
+// A numeric field = bytes [p, p+L) of the buffer, `nb` = its N bits (bit i: byte p+i is not a digit).
+// Accepts  D+ [ '.' D* ] [ (e|E) [+-] D{1,3} ]  and '.' D+ forms with a mantissa of <= 8 bytes and
+// yields value = m * 10^e10 (m < 10^8, all digits kept).  Anything else: false (generic scanner).
+template <class BR>
+JX_HD bool decimal5(const BR& B, int p, int L, uint32_t nb, uint32_t& m, int& e10) {
+  if (L < 1 || L > 14) return false;
+  int dot = -1, epos = L, estart = L;
+  bool eneg = false;
+  if (nb) {
+    const int b1 = ctz32(nb);
+    const uint32_t c1 = B(p + b1);
+    uint32_t rest = nb & (nb - 1u);
+    int ep = -1;
+    if (c1 == '.') {
+      dot = b1;
+      if (rest) { ep = ctz32(rest); rest &= rest - 1u; }
+    } else {
+      ep = b1;
+    }
+    if (ep >= 0) {
+      if ((B(p + ep) | 0x20u) != 'e') return false;
+      epos = ep; estart = ep + 1;
+      if (rest) {                                        // only a sign right after the 'e' may remain
+        if (rest != (1u << (ep + 1))) return false;
+        const uint32_t cs = B(p + ep + 1);
+        if (cs == '-') eneg = true; else if (cs != '+') return false;
+        estart = ep + 2;
+      }
+    } else if (rest) return false;
+  }
+  const int nman = epos, nexp = L - estart;              // mantissa bytes (with the dot), exponent digits
+  if (nman < 1 || nman > 8 || nman - (dot >= 0) < 1) return false;
+  if (epos < L && (nexp < 1 || nexp > 3)) return false;
+  m = digits_upto8(B.load32(p), B.load32(p + 4), nman, dot);
+  int ex = 0;
+  if (epos < L) {
+    const uint32_t w = B.load32(p + L - 4);              // the exponent digits are the last bytes of the field
+    const uint32_t keep = ~below32(8 * (4 - nexp));      // mask before subtracting: no borrow out of 'e' / '-'
+    ex = (int)digits4((w & keep) - (0x30303030u & keep));
+    if (eneg) ex = -ex;
+  }
+  e10 = ex - (dot >= 0 ? nman - 1 - dot : 0);
+  return true;
+}
+
+// evalue: flag = (value < 1e-10), decided like dec_lt_1e10 (<= 8 significant digits: integer compare)
+template <class BR>
+JX_HD bool evalue5(const BR& B, int p, int L, uint32_t nb, int& flag) {
+  uint32_t m; int e10;
+  if (!decimal5(B, p, L, nb, m, e10)) return false;
+  const int k = -10 - e10;                               // value < 1e-10  <=>  m < 10^k
+  const int kc = k < 0 ? 0 : (k > 9 ? 9 : k);
+  flag = (m == 0u || k >= 9 || (k > 0 && m < pow10_u32(kc))) ? 1 : 0;
+  return true;
+}
+
+// score -> float32 exactly like strtof: an integer < 2^24 divided by an exact power of ten is one
+// correctly rounded operation; everything else goes through dec_to_f32's exact routes
+template <class BR>
+JX_HD bool score5(const BR& B, int p, int L, uint32_t nb, float& out) {
+  uint32_t m; int e10;
+  if (!decimal5(B, p, L, nb, m, e10)) return false;
+  if (m < (1u << 24) && e10 <= 0 && e10 >= -10) {
+    const float fm = (float)m;
+#if defined(__CUDA_ARCH__)
+    out = __fdiv_rn(fm, pow10_f32(-e10));
+#else
+    out = fm / pow10_f32(-e10);
+#endif
+    return true;
+  }
+  Dec d; d.m = m; d.e10 = m ? e10 : 0; d.neg = false; d.ok = true; d.dropped = false; d.special = false;
+  return dec_to_f32(d, out);
+}
+
+// ---- the line ----------------------------------------------------------------------------------------------
+// [s, e) = the line without its terminator.  `B` = byte / unaligned-word view of the text,
+// `mw` / `mn` = W / N mask words of the same buffer.  Three windows of mask bits cover the line:
+//   64 bits from the line start     -> tabs 1..3 (both names and pctid must end inside it)
+//   64 bits from tab 3              -> fields 4..10 up to tab 10
+//   the last 32 bits of the line    -> tabs 10, 11, evalue and score
+// Fills the name spans, score and evalue flag; `qbar`/`sbar` are left at -2 ("not searched": the
+// caller knows whether the tile can contain a '|').
+template <class BR, class MW, class MN>
+JX_HD bool fast_line5(const BR& B, const MW& mw, const MN& mn, int s, int e, LineTok& t) {
+  t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false; t.qbar = t.sbar = -2;
+  const int len = e - s;
+  if (len < 23) return false;
+  // tabs 1..3: the first three bytes <= 0x20; all three must be tabs (a tab is not in N), no empty field
+  const uint64_t N0 = bits64(mn, s);
+  uint64_t W0 = bits64(mw, s);
+  if (len < 64) W0 &= below64(len);
+  if (popc64(W0) < 3) return false;
+  const int t0 = ctz64(W0);
+  const uint64_t W1 = W0 & (W0 - 1ull);
+  const int t1 = ctz64(W1);
+  const uint64_t W2 = W1 & (W1 - 1ull);
+  const int t2 = ctz64(W2);
+  const uint64_t upto_t2 = W2 ^ (W2 - 1ull);             // bits <= t2 (plus nothing else: W2's lowest bit is t2)
+  if ((W0 & N0 & upto_t2) != 0ull || t0 < 1 || t1 - t0 < 2 || t2 - t1 < 2) return false;
+  // field 3 (pctid): digits with at most one '.', at least one digit
+  const int lp = t2 - t1 - 1;
+  if (lp > 32) return false;
+  const uint32_t pb = (uint32_t)(N0 >> (t1 + 1)) & below32(lp);
+  if (pb) {
+    if ((pb & (pb - 1u)) || lp < 2 || B(s + t1 + 1 + ctz32(pb)) != '.') return false;
+  }
+  // tabs 10, 11 from the end of the line
+  const int a = len > 32 ? len - 32 : 0;
+  const uint32_t Nt = bits32(mn, s + a);
+  const uint32_t Wt = bits32(mw, s + a) & below32(len - a);
+  if (!Wt) return false;
+  const int h10 = hibit32(Wt);
+  const uint32_t Wt2 = Wt & ~(1u << h10);
+  if (!Wt2) return false;
+  const int h9 = hibit32(Wt2);
+  if (((Nt >> h10) | (Nt >> h9)) & 1u) return false;     // both must be tabs
+  const int t10 = a + h10, t9 = a + h9;
+  // fields 4..10: between tab 3 and tab 10 exactly 6 more tabs, digits otherwise, no empty field
+  const int dm = t9 - t2;
+  if (dm < 2 || dm > 63) return false;
+  const uint64_t Wm = bits64(mw, s + t2), Nm = bits64(mn, s + t2);
+  const uint64_t mid = below64(dm + 1);                  // tab 3 .. tab 10 inclusive
+  if (popc64(Wm & mid) != 8 || (Nm & mid) != 0ull || (Wm & (Wm >> 1) & mid) != 0ull) return false;
+  const int le = t10 - t9 - 1, ls = len - t10 - 1;
+  if (le > 14 || ls > 14) return false;
+  const uint32_t eb = (Nt >> (h9 + 1)) & below32(le);
+  const uint32_t sb = (h10 < 31 ? (Nt >> (h10 + 1)) : 0u) & below32(ls);
+  if (!evalue5(B, s + t9 + 1, le, eb, t.eflag)) return false;
+  if (!score5(B, s + t10 + 1, ls, sb, t.score)) return false;
+  t.qa = s; t.qb = s + t0; t.sa = s + t0 + 1; t.sb = s + t1;
+  t.nconv = 12;
+  return true;
+}
+
+// position of the first '|' in [a, b), or -1 (only called for tiles that may hold one)
+template <class BR>
+JX_HD int find_bar(const BR& B, int a, int b) {
+  int bar = -1;
+  for (int p = a; p < b && bar < 0; p += 4) {
+    const uint32_t f = swar_eq(B.load32(p), 0x7C7C7C7Cu);
+    if (f) { const int q = p + first_flag(f); if (q < b) bar = q; }
+  }
+  return bar;
+}
+
+// gene_name with the first '|' already located (bar = its position or -1); cbook.py:308-329
+template <class BR>
+JX_HD int strip5(const BR& B, int a, int b, int bar) {
+  const int end = bar >= 0 ? bar : b;
+  if (end - a < 2) return end;
+  const bool ev = B(a) == 'e' && B(a + 1) == 'v';
+  // rsplit('.', 1) leaves a one-character suffix iff the last '.' sits at end-2
+  return (!ev && B(end - 2) == '.' && B(end - 1) != '.') ? end - 2 : end;
+}
+
+// word hash of [a, b) streaming aligned words (one load + one funnel shift per 4 bytes)
+template <class TW>
+JX_HD uint64_t fast_hash5(const TW& wr, int a, int b) {
+  NameHash h; h.init();
+  const int sh = (a & 3) * 8, len = b - a;
+  int i = a >> 2;
+  uint32_t cur = wr(i);
+  int rem = len;
+  for (; rem > 4; rem -= 4) {
+    const uint32_t nxt = wr(++i);
+    h.word(funnel_r(cur, nxt, sh));
+    cur = nxt;
+  }
+  if (rem > 0) {
+    const uint32_t w = funnel_r(cur, wr(i + 1), sh);
+    h.word(rem < 4 ? (w & ((1u << (8 * rem)) - 1u)) : w);
+  }
+  return h.finish((uint32_t)len);
+}
+
+}  // namespace jx

@@ -5,6 +5,8 @@
 #include <cstring>
 #include "jx_parse.cuh"
 #include "jx_format.cuh"
+#include "jx_fast5.cuh"
+#include <vector>
 
 namespace {
 struct PtrReader { const unsigned char* p; inline uint32_t operator()(int i) const { return p[i]; } };
@@ -174,6 +176,46 @@ int probe_fast_line4(const char* buf, int s, int e, int* spans, float* score, in
     else { uint64_t h2; strip_ends[k] = jx::fast_strip_hash(B, a, b, true, h2); hashes[k] = h2; }
   }
   return 1;
+}
+
+// v5: masks built with the kernel's own classifier over a padded copy of the buffer
+int probe_fast_line5(const char* buf, int buflen, int s, int e, int* spans, float* score, int* eflag, int* strip_ends,
+                     unsigned long long* hashes) {
+  const int padded = ((buflen + 31) / 32) * 32 + 256;
+  std::vector<unsigned char> text((size_t)padded, (unsigned char)'\n');
+  memcpy(text.data(), buf, (size_t)buflen);
+  std::vector<uint32_t> mw((size_t)padded / 32), mn((size_t)padded / 32);
+  uint32_t hi = 0;
+  for (int seg = 0; seg < padded / 32; ++seg) {
+    uint32_t w[8];
+    memcpy(w, text.data() + 32 * seg, 32);
+    jx::classify32(w, mw[(size_t)seg], mn[(size_t)seg], hi);
+  }
+  struct MaskRd { const uint32_t* p; inline uint32_t operator()(int i) const { return p[i]; } };
+  WordRd wr{text.data()};
+  MaskRd rw{mw.data()}, rn{mn.data()};
+  jx::LineTok t;
+  jx::WordBytes<WordRd> B(wr);
+  if (!jx::fast_line5(B, rw, rn, s, e, t)) return 0;
+  spans[0] = t.qa; spans[1] = t.qb; spans[2] = t.sa; spans[3] = t.sb;
+  *score = t.score; *eflag = t.eflag;
+  const bool maybe_bar = (hi & 0x80808080u) != 0u;
+  for (int k = 0; k < 2; ++k) {
+    const int a = k ? t.sa : t.qa, b = k ? t.sb : t.qb;
+    const int bar = maybe_bar ? jx::find_bar(B, a, b) : -1;
+    strip_ends[k] = jx::strip5(B, a, b, bar);
+    hashes[k] = jx::fast_hash5(wr, a, strip_ends[k]);
+  }
+  return 1;
+}
+
+// byte classes of one 32-byte block: the kernel's SWAR classifier (for comparison with the definition)
+void probe_classify32(const unsigned char* bytes32, unsigned* wmask, unsigned* nmask, unsigned* hi) {
+  uint32_t w[8];
+  memcpy(w, bytes32, 32);
+  uint32_t h = 0, a, b;
+  jx::classify32(w, a, b, h);
+  *wmask = a; *nmask = b; *hi = h & 0x80808080u;
 }
 
 }  // extern "C"

@@ -7,15 +7,19 @@
 //   qorder[query]/sorder[..]  src/jcvi/compara/blastfilter.py:56-84, synteny.py:261-283, 339-357
 //   filter_cscore pass 1      src/jcvi/compara/blastfilter.py:227-232 (optional, fused)
 //
-// Layout.  The text is cut into 8 KiB tiles; one CTA of 256 threads stages a tile (+1 KiB of
-// look-ahead) in shared memory with coalesced 16-byte loads, builds a bit mask of line
-// terminators with SIMD-in-word compares, numbers the lines that START in the tile with a
-// block scan, and publishes the tile's line count to a decoupled look-back chain so that every
-// line learns its global ordinal in the same pass (no separate newline-count pass over the
-// text).  Lines are then parsed one per thread straight out of shared memory and the record is
-// written at recs[ordinal] -- 16-byte stores, consecutive threads -> consecutive addresses.
-// HBM traffic per line: the line's bytes once + 16 bytes of record.
+// Layout.  The text is cut into 8 KiB tiles; one CTA of 128 threads stages a tile (+1 KiB of
+// look-ahead) in shared memory with coalesced 16-byte loads and classifies every byte ONCE,
+// branch-free, into two bit-per-byte masks (W: byte <= 0x20, N: neither digit nor tab; see
+// jx_fast5.cuh) from which the terminator mask follows.  The lines that START in the tile are
+// numbered with a block scan, and the tile's line count is published to a decoupled look-back
+// chain so that every line learns its global ordinal in the same pass (no separate
+// newline-count pass over the text).  Lines are then parsed one per thread from the masks and
+// the staged words -- field boundaries are bit positions, validation is mask arithmetic, numbers
+// are converted from words -- and the record is written at recs[ordinal]: 16-byte stores,
+// consecutive threads -> consecutive addresses.  Irregular lines take the generic
+// sscanf-faithful scanner.  HBM traffic per line: the line's bytes once + 16 bytes of record.
 #include "jx_internal.cuh"
+#include "jx_fast5.cuh"
 
 namespace {
 
@@ -83,51 +87,66 @@ __device__ int table_lookup_bytes(R& rd, int a, int b, const uint64_t* tab, uint
 }
 
 // fast probe with a precomputed hash and the first slot already loaded (so that the query and
-// subject probes are in flight together); single-exit loops keep the warp converged
-__device__ __forceinline__ int table_probe_words(const jx::WordBytes<SmemWords>& B, int a, int b, uint64_t h,
+// subject probes are in flight together).  The chain walk (cheap) is separated from the name
+// verification (blob loads) so that a warp runs the verification once with all its lanes instead
+// of once per chain position; all loops are single-exit to keep the warp converged.
+__device__ __forceinline__ int table_probe_words(const SmemWords& wr, int a, int b, uint64_t h,
                                                  uint64_t slot, const uint64_t* tab, uint32_t mask,
                                                  const uint32_t* meta, const uint32_t* blob) {
-  if (b <= a) return -1;
   const uint32_t tag = (uint32_t)(h >> 32), len = (uint32_t)(b - a);
+  const int sh = (a & 3) * 8;
   uint32_t idx = (uint32_t)h & mask;
-  int res = -2;
+  int res = b > a ? -2 : -1;
   while (res == -2) {
+    bool walk = slot != 0ull && (uint32_t)(slot >> 32) != tag;
+    while (walk) {
+      idx = (idx + 1) & mask;
+      slot = __ldg(tab + idx);
+      walk = slot != 0ull && (uint32_t)(slot >> 32) != tag;
+    }
     if (!slot) { res = -1; }
     else {
-      if ((uint32_t)(slot >> 32) == tag) {
-        const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r);
-        if ((m & 127u) == len) {
-          const uint32_t* bw = blob + (m >> 7);
-          uint32_t diff = 0;
-          for (uint32_t i = 0; i < len; i += 4) {
-            uint32_t w = B.load32(a + (int)i);
-            const uint32_t rem = len - i;
-            if (rem < 4) w &= (1u << (8 * rem)) - 1u;
-            diff |= w ^ __ldg(bw + (i >> 2));
-          }
-          if (!diff) res = (int)r;
+      const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r);
+      uint32_t diff = (m & 127u) ^ len;
+      if (!diff) {
+        const uint32_t* bw = blob + (m >> 7);
+        int wi = a >> 2;
+        uint32_t cur = wr(wi);
+        for (uint32_t i = 0; i < len; i += 4) {
+          const uint32_t nxt = wr(++wi);
+          uint32_t w = __funnelshift_r(cur, nxt, (uint32_t)sh);
+          cur = nxt;
+          const uint32_t rem = len - i;
+          if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+          diff |= w ^ __ldg(bw + (i >> 2));
         }
       }
-      if (res == -2) { idx = (idx + 1) & mask; slot = __ldg(tab + idx); }
+      if (!diff) res = (int)r;
+      else { idx = (idx + 1) & mask; slot = __ldg(tab + idx); }
     }
   }
   return res;
 }
 
-__device__ __forceinline__ uint32_t term_nibble(uint32_t x) {   // 4 bytes -> 4 terminator bits
-  const uint32_t f = jx::swar_eq(x, 0x0A0A0A0Au) | jx::swar_eq(x, 0x0D0D0D0Du);
-  return (((f >> 7) * 0x00204081u) >> 21) & 0xFu;
-}
-__device__ __forceinline__ uint32_t term_mask32(const uint32_t* w) {   // 8 words -> 32 bits
-  uint32_t m = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) m |= term_nibble(w[k]) << (4 * k);
-  return m;
-}
+struct SmemText {              // byte and unaligned-word views of the staged window
+  const uint8_t* sm;
+  const uint32_t* w;
+  __device__ __forceinline__ uint32_t operator()(int p) const { return sm[p]; }
+  __device__ __forceinline__ uint32_t load32(int p) const {   // bytes [p, p+4)
+    const int i = p >> 2;
+    return __funnelshift_r(w[i], w[i + 1], (uint32_t)(p & 3) * 8u);
+  }
+};
+struct MaskWords {             // one of the bit-per-byte class masks of the window
+  const uint32_t* m;
+  __device__ __forceinline__ uint32_t operator()(int i) const { return m[i]; }
+};
 
 __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   __shared__ __align__(16) uint32_t smw[JX_WIN / 4 + 8];
   __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
+  __shared__ uint32_t s_w[JX_WIN / 32];         // byte <= 0x20
+  __shared__ uint32_t s_n[JX_WIN / 32];         // byte is neither a digit nor a tab
   __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per 64-byte segment
   __shared__ unsigned long long s_start[JX_TOK_THREADS];
   __shared__ uint16_t s_lpos[LCAP];             // start offset of every line of the tile
@@ -158,9 +177,26 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   }
   __syncthreads();
 
-  // ---- terminator masks (SWAR, 32 bytes per mask word) ---------------------------------------------
-  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) s_term[seg] = term_mask32(smw + seg * 8);
-  __syncthreads();
+  // ---- byte classes (SWAR, 32 bytes per mask word) and the terminator mask -----------------------------
+  uint32_t hiacc = 0;
+  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) {
+    const uint4 v0 = reinterpret_cast<const uint4*>(smw)[2 * seg], v1 = reinterpret_cast<const uint4*>(smw)[2 * seg + 1];
+    const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t wm, nm;
+    jx::classify32(w8, wm, nm, hiacc);
+    s_w[seg] = wm;
+    s_n[seg] = nm;
+    // a terminator is a byte <= 0x20 that is not a tab: usually the only such bytes, checked by value
+    uint32_t c = wm & nm, term = 0;
+    while (c) {
+      const int b = __ffs((int)c) - 1;
+      c &= c - 1u;
+      const uint32_t ch = sm[seg * 32 + b];
+      if (ch == '\n' || ch == '\r') term |= 1u << b;
+    }
+    s_term[seg] = term;
+  }
+  const int has_bar = __syncthreads_or((hiacc & 0x80808080u) != 0u);   // may the tile hold a '|' ?
 
   // ---- line starts inside the tile (64 bytes per thread) + block scan ----------------------------------
   unsigned long long starts;
@@ -214,7 +250,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
         int first = isinc ? __ffs(isinc) - 1 : 32;
         unsigned upto = first < 31 ? ((2u << first) - 1u) : 0xFFFFFFFFu;
         if (notready & upto) {             // spin until every needed predecessor has published
-          if (++spins > (1u << 24)) { if (lane == 0) atomicExch(a.stats + 10, 1ull); break; }   // never hang the GPU
+          if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.stats + 10, 1ull); break; }   // never hang the GPU
+          __nanosleep(64);                  // the predecessor is still scanning: leave the issue slots to it
           continue;
         }
         unsigned long long v = ((upto >> lane) & 1u) ? (d & VAL_MASK) : 0ull;
@@ -234,7 +271,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   // ---- parse: one line per thread -----------------------------------------------------------------
   WinReader rd{sm, a.text, base, a.n};
   const SmemWords wr{smw};
-  const jx::WordBytes<SmemWords> B(wr);
+  const MaskWords mwr{s_w}, mnr{s_n};
+  const SmemText B{sm, smw};
   uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
   unsigned long long first_bad = 0;
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
@@ -263,7 +301,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
       ++c_comment;
     } else if (s < e) {
       jx::LineTok t;
-      const bool fast = (e + 8 <= JX_WIN) && jx::fast_line(wr, s, e, t);
+      const bool fast = (e + 8 <= JX_WIN) && jx::fast_line5(B, mwr, mnr, s, e, t);
       if (!fast) jx::tokenize_line(rd, s, e, t);
       bool bad = false, selfhit = false;
       int qi = -1, si = -1;
@@ -271,17 +309,33 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
         if (t.longname) { bad = true; ++c_long; }
         int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
         if (a.is_self && (qb - qa) == (sb - sa)) {      // `is_self and query == subject` on raw names
-          selfhit = true;
-          for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
+          if (fast) {
+            uint32_t diff = 0;
+            for (int i = 0; i < qb - qa; i += 4) {
+              uint32_t d = B.load32(qa + i) ^ B.load32(sa + i);
+              const int rem = qb - qa - i;
+              if (rem < 4) d &= (1u << (8 * rem)) - 1u;
+              diff |= d;
+            }
+            selfhit = diff == 0u;
+          } else {
+            selfhit = true;
+            for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
+          }
         }
         if (!selfhit && !bad) {
           if (fast) {
-            if (a.strip) { qb = jx::fast_strip(B, qa, qb, t.qbar); sb = jx::fast_strip(B, sa, sb, t.sbar); }
-            const uint64_t hq = jx::fast_hash(B, qa, qb), hs = jx::fast_hash(B, sa, sb);
+            if (a.strip) {
+              int qbar = -1, sbar = -1;
+              if (has_bar) { qbar = jx::find_bar(B, qa, qb); sbar = jx::find_bar(B, sa, sb); }
+              qb = jx::strip5(B, qa, qb, qbar);
+              sb = jx::strip5(B, sa, sb, sbar);
+            }
+            const uint64_t hq = jx::fast_hash5(wr, qa, qb), hs = jx::fast_hash5(wr, sa, sb);
             const uint64_t slot_q = __ldg(a.qtab + ((uint32_t)hq & a.qmask));
             const uint64_t slot_s = __ldg(a.stab + ((uint32_t)hs & a.smask));
-            qi = table_probe_words(B, qa, qb, hq, slot_q, a.qtab, a.qmask, a.qmeta, a.qblob);
-            si = table_probe_words(B, sa, sb, hs, slot_s, a.stab, a.smask, a.smeta, a.sblob);
+            qi = table_probe_words(wr, qa, qb, hq, slot_q, a.qtab, a.qmask, a.qmeta, a.qblob);
+            si = table_probe_words(wr, sa, sb, hs, slot_s, a.stab, a.smask, a.smeta, a.sblob);
           } else {
             if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
             qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
@@ -325,12 +379,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   // ---- counters ---------------------------------------------------------------------------------------
   uint32_t vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
 #pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    uint32_t v = vals[i];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    vals[i] = v;
-  }
+  for (int i = 0; i < 7; ++i) vals[i] = __reduce_add_sync(0xFFFFFFFFu, vals[i]);
   if (lane == 0) {
     if (vals[0]) atomicAdd(a.stats + 1, (unsigned long long)vals[0]);
     if (vals[1]) atomicAdd(a.stats + 2, (unsigned long long)vals[1]);

@@ -164,7 +164,7 @@ def test_hash_is_stable(probe):
     assert h1 != h2 and probe.probe_hash(b"Ag000123x", 8) == h1
 
 
-@pytest.mark.parametrize("version", [2, 3, 4])
+@pytest.mark.parametrize("version", [2, 3, 4, 5])
 def test_fast_line_agrees_with_generic_scanner(probe, version):
     """The SWAR fast path (jx::fast_line) must either refuse a line or produce exactly what the
     generic sscanf-faithful scanner produces (spans, score bits, evalue flag, stripped name,
@@ -185,7 +185,7 @@ def test_fast_line_agrees_with_generic_scanner(probe, version):
         f += [str(rng.integers(0, 10 ** int(rng.integers(1, 7)))) for _ in range(7)]
         f += [evs[rng.integers(len(evs))], nums[rng.integers(len(nums))]]
         ln = "\t".join(f)
-        r = rng.integers(0, 14)
+        r = rng.integers(0, 28)             # half of the lines stay regular
         if r == 0: ln = ln.replace("\t", " ", 1)
         elif r == 1: ln = ln + "\textra"
         elif r == 2: ln = "\t".join(f[:9])
@@ -212,8 +212,10 @@ def test_fast_line_agrees_with_generic_scanner(probe, version):
                 ok = probe.probe_fast_line(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
             elif version == 3:
                 ok = probe.probe_fast_line3(buf, s, len(buf), spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
-            else:
+            elif version == 4:
                 ok = probe.probe_fast_line4(buf, s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
+            else:
+                ok = probe.probe_fast_line5(buf, len(buf), s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
             gsp = (ctypes.c_int * 4)(); gsc = ctypes.c_float(); gnc = ctypes.c_int(); gef = ctypes.c_int()
             fl = probe.probe_line(ln.encode(), len(ln), gsp, ctypes.byref(gsc), ctypes.byref(gnc), ctypes.byref(gef))
             if not ok:
@@ -229,3 +231,70 @@ def test_fast_line_agrees_with_generic_scanner(probe, version):
                 assert ends[k] - pad - gsp[2 * k] == b, (ln, k)
                 assert hs[k] == probe.probe_hash(name[:b].encode(), b), (ln, k)
     assert nfast > 0.2 * 4 * len(lines)
+
+
+def test_byte_class_masks_match_definition(probe):
+    """Phase A of the v5 tokenizer: W = byte <= 0x20, N = neither digit nor tab, '|' detector."""
+    rng = np.random.default_rng(11)
+    blocks = [bytes(range(k, k + 32)) for k in range(0, 256, 32)]
+    blocks += [bytes(rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(3000)]
+    blocks += [bytes(rng.choice(np.frombuffer(b"0123456789\t\n\r .|e-+Az", dtype=np.uint8), 32)) for _ in range(3000)]
+    for b in blocks:
+        wm, nm, hi = ctypes.c_uint(), ctypes.c_uint(), ctypes.c_uint()
+        probe.probe_classify32(b, ctypes.byref(wm), ctypes.byref(nm), ctypes.byref(hi))
+        want_w = sum(1 << i for i, c in enumerate(b) if c <= 0x20)
+        want_n = sum(1 << i for i, c in enumerate(b) if not (0x30 <= c <= 0x39 or c == 9))
+        assert wm.value == want_w and nm.value == want_n, b
+        if any(c == 0x7C for c in b):
+            assert hi.value != 0, b
+        if all((c & 0x7F) < 0x7C for c in b):
+            assert hi.value == 0, b
+
+
+def test_fast_line5_alignments_and_formats(probe):
+    """v5 reads its masks at a bit offset (line start mod 32) and converts numbers from words: sweep
+    every alignment, name lengths up to the 128-byte line limit and the number formats the aligners
+    and jcvi's own writers produce (%d, %.1f, %.2f, %.2g, %.3g, %g, %e)."""
+    rng = np.random.default_rng(2025)
+    alphabet = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789_.-|"
+
+    def name():
+        n = int(rng.integers(1, 36))
+        return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet) - (0 if rng.random() < 0.05 else 1), n))
+
+    def num(kind):
+        x = float(10 ** rng.uniform(-3, 6)) if kind == "score" else float(10 ** rng.uniform(-200, 2))
+        if rng.random() < 0.1:
+            x = 0.0
+        fmt = ["%d", "%.1f", "%.2f", "%.2g", "%.3g", "%g", "%e", "%.3e", "%.0f"][int(rng.integers(0, 9))]
+        return (fmt % (int(x) if fmt == "%d" else x)).replace("e", "E" if rng.random() < 0.1 else "e")
+
+    naccept = ntotal = 0
+    for it in range(6000):
+        f = [name(), name(), "%.2f" % rng.uniform(0, 100) if rng.random() < 0.8 else str(int(rng.integers(0, 101)))]
+        f += [str(int(rng.integers(0, 10 ** int(rng.integers(1, 7))))) for _ in range(7)]
+        f += [num("evalue"), num("score")]
+        ln = "\t".join(f)
+        pad = it % 41
+        raw = (b"#" * pad) + ln.encode()
+        buf = raw + (b"\n" if it % 3 else b"\r\n") + b"\0" * 24
+        s, n = pad, len(raw)
+        spans = (ctypes.c_int * 4)(); score = ctypes.c_float(); eflag = ctypes.c_int()
+        ends = (ctypes.c_int * 2)(); hs = (ctypes.c_ulonglong * 2)()
+        ok = probe.probe_fast_line5(buf, len(buf), s, n, spans, ctypes.byref(score), ctypes.byref(eflag), ends, hs)
+        gsp = (ctypes.c_int * 4)(); gsc = ctypes.c_float(); gnc = ctypes.c_int(); gef = ctypes.c_int()
+        fl = probe.probe_line(ln.encode(), len(ln), gsp, ctypes.byref(gsc), ctypes.byref(gnc), ctypes.byref(gef))
+        ntotal += 1
+        if not ok:
+            continue
+        naccept += 1
+        assert fl == 0 and gnc.value == 12, ln
+        assert [x - pad for x in spans] == list(gsp), ln
+        assert f32bits(score.value) == f32bits(gsc.value), ln
+        assert eflag.value == gef.value, ln
+        for k in (0, 1):
+            nm = ln[gsp[2 * k]:gsp[2 * k + 1]]
+            b = probe.probe_strip(nm.encode(), len(nm))
+            assert ends[k] - pad - gsp[2 * k] == b, (ln, k)
+            assert hs[k] == probe.probe_hash(nm[:b].encode(), b), (ln, k)
+    assert naccept > 0.6 * ntotal, (naccept, ntotal)
