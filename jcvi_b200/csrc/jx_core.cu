@@ -3,6 +3,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "jx_internal.cuh"
+#include "jx_fast5.cuh"
 
 namespace {
 struct HostReader {
@@ -109,24 +110,27 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
   d.h_names.assign(bed->names, bed->names + blob);
   d.h_off.assign(bed->name_off, bed->name_off + G + 1);
   d.h_chr_lex.assign(bed->chr_lex, bed->chr_lex + G);
-  // open-addressing table at load factor <= 0.5, built on the host with the same hash the
-  // kernels use (jx_parse.cuh name_hash)
+  // open-addressing table of 32-byte slots at load factor <= 0.5, built on the host with the same
+  // hash the kernels use (jx_fast5.cuh slot_hash_*)
   uint32_t cap = 16;
   while ((int64_t)cap < 2 * G + 2) cap <<= 1;
-  std::vector<uint64_t> tab(cap, 0);
+  std::vector<uint32_t> tab((size_t)cap * 8, 0u);
   HostReader rd{(const unsigned char*)bed->names};
   for (int64_t r = 0; r < G; ++r) {
     if (bed->indexable && !bed->indexable[r]) continue;
     uint32_t a = bed->name_off[r], b = bed->name_off[r + 1];
     if (b - a >= 128u) continue;   // can never match: BLAST names of 128+ bytes are rejected
-    uint64_t h = jx::name_hash(rd, (int)a, (int)b);
-    uint32_t idx = (uint32_t)h & (cap - 1);
-    while (tab[idx]) idx = (idx + 1) & (cap - 1);
-    tab[idx] = (h & 0xFFFFFFFF00000000ull) | (uint64_t)(r + 1);
+    uint32_t idx = jx::slot_hash_bytes(rd, (int)a, (int)b) & (cap - 1);
+    while (tab[(size_t)idx * 8]) idx = (idx + 1) & (cap - 1);
+    uint32_t* slot = &tab[(size_t)idx * 8];
+    slot[0] = (uint32_t)(r + 1);
+    slot[1] = bed->name_id[r];
+    for (uint32_t i = 0; i < 4 * JX_SLOT_WORDS && a + i < b; ++i)
+      slot[2 + (i >> 2)] |= (uint32_t)(unsigned char)bed->names[a + i] << (8 * (i & 3));
   }
   d.tmask = cap - 1;
   int rc;
-  if ((rc = upload(ctx, &d.table, tab.data(), tab.size()))) return rc;
+  if ((rc = upload(ctx, &d.table, reinterpret_cast<const uint4*>(tab.data()), tab.size() / 4))) return rc;
   {
     // word-aligned, zero-padded copy of the names so that the kernel verifies a probe with
     // 32-bit compares against shared-memory words

@@ -19,33 +19,43 @@
 namespace jx {
 
 // ---- phase A: classification -------------------------------------------------------------------
-// 4 text bytes -> 0x80 flags per byte.  `hi` accumulates bit 7 of (low7 + 4): set when a byte's low
-// seven bits are >= 0x7C, i.e. the tile may contain a '|' (gene_name cuts there).
-JX_HD void classify4(uint32_t x, uint32_t& wf, uint32_t& nf, uint32_t& hi) {
+// 4 text bytes -> 0x80 flags per byte: `wf` = byte <= 0x20, `df` = byte is a digit or a tab (N is the
+// complement).  `hi` accumulates bit 7 of (low7 + 4): set when a byte's low seven bits are >= 0x7C,
+// i.e. the tile may contain a '|' (gene_name cuts there).
+JX_HD void classify4(uint32_t x, uint32_t& wf, uint32_t& df, uint32_t& hi) {
   const uint32_t a = x & 0x7F7F7F7Fu;
-  wf = ~((a + 0x5F5F5F5Fu) | x) & 0x80808080u;                  // low7 < 0x21 and bit7 clear
-  const uint32_t dig = (a + 0x50505050u) & ~(a + 0x46464646u);   // bit7: 0x30 <= low7 <= 0x39
-  const uint32_t tab = (a + 0x77777777u) & ~(a + 0x76767676u);   // bit7: low7 == 0x09
-  nf = ~((dig | tab) & ~x) & 0x80808080u;
+  const uint32_t nx = ~x & 0x80808080u;                          // bytes < 0x80
+  wf = ~(a + 0x5F5F5F5Fu) & nx;                                  // low7 < 0x21
+  const uint32_t ud = (a ^ 0x30303030u) + 0x76767676u;           // bit7 clear iff low7 in '0'..'9'
+  const uint32_t ut = (a ^ 0x09090909u) + 0x7F7F7F7Fu;           // bit7 clear iff low7 == 0x09
+  df = ~(ud & ut) & nx;
   hi |= a + 0x04040404u;
 }
-// flags of 8 consecutive bytes (two words) -> 8 mask bits in text order
-JX_HD uint32_t gather8(uint32_t f0, uint32_t f1) { return (((f0 >> 4) | f1) * 0x00204081u) >> 24; }
+// flags of 8 consecutive bytes (two words) -> 8 mask bits in text order, in the top byte of the result
+JX_HD uint32_t gather8_top(uint32_t f0, uint32_t f1) { return ((f0 >> 4) + f1) * 0x00204081u; }
+JX_HD uint32_t top_bytes(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {   // byte3 of each -> one word
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
+#else
+  return (p0 >> 24) | ((p1 >> 24) << 8) | ((p2 >> 24) << 16) | (p3 & 0xFF000000u);
+#endif
+}
 
-// 32 text bytes (8 aligned words) -> one word of each mask
+// 32 text bytes (8 aligned words) -> one word of each mask (W: byte <= 0x20, N: neither digit nor tab)
 JX_HD void classify32(const uint32_t* w, uint32_t& wmask, uint32_t& nmask, uint32_t& hi) {
-  uint32_t wm = 0, nm = 0;
+  uint32_t pw[4], pd[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int k = 0; k < 4; ++k) {
-    uint32_t w0, n0, w1, n1;
-    classify4(w[2 * k], w0, n0, hi);
-    classify4(w[2 * k + 1], w1, n1, hi);
-    wm |= gather8(w0, w1) << (8 * k);
-    nm |= gather8(n0, n1) << (8 * k);
+    uint32_t w0, d0, w1, d1;
+    classify4(w[2 * k], w0, d0, hi);
+    classify4(w[2 * k + 1], w1, d1, hi);
+    pw[k] = gather8_top(w0, w1);
+    pd[k] = gather8_top(d0, d1);
   }
-  wmask = wm; nmask = nm;
+  wmask = top_bytes(pw[0], pw[1], pw[2], pw[3]);
+  nmask = ~top_bytes(pd[0], pd[1], pd[2], pd[3]);
 }
 
 // ---- small bit helpers ----------------------------------------------------------------------------
@@ -299,6 +309,54 @@ JX_HD int strip5(const BR& B, int a, int b, int bar) {
   return (!ev && B(end - 2) == '.' && B(end - 1) != '.') ? end - 2 : end;
 }
 
+// ---- name table slots -------------------------------------------------------------------------------
+// One 32-byte slot (one DRAM/L2 sector) per BED name: { rank + 1 (0 = empty), name id, the first 24
+// bytes of the name, zero padded }.  A probe for a name of <= 23 bytes is ONE memory round trip: the
+// slot's six name words are compared with the query's six zero-padded words (the zero byte after
+// the name makes the comparison length-exact); longer names continue in the word blob.  The hash
+// runs over max(6, ceil(len/4)) zero-padded little-endian words.
+#define JX_SLOT_WORDS 6
+JX_HD uint32_t slot_hash_init() { return 0x2F0B4A87u; }
+JX_HD uint32_t slot_hash_step(uint32_t h, uint32_t w) { return (h ^ w) * 0x9E3779B1u; }
+JX_HD uint32_t slot_hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ (len * 0x85EBCA77u)); }
+template <class R>
+JX_HD uint32_t slot_hash_bytes(R& rd, int a, int b) {            // generic (byte reader) form
+  uint32_t h = slot_hash_init();
+  const int nw = (b - a + 3) >> 2;
+  for (int k = 0; k < (nw > JX_SLOT_WORDS ? nw : JX_SLOT_WORDS); ++k) {
+    uint32_t w = 0;
+    for (int j = 0; j < 4; ++j) { const int p = a + 4 * k + j; if (p < b) w |= rd(p) << (8 * j); }
+    h = slot_hash_step(h, w);
+  }
+  return slot_hash_finish(h, (uint32_t)(b - a));
+}
+// the six zero-padded words of a name of <= 24 bytes, from aligned words
+template <class TW>
+JX_HD void name_words6(const TW& wr, int a, int len, uint32_t* w) {
+  const int i = a >> 2, sh = (a & 3) * 8;
+  uint32_t x[JX_SLOT_WORDS + 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k <= JX_SLOT_WORDS; ++k) x[k] = wr(i + k);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < JX_SLOT_WORDS; ++k) {
+    const int keep = len - 4 * k;                                  // bytes of this word inside the name
+    const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u);
+    w[k] = funnel_r(x[k], x[k + 1], sh) & m;
+  }
+}
+JX_HD uint32_t slot_hash6(const uint32_t* w, int len) {
+  uint32_t h = slot_hash_init();
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < JX_SLOT_WORDS; ++k) h = slot_hash_step(h, w[k]);
+  return slot_hash_finish(h, (uint32_t)len);
+}
+
 // word hash of [a, b) streaming aligned words (one load + one funnel shift per 4 bytes)
 template <class TW>
 JX_HD uint64_t fast_hash5(const TW& wr, int a, int b) {
@@ -306,14 +364,13 @@ JX_HD uint64_t fast_hash5(const TW& wr, int a, int b) {
   const int sh = (a & 3) * 8, len = b - a;
   int i = a >> 2;
   uint32_t cur = wr(i);
-  int rem = len;
-  for (; rem > 4; rem -= 4) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int rem = len; rem > 0; rem -= 4) {
     const uint32_t nxt = wr(++i);
-    h.word(funnel_r(cur, nxt, sh));
+    const uint32_t w = funnel_r(cur, nxt, sh);
     cur = nxt;
-  }
-  if (rem > 0) {
-    const uint32_t w = funnel_r(cur, wr(i + 1), sh);
     h.word(rem < 4 ? (w & ((1u << (8 * rem)) - 1u)) : w);
   }
   return h.finish((uint32_t)len);

@@ -33,7 +33,7 @@ constexpr int JX_WIN = JX_TILE + JX_OVER;
 struct SideDev {
   int64_t G = 0;
   int32_t n_chr = 0;
-  uint64_t* table = nullptr;   // open addressing: (tag32 << 32) | (rank + 1), 0 = empty
+  uint4* table = nullptr;      // open addressing, two uint4 per 32-byte slot: {rank + 1 (0 = empty), name id, name[24]}
   uint32_t tmask = 0;
   uint32_t* blobw = nullptr;     // accn bytes, each name padded with zeros to a 4-byte boundary
   uint32_t* name_meta = nullptr; // per rank: (word offset into blobw << 7) | byte length (< 128)

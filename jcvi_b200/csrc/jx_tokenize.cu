@@ -30,8 +30,8 @@ struct TokArgs {
   uint32_t* ticket;          // global tile ticket (monotone across launches)
   uint4* recs;
   uint32_t rec_cap;
-  const uint64_t* qtab; uint32_t qmask; const uint32_t* qmeta; const uint32_t* qblob;
-  const uint64_t* stab; uint32_t smask; const uint32_t* smeta; const uint32_t* sblob;
+  const uint4* qtab; uint32_t qmask; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
+  const uint4* stab; uint32_t smask; const uint32_t* smeta; const uint32_t* sblob;
   const int32_t* qchr; const int32_t* schr;   // chr_lex per gene (near-diagonal rule)
   const uint32_t* qnid; const uint32_t* snid;
   uint32_t* best;
@@ -61,68 +61,39 @@ struct SmemWords {             // aligned 32-bit words of the window
   __device__ __forceinline__ uint32_t operator()(int i) const { return w[i]; }
 };
 
-// generic (byte reader) probe: assembles words to match the word-based hash / blob layout
+// generic (byte reader) probe: any name length < 128, verified against the word blob
 template <class R>
-__device__ int table_lookup_bytes(R& rd, int a, int b, const uint64_t* tab, uint32_t mask, const uint32_t* meta,
+__device__ int table_lookup_bytes(R& rd, int a, int b, const uint4* tab, uint32_t mask, const uint32_t* meta,
                                   const uint32_t* blob) {
   if (b <= a || b - a >= 128) return -1;
-  const uint64_t h = jx::name_hash(rd, a, b);
-  const uint32_t tag = (uint32_t)(h >> 32);
-  uint32_t idx = (uint32_t)h & mask;
+  uint32_t idx = jx::slot_hash_bytes(rd, a, b) & mask;
   for (;;) {
-    const uint64_t slot = __ldg(tab + idx);
-    if (!slot) return -1;
-    if ((uint32_t)(slot >> 32) == tag) {
-      const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r), len = m & 127u;
-      if (len == (uint32_t)(b - a)) {
-        const uint32_t* bw = blob + (m >> 7);
-        bool eq = true;
-        for (uint32_t i = 0; i < len && eq; ++i)
-          eq = ((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) == rd(a + (int)i);
-        if (eq) return (int)r;
-      }
+    const uint32_t r1 = __ldg(tab + 2 * idx).x;
+    if (!r1) return -1;
+    const uint32_t r = r1 - 1u, m = __ldg(meta + r), len = m & 127u;
+    if (len == (uint32_t)(b - a)) {
+      const uint32_t* bw = blob + (m >> 7);
+      bool eq = true;
+      for (uint32_t i = 0; i < len && eq; ++i)
+        eq = ((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) == rd(a + (int)i);
+      if (eq) return (int)r;
     }
     idx = (idx + 1) & mask;
   }
 }
 
-// fast probe with a precomputed hash and the first slot already loaded (so that the query and
-// subject probes are in flight together).  The chain walk (cheap) is separated from the name
-// verification (blob loads) so that a warp runs the verification once with all its lanes instead
-// of once per chain position; all loops are single-exit to keep the warp converged.
-__device__ __forceinline__ int table_probe_words(const SmemWords& wr, int a, int b, uint64_t h,
-                                                 uint64_t slot, const uint64_t* tab, uint32_t mask,
-                                                 const uint32_t* meta, const uint32_t* blob) {
-  const uint32_t tag = (uint32_t)(h >> 32), len = (uint32_t)(b - a);
-  const int sh = (a & 3) * 8;
-  uint32_t idx = (uint32_t)h & mask;
-  int res = b > a ? -2 : -1;
+// fast probe of a name of <= 23 bytes given as six zero-padded words, first slot already loaded (so
+// that the query and subject probes are in flight together): one 32-byte slot decides; the
+// single-exit loop only repeats on a hash collision
+__device__ __forceinline__ int slot_resolve(const uint32_t* w, uint4 s0, uint4 s1, uint32_t idx, const uint4* tab,
+                                            uint32_t mask, uint32_t& nid) {
+  int res = -2;
   while (res == -2) {
-    bool walk = slot != 0ull && (uint32_t)(slot >> 32) != tag;
-    while (walk) {
-      idx = (idx + 1) & mask;
-      slot = __ldg(tab + idx);
-      walk = slot != 0ull && (uint32_t)(slot >> 32) != tag;
-    }
-    if (!slot) { res = -1; }
+    if (!s0.x) { res = -1; }
     else {
-      const uint32_t r = (uint32_t)slot - 1u, m = __ldg(meta + r);
-      uint32_t diff = (m & 127u) ^ len;
-      if (!diff) {
-        const uint32_t* bw = blob + (m >> 7);
-        int wi = a >> 2;
-        uint32_t cur = wr(wi);
-        for (uint32_t i = 0; i < len; i += 4) {
-          const uint32_t nxt = wr(++wi);
-          uint32_t w = __funnelshift_r(cur, nxt, (uint32_t)sh);
-          cur = nxt;
-          const uint32_t rem = len - i;
-          if (rem < 4) w &= (1u << (8 * rem)) - 1u;
-          diff |= w ^ __ldg(bw + (i >> 2));
-        }
-      }
-      if (!diff) res = (int)r;
-      else { idx = (idx + 1) & mask; slot = __ldg(tab + idx); }
+      const uint32_t diff = (s0.z ^ w[0]) | (s0.w ^ w[1]) | (s1.x ^ w[2]) | (s1.y ^ w[3]) | (s1.z ^ w[4]) | (s1.w ^ w[5]);
+      if (!diff) { res = (int)(s0.x - 1u); nid = s0.y; }
+      else { idx = (idx + 1) & mask; s0 = __ldg(tab + 2 * idx); s1 = __ldg(tab + 2 * idx + 1); }
     }
   }
   return res;
@@ -254,11 +225,15 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
           __nanosleep(64);                  // the predecessor is still scanning: leave the issue slots to it
           continue;
         }
-        unsigned long long v = ((upto >> lane) & 1u) ? (d & VAL_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        excl += v;
-        if (first < 32) break;
+        // aggregates are per-tile line counts (<= 8 Ki): their sum fits 32 bits; the one inclusive
+        // prefix (lane `first`) is 62 bits wide and is fetched on its own
+        const uint32_t agg = ((int)lane < first) ? (uint32_t)d : 0u;
+        excl += __reduce_add_sync(0xFFFFFFFFu, agg);
+        if (first < 32) {
+          const unsigned long long incv = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(d & VAL_MASK), first);
+          excl += incv;
+          break;
+        }
         j -= 32;
       }
       if (lane == 0) atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)(FLAG_INC | (excl + nlines)));
@@ -305,6 +280,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
       if (!fast) jx::tokenize_line(rd, s, e, t);
       bool bad = false, selfhit = false;
       int qi = -1, si = -1;
+      uint32_t nidq = 0, nids = 0;
+      bool have_nid = false;
       if (t.nconv >= 2) {
         if (t.longname) { bad = true; ++c_long; }
         int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
@@ -331,11 +308,21 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
               qb = jx::strip5(B, qa, qb, qbar);
               sb = jx::strip5(B, sa, sb, sbar);
             }
-            const uint64_t hq = jx::fast_hash5(wr, qa, qb), hs = jx::fast_hash5(wr, sa, sb);
-            const uint64_t slot_q = __ldg(a.qtab + ((uint32_t)hq & a.qmask));
-            const uint64_t slot_s = __ldg(a.stab + ((uint32_t)hs & a.smask));
-            qi = table_probe_words(wr, qa, qb, hq, slot_q, a.qtab, a.qmask, a.qmeta, a.qblob);
-            si = table_probe_words(wr, sa, sb, hs, slot_s, a.stab, a.smask, a.smeta, a.sblob);
+            const int lq = qb - qa, lsn = sb - sa;
+            if (lq > 0 && lsn > 0 && lq < 4 * JX_SLOT_WORDS && lsn < 4 * JX_SLOT_WORDS) {
+              uint32_t wq[JX_SLOT_WORDS], ws[JX_SLOT_WORDS];
+              jx::name_words6(wr, qa, lq, wq);
+              jx::name_words6(wr, sa, lsn, ws);
+              const uint32_t iq = jx::slot_hash6(wq, lq) & a.qmask, is = jx::slot_hash6(ws, lsn) & a.smask;
+              const uint4 q0 = __ldg(a.qtab + 2 * iq), q1 = __ldg(a.qtab + 2 * iq + 1);
+              const uint4 s0 = __ldg(a.stab + 2 * is), s1 = __ldg(a.stab + 2 * is + 1);
+              qi = slot_resolve(wq, q0, q1, iq, a.qtab, a.qmask, nidq);
+              si = slot_resolve(ws, s0, s1, is, a.stab, a.smask, nids);
+              have_nid = true;
+            } else {                                   // long (>= 24 bytes) or empty stripped name
+              qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
+              if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
+            }
           } else {
             if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
             qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
@@ -362,8 +349,9 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
           const uint32_t sbits = __float_as_uint(t.score);
           rec = make_uint4((uint32_t)qi, (uint32_t)si, sbits, ((uint32_t)s << 1) | (uint32_t)t.eflag);
           if (a.best && t.score > 0.f) {            // best_score[name] = max(score), starting at 0.0
-            uint32_t* bq = a.best + a.qnid[qi];
-            uint32_t* bs = a.best + a.snid[si];
+            if (!have_nid) { nidq = a.qnid[qi]; nids = a.snid[si]; }   // is_self may have swapped qi/si: both updated
+            uint32_t* bq = a.best + nidq;
+            uint32_t* bs = a.best + nids;
             if (__ldcg(bq) < sbits) atomicMax(bq, sbits);
             if (__ldcg(bs) < sbits) atomicMax(bs, sbits);
           }
