@@ -113,7 +113,10 @@ struct MaskWords {             // one of the bit-per-byte class masks of the win
   __device__ __forceinline__ uint32_t operator()(int i) const { return m[i]; }
 };
 
-__global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
+#ifndef JX_TOK_MINBLK
+#define JX_TOK_MINBLK 9
+#endif
+__global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(const TokArgs a) {
   __shared__ __align__(16) uint32_t smw[JX_WIN / 4 + 8];
   __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
   __shared__ uint32_t s_w[JX_WIN / 32];         // byte <= 0x20
@@ -203,11 +206,15 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   }
 
   // ---- decoupled look-back: global ordinal of the tile's first line ---------------------------------
-  if (warp == 0) {
-    if (lane == 0) {
-      uint64_t d = (tile == 0 ? FLAG_INC : FLAG_AGG) | (uint64_t)nlines;
-      atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)d);
-    }
+  // The tile's own count is published at once; the walk over the predecessors' descriptors is done
+  // by warp 0 AFTER the lines are parsed when every thread holds at most one line (the normal case):
+  // by then the predecessors have published, the walk does not spin, and no warp waits for it
+  // before parsing.  Tiles with more lines than threads resolve their ordinal first.
+  if (tid == 0) {
+    const uint64_t d = (tile == 0 ? FLAG_INC : FLAG_AGG) | (uint64_t)nlines;
+    atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)d);
+  }
+  auto look_back = [&]() {      // all 32 lanes of warp 0
     unsigned long long excl = 0;
     if (tile > 0) {
       int64_t j = (int64_t)tile - 1;
@@ -239,9 +246,10 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
       if (lane == 0) atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)(FLAG_INC | (excl + nlines)));
     }
     if (lane == 0) s_base = excl;
-  }
-  __syncthreads();
-  const unsigned long long line_base = s_base;
+  };
+  const bool defer = nlines <= JX_TOK_THREADS;     // uniform over the CTA
+  if (!defer && warp == 0) look_back();
+  __syncthreads();                                 // line starts (and, if resolved, s_base) visible
 
   // ---- parse: one line per thread -----------------------------------------------------------------
   WinReader rd{sm, a.text, base, a.n};
@@ -250,6 +258,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
   const SmemText B{sm, smw};
   uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
   unsigned long long first_bad = 0;
+  uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
+  bool have_held = false;
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
     const uint32_t k = k0 + tid;
     if (k >= nlines) break;
@@ -360,9 +370,20 @@ __global__ void __launch_bounds__(JX_TOK_THREADS) k_tokenize(const TokArgs a) {
     } else {
       ++c_unmapped;   // empty line: a BlastLine with empty names, never in the BED
     }
-    const unsigned long long ord = line_base + k;
-    if (ord < a.rec_cap) a.recs[ord] = rec;
+    if (defer) { held = rec; have_held = true; }
+    else {
+      const unsigned long long ord = s_base + k;
+      if (ord < a.rec_cap) a.recs[ord] = rec;
+    }
   }
+  if (defer) {
+    __syncwarp();
+    if (warp == 0) look_back();
+    __syncthreads();
+    const unsigned long long ord = s_base + tid;
+    if (have_held && ord < a.rec_cap) a.recs[ord] = held;
+  }
+  const unsigned long long line_base = s_base;
 
   // ---- counters ---------------------------------------------------------------------------------------
   uint32_t vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
