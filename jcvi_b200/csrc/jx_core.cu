@@ -2,6 +2,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <string>
+#include <unordered_map>
 #include "jx_internal.cuh"
 #include "jx_fast5.cuh"
 
@@ -60,7 +63,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int s = 0; s < 2; ++s) {
     SideDev& d = ctx->side[s];
-    cudaFree(d.table); cudaFree(d.blobw); cudaFree(d.name_meta); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
+    cudaFree(d.table); cudaFree(d.disp); cudaFree(d.blobw); cudaFree(d.name_meta); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
     cudaFree(d.chr_end); cudaFree(d.length); cudaFree(d.lexrank); cudaFree(d.name_id);
   }
   cudaFree(ctx->q_same_s);
@@ -110,27 +113,83 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
   d.h_names.assign(bed->names, bed->names + blob);
   d.h_off.assign(bed->name_off, bed->name_off + G + 1);
   d.h_chr_lex.assign(bed->chr_lex, bed->chr_lex + G);
-  // open-addressing table of 32-byte slots at load factor <= 0.5, built on the host with the same
-  // hash the kernels use (jx_fast5.cuh slot_hash_*)
-  uint32_t cap = 16;
-  while ((int64_t)cap < 2 * G + 2) cap <<= 1;
-  std::vector<uint32_t> tab((size_t)cap * 8, 0u);
-  HostReader rd{(const unsigned char*)bed->names};
-  for (int64_t r = 0; r < G; ++r) {
-    if (bed->indexable && !bed->indexable[r]) continue;
-    uint32_t a = bed->name_off[r], b = bed->name_off[r + 1];
-    if (b - a >= 128u) continue;   // can never match: BLAST names of 128+ bytes are rejected
-    uint32_t idx = jx::slot_hash_bytes(rd, (int)a, (int)b) & (cap - 1);
-    while (tab[(size_t)idx * 8]) idx = (idx + 1) & (cap - 1);
-    uint32_t* slot = &tab[(size_t)idx * 8];
-    slot[0] = (uint32_t)(r + 1);
-    slot[1] = bed->name_id[r];
-    for (uint32_t i = 0; i < 4 * JX_SLOT_WORDS && a + i < b; ++i)
-      slot[2 + (i >> 2)] |= (uint32_t)(unsigned char)bed->names[a + i] << (8 * (i & 3));
-  }
-  d.tmask = cap - 1;
+  // perfect hash table of 32-byte slots at load factor <= 0.5 (hash-and-displace), built on the host
+  // with the same hash the kernels use (jx_fast5.cuh slot_hash_* / slot_index)
   int rc;
-  if ((rc = upload(ctx, &d.table, reinterpret_cast<const uint4*>(tab.data()), tab.size() / 4))) return rc;
+  {
+    HostReader rd{(const unsigned char*)bed->names};
+    std::vector<std::pair<uint32_t, int64_t>> keys;     // (hash, rank); the last rank of a repeated name wins
+    {
+      std::unordered_map<std::string, int64_t> uniq;
+      for (int64_t r = 0; r < G; ++r) {
+        if (bed->indexable && !bed->indexable[r]) continue;
+        const uint32_t a = bed->name_off[r], b = bed->name_off[r + 1];
+        if (b - a >= 128u) continue;   // can never match: BLAST names of 128+ bytes are rejected
+        uniq[std::string(bed->names + a, bed->names + b)] = r;
+      }
+      keys.reserve(uniq.size());
+      for (const auto& kv : uniq) {
+        const int64_t r = kv.second;
+        keys.emplace_back(jx::slot_hash_bytes(rd, (int)bed->name_off[r], (int)bed->name_off[r + 1]), r);
+      }
+    }
+    const size_t n = keys.size();
+    uint32_t cbits = 4;
+    while ((1ull << cbits) < 2 * (uint64_t)n + 2) ++cbits;
+    std::vector<uint32_t> tab;
+    std::vector<uint16_t> disp;
+    uint32_t bbits = 1;
+    for (;; ++cbits) {
+      if (cbits > 30) { ctx->err = "BED name table does not fit"; return JX_EARG; }
+      bbits = 1;
+      while ((1ull << bbits) < (uint64_t)n / 2 + 1 && bbits < 28) ++bbits;
+      const uint32_t nb = 1u << bbits, cap = 1u << cbits, cshift = 32 - cbits, bshift = 32 - bbits;
+      std::vector<std::vector<uint32_t>> bucket(nb);
+      for (uint32_t k = 0; k < n; ++k) bucket[keys[k].first >> bshift].push_back(k);
+      std::vector<uint32_t> order(nb);
+      for (uint32_t i = 0; i < nb; ++i) order[i] = i;
+      std::stable_sort(order.begin(), order.end(),
+                       [&](uint32_t x, uint32_t y) { return bucket[x].size() > bucket[y].size(); });
+      std::vector<int64_t> owner((size_t)cap, -1);
+      disp.assign(nb, 0);
+      bool ok = true;
+      std::vector<uint32_t> pos;
+      for (uint32_t bi : order) {
+        const auto& ks = bucket[bi];
+        if (ks.empty()) break;
+        uint32_t d = 0;
+        for (; d < 65536u; ++d) {
+          pos.clear();
+          bool free_all = true;
+          for (uint32_t k : ks) {
+            const uint32_t p = jx::slot_index(keys[k].first, d, cshift);
+            if (owner[p] >= 0 || std::find(pos.begin(), pos.end(), p) != pos.end()) { free_all = false; break; }
+            pos.push_back(p);
+          }
+          if (free_all) break;
+        }
+        if (d == 65536u) { ok = false; break; }       // (two names with the same 32-bit hash, or bad luck): grow
+        disp[bi] = (uint16_t)d;
+        for (size_t i = 0; i < ks.size(); ++i) owner[pos[i]] = keys[ks[i]].second;
+      }
+      if (!ok) continue;
+      tab.assign((size_t)cap * 8, 0u);
+      for (uint32_t p = 0; p < cap; ++p) {
+        const int64_t r = owner[p];
+        if (r < 0) continue;
+        uint32_t* slot = &tab[(size_t)p * 8];
+        const uint32_t a = bed->name_off[r], b = bed->name_off[r + 1];
+        slot[0] = (uint32_t)(r + 1);
+        slot[1] = bed->name_id[r];
+        for (uint32_t i = 0; i < 4 * JX_SLOT_WORDS && a + i < b; ++i)
+          slot[2 + (i >> 2)] |= (uint32_t)(unsigned char)bed->names[a + i] << (8 * (i & 3));
+      }
+      d.bshift = bshift; d.cshift = cshift;
+      break;
+    }
+    if ((rc = upload(ctx, &d.table, reinterpret_cast<const uint4*>(tab.data()), tab.size() / 4))) return rc;
+    if ((rc = upload(ctx, &d.disp, disp.data(), disp.size()))) return rc;
+  }
   {
     // word-aligned, zero-padded copy of the names so that the kernel verifies a probe with
     // 32-bit compares against shared-memory words

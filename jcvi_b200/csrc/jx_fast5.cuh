@@ -236,8 +236,13 @@ JX_HD bool score5(const BR& B, int p, int L, uint32_t nb, float& out) {
 //   the last 32 bits of the line    -> tabs 10, 11, evalue and score
 // Fills the name spans, score and evalue flag; `qbar`/`sbar` are left at -2 ("not searched": the
 // caller knows whether the tile can contain a '|').
+struct Line5Tail {              // what the second half of the parse needs: the two decimal fields
+  int pe, le, ps, ls;          // absolute start and length of evalue / score
+  uint32_t eb, sb;             // their N bits
+};
+// first half: structure, names, integer fields
 template <class BR, class MW, class MN>
-JX_HD bool fast_line5(const BR& B, const MW& mw, const MN& mn, int s, int e, LineTok& t) {
+JX_HD bool fast_line5_head(const BR& B, const MW& mw, const MN& mn, int s, int e, LineTok& t, Line5Tail& tail) {
   t.score = 0.f; t.nconv = 0; t.eflag = 1; t.hard = false; t.longname = false; t.qbar = t.sbar = -2;
   const int len = e - s;
   if (len < 23) return false;
@@ -251,7 +256,7 @@ JX_HD bool fast_line5(const BR& B, const MW& mw, const MN& mn, int s, int e, Lin
   const int t1 = ctz64(W1);
   const uint64_t W2 = W1 & (W1 - 1ull);
   const int t2 = ctz64(W2);
-  const uint64_t upto_t2 = W2 ^ (W2 - 1ull);             // bits <= t2 (plus nothing else: W2's lowest bit is t2)
+  const uint64_t upto_t2 = W2 ^ (W2 - 1ull);             // bits <= t2 (W2's lowest bit is t2)
   if ((W0 & N0 & upto_t2) != 0ull || t0 < 1 || t1 - t0 < 2 || t2 - t1 < 2) return false;
   // field 3 (pctid): digits with at most one '.', at least one digit
   const int lp = t2 - t1 - 1;
@@ -277,15 +282,26 @@ JX_HD bool fast_line5(const BR& B, const MW& mw, const MN& mn, int s, int e, Lin
   const uint64_t Wm = bits64(mw, s + t2), Nm = bits64(mn, s + t2);
   const uint64_t mid = below64(dm + 1);                  // tab 3 .. tab 10 inclusive
   if (popc64(Wm & mid) != 8 || (Nm & mid) != 0ull || (Wm & (Wm >> 1) & mid) != 0ull) return false;
-  const int le = t10 - t9 - 1, ls = len - t10 - 1;
-  if (le > 14 || ls > 14) return false;
-  const uint32_t eb = (Nt >> (h9 + 1)) & below32(le);
-  const uint32_t sb = (h10 < 31 ? (Nt >> (h10 + 1)) : 0u) & below32(ls);
-  if (!evalue5(B, s + t9 + 1, le, eb, t.eflag)) return false;
-  if (!score5(B, s + t10 + 1, ls, sb, t.score)) return false;
+  tail.le = t10 - t9 - 1; tail.ls = len - t10 - 1;
+  if (tail.le > 14 || tail.ls > 14) return false;
+  tail.eb = (Nt >> (h9 + 1)) & below32(tail.le);
+  tail.sb = (h10 < 31 ? (Nt >> (h10 + 1)) : 0u) & below32(tail.ls);
+  tail.pe = s + t9 + 1; tail.ps = s + t10 + 1;
   t.qa = s; t.qb = s + t0; t.sa = s + t0 + 1; t.sb = s + t1;
+  return true;
+}
+// second half: evalue and score
+template <class BR>
+JX_HD bool fast_line5_tail(const BR& B, const Line5Tail& tail, LineTok& t) {
+  if (!evalue5(B, tail.pe, tail.le, tail.eb, t.eflag)) return false;
+  if (!score5(B, tail.ps, tail.ls, tail.sb, t.score)) return false;
   t.nconv = 12;
   return true;
+}
+template <class BR, class MW, class MN>
+JX_HD bool fast_line5(const BR& B, const MW& mw, const MN& mn, int s, int e, LineTok& t) {
+  Line5Tail tail;
+  return fast_line5_head(B, mw, mn, s, e, t, tail) && fast_line5_tail(B, tail, t);
 }
 
 // position of the first '|' in [a, b), or -1 (only called for tiles that may hold one)
@@ -316,6 +332,13 @@ JX_HD int strip5(const BR& B, int a, int b, int bar) {
 // the name makes the comparison length-exact); longer names continue in the word blob.  The hash
 // runs over max(6, ceil(len/4)) zero-padded little-endian words.
 #define JX_SLOT_WORDS 6
+// The slots form a PERFECT hash table (hash-and-displace, built on the host in jx_bed_load): the
+// top bits of the name hash select a bucket, the bucket's 16-bit displacement d re-mixes the hash
+// into a slot that no other name uses.  A lookup is one small-table load + one slot load and never
+// walks a chain, so all lanes of a warp take the same path.
+JX_HD uint32_t slot_index(uint32_t h, uint32_t d, uint32_t cshift) {
+  return ((h ^ (d * 0x85EBCA6Bu)) * 0x9E3779B1u) >> cshift;
+}
 JX_HD uint32_t slot_hash_init() { return 0x2F0B4A87u; }
 JX_HD uint32_t slot_hash_step(uint32_t h, uint32_t w) { return (h ^ w) * 0x9E3779B1u; }
 JX_HD uint32_t slot_hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ (len * 0x85EBCA77u)); }

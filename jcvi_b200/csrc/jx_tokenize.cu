@@ -30,8 +30,8 @@ struct TokArgs {
   uint32_t* ticket;          // global tile ticket (monotone across launches)
   uint4* recs;
   uint32_t rec_cap;
-  const uint4* qtab; uint32_t qmask; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
-  const uint4* stab; uint32_t smask; const uint32_t* smeta; const uint32_t* sblob;
+  const uint4* qtab; const uint16_t* qdisp; uint32_t qbshift, qcshift; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
+  const uint4* stab; const uint16_t* sdisp; uint32_t sbshift, scshift; const uint32_t* smeta; const uint32_t* sblob;
   const int32_t* qchr; const int32_t* schr;   // chr_lex per gene (near-diagonal rule)
   const uint32_t* qnid; const uint32_t* snid;
   uint32_t* best;
@@ -63,40 +63,19 @@ struct SmemWords {             // aligned 32-bit words of the window
 
 // generic (byte reader) probe: any name length < 128, verified against the word blob
 template <class R>
-__device__ int table_lookup_bytes(R& rd, int a, int b, const uint4* tab, uint32_t mask, const uint32_t* meta,
-                                  const uint32_t* blob) {
+__device__ int table_lookup_bytes(R& rd, int a, int b, const uint4* tab, const uint16_t* disp, uint32_t bshift,
+                                  uint32_t cshift, const uint32_t* meta, const uint32_t* blob) {
   if (b <= a || b - a >= 128) return -1;
-  uint32_t idx = jx::slot_hash_bytes(rd, a, b) & mask;
-  for (;;) {
-    const uint32_t r1 = __ldg(tab + 2 * idx).x;
-    if (!r1) return -1;
-    const uint32_t r = r1 - 1u, m = __ldg(meta + r), len = m & 127u;
-    if (len == (uint32_t)(b - a)) {
-      const uint32_t* bw = blob + (m >> 7);
-      bool eq = true;
-      for (uint32_t i = 0; i < len && eq; ++i)
-        eq = ((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) == rd(a + (int)i);
-      if (eq) return (int)r;
-    }
-    idx = (idx + 1) & mask;
-  }
-}
-
-// fast probe of a name of <= 23 bytes given as six zero-padded words, first slot already loaded (so
-// that the query and subject probes are in flight together): one 32-byte slot decides; the
-// single-exit loop only repeats on a hash collision
-__device__ __forceinline__ int slot_resolve(const uint32_t* w, uint4 s0, uint4 s1, uint32_t idx, const uint4* tab,
-                                            uint32_t mask, uint32_t& nid) {
-  int res = -2;
-  while (res == -2) {
-    if (!s0.x) { res = -1; }
-    else {
-      const uint32_t diff = (s0.z ^ w[0]) | (s0.w ^ w[1]) | (s1.x ^ w[2]) | (s1.y ^ w[3]) | (s1.z ^ w[4]) | (s1.w ^ w[5]);
-      if (!diff) { res = (int)(s0.x - 1u); nid = s0.y; }
-      else { idx = (idx + 1) & mask; s0 = __ldg(tab + 2 * idx); s1 = __ldg(tab + 2 * idx + 1); }
-    }
-  }
-  return res;
+  const uint32_t h = jx::slot_hash_bytes(rd, a, b);
+  const uint32_t idx = jx::slot_index(h, __ldg(disp + (h >> bshift)), cshift);
+  const uint32_t r1 = __ldg(tab + 2 * idx).x;
+  if (!r1) return -1;
+  const uint32_t r = r1 - 1u, m = __ldg(meta + r), len = m & 127u;
+  if (len != (uint32_t)(b - a)) return -1;
+  const uint32_t* bw = blob + (m >> 7);
+  for (uint32_t i = 0; i < len; ++i)
+    if (((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) != rd(a + (int)i)) return -1;
+  return (int)r;
 }
 
 struct SmemText {              // byte and unaligned-word views of the staged window
@@ -323,20 +302,26 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
               uint32_t wq[JX_SLOT_WORDS], ws[JX_SLOT_WORDS];
               jx::name_words6(wr, qa, lq, wq);
               jx::name_words6(wr, sa, lsn, ws);
-              const uint32_t iq = jx::slot_hash6(wq, lq) & a.qmask, is = jx::slot_hash6(ws, lsn) & a.smask;
-              const uint4 q0 = __ldg(a.qtab + 2 * iq), q1 = __ldg(a.qtab + 2 * iq + 1);
-              const uint4 s0 = __ldg(a.stab + 2 * is), s1 = __ldg(a.stab + 2 * is + 1);
-              qi = slot_resolve(wq, q0, q1, iq, a.qtab, a.qmask, nidq);
-              si = slot_resolve(ws, s0, s1, is, a.stab, a.smask, nids);
+              // perfect hash: one displacement load + one 32-byte slot per name, no chain to walk
+              const uint32_t hq = jx::slot_hash6(wq, lq), hs = jx::slot_hash6(ws, lsn);
+              const uint32_t dq = __ldg(a.qdisp + (hq >> a.qbshift)), ds = __ldg(a.sdisp + (hs >> a.sbshift));
+              const uint4* pq = a.qtab + 2 * jx::slot_index(hq, dq, a.qcshift);
+              const uint4* ps = a.stab + 2 * jx::slot_index(hs, ds, a.scshift);
+              const uint4 q0 = __ldg(pq), q1 = __ldg(pq + 1), s0 = __ldg(ps), s1 = __ldg(ps + 1);
+              const uint32_t dfq = (q0.z ^ wq[0]) | (q0.w ^ wq[1]) | (q1.x ^ wq[2]) | (q1.y ^ wq[3]) | (q1.z ^ wq[4]) | (q1.w ^ wq[5]);
+              const uint32_t dfs = (s0.z ^ ws[0]) | (s0.w ^ ws[1]) | (s1.x ^ ws[2]) | (s1.y ^ ws[3]) | (s1.z ^ ws[4]) | (s1.w ^ ws[5]);
+              qi = (q0.x && !dfq) ? (int)(q0.x - 1u) : -1;
+              si = (s0.x && !dfs) ? (int)(s0.x - 1u) : -1;
+              nidq = q0.y; nids = s0.y;
               have_nid = true;
             } else {                                   // long (>= 24 bytes) or empty stripped name
-              qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
-              if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
+              qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob);
+              if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob);
             }
           } else {
             if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
-            qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qmask, a.qmeta, a.qblob);
-            if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.smask, a.smeta, a.sblob);
+            qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob);
+            if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob);
           }
         }
       }
@@ -499,8 +484,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     JX_TRACE("tok: allocs");
     TokArgs a;
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.recs = recs; a.rec_cap = (uint32_t)cap64;
-    a.qtab = Q.table; a.qmask = Q.tmask; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
-    a.stab = S.table; a.smask = S.tmask; a.smeta = S.name_meta; a.sblob = S.blobw;
+    a.qtab = Q.table; a.qdisp = Q.disp; a.qbshift = Q.bshift; a.qcshift = Q.cshift; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
+    a.stab = S.table; a.sdisp = S.disp; a.sbshift = S.bshift; a.scshift = S.cshift; a.smeta = S.name_meta; a.sblob = S.blobw;
     a.qchr = Q.chr_lex; a.schr = S.chr_lex; a.qnid = Q.name_id; a.snid = S.name_id;
     a.best = mode.best; a.excl = mode.excl; a.n_excl = mode.n_excl;
     a.strip = mode.strip; a.is_self = ctx->is_self ? 1 : 0; a.neardiag = mode.neardiag;
