@@ -464,6 +464,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   int rc;
 
   const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+  JX_TRACE("lo: enter");
 
   // ---- raw records: reuse the ones jx_blastfilter just produced from the same held text (the
   // reference parses the raw table twice: blastfilter.py:48 and synteny.py:1939), else tokenize
@@ -515,6 +516,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_ALLOC(aord, uint32_t, na, false);
   std::vector<uint32_t> ablock_h(na);
   for (uint32_t i = 0; i < na; ++i) ablock_h[i] = (uint32_t)a_block[aline_h[i]];
+  JX_TRACE("lo: records ready");
   JX_CK(cudaMemcpyAsync(akey, akeys_h.data(), (size_t)na * 8, cudaMemcpyHostToDevice, ctx->stream));
   {
     std::vector<uint32_t> iota(na);
@@ -535,6 +537,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_ALLOC(dablock, uint32_t, na, false);
   JX_CK(cudaMemcpyAsync(dablock, ablock_sorted.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
   JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
+  JX_TRACE("lo: anchors sorted (host round trip)");
   JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
 
   // ---- raw records -> candidates near an anchor -> unique (qi,si), first occurrence ------------------------
@@ -557,6 +560,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_CK(cudaStreamSynchronize(ctx->stream));
   JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
   JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
+  JX_TRACE("lo: select_cell");
   if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist, C, Cidx,
                      d_cnt + 1);
   uint32_t nC = 0;
@@ -567,6 +571,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   if (nC) {
     JX_ALLOC(keys, uint64_t, nC, false);
     JX_ALLOC(vals, uint32_t, nC, false);
+  JX_TRACE("lo: keep_near");
     JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
     uint64_t* ks = keys; uint32_t* vs = vals;
     if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
@@ -599,6 +604,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   // ---- nearest anchor per hit -------------------------------------------------------------------------------
   JX_ALLOC(best_a, uint32_t, nh, false);
   JX_ALLOC(state, uint8_t, nh, false);
+  JX_TRACE("lo: dedupe+lookup");
   JX_LAUNCH(k_nearest, nblk(nh, 128), 128, 0, hkey, nh, sb, aks, dablock, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist,
             best_a, state);
   JX_ALLOC(f1, uint32_t, nh, false);
@@ -667,6 +673,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   if (nlift) {
     JX_ALLOC(k1, uint64_t, nlift, false);
     JX_ALLOC(v1, uint32_t, nlift, false);
+  JX_TRACE("lo: nearest+ambiguous");
     JX_LAUNCH(k_lift_keys, nblk(nh), 256, 0, state, pos1, hkey, hline, sb, Q.chr_lex, S.chr_lex, (uint64_t)S.n_chr, nh, k1, v1);
     uint64_t* k1s = k1; uint32_t* v1s = v1;
     const uint64_t maxcp = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
@@ -687,6 +694,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
     JX_CK(cudaMemcpyAsync(out->block, ob, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
   JX_CK(cudaStreamSynchronize(ctx->stream));
+  JX_TRACE("lo: order+emit");
   JX_CK(cudaGetLastError());
   return JX_OK;
 }

@@ -190,9 +190,11 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
   JX_ALLOC(ny, uint32_t, n, true);
   JX_ALLOC(d_in, uint32_t, 1, true);
   JX_CK(cudaMemsetAsync(birth, 0xFF, (size_t)n * 4, ctx->stream));
+  JX_TRACE("scan: points ready");
   JX_LAUNCH(k_iota, nblk(n), 256, 0, parent, n);
   JX_LAUNCH(k_link, nblk(n, 128), 128, 0, px, py, cp, n, o->xdist, o->ydist, is_self, o->intrabound, parent, hasprev);
   JX_LAUNCH(k_label, nblk(n), 256, 0, parent, hasprev, n, label, birth);
+  JX_TRACE("scan: link+label");
   JX_LAUNCH(k_count_x, nblk(n), 256, 0, px, cp, label, n, nx);
   {
     JX_ALLOC(yk, uint64_t, n, false);
@@ -203,6 +205,7 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
     JX_LAUNCH(k_count_unique, nblk(n), 256, 0, yks, n, ny);
   }
   JX_ALLOC(flag, uint32_t, n, false);
+  JX_TRACE("scan: counts");
   JX_LAUNCH(k_pass_flags, nblk(n), 256, 0, label, birth, nx, ny, n, o->min_size, flag, d_in);
   uint32_t* pos; uint32_t m;
   int rc = compact_positions(ctx, arena, flag, n, pos, m);
@@ -217,6 +220,7 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
   if (m) {
     JX_ALLOC(okeys, uint64_t, m, false);
     JX_ALLOC(ovals, uint32_t, m, false);
+  JX_TRACE("scan: flags+compact");
     JX_LAUNCH(k_out_keys, nblk(n), 256, 0, flag, pos, label, birth, n, okeys, ovals);
     uint64_t* ok = okeys; uint32_t* ov = ovals;
     if ((rc = jx_sort_pairs(ctx, arena, ok, ov, m, 0, 64))) return rc;
@@ -225,6 +229,7 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
     JX_ALLOC(osc, float, m, false);
     JX_ALLOC(oidx, uint32_t, m, false);
     JX_ALLOC(head, uint32_t, m, false);
+    JX_TRACE("scan: out sort");
     JX_LAUNCH(k_emit, nblk(m), 256, 0, ok, ov, m, px, py, psc, pidx, oq, os, osc, oidx, head);
     std::vector<uint32_t> hhead(m), hidx(m);
     JX_CK(cudaMemcpyAsync(out->q_rank, oq, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -233,6 +238,7 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
     JX_CK(cudaMemcpyAsync(hhead.data(), head, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaMemcpyAsync(hidx.data(), oidx, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaStreamSynchronize(ctx->stream));
+    JX_TRACE("scan: emit + D2H");
     int64_t nb = 0;
     for (uint32_t t = 0; t < m; ++t) nb += hhead[t];
     free(out->block_start);
@@ -273,6 +279,7 @@ int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, si
   if (nC) {
     JX_ALLOC(keys, uint64_t, nC, false);
     JX_ALLOC(vals, uint32_t, nC, false);
+  JX_TRACE("scan: select_valid");
     JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
     uint64_t* ks = keys; uint32_t* vs = vals;
     if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
@@ -295,6 +302,7 @@ int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, si
     JX_ALLOC(x1, int32_t, n, false);
     JX_ALLOC(y1, int32_t, n, false);
     JX_ALLOC(s1, float, n, false);
+  JX_TRACE("scan: dedupe+sorts");
     JX_LAUNCH(k_permute<int32_t>, nblk(n), 256, 0, x0, perm, n, x1);
     JX_LAUNCH(k_permute<int32_t>, nblk(n), 256, 0, y0, perm, n, y1);
     JX_LAUNCH(k_permute<float>, nblk(n), 256, 0, s0, perm, n, s1);

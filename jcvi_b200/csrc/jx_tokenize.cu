@@ -27,7 +27,8 @@ struct TokArgs {
   const uint8_t* text;
   int64_t n;                 // total bytes of text
   uint64_t* desc;            // decoupled look-back descriptors, one per tile of the whole text
-  uint32_t* ticket;          // global tile ticket (monotone across launches)
+  uint32_t* ticket;          // ticket counter of this launch: tile = tile_begin + ticket
+  uint32_t tile_begin, tile_end;   // tiles of this launch
   uint4* recs;
   uint32_t rec_cap;
   const uint4* qtab; const uint16_t* qdisp; uint32_t qbshift, qcshift; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
@@ -44,7 +45,10 @@ struct TokArgs {
 #define FLAG_INC (2ull << 62)
 #define VAL_MASK ((1ull << 62) - 1)
 
-constexpr int LCAP = 1024;     // line starts of a tile kept in shared memory (more -> search path)
+#ifndef JX_LCAP
+#define JX_LCAP 1024
+#endif
+constexpr int LCAP = JX_LCAP;     // line starts of a tile kept in shared memory (more -> search path)
 
 struct WinReader {             // byte view: shared-memory window, global memory beyond it
   const uint8_t* sm;
@@ -93,10 +97,36 @@ struct MaskWords {             // one of the bit-per-byte class masks of the win
 };
 
 #ifndef JX_TOK_MINBLK
-#define JX_TOK_MINBLK 9
+#define JX_TOK_MINBLK 7
 #endif
+constexpr int STAGE_BYTES = JX_WIN + 32;          // one staged window (+ slack for unaligned word reads)
+
+// ---- TMA (bulk async copy) + mbarrier, PTX for sm_90+/sm_100a -------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0u;
+}
+
+// Persistent CTAs: each takes tiles from the launch's ticket counter and keeps the NEXT tile's bytes
+// in flight (one bulk copy issued by one thread into the other half of a double buffer) while it
+// works on the current one, so the HBM latency of staging is off the critical path and costs no
+// load/store instructions.
 __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(const TokArgs a) {
-  __shared__ __align__(16) uint32_t smw[JX_WIN / 4 + 8];
+  __shared__ __align__(128) uint8_t s_text[2][STAGE_BYTES];
+  __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
   __shared__ uint32_t s_w[JX_WIN / 32];         // byte <= 0x20
   __shared__ uint32_t s_n[JX_WIN / 32];         // byte is neither a digit nor a tab
@@ -104,31 +134,61 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   __shared__ unsigned long long s_start[JX_TOK_THREADS];
   __shared__ uint16_t s_lpos[LCAP];             // start offset of every line of the tile
   __shared__ uint32_t s_warp[JX_TOK_THREADS / 32];
-  __shared__ uint32_t s_tile, s_nlines;
+  __shared__ uint32_t s_next[2];
   __shared__ unsigned long long s_base;
-  const uint8_t* sm = reinterpret_cast<const uint8_t*>(smw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const int64_t base = (int64_t)tile * JX_TILE;
+  uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0, c_lines = 0;
+  unsigned long long first_bad = 0;
+  bool overflow = false;
 
-  // ---- stage the window: coalesced 16-byte loads, '\n' beyond the end of the text ------------
-  for (int v = tid; v < JX_WIN / 16 + 2; v += JX_TOK_THREADS) {
-    const int64_t gp = base + (int64_t)v * 16;
-    uint4 val;
-    if (gp + 16 <= a.n) {
-      val = __ldcs(reinterpret_cast<const uint4*>(a.text + gp));
-    } else {
-      uint8_t tmp[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) tmp[i] = (gp + i < a.n) ? a.text[gp + i] : (uint8_t)'\n';
-      val = *reinterpret_cast<uint4*>(tmp);
+  // bytes of tile t that exist in the text, capped at one stage; the bulk copy moves the 16-byte multiple
+  auto avail_of = [&](uint32_t t) -> uint32_t {
+    const int64_t left = a.n - (int64_t)t * JX_TILE;
+    return (uint32_t)(left < (int64_t)STAGE_BYTES ? (left < 0 ? 0 : left) : STAGE_BYTES);
+  };
+  auto issue = [&](uint32_t t, int stage) {      // one thread
+    const uint32_t bytes = avail_of(t) & ~15u;
+    if (bytes) {
+      mbar_expect_tx(&s_bar[stage], bytes);
+      bulk_g2s(s_text[stage], a.text + (int64_t)t * JX_TILE, bytes, &s_bar[stage]);
     }
-    reinterpret_cast<uint4*>(smw)[v] = val;
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t t = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[0] = t;
+    if (t < a.tile_end) issue(t, 0);
   }
   __syncthreads();
+  uint32_t tile = s_next[0];
+
+  for (uint32_t it = 0; tile < a.tile_end; ++it) {
+  const int stage = (int)(it & 1u);
+  const uint32_t* smw = reinterpret_cast<const uint32_t*>(s_text[stage]);
+  const uint8_t* sm = s_text[stage];
+  const int64_t base = (int64_t)tile * JX_TILE;
+  if (tid == 0) {                                 // take the next tile and start its copy
+    const uint32_t t = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[stage ^ 1] = t;
+    if (t < a.tile_end) issue(t, stage ^ 1);
+  }
+  // ---- the window: wait for the bulk copy, '\n' beyond the end of the text ---------------------------
+  {
+    const uint32_t avail = avail_of(tile), bulk = avail & ~15u;
+    if (bulk) {
+      const uint32_t parity = (it >> 1) & 1u;
+      while (!mbar_try_wait(&s_bar[stage], parity)) {}
+    }
+    if (avail < (uint32_t)STAGE_BYTES) {          // last tiles of the text only
+      uint8_t* wsm = s_text[stage];
+      for (uint32_t i = bulk + tid; i < (uint32_t)STAGE_BYTES; i += JX_TOK_THREADS)
+        wsm[i] = i < avail ? a.text[base + i] : (uint8_t)'\n';
+      __syncthreads();
+    }
+  }
 
   // ---- byte classes (SWAR, 32 bytes per mask word) and the terminator mask -----------------------------
   uint32_t hiacc = 0;
@@ -235,8 +295,6 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   const SmemWords wr{smw};
   const MaskWords mwr{s_w}, mnr{s_n};
   const SmemText B{sm, smw};
-  uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0;
-  unsigned long long first_bad = 0;
   uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
   bool have_held = false;
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
@@ -368,7 +426,13 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     const unsigned long long ord = s_base + tid;
     if (have_held && ord < a.rec_cap) a.recs[ord] = held;
   }
-  const unsigned long long line_base = s_base;
+  if (tid == 0) {
+    c_lines += nlines;
+    if (s_base + nlines > a.rec_cap) overflow = true;
+  }
+  __syncthreads();                                 // this stage and the scratch arrays are free again
+  tile = s_next[stage ^ 1];
+  }  // tiles
 
   // ---- counters ---------------------------------------------------------------------------------------
   uint32_t vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
@@ -385,8 +449,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   }
   if (first_bad) atomicMin(a.stats + 7, first_bad);
   if (tid == 0) {
-    atomicAdd(a.stats + 0, (unsigned long long)nlines);
-    if (line_base + nlines > a.rec_cap) atomicExch(a.stats + 6, 1ull);
+    if (c_lines) atomicAdd(a.stats + 0, (unsigned long long)c_lines);
+    if (overflow) atomicExch(a.stats + 6, 1ull);
   }
 }
 
@@ -434,7 +498,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   // record capacity: lines are >= 24 bytes in any real table; retry with the exact worst case
   // (every byte a line) only if that guess overflows.
   JX_ALLOC(d_stats, unsigned long long, 12, true);
-  JX_ALLOC(d_ticket, uint32_t, 1, true);
+  JX_ALLOC(d_ticket, uint32_t, (size_t)std::max<int64_t>(nchunks, 1), true);   // one ticket counter per launch
   const bool to_cache = held && ((mode.fill_cache && !ctx->is_self && mode.n_excl == 0 && !mode.neardiag) || mode.persist);
   if (to_cache) ctx->cache.valid = false;    // about to overwrite the retained records
   uint64_t* d_desc = nullptr;
@@ -473,7 +537,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     out.recs = recs;
     if (attempt) {
       JX_CK(cudaMemsetAsync(d_stats, 0, 12 * sizeof(unsigned long long), ctx->stream));
-      JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), ctx->stream));
+      JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(nchunks, 1), ctx->stream));
       JX_CK(cudaMemsetAsync(d_desc, 0, (size_t)ntiles * sizeof(uint64_t), ctx->stream));
       if (mode.best) JX_CK(cudaMemsetAsync(mode.best, 0, (size_t)ctx->n_name_ids * sizeof(uint32_t), ctx->stream));
     }
@@ -483,7 +547,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     }
     JX_TRACE("tok: allocs");
     TokArgs a;
-    a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.recs = recs; a.rec_cap = (uint32_t)cap64;
+    a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.tile_begin = 0; a.tile_end = 0; a.recs = recs; a.rec_cap = (uint32_t)cap64;
     a.qtab = Q.table; a.qdisp = Q.disp; a.qbshift = Q.bshift; a.qcshift = Q.cshift; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
     a.stab = S.table; a.sdisp = S.disp; a.sbshift = S.bshift; a.scshift = S.cshift; a.smeta = S.name_meta; a.sblob = S.blobw;
     a.qchr = Q.chr_lex; a.schr = S.chr_lex; a.qnid = Q.name_id; a.snid = S.name_id;
@@ -491,9 +555,27 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     a.strip = mode.strip; a.is_self = ctx->is_self ? 1 : 0; a.neardiag = mode.neardiag;
     a.stats = d_stats;
     const int64_t tiles_per_chunk = CHUNK / JX_TILE;
-    for (int64_t c = 0; c < std::max<int64_t>(nchunks, 0); ++c) {
-      int64_t t0 = c * tiles_per_chunk, t1 = std::min(ntiles, t0 + tiles_per_chunk);
-      if ((!on_device || held) && attempt == 0 && !copied.empty()) {
+    // persistent CTAs: as many as are resident at once
+    static int64_t resident = 0;
+    if (!resident) {
+      int per_sm = 0, n_sm = 0;
+      JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize, JX_TOK_THREADS, 0));
+      JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+      resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
+    }
+    // copies still in flight: one launch per 64 MiB chunk, each behind its copy; a text that is already
+    // resident is tokenized by ONE launch (no ramp-up / ramp-down per chunk)
+    bool pending = (!on_device || held) && attempt == 0 && !copied.empty();
+    if (pending && held && cudaEventQuery(copied.back()) == cudaSuccess) pending = false;
+#ifdef JX_TOK_ALWAYS_CHUNKED
+    const int64_t launch_tiles = tiles_per_chunk;
+#else
+    const int64_t launch_tiles = pending ? tiles_per_chunk : std::max<int64_t>(ntiles, 1);
+#endif
+    const int64_t nlaunch = (ntiles + launch_tiles - 1) / launch_tiles;
+    for (int64_t c = 0; c < nlaunch; ++c) {
+      int64_t t0 = c * launch_tiles, t1 = std::min(ntiles, t0 + launch_tiles);
+      if (pending) {
         // a tile's look-ahead may reach into the next chunk: wait for that copy too
         JX_CK(cudaStreamWaitEvent(ctx->stream, copied[(size_t)std::min(c + 1, nchunks - 1)], 0));
       }
@@ -501,7 +583,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       JX_CK(cudaEventCreate(&e0));
       JX_CK(cudaEventCreate(&e1));
       JX_CK(cudaEventRecord(e0, ctx->stream));
-      JX_LAUNCH(k_tokenize, (unsigned)(t1 - t0), JX_TOK_THREADS, 0, a);
+      a.ticket = d_ticket + c; a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
+      JX_LAUNCH(k_tokenize, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
     }

@@ -124,3 +124,44 @@ def test_crlf_and_lone_cr(tmp_path, mods):
     last = os.path.join(d, "A.B.last")
     open(last, "w", newline="").write(body)
     _check_all(d, mods, last, qbed, sbed)
+
+
+def test_name_table_boundaries(tmp_path, mods):
+    """Names of every length 1..40 around the 24-byte slot of the perfect-hash table, names that
+    share their first 24 bytes, '|' cuts and isoform suffixes, hits against names that are not in
+    the BED (lookups must miss), a BED accn repeated on two lines (the last one wins), and number
+    formats that take the word-arithmetic and the generic routes."""
+    rng = np.random.default_rng(77)
+    nq = ns = 1000
+
+    def base(prefix, i):
+        L = 1 + (i * 7) % 40
+        core = "%s%d" % (prefix, i)
+        if L > len(core):
+            core = core + "_" + "k" * (L - len(core) - 1)
+        if i % 10 == 3:
+            core = "SHAREDPREFIX_OF_24_BYTES" + core          # equal first 24 bytes, differ after
+        return core
+    qb = [base("q", i) for i in range(nq)]
+    sb = [base("s", i) for i in range(ns)]
+    assert len(set(qb)) == nq and len(set(sb)) == ns
+    d = str(tmp_path)
+    qbed, sbed = _beds(d, qb, sb)
+    with open(qbed, "a") as fw:                                # repeated accn: Bed.order keeps the last
+        fw.write("Achr9\t5\t900\t%s\n" % qb[17])
+
+    def qn(i):
+        r = i % 6
+        return qb[i] + (".1" if r == 0 else "|tail.2" if r == 1 else ".2|x" if r == 2 else "")
+    sn = lambda i: sb[i] + (".3" if i % 2 else "")
+    lines = _lines(rng, nq, ns, 40000, qn, sn)
+    for k in range(0, len(lines), 23):                         # unknown names
+        f = lines[k].split("\t"); f[k % 2] = f[k % 2] + "Z"; lines[k] = "\t".join(f)
+    for k in range(5, len(lines), 31):                         # scores / evalues in other notations
+        f = lines[k].split("\t")
+        f[11] = ["1.06e+03", "1234", "0.5", "12345678", "7.", "1e2"][k % 6]
+        f[10] = ["0.0", "1E-11", "3", "1.5e-180", "0.00000000001", "5e-010"][k % 6]
+        lines[k] = "\t".join(f)
+    last = os.path.join(d, "A.B.last")
+    open(last, "w").write("\n".join(lines) + "\n")
+    _check_all(d, mods, last, qbed, sbed)
