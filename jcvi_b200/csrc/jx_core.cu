@@ -63,7 +63,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int s = 0; s < 2; ++s) {
     SideDev& d = ctx->side[s];
-    cudaFree(d.table); cudaFree(d.disp); cudaFree(d.blobw); cudaFree(d.name_meta); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
+    cudaFree(d.table); cudaFree(d.disp); cudaFree(d.ovf_hash); cudaFree(d.ovf_rank); cudaFree(d.blobw); cudaFree(d.name_meta); cudaFree(d.chr_lex); cudaFree(d.chr_begin);
     cudaFree(d.chr_end); cudaFree(d.length); cudaFree(d.lexrank); cudaFree(d.name_id);
   }
   cudaFree(ctx->q_same_s);
@@ -133,6 +133,19 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
         keys.emplace_back(jx::slot_hash_bytes(rd, (int)bed->name_off[r], (int)bed->name_off[r + 1]), r);
       }
     }
+    // names with identical 32-bit hashes cannot be separated by any displacement (expected from ~10^5
+    // names on): the first keeps its place in the table, the others go to a small sorted overflow
+    // list that lookups consult only after a miss
+    std::sort(keys.begin(), keys.end());
+    std::vector<uint32_t> ovf_hash, ovf_rank;
+    {
+      size_t w = 0;
+      for (size_t k = 0; k < keys.size(); ++k) {
+        if (w && keys[w - 1].first == keys[k].first) { ovf_hash.push_back(keys[k].first); ovf_rank.push_back((uint32_t)keys[k].second); }
+        else keys[w++] = keys[k];
+      }
+      keys.resize(w);
+    }
     const size_t n = keys.size();
     uint32_t cbits = 4;
     while ((1ull << cbits) < 2 * (uint64_t)n + 2) ++cbits;
@@ -142,7 +155,7 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
     for (;; ++cbits) {
       if (cbits > 30) { ctx->err = "BED name table does not fit"; return JX_EARG; }
       bbits = 1;
-      while ((1ull << bbits) < (uint64_t)n / 2 + 1 && bbits < 28) ++bbits;
+      while ((1ull << bbits) < (uint64_t)n / 8 + 1 && bbits < 28) ++bbits;   // ~8 names per bucket: the displacement table stays L1-resident
       const uint32_t nb = 1u << bbits, cap = 1u << cbits, cshift = 32 - cbits, bshift = 32 - bbits;
       std::vector<std::vector<uint32_t>> bucket(nb);
       for (uint32_t k = 0; k < n; ++k) bucket[keys[k].first >> bshift].push_back(k);
@@ -189,6 +202,9 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
     }
     if ((rc = upload(ctx, &d.table, reinterpret_cast<const uint4*>(tab.data()), tab.size() / 4))) return rc;
     if ((rc = upload(ctx, &d.disp, disp.data(), disp.size()))) return rc;
+    d.n_ovf = (uint32_t)ovf_hash.size();
+    if ((rc = upload(ctx, &d.ovf_hash, ovf_hash.data(), ovf_hash.size()))) return rc;
+    if ((rc = upload(ctx, &d.ovf_rank, ovf_rank.data(), ovf_rank.size()))) return rc;
   }
   {
     // word-aligned, zero-padded copy of the names so that the kernel verifies a probe with

@@ -340,7 +340,7 @@ JX_HD uint32_t slot_index(uint32_t h, uint32_t d, uint32_t cshift) {
   return ((h ^ (d * 0x85EBCA6Bu)) * 0x9E3779B1u) >> cshift;
 }
 JX_HD uint32_t slot_hash_init() { return 0x2F0B4A87u; }
-JX_HD uint32_t slot_hash_step(uint32_t h, uint32_t w) { return (h ^ w) * 0x9E3779B1u; }
+JX_HD uint32_t slot_hash_step(uint32_t h, uint32_t w) { return rotl32(h ^ w, 13) * 0x9E3779B1u; }   // the rotation keeps equal hashes at the birthday rate
 JX_HD uint32_t slot_hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ (len * 0x85EBCA77u)); }
 template <class R>
 JX_HD uint32_t slot_hash_bytes(R& rd, int a, int b) {            // generic (byte reader) form

@@ -218,4 +218,10 @@ void probe_classify32(const unsigned char* bytes32, unsigned* wmask, unsigned* n
   *wmask = a; *nmask = b; *hi = h & 0x80808080u;
 }
 
+// 32-bit slot hash (name table) of n names stored back to back with offsets off[0..n]
+void probe_slot_hash_many(const char* blob, const unsigned* off, long n, unsigned* out) {
+  PtrReader rd{(const unsigned char*)blob};
+  for (long i = 0; i < n; ++i) out[i] = jx::slot_hash_bytes(rd, (int)off[i], (int)off[i + 1]);
+}
+
 }  // extern "C"

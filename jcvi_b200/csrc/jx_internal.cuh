@@ -36,6 +36,9 @@ struct SideDev {
   uint4* table = nullptr;      // perfect hash, two uint4 per 32-byte slot: {rank + 1 (0 = empty), name id, name[24]}
   uint16_t* disp = nullptr;    // per bucket displacement (hash-and-displace)
   uint32_t bshift = 31, cshift = 28;   // bucket = hash >> bshift, slot = slot_index(hash, disp[bucket], cshift)
+  uint32_t* ovf_hash = nullptr;  // names whose 32-bit hash equals that of a name in the table (sorted by hash; rare)
+  uint32_t* ovf_rank = nullptr;
+  uint32_t n_ovf = 0;
   uint32_t* blobw = nullptr;     // accn bytes, each name padded with zeros to a 4-byte boundary
   uint32_t* name_meta = nullptr; // per rank: (word offset into blobw << 7) | byte length (< 128)
   int32_t *chr_lex = nullptr, *chr_begin = nullptr, *chr_end = nullptr, *length = nullptr;

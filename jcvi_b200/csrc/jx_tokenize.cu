@@ -33,6 +33,8 @@ struct TokArgs {
   uint32_t rec_cap;
   const uint4* qtab; const uint16_t* qdisp; uint32_t qbshift, qcshift; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
   const uint4* stab; const uint16_t* sdisp; uint32_t sbshift, scshift; const uint32_t* smeta; const uint32_t* sblob;
+  const uint32_t* qovh; const uint32_t* qovr; uint32_t qnov;   // overflow lists (equal 32-bit hashes), usually empty
+  const uint32_t* sovh; const uint32_t* sovr; uint32_t snov;
   const int32_t* qchr; const int32_t* schr;   // chr_lex per gene (near-diagonal rule)
   const uint32_t* qnid; const uint32_t* snid;
   uint32_t* best;
@@ -66,20 +68,41 @@ struct SmemWords {             // aligned 32-bit words of the window
 };
 
 // generic (byte reader) probe: any name length < 128, verified against the word blob
+struct SideTab {
+  const uint4* tab; const uint16_t* disp; uint32_t bshift, cshift;
+  const uint32_t* meta; const uint32_t* blob;
+  const uint32_t* ovh; const uint32_t* ovr; uint32_t nov;
+};
 template <class R>
-__device__ int table_lookup_bytes(R& rd, int a, int b, const uint4* tab, const uint16_t* disp, uint32_t bshift,
-                                  uint32_t cshift, const uint32_t* meta, const uint32_t* blob) {
-  if (b <= a || b - a >= 128) return -1;
-  const uint32_t h = jx::slot_hash_bytes(rd, a, b);
-  const uint32_t idx = jx::slot_index(h, __ldg(disp + (h >> bshift)), cshift);
-  const uint32_t r1 = __ldg(tab + 2 * idx).x;
-  if (!r1) return -1;
-  const uint32_t r = r1 - 1u, m = __ldg(meta + r), len = m & 127u;
-  if (len != (uint32_t)(b - a)) return -1;
+__device__ bool name_equals(R& rd, int a, int b, uint32_t r, const uint32_t* meta, const uint32_t* blob) {
+  const uint32_t m = __ldg(meta + r), len = m & 127u;
+  if (len != (uint32_t)(b - a)) return false;
   const uint32_t* bw = blob + (m >> 7);
   for (uint32_t i = 0; i < len; ++i)
-    if (((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) != rd(a + (int)i)) return -1;
-  return (int)r;
+    if (((__ldg(bw + (i >> 2)) >> (8 * (i & 3))) & 0xFFu) != rd(a + (int)i)) return false;
+  return true;
+}
+__device__ __forceinline__ bool ovf_has(const uint32_t* ovh, uint32_t nov, uint32_t h) {   // is h in the sorted list?
+  uint32_t lo = 0, hi = nov;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(ovh + mid) < h) lo = mid + 1; else hi = mid; }
+  return lo < nov && __ldg(ovh + lo) == h;
+}
+template <class R>
+__device__ int table_lookup_bytes(R& rd, int a, int b, const SideTab& T) {
+  if (b <= a || b - a >= 128) return -1;
+  const uint32_t h = jx::slot_hash_bytes(rd, a, b);
+  const uint32_t idx = jx::slot_index(h, __ldg(T.disp + (h >> T.bshift)), T.cshift);
+  const uint32_t r1 = __ldg(T.tab + 2 * idx).x;
+  if (r1 && name_equals(rd, a, b, r1 - 1u, T.meta, T.blob)) return (int)(r1 - 1u);
+  if (T.nov) {                                    // names sharing the 32-bit hash of a table entry
+    uint32_t lo = 0, hi = T.nov;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(T.ovh + mid) < h) lo = mid + 1; else hi = mid; }
+    for (; lo < T.nov && __ldg(T.ovh + lo) == h; ++lo) {
+      const uint32_t r = __ldg(T.ovr + lo);
+      if (name_equals(rd, a, b, r, T.meta, T.blob)) return (int)r;
+    }
+  }
+  return -1;
 }
 
 struct SmemText {              // byte and unaligned-word views of the staged window
@@ -254,33 +277,54 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)d);
   }
   auto look_back = [&]() {      // all 32 lanes of warp 0
+    // LBW windows of 32 descriptors are fetched per round (independent loads, one memory latency).
+    // Measured on B200: 1 window 0.0728 ms / 64 MiB, 2: 0.0730, 4: 0.0749, 8: 0.0802 -- wider rounds only
+    // add polling traffic, so one window it is.
+#ifndef JX_LBW
+#define JX_LBW 1
+#endif
+    constexpr int LBW = JX_LBW;
     unsigned long long excl = 0;
     if (tile > 0) {
       int64_t j = (int64_t)tile - 1;
       uint32_t spins = 0;
-      for (;;) {
-        int64_t idx = j - lane;
-        uint64_t d = idx >= 0 ? *((volatile uint64_t*)(a.desc + idx)) : FLAG_INC;
-        uint32_t flag = (uint32_t)(d >> 62);
-        unsigned notready = __ballot_sync(0xFFFFFFFFu, flag == 0);
-        unsigned isinc = __ballot_sync(0xFFFFFFFFu, flag == 2);
-        int first = isinc ? __ffs(isinc) - 1 : 32;
-        unsigned upto = first < 31 ? ((2u << first) - 1u) : 0xFFFFFFFFu;
-        if (notready & upto) {             // spin until every needed predecessor has published
-          if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.stats + 10, 1ull); break; }   // never hang the GPU
-          __nanosleep(64);                  // the predecessor is still scanning: leave the issue slots to it
-          continue;
+      bool done = false;
+      while (!done) {
+        uint64_t d[LBW];
+#pragma unroll
+        for (int w = 0; w < LBW; ++w) {
+          const int64_t idx = j - 32 * w - lane;
+          d[w] = idx >= 0 ? *((volatile uint64_t*)(a.desc + idx)) : FLAG_INC;
         }
-        // aggregates are per-tile line counts (<= 8 Ki): their sum fits 32 bits; the one inclusive
-        // prefix (lane `first`) is 62 bits wide and is fetched on its own
-        const uint32_t agg = ((int)lane < first) ? (uint32_t)d : 0u;
-        excl += __reduce_add_sync(0xFFFFFFFFu, agg);
-        if (first < 32) {
-          const unsigned long long incv = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(d & VAL_MASK), first);
-          excl += incv;
-          break;
+        bool stalled = false;
+#pragma unroll
+        for (int w = 0; w < LBW; ++w) {
+          if (!done && !stalled) {
+            const uint32_t flag = (uint32_t)(d[w] >> 62);
+            const unsigned notready = __ballot_sync(0xFFFFFFFFu, flag == 0);
+            const unsigned isinc = __ballot_sync(0xFFFFFFFFu, flag == 2);
+            const int first = isinc ? __ffs(isinc) - 1 : 32;
+            const unsigned upto = first < 31 ? ((2u << first) - 1u) : 0xFFFFFFFFu;
+            if (notready & upto) {
+              stalled = true;               // a needed predecessor has not published yet: poll again from here
+            } else {
+              // aggregates are per-tile line counts (<= 8 Ki): their sum fits 32 bits; the one
+              // inclusive prefix (lane `first`) is 62 bits wide and is fetched on its own
+              const uint32_t agg = ((int)lane < first) ? (uint32_t)d[w] : 0u;
+              excl += __reduce_add_sync(0xFFFFFFFFu, agg);
+              if (first < 32) {
+                excl += __shfl_sync(0xFFFFFFFFu, (unsigned long long)(d[w] & VAL_MASK), first);
+                done = true;
+              } else {
+                j -= 32;
+              }
+            }
+          }
         }
-        j -= 32;
+        if (stalled) {
+          if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.stats + 10, 1ull); done = true; }   // never hang the GPU
+          else __nanosleep(64);
+        }
       }
       if (lane == 0) atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)(FLAG_INC | (excl + nlines)));
     }
@@ -295,6 +339,8 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   const SmemWords wr{smw};
   const MaskWords mwr{s_w}, mnr{s_n};
   const SmemText B{sm, smw};
+  const SideTab TQ{a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob, a.qovh, a.qovr, a.qnov};
+  const SideTab TS{a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob, a.sovh, a.sovr, a.snov};
   uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
   bool have_held = false;
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
@@ -372,14 +418,22 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
               si = (s0.x && !dfs) ? (int)(s0.x - 1u) : -1;
               nidq = q0.y; nids = s0.y;
               have_nid = true;
+              if ((a.qnov | a.snov) && (qi < 0 || si < 0)) {   // a miss may be a name parked in an overflow list
+                const bool maybe = (qi < 0 && ovf_has(a.qovh, a.qnov, hq)) || (si < 0 && ovf_has(a.sovh, a.snov, hs));
+                if (maybe) {
+                  have_nid = false;
+                  qi = table_lookup_bytes(rd, qa, qb, TQ);
+                  si = qi >= 0 ? table_lookup_bytes(rd, sa, sb, TS) : -1;
+                }
+              }
             } else {                                   // long (>= 24 bytes) or empty stripped name
-              qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob);
-              if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob);
+              qi = table_lookup_bytes(rd, qa, qb, TQ);
+              if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, TS);
             }
           } else {
             if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
-            qi = table_lookup_bytes(rd, qa, qb, a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob);
-            if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob);
+            qi = table_lookup_bytes(rd, qa, qb, TQ);
+            if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, TS);
           }
         }
       }
@@ -405,8 +459,9 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
             if (!have_nid) { nidq = a.qnid[qi]; nids = a.snid[si]; }   // is_self may have swapped qi/si: both updated
             uint32_t* bq = a.best + nidq;
             uint32_t* bs = a.best + nids;
-            if (__ldcg(bq) < sbits) atomicMax(bq, sbits);
-            if (__ldcg(bs) < sbits) atomicMax(bs, sbits);
+            const uint32_t vq = __ldcg(bq), vs = __ldcg(bs);     // both reads in flight together
+            if (vq < sbits) atomicMax(bq, sbits);
+            if (vs < sbits) atomicMax(bs, sbits);
           }
         }
       }
@@ -550,6 +605,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.tile_begin = 0; a.tile_end = 0; a.recs = recs; a.rec_cap = (uint32_t)cap64;
     a.qtab = Q.table; a.qdisp = Q.disp; a.qbshift = Q.bshift; a.qcshift = Q.cshift; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
     a.stab = S.table; a.sdisp = S.disp; a.sbshift = S.bshift; a.scshift = S.cshift; a.smeta = S.name_meta; a.sblob = S.blobw;
+    a.qovh = Q.ovf_hash; a.qovr = Q.ovf_rank; a.qnov = Q.n_ovf; a.sovh = S.ovf_hash; a.sovr = S.ovf_rank; a.snov = S.n_ovf;
     a.qchr = Q.chr_lex; a.schr = S.chr_lex; a.qnid = Q.name_id; a.snid = S.name_id;
     a.best = mode.best; a.excl = mode.excl; a.n_excl = mode.n_excl;
     a.strip = mode.strip; a.is_self = ctx->is_self ? 1 : 0; a.neardiag = mode.neardiag;

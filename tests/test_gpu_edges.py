@@ -165,3 +165,39 @@ def test_name_table_boundaries(tmp_path, mods):
     last = os.path.join(d, "A.B.last")
     open(last, "w").write("\n".join(lines) + "\n")
     _check_all(d, mods, last, qbed, sbed)
+
+
+def test_names_with_equal_hashes(tmp_path, mods):
+    """Two BED names with the same 32-bit table hash cannot both live in the perfect-hash table: the
+    second goes to the overflow list that lookups consult after a miss.  Colliding names are found
+    by a birthday search with the library's own hash."""
+    import ctypes
+    probe = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jcvi_b200",
+                                     "libjx_hostprobe.so"))
+    n = 700000
+    names = ["Ag%06d" % (7 * i + 3) for i in range(n)]      # ~n^2 / 2^33 = 57 pairs of equal hashes expected
+    blob = "".join(names).encode()
+    off = np.concatenate([[0], np.cumsum([len(x) for x in names])]).astype(np.uint32)
+    out = np.zeros(n, dtype=np.uint32)
+    probe.probe_slot_hash_many(blob, off.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(n), out.ctypes.data_as(ctypes.c_void_p))
+    order = np.argsort(out, kind="stable")
+    same = np.nonzero(out[order][1:] == out[order][:-1])[0]
+    assert len(same) >= 5, "birthday search found too few collisions"
+    coll = sorted(set(order[same].tolist()) | set(order[same + 1].tolist()))
+    rng = np.random.default_rng(5)
+    others = rng.choice(n, 1500, replace=False).tolist()
+    qset = sorted(set(coll) | set(others[:700]))
+    sset = sorted(set(coll) | set(others[700:]))
+    d = str(tmp_path)
+    qbed, sbed = _beds(d, [names[i] for i in qset], [names[i] for i in sset])
+    nq, ns = len(qset), len(sset)
+    qn = lambda i: names[qset[i]] + ".1"
+    sn = lambda i: names[sset[i]]
+    lines = _lines(rng, nq, ns, 20000, qn, sn)
+    cq = [k for k, i in enumerate(qset) if i in set(coll)]
+    cs = [k for k, i in enumerate(sset) if i in set(coll)]
+    for k in range(0, len(lines), 7):                          # make sure the colliding names are hit
+        f = lines[k].split("\t"); f[0] = qn(cq[k % len(cq)]); f[1] = sn(cs[(k // 7) % len(cs)]); lines[k] = "\t".join(f)
+    last = os.path.join(d, "A.B.last")
+    open(last, "w").write("\n".join(lines) + "\n")
+    _check_all(d, mods, last, qbed, sbed)
