@@ -80,6 +80,18 @@ __global__ void k_lookup(const uint64_t* hkey, const float* hsc, uint32_t nh, co
   if (lo < nh && hkey[lo] == key) { acc[t] = 1; raw[t] = hsc[lo]; }
 }
 
+__global__ void k_iota_u32(uint32_t* p, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+// block id of every anchor in sorted order; two equal neighbours = duplicate anchors (read_anchors' assert)
+__global__ void k_anchor_blocks(const uint64_t* keys, const uint32_t* order, const uint32_t* block_in, uint32_t n,
+                                uint32_t* block_out, uint32_t* dup) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  block_out[i] = block_in[order[i]];
+  if (i && keys[i] == keys[i - 1]) atomicExch(dup, 1u);
+}
 __global__ void k_rowptr(const uint64_t* akey, uint32_t na, int sb, uint32_t G, uint32_t* rowptr) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g > G) return;
@@ -518,24 +530,16 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   for (uint32_t i = 0; i < na; ++i) ablock_h[i] = (uint32_t)a_block[aline_h[i]];
   JX_TRACE("lo: records ready");
   JX_CK(cudaMemcpyAsync(akey, akeys_h.data(), (size_t)na * 8, cudaMemcpyHostToDevice, ctx->stream));
-  {
-    std::vector<uint32_t> iota(na);
-    for (uint32_t i = 0; i < na; ++i) iota[i] = i;
-    JX_CK(cudaMemcpyAsync(aord, iota.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_CK(cudaStreamSynchronize(ctx->stream));
-  }
+  JX_ALLOC(dablock0, uint32_t, na, false);
+  JX_CK(cudaMemcpyAsync(dablock0, ablock_h.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_LAUNCH(k_iota_u32, nblk(na), 256, 0, aord, na);
   uint64_t* aks = akey; uint32_t* aos = aord;
   if ((rc = jx_sort_pairs(ctx, arena, aks, aos, na, 0, sb + qb))) return rc;
-  std::vector<uint64_t> aks_h(na); std::vector<uint32_t> aos_h(na);
-  JX_CK(cudaMemcpyAsync(aks_h.data(), aks, (size_t)na * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaMemcpyAsync(aos_h.data(), aos, (size_t)na * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
-  for (uint32_t i = 1; i < na; ++i)
-    if (aks_h[i] == aks_h[i - 1]) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
-  std::vector<uint32_t> ablock_sorted(na);
-  for (uint32_t i = 0; i < na; ++i) ablock_sorted[i] = ablock_h[aos_h[i]];
+  // block of every sorted anchor and the duplicate check stay on the device; the flag comes back with
+  // the first count read below
   JX_ALLOC(dablock, uint32_t, na, false);
-  JX_CK(cudaMemcpyAsync(dablock, ablock_sorted.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_ALLOC(d_dup, uint32_t, 1, true);
+  JX_LAUNCH(k_anchor_blocks, nblk(na), 256, 0, aks, aos, dablock0, na, dablock, d_dup);
   JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
   JX_TRACE("lo: anchors sorted (host round trip)");
   JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
@@ -555,9 +559,11 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
     unsigned grid = std::min<unsigned>(nblk((n_lines + 3) / 4), 148u * 8u);
     JX_LAUNCH(k_select_cell, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, C0, C0idx, d_cnt);
   }
-  uint32_t nC0 = 0;
+  uint32_t nC0 = 0, h_dup = 0;
   JX_CK(cudaMemcpyAsync(&nC0, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&h_dup, d_dup, 4, cudaMemcpyDeviceToHost, ctx->stream));
   JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (h_dup) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
   JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
   JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
   JX_TRACE("lo: select_cell");
