@@ -21,8 +21,14 @@ namespace {
 // 4 records per thread and iteration: the four 16-byte loads and the eight table gathers are all
 // in flight before anything is consumed (the first version was latency bound: long-scoreboard
 // stalls 84 warps per issue, 11 % issue utilisation)
-__global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ best,
-                         const uint32_t* __restrict__ qnid, const uint32_t* __restrict__ snid, double cscore,
+// best score per gene rank (the table is keyed by name id: one gather level less in k_select)
+__global__ void k_gene_best(const uint32_t* __restrict__ best, const uint32_t* __restrict__ nid, uint32_t G, uint32_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < G) out[i] = best[nid[i]];
+}
+
+__global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bestq,
+                         const uint32_t* __restrict__ bests, double cscore,
                          int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
                          uint32_t* errflag) {
   constexpr int U = 4;
@@ -30,23 +36,18 @@ __global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, 
   const uint32_t nround = (n + (32u * U - 1)) / (32u * U) * (32u * U);
   const uint32_t lane = threadIdx.x & 31u, wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U;
   for (uint32_t i0 = wbase; i0 < nround; i0 += stride) {
-    uint4 r[U]; uint32_t iq[U], is[U]; bool keep[U];
+    uint4 r[U]; bool keep[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t i = i0 + u * 32u + lane;
       r[u] = i < n ? __ldcs(recs + i) : make_uint4(JX_NOREC, 0, 0, 0);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      keep[u] = r[u].x != JX_NOREC;
-      iq[u] = keep[u] && use_cscore ? __ldg(qnid + r[u].x) : 0u;
-      is[u] = keep[u] && use_cscore ? __ldg(snid + r[u].y) : 0u;
-    }
     uint32_t bq[U], bs[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      bq[u] = keep[u] && use_cscore ? __ldg(best + iq[u]) : 0u;
-      bs[u] = keep[u] && use_cscore ? __ldg(best + is[u]) : 0u;
+      keep[u] = r[u].x != JX_NOREC;
+      bq[u] = keep[u] && use_cscore ? __ldg(bestq + r[u].x) : 0u;
+      bs[u] = keep[u] && use_cscore ? __ldg(bests + r[u].y) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -64,11 +65,11 @@ __global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, 
         }
       }
     }
+    uint32_t slot[U];
+    warp_append_multi<U>(keep, counter, slot);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t slot = warp_append(keep[u], counter);
-      if (keep[u]) { out[slot] = r[u]; out_idx[slot] = i0 + u * 32u + lane; }
-    }
+    for (int u = 0; u < U; ++u)
+      if (keep[u]) { out[slot[u]] = r[u]; out_idx[slot[u]] = i0 + u * 32u + lane; }
   }
 }
 
@@ -516,7 +517,13 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   JX_ALLOC(d_cnt, uint32_t, 2, true);
   if (nrec) {
     unsigned grid = std::min<unsigned>(nblk((nrec + 3) / 4), 148u * 8u);
-    JX_LAUNCH(k_select, grid, 256, 0, tok.recs, nrec, d_best, Q.name_id, S.name_id, opts->cscore, use_cscore ? 1 : 0, C,
+    JX_ALLOC(bestq, uint32_t, (size_t)Q.G + 1, false);
+    JX_ALLOC(bests, uint32_t, (size_t)S.G + 1, false);
+    if (use_cscore) {
+      JX_LAUNCH(k_gene_best, nblk((size_t)Q.G), 256, 0, d_best, Q.name_id, (uint32_t)Q.G, bestq);
+      JX_LAUNCH(k_gene_best, nblk((size_t)S.G), 256, 0, d_best, S.name_id, (uint32_t)S.G, bests);
+    }
+    JX_LAUNCH(k_select, grid, 256, 0, tok.recs, nrec, bestq, bests, opts->cscore, use_cscore ? 1 : 0, C,
               Cidx, d_cnt, d_cnt + 1);
   }
   uint32_t h_cnt[2] = {0, 0};

@@ -212,4 +212,26 @@ __device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* counter) {
   base = __shfl_sync(0xFFFFFFFFu, base, leader);
   return base + __popc(m & ((1u << lane) - 1));
 }
+// the same for U predicates per lane with ONE atomic per warp: the counter is a single address, and
+// 20 M records / 32 atomics on it (0.5 ns each, serialised in L2) used to be most of the selection
+// kernels' time
+template <int U>
+__device__ __forceinline__ void warp_append_multi(const bool (&pred)[U], uint32_t* counter, uint32_t (&slot)[U]) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t total = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred[u]);
+    slot[u] = total + __popc(m & lt);
+    total += __popc(m);
+  }
+  uint32_t base = 0;
+  if (total) {
+    if (lane == 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) slot[u] += base;
+}
 #endif

@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(256) k_select_cell(const uint4* __restrict__ r
       w[u] = keep[u] ? __ldg(bitmap + (bit >> 5)) >> (bit & 31) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      keep[u] = keep[u] && (w[u] & 1u);
-      const uint32_t slot = warp_append(keep[u], counter);
-      if (keep[u]) { out[slot] = r[u]; out_idx[slot] = i0 + u * 32u + lane; }
-    }
+    for (int u = 0; u < U; ++u) keep[u] = keep[u] && (w[u] & 1u);
+    uint32_t slot[U];
+    warp_append_multi<U>(keep, counter, slot);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (keep[u]) { out[slot[u]] = r[u]; out_idx[slot[u]] = i0 + u * 32u + lane; }
   }
 }
 __global__ void k_keep_near(const uint4* __restrict__ cand, const uint32_t* __restrict__ cand_idx, uint32_t n, int sb,
