@@ -32,10 +32,12 @@ __global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, 
                          int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
                          uint32_t* errflag) {
   constexpr int U = 4;
+  __shared__ uint32_t s_cnt[256 / 32 + 1];
   const uint32_t stride = gridDim.x * blockDim.x * U;
-  const uint32_t nround = (n + (32u * U - 1)) / (32u * U) * (32u * U);
-  const uint32_t lane = threadIdx.x & 31u, wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U;
-  for (uint32_t i0 = wbase; i0 < nround; i0 += stride) {
+  const uint32_t lane = threadIdx.x & 31u, woff = (threadIdx.x & ~31u) * U;
+  // the trip count is uniform over the CTA (block_append_multi synchronises)
+  for (uint64_t c0 = (uint64_t)blockIdx.x * blockDim.x * U; c0 < n; c0 += stride) {
+    const uint32_t i0 = (uint32_t)c0 + woff;
     uint4 r[U]; bool keep[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, 
       }
     }
     uint32_t slot[U];
-    warp_append_multi<U>(keep, counter, slot);
+    block_append_multi<U>(keep, counter, slot, s_cnt);
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (keep[u]) { out[slot[u]] = r[u]; out_idx[slot[u]] = i0 + u * 32u + lane; }

@@ -212,6 +212,33 @@ __device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* counter) {
   base = __shfl_sync(0xFFFFFFFFu, base, leader);
   return base + __popc(m & ((1u << lane) - 1));
 }
+// U predicates per lane, ONE atomic per CTA: every warp of the CTA must call this the same number of
+// times (uniform trip counts); `s_cnt` is a shared array of blockDim.x / 32 + 1 words
+template <int U>
+__device__ __forceinline__ void block_append_multi(const bool (&pred)[U], uint32_t* counter, uint32_t (&slot)[U],
+                                                   uint32_t* s_cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t total = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred[u]);
+    slot[u] = total + __popc(m & lt);
+    total += __popc(m);
+  }
+  if (lane == 0) s_cnt[warp] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t sum = 0;
+    for (int w = 0; w < nwarp; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = sum; sum += c; }
+    s_cnt[nwarp] = sum ? atomicAdd(counter, sum) : 0u;
+  }
+  __syncthreads();
+  const uint32_t base = s_cnt[nwarp] + s_cnt[warp];
+  __syncthreads();                       // s_cnt is reused by the next call
+#pragma unroll
+  for (int u = 0; u < U; ++u) slot[u] += base;
+}
 // the same for U predicates per lane with ONE atomic per warp: the counter is a single address, and
 // 20 M records / 32 atomics on it (0.5 ns each, serialised in L2) used to be most of the selection
 // kernels' time

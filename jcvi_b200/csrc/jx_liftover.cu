@@ -142,10 +142,12 @@ __device__ __forceinline__ bool anchor_within(int32_t x, int32_t y, int sb, cons
 __global__ void __launch_bounds__(256) k_select_cell(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bitmap,
                                                      int cshift, uint32_t nsc, uint4* out, uint32_t* out_idx, uint32_t* counter) {
   constexpr int U = 4;
+  __shared__ uint32_t s_cnt[256 / 32 + 1];
   const uint32_t stride = gridDim.x * blockDim.x * U;
-  const uint32_t nround = (n + (32u * U - 1)) / (32u * U) * (32u * U);
-  const uint32_t lane = threadIdx.x & 31u, wbase = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * U;
-  for (uint32_t i0 = wbase; i0 < nround; i0 += stride) {
+  const uint32_t lane = threadIdx.x & 31u, woff = (threadIdx.x & ~31u) * U;
+  // the trip count is uniform over the CTA (block_append_multi synchronises)
+  for (uint64_t c0 = (uint64_t)blockIdx.x * blockDim.x * U; c0 < n; c0 += stride) {
+    const uint32_t i0 = (uint32_t)c0 + woff;
     uint4 r[U]; bool keep[U]; uint32_t w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(256) k_select_cell(const uint4* __restrict__ r
 #pragma unroll
     for (int u = 0; u < U; ++u) keep[u] = keep[u] && (w[u] & 1u);
     uint32_t slot[U];
-    warp_append_multi<U>(keep, counter, slot);
+    block_append_multi<U>(keep, counter, slot, s_cnt);
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (keep[u]) { out[slot[u]] = r[u]; out_idx[slot[u]] = i0 + u * 32u + lane; }
