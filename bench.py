@@ -175,7 +175,7 @@ def impl_reference(args):
                                    "oracle/jcvi_oracle.cpp single thread (the reference is single-threaded Python)" % n},
         "e2e": {"value": val, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def impl_ours(args):
@@ -310,7 +310,7 @@ def impl_ours(args):
         roof = {"bound": "hbm", "kernel": "k_tokenize (K1 tokenizer + K2 hash join, fused K4 best-score)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback",
-                "traffic": traffic, "traffic_note": "dram__bytes_read+write of one full 64 MiB launch (67.1 MB text + 15.1 MB records algorithmic), profiles/r1_tokenize_traffic.json",
+                "traffic": traffic, "traffic_note": "dram__bytes_read+write of one launch over the whole resident table (1426.7 MB text + 320.0 MB records algorithmic), ncu capture in profiles/r1_tokenize_traffic.json",
                 "launches": tok_launches, "avg_launch_ms": tok_ms / max(tok_launches, 1),
                 "algorithmic_bytes_per_launch": alg_bytes / max(tok_launches, 1),
                 "share_of_step": tok_ms / dev_ms if dev_ms else None}
@@ -354,13 +354,35 @@ def impl_ours(args):
                                        "byte-identical: %s" % (ncpu, times[0], t_cli, parity)},
             "wall_ms_per_step": wall_ms / args.steps,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library prints on fd 1 (NCCL's version
+    banner, ...) is sent to stderr; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
