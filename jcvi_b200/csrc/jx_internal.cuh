@@ -24,10 +24,21 @@
 #ifndef JX_TOK_MINBLOCKS
 #define JX_TOK_MINBLOCKS 8
 #endif
-constexpr int JX_TOK_THREADS = 128;
+constexpr int JX_TOK_THREADS = 128;                      // threads per CTA of the tokenizer
+// JX_GROUP threads cooperate on one tile.  128: one 8 KiB tile per CTA (phases separated by CTA
+// barriers).  32: every warp owns its own 1920-byte tiles (+128 bytes of look-ahead = 64 mask words,
+// two per lane) and never waits for another warp.
+#ifndef JX_GROUP
+#define JX_GROUP 128
+#endif
 constexpr int JX_SEG = 64;                               // bytes of the tile owned by one thread
-constexpr int JX_TILE = JX_TOK_THREADS * JX_SEG;         // 8192
-constexpr int JX_OVER = 1024;                            // look-ahead staged in shared memory
+#if JX_GROUP == 32
+constexpr int JX_TILE = 30 * JX_SEG;                     // 1920
+constexpr int JX_OVER = 128;                             // look-ahead staged in shared memory
+#else
+constexpr int JX_TILE = JX_GROUP * JX_SEG;               // 8192
+constexpr int JX_OVER = 1024;
+#endif
 constexpr int JX_WIN = JX_TILE + JX_OVER;
 
 struct SideDev {

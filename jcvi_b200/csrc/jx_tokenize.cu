@@ -48,7 +48,11 @@ struct TokArgs {
 #define VAL_MASK ((1ull << 62) - 1)
 
 #ifndef JX_LCAP
+#if JX_GROUP == 32
+#define JX_LCAP 128
+#else
 #define JX_LCAP 1024
+#endif
 #endif
 constexpr int LCAP = JX_LCAP;     // line starts of a tile kept in shared memory (more -> search path)
 
@@ -148,19 +152,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // works on the current one, so the HBM latency of staging is off the critical path and costs no
 // load/store instructions.
 __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(const TokArgs a) {
-  __shared__ __align__(128) uint8_t s_text[2][STAGE_BYTES];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ uint32_t s_term[JX_WIN / 32];      // terminator bit per byte of the window
-  __shared__ uint32_t s_w[JX_WIN / 32];         // byte <= 0x20
-  __shared__ uint32_t s_n[JX_WIN / 32];         // byte is neither a digit nor a tab
-  __shared__ uint32_t s_pref[JX_TOK_THREADS];   // exclusive prefix of line starts per 64-byte segment
-  __shared__ unsigned long long s_start[JX_TOK_THREADS];
-  __shared__ uint16_t s_lpos[LCAP];             // start offset of every line of the tile
-  __shared__ uint32_t s_warp[JX_TOK_THREADS / 32];
-  __shared__ uint32_t s_next[2];
-  __shared__ unsigned long long s_base;
+  constexpr int NGRP = JX_TOK_THREADS / JX_GROUP;          // independent tile groups per CTA
+  constexpr int GWARPS = JX_GROUP / 32;
+  __shared__ __align__(128) uint8_t g_text[NGRP][2][STAGE_BYTES];
+  __shared__ __align__(8) uint64_t g_bar[NGRP][2];
+  __shared__ uint32_t g_term[NGRP][JX_WIN / 32];      // terminator bit per byte of the window
+  __shared__ uint32_t g_w[NGRP][JX_WIN / 32];         // byte <= 0x20
+  __shared__ uint32_t g_n[NGRP][JX_WIN / 32];         // byte is neither a digit nor a tab
+  __shared__ uint32_t g_pref[NGRP][JX_GROUP];         // exclusive prefix of line starts per 64-byte segment
+  __shared__ unsigned long long g_start[NGRP][JX_GROUP];
+  __shared__ uint16_t g_lpos[NGRP][LCAP];             // start offset of every line of the tile
+  __shared__ uint32_t g_warp[NGRP][GWARPS];
+  __shared__ uint32_t g_next[NGRP][2];
+  __shared__ unsigned long long g_base[NGRP];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = threadIdx.x / JX_GROUP;
+  const int tid = threadIdx.x % JX_GROUP, lane = tid & 31, warp = tid >> 5;   // within the group
+  uint8_t (*s_text)[STAGE_BYTES] = g_text[grp];
+  uint64_t* s_bar = g_bar[grp];
+  uint32_t* s_term = g_term[grp]; uint32_t* s_w = g_w[grp]; uint32_t* s_n = g_n[grp];
+  uint32_t* s_pref = g_pref[grp]; unsigned long long* s_start = g_start[grp];
+  uint16_t* s_lpos = g_lpos[grp]; uint32_t* s_warp = g_warp[grp]; uint32_t* s_next = g_next[grp];
+  unsigned long long& s_base = g_base[grp];
+  // group-wide synchronisation: a CTA barrier for one group per CTA, a warp barrier for warp groups
+  auto gsync = [&]() { if (JX_GROUP == 32) __syncwarp(); else __syncthreads(); };
+  auto gany = [&](bool p) -> bool {
+    if (JX_GROUP == 32) { __syncwarp(); return __any_sync(0xFFFFFFFFu, p) != 0; }
+    return __syncthreads_or(p) != 0;
+  };
   uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0, c_lines = 0;
   unsigned long long first_bad = 0;
   bool overflow = false;
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     s_next[0] = t;
     if (t < a.tile_end) issue(t, 0);
   }
-  __syncthreads();
+  gsync();
   uint32_t tile = s_next[0];
 
   for (uint32_t it = 0; tile < a.tile_end; ++it) {
@@ -207,15 +226,15 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     }
     if (avail < (uint32_t)STAGE_BYTES) {          // last tiles of the text only
       uint8_t* wsm = s_text[stage];
-      for (uint32_t i = bulk + tid; i < (uint32_t)STAGE_BYTES; i += JX_TOK_THREADS)
+      for (uint32_t i = bulk + tid; i < (uint32_t)STAGE_BYTES; i += JX_GROUP)
         wsm[i] = i < avail ? a.text[base + i] : (uint8_t)'\n';
-      __syncthreads();
+      gsync();
     }
   }
 
   // ---- byte classes (SWAR, 32 bytes per mask word) and the terminator mask -----------------------------
   uint32_t hiacc = 0;
-  for (int seg = tid; seg < JX_WIN / 32; seg += JX_TOK_THREADS) {
+  for (int seg = tid; seg < JX_WIN / 32; seg += JX_GROUP) {
     const uint4 v0 = reinterpret_cast<const uint4*>(smw)[2 * seg], v1 = reinterpret_cast<const uint4*>(smw)[2 * seg + 1];
     const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     uint32_t wm, nm;
@@ -232,11 +251,11 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     }
     s_term[seg] = term;
   }
-  const int has_bar = __syncthreads_or((hiacc & 0x80808080u) != 0u);   // may the tile hold a '|' ?
+  const bool has_bar = gany((hiacc & 0x80808080u) != 0u);   // may the tile hold a '|' ?  (also: masks visible)
 
   // ---- line starts inside the tile (64 bytes per thread) + block scan ----------------------------------
-  unsigned long long starts;
-  {
+  unsigned long long starts = 0;
+  if (tid * JX_SEG < JX_TILE) {
     const unsigned long long term = (unsigned long long)s_term[2 * tid] | ((unsigned long long)s_term[2 * tid + 1] << 32);
     uint32_t prevbit;
     if (tid == 0) prevbit = (base == 0) ? 1u : (uint32_t)jx::is_term(a.text[base - 1]);
@@ -250,11 +269,15 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   uint32_t inc = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
   uint32_t wbase = 0, nlines = 0;
+  if (JX_GROUP == 32) {
+    nlines = __shfl_sync(0xFFFFFFFFu, inc, 31);
+  } else {
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
 #pragma unroll
-  for (int w = 0; w < JX_TOK_THREADS / 32; ++w) { const uint32_t v = s_warp[w]; if (w < warp) wbase += v; nlines += v; }
+    for (int w = 0; w < GWARPS; ++w) { const uint32_t v = s_warp[w]; if (w < warp) wbase += v; nlines += v; }
+  }
   const uint32_t mypref = wbase + inc - cnt;
   s_pref[tid] = mypref;
   s_start[tid] = starts;
@@ -330,9 +353,9 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     }
     if (lane == 0) s_base = excl;
   };
-  const bool defer = nlines <= JX_TOK_THREADS;     // uniform over the CTA
+  const bool defer = nlines <= JX_GROUP;           // uniform over the group
   if (!defer && warp == 0) look_back();
-  __syncthreads();                                 // line starts (and, if resolved, s_base) visible
+  gsync();                                         // line starts (and, if resolved, s_base) visible
 
   // ---- parse: one line per thread -----------------------------------------------------------------
   WinReader rd{sm, a.text, base, a.n};
@@ -343,13 +366,13 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   const SideTab TS{a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob, a.sovh, a.sovr, a.snov};
   uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
   bool have_held = false;
-  for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
+  for (uint32_t k0 = 0; k0 < nlines; k0 += JX_GROUP) {
     const uint32_t k = k0 + tid;
     if (k >= nlines) break;
     int s;
     if (k < LCAP) s = s_lpos[k];
     else {   // overfull tile (average line < 8 bytes): locate the line through the prefix array
-      int lo = 0, hi = JX_TOK_THREADS - 1;
+      int lo = 0, hi = JX_GROUP - 1;
       while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= k) lo = mid; else hi = mid - 1; }
       unsigned long long m = s_start[lo];
       for (uint32_t r = k - s_pref[lo]; r; --r) m &= m - 1;
@@ -477,7 +500,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   if (defer) {
     __syncwarp();
     if (warp == 0) look_back();
-    __syncthreads();
+    gsync();
     const unsigned long long ord = s_base + tid;
     if (have_held && ord < a.rec_cap) a.recs[ord] = held;
   }
@@ -485,7 +508,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     c_lines += nlines;
     if (s_base + nlines > a.rec_cap) overflow = true;
   }
-  __syncthreads();                                 // this stage and the scratch arrays are free again
+  gsync();                                         // this stage and the scratch arrays are free again
   tile = s_next[stage ^ 1];
   }  // tiles
 
@@ -553,7 +576,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   // record capacity: lines are >= 24 bytes in any real table; retry with the exact worst case
   // (every byte a line) only if that guess overflows.
   JX_ALLOC(d_stats, unsigned long long, 12, true);
-  JX_ALLOC(d_ticket, uint32_t, (size_t)std::max<int64_t>(nchunks, 1), true);   // one ticket counter per launch
+  JX_ALLOC(d_ticket, uint32_t, (size_t)nchunks + 2, true);   // one ticket counter per launch
   const bool to_cache = held && ((mode.fill_cache && !ctx->is_self && mode.n_excl == 0 && !mode.neardiag) || mode.persist);
   if (to_cache) ctx->cache.valid = false;    // about to overwrite the retained records
   uint64_t* d_desc = nullptr;
@@ -592,7 +615,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     out.recs = recs;
     if (attempt) {
       JX_CK(cudaMemsetAsync(d_stats, 0, 12 * sizeof(unsigned long long), ctx->stream));
-      JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(nchunks, 1), ctx->stream));
+      JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t) * ((size_t)nchunks + 2), ctx->stream));
       JX_CK(cudaMemsetAsync(d_desc, 0, (size_t)ntiles * sizeof(uint64_t), ctx->stream));
       if (mode.best) JX_CK(cudaMemsetAsync(mode.best, 0, (size_t)ctx->n_name_ids * sizeof(uint32_t), ctx->stream));
     }
