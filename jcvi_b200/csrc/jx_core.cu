@@ -71,6 +71,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
   cudaFree(ctx->held_text);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+  if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
   cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);
   cudaFree(ctx->lastf.q); cudaFree(ctx->lastf.s); cudaFree(ctx->lastf.score);
   for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }

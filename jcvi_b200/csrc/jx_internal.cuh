@@ -92,6 +92,8 @@ struct jx_ctx {
   bool sess_open = false;
   char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text
   size_t pin_cap = 0;
+  char* pin_small = nullptr;     // grow-only pinned staging for small result arrays (one D2H instead of several pageable ones)
+  size_t pin_small_cap = 0;
   uint8_t* held_text = nullptr;
   int64_t held_n = 0;
   int64_t held_cap = 0;
@@ -119,6 +121,19 @@ inline void jx_trace_point(jx_ctx* ctx, const char* label) {
   ctx->trace_t0 = t;
 }
 #define JX_TRACE(label) jx_trace_point(ctx, label)
+
+// pinned staging of at least `bytes` (valid until the next call of this function on the context)
+inline int jx_pin_small(jx_ctx* ctx, size_t bytes, char** out) {
+  if (ctx->pin_small_cap < bytes) {
+    if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
+    ctx->pin_small = nullptr; ctx->pin_small_cap = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    if (cudaMallocHost((void**)&ctx->pin_small, cap) != cudaSuccess) { ctx->err = "cudaMallocHost failed"; return JX_ECUDA; }
+    ctx->pin_small_cap = cap;
+  }
+  *out = ctx->pin_small;
+  return JX_OK;
+}
 
 #define JX_LAUNCH(kernel, grid, block, smem, ...)                                           \
   do {                                                                                      \

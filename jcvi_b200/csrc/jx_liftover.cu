@@ -692,15 +692,19 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
     JX_LAUNCH(k_block_keys, nblk(nlift), 256, 0, v1s, hit_block, nlift, k2);
     uint64_t* k2s = k2;
     if ((rc = jx_sort_pairs(ctx, arena, k2s, v1s, nlift, 0, 32))) return rc;
-    JX_ALLOC(oq, int32_t, nlift, false);
-    JX_ALLOC(os, int32_t, nlift, false);
-    JX_ALLOC(osc, float, nlift, false);
-    JX_ALLOC(ob, int32_t, nlift, false);
+    // one device block, one copy into pinned staging (instead of four synchronous pageable copies)
+    JX_ALLOC(oblk, uint32_t, (size_t)nlift * 4, false);
+    int32_t* oq = (int32_t*)oblk; int32_t* os = (int32_t*)(oblk + nlift); float* osc = (float*)(oblk + 2 * (size_t)nlift);
+    int32_t* ob = (int32_t*)(oblk + 3 * (size_t)nlift);
     JX_LAUNCH(k_emit_lifted, nblk(nlift), 256, 0, v1s, nlift, hkey, hsc, hit_block, sb, oq, os, osc, ob);
-    JX_CK(cudaMemcpyAsync(out->q_rank, oq, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->s_rank, os, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->score, osc, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->block, ob, (size_t)nlift * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    char* stage = nullptr;
+    if ((rc = jx_pin_small(ctx, (size_t)nlift * 16, &stage))) return rc;
+    JX_CK(cudaMemcpyAsync(stage, oblk, (size_t)nlift * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out->q_rank, stage, (size_t)nlift * 4);
+    memcpy(out->s_rank, stage + (size_t)nlift * 4, (size_t)nlift * 4);
+    memcpy(out->score, stage + (size_t)nlift * 8, (size_t)nlift * 4);
+    memcpy(out->block, stage + (size_t)nlift * 12, (size_t)nlift * 4);
   }
   JX_CK(cudaStreamSynchronize(ctx->stream));
   JX_TRACE("lo: order+emit");

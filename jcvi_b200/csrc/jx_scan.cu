@@ -224,20 +224,22 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
     JX_LAUNCH(k_out_keys, nblk(n), 256, 0, flag, pos, label, birth, n, okeys, ovals);
     uint64_t* ok = okeys; uint32_t* ov = ovals;
     if ((rc = jx_sort_pairs(ctx, arena, ok, ov, m, 0, 64))) return rc;
-    JX_ALLOC(oq, int32_t, m, false);
-    JX_ALLOC(os, int32_t, m, false);
-    JX_ALLOC(osc, float, m, false);
-    JX_ALLOC(oidx, uint32_t, m, false);
-    JX_ALLOC(head, uint32_t, m, false);
+    // the five result arrays are one device block: ONE copy into pinned staging instead of five
+    // synchronous pageable copies
+    JX_ALLOC(oblk, uint32_t, (size_t)m * 5, false);
+    int32_t* oq = (int32_t*)oblk; int32_t* os = (int32_t*)(oblk + m); float* osc = (float*)(oblk + 2 * (size_t)m);
+    uint32_t* oidx = oblk + 3 * (size_t)m; uint32_t* head = oblk + 4 * (size_t)m;
     JX_TRACE("scan: out sort");
     JX_LAUNCH(k_emit, nblk(m), 256, 0, ok, ov, m, px, py, psc, pidx, oq, os, osc, oidx, head);
-    std::vector<uint32_t> hhead(m), hidx(m);
-    JX_CK(cudaMemcpyAsync(out->q_rank, oq, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->s_rank, os, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->score, osc, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(hhead.data(), head, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(hidx.data(), oidx, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    char* stage = nullptr;
+    if ((rc = jx_pin_small(ctx, (size_t)m * 20, &stage))) return rc;
+    JX_CK(cudaMemcpyAsync(stage, oblk, (size_t)m * 20, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out->q_rank, stage, (size_t)m * 4);
+    memcpy(out->s_rank, stage + (size_t)m * 4, (size_t)m * 4);
+    memcpy(out->score, stage + (size_t)m * 8, (size_t)m * 4);
+    const uint32_t* hidx = (const uint32_t*)(stage + (size_t)m * 12);
+    const uint32_t* hhead = (const uint32_t*)(stage + (size_t)m * 16);
     JX_TRACE("scan: emit + D2H");
     int64_t nb = 0;
     for (uint32_t t = 0; t < m; ++t) nb += hhead[t];
