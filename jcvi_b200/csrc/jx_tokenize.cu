@@ -156,9 +156,10 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   constexpr int GWARPS = JX_GROUP / 32;
   __shared__ __align__(128) uint8_t g_text[NGRP][2][STAGE_BYTES];
   __shared__ __align__(8) uint64_t g_bar[NGRP][2];
-  __shared__ uint32_t g_term[NGRP][JX_WIN / 32];      // terminator bit per byte of the window
-  __shared__ uint32_t g_w[NGRP][JX_WIN / 32];         // byte <= 0x20
-  __shared__ uint32_t g_n[NGRP][JX_WIN / 32];         // byte is neither a digit nor a tab
+  // (+2 words: a 64-bit mask window that starts in the last words reads past the window; those bits are masked off)
+  __shared__ uint32_t g_term[NGRP][JX_WIN / 32 + 2];      // terminator bit per byte of the window
+  __shared__ uint32_t g_w[NGRP][JX_WIN / 32 + 2];         // byte <= 0x20
+  __shared__ uint32_t g_n[NGRP][JX_WIN / 32 + 2];         // byte is neither a digit nor a tab
   __shared__ uint32_t g_pref[NGRP][JX_GROUP];         // exclusive prefix of line starts per 64-byte segment
   __shared__ unsigned long long g_start[NGRP][JX_GROUP];
   __shared__ uint16_t g_lpos[NGRP][LCAP];             // start offset of every line of the tile
