@@ -88,12 +88,7 @@ int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, i
   if (!ctx) return JX_EARG;
   cudaSetDevice(ctx->device);
   JX_CK(cudaStreamSynchronize(ctx->stream));
-  for (auto& ev : ctx->tok_events) {
-    float t = 0;
-    if (cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) { ctx->tok_ms_acc += t; ++ctx->tok_launches_acc; }
-    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
-  }
-  ctx->tok_events.clear();
+  jx_harvest_tok_events(ctx);
   if (ms) *ms = ctx->tok_ms_acc;
   if (launches) *launches = ctx->tok_launches_acc;
   if (bytes) *bytes = ctx->tok_bytes;

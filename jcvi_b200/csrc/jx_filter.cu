@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, 
                          const uint32_t* __restrict__ bests, double cscore,
                          int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
                          uint32_t* errflag) {
-  constexpr int U = 4;
+#ifndef JX_SEL_U
+#define JX_SEL_U 4
+#endif
+  constexpr int U = JX_SEL_U;
   __shared__ uint32_t s_cnt[256 / 32 + 1];
   const uint32_t stride = gridDim.x * blockDim.x * U;
   const uint32_t lane = threadIdx.x & 31u, woff = (threadIdx.x & ~31u) * U;

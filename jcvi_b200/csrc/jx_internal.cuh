@@ -74,6 +74,7 @@ struct jx_ctx {
   int64_t launches = 0;
   // tokenizer timing (CUDA events on `stream`)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
+  int64_t tok_resident = 0;      // persistent tokenizer CTAs that fit on this device at once
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
   // records of the last jx_blastfilter pass over the held text, for jx_liftover_text
@@ -121,6 +122,17 @@ inline void jx_trace_point(jx_ctx* ctx, const char* label) {
   ctx->trace_t0 = t;
 }
 #define JX_TRACE(label) jx_trace_point(ctx, label)
+
+// fold finished tokenizer launch timings into the accumulators (call after a stream synchronise);
+// keeps the event list from growing when nobody asks for jx_tokenizer_timing
+inline void jx_harvest_tok_events(jx_ctx* ctx) {
+  for (auto& ev : ctx->tok_events) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) { ctx->tok_ms_acc += t; ++ctx->tok_launches_acc; }
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  ctx->tok_events.clear();
+}
 
 // pinned staging of at least `bytes` (valid until the next call of this function on the context)
 inline int jx_pin_small(jx_ctx* ctx, size_t bytes, char** out) {

@@ -141,7 +141,10 @@ __device__ __forceinline__ bool anchor_within(int32_t x, int32_t y, int sb, cons
 // loop executes with full warps (one fused kernel ran with 5 of 32 lanes active).
 __global__ void __launch_bounds__(256) k_select_cell(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bitmap,
                                                      int cshift, uint32_t nsc, uint4* out, uint32_t* out_idx, uint32_t* counter) {
-  constexpr int U = 4;
+#ifndef JX_SEL_U
+#define JX_SEL_U 4
+#endif
+  constexpr int U = JX_SEL_U;
   __shared__ uint32_t s_cnt[256 / 32 + 1];
   const uint32_t stride = gridDim.x * blockDim.x * U;
   const uint32_t lane = threadIdx.x & 31u, woff = (threadIdx.x & ~31u) * U;

@@ -636,13 +636,13 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     a.stats = d_stats;
     const int64_t tiles_per_chunk = CHUNK / JX_TILE;
     // persistent CTAs: as many as are resident at once
-    static int64_t resident = 0;
-    if (!resident) {
+    if (!ctx->tok_resident) {
       int per_sm = 0, n_sm = 0;
       JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize, JX_TOK_THREADS, 0));
       JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-      resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
+      ctx->tok_resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
     }
+    const int64_t resident = ctx->tok_resident;
     // copies still in flight: one launch per 64 MiB chunk, each behind its copy; a text that is already
     // resident is tokenized by ONE launch (no ramp-up / ramp-down per chunk)
     bool pending = (!on_device || held) && attempt == 0 && !copied.empty();
@@ -673,6 +673,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     JX_CK(cudaGetLastError());
     JX_CK(cudaMemcpyAsync(out.stats, d_stats, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaStreamSynchronize(ctx->stream));
+    jx_harvest_tok_events(ctx);
     if (!out.stats[6]) break;
     if (attempt == 1) { ctx->err = "record buffer overflow"; return JX_EINTERNAL; }
   }
