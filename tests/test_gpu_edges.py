@@ -201,3 +201,25 @@ def test_names_with_equal_hashes(tmp_path, mods):
     last = os.path.join(d, "A.B.last")
     open(last, "w").write("\n".join(lines) + "\n")
     _check_all(d, mods, last, qbed, sbed)
+
+
+def test_tiny_and_truncated_tables(tmp_path, mods):
+    """Texts shorter than one 16-byte bulk-copy granule, ending mid-line, or ending exactly on a
+    granule boundary: the last tile is staged partly by the bulk copy and partly by hand."""
+    import oracle
+    bf, _ = mods
+    rng = np.random.default_rng(9)
+    nq = ns = 50
+    d = str(tmp_path)
+    qbed, sbed = _beds(d, ["Ag%06d" % i for i in range(nq)], ["Bg%06d" % i for i in range(ns)])
+    body = "\n".join(_lines(rng, nq, ns, 40, lambda i: "Ag%06d.1" % i, lambda i: "Bg%06d.1" % i)) + "\n"
+    cut_at = [0, 1, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, len(body) - 1, len(body)]
+    first = body.index("\n") + 1
+    cut_at += [first - 1, first, first + 1, first + 16, 8 * first]
+    beds = ["--qbed=" + qbed, "--sbed=" + sbed]
+    for n in sorted(set(cut_at)):
+        last = os.path.join(d, "t%d.last" % n)
+        open(last, "w").write(body[:n])
+        oracle.blastfilter(last, qbed, sbed, out_path=last + ".orc", cscore=0)
+        bf.main([last] + beds + ["--cscore=0"])
+        assert read(last + ".filtered") == read(last + ".orc"), n
