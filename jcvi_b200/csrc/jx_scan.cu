@@ -75,6 +75,29 @@ __global__ void k_iota(uint32_t* p, uint32_t n) {
   if (i < n) p[i] = i;
 }
 
+// records known to be valid and pair-unique (blastfilter's own survivors): one sort on
+// (chromosome pair, qi, si) replaces select + pair de-duplication + the stable pair sort
+__global__ void k_point_keys(const uint4* __restrict__ recs, uint32_t n, int sb, int qb, const int32_t* __restrict__ qchr,
+                             const int32_t* __restrict__ schr, int64_t nschr, uint64_t* keys, uint32_t* vals) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint4 r = recs[t];
+  const uint64_t cp = (uint64_t)qchr[r.x] * (uint64_t)nschr + (uint64_t)schr[r.y];
+  keys[t] = (cp << (sb + qb)) | ((uint64_t)r.x << sb) | (uint64_t)r.y;
+  vals[t] = t;
+}
+__global__ void k_points_from_keys(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                   const uint4* __restrict__ recs, uint32_t n, int sb, int qb, int32_t* px, int32_t* py,
+                                   float* psc, uint64_t* cpkey) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint64_t k = keys[t];
+  px[t] = (int32_t)((k >> sb) & ((1ull << qb) - 1));
+  py[t] = (int32_t)(k & ((1ull << sb) - 1));
+  cpkey[t] = k >> (sb + qb);
+  psc[t] = __uint_as_float(recs[vals[t]].z);
+}
+
 // synteny_scan inner loops: for point i walk back while x_i - x_j <= xdist (same chromosome pair)
 __global__ void k_link(const int32_t* __restrict__ px, const int32_t* __restrict__ py, const uint64_t* __restrict__ cp,
                        uint32_t n, int xdist, int ydist, int is_self, int intrabound, uint32_t* parent, uint8_t* hasprev) {
@@ -261,10 +284,30 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
 
 // records (file order, holes marked JX_NOREC) -> scan
 int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, size_t nvalid_hint, const jx_scan_opts* o,
-                 jx_scan_result* out) {
+                 jx_scan_result* out, bool valid_unique = false) {
   const SideDev& Q = ctx->side[0];
   const SideDev& S = ctx->side[1];
   int rc;
+  {
+    const int sb0 = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb0 = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+    const uint64_t maxcp0 = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
+    if (valid_unique && nrec && jx_bits(maxcp0) + sb0 + qb0 <= 64) {
+      const uint32_t n = nrec;
+      JX_ALLOC(keys, uint64_t, n, false);
+      JX_ALLOC(vals, uint32_t, n, false);
+      JX_LAUNCH(k_point_keys, nblk(n), 256, 0, recs, n, sb0, qb0, Q.chr_lex, S.chr_lex, (int64_t)S.n_chr, keys, vals);
+      uint64_t* ks = keys; uint32_t* vs = vals;
+      if ((rc = jx_sort_pairs(ctx, arena, ks, vs, n, 0, jx_bits(maxcp0) + sb0 + qb0))) return rc;
+      JX_ALLOC(x1, int32_t, n, false);
+      JX_ALLOC(y1, int32_t, n, false);
+      JX_ALLOC(s1, float, n, false);
+      JX_ALLOC(c1, uint64_t, n, false);
+      JX_LAUNCH(k_points_from_keys, nblk(n), 256, 0, ks, vs, recs, n, sb0, qb0, x1, y1, s1, c1);
+      JX_TRACE("scan: single sort (valid, unique input)");
+      out->stats[1] = n;
+      return scan_sorted_points(ctx, arena, x1, y1, s1, c1, nullptr, n, ctx->is_self ? 1 : 0, o, out);
+    }
+  }
   JX_ALLOC(C, uint4, nvalid_hint + 1, false);
   JX_ALLOC(Cidx, uint32_t, nvalid_hint + 1, false);
   JX_ALLOC(d_cnt, uint32_t, 1, true);
@@ -368,10 +411,12 @@ int jx_scan_filtered(jx_ctx* ctx, const jx_filter_result* f, const jx_scan_opts*
   JX_ALLOC(dsc, float, n, false);
   JX_ALLOC(recs, uint4, n, false);
   JX_ALLOC(bad, uint32_t, 1, true);
+  bool resident_survivors = false;
   if (n) {
     const int32_t* srcq = dq; const int32_t* srcs = ds; const float* srcsc = dsc;
     if (f->device_token && f->device_token == ctx->lastf.token && (int64_t)n == ctx->lastf.n) {
       srcq = ctx->lastf.q; srcs = ctx->lastf.s; srcsc = ctx->lastf.score;      // still resident: no round trip
+      resident_survivors = true;
     } else {
       if (!f->q_rank || !f->s_rank || !f->score) { ctx->err = "filter result has no host arrays and is no longer resident"; return JX_EARG; }
       JX_CK(cudaMemcpyAsync(dq, f->q_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -386,7 +431,9 @@ int jx_scan_filtered(jx_ctx* ctx, const jx_filter_result* f, const jx_scan_opts*
   JX_CK(cudaStreamSynchronize(ctx->stream));
   if (hbad) { ctx->err = "score outside the exactly handled %.3g range"; return JX_EUNSUPPORTED; }
   out->stats[0] = n;
-  return scan_records(ctx, arena, recs, n, n, opts, out);
+  // the library's own survivors are valid and pair-unique (blastfilter de-duplicates twice); a self
+  // comparison re-orients pairs (qi <= si) and can make duplicates, and host arrays may be anything
+  return scan_records(ctx, arena, recs, n, n, opts, out, resident_survivors && !ctx->is_self);
 }
 
 int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const float* score, const int64_t* group,
