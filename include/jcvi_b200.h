@@ -67,6 +67,10 @@ int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, i
  * jx_text_release or jx_ctx_destroy.  Pinned host memory gives full PCIe speed. */
 int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t* device_ptr);
 int jx_text_release(jx_ctx* ctx);
+/* jx_liftover_text on the SAME resident text re-uses the records jx_blastfilter just tokenized (the
+ * reference parses the raw table twice: blastfilter.py:48 and synteny.py:1939).  on = 0 turns that
+ * off (every call tokenizes); default 1.  Results are identical either way. */
+int jx_set_record_reuse(jx_ctx* ctx, int on);
 
 /* ---- BED side tables -------------------------------------------------------------------
  * Replaces the name -> (rank, BedLine) dicts of Bed.order (formats/bed.py:196-198) and the

@@ -60,7 +60,7 @@ EXPORTS = [
     "jx_ctx_create", "jx_ctx_destroy", "jx_last_error", "jx_version", "jx_launch_count", "jx_stream_handle",
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
-    "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release",
+    "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse",
     "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_free", "jx_abi_sizes",
 ]
 
@@ -109,6 +109,7 @@ def lib():
                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.jx_text_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64)]
         L.jx_text_release.argtypes = [ctypes.c_void_p]
+        L.jx_set_record_reuse.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.jx_cscore_begin.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
         L.jx_cscore_finish.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p), c_i64p, c_i64p]

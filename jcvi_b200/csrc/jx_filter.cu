@@ -504,7 +504,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     JX_ALLOC(b, uint32_t, (size_t)ctx->n_name_ids + 1, true);
     d_best = b; mode.best = b;
   }
-  mode.fill_cache = true;      // jx_liftover_text on the same held text reuses these records
+  mode.fill_cache = ctx->record_reuse;      // jx_liftover_text on the same held text reuses these records
   TokOut tok;
   if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
   out->stats[0] = (int64_t)(tok.stats[0] - tok.stats[1]);

@@ -74,6 +74,7 @@ struct jx_ctx {
   int64_t launches = 0;
   // tokenizer timing (CUDA events on `stream`)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
+  bool record_reuse = true;      // jx_set_record_reuse
   int64_t tok_resident = 0;      // persistent tokenizer CTAs that fit on this device at once
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)

@@ -706,6 +706,13 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
 
 extern "C" {
 
+int jx_set_record_reuse(jx_ctx* ctx, int on) {
+  if (!ctx) return JX_EARG;
+  ctx->record_reuse = on != 0;
+  if (!on) ctx->cache.valid = false;
+  return JX_OK;
+}
+
 int jx_text_release(jx_ctx* ctx) {
   if (!ctx) return JX_EARG;
   cudaSetDevice(ctx->device);

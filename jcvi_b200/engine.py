@@ -167,6 +167,11 @@ class Engine(object):
     def release_text(self):
         self._check(self.lib.jx_text_release(self.ctx))
 
+    def set_record_reuse(self, on=True):
+        """liftover re-uses the records blastfilter tokenized from the same resident text (default);
+        off: every call tokenizes, like the reference's two passes over the raw table."""
+        self._check(self.lib.jx_set_record_reuse(self.ctx, int(bool(on))))
+
     # ---- stages ---------------------------------------------------------------------------------
     def blastfilter(self, text, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None, want_text=True,
                     want_mothers=False, raw=False, skip_arrays=False):

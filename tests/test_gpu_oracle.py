@@ -246,3 +246,34 @@ def test_batch_scan_on_hit_objects(mods):
         pts = [(h.qi, h.si, h.score) for h in hits if (h.qseqid, h.sseqid) == cp]
         want.extend(syn.synteny_scan(pts, 12, 12, 3))
     assert got == want and len(got) >= 4
+
+
+def test_record_reuse_switch_gives_identical_results():
+    """jx_set_record_reuse(0): liftover tokenizes the resident table again instead of re-using
+    blastfilter's records -- same lifted pairs either way."""
+    import torch
+    import bench
+    from jcvi_b200.engine import Engine
+    w = bench.make_workload(7, 300_000, genes=3000)
+    e = Engine(0)
+    try:
+        e.load_pair(w["qbed"], w["sbed"], False)
+        dev = e.upload(torch.from_numpy(w["text"]).pin_memory())
+        outs = []
+        for on in (True, False, True):
+            e.set_record_reuse(on)
+            r = e.blastfilter(dev, want_text=False, raw=True, skip_arrays=True)
+            s = e.scan_filtered(r)
+            e.free_filter(r)
+            blk = np.repeat(np.arange(s.n_blocks, dtype=np.int32), np.diff(s.block_start))
+            before = e.tokenizer_timing(reset=True)[1]
+            l = e.liftover_text(dev, s.q_rank, s.s_rank, blk, dist=10)
+            launches = e.tokenizer_timing(reset=True)[1]
+            assert (launches == 0) == on            # reuse on: no tokenizer launch inside liftover
+            outs.append((s.q_rank.copy(), l.q_rank.copy(), l.s_rank.copy(), l.block.copy(), l.accepted.copy(), l.raw_score.copy()))
+        assert outs[0][1].size > 0
+        for o in outs[1:]:
+            for a, b in zip(outs[0], o):
+                assert np.array_equal(a, b)
+    finally:
+        e.close()
