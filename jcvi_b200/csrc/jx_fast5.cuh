@@ -365,9 +365,10 @@ JX_HD void name_words6(const TW& wr, int a, int len, uint32_t* w) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
+  const int full = len >> 2;                                       // words entirely inside the name
+  const uint32_t last = (1u << (8 * (len & 3))) - 1u;              // mask of the partial word (0 when len % 4 == 0)
   for (int k = 0; k < JX_SLOT_WORDS; ++k) {
-    const int keep = len - 4 * k;                                  // bytes of this word inside the name
-    const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u);
+    const uint32_t m = k < full ? 0xFFFFFFFFu : (k == full ? last : 0u);
     w[k] = funnel_r(x[k], x[k + 1], sh) & m;
   }
 }

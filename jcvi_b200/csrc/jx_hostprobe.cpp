@@ -224,4 +224,14 @@ void probe_slot_hash_many(const char* blob, const unsigned* off, long n, unsigne
   for (long i = 0; i < n; ++i) out[i] = jx::slot_hash_bytes(rd, (int)off[i], (int)off[i + 1]);
 }
 
+// the kernel's route to the slot hash: six zero-padded words read from aligned text words (buffer must
+// have 32 readable bytes after the name); must equal probe_slot_hash_many's byte-wise definition
+unsigned probe_slot_hash6(const char* buf, int a, int len, unsigned* words6) {
+  WordRd wr{(const unsigned char*)buf};
+  uint32_t w[JX_SLOT_WORDS];
+  jx::name_words6(wr, a, len, w);
+  for (int k = 0; k < JX_SLOT_WORDS; ++k) words6[k] = w[k];
+  return jx::slot_hash6(w, len);
+}
+
 }  // extern "C"

@@ -298,3 +298,23 @@ def test_fast_line5_alignments_and_formats(probe):
             assert ends[k] - pad - gsp[2 * k] == b, (ln, k)
             assert hs[k] == probe.probe_hash(nm[:b].encode(), b), (ln, k)
     assert naccept > 0.6 * ntotal, (naccept, ntotal)
+
+
+def test_slot_hash_word_route_equals_byte_route(probe):
+    """Host table build hashes names byte-wise (slot_hash_bytes); the kernel hashes six zero-padded
+    words taken from aligned text words at any alignment (name_words6 + slot_hash6).  They must agree,
+    and the words must be the name's bytes followed by zeros."""
+    rng = np.random.default_rng(31)
+    alphabet = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789_.-|", dtype=np.uint8)
+    for it in range(4000):
+        L = int(rng.integers(1, 24))
+        pad = int(rng.integers(0, 9))
+        name = bytes(rng.choice(alphabet, L))
+        buf = b"\t" * pad + name + b"\t" + bytes(rng.choice(alphabet, 40))      # junk after the name must not leak in
+        words = (ctypes.c_uint * 6)()
+        h6 = probe.probe_slot_hash6(buf, pad, L, words)
+        off = np.array([0, L], dtype=np.uint32)
+        out = np.zeros(1, dtype=np.uint32)
+        probe.probe_slot_hash_many(name, off.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(1), out.ctypes.data_as(ctypes.c_void_p))
+        assert (h6 & 0xFFFFFFFF) == int(out[0]), (name, pad)
+        assert np.array(list(words), dtype="<u4").tobytes() == name + b"\0" * (24 - L), (name, pad)
