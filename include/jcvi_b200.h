@@ -222,6 +222,29 @@ int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_dev
                   int64_t* lines_len, int64_t* n_lines);
 void jx_free(void* p);
 
+/* ---- jcvi.formats.blast cscore (src/jcvi/formats/blast.py:1098-1189) ------------
+ * `cscore` has no BED: its dictionaries are keyed by whatever (gene_name-stripped) names the table
+ * holds.  jx_distinct_names returns one representative raw line per distinct name of the table
+ * (`\n`-terminated, first occurrence) and, per representative, which column the name is in
+ * (side[i]: 0 = query, 1 = subject).  The caller turns them into a name list, loads it as the name
+ * table of both sides (jx_bed_load, jx_pair_setup) and runs jx_cscore_begin / jx_cscore_finish with
+ * the cutoff; jx_session_counts then must report 0 unmapped lines -- anything else means two
+ * different names shared the 64-bit hash of this `seed` (retry with another seed) or a line with
+ * fewer than two fields (counts[2] of jx_distinct_names' stats).  stats: 0 non-'#' lines, 1 lines
+ * with two names, 2 lines with fewer than two fields, 3 '#' lines.  Buffers: jx_free. */
+int jx_distinct_names(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
+                      uint32_t seed, char** lines, int64_t* lines_len, uint8_t** side, int64_t* n_names,
+                      int64_t stats[4]);
+/* float32 best score per name id of the open jx_cscore_begin session (first n entries) */
+int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
+/* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */
+int jx_session_counts(jx_ctx* ctx, int64_t out[3]);
+/* HOST helper for the few lines that survive a filter: BlastLine(line) and str(BlastLine) with the
+ * very glibc calls cblast.pyx makes (sscanf format cblast.pyx:15, start<=stop swap 114-120, sprintf
+ * format cblast.pyx:17).  query128 / subject128: char[128]; returns the number of converted fields. */
+int jx_host_blastline(const char* line, char* query128, char* subject128, float* pctid, float* score,
+                      char* str_out, int str_cap);
+
 #ifdef __cplusplus
 }
 #endif

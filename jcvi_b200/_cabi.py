@@ -60,7 +60,8 @@ EXPORTS = [
     "jx_ctx_create", "jx_ctx_destroy", "jx_last_error", "jx_version", "jx_launch_count", "jx_stream_handle",
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
-    "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse",
+    "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse", "jx_distinct_names", "jx_best_table_copy", "jx_session_counts",
+    "jx_host_blastline",
     "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_free", "jx_abi_sizes",
 ]
 
@@ -110,6 +111,14 @@ def lib():
         L.jx_text_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64)]
         L.jx_text_release.argtypes = [ctypes.c_void_p]
         L.jx_set_record_reuse.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.jx_distinct_names.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                        ctypes.POINTER(ctypes.c_int64)]
+        L.jx_best_table_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+        L.jx_session_counts.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+        L.jx_host_blastline.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float),
+                                        ctypes.POINTER(ctypes.c_float), ctypes.c_char_p, ctypes.c_int]
         L.jx_cscore_begin.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
         L.jx_cscore_finish.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p), c_i64p, c_i64p]

@@ -381,6 +381,35 @@ JX_HD uint32_t slot_hash6(const uint32_t* w, int len) {
   return slot_hash_finish(h, (uint32_t)len);
 }
 
+// ---- 64-bit name hash for tables without a BED (formats.blast cscore: the set of names is whatever
+// the table holds).  Two 32-bit chains over the same zero-padded words as the slot hash; `seed` lets
+// the caller retry in the (2^-64 per pair) event that two different names collide.  Never 0.
+JX_HD uint32_t name64_step2(uint32_t h, uint32_t w) { return rotl32(h + w, 7) * 0xC2B2AE35u; }
+JX_HD uint64_t name64_finish(uint32_t h1, uint32_t h2, uint32_t len) {
+  const uint32_t a = fmix32(h1 ^ (len * 0x85EBCA77u)), b = fmix32(h2 ^ (a + len));
+  const uint64_t h = ((uint64_t)a << 32) | b;
+  return (h == 0ull || h == ~0ull) ? 1ull : h;          // 0 = no name, ~0 = sort sentinel
+}
+JX_HD uint64_t name64_words6(const uint32_t* w, int len, uint32_t seed) {
+  uint32_t h1 = slot_hash_init() ^ seed, h2 = 0x9747B28Cu + seed * 0x85EBCA6Bu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < JX_SLOT_WORDS; ++k) { h1 = slot_hash_step(h1, w[k]); h2 = name64_step2(h2, w[k]); }
+  return name64_finish(h1, h2, (uint32_t)len);
+}
+template <class R>
+JX_HD uint64_t name64_bytes(R& rd, int a, int b, uint32_t seed) {   // generic (byte reader) form, any length
+  uint32_t h1 = slot_hash_init() ^ seed, h2 = 0x9747B28Cu + seed * 0x85EBCA6Bu;
+  const int nw = (b - a + 3) >> 2;
+  for (int k = 0; k < (nw > JX_SLOT_WORDS ? nw : JX_SLOT_WORDS); ++k) {
+    uint32_t w = 0;
+    for (int j = 0; j < 4; ++j) { const int p = a + 4 * k + j; if (p < b) w |= rd(p) << (8 * j); }
+    h1 = slot_hash_step(h1, w); h2 = name64_step2(h2, w);
+  }
+  return name64_finish(h1, h2, (uint32_t)(b - a));
+}
+
 // word hash of [a, b) streaming aligned words (one load + one funnel shift per 4 bytes)
 template <class TW>
 JX_HD uint64_t fast_hash5(const TW& wr, int a, int b) {

@@ -197,9 +197,12 @@ struct TokMode {
   int64_t n_excl = 0;
   bool fill_cache = false;     // keep records/descriptors in ctx->cache (held text only)
   bool persist = false;        // like fill_cache but also for self comparisons / exclusions (sharded session)
+  bool names = false;          // no BED: emit a 64-bit hash of both (stripped) names per line instead of ranks
+  uint32_t seed = 0;           // of that hash
 };
 struct TokOut {
   uint4* recs = nullptr;       // [n_lines]
+  uint4* hashes = nullptr;     // [n_lines] names mode: {hq.lo, hq.hi, hs.lo, hs.hi}, 0 = no name
   uint64_t* desc = nullptr;    // per tile: (2 << 62) | inclusive line count
   int64_t ntiles = 0;
   const uint8_t* d_text = nullptr;

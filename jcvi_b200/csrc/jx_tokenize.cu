@@ -31,6 +31,8 @@ struct TokArgs {
   uint32_t tile_begin, tile_end;   // tiles of this launch
   uint4* recs;
   uint32_t rec_cap;
+  uint4* hashes;             // names mode only
+  uint32_t seed;
   const uint4* qtab; const uint16_t* qdisp; uint32_t qbshift, qcshift; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
   const uint4* stab; const uint16_t* sdisp; uint32_t sbshift, scshift; const uint32_t* smeta; const uint32_t* sblob;
   const uint32_t* qovh; const uint32_t* qovr; uint32_t qnov;   // overflow lists (equal 32-bit hashes), usually empty
@@ -151,6 +153,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // in flight (one bulk copy issued by one thread into the other half of a double buffer) while it
 // works on the current one, so the HBM latency of staging is off the critical path and costs no
 // load/store instructions.
+// NAMES = false: ranks through the BED name tables (the path's kernel).  NAMES = true: no table, the
+// record keeps only the line position and `hashes` receives a 64-bit hash of both names
+// (jx_distinct_names, formats.blast cscore); a separate instantiation, so the main one is unchanged.
+template <bool NAMES>
 __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(const TokArgs a) {
   constexpr int NGRP = JX_TOK_THREADS / JX_GROUP;          // independent tile groups per CTA
   constexpr int GWARPS = JX_GROUP / 32;
@@ -367,6 +373,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   const SideTab TS{a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob, a.sovh, a.sovr, a.snov};
   uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
   bool have_held = false;
+  uint4 hheld = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_GROUP) {
     const uint32_t k = k0 + tid;
     if (k >= nlines) break;
@@ -389,12 +396,44 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
       else { e = JX_WIN; while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e; }
     }
     uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+    uint4 hrec = make_uint4(0u, 0u, 0u, 0u);
     if (s < e && sm[s] == '#') {
       ++c_comment;
     } else if (s < e) {
       jx::LineTok t;
       const bool fast = (e + 8 <= JX_WIN) && jx::fast_line5(B, mwr, mnr, s, e, t);
       if (!fast) jx::tokenize_line(rd, s, e, t);
+      if (NAMES) {
+        if (t.nconv >= 2 && !t.longname && !t.hard) {
+          int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
+          uint64_t hq, hs;
+          if (fast) {
+            if (a.strip) {
+              int qbar = -1, sbar = -1;
+              if (has_bar) { qbar = jx::find_bar(B, qa, qb); sbar = jx::find_bar(B, sa, sb); }
+              qb = jx::strip5(B, qa, qb, qbar);
+              sb = jx::strip5(B, sa, sb, sbar);
+            }
+          } else if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
+          const int lq = qb - qa, lsn = sb - sa;
+          if (fast && lq > 0 && lsn > 0 && lq < 4 * JX_SLOT_WORDS && lsn < 4 * JX_SLOT_WORDS) {
+            uint32_t wq[JX_SLOT_WORDS], ws[JX_SLOT_WORDS];
+            jx::name_words6(wr, qa, lq, wq);
+            jx::name_words6(wr, sa, lsn, ws);
+            hq = jx::name64_words6(wq, lq, a.seed);
+            hs = jx::name64_words6(ws, lsn, a.seed);
+          } else {
+            hq = lq > 0 ? jx::name64_bytes(rd, qa, qb, a.seed) : 0ull;
+            hs = lsn > 0 ? jx::name64_bytes(rd, sa, sb, a.seed) : 0ull;
+          }
+          hrec = make_uint4((uint32_t)hq, (uint32_t)(hq >> 32), (uint32_t)hs, (uint32_t)(hs >> 32));
+          ++c_mapped;
+        } else {
+          if (t.longname) { ++c_long; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+          else if (t.hard) { ++c_hard; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+          else ++c_unmapped;            // fewer than two fields
+        }
+      } else {
       bool bad = false, selfhit = false;
       int qi = -1, si = -1;
       uint32_t nidq = 0, nids = 0;
@@ -489,13 +528,17 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
           }
         }
       }
+      }  // !NAMES
     } else {
-      ++c_unmapped;   // empty line: a BlastLine with empty names, never in the BED
+      // an empty segment between the '\r' and the '\n' of a CR LF pair is not a line (universal newlines);
+      // a real blank line is a BlastLine with empty names, never in the BED
+      const uint32_t prev = s > 0 ? sm[s - 1] : (base > 0 ? a.text[base - 1] : 0u);
+      if (!(prev == '\r' && sm[s] == '\n')) ++c_unmapped;
     }
-    if (defer) { held = rec; have_held = true; }
+    if (defer) { held = rec; have_held = true; if (NAMES) hheld = hrec; }
     else {
       const unsigned long long ord = s_base + k;
-      if (ord < a.rec_cap) a.recs[ord] = rec;
+      if (ord < a.rec_cap) { a.recs[ord] = rec; if (NAMES) a.hashes[ord] = hrec; }
     }
   }
   if (defer) {
@@ -503,7 +546,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     if (warp == 0) look_back();
     gsync();
     const unsigned long long ord = s_base + tid;
-    if (have_held && ord < a.rec_cap) a.recs[ord] = held;
+    if (have_held && ord < a.rec_cap) { a.recs[ord] = held; if (NAMES) a.hashes[ord] = hheld; }
   }
   if (tid == 0) {
     c_lines += nlines;
@@ -537,7 +580,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
 
 int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
                      const TokMode& mode, TokOut& out) {
-  if (!ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
+  if (!mode.names && !ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
   if (nbytes < 0 || (nbytes && !text)) return JX_EARG;
   const int64_t ntiles = (nbytes + JX_TILE - 1) / JX_TILE;
   out.ntiles = ntiles;
@@ -614,6 +657,9 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       recs = rr;
     }
     out.recs = recs;
+    uint4* hashes = nullptr;
+    if (mode.names) { JX_ALLOC(hh, uint4, (size_t)cap64, false); hashes = hh; }
+    out.hashes = hashes;
     if (attempt) {
       JX_CK(cudaMemsetAsync(d_stats, 0, 12 * sizeof(unsigned long long), ctx->stream));
       JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t) * ((size_t)nchunks + 2), ctx->stream));
@@ -627,6 +673,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     JX_TRACE("tok: allocs");
     TokArgs a;
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.tile_begin = 0; a.tile_end = 0; a.recs = recs; a.rec_cap = (uint32_t)cap64;
+    a.hashes = hashes; a.seed = mode.seed;
     a.qtab = Q.table; a.qdisp = Q.disp; a.qbshift = Q.bshift; a.qcshift = Q.cshift; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
     a.stab = S.table; a.sdisp = S.disp; a.sbshift = S.bshift; a.scshift = S.cshift; a.smeta = S.name_meta; a.sblob = S.blobw;
     a.qovh = Q.ovf_hash; a.qovr = Q.ovf_rank; a.qnov = Q.n_ovf; a.sovh = S.ovf_hash; a.sovr = S.ovf_rank; a.snov = S.n_ovf;
@@ -638,7 +685,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     // persistent CTAs: as many as are resident at once
     if (!ctx->tok_resident) {
       int per_sm = 0, n_sm = 0;
-      JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize, JX_TOK_THREADS, 0));
+      JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<false>, JX_TOK_THREADS, 0));
       JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->tok_resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
     }
@@ -664,7 +711,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       JX_CK(cudaEventCreate(&e1));
       JX_CK(cudaEventRecord(e0, ctx->stream));
       a.ticket = d_ticket + c; a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
-      JX_LAUNCH(k_tokenize, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      if (mode.names) JX_LAUNCH(k_tokenize<true>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else JX_LAUNCH(k_tokenize<false>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
     }

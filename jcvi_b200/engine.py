@@ -154,6 +154,64 @@ class Engine(object):
         self._beds = (qbed, sbed)          # keep alive: the cache key uses id()
         self.Gq, self.Gs = tq["G"], ts["G"]
 
+    def load_names(self, names):
+        """No BED (formats.blast cscore): `names` (sorted, distinct byte strings) become the name table
+        of BOTH sides; rank == name id == position in the list."""
+        G = len(names)
+        blob = np.frombuffer(b"".join(names) or b"\0", dtype=np.uint8)
+        off = np.zeros(G + 1, dtype=np.uint32)
+        np.cumsum([len(x) for x in names], out=off[1:])
+        ones = np.ones(max(G, 1), dtype=np.uint8)
+        zeros = np.zeros(max(G, 1), dtype=np.int32)
+        ends = np.full(max(G, 1), G, dtype=np.int32)
+        ids = np.arange(max(G, 1), dtype=np.uint32)
+        b = C.JxBed()
+        b.n_genes = G
+        keep = [blob, off, ones, zeros, ends, ids]
+        (b.names, b.name_off, b.indexable, b.chr_lex, b.chr_begin, b.chr_end, b.length, b.accn_lexrank, b.name_id) = [
+            C.ptr(a) for a in (blob, off, ones, zeros, zeros, ends, zeros, ids, ids)]
+        b.n_chr = 1
+        for side in (0, 1):
+            self._check(self.lib.jx_bed_load(self.ctx, side, ctypes.byref(b)))
+        same = np.full(max(G, 1), -1, dtype=np.int32)          # no `query == subject` rule in cscore
+        self._check(self.lib.jx_pair_setup(self.ctx, 0, C.ptr(same), G))
+        self._pair = None
+        self._beds = None
+        self.Gq = self.Gs = G
+        del keep
+
+    def distinct_names(self, text, strip_names=True, seed=0):
+        """-> (list of representative raw lines (bytes, no terminator), uint8 side per line, stats dict)"""
+        p, n, dev, keep = _text_ptr(text)
+        buf = ctypes.c_void_p(); ln = ctypes.c_int64(); side = ctypes.c_void_p(); cnt = ctypes.c_int64()
+        st = (ctypes.c_int64 * 4)()
+        self._check(self.lib.jx_distinct_names(self.ctx, p, n, dev, int(bool(strip_names)), int(seed), ctypes.byref(buf),
+                                               ctypes.byref(ln), ctypes.byref(side), ctypes.byref(cnt), st))
+        try:
+            raw = ctypes.string_at(buf, ln.value) if ln.value else b""
+            sides = np.frombuffer(ctypes.string_at(side, cnt.value), dtype=np.uint8) if cnt.value else np.zeros(0, np.uint8)
+        finally:
+            self.lib.jx_free(buf); self.lib.jx_free(side)
+        lines = raw.split(b"\n")[:cnt.value]
+        return lines, sides, dict(zip(("lines", "named", "short", "comments"), list(st)))
+
+    def best_table(self, n):
+        out = np.zeros(max(int(n), 1), dtype=np.float32)
+        self._check(self.lib.jx_best_table_copy(self.ctx, C.ptr(out), int(n)))
+        return out[:n]
+
+    def session_counts(self):
+        st = (ctypes.c_int64 * 3)()
+        self._check(self.lib.jx_session_counts(self.ctx, st))
+        return dict(zip(("lines", "mapped", "unmapped"), list(st)))
+
+    def host_blastline(self, line):
+        """BlastLine(line) the way cblast does it (glibc): -> (nconv, query, subject, pctid, score, str(b))"""
+        q = ctypes.create_string_buffer(128); s = ctypes.create_string_buffer(128); out = ctypes.create_string_buffer(1024)
+        pct = ctypes.c_float(); sc = ctypes.c_float()
+        n = self.lib.jx_host_blastline(line, q, s, ctypes.byref(pct), ctypes.byref(sc), out, 1024)
+        return n, q.value, s.value, pct.value, sc.value, out.value
+
     def upload(self, text):
         """Start the asynchronous upload of a host text; the returned DeviceText can be handed to
         blastfilter / scan_text / liftover_text, which overlap tokenizing with the copy."""

@@ -8,6 +8,7 @@ from .oracle import (  # noqa: F401
     blastfilter,
     scan,
     liftover,
+    cscore,
     kdtree,
     gene_name,
     natcmp,

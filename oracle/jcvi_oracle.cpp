@@ -955,4 +955,61 @@ int orc_blastline_str(const char* line, char* out, int cap) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// formats.blast cscore  (src/jcvi/formats/blast.py:1098-1189): two passes over the table with
+// dictionaries keyed by the (gene_name-stripped) names themselves; no BED.
+//   pass 1 (1146-1157): best_score[name] = max score over every line naming it (starting at 0.0)
+//   pass 2 (1159-1172): s = score / max(best[q], best[s]); keep s > cutoff; per (q, s) the largest s,
+//                       the first line on ties
+//   output (1174-1186): sorted by (query, subject); "{:.2f}" of s, optionally "{:.1f}" of pctid;
+//                       --writeblast prints str(BlastLine) of the chosen line
+// returns 0, -1 on I/O error, -2 on an unparsable line (128+ byte name), -3 ZeroDivisionError
+// ---------------------------------------------------------------------------------
+int orc_cscore(const char* blast_file, const char* out_path, const char* blast_out_path, double cutoff, int pct,
+               int strip_names) {
+  std::vector<BlastLine> lines;
+  if (!load_blast(blast_file, lines)) return g_err.empty() ? -1 : -2;
+  auto nm = [&](const char* raw) { return strip_names ? gene_name(raw) : std::string(raw); };
+  std::map<std::string, double> best;
+  for (const BlastLine& b : lines) {
+    const std::string q = nm(b.query), s = nm(b.subject);
+    const double score = (double)b.score;
+    double& bq = best[q];                 // defaultdict(float): the lookup creates the key
+    if (score > bq) bq = score;
+    double& bs = best[s];
+    if (score > bs) bs = score;
+  }
+  struct Pick { double s; float pctid; const BlastLine* b; };
+  std::map<std::pair<std::string, std::string>, Pick> pairs;   // std::map iterates in sorted(tuple) order
+  for (const BlastLine& b : lines) {
+    const std::string q = nm(b.query), s = nm(b.subject);
+    const double den = std::max(best[q], best[s]);
+    if (den == 0.0) { g_err = "float division by zero"; return -3; }
+    const double c = (double)b.score / den;
+    if (c > cutoff) {
+      auto key = std::make_pair(q, s);
+      auto it = pairs.find(key);
+      if (it == pairs.end() || c > it->second.s) pairs[key] = Pick{c, b.pctid, &b};
+    }
+  }
+  FILE* fw = fopen(out_path, "w");
+  if (!fw) return -1;
+  FILE* fwb = blast_out_path && *blast_out_path ? fopen(blast_out_path, "w") : nullptr;
+  char buf[1024];
+  for (const auto& kv : pairs) {
+    fprintf(fw, "%s\t%s\t%.2f", kv.first.first.c_str(), kv.first.second.c_str(), kv.second.s);
+    if (pct) fprintf(fw, "\t%.1f", (double)kv.second.pctid);
+    fputc('\n', fw);
+    if (fwb) {
+      const BlastLine& bl = *kv.second.b;
+      snprintf(buf, sizeof buf, kBlastOutput, bl.query, bl.subject, bl.pctid, bl.hitlen, bl.nmismatch, bl.ngaps, bl.qstart,
+               bl.qstop, bl.sstart, bl.sstop, bl.evalue, bl.score);
+      fprintf(fwb, "%s\n", buf);
+    }
+  }
+  fclose(fw);
+  if (fwb) fclose(fwb);
+  return 0;
+}
+
 }  // extern "C"

@@ -85,6 +85,16 @@ def liftover(blast_file, anchor_file, qbed, sbed, out_path=None, strip_names=Tru
     return out
 
 
+def cscore(blast_file, out_path, cutoff=0.9999, pct=False, writeblast=False, strip_names=True):
+    """formats/blast.py:1098-1189 (`jcvi.formats.blast cscore`).  Writes out_path and, with writeblast,
+    out_path + ".filtered.blast".  ZeroDivisionError like the reference when a line's names never scored."""
+    rc = _lib().orc_cscore(_b(blast_file), _b(out_path), _b(out_path + ".filtered.blast") if writeblast else _b(None),
+                           ctypes.c_double(cutoff), int(bool(pct)), int(bool(strip_names)))
+    if rc == -3:
+        raise ZeroDivisionError("float division by zero")
+    _check(rc)
+
+
 def kdtree(anchors, queries, bound):
     """Restated cKDTree(anchors, leafsize=16).query(queries, p=1, distance_upper_bound=bound)."""
     a = np.ascontiguousarray(anchors, dtype=np.int64).reshape(-1, 2)
