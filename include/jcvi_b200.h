@@ -235,6 +235,14 @@ void jx_free(void* p);
 int jx_distinct_names(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
                       uint32_t seed, char** lines, int64_t* lines_len, uint8_t** side, int64_t* n_names,
                       int64_t stats[4]);
+/* The whole of `cscore` in one call: the cscore output file as text (`query\tsubject\t{:.2f}[\t{:.1f}]\n`,
+ * sorted by (query, subject)) and, with want_blast, the `--writeblast` file (str(BlastLine) per pair).
+ * JX_EUNSUPPORTED when a line has fewer than two fields (the reference raises ZeroDivisionError or keys
+ * its dictionaries with ""), JX_EZERODIV like the reference when a line's names never scored.  Replaces
+ * the name tables loaded with jx_bed_load.  stats as jx_distinct_names.  Buffers: jx_free. */
+int jx_blast_cscore(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
+                    double cutoff, int want_pct, int want_blast, char** out, int64_t* out_len,
+                    char** blast_out, int64_t* blast_len, int64_t stats[4]);
 /* float32 best score per name id of the open jx_cscore_begin session (first n entries) */
 int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
 /* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */

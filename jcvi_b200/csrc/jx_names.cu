@@ -5,7 +5,11 @@
 // table of both sides (jx_bed_load) and the rest of `cscore` is the existing C-score machinery
 // (jx_cscore_begin / jx_cscore_finish).  Also here: the host-side BlastLine helpers the Python
 // layer uses on the few surviving lines (the same glibc sscanf / sprintf calls cblast.pyx makes).
+#include <algorithm>
 #include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
 #include "jx_internal.cuh"
 
 namespace {
@@ -133,6 +137,141 @@ int jx_host_blastline(const char* line, char* query128, char* subject128, float*
     snprintf(str_out, (size_t)str_cap, "%s\t%s\t%.2f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.2g\t%.3g", q, s, (double)pct, hitlen,
              nmismatch, ngaps, qstart, qstop, sstart, sstop, evalue, (double)sc);
   return nconv;
+}
+
+// ---- the whole of `jcvi.formats.blast cscore` (src/jcvi/formats/blast.py:1098-1189) in one call -------
+// GPU: both passes over the table (distinct names; per-name best score + float64 ratio predicate).
+// Host, O(distinct names) + O(surviving lines): the name list, the reference's `pairs` dictionary
+// (largest C-score per (query, subject), first line on ties), sorted(), the "{:.2f}" / "{:.1f}" writer
+// and str(BlastLine) -- with the same glibc calls cblast makes.
+namespace {
+struct PtrBytes { const unsigned char* p; inline uint32_t operator()(int i) const { return p[i]; } };
+inline bool c_isspace(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+// gene_name (cbook.py:308-329) through the tokenizer's own strip_isoform
+inline std::string host_gene_name(const char* s, size_t n) {
+  PtrBytes rd{(const unsigned char*)s};
+  int b = (int)n;
+  jx::strip_isoform(rd, 0, b);
+  return std::string(s, (size_t)b);
+}
+}  // namespace
+
+int jx_blast_cscore(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, double cutoff,
+                    int want_pct, int want_blast, char** out, int64_t* out_len, char** blast_out, int64_t* blast_len,
+                    int64_t stats[4]) {
+  if (!ctx || !out || !out_len) return JX_EARG;
+  *out = nullptr; *out_len = 0;
+  if (blast_out) *blast_out = nullptr;
+  if (blast_len) *blast_len = 0;
+  cudaSetDevice(ctx->device);
+  int rc;
+  uint64_t dptr = 0;
+  if (!text_on_device) {
+    if ((rc = jx_text_upload(ctx, text, nbytes, &dptr))) return rc;
+  } else dptr = (uint64_t)(uintptr_t)text;
+  const char* dtext = (const char*)(uintptr_t)dptr;
+
+  std::vector<std::string> names;
+  bool separated = false;
+  for (uint32_t seed = 0; seed < 4 && !separated; ++seed) {
+    char* lines = nullptr; int64_t lines_len = 0; uint8_t* side = nullptr; int64_t n = 0; int64_t st[4] = {0, 0, 0, 0};
+    if ((rc = jx_distinct_names(ctx, dtext, nbytes, 1, strip_names, seed, &lines, &lines_len, &side, &n, st))) return rc;
+    if (stats) memcpy(stats, st, sizeof st);
+    if (st[2]) {
+      free(lines); free(side);
+      ctx->err = std::to_string(st[2]) + " line(s) with fewer than two fields (a BlastLine with an empty name: the "
+                 "reference divides by best_score[\"\"] == 0.0)";
+      return JX_EUNSUPPORTED;
+    }
+    names.clear();
+    names.reserve((size_t)n);
+    const char* p = lines; const char* end = lines + lines_len;
+    for (int64_t i = 0; i < n && p < end; ++i) {
+      const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+      if (!eol) eol = end;
+      const char* q = p;
+      for (int col = 0;; ++col) {                       // sscanf("%s %s"): whitespace-delimited tokens
+        while (q < eol && c_isspace((unsigned char)*q)) ++q;
+        const char* t0 = q;
+        while (q < eol && !c_isspace((unsigned char)*q)) ++q;
+        if (col == (int)side[i]) { names.push_back(strip_names ? host_gene_name(t0, (size_t)(q - t0)) : std::string(t0, q)); break; }
+      }
+      p = eol + 1;
+    }
+    free(lines); free(side);
+    std::sort(names.begin(), names.end());
+    names.erase(std::unique(names.begin(), names.end()), names.end());
+    // the names become the name table of both sides: rank == name id == position in sorted order
+    const size_t G = names.size();
+    std::string blob; std::vector<uint32_t> off(G + 1, 0);
+    for (size_t i = 0; i < G; ++i) { blob += names[i]; off[i + 1] = (uint32_t)blob.size(); }
+    std::vector<uint8_t> ones(G + 1, 1);
+    std::vector<int32_t> zeros(G + 1, 0), ends(G + 1, (int32_t)G), same(G + 1, -1);
+    std::vector<uint32_t> ids(G + 1);
+    for (size_t i = 0; i <= G; ++i) ids[i] = (uint32_t)i;
+    jx_bed b;
+    b.n_genes = (int64_t)G; b.names = blob.data(); b.name_off = off.data(); b.indexable = ones.data();
+    b.chr_lex = zeros.data(); b.chr_begin = zeros.data(); b.chr_end = ends.data(); b.length = zeros.data();
+    b.accn_lexrank = ids.data(); b.name_id = ids.data(); b.n_chr = 1;
+    if ((rc = jx_bed_load(ctx, 0, &b)) || (rc = jx_bed_load(ctx, 1, &b))) return rc;
+    if ((rc = jx_pair_setup(ctx, 0, same.data(), (uint32_t)G))) return rc;
+    uint64_t best_ptr = 0; uint32_t n_ids = 0;
+    if ((rc = jx_cscore_begin(ctx, dtext, nbytes, 1, strip_names, nullptr, 0, &best_ptr, &n_ids))) return rc;
+    int64_t cnt[3];
+    if ((rc = jx_session_counts(ctx, cnt))) return rc;
+    separated = cnt[2] == 0;        // an unmapped line = a name that lost its table entry to a 64-bit hash collision
+  }
+  if (!separated) { ctx->err = "could not separate the names of the table"; return JX_EINTERNAL; }
+  const size_t G = names.size();
+  std::vector<float> best(G + 1, 0.f);
+  if (G && (rc = jx_best_table_copy(ctx, best.data(), (uint32_t)G))) return rc;
+  char* kept = nullptr; int64_t kept_len = 0, n_kept = 0;
+  if ((rc = jx_cscore_finish(ctx, cutoff, &kept, &kept_len, &n_kept))) return rc;
+
+  struct Pick { double s; float pctid; std::string str; };
+  std::map<std::pair<std::string, std::string>, Pick> pairs;      // iterates like sorted(pairs.items())
+  {
+    const char* p = kept; const char* end = kept + kept_len;
+    std::string row;
+    char q128[128], s128[128], sbuf[1024];
+    for (int64_t i = 0; i < n_kept && p < end; ++i) {
+      const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+      if (!eol) eol = end;
+      row.assign(p, eol);
+      float pct = 0.f, sc = 0.f;
+      jx_host_blastline(row.c_str(), q128, s128, &pct, &sc, want_blast ? sbuf : nullptr, (int)sizeof sbuf);
+      std::string qn = strip_names ? host_gene_name(q128, strlen(q128)) : std::string(q128);
+      std::string sn = strip_names ? host_gene_name(s128, strlen(s128)) : std::string(s128);
+      const auto iq = std::lower_bound(names.begin(), names.end(), qn), is = std::lower_bound(names.begin(), names.end(), sn);
+      if (iq == names.end() || *iq != qn || is == names.end() || *is != sn) { free(kept); ctx->err = "name table lost a name"; return JX_EINTERNAL; }
+      const double den = std::max((double)best[(size_t)(iq - names.begin())], (double)best[(size_t)(is - names.begin())]);
+      const double c = (double)sc / den;                 // den > 0: the device predicate already divided by it
+      if (c > cutoff) {
+        auto key = std::make_pair(std::move(qn), std::move(sn));
+        auto it = pairs.find(key);
+        if (it == pairs.end()) pairs.emplace(std::move(key), Pick{c, pct, want_blast ? std::string(sbuf) : std::string()});
+        else if (c > it->second.s) it->second = Pick{c, pct, want_blast ? std::string(sbuf) : std::string()};
+      }
+      p = eol + 1;
+    }
+  }
+  free(kept);
+  std::string o, ob;
+  char num[64];
+  for (const auto& kv : pairs) {
+    o += kv.first.first; o += '\t'; o += kv.first.second;
+    snprintf(num, sizeof num, "\t%.2f", kv.second.s); o += num;
+    if (want_pct) { snprintf(num, sizeof num, "\t%.1f", (double)kv.second.pctid); o += num; }
+    o += '\n';
+    if (want_blast) { ob += kv.second.str; ob += '\n'; }
+  }
+  *out = (char*)malloc(o.size() + 1); memcpy(*out, o.data(), o.size()); (*out)[o.size()] = 0; *out_len = (int64_t)o.size();
+  if (want_blast && blast_out && blast_len) {
+    *blast_out = (char*)malloc(ob.size() + 1); memcpy(*blast_out, ob.data(), ob.size()); (*blast_out)[ob.size()] = 0;
+    *blast_len = (int64_t)ob.size();
+  }
+  if (!text_on_device) jx_text_release(ctx);
+  return JX_OK;
 }
 
 }  // extern "C"

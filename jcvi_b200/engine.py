@@ -195,6 +195,24 @@ class Engine(object):
         lines = raw.split(b"\n")[:cnt.value]
         return lines, sides, dict(zip(("lines", "named", "short", "comments"), list(st)))
 
+    def blast_cscore(self, text, cutoff=0.9999, strip_names=True, pct=False, writeblast=False):
+        """`jcvi.formats.blast cscore` in one call -> (cscore file bytes, --writeblast file bytes or None, stats)."""
+        p, n, dev, keep = _text_ptr(text)
+        out = ctypes.c_void_p(); ln = ctypes.c_int64(); bout = ctypes.c_void_p(); bln = ctypes.c_int64()
+        st = (ctypes.c_int64 * 4)()
+        rc = self.lib.jx_blast_cscore(self.ctx, p, n, dev, int(bool(strip_names)), float(cutoff), int(bool(pct)),
+                                      int(bool(writeblast)), ctypes.byref(out), ctypes.byref(ln), ctypes.byref(bout),
+                                      ctypes.byref(bln), st)
+        self._pair = None                      # the name tables now hold the table's own names
+        self._beds = None
+        try:
+            self._check(rc)
+            a = ctypes.string_at(out, ln.value) if ln.value else b""
+            b = (ctypes.string_at(bout, bln.value) if bln.value else b"") if writeblast else None
+        finally:
+            self.lib.jx_free(out); self.lib.jx_free(bout)
+        return a, b, dict(zip(("lines", "named", "short", "comments"), list(st)))
+
     def best_table(self, n):
         out = np.zeros(max(int(n), 1), dtype=np.float32)
         self._check(self.lib.jx_best_table_copy(self.ctx, C.ptr(out), int(n)))

@@ -1,11 +1,12 @@
 """Drop-in for `jcvi.formats.blast cscore` (src/jcvi/formats/blast.py:1098-1189), the reciprocal-best-hit
 C-score filter that runs on a raw BLAST/LAST table without BED files.
 
-The two passes over the table run on the GPU: `jx_distinct_names` finds one representative line per
-distinct name, the names become the name table of both sides, and `jx_cscore_begin` /
-`jx_cscore_finish` are the path's own tokenizer + per-name best score + float64 ratio predicate.
-What is left for the host is O(surviving lines): the `pairs` dictionary, `sorted()` and the `{:.2f}`
-writer of the reference, on values parsed with the same glibc calls cblast makes."""
+`cscore()` is one C-ABI call (`jx_blast_cscore`): the two passes over the table run on the GPU
+(`jx_distinct_names` finds one representative line per distinct name, the names become the name table of
+both sides, `jx_cscore_begin` / `jx_cscore_finish` are the path's own tokenizer + per-name best score +
+float64 ratio predicate); the library's host side does what is O(distinct names) + O(surviving lines):
+the `pairs` dictionary, `sorted()` and the `{:.2f}` writer, on values parsed with the same glibc calls
+cblast makes.  `cscore_pairs()` is the same thing step by step in Python, for library use."""
 import sys
 
 import numpy as np
@@ -60,23 +61,18 @@ def cscore(args):
     if len(args) != 1:
         sys.exit(not p.print_help())
     (blastfile,) = args
-    pairs = cscore_pairs(read_text_file(blastfile), opts.cutoff, opts.strip_names)
-
+    logger.debug("Register best scores ..")
+    out, blast_out, _ = get_engine().blast_cscore(read_text_file(blastfile), cutoff=opts.cutoff, strip_names=opts.strip_names,
+                                                  pct=opts.pct, writeblast=opts.writeblast)
     fw, close_fw = _open_out(opts.outfile)
-    fwb = open(opts.outfile + ".filtered.blast", "w") if opts.writeblast else None
-    for (query, subject), (s, pctid, line) in sorted(pairs.items()):
-        cols = [query.decode(), subject.decode(), "{0:.2f}".format(s)]
-        if opts.pct:
-            cols.append("{0:.1f}".format(pctid))
-        print("\t".join(cols), file=fw)
-        if fwb is not None:
-            print(line.decode(), file=fwb)
+    fw.write(out.decode())
     if close_fw:
         fw.close()
     else:
         fw.flush()
-    if fwb is not None:
-        fwb.close()
+    if opts.writeblast:
+        with open(opts.outfile + ".filtered.blast", "w") as fwb:
+            fwb.write(blast_out.decode())
 
 
 def cscore_pairs(text, cutoff, strip_names=True, engine=None):

@@ -76,3 +76,17 @@ def test_gpu_cscore_matches_oracle_on_a_larger_table(tmp_path):
         assert len(read(last + "." + tag + ".gpu")) > 1000
         if kw["writeblast"]:
             assert read(last + "." + tag + ".gpu.filtered.blast") == read(last + "." + tag + ".orc.filtered.blast")
+
+
+@pytest.mark.gpu
+def test_gpu_cscore_pairs_python_route_equals_one_call(golden):
+    """`cscore_pairs` (the same steps from Python, for library use) and `jx_blast_cscore` agree."""
+    from jcvi_b200.formats import blast as gblast
+    from jcvi_b200.apps_base import read_text_file
+    d, cases = golden("cscore")
+    c = [x for x in cases if x["argv"] and "--writeblast" in x["argv"]][0]
+    inp = os.path.join(d, c["input"])
+    pairs = gblast.cscore_pairs(read_text_file(inp), 0.7, True)
+    lines = ["%s\t%s\t%.2f\t%.1f" % (q.decode(), s.decode(), v[0], v[1]) for (q, s), v in sorted(pairs.items())]
+    assert ("\n".join(lines) + "\n").encode() == read(os.path.join(d, c["out"]))
+    assert ("\n".join(v[2].decode() for _, v in sorted(pairs.items())) + "\n").encode() == read(os.path.join(d, c["blast_out"]))
