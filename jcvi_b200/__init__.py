@@ -23,6 +23,12 @@ def install():
     jbf.blastfilter_main = bf.blastfilter_main
     for name in ("scan", "liftover", "batch_scan", "synteny_scan", "synteny_liftover"):
         setattr(jsyn, name, getattr(syn, name))
+    try:                                   # formats.blast cscore
+        from .formats import blast as gblast
+        jblast = importlib.import_module("jcvi.formats.blast")
+        jblast.cscore = gblast.cscore
+    except ImportError:
+        pass
     try:
         jcat = importlib.import_module("jcvi.compara.catalog")
         if hasattr(jcat, "blastfilter_main"):
@@ -30,5 +36,8 @@ def install():
         for name in ("scan", "liftover"):
             if hasattr(jcat, name):
                 setattr(jcat, name, getattr(syn, name))
+        if hasattr(jcat, "cscore"):            # `from jcvi.formats.blast import cscore` (catalog.py:20)
+            from .formats import blast as gblast
+            jcat.cscore = gblast.cscore
     except ImportError:
         pass

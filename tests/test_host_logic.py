@@ -171,8 +171,13 @@ def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
     (pkg / "synteny.py").write_text("def scan(a):\n    return 'ref'\ndef liftover(a):\n    return 'ref'\ndef mcscan(a):\n    return 'ref'\n"
                                     "def batch_scan(*a, **k):\n    return 'ref'\ndef synteny_scan(*a, **k):\n    return 'ref'\n"
                                     "def synteny_liftover(*a, **k):\n    return 'ref'\n")
+    fm = tmp_path / "jcvi" / "formats"
+    fm.mkdir()
+    (fm / "__init__.py").write_text("")
+    (fm / "blast.py").write_text("def cscore(args):\n    return 'ref'\ndef filter(args):\n    return 'ref'\n")
     (pkg / "catalog.py").write_text("from ..compara.blastfilter import main as blastfilter_main\n"
-                                    "from ..compara.synteny import liftover, mcscan, scan\n")
+                                    "from ..compara.synteny import liftover, mcscan, scan\n"
+                                    "from ..formats.blast import cscore, filter as blast_filter\n")
     monkeypatch.syspath_prepend(str(tmp_path))
     for m in [k for k in sys.modules if k == "jcvi" or k.startswith("jcvi.")]:
         monkeypatch.delitem(sys.modules, m)
@@ -182,6 +187,9 @@ def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
     cat = importlib.import_module("jcvi.compara.catalog")
     assert cat.blastfilter_main is gbf.main and cat.scan is gsyn.scan and cat.liftover is gsyn.liftover
     assert cat.mcscan(None) == "ref"                                   # untouched
+    from jcvi_b200.formats import blast as gblast
+    assert cat.cscore is gblast.cscore and importlib.import_module("jcvi.formats.blast").cscore is gblast.cscore
+    assert cat.blast_filter(None) == "ref"                             # untouched
     assert importlib.import_module("jcvi.compara.synteny").batch_scan is gsyn.batch_scan
     for m in [k for k in sys.modules if k == "jcvi" or k.startswith("jcvi.")]:
         monkeypatch.delitem(sys.modules, m)
