@@ -72,6 +72,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaFree(ctx->held_text);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
+  if (ctx->ws) cudaFree(ctx->ws);
   cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);
   cudaFree(ctx->lastf.q); cudaFree(ctx->lastf.s); cudaFree(ctx->lastf.score);
   for (auto& ev : ctx->tok_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }

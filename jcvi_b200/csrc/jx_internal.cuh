@@ -75,6 +75,11 @@ struct jx_ctx {
   // tokenizer timing (CUDA events on `stream`)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tok_events;
   bool record_reuse = true;      // jx_set_record_reuse
+  // per-call scratch: one grow-only device workspace handed out by bump pointer (Arena); requests that
+  // do not fit fall back to cudaMallocAsync and make the workspace grow for the next call
+  char* ws = nullptr;
+  size_t ws_cap = 0, ws_used = 0, ws_virtual = 0, ws_need = 0;
+  int ws_depth = 0;
   int64_t tok_resident = 0;      // persistent tokenizer CTAs that fit on this device at once
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
@@ -157,18 +162,44 @@ inline int jx_pin_small(jx_ctx* ctx, size_t bytes, char** out) {
 // stream-ordered scratch allocations, released when the Arena goes out of scope
 struct Arena {
   jx_ctx* ctx;
-  std::vector<void*> ptrs;
-  explicit Arena(jx_ctx* c) : ctx(c) {}
+  std::vector<void*> ptrs;       // fall-back allocations (cudaMallocAsync)
+  size_t mark, vmark;
+  explicit Arena(jx_ctx* c) : ctx(c), mark(c->ws_used), vmark(c->ws_virtual) { ++c->ws_depth; }
   ~Arena() {
     for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+    ctx->ws_used = mark;
+    ctx->ws_virtual = vmark;
+    if (--ctx->ws_depth == 0 && ctx->ws_need > ctx->ws_cap) {
+      // grow to what this call would have needed (bounded: a quarter of the device); every kernel that
+      // used the old block was enqueued on ctx->stream
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      size_t want = ctx->ws_need + ctx->ws_need / 4 + (64u << 20);
+      if (want > total_b / 4) want = total_b / 4;
+      if (want > ctx->ws_cap && want - ctx->ws_cap < free_b / 2) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->ws) cudaFree(ctx->ws);
+        ctx->ws = nullptr; ctx->ws_cap = 0;
+        if (cudaMalloc((void**)&ctx->ws, want) == cudaSuccess) ctx->ws_cap = want;
+        else cudaGetLastError();
+      }
+      ctx->ws_need = 0;
+    }
   }
   template <class T>
   T* alloc(size_t n, bool zero = false) {
     void* p = nullptr;
-    size_t bytes = (n ? n : 1) * sizeof(T);
-    if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) return nullptr;
-    ptrs.push_back(p);
-    if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    const size_t bytes = (((n ? n : 1) * sizeof(T)) + 255) & ~(size_t)255;
+    ctx->ws_virtual += bytes;
+    if (ctx->ws_virtual > ctx->ws_need) ctx->ws_need = ctx->ws_virtual;
+    if (ctx->ws && ctx->ws_used + bytes <= ctx->ws_cap) {
+      p = ctx->ws + ctx->ws_used;
+      ctx->ws_used += bytes;
+    } else {
+      if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) return nullptr;
+      ptrs.push_back(p);
+    }
+    if (zero) cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream);
     return (T*)p;
   }
 };
