@@ -243,6 +243,17 @@ int jx_distinct_names(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on
 int jx_blast_cscore(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names,
                     double cutoff, int want_pct, int want_blast, char** out, int64_t* out_len,
                     char** blast_out, int64_t* blast_len, int64_t stats[4]);
+/* `jcvi.formats.blast filter` (src/jcvi/formats/blast.py:620-709): the rows whose BlastLine passes
+ *   remove = score < o.score or pctid < o.pctid or hitlen < o.hitlen or evalue > o.evalue or noids
+ *   if inverse: remove = not remove;   remove = remove or (noself and query == subject)
+ * in file order, each as row.rstrip() + "\n" ('#' rows are skipped).  use_ids: `query in ids and subject
+ * in ids` on the raw names, against the name list loaded on both sides with jx_bed_load.  Comparisons are
+ * the reference's: float32 score / pctid widened to double, C int hitlen, strtod(evalue) > cutoff decided
+ * exactly (JX_EUNSUPPORTED when a row would need more than the exact routes).  stats: 0 rows, 1 kept,
+ * 2 removed, 3 '#' rows.  Buffer: jx_free. */
+int jx_blast_filter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, double score,
+                    double pctid, int64_t hitlen, double evalue, int noself, int inverse, int use_ids,
+                    char** out, int64_t* out_len, int64_t stats[4]);
 /* float32 best score per name id of the open jx_cscore_begin session (first n entries) */
 int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
 /* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */

@@ -27,6 +27,7 @@ def install():
         from .formats import blast as gblast
         jblast = importlib.import_module("jcvi.formats.blast")
         jblast.cscore = gblast.cscore
+        jblast.filter = gblast.filter
     except ImportError:
         pass
     try:
@@ -39,5 +40,8 @@ def install():
         if hasattr(jcat, "cscore"):            # `from jcvi.formats.blast import cscore` (catalog.py:20)
             from .formats import blast as gblast
             jcat.cscore = gblast.cscore
+        if hasattr(jcat, "blast_filter"):      # `from ..formats.blast import filter as blast_filter` (catalog.py:33)
+            from .formats import blast as gblast
+            jcat.blast_filter = gblast.filter
     except ImportError:
         pass

@@ -61,7 +61,7 @@ EXPORTS = [
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
     "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse", "jx_distinct_names", "jx_best_table_copy", "jx_session_counts",
-    "jx_host_blastline", "jx_blast_cscore",
+    "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter",
     "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_free", "jx_abi_sizes",
 ]
 
@@ -116,6 +116,9 @@ def lib():
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
                                         ctypes.POINTER(ctypes.c_int64)]
         L.jx_best_table_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+        L.jx_blast_filter.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         L.jx_blast_cscore.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                       ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]

@@ -304,6 +304,71 @@ JX_HD bool fast_line5(const BR& B, const MW& mw, const MN& mn, int s, int e, Lin
   return fast_line5_head(B, mw, mn, s, e, t, tail) && fast_line5_tail(B, tail, t);
 }
 
+// ---- formats.blast filter (src/jcvi/formats/blast.py:620-709): every field the predicate reads -----------------
+struct FilterFields {
+  float score, pct;             // float32 like the Cython object's C floats (0 when not converted)
+  long long hitlen;
+  int ev_gt;                    // strtod(evalue) > cutoff
+  int qa, qb, sa, sb;           // raw name spans
+  bool hard, longname, fast;
+};
+// [s, e) = the row without its terminator (may be empty: BlastLine of "\n", every field 0).  `try_fast`: the
+// row lies inside the window the masks cover.  Fast route = fast_line5_head's structure check + word
+// arithmetic; everything else goes through the sscanf-faithful scanner.
+template <class BR, class MW, class MN, class R>
+JX_HD void filter_parse(const BR& B, const MW& mw, const MN& mn, R& rd, int s, int e, bool try_fast, double cutoff_evalue,
+                        FilterFields& f) {
+  const int ev0 = (0.0 > cutoff_evalue) ? 1 : 0;
+  f.score = 0.f; f.pct = 0.f; f.hitlen = 0; f.ev_gt = ev0; f.qa = f.qb = f.sa = f.sb = s;
+  f.hard = false; f.longname = false; f.fast = false;
+  if (s < e && try_fast) {
+    LineTok t; Line5Tail tail;
+    if (fast_line5_head(B, mw, mn, s, e, t, tail)) {
+      // pctid = [tab2+1, tab3), hitlen = [tab3+1, tab4): the next two separators after the subject name
+      const int p0 = t.sb + 1;
+      const uint64_t Wx = bits64(mw, p0);
+      const uint64_t Wy = Wx & (Wx - 1ull);
+      const int lp = Wx ? ctz64(Wx) : 99;
+      const int lh = Wy ? ctz64(Wy) - lp - 1 : 0;          // both separators inside the 64-byte window, else generic
+      const uint32_t pb = (uint32_t)bits64(mn, p0) & below32(lp > 32 ? 32 : lp);
+      uint32_t em = 0; int ee = 0;
+      float pct = 0.f, score = 0.f;
+      if (lp <= 14 && lh >= 1 && lh <= 8 && score5(B, p0, lp, pb, pct) && score5(B, tail.ps, tail.ls, tail.sb, score) &&
+          decimal5(B, tail.pe, tail.le, tail.eb, em, ee)) {
+        Dec d; d.m = em; d.e10 = em ? ee : 0; d.neg = false; d.ok = true; d.dropped = false; d.special = false;
+        const int g = dec_gt_double(d, cutoff_evalue);
+        if (g >= 0) {
+          f.hitlen = (long long)digits_upto8(B.load32(p0 + lp + 1), B.load32(p0 + lp + 5), lh, -1);
+          f.pct = pct; f.score = score; f.ev_gt = g; f.fast = true;
+          f.qa = t.qa; f.qb = t.qb; f.sa = t.sa; f.sb = t.sb;
+          return;
+        }
+      }
+    }
+  }
+  if (s >= e) return;
+  FullTok ft;
+  tokenize_line_full(rd, s, e, ft);
+  f.qa = ft.qa; f.qb = ft.qb; f.sa = ft.sa; f.sb = ft.sb; f.hitlen = ft.hitlen;
+  f.hard = ft.hard; f.longname = ft.longname;
+  if (ft.pctid.ok && !dec_to_f32(ft.pctid, f.pct)) f.hard = true;
+  if (ft.score.ok && !dec_to_f32(ft.score, f.score)) f.hard = true;
+  if (ft.evalue.ok) { const int g = dec_gt_double(ft.evalue, cutoff_evalue); if (g < 0) f.hard = true; else f.ev_gt = g; }
+}
+// the predicate of blast.py:681-699 (noids: `not (query in ids and subject in ids)`, false without --ids)
+template <class R>
+JX_HD bool filter_remove(R& rd, const FilterFields& f, double c_score, double c_pctid, long long c_hitlen, bool noids,
+                         bool inverse, bool noself) {
+  bool remove = ((double)f.score < c_score) || ((double)f.pct < c_pctid) || (f.hitlen < c_hitlen) || f.ev_gt || noids;
+  if (inverse) remove = !remove;
+  if (noself && (f.qb - f.qa) == (f.sb - f.sa)) {          // c.query == c.subject
+    bool same = true;
+    for (int i = 0; i < f.qb - f.qa; ++i) same = same && (rd(f.qa + i) == rd(f.sa + i));
+    remove = remove || same;
+  }
+  return remove;
+}
+
 // position of the first '|' in [a, b), or -1 (only called for tiles that may hold one)
 template <class BR>
 JX_HD int find_bar(const BR& B, int a, int b) {

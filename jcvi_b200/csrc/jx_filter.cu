@@ -202,11 +202,14 @@ __global__ void k_gather_out(const uint32_t* Fj, uint32_t n, const uint4* C, con
   ooff[t] = (uint64_t)lo * JX_TILE + (r.w >> 1);
 }
 
-__global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, const uint32_t* idx, uint32_t cnt, uint32_t* len) {
+__global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, const uint32_t* idx, uint32_t cnt, uint32_t* len,
+                           int rstrip = 0) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt) return;
   int64_t p = (int64_t)off[idx ? idx[t] : t], e = p;
   while (e < n && !jx::is_term(text[e])) ++e;
+  if (rstrip)                          // str.rstrip(): ASCII white space and the separators 0x1c-0x1f
+    while (e > p && (jx::is_space(text[e - 1]) || (uint32_t)(text[e - 1] - 0x1Cu) <= 3u)) --e;
   len[t] = (uint32_t)(e - p) + 1;      // + '\n'
 }
 __global__ void k_copy_lines(const uint8_t* text, const uint64_t* off, const uint32_t* idx, const uint32_t* len,
@@ -367,7 +370,7 @@ __global__ void k_line_off(const uint32_t* idx, uint32_t cnt, const uint4* recs,
 }  // namespace
 
 int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
-                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len) {
+                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip) {
   *out = nullptr; *out_len = 0;
   if (!cnt) { *out = (char*)calloc(1, 1); return JX_OK; }
   int rc;
@@ -375,7 +378,7 @@ int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nb
   JX_ALLOC(len, uint32_t, cnt, false);
   JX_ALLOC(pos, uint32_t, cnt, false);
   JX_LAUNCH(k_line_off, nblk(cnt), 256, 0, rec_idx, cnt, recs, desc, ntiles, off);
-  JX_LAUNCH(k_line_len, nblk(cnt), 256, 0, d_text, nbytes, off, (const uint32_t*)nullptr, cnt, len);
+  JX_LAUNCH(k_line_len, nblk(cnt), 256, 0, d_text, nbytes, off, (const uint32_t*)nullptr, cnt, len, rstrip);
   if ((rc = jx_exclusive_sum(ctx, arena, len, pos, cnt))) return rc;
   uint32_t h[2];
   JX_CK(cudaMemcpyAsync(&h[0], pos + cnt - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -7,6 +7,7 @@
 #include "jx_format.cuh"
 #include "jx_fast5.cuh"
 #include <vector>
+#include <string>
 
 namespace {
 struct PtrReader { const unsigned char* p; inline uint32_t operator()(int i) const { return p[i]; } };
@@ -209,6 +210,50 @@ int probe_fast_line5(const char* buf, int buflen, int s, int e, int* spans, floa
   return 1;
 }
 
+// formats.blast filter: the kernel's per-row decision (filter_parse + filter_remove, masks built with the kernel's
+// classifier) for rows [rs[i], re[i]) of buf, on both routes, next to the reference's own arithmetic (glibc sscanf with
+// the cblast.pyx:15 format, C float / int / double compares).  out[3 i + 0]: fast allowed, + 1: generic only,
+// + 2: glibc;  1 kept, 0 removed, -1 refused (hard), -2 name of 128+ bytes.  route[i] = 1 when the fast route decided.
+void probe_filter_rows(const char* buf, int buflen, const int* rs, const int* re, long n, double c_score, double c_pctid,
+                       long long c_hitlen, double c_evalue, int noself, int inverse, signed char* out, signed char* route) {
+  const int padded = ((buflen + 31) / 32) * 32 + 256;
+  std::vector<unsigned char> text((size_t)padded, (unsigned char)'\n');
+  memcpy(text.data(), buf, (size_t)buflen);
+  std::vector<uint32_t> mw((size_t)padded / 32 + 2), mn((size_t)padded / 32 + 2);
+  uint32_t hi = 0;
+  for (int seg = 0; seg < padded / 32; ++seg) {
+    uint32_t w[8];
+    memcpy(w, text.data() + 32 * seg, 32);
+    jx::classify32(w, mw[(size_t)seg], mn[(size_t)seg], hi);
+  }
+  struct MaskRd { const uint32_t* p; inline uint32_t operator()(int i) const { return p[i]; } };
+  WordRd wr{text.data()};
+  MaskRd rw{mw.data()}, rn{mn.data()};
+  jx::WordBytes<WordRd> B(wr);
+  PtrReader rd{text.data()};
+  for (long i = 0; i < n; ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      jx::FilterFields f;
+      jx::filter_parse(B, rw, rn, rd, rs[i], re[i], pass == 0, c_evalue, f);
+      if (pass == 0) route[i] = f.fast ? 1 : 0;
+      signed char r;
+      if (f.longname) r = -2;
+      else if (f.hard) r = -1;
+      else r = jx::filter_remove(rd, f, c_score, c_pctid, c_hitlen, false, inverse != 0, noself != 0) ? 0 : 1;
+      out[3 * i + pass] = r;
+    }
+    std::string row((const char*)text.data() + rs[i], (size_t)(re[i] - rs[i]));
+    char q[4096], sb[4096]; float pct = 0, score = 0; double ev = 0; int ints[7] = {0, 0, 0, 0, 0, 0, 0};
+    q[0] = sb[0] = 0;
+    sscanf(row.c_str(), "%4095s\t%4095s\t%f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lf\t%f", q, sb, &pct, ints, ints + 1, ints + 2,
+           ints + 3, ints + 4, ints + 5, ints + 6, &ev, &score);
+    bool remove = (double)score < c_score || (double)pct < c_pctid || (long long)ints[0] < c_hitlen || ev > c_evalue;
+    if (inverse) remove = !remove;
+    remove = remove || (noself && strcmp(q, sb) == 0);
+    out[3 * i + 2] = (strlen(q) >= 128 || strlen(sb) >= 128) ? -2 : (remove ? 0 : 1);
+  }
+}
+
 // byte classes of one 32-byte block: the kernel's SWAR classifier (for comparison with the definition)
 void probe_classify32(const unsigned char* bytes32, unsigned* wmask, unsigned* nmask, unsigned* hi) {
   uint32_t w[8];
@@ -235,3 +280,13 @@ unsigned probe_slot_hash6(const char* buf, int a, int len, unsigned* words6) {
 }
 
 }  // extern "C"
+
+// strtod(s) > c decided by the kernel's exact routine: 1 / 0 / -1 refused / -2 no conversion
+extern "C" int probe_gt_double(const char* s, double c) {
+  PtrReader rd{(const unsigned char*)s};
+  jx::Dec d;
+  jx::scan_decimal(rd, 0, (int)strlen(s), d);
+  if (d.special) return -1;
+  if (!d.ok) return -2;
+  return jx::dec_gt_double(d, c);
+}

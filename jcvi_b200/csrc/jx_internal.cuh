@@ -229,6 +229,11 @@ struct TokMode {
   bool fill_cache = false;     // keep records/descriptors in ctx->cache (held text only)
   bool persist = false;        // like fill_cache but also for self comparisons / exclusions (sharded session)
   bool names = false;          // no BED: emit a 64-bit hash of both (stripped) names per line instead of ranks
+  // formats.blast filter (blast.py:620-709): keep / drop every line by a predicate on its fields
+  bool filter = false;
+  double f_score = 0, f_pctid = 0, f_evalue = 0;
+  long long f_hitlen = 0;
+  bool f_noself = false, f_inverse = false, f_ids = false;
   uint32_t seed = 0;           // of that hash
 };
 struct TokOut {
@@ -248,7 +253,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
 
 // raw text lines of the records rec_idx[0..cnt) (device array, file order) -> malloc'ed host buffer
 int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
-                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len);
+                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip = 0);
 
 // ---- shared device helpers ---------------------------------------------------------------------
 #if defined(__CUDACC__)

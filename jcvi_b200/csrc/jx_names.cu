@@ -41,9 +41,64 @@ __global__ void k_take_reps(const uint32_t* __restrict__ vals, const uint32_t* _
   side[pos[t]] = (uint8_t)(v & 1u);
 }
 
+__global__ void k_keep_flags(const uint4* __restrict__ recs, uint32_t n, uint32_t* flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = recs[i].x != JX_NOREC ? 1u : 0u;
+}
+__global__ void k_keep_idx(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n, uint32_t* idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) idx[pos[i]] = i;
+}
+
 }  // namespace
 
 extern "C" {
+
+// `jcvi.formats.blast filter` (src/jcvi/formats/blast.py:620-709): the rows whose BlastLine passes
+//   remove = score < o.score or pctid < o.pctid or hitlen < o.hitlen or evalue > o.evalue or noids
+//   if inverse: remove = not remove;  remove = remove or (noself and query == subject)
+// in file order, each as row.rstrip() + "\n".  use_ids: "c.query in ids and c.subject in ids" against the
+// names loaded with jx_bed_load (the ids file as a name list on both sides, raw names).
+int jx_blast_filter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, double score, double pctid,
+                    int64_t hitlen, double evalue, int noself, int inverse, int use_ids, char** out, int64_t* out_len,
+                    int64_t stats[4]) {
+  if (!ctx || !out || !out_len) return JX_EARG;
+  *out = nullptr; *out_len = 0;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  int rc;
+  TokMode mode;
+  mode.strip = 0;
+  mode.filter = true;
+  mode.f_score = score; mode.f_pctid = pctid; mode.f_hitlen = (long long)hitlen; mode.f_evalue = evalue;
+  mode.f_noself = noself != 0; mode.f_inverse = inverse != 0; mode.f_ids = use_ids != 0;
+  TokOut tok;
+  if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+  if (stats) {
+    stats[0] = (int64_t)(tok.stats[0] - tok.stats[1]);   // rows (non-'#'; includes CR LF gaps)
+    stats[1] = (int64_t)tok.stats[2];                    // kept
+    stats[2] = (int64_t)tok.stats[3];                    // removed
+    stats[3] = (int64_t)tok.stats[1];                    // '#' lines
+  }
+  const uint32_t n = tok.n_lines;
+  uint32_t cnt = 0;
+  uint32_t* idx = nullptr;
+  if (n) {
+    JX_ALLOC(flag, uint32_t, n, false);
+    JX_ALLOC(pos, uint32_t, n, false);
+    JX_LAUNCH(k_keep_flags, nblk(n), 256, 0, tok.recs, n, flag);
+    if ((rc = jx_exclusive_sum(ctx, arena, flag, pos, n))) return rc;
+    uint32_t h[2];
+    JX_CK(cudaMemcpyAsync(&h[0], pos + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(&h[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    cnt = h[0] + h[1];
+    JX_ALLOC(ix, uint32_t, (size_t)cnt + 1, false);
+    if (cnt) JX_LAUNCH(k_keep_idx, nblk(n), 256, 0, flag, pos, n, ix);
+    idx = ix;
+  }
+  return jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, idx, cnt, out, out_len, 1);
+}
 
 int jx_distinct_names(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, uint32_t seed,
                       char** lines, int64_t* lines_len, uint8_t** side, int64_t* n_names, int64_t stats[4]) {

@@ -168,6 +168,20 @@ JX_HD float bits_to_float(uint32_t u) {
   union { uint32_t u; float f; } x; x.u = u; return x.f;
 #endif
 }
+JX_HD uint64_t double_to_bits(double f) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(f);
+#else
+  union { uint64_t u; double f; } x; x.f = f; return x.u;
+#endif
+}
+JX_HD double bits_to_double(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  union { uint64_t u; double f; } x; x.u = u; return x.f;
+#endif
+}
 JX_HD uint32_t float_to_bits(float f) {
 #if defined(__CUDA_ARCH__)
   return __float_as_uint(f);
@@ -457,6 +471,183 @@ JX_HD void tokenize_line(R& rd, int s, int e, LineTok& t) {
   if (!dec_to_f32(d, t.score)) t.hard = true;
 }
 
+
+// ---- every field (formats.blast filter) ----------------------------------------------------------
+// `jcvi.formats.blast filter` (src/jcvi/formats/blast.py:620-709) tests score, pctid, hitlen and evalue
+// of every BlastLine.  Fields sscanf does not reach keep the zero initialisation of the Cython object.
+struct FullTok {
+  int qa, qb, sa, sb;   // raw name spans (empty when not converted)
+  Dec pctid, evalue, score;   // .ok = converted
+  long long hitlen;     // value of the %d conversion (0 when not converted)
+  int nconv;
+  bool hard;            // something the device cannot reproduce exactly (special floats, 10+ digit ints, ...)
+  bool longname;
+};
+// [+-]? d+ with its value; returns the position after it (p when nothing matched); > 9 digits -> *big
+template <class R>
+JX_HD int scan_int_value(R& rd, int p, int e, long long& val, bool& big) {
+  int q = p; bool neg = false;
+  if (q < e) { uint32_t c = rd(q); if (c == '-') { neg = true; ++q; } else if (c == '+') { ++q; } }
+  const int q0 = q; long long v = 0; int nd = 0;
+  while (q < e && is_digit(rd(q))) { if (nd < 18) v = v * 10 + (long long)(rd(q) - '0'); if (nd > 0 || rd(q) != '0') ++nd; ++q; }
+  if (q == q0) return p;
+  big = nd > 9;
+  val = neg ? -v : v;
+  return q;
+}
+template <class R>
+JX_HD void tokenize_line_full(R& rd, int s, int e, FullTok& t) {
+  t.qa = t.qb = t.sa = t.sb = s; t.nconv = 0; t.hard = false; t.longname = false; t.hitlen = 0;
+  t.pctid.ok = t.evalue.ok = t.score.ok = false; t.pctid.m = t.evalue.m = t.score.m = 0;
+  t.pctid.special = t.evalue.special = t.score.special = false;
+  int p = s;
+  while (p < e && is_space(rd(p))) ++p;
+  t.qa = p; while (p < e && !is_space(rd(p))) ++p; t.qb = p;
+  if (t.qb == t.qa) return;
+  t.nconv = 1;
+  while (p < e && is_space(rd(p))) ++p;
+  t.sa = p; while (p < e && !is_space(rd(p))) ++p; t.sb = p;
+  if (t.sb == t.sa) { t.sa = t.sb = s; return; }
+  t.nconv = 2;
+  if (t.qb - t.qa >= 128 || t.sb - t.sa >= 128) t.longname = true;
+  while (p < e && is_space(rd(p))) ++p;
+  Dec d;
+  int p2 = scan_decimal(rd, p, e, d);            // %f pctid
+  if (d.special) { t.hard = true; return; }
+  if (!d.ok) return;
+  t.pctid = d; p = p2; t.nconv = 3;
+  for (int k = 0; k < 7; ++k) {                   // 7 x %d; the first is hitlen
+    while (p < e && is_space(rd(p))) ++p;
+    long long v = 0; bool big = false;
+    p2 = scan_int_value(rd, p, e, v, big);
+    if (p2 == p) return;
+    if (k == 0) { t.hitlen = v; if (big) t.hard = true; }
+    p = p2; ++t.nconv;
+  }
+  while (p < e && is_space(rd(p))) ++p;
+  p2 = scan_decimal(rd, p, e, d);                 // %lf evalue
+  if (d.special) { t.hard = true; return; }
+  if (!d.ok) return;
+  t.evalue = d; p = p2; t.nconv = 11;
+  while (p < e && is_space(rd(p))) ++p;
+  p2 = scan_decimal(rd, p, e, d);                 // %f score
+  if (d.special) { t.hard = true; return; }
+  if (!d.ok) return;
+  t.score = d; t.nconv = 12;
+}
+
+// ---- strtod(text) > c, decided exactly ----------------------------------------------------------------
+// (formats.blast filter, blast.py:690: `c.evalue > evalue`, c.evalue = the %lf conversion of the field.)
+// strtod rounds the decimal x = m * 10^e10 to nearest-even.  For a finite a >= 0 with a = k * 2^q (k < 2^53 the
+// significand as an integer, q >= -1074), the next double is (k + 1) * 2^q, so
+//     RN(x) > a   <=>   x > mid  or  (x == mid and k odd),   mid = (2 k + 1) * 2^(q - 1)
+// (a = DBL_MAX: RN(x) = inf beyond the same midpoint; a = 0: mid = 2^-1075).  x and mid are compared as
+// integers after clearing the power of ten: a fixed-size big integer (1088 bits: 5^364 * 2^64 fits) is
+// only built when a bit-length estimate cannot separate them, i.e. for values within ~2 decades of a.
+struct Big { uint32_t w[34]; int n; };                      // little-endian words, n = words in use (no leading zeros)
+JX_HD void big_set(Big& b, uint64_t v) {
+  b.w[0] = (uint32_t)v; b.w[1] = (uint32_t)(v >> 32);
+  b.n = b.w[1] ? 2 : (b.w[0] ? 1 : 0);
+}
+JX_HD bool big_mul_small(Big& b, uint32_t f) {              // false: would not fit
+  uint64_t carry = 0;
+  for (int i = 0; i < b.n; ++i) { const uint64_t t = (uint64_t)b.w[i] * f + carry; b.w[i] = (uint32_t)t; carry = t >> 32; }
+  if (carry) { if (b.n >= 34) return false; b.w[b.n++] = (uint32_t)carry; }
+  return true;
+}
+JX_HD bool big_mul_pow5(Big& b, int n) {                    // b *= 5^n
+  while (n >= 13) { if (!big_mul_small(b, 1220703125u)) return false; n -= 13; }   // 5^13 < 2^32
+  uint32_t f = 1; while (n-- > 0) f *= 5u;
+  return f == 1u || big_mul_small(b, f);
+}
+JX_HD int big_bitlen(const Big& b) {
+  if (!b.n) return 0;
+  uint32_t t = b.w[b.n - 1]; int l = 0; while (t) { ++l; t >>= 1; }
+  return 32 * (b.n - 1) + l;
+}
+JX_HD int u64_bitlen(uint64_t v) { int l = 0; while (v) { ++l; v >>= 1; } return l; }
+// sign of  A * 2^ea  -  S * 2^es   (A big, S 64-bit, both > 0)
+JX_HD int big_cmp_scaled(const Big& A, int ea, uint64_t S, int es) {
+  const int la = big_bitlen(A) + ea, ls = u64_bitlen(S) + es;
+  if (la != ls) return la > ls ? 1 : -1;
+  const int sh = es - ea;                                  // compare A with S * 2^sh (sh >= 0) or A * 2^-sh with S
+  if (sh < 0) {                                            // then A < 2^64 (equal top bits): shift it instead
+    const uint64_t av = (uint64_t)A.w[0] | ((uint64_t)(A.n > 1 ? A.w[1] : 0u) << 32);
+    const uint64_t sa = av << (-sh);
+    return sa > S ? 1 : (sa < S ? -1 : 0);
+  }
+  const int ws = sh >> 5, bs = sh & 31;                    // word i of S << sh
+  for (int i = A.n - 1; i >= 0; --i) {
+    const int j = i - ws;                                  // bits [32 j - bs, 32 j - bs + 32) of S
+    uint32_t sw = 0;
+    if (j >= 0 && j <= 2) {
+      const uint64_t lo = j == 0 ? (S << bs) : (S >> (32 * j - bs));
+      sw = (uint32_t)lo;
+      if (j == 0 && bs == 0) sw = (uint32_t)S;
+    } else if (j == -1 || j > 2) sw = 0;
+    if (A.w[i] != sw) return A.w[i] > sw ? 1 : -1;
+  }
+  return 0;
+}
+// sign of  m * 10^e10  -  K * 2^Q   (m, K > 0);  2: the big integer would not fit (never for inputs that
+// pass dec_gt_double's estimate)
+JX_HD int dec_cmp_dyadic(uint64_t m, int e10, uint64_t K, int Q) {
+  Big b;
+  if (e10 >= 0) {                                          // m 5^e 2^e  vs  K 2^Q
+    big_set(b, m);
+    if (!big_mul_pow5(b, e10)) return 2;
+    return big_cmp_scaled(b, e10, K, Q);
+  }
+  big_set(b, K);                                           // m  vs  K 5^n 2^(Q + n)
+  if (!big_mul_pow5(b, -e10)) return 2;
+  return -big_cmp_scaled(b, Q - e10, m, 0);
+}
+// RN(m * 10^e10 [+ dropped digits]) > a  for finite a >= 0 and m > 0:  1 / 0 / -1 (not decidable: only with
+// dropped digits straddling the midpoint)
+JX_HD int dec_gt_nonneg(uint64_t m, int e10, bool dropped, double a) {
+  const uint64_t bits = double_to_bits(a);
+  const int be = (int)((bits >> 52) & 0x7FFu);
+  const uint64_t frac = bits & ((1ull << 52) - 1ull);
+  const uint64_t k = be ? (frac | (1ull << 52)) : frac;
+  const int q = be ? be - 1075 : -1074;
+  const uint64_t K = 2ull * k + 1ull; const int Q = q - 1;
+  // estimate: log2(mid) in [bitlen(K) - 1 + Q, bitlen(K) + Q), log10(x) in [nd - 1 + e10, nd + e10 (+ dropped))
+  int nd = 1; { uint64_t t = m; while (t >= 10u) { t /= 10u; ++nd; } }
+  const double l2lo = (double)(u64_bitlen(K) - 1 + Q), l2hi = l2lo + 1.0;
+  const double LOG2_10 = 3.321928094887362;
+  if ((double)(nd - 1 + e10) * LOG2_10 > l2hi + 1.0) return 1;
+  if ((double)(nd + e10 + (dropped ? 1 : 0)) * LOG2_10 < l2lo - 1.0) return 0;
+  const int c0 = dec_cmp_dyadic(m, e10, K, Q);
+  if (c0 == 2) return -1;
+  if (!dropped) return (c0 > 0 || (c0 == 0 && (k & 1ull))) ? 1 : 0;
+  if (c0 >= 0) return 1;                                   // x > m 10^e10 >= mid
+  const int c1 = dec_cmp_dyadic(m + 1ull, e10, K, Q);
+  if (c1 == 2) return -1;
+  if (c1 <= 0) return 0;                                   // x < (m + 1) 10^e10 <= mid
+  return -1;
+}
+JX_HD double next_down_pos(double a) { return bits_to_double(double_to_bits(a) - 1ull); }   // a > 0 finite
+// strtod(text) > c  for the scanned decimal d:  1 / 0 / -1 (refused)
+JX_HD int dec_gt_double(const Dec& d, double c) {
+  if (d.special || !d.ok) return -1;
+  if (c != c) return 0;                                    // nan
+  const uint64_t cb = double_to_bits(c);
+  const bool cneg = (cb >> 63) != 0ull;
+  const bool cinf = ((cb >> 52) & 0x7FFull) == 0x7FFull;
+  if (cinf) return cneg ? 1 : 0;
+  if (d.m == 0 && !d.dropped) return 0.0 > c ? 1 : 0;      // +-0.0 > c
+  if (!d.dropped && d.m < (1ull << 53) && d.e10 >= -22 && d.e10 <= 22) {   // one correctly rounded operation
+    const double v = d.e10 < 0 ? (double)d.m / pow10_exact(-d.e10) : (double)d.m * pow10_exact(d.e10);
+    return (d.neg ? -v : v) > c ? 1 : 0;
+  }
+  if (d.m == 0) return -1;                                 // only dropped digits (20+ leading zeros): refuse
+  const double ac = cneg ? -c : c;
+  if (!d.neg) return (cneg && ac != 0.0) ? 1 : dec_gt_nonneg(d.m, d.e10, d.dropped, ac);
+  // negative value -RN(x):  > c  <=>  c < 0 and RN(x) < |c|  <=>  c < 0 and not RN(x) > pred(|c|)
+  if (!cneg || ac == 0.0) return 0;
+  const int g = dec_gt_nonneg(d.m, d.e10, d.dropped, next_down_pos(ac));
+  return g < 0 ? -1 : 1 - g;
+}
 
 // ---- fast path -------------------------------------------------------------------------------
 // Word-at-a-time (SWAR) parse of a REGULAR line: 12+ fields separated by single tabs, names made

@@ -33,6 +33,7 @@ struct TokArgs {
   uint32_t rec_cap;
   uint4* hashes;             // names mode only
   uint32_t seed;
+  double f_score, f_pctid, f_evalue; long long f_hitlen; int f_noself, f_inverse, f_ids;   // filter mode only
   const uint4* qtab; const uint16_t* qdisp; uint32_t qbshift, qcshift; const uint32_t* qmeta; const uint32_t* qblob;   // 2 x uint4 per slot
   const uint4* stab; const uint16_t* sdisp; uint32_t sbshift, scshift; const uint32_t* smeta; const uint32_t* sblob;
   const uint32_t* qovh; const uint32_t* qovr; uint32_t qnov;   // overflow lists (equal 32-bit hashes), usually empty
@@ -153,11 +154,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // in flight (one bulk copy issued by one thread into the other half of a double buffer) while it
 // works on the current one, so the HBM latency of staging is off the critical path and costs no
 // load/store instructions.
-// NAMES = false: ranks through the BED name tables (the path's kernel).  NAMES = true: no table, the
+// MODE 0: ranks through the BED name tables (the path's kernel).  MODE 1 (NAMES): no table, the
 // record keeps only the line position and `hashes` receives a 64-bit hash of both names
 // (jx_distinct_names, formats.blast cscore); a separate instantiation, so the main one is unchanged.
-template <bool NAMES>
+// MODE 2: formats.blast filter -- every line is kept or dropped by a predicate on its own fields.
+template <int MODE>
 __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(const TokArgs a) {
+  constexpr bool NAMES = MODE == 1;
+  constexpr bool FILTER = MODE == 2;
   constexpr int NGRP = JX_TOK_THREADS / JX_GROUP;          // independent tile groups per CTA
   constexpr int GWARPS = JX_GROUP / 32;
   __shared__ __align__(128) uint8_t g_text[NGRP][2][STAGE_BYTES];
@@ -399,6 +403,26 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     uint4 hrec = make_uint4(0u, 0u, 0u, 0u);
     if (s < e && sm[s] == '#') {
       ++c_comment;
+    } else if (FILTER) {
+      // ---- formats.blast filter: BlastLine(row) then the predicate of blast.py:681-699 ------------------
+      const uint32_t prevc = s > 0 ? sm[s - 1] : (base > 0 ? a.text[base - 1] : 0u);
+      const bool crlf_gap = s >= e && prevc == '\r' && sm[s] == '\n';     // not a row (universal newlines)
+      if (!crlf_gap) {
+        jx::FilterFields ff;
+        jx::filter_parse(B, mwr, mnr, rd, s, e, e + 8 <= JX_WIN, a.f_evalue, ff);
+        if (ff.longname) ++c_long;
+        if (ff.hard || ff.longname) { ++c_hard; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; }
+        else {
+          bool noids = false;
+          if (a.f_ids) {                                  // c.query in ids and c.subject in ids (raw names)
+            const bool inq = table_lookup_bytes(rd, ff.qa, ff.qb, TQ) >= 0;
+            const bool ins = inq && table_lookup_bytes(rd, ff.sa, ff.sb, TS) >= 0;
+            noids = !(inq && ins);
+          }
+          const bool remove = jx::filter_remove(rd, ff, a.f_score, a.f_pctid, a.f_hitlen, noids, a.f_inverse != 0, a.f_noself != 0);
+          if (!remove) { rec.x = 1u; ++c_mapped; } else ++c_unmapped;
+        }
+      }
     } else if (s < e) {
       jx::LineTok t;
       const bool fast = (e + 8 <= JX_WIN) && jx::fast_line5(B, mwr, mnr, s, e, t);
@@ -580,7 +604,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
 
 int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
                      const TokMode& mode, TokOut& out) {
-  if (!mode.names && !ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
+  if (!mode.names && !(mode.filter && !mode.f_ids) && !ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
   if (nbytes < 0 || (nbytes && !text)) return JX_EARG;
   const int64_t ntiles = (nbytes + JX_TILE - 1) / JX_TILE;
   out.ntiles = ntiles;
@@ -674,6 +698,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     TokArgs a;
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.tile_begin = 0; a.tile_end = 0; a.recs = recs; a.rec_cap = (uint32_t)cap64;
     a.hashes = hashes; a.seed = mode.seed;
+    a.f_score = mode.f_score; a.f_pctid = mode.f_pctid; a.f_evalue = mode.f_evalue; a.f_hitlen = mode.f_hitlen;
+    a.f_noself = mode.f_noself; a.f_inverse = mode.f_inverse; a.f_ids = mode.f_ids;
     a.qtab = Q.table; a.qdisp = Q.disp; a.qbshift = Q.bshift; a.qcshift = Q.cshift; a.qmeta = Q.name_meta; a.qblob = Q.blobw;
     a.stab = S.table; a.sdisp = S.disp; a.sbshift = S.bshift; a.scshift = S.cshift; a.smeta = S.name_meta; a.sblob = S.blobw;
     a.qovh = Q.ovf_hash; a.qovr = Q.ovf_rank; a.qnov = Q.n_ovf; a.sovh = S.ovf_hash; a.sovr = S.ovf_rank; a.snov = S.n_ovf;
@@ -685,7 +711,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     // persistent CTAs: as many as are resident at once
     if (!ctx->tok_resident) {
       int per_sm = 0, n_sm = 0;
-      JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<false>, JX_TOK_THREADS, 0));
+      JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<0>, JX_TOK_THREADS, 0));
       JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->tok_resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
     }
@@ -711,8 +737,9 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       JX_CK(cudaEventCreate(&e1));
       JX_CK(cudaEventRecord(e0, ctx->stream));
       a.ticket = d_ticket + c; a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
-      if (mode.names) JX_LAUNCH(k_tokenize<true>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
-      else JX_LAUNCH(k_tokenize<false>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      if (mode.filter) JX_LAUNCH(k_tokenize<2>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else if (mode.names) JX_LAUNCH(k_tokenize<1>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else JX_LAUNCH(k_tokenize<0>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
     }

@@ -213,6 +213,22 @@ class Engine(object):
             self.lib.jx_free(out); self.lib.jx_free(bout)
         return a, b, dict(zip(("lines", "named", "short", "comments"), list(st)))
 
+    def blast_filter(self, text, score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, inverse=False, ids=None):
+        """`jcvi.formats.blast filter` -> (bytes of the kept rows, stats).  ids: iterable of names (bytes) or None."""
+        use_ids = bool(ids)
+        if use_ids:
+            self.load_names(sorted(set(ids)))
+        p, n, dev, keep = _text_ptr(text)
+        out = ctypes.c_void_p(); ln = ctypes.c_int64(); st = (ctypes.c_int64 * 4)()
+        rc = self.lib.jx_blast_filter(self.ctx, p, n, dev, float(score), float(pctid), int(hitlen), float(evalue),
+                                      int(bool(noself)), int(bool(inverse)), int(use_ids), ctypes.byref(out), ctypes.byref(ln), st)
+        try:
+            self._check(rc)
+            a = ctypes.string_at(out, ln.value) if ln.value else b""
+        finally:
+            self.lib.jx_free(out)
+        return a, dict(zip(("rows", "kept", "removed", "comments"), list(st)))
+
     def best_table(self, n):
         out = np.zeros(max(int(n), 1), dtype=np.float32)
         self._check(self.lib.jx_best_table_copy(self.ctx, C.ptr(out), int(n)))

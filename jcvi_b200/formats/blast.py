@@ -75,6 +75,58 @@ def cscore(args):
             fwb.write(blast_out.decode())
 
 
+def filtered_blastfile_name(blastfile, pctid, hitlen, inverse=False):
+    """blast.py:604-617."""
+    pctid_str = "{:.1f}".format(pctid).replace(".", "_").replace("_0", "")
+    newblastfile = blastfile + ".P{0}L{1}".format(pctid_str, hitlen)
+    if inverse:
+        newblastfile += ".inverse"
+    return newblastfile
+
+
+def filter(args):
+    """
+    %prog filter test.blast
+
+    Produce a new blast file and filter based on:
+    - score: >= cutoff
+    - pctid: >= cutoff
+    - hitlen: >= cutoff
+    - evalue: <= cutoff
+    - ids: valid ids
+
+    Use --inverse to obtain the complementary records for the criteria above.
+
+    - noself: remove self-self hits
+    """
+    p = OptionParser(filter.__doc__)
+    p.add_argument("--score", dest="score", default=0, type=int, help="Score cutoff")
+    p.add_argument("--pctid", default=95, type=float, help="Sequence percent identity")
+    p.add_argument("--hitlen", default=100, type=int, help="Minimum overlap length")
+    p.add_argument("--evalue", default=0.01, type=float, help="E-value cutoff")
+    p.add_argument("--noself", default=False, action="store_true", help="Remove self-self hits")
+    p.add_argument("--ids", help="Path to file with ids to retain")
+    p.add_argument("--inverse", default=False, action="store_true", help="Similar to grep -v, inverse")
+    p.set_outfile(outfile=None)
+    opts, args = p.parse_args(args)
+    if len(args) != 1:
+        sys.exit(not p.print_help())
+    ids = None
+    if opts.ids:
+        ids = set()
+        for row in read_text_file(opts.ids).tobytes().splitlines():
+            if row[:1] == b"#":
+                continue
+            ids.update(row.replace(b",", b"\t").split())
+    (blastfile,) = args
+    out, _ = get_engine().blast_filter(read_text_file(blastfile), score=opts.score, pctid=opts.pctid, hitlen=opts.hitlen,
+                                       evalue=opts.evalue, noself=opts.noself, inverse=opts.inverse, ids=ids)
+    newblastfile = filtered_blastfile_name(opts.outfile or blastfile, opts.pctid, opts.hitlen, opts.inverse)
+    with open(newblastfile, "wb") as fw:
+        fw.write(out)
+    return newblastfile
+
+
 def cscore_pairs(text, cutoff, strip_names=True, engine=None):
     """-> {(query, subject): (cscore, pctid, str(BlastLine))} exactly as the reference's `pairs` dict
     (blast.py:1158-1172); names are bytes."""
@@ -123,9 +175,9 @@ def cscore_pairs(text, cutoff, strip_names=True, engine=None):
 
 
 def main():
-    actions = {"cscore": cscore}
+    actions = {"cscore": cscore, "filter": filter}
     if len(sys.argv) < 2 or sys.argv[1] not in actions:
-        print("usage: python -m jcvi_b200.formats.blast cscore blastfile [options]", file=sys.stderr)
+        print("usage: python -m jcvi_b200.formats.blast cscore|filter blastfile [options]", file=sys.stderr)
         sys.exit(1)
     actions[sys.argv[1]](sys.argv[2:])
 

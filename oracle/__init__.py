@@ -9,6 +9,7 @@ from .oracle import (  # noqa: F401
     scan,
     liftover,
     cscore,
+    blast_filter,
     kdtree,
     gene_name,
     natcmp,

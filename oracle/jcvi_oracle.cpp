@@ -25,6 +25,7 @@
 //     -- build (balanced, compact, leafsize=16) and k=1, p=1 query; validated
 //     black-box against the installed scipy in tests/test_oracle_kdtree.py.
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1010,6 +1011,53 @@ int orc_cscore(const char* blast_file, const char* out_path, const char* blast_o
   fclose(fw);
   if (fwb) fclose(fwb);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// formats.blast filter  (src/jcvi/formats/blast.py:620-709): one pass, one predicate per row.
+//   ids_path: file of ids to retain ('#' lines skipped, commas are separators, blast.py:655-662) or NULL
+// Output rows are row.rstrip() + "\n" (ASCII white space and 0x1c-0x1f; non-ASCII Unicode spaces are
+// not reproduced).  returns 0, -1 I/O error, -2 unparsable row (128+ byte name)
+// ---------------------------------------------------------------------------------
+int orc_blast_filter(const char* blast_file, const char* out_path, const char* ids_path, double score, double pctid,
+                     long hitlen, double evalue, int noself, int inverse) {
+  std::string txt;
+  if (!read_file(blast_file, txt)) return -1;
+  std::unordered_set<std::string> ids;
+  const bool use_ids = ids_path && *ids_path;
+  if (use_ids) {
+    std::string itxt;
+    if (!read_file(ids_path, itxt)) return -1;
+    for_each_line(itxt.data(), itxt.size(), [&](const char* b, const char* e) {
+      if (b < e && *b == '#') return;
+      std::string row(b, e);
+      for (char& c : row) if (c == ',') c = '\t';
+      for (const std::string& t : split_ws(row)) ids.insert(t);
+    });
+  }
+  FILE* fw = fopen(out_path, "w");
+  if (!fw) return -1;
+  std::string scratch;
+  bool ok = true;
+  for_each_line(txt.data(), txt.size(), [&](const char* b, const char* e) {
+    if (!ok) return;
+    if (b < e && *b == '#') return;
+    BlastLine c;
+    if (!parse_blast_line(b, e, c, scratch)) { ok = false; return; }
+    bool noids = false;
+    if (use_ids && ids.size()) noids = !(ids.count(c.query) && ids.count(c.subject));
+    bool remove = (double)c.score < score || (double)c.pctid < pctid || (long)c.hitlen < hitlen || c.evalue > evalue || noids;
+    if (inverse) remove = !remove;
+    remove = remove || (noself && strcmp(c.query, c.subject) == 0);
+    if (!remove) {
+      const char* r = e;
+      while (r > b && (isspace((unsigned char)r[-1]) || ((unsigned char)r[-1] >= 0x1c && (unsigned char)r[-1] <= 0x1f))) --r;
+      fwrite(b, 1, (size_t)(r - b), fw);
+      fputc('\n', fw);
+    }
+  });
+  fclose(fw);
+  return ok ? 0 : -2;
 }
 
 }  // extern "C"

@@ -95,6 +95,12 @@ def cscore(blast_file, out_path, cutoff=0.9999, pct=False, writeblast=False, str
     _check(rc)
 
 
+def blast_filter(blast_file, out_path, score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, ids=None, inverse=False):
+    """formats/blast.py:620-709 (`jcvi.formats.blast filter`); writes out_path."""
+    _check(_lib().orc_blast_filter(_b(blast_file), _b(out_path), _b(ids), ctypes.c_double(score), ctypes.c_double(pctid),
+                                   ctypes.c_long(int(hitlen)), ctypes.c_double(evalue), int(bool(noself)), int(bool(inverse))))
+
+
 def kdtree(anchors, queries, bound):
     """Restated cKDTree(anchors, leafsize=16).query(queries, p=1, distance_upper_bound=bound)."""
     a = np.ascontiguousarray(anchors, dtype=np.int64).reshape(-1, 2)

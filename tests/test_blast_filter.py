@@ -1,0 +1,193 @@
+"""`jcvi.formats.blast filter` (src/jcvi/formats/blast.py:620-709).
+
+CPU: the oracle's restatement against golden vectors produced by the unmodified reference
+(tests/golden/make_golden_filter.py).  GPU: the drop-in (`jcvi_b200.formats.blast.filter`) against the
+same vectors and against the oracle on a larger synthetic table."""
+import os
+
+import pytest
+
+from conftest import read
+
+
+def _argv_to_kwargs(argv, d):
+    kw = dict(score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, inverse=False, ids=None)
+    for a in argv:
+        k, _, v = a.lstrip("-").partition("=")
+        if k in ("noself", "inverse"):
+            kw[k] = True
+        elif k == "ids":
+            kw[k] = os.path.join(d, v)
+        elif k in ("score", "hitlen"):
+            kw[k] = int(v)
+        else:
+            kw[k] = float(v)
+    return kw
+
+
+def test_oracle_filter_matches_reference_golden(golden):
+    import oracle
+    d, cases = golden("blast_filter")
+    assert len(cases) >= 24
+    for c in cases:
+        out = os.path.join(d, c["out"] + ".orc")
+        oracle.blast_filter(os.path.join(d, c["input"]), out, **_argv_to_kwargs(c["argv"], d))
+        assert read(out) == read(os.path.join(d, c["out"])), c
+
+
+def test_filtered_blastfile_name():
+    """blast.py:604-617; tests/formats/test_blast.py of the reference pins the same strings."""
+    from jcvi_b200.formats.blast import filtered_blastfile_name as f
+    assert f("a.last", 95.0, 100) == "a.last.P95L100"
+    assert f("a.last", 98.5, 0, True) == "a.last.P98_5L0.inverse"
+    assert f("a.last", 0.0, -10) == "a.last.P0L-10"
+
+
+@pytest.mark.gpu
+def test_gpu_filter_matches_reference_golden(golden):
+    from jcvi_b200.formats import blast as gblast
+    d, cases = golden("blast_filter")
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        for c in cases:
+            got = gblast.filter([c["input"], "-o", c["outfile"] + ".gpu"] + c["argv"])
+            assert os.path.basename(got) == c["out"].replace(c["outfile"], c["outfile"] + ".gpu"), c
+            assert read(got) == read(c["out"]), c
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.gpu
+def test_gpu_filter_matches_oracle_on_a_larger_table(tmp_path):
+    import oracle
+    from jcvi_b200 import synth
+    from jcvi_b200.formats import blast as gblast
+    d = str(tmp_path)
+    _, _, text = synth.make_pair(35, 6000, 6000, 500000, Kq=5, Ks=5, self_mode=True)
+    last = os.path.join(d, "A.A.last")
+    open(last, "wb").write(bytes(text))
+    names = sorted({ln.split(b"\t")[0] for ln in bytes(text).split(b"\n")[3:200000:7] if ln})
+    ids = os.path.join(d, "keep.ids")
+    open(ids, "wb").write(b"\n".join(names) + b"\n")
+    for tag, argv in (("orth", ["--pctid=98", "--inverse", "--noself"]),
+                      ("cut", ["--pctid=50", "--hitlen=200", "--score=300", "--evalue=1e-40"]),
+                      ("ids", ["--pctid=30", "--hitlen=0", "--ids=" + ids, "--noself"])):
+        out = last + "." + tag + ".orc"
+        oracle.blast_filter(last, out, **_argv_to_kwargs(argv, d))
+        got = gblast.filter([last, "-o", last + "." + tag] + argv)
+        assert read(got) == read(out), tag
+        assert 1000 < len(read(got)) < len(bytes(text))
+
+
+def _rows(text):
+    """Row spans as Python's universal-newlines text mode yields them ('\\n', '\\r\\n', lone '\\r')."""
+    import re
+    spans, p = [], 0
+    for m in re.finditer(rb"\r\n|\n|\r", text):
+        spans.append((p, m.start()))
+        p = m.end()
+    if p < len(text):
+        spans.append((p, len(text)))
+    return spans
+
+
+def test_kernel_row_decision_on_the_host_equals_glibc(golden):
+    """The kernel's per-row code (jx_fast5.cuh filter_parse / filter_remove, host build, both the fast and the
+    generic route) against the reference's arithmetic (glibc sscanf + C compares) on every row of the golden
+    inputs, for every golden option set (without --ids: that is the name table's business)."""
+    import ctypes
+    import subprocess
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "jcvi_b200", "csrc")
+    so = os.path.join(root, "jcvi_b200", "libjx_hostprobe.so")
+    srcs = [os.path.join(csrc, f) for f in ("jx_hostprobe.cpp", "jx_parse.cuh", "jx_fast5.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
+    L = ctypes.CDLL(so)
+    d, cases = golden("blast_filter")
+    n_fast = n_rows = 0
+    for c in cases:
+        kw = _argv_to_kwargs(c["argv"], d)
+        text = read(os.path.join(d, c["input"]))
+        spans = [(s, e) for s, e in _rows(text) if text[s:s + 1] != b"#"]
+        rs = np.array([s for s, _ in spans], dtype=np.int32)
+        re_ = np.array([e for _, e in spans], dtype=np.int32)
+        out = np.zeros(3 * len(spans), dtype=np.int8)
+        route = np.zeros(len(spans), dtype=np.int8)
+        L.probe_filter_rows(text, len(text), rs.ctypes.data_as(ctypes.c_void_p), re_.ctypes.data_as(ctypes.c_void_p),
+                            ctypes.c_long(len(spans)), ctypes.c_double(kw["score"]), ctypes.c_double(kw["pctid"]),
+                            ctypes.c_longlong(kw["hitlen"]), ctypes.c_double(kw["evalue"]), int(kw["noself"]),
+                            int(kw["inverse"]), out.ctypes.data_as(ctypes.c_void_p), route.ctypes.data_as(ctypes.c_void_p))
+        out = out.reshape(-1, 3)
+        bad = np.nonzero((out[:, 0] != out[:, 2]) | (out[:, 1] != out[:, 2]))[0]
+        assert len(bad) == 0, (c["input"], c["argv"], [(text[spans[i][0]:spans[i][1]], out[i].tolist(), int(route[i])) for i in bad[:5]])
+        n_fast += int(route.sum()); n_rows += len(spans)
+        if not kw["ids"]:                  # and the kept rows are the reference's output
+            kept = b"".join(text[s:e].rstrip() + b"\n" for (s, e), o in zip(spans, out[:, 0]) if o == 1)
+            assert kept == read(os.path.join(d, c["out"])), c
+    assert n_fast > 0.8 * n_rows           # the fast route is the one being exercised
+
+
+def test_exact_strtod_greater_than_cutoff_on_the_host():
+    """jx_parse.cuh dec_gt_double (host build): `strtod(text) > c` for decimals at, next to and half-way between
+    the doubles around c -- the decision `c.evalue > evalue` (blast.py:690) needs.  Python's float() is the
+    correctly rounded conversion glibc's strtod is.  Refusals (-1) are allowed only beyond 19 significant digits."""
+    import ctypes
+    import math
+    import random
+    import struct
+    from decimal import Decimal, getcontext
+    from fractions import Fraction
+    getcontext().prec = 1200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = ctypes.CDLL(os.path.join(root, "jcvi_b200", "libjx_hostprobe.so"))
+    L.probe_gt_double.argtypes = [ctypes.c_char_p, ctypes.c_double]
+    rng = random.Random(11)
+    fixed = [0.0, 0.01, 1e-30, 1e-300, 5e-324, 1.7976931348623157e308, 1e-10, 1.0, 10.0, 1e22, 1e23, 2.0 ** 53,
+             2.2250738585072014e-308]
+
+    def cutoff():
+        k = rng.random()
+        if k < 0.15:
+            return rng.choice(fixed)
+        bits = rng.getrandbits(63)
+        if (bits >> 52) & 0x7FF == 0x7FF:
+            bits &= ~(1 << 62)
+        if k < 0.6:
+            bits = (bits & ((1 << 52) - 1)) | ((1023 + rng.randint(-120, 120)) << 52)
+        return struct.unpack("<d", struct.pack("<Q", bits))[0]
+
+    def text(fr, digits, bump):
+        d = Decimal(fr.numerator) / Decimal(fr.denominator)
+        if d == 0:
+            return "0"
+        _, dig, ex = d.as_tuple()
+        keep = dig[:digits]
+        m = max(int("".join(map(str, keep))) + bump, 0)
+        e = ex + len(dig) - len(keep)
+        return "%de%d" % (m, e) if rng.random() < 0.5 else "%s.%se%d" % (str(m)[0], str(m)[1:] or "0", e + len(str(m)) - 1)
+
+    n = 0
+    for _ in range(400):
+        c = cutoff() * (-1 if rng.random() < 0.2 else 1)
+        ac = abs(c)
+        up = math.nextafter(ac, math.inf)
+        dn = math.nextafter(ac, -math.inf) if ac > 0 else 0.0
+        points = [Fraction(ac), Fraction(dn), (Fraction(ac) + Fraction(dn)) / 2]
+        points += [Fraction(up), (Fraction(ac) + Fraction(up)) / 2] if up != math.inf else [Fraction(ac) + Fraction(2) ** 970]
+        cands = [repr(ac), repr(dn), "1e-400", "2.4703282292062327e-324", "2.4703282292062328e-324", "1e400", "0e10"]
+        for fr in points:
+            for digits in (rng.randint(1, 16), 17, 18, 19, rng.randint(20, 40)):
+                cands += [text(fr, digits, b) for b in (-1, 0, 1)]
+        for s in cands:
+            for t in (s, "-" + s):
+                got = L.probe_gt_double(t.encode(), c)
+                digs = t.lstrip("-").split("e")[0].replace(".", "").lstrip("0")
+                if got == -1:
+                    assert len(digs) > 19, (t, c)
+                else:
+                    assert got == (1 if float(t) > c else 0), (t, c, got)
+                n += 1
+    assert n > 50000

@@ -189,7 +189,7 @@ def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
     assert cat.mcscan(None) == "ref"                                   # untouched
     from jcvi_b200.formats import blast as gblast
     assert cat.cscore is gblast.cscore and importlib.import_module("jcvi.formats.blast").cscore is gblast.cscore
-    assert cat.blast_filter(None) == "ref"                             # untouched
+    assert cat.blast_filter is gblast.filter and importlib.import_module("jcvi.formats.blast").filter is gblast.filter
     assert importlib.import_module("jcvi.compara.synteny").batch_scan is gsyn.batch_scan
     for m in [k for k in sys.modules if k == "jcvi" or k.startswith("jcvi.")]:
         monkeypatch.delitem(sys.modules, m)
