@@ -24,7 +24,10 @@
 #ifndef JX_TOK_MINBLOCKS
 #define JX_TOK_MINBLOCKS 8
 #endif
-constexpr int JX_TOK_THREADS = 128;                      // threads per CTA of the tokenizer
+#ifndef JX_TOK_THREADS_DEF
+#define JX_TOK_THREADS_DEF 128
+#endif
+constexpr int JX_TOK_THREADS = JX_TOK_THREADS_DEF;       // threads per CTA of the tokenizer
 // JX_GROUP threads cooperate on one tile.  128: one 8 KiB tile per CTA (phases separated by CTA
 // barriers).  32: every warp owns its own 1920-byte tiles (+128 bytes of look-ahead = 64 mask words,
 // two per lane) and never waits for another warp.
@@ -36,8 +39,11 @@ constexpr int JX_SEG = 64;                               // bytes of the tile ow
 constexpr int JX_TILE = 30 * JX_SEG;                     // 1920
 constexpr int JX_OVER = 128;                             // look-ahead staged in shared memory
 #else
+#ifndef JX_OVER_DEF
+#define JX_OVER_DEF 1024
+#endif
 constexpr int JX_TILE = JX_GROUP * JX_SEG;               // 8192
-constexpr int JX_OVER = 1024;
+constexpr int JX_OVER = JX_OVER_DEF;
 #endif
 constexpr int JX_WIN = JX_TILE + JX_OVER;
 

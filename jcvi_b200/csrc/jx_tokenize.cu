@@ -211,28 +211,28 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t t = a.tile_begin + atomicAdd(a.ticket, 1u);
-    s_next[0] = t;
-    if (t < a.tile_end) issue(t, 0);
+    // the CTA's first two tiles: both copies in flight at once
+    const uint32_t t0 = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[0] = t0;
+    if (t0 < a.tile_end) issue(t0, 0);
+    const uint32_t t1 = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[1] = t1;
+    if (t1 < a.tile_end) issue(t1, 1);
   }
   gsync();
-  uint32_t tile = s_next[0];
 
-  for (uint32_t it = 0; tile < a.tile_end; ++it) {
-  const int stage = (int)(it & 1u);
+  // ---- prepare(tile): wait for its bytes, classify them, count and locate its line starts, PUBLISH the count ----
+  // Runs one tile AHEAD of the parse (software pipeline, see the loop below): the tile's aggregate is in the
+  // look-back chain before this CTA blocks in the look-back of the tile it is parsing, so no CTA's
+  // publication ever waits behind another CTA's look-back.
+  auto prepare = [&](const uint32_t tile, const int stage, const uint32_t parity, uint32_t& nlines_out, bool& has_bar_out) {
   const uint32_t* smw = reinterpret_cast<const uint32_t*>(s_text[stage]);
   const uint8_t* sm = s_text[stage];
   const int64_t base = (int64_t)tile * JX_TILE;
-  if (tid == 0) {                                 // take the next tile and start its copy
-    const uint32_t t = a.tile_begin + atomicAdd(a.ticket, 1u);
-    s_next[stage ^ 1] = t;
-    if (t < a.tile_end) issue(t, stage ^ 1);
-  }
   // ---- the window: wait for the bulk copy, '\n' beyond the end of the text ---------------------------
   {
     const uint32_t avail = avail_of(tile), bulk = avail & ~15u;
     if (bulk) {
-      const uint32_t parity = (it >> 1) & 1u;
       while (!mbar_try_wait(&s_bar[stage], parity)) {}
     }
     if (avail < (uint32_t)STAGE_BYTES) {          // last tiles of the text only
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     }
     s_term[seg] = term;
   }
-  const bool has_bar = gany((hiacc & 0x80808080u) != 0u);   // may the tile hold a '|' ?  (also: masks visible)
+  has_bar_out = gany((hiacc & 0x80808080u) != 0u);   // may the tile hold a '|' ?  (also: masks visible)
 
   // ---- line starts inside the tile (64 bytes per thread) + block scan ----------------------------------
   unsigned long long starts = 0;
@@ -300,17 +300,19 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
       m &= m - 1;
     }
   }
-
-  // ---- decoupled look-back: global ordinal of the tile's first line ---------------------------------
-  // The tile's own count is published at once; the walk over the predecessors' descriptors is done
-  // by warp 0 AFTER the lines are parsed when every thread holds at most one line (the normal case):
-  // by then the predecessors have published, the walk does not spin, and no warp waits for it
-  // before parsing.  Tiles with more lines than threads resolve their ordinal first.
+  // the tile's own count goes into the look-back chain at once
   if (tid == 0) {
     const uint64_t d = (tile == 0 ? FLAG_INC : FLAG_AGG) | (uint64_t)nlines;
     atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)d);
   }
-  auto look_back = [&]() {      // all 32 lanes of warp 0
+  nlines_out = nlines;
+  };
+
+  // ---- decoupled look-back: global ordinal of the tile's first line ---------------------------------
+  // The walk over the predecessors' descriptors is done by warp 0 AFTER the tile's lines are parsed AND the
+  // next tile's count is published, when every thread holds at most one line (the normal case).  Tiles with
+  // more lines than threads resolve their ordinal first.
+  auto look_back = [&](const uint32_t tile, const uint32_t nlines) {      // all 32 lanes of warp 0
     // LBW windows of 32 descriptors are fetched per round (independent loads, one memory latency).
     // Measured on B200: 1 window 0.0728 ms / 64 MiB, 2: 0.0730, 4: 0.0749, 8: 0.0802 -- wider rounds only
     // add polling traffic, so one window it is.
@@ -364,9 +366,27 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
     }
     if (lane == 0) s_base = excl;
   };
+  // ---- the pipeline: iteration `it` parses tile T[it] (prepared one iteration earlier), then prepares T[it+1],
+  // then resolves T[it]'s ordinal and stores its records.  Tile T[j] lives in stage j & 1; its ticket is
+  // taken (and its copy started) right after the parse of T[j-2] has released that stage.
+  uint32_t tile = a.tile_end, nlines = 0;
+  bool has_bar = false;
+  for (int it = -1;; ++it) {
+  const bool have_cur = it >= 0;                   // uniform; then tile < a.tile_end
+  const int stage = it & 1;
+  const uint32_t* smw = reinterpret_cast<const uint32_t*>(s_text[stage]);
+  const uint8_t* sm = s_text[stage];
+  const int64_t base = (int64_t)tile * JX_TILE;
   const bool defer = nlines <= JX_GROUP;           // uniform over the group
-  if (!defer && warp == 0) look_back();
-  gsync();                                         // line starts (and, if resolved, s_base) visible
+  uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
+  bool have_held = false;
+  uint4 hheld = make_uint4(0u, 0u, 0u, 0u);
+  if (have_cur) {
+  if (!defer) {
+    gsync();                                       // nobody still reads the previous tile's s_base
+    if (warp == 0) look_back(tile, nlines);
+    gsync();
+  }
 
   // ---- parse: one line per thread -----------------------------------------------------------------
   WinReader rd{sm, a.text, base, a.n};
@@ -375,9 +395,6 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   const SmemText B{sm, smw};
   const SideTab TQ{a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob, a.qovh, a.qovr, a.qnov};
   const SideTab TS{a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob, a.sovh, a.sovr, a.snov};
-  uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
-  bool have_held = false;
-  uint4 hheld = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t k0 = 0; k0 < nlines; k0 += JX_GROUP) {
     const uint32_t k = k0 + tid;
     if (k >= nlines) break;
@@ -565,19 +582,36 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
       if (ord < a.rec_cap) { a.recs[ord] = rec; if (NAMES) a.hashes[ord] = hrec; }
     }
   }
-  if (defer) {
-    __syncwarp();
-    if (warp == 0) look_back();
-    gsync();
-    const unsigned long long ord = s_base + tid;
-    if (have_held && ord < a.rec_cap) { a.recs[ord] = held; if (NAMES) a.hashes[ord] = hheld; }
+  gsync();                                         // this stage and the mask / line-start arrays are free again
+  if (tid == 0) {                                  // T[it + 2] goes into the stage just released
+    const uint32_t t = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[stage] = t;
+    if (t < a.tile_end) issue(t, stage);
   }
-  if (tid == 0) {
-    c_lines += nlines;
-    if (s_base + nlines > a.rec_cap) overflow = true;
+  }  // have_cur: parse
+
+  // ---- the next tile: classified, counted and published before this CTA waits for anybody ----------------
+  const uint32_t nxt = s_next[(it + 1) & 1];
+  uint32_t nxt_lines = 0;
+  bool nxt_bar = false;
+  if (nxt < a.tile_end) prepare(nxt, (it + 1) & 1, (uint32_t)((it + 1) >> 1) & 1u, nxt_lines, nxt_bar);
+
+  if (have_cur && defer) {
+    if (warp == 0) look_back(tile, nlines);
   }
-  gsync();                                         // this stage and the scratch arrays are free again
-  tile = s_next[stage ^ 1];
+  gsync();                                         // s_base; the next tile's arrays; s_next
+  if (have_cur) {
+    if (defer) {
+      const unsigned long long ord = s_base + tid;
+      if (have_held && ord < a.rec_cap) { a.recs[ord] = held; if (NAMES) a.hashes[ord] = hheld; }
+    }
+    if (tid == 0) {
+      c_lines += nlines;
+      if (s_base + nlines > a.rec_cap) overflow = true;
+    }
+  }
+  if (nxt >= a.tile_end) break;
+  tile = nxt; nlines = nxt_lines; has_bar = nxt_bar;
   }  // tiles
 
   // ---- counters ---------------------------------------------------------------------------------------
