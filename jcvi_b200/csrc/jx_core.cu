@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include "jx_internal.cuh"
 #include "jx_fast5.cuh"
@@ -290,5 +291,66 @@ int jx_exclusive_sum(jx_ctx* ctx, Arena& arena, const uint32_t* in, uint32_t* ou
   JX_ALLOC(t, uint8_t, tmp, false);
   JX_CK(cub::DeviceScan::ExclusiveSum(t, tmp, in, out, (int)n, ctx->stream));
   ++ctx->launches;
+  return JX_OK;
+}
+
+int jx_exclusive_sum64(jx_ctx* ctx, Arena& arena, const uint32_t* in, uint64_t* out, size_t n) {
+  if (n == 0) return JX_OK;
+  size_t tmp = 0;
+  JX_CK(cub::DeviceScan::ExclusiveScan(nullptr, tmp, in, out, cub::Sum(), (uint64_t)0, (int)n, ctx->stream));
+  JX_ALLOC(t, uint8_t, tmp, false);
+  JX_CK(cub::DeviceScan::ExclusiveScan(t, tmp, in, out, cub::Sum(), (uint64_t)0, (int)n, ctx->stream));
+  ++ctx->launches;
+  return JX_OK;
+}
+
+// Large device -> pageable host copy: 16 MiB chunks through two pinned staging halves; while chunk c + 1 crosses
+// PCIe, chunk c is copied from staging into `host` by a few host threads (a plain cudaMemcpy to pageable memory
+// runs at a fraction of the link rate and first-touches every page on one thread).
+int jx_d2h_big(jx_ctx* ctx, char* host, const uint8_t* dev, size_t bytes) {
+  constexpr size_t CH = 16u << 20;
+  if (bytes <= (1u << 20)) {
+    JX_CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    return JX_OK;
+  }
+  char* stage = nullptr;
+  int rc;
+  if ((rc = jx_pin_small(ctx, 2 * CH, &stage))) return rc;
+  cudaEvent_t ev[2];
+  JX_CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  JX_CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  const size_t nch = (bytes + CH - 1) / CH;
+  const unsigned hw = std::thread::hardware_concurrency();
+  const unsigned nt = std::max(1u, std::min(4u, hw ? hw : 1u));
+  auto drain = [&](size_t c) {                     // staging half of chunk c -> host
+    const size_t o = c * CH, len = std::min(CH, bytes - o);
+    const char* src = stage + (c & 1) * CH;
+    if (nt == 1 || len < (4u << 20)) { memcpy(host + o, src, len); return; }
+    std::vector<std::thread> th;
+    const size_t part = ((len + nt - 1) / nt + 4095) & ~(size_t)4095;
+    for (unsigned t = 0; t < nt; ++t) {
+      const size_t a = (size_t)t * part;
+      if (a >= len) break;
+      const size_t l = std::min(part, len - a);
+      th.emplace_back([=]() { memcpy(host + o + a, src + a, l); });
+    }
+    for (auto& x : th) x.join();
+  };
+  cudaError_t err = cudaSuccess;
+  for (size_t c = 0; c < nch && err == cudaSuccess; ++c) {
+    const size_t o = c * CH, len = std::min(CH, bytes - o);
+    if (c >= 2) { /* the half is free: chunk c - 2 was drained before chunk c - 1 was waited for */ }
+    err = cudaMemcpyAsync(stage + (c & 1) * CH, dev + o, len, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaEventRecord(ev[c & 1], ctx->stream);
+    if (c >= 1 && err == cudaSuccess) {
+      err = cudaEventSynchronize(ev[(c - 1) & 1]);
+      if (err == cudaSuccess) drain(c - 1);
+    }
+  }
+  if (err == cudaSuccess) err = cudaEventSynchronize(ev[(nch - 1) & 1]);
+  if (err == cudaSuccess) drain(nch - 1);
+  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  if (err != cudaSuccess) { ctx->err = std::string("jx_d2h_big: ") + cudaGetErrorString(err); return JX_ECUDA; }
   return JX_OK;
 }

@@ -389,8 +389,8 @@ int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nb
   JX_ALLOC(packed, uint8_t, (size_t)total, false);
   JX_LAUNCH(k_copy_lines, nblk((size_t)cnt * 32), 256, 0, d_text, off, (const uint32_t*)nullptr, len, pos, cnt, packed);
   char* host = (char*)malloc((size_t)total + 1);
-  JX_CK(cudaMemcpyAsync(host, packed, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (!host) { ctx->err = "out of host memory"; return JX_EINTERNAL; }
+  if ((rc = jx_d2h_big(ctx, host, packed, (size_t)total))) { free(host); return rc; }
   host[total] = 0;
   *out = host; *out_len = (int64_t)total;
   return JX_OK;

@@ -223,6 +223,9 @@ struct Arena {
 int jx_sort_pairs(jx_ctx* ctx, Arena& arena, uint64_t*& keys, uint32_t*& vals, size_t n, int begin_bit, int end_bit);
 int jx_sort_keys(jx_ctx* ctx, Arena& arena, uint64_t*& keys, size_t n, int begin_bit, int end_bit);
 int jx_exclusive_sum(jx_ctx* ctx, Arena& arena, const uint32_t* in, uint32_t* out, size_t n);
+int jx_exclusive_sum64(jx_ctx* ctx, Arena& arena, const uint32_t* in, uint64_t* out, size_t n);
+// device -> pageable host, pipelined through pinned staging (stream-synchronous on return)
+int jx_d2h_big(jx_ctx* ctx, char* host, const uint8_t* dev, size_t bytes);
 inline int jx_bits(uint64_t maxval) { int b = 1; while (b < 64 && (maxval >> b)) ++b; return b; }
 
 // ---- tokenizer (jx_tokenize.cu) -----------------------------------------------------------------

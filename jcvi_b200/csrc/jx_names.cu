@@ -41,13 +41,23 @@ __global__ void k_take_reps(const uint32_t* __restrict__ vals, const uint32_t* _
   side[pos[t]] = (uint8_t)(v & 1u);
 }
 
-__global__ void k_keep_flags(const uint4* __restrict__ recs, uint32_t n, uint32_t* flag) {
+// formats.blast filter: the tokenizer's filter-mode records are {keep, rstripped length, 64-bit row offset}
+__global__ void k_kept_len(const uint4* __restrict__ recs, uint32_t n, uint32_t* len) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = recs[i].x != JX_NOREC ? 1u : 0u;
+  if (i < n) { const uint4 r = recs[i]; len[i] = r.x == 1u ? r.y + 1u : 0u; }      // + '\n'
 }
-__global__ void k_keep_idx(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n, uint32_t* idx) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flag[i]) idx[pos[i]] = i;
+// one warp per row
+__global__ void k_copy_kept(const uint8_t* __restrict__ text, const uint4* __restrict__ recs, const uint64_t* __restrict__ pos,
+                            uint32_t n, uint8_t* out) {
+  const uint32_t w = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const uint4 r = recs[w];
+  if (r.x != 1u) return;
+  const uint8_t* src = text + (((uint64_t)r.w << 32) | r.z);
+  uint8_t* dst = out + pos[w];
+  const uint32_t L = r.y;
+  for (uint32_t i = lane; i < L; i += 32) dst[i] = src[i];
+  if (lane == 0) dst[L] = '\n';
 }
 
 }  // namespace
@@ -81,23 +91,25 @@ int jx_blast_filter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_d
     stats[3] = (int64_t)tok.stats[1];                    // '#' lines
   }
   const uint32_t n = tok.n_lines;
-  uint32_t cnt = 0;
-  uint32_t* idx = nullptr;
-  if (n) {
-    JX_ALLOC(flag, uint32_t, n, false);
-    JX_ALLOC(pos, uint32_t, n, false);
-    JX_LAUNCH(k_keep_flags, nblk(n), 256, 0, tok.recs, n, flag);
-    if ((rc = jx_exclusive_sum(ctx, arena, flag, pos, n))) return rc;
-    uint32_t h[2];
-    JX_CK(cudaMemcpyAsync(&h[0], pos + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(&h[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaStreamSynchronize(ctx->stream));
-    cnt = h[0] + h[1];
-    JX_ALLOC(ix, uint32_t, (size_t)cnt + 1, false);
-    if (cnt) JX_LAUNCH(k_keep_idx, nblk(n), 256, 0, flag, pos, n, ix);
-    idx = ix;
-  }
-  return jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, idx, cnt, out, out_len, 1);
+  if (!n) { *out = (char*)calloc(1, 1); return JX_OK; }
+  JX_ALLOC(len, uint32_t, n, false);
+  JX_ALLOC(pos, uint64_t, n, false);
+  JX_LAUNCH(k_kept_len, nblk(n), 256, 0, tok.recs, n, len);
+  if ((rc = jx_exclusive_sum64(ctx, arena, len, pos, n))) return rc;
+  uint64_t hp = 0; uint32_t hl = 0;
+  JX_CK(cudaMemcpyAsync(&hp, pos + n - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&hl, len + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  const uint64_t total = hp + hl;
+  if (!total) { *out = (char*)calloc(1, 1); return JX_OK; }
+  JX_ALLOC(packed, uint8_t, (size_t)total, false);
+  JX_LAUNCH(k_copy_kept, nblk((size_t)n * 32), 256, 0, tok.d_text, tok.recs, pos, n, packed);
+  char* host = (char*)malloc((size_t)total + 1);
+  if (!host) { ctx->err = "out of host memory"; return JX_EINTERNAL; }
+  if ((rc = jx_d2h_big(ctx, host, packed, (size_t)total))) { free(host); return rc; }
+  host[total] = 0;
+  *out = host; *out_len = (int64_t)total;
+  return JX_OK;
 }
 
 int jx_distinct_names(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, uint32_t seed,

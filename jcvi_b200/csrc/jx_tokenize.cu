@@ -437,7 +437,14 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
             noids = !(inq && ins);
           }
           const bool remove = jx::filter_remove(rd, ff, a.f_score, a.f_pctid, a.f_hitlen, noids, a.f_inverse != 0, a.f_noself != 0);
-          if (!remove) { rec.x = 1u; ++c_mapped; } else ++c_unmapped;
+          if (!remove) {
+            // filter-mode record: {1, length of row.rstrip(), 64-bit offset of the row in the text}
+            int r = e;                                   // str.rstrip(): ASCII white space and 0x1c-0x1f
+            while (r > s) { const uint32_t ch = rd(r - 1); if (jx::is_space(ch) || (ch - 0x1Cu) <= 3u) --r; else break; }
+            const unsigned long long o = (unsigned long long)(base + s);
+            rec = make_uint4(1u, (uint32_t)(r - s), (uint32_t)o, (uint32_t)(o >> 32));
+            ++c_mapped;
+          } else ++c_unmapped;
         }
       }
     } else if (s < e) {

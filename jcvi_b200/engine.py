@@ -213,8 +213,11 @@ class Engine(object):
             self.lib.jx_free(out); self.lib.jx_free(bout)
         return a, b, dict(zip(("lines", "named", "short", "comments"), list(st)))
 
-    def blast_filter(self, text, score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, inverse=False, ids=None):
-        """`jcvi.formats.blast filter` -> (bytes of the kept rows, stats).  ids: iterable of names (bytes) or None."""
+    def blast_filter(self, text, score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, inverse=False, ids=None,
+                     sink=None):
+        """`jcvi.formats.blast filter` -> (bytes of the kept rows, stats).  ids: iterable of names (bytes) or None.
+        sink: a binary file object; the rows are then written to it straight from the library's buffer (no Python
+        copy of a multi-GB result) and b"" is returned in their place."""
         use_ids = bool(ids)
         if use_ids:
             self.load_names(sorted(set(ids)))
@@ -224,7 +227,12 @@ class Engine(object):
                                       int(bool(noself)), int(bool(inverse)), int(use_ids), ctypes.byref(out), ctypes.byref(ln), st)
         try:
             self._check(rc)
-            a = ctypes.string_at(out, ln.value) if ln.value else b""
+            if sink is not None:
+                if ln.value:
+                    sink.write(memoryview((ctypes.c_char * ln.value).from_address(out.value)))
+                a = b""
+            else:
+                a = ctypes.string_at(out, ln.value) if ln.value else b""
         finally:
             self.lib.jx_free(out)
         return a, dict(zip(("rows", "kept", "removed", "comments"), list(st)))

@@ -119,11 +119,11 @@ def filter(args):
                 continue
             ids.update(row.replace(b",", b"\t").split())
     (blastfile,) = args
-    out, _ = get_engine().blast_filter(read_text_file(blastfile), score=opts.score, pctid=opts.pctid, hitlen=opts.hitlen,
-                                       evalue=opts.evalue, noself=opts.noself, inverse=opts.inverse, ids=ids)
     newblastfile = filtered_blastfile_name(opts.outfile or blastfile, opts.pctid, opts.hitlen, opts.inverse)
+    text = read_text_file(blastfile)
     with open(newblastfile, "wb") as fw:
-        fw.write(out)
+        get_engine().blast_filter(text, score=opts.score, pctid=opts.pctid, hitlen=opts.hitlen, evalue=opts.evalue,
+                                  noself=opts.noself, inverse=opts.inverse, ids=ids, sink=fw)
     return newblastfile
 
 

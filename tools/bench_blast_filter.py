@@ -13,20 +13,21 @@ w = bench.make_workload(100, hits)
 text = w["text"]
 eng = get_engine(0)
 pin = torch.from_numpy(text).pin_memory()
+devnull = open(os.devnull, 'wb')
 sets = (("catalog.ortholog's --pctid=98 --inverse --noself", dict(pctid=98.0, inverse=True, noself=True)),
         ("--pctid=60 --hitlen=150 --score=400 --evalue=1e-30", dict(pctid=60.0, hitlen=150, score=400, evalue=1e-30)))
 for tag, kw in sets:
     for rep in range(3):
         t0 = time.perf_counter()
-        out, st = eng.blast_filter(pin.numpy(), **kw)
+        out, st = eng.blast_filter(pin.numpy(), sink=devnull, **kw)
         t1 = time.perf_counter()
-    print("%s | host buffer in, rows out: %.1f ms = %.3g hits/s (%d of %d rows kept, %.1f MB out)" % (
-        tag, (t1 - t0) * 1e3, w["n_hits"] / (t1 - t0), st["kept"], st["rows"], len(out) / 1e6))
+    print("%s | host buffer in, rows out: %.1f ms = %.3g hits/s (%d of %d rows kept)" % (
+        tag, (t1 - t0) * 1e3, w["n_hits"] / (t1 - t0), st["kept"], st["rows"]))
     dev = eng.upload(pin)
     for rep in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out, st = eng.blast_filter(dev, **kw)
+        out, st = eng.blast_filter(dev, sink=devnull, **kw)
         t1 = time.perf_counter()
     eng.release_text()
     tt = eng.tokenizer_timing()
