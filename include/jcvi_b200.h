@@ -220,6 +220,14 @@ int jx_cscore_finish(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_le
 int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
                   const int32_t* a_qi, const int32_t* a_si, int64_t n_anchor_lines, char** lines,
                   int64_t* lines_len, int64_t* n_lines);
+/* The same two calls with the packed lines LEFT ON THE DEVICE (for ranks that exchange them GPU to GPU over
+ * NVLink instead of through host memory): *lines_dev is a device pointer into a context-owned buffer, valid
+ * until the next jx_*_device call on the context; nothing to free.  jx_near_lines(_device) on the slice that
+ * jx_cscore_begin just tokenized (same held text, no exclusions, not a self comparison) re-uses its records. */
+int jx_cscore_finish_device(jx_ctx* ctx, double cscore, uint64_t* lines_dev, int64_t* lines_len, int64_t* n_lines);
+int jx_near_lines_device(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                         const int32_t* a_qi, const int32_t* a_si, int64_t n_anchor_lines, uint64_t* lines_dev,
+                         int64_t* lines_len, int64_t* n_out);
 void jx_free(void* p);
 
 /* ---- jcvi.formats.blast cscore (src/jcvi/formats/blast.py:1098-1189) ------------

@@ -62,7 +62,7 @@ EXPORTS = [
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
     "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse", "jx_distinct_names", "jx_best_table_copy", "jx_session_counts",
     "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter",
-    "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_free", "jx_abi_sizes",
+    "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
 ]
 
 _lib = None
@@ -130,6 +130,9 @@ def lib():
         L.jx_cscore_finish.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p), c_i64p, c_i64p]
         L.jx_near_lines.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), c_i64p, c_i64p]
+        L.jx_cscore_finish_device.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_uint64), c_i64p, c_i64p]
+        L.jx_near_lines_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64), c_i64p, c_i64p]
         L.jx_free.argtypes = [ctypes.c_void_p]
         L.jx_free.restype = None
         sizes = (ctypes.c_int32 * 6)()

@@ -71,6 +71,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
   cudaFree(ctx->held_text);
+  cudaFree(ctx->lines_dev);
   if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
   if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
   if (ctx->ws) cudaFree(ctx->ws);

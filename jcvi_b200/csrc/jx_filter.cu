@@ -370,9 +370,11 @@ __global__ void k_line_off(const uint32_t* idx, uint32_t cnt, const uint4* recs,
 }  // namespace
 
 int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
-                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip) {
-  *out = nullptr; *out_len = 0;
-  if (!cnt) { *out = (char*)calloc(1, 1); return JX_OK; }
+                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip, uint64_t* dev_out) {
+  if (out) *out = nullptr;
+  *out_len = 0;
+  if (dev_out) *dev_out = 0;
+  if (!cnt) { if (!dev_out) *out = (char*)calloc(1, 1); return JX_OK; }
   int rc;
   JX_ALLOC(off, uint64_t, cnt, false);
   JX_ALLOC(len, uint32_t, cnt, false);
@@ -386,6 +388,19 @@ int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nb
   JX_CK(cudaStreamSynchronize(ctx->stream));
   const uint64_t total = (uint64_t)h[0] + h[1];
   if (total >= 0xFFFFFFF0ull) { ctx->err = "gathered lines exceed 4 GiB; use more ranks"; return JX_EUNSUPPORTED; }
+  if (dev_out) {                                   // context-owned device result (valid until the next one)
+    if (ctx->lines_dev_cap < total + 16) {
+      JX_CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->lines_dev); ctx->lines_dev = nullptr; ctx->lines_dev_cap = 0;
+      const size_t cap = (size_t)(total + total / 4 + (1u << 20));
+      JX_CK(cudaMalloc((void**)&ctx->lines_dev, cap));
+      ctx->lines_dev_cap = cap;
+    }
+    JX_LAUNCH(k_copy_lines, nblk((size_t)cnt * 32), 256, 0, d_text, off, (const uint32_t*)nullptr, len, pos, cnt, ctx->lines_dev);
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    *dev_out = (uint64_t)(uintptr_t)ctx->lines_dev; *out_len = (int64_t)total;
+    return JX_OK;
+  }
   JX_ALLOC(packed, uint8_t, (size_t)total, false);
   JX_LAUNCH(k_copy_lines, nblk((size_t)cnt * 32), 256, 0, d_text, off, (const uint32_t*)nullptr, len, pos, cnt, packed);
   char* host = (char*)malloc((size_t)total + 1);
@@ -437,8 +452,17 @@ int jx_cscore_begin(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_d
   return JX_OK;
 }
 
+static int cscore_finish_impl(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_len, int64_t* n_lines, uint64_t* dev_out);
 int jx_cscore_finish(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_len, int64_t* n_lines) {
   if (!ctx || !lines || !lines_len || !n_lines) return JX_EARG;
+  return cscore_finish_impl(ctx, cscore, lines, lines_len, n_lines, nullptr);
+}
+int jx_cscore_finish_device(jx_ctx* ctx, double cscore, uint64_t* lines_dev, int64_t* lines_len, int64_t* n_lines) {
+  if (!ctx || !lines_dev || !lines_len || !n_lines) return JX_EARG;
+  char* unused = nullptr;
+  return cscore_finish_impl(ctx, cscore, &unused, lines_len, n_lines, lines_dev);
+}
+static int cscore_finish_impl(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_len, int64_t* n_lines, uint64_t* dev_out) {
   if (!ctx->sess_open || !ctx->cache.valid) { ctx->err = "jx_cscore_finish without jx_cscore_begin"; return JX_EARG; }
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
@@ -466,11 +490,11 @@ int jx_cscore_finish(jx_ctx* ctx, double cscore, char** lines, int64_t* lines_le
     if (cnt) JX_LAUNCH(k_compact_idx, nblk(n), 256, 0, flags, pos, n, ix);
     idx = ix;
   }
-  rc = jx_gather_lines(ctx, arena, c.text, c.nbytes, c.desc, c.ntiles, c.recs, idx, cnt, lines, lines_len);
+  rc = jx_gather_lines(ctx, arena, c.text, c.nbytes, c.desc, c.ntiles, c.recs, idx, cnt, lines, lines_len, 0, dev_out);
   if (rc) return rc;
   *n_lines = cnt;
   ctx->sess_open = false;
-  c.valid = false;
+  c.valid = c.plain;          // plain records stay for jx_near_lines / jx_liftover_text on the same held text
   return JX_OK;
 }
 

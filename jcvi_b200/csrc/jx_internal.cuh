@@ -94,6 +94,7 @@ struct jx_ctx {
     uint4* recs = nullptr; size_t recs_cap = 0;       // context-owned, grow-only
     uint64_t* desc = nullptr; size_t desc_cap = 0;
     bool valid = false;
+    bool plain = false;       // records of a non-self pass without exclusions or the near-diagonal rule: any stage may reuse them
     const uint8_t* text = nullptr; int64_t nbytes = 0; int strip = 0;
     int64_t ntiles = 0; uint32_t n_lines = 0;
     unsigned long long stats[12] = {0};
@@ -103,6 +104,8 @@ struct jx_ctx {
   int64_t token_counter = 0;
   uint32_t* sess_best = nullptr; size_t sess_best_cap = 0;   // jx_cscore_begin/finish session
   bool sess_open = false;
+  uint8_t* lines_dev = nullptr;  // grow-only device buffer of the last jx_*_device result (packed raw lines)
+  size_t lines_dev_cap = 0;
   char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text
   size_t pin_cap = 0;
   char* pin_small = nullptr;     // grow-only pinned staging for small result arrays (one D2H instead of several pageable ones)
@@ -262,7 +265,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
 
 // raw text lines of the records rec_idx[0..cnt) (device array, file order) -> malloc'ed host buffer
 int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
-                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip = 0);
+                    const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip = 0,
+                    uint64_t* dev_out = nullptr);   // dev_out: leave the packed lines in ctx->lines_dev instead (no host copy)
 
 // ---- shared device helpers ---------------------------------------------------------------------
 #if defined(__CUDACC__)

@@ -490,7 +490,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   unsigned long long tstats[12];
   {
     auto& c = ctx->cache;
-    if (c.valid && text_on_device && (const uint8_t*)text == c.text && nbytes == c.nbytes && (strip_names != 0) == (c.strip != 0) &&
+    if (c.valid && c.plain && text_on_device && (const uint8_t*)text == c.text && nbytes == c.nbytes && (strip_names != 0) == (c.strip != 0) &&
         !ctx->is_self) {
       recs = c.recs; n_lines = c.n_lines;
       memcpy(tstats, c.stats, sizeof tstats);
@@ -726,9 +726,25 @@ __global__ void k_narrow_idx(const uint64_t* in, uint32_t n, uint32_t* out) {
 }
 }  // namespace
 
+static int near_lines_impl(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                           const int32_t* a_qi, const int32_t* a_si, int64_t n_lines64, char** lines, int64_t* lines_len,
+                           int64_t* n_out, uint64_t* dev_out);
 int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
                   const int32_t* a_qi, const int32_t* a_si, int64_t n_lines64, char** lines, int64_t* lines_len,
                   int64_t* n_out) {
+  if (!lines) return JX_EARG;
+  return near_lines_impl(ctx, text, nbytes, text_on_device, strip_names, dist, a_qi, a_si, n_lines64, lines, lines_len, n_out, nullptr);
+}
+int jx_near_lines_device(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                         const int32_t* a_qi, const int32_t* a_si, int64_t n_lines64, uint64_t* lines_dev, int64_t* lines_len,
+                         int64_t* n_out) {
+  if (!lines_dev) return JX_EARG;
+  char* unused = nullptr;
+  return near_lines_impl(ctx, text, nbytes, text_on_device, strip_names, dist, a_qi, a_si, n_lines64, &unused, lines_len, n_out, lines_dev);
+}
+static int near_lines_impl(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist,
+                           const int32_t* a_qi, const int32_t* a_si, int64_t n_lines64, char** lines, int64_t* lines_len,
+                           int64_t* n_out, uint64_t* dev_out) {
   if (!ctx || !lines || !lines_len || !n_out || n_lines64 < 0 || n_lines64 >= (1ll << 31) || dist < 0) return JX_EARG;
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
@@ -737,17 +753,28 @@ int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_dev
   *lines = nullptr; *lines_len = 0; *n_out = 0;
   int rc;
   const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
-  TokMode mode;
-  mode.strip = strip_names;
-  mode.neardiag = ctx->is_self ? 1 : 0;
+  if (dev_out) *dev_out = 0;
   TokOut tok;
-  if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+  {
+    auto& c = ctx->cache;                   // records of the same held slice (jx_cscore_begin / jx_blastfilter), one-shot
+    if (c.valid && c.plain && text_on_device && (const uint8_t*)text == c.text && nbytes == c.nbytes &&
+        (strip_names != 0) == (c.strip != 0) && !ctx->is_self) {
+      tok.recs = c.recs; tok.desc = c.desc; tok.ntiles = c.ntiles; tok.n_lines = c.n_lines; tok.d_text = c.text; tok.nbytes = c.nbytes;
+      memcpy(tok.stats, c.stats, sizeof tok.stats);
+      c.valid = false;
+    } else {
+      TokMode mode;
+      mode.strip = strip_names;
+      mode.neardiag = ctx->is_self ? 1 : 0;
+      if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+    }
+  }
   std::vector<uint64_t> akeys_h;
   for (int64_t t = 0; t < n_lines64; ++t)
     if (a_qi[t] >= 0 && a_si[t] >= 0 && a_qi[t] < Q.G && a_si[t] < S.G)
       akeys_h.push_back(((uint64_t)(uint32_t)a_qi[t] << sb) | (uint32_t)a_si[t]);
   const uint32_t na = (uint32_t)akeys_h.size();
-  if (!na || !tok.stats[2]) { *lines = (char*)calloc(1, 1); return JX_OK; }
+  if (!na || !tok.stats[2]) { if (!dev_out) *lines = (char*)calloc(1, 1); return JX_OK; }
   JX_ALLOC(akey, uint64_t, na, false);
   JX_CK(cudaMemcpyAsync(akey, akeys_h.data(), (size_t)na * 8, cudaMemcpyHostToDevice, ctx->stream));
   uint64_t* aks = akey;
@@ -784,7 +811,7 @@ int jx_near_lines(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_dev
     if ((rc = jx_sort_keys(ctx, arena, ks, nC, 0, 32))) return rc;
     JX_LAUNCH(k_narrow_idx, nblk(nC), 256, 0, ks, nC, idx);
   }
-  if ((rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, idx, nC, lines, lines_len))) return rc;
+  if ((rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, idx, nC, lines, lines_len, 0, dev_out))) return rc;
   *n_out = nC;
   return JX_OK;
 }

@@ -798,7 +798,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   ctx->tok_lines += (int64_t)out.stats[0];
   if (to_cache && !out.stats[4] && !out.stats[5] && !out.stats[10] && !out.stats[11]) {
     auto& c = ctx->cache;
-    c.valid = true; c.text = d_text; c.nbytes = nbytes; c.strip = mode.strip; c.ntiles = ntiles; c.n_lines = out.n_lines;
+    c.valid = true; c.plain = !ctx->is_self && mode.n_excl == 0 && !mode.neardiag; c.text = d_text; c.nbytes = nbytes; c.strip = mode.strip; c.ntiles = ntiles; c.n_lines = out.n_lines;
     memcpy(c.stats, out.stats, sizeof c.stats);
   }
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }

@@ -393,18 +393,43 @@ class Engine(object):
         finally:
             self.lib.jx_free(buf)
 
-    def cscore_finish(self, cscore):
-        """-> (uint8 array of the slice's raw lines that pass the C-score filter, file order; count)."""
-        buf = ctypes.c_void_p(); ln = ctypes.c_int64(); cnt = ctypes.c_int64()
+    def _device_lines(self, ptr, nbytes):
+        """torch uint8 view of a context-owned device result (valid until the next *_device call)."""
+        import torch
+
+        class _Dev(object):
+            pass
+        if not nbytes:
+            return torch.empty(0, dtype=torch.uint8, device="cuda:%d" % self.device)
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(d, device="cuda:%d" % self.device)
+
+    def cscore_finish(self, cscore, device=False):
+        """-> (uint8 array of the slice's raw lines that pass the C-score filter, file order; count).
+        device=True: a torch CUDA tensor viewing the library's device buffer instead (no host copy)."""
+        ln = ctypes.c_int64(); cnt = ctypes.c_int64()
+        if device:
+            dptr = ctypes.c_uint64()
+            self._check(self.lib.jx_cscore_finish_device(self.ctx, float(cscore or 0.0), ctypes.byref(dptr), ctypes.byref(ln), ctypes.byref(cnt)))
+            return self._device_lines(dptr.value, ln.value), cnt.value
+        buf = ctypes.c_void_p()
         self._check(self.lib.jx_cscore_finish(self.ctx, float(cscore or 0.0), ctypes.byref(buf), ctypes.byref(ln), ctypes.byref(cnt)))
         return self._take_lines(buf, ln), cnt.value
 
-    def near_lines(self, text, a_qi, a_si, strip_names=True, dist=10):
-        """-> (uint8 array of the raw lines whose hit lies within `dist` of an anchor; count)."""
+    def near_lines(self, text, a_qi, a_si, strip_names=True, dist=10, device=False):
+        """-> (uint8 array of the raw lines whose hit lies within `dist` of an anchor; count).
+        device=True: a torch CUDA tensor viewing the library's device buffer instead."""
         p, n, dev, keep = _text_ptr(text)
         a_qi = np.ascontiguousarray(a_qi, dtype=np.int32)
         a_si = np.ascontiguousarray(a_si, dtype=np.int32)
-        buf = ctypes.c_void_p(); ln = ctypes.c_int64(); cnt = ctypes.c_int64()
+        ln = ctypes.c_int64(); cnt = ctypes.c_int64()
+        if device:
+            dptr = ctypes.c_uint64()
+            self._check(self.lib.jx_near_lines_device(self.ctx, p, n, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si),
+                                                      len(a_qi), ctypes.byref(dptr), ctypes.byref(ln), ctypes.byref(cnt)))
+            return self._device_lines(dptr.value, ln.value), cnt.value
+        buf = ctypes.c_void_p()
         self._check(self.lib.jx_near_lines(self.ctx, p, n, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si),
                                            len(a_qi), ctypes.byref(buf), ctypes.byref(ln), ctypes.byref(cnt)))
         return self._take_lines(buf, ln), cnt.value

@@ -62,6 +62,43 @@ def _gather_bytes(arr, dst=0, device=None):
     return [bufs[r][: sizes[r]].cpu().numpy() for r in range(world)]
 
 
+def _gather_device(t, dst=0, device=None):
+    """Gather variable-length CUDA uint8 tensors on rank `dst` into ONE contiguous CUDA tensor (rank order) with
+    point-to-point NCCL transfers straight into their final place: the lines never touch host memory.
+    Returns None on the other ranks."""
+    import torch
+    import torch.distributed as dist
+    rank, world = rank_world()
+    dev = torch.device("cuda", device if device is not None else torch.cuda.current_device())
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = t.numel()
+    dist.all_reduce(sizes)
+    sizes = sizes.tolist()
+    ops, out = [], None
+    if rank == dst:
+        out = torch.empty(max(sum(sizes), 1), dtype=torch.uint8, device=dev)
+        off = 0
+        for r in range(world):
+            if r == rank:
+                out[off:off + sizes[r]].copy_(t)
+            elif sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, out[off:off + sizes[r]], r))
+            off += sizes[r]
+    elif t.numel():
+        ops.append(dist.P2POp(dist.isend, t, dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    torch.cuda.current_stream(dev).synchronize()      # the library reads `out` on its own stream next
+    return out[: sum(sizes)] if rank == dst else None
+
+
+def _use_device_exchange():
+    import torch.distributed as dist
+    _, world = rank_world()
+    return world > 1 and dist.is_initialized() and dist.get_backend() == "nccl"
+
+
 def _as_u8(text):
     """numpy view of the text; torch CPU tensors (pinned or not) are viewed without a copy."""
     if hasattr(text, "numpy") and hasattr(text, "is_cuda") and not text.is_cuda:
@@ -92,11 +129,17 @@ def blastfilter_sharded(text, qbed, sbed, is_self, strip_names=True, cscore=0.7,
         best = eng.best_table_tensor(ptr, n)
         dist.all_reduce(best, op=dist.ReduceOp.MAX)          # ncclAllReduce(max) over NVLink, in place
         torch.cuda.synchronize(eng.device)
-    lines, cnt = eng.cscore_finish(cscore)
-    parts = _gather_bytes(lines, device=eng.device)
-    if rank != 0:
-        return None
-    merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    if _use_device_exchange():                               # survivors go GPU to GPU over NVLink
+        lines, cnt = eng.cscore_finish(cscore, device=True)
+        merged = _gather_device(lines, device=eng.device)
+        if rank != 0:
+            return None
+    else:
+        lines, cnt = eng.cscore_finish(cscore)
+        parts = _gather_bytes(lines, device=eng.device)
+        if rank != 0:
+            return None
+        merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
     # survivors only: the C-score filter is done, exclusions were applied while tokenizing
     return eng.blastfilter(merged, strip_names=strip_names, cscore=0, tandem_Nmax=tandem_Nmax, want_text=want_text)
 
@@ -108,9 +151,15 @@ def liftover_sharded(text, a_qi, a_si, a_block, qbed, sbed, is_self, strip_names
     eng.load_pair(qbed, sbed, is_self)
     text, owner = _as_u8(text)
     lo, hi = slice_bounds(text, rank, world)
-    lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist)
-    parts = _gather_bytes(lines, device=eng.device)
-    if rank != 0:
-        return None
-    merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    if _use_device_exchange():
+        lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist, device=True)
+        merged = _gather_device(lines, device=eng.device)
+        if rank != 0:
+            return None
+    else:
+        lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist)
+        parts = _gather_bytes(lines, device=eng.device)
+        if rank != 0:
+            return None
+        merged = np.concatenate(parts) if len(parts) > 1 else parts[0]
     return eng.liftover_text(merged, a_qi, a_si, a_block, strip_names=strip_names, dist=dist)
