@@ -153,3 +153,28 @@ def as_np(p, n, dtype):
     if n == 0 or not p:
         return np.zeros(0, dtype=dtype)
     return np.ctypeslib.as_array(p, shape=(n,)).astype(dtype, copy=True)
+
+
+class _Owner(object):
+    """Keeps a library result alive for the numpy views taken from it; frees it when the last view is gone."""
+
+    def __init__(self, free, struct):
+        self._free, self._struct = free, struct
+
+    def __del__(self):
+        try:
+            self._free(ctypes.byref(self._struct))
+        except Exception:
+            pass
+
+
+def view_np(p, n, dtype, owner):
+    """numpy VIEW of a library-owned array (no copy): the ctypes buffer object the ndarray is based on holds a
+    reference to `owner`, so the memory lives exactly as long as somebody can reach it."""
+    if n == 0 or not p:
+        return np.zeros(0, dtype=dtype)
+    dt = np.dtype(dtype)
+    buf = (ctypes.c_char * (int(n) * dt.itemsize)).from_address(ctypes.cast(p, ctypes.c_void_p).value)
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dt, count=int(n))
+

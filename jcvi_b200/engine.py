@@ -79,15 +79,19 @@ class ScanResult(object):
 
 
 class LiftoverResult(object):
-    def __init__(self, r, n_lines):
+    """Views (no copies) of the library's result arrays -- 1.7 M lifted pairs at C3 size are 27 MB that need not
+    be copied and page-faulted again; the result is freed when the last array is unreachable."""
+
+    def __init__(self, r, n_lines, lib):
+        own = C._Owner(lib.jx_liftover_result_free, r)
         n = r.n_lifted
         self.n_lifted = n
-        self.q_rank = C.as_np(r.q_rank, n, np.int32)
-        self.s_rank = C.as_np(r.s_rank, n, np.int32)
-        self.score = C.as_np(r.score, n, np.float32)
-        self.block = C.as_np(r.block, n, np.int32)
-        self.accepted = C.as_np(r.accepted, n_lines, np.uint8)
-        self.raw_score = C.as_np(r.raw_score, n_lines, np.float32)
+        self.q_rank = C.view_np(r.q_rank, n, np.int32, own)
+        self.s_rank = C.view_np(r.s_rank, n, np.int32, own)
+        self.score = C.view_np(r.score, n, np.float32, own)
+        self.block = C.view_np(r.block, n, np.int32, own)
+        self.accepted = C.view_np(r.accepted, n_lines, np.uint8, own)
+        self.raw_score = C.view_np(r.raw_score, n_lines, np.float32, own)
         self.stats = dict(zip(("lines", "hits", "anchors", "lifted", "tree_walked", "comments"), list(r.stats)[:6]))
 
 
@@ -349,11 +353,10 @@ class Engine(object):
         r = C.JxLiftoverResult()
         rc = self.lib.jx_liftover_text(self.ctx, p, n, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si),
                                        C.ptr(a_block), len(a_qi), ctypes.byref(r))
-        try:
-            self._check(rc)
-            return LiftoverResult(r, len(a_qi))
-        finally:
+        if rc != 0:
             self.lib.jx_liftover_result_free(ctypes.byref(r))
+            self._check(rc)
+        return LiftoverResult(r, len(a_qi), self.lib)          # owns `r`
 
     def nearest_anchor(self, points, anchors, dist):
         pts = np.ascontiguousarray(points, dtype=np.int64).reshape(-1, 2)
