@@ -27,7 +27,13 @@ __global__ void k_gene_best(const uint32_t* __restrict__ best, const uint32_t* _
   if (i < G) out[i] = best[nid[i]];
 }
 
-__global__ void __launch_bounds__(256) k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bestq,
+#ifndef JX_SEL_MINB
+#define JX_SEL_MINB 4
+#endif
+#ifndef JX_SEL_GRID
+#define JX_SEL_GRID 8
+#endif
+__global__ void __launch_bounds__(256, JX_SEL_MINB) k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bestq,
                          const uint32_t* __restrict__ bests, double cscore,
                          int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
                          uint32_t* errflag) {
@@ -548,7 +554,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   JX_ALLOC(Cidx, uint32_t, capC, false);
   JX_ALLOC(d_cnt, uint32_t, 2, true);
   if (nrec) {
-    unsigned grid = std::min<unsigned>(nblk((nrec + 3) / 4), 148u * 8u);
+    unsigned grid = std::min<unsigned>(nblk((nrec + 3) / 4), 148u * JX_SEL_GRID);
     JX_ALLOC(bestq, uint32_t, (size_t)Q.G + 1, false);
     JX_ALLOC(bests, uint32_t, (size_t)S.G + 1, false);
     if (use_cscore) {

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <map>
 
+#include <thread>
 #include "jx_internal.cuh"
 
 namespace {
@@ -704,10 +705,14 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
     if ((rc = jx_pin_small(ctx, (size_t)nlift * 16, &stage))) return rc;
     JX_CK(cudaMemcpyAsync(stage, oblk, (size_t)nlift * 16, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaStreamSynchronize(ctx->stream));
-    memcpy(out->q_rank, stage, (size_t)nlift * 4);
-    memcpy(out->s_rank, stage + (size_t)nlift * 4, (size_t)nlift * 4);
-    memcpy(out->score, stage + (size_t)nlift * 8, (size_t)nlift * 4);
-    memcpy(out->block, stage + (size_t)nlift * 12, (size_t)nlift * 4);
+    void* dst[4] = {out->q_rank, out->s_rank, out->score, out->block};
+    if (nlift < (1u << 18)) {
+      for (int k = 0; k < 4; ++k) memcpy(dst[k], stage + (size_t)nlift * 4 * k, (size_t)nlift * 4);
+    } else {                                       // fresh pages: fault and fill the four arrays side by side
+      std::thread th[4];
+      for (int k = 0; k < 4; ++k) th[k] = std::thread([=]() { memcpy(dst[k], stage + (size_t)nlift * 4 * k, (size_t)nlift * 4); });
+      for (int k = 0; k < 4; ++k) th[k].join();
+    }
   }
   JX_CK(cudaStreamSynchronize(ctx->stream));
   JX_TRACE("lo: order+emit");
