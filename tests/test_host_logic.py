@@ -193,3 +193,43 @@ def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
     assert importlib.import_module("jcvi.compara.synteny").batch_scan is gsyn.batch_scan
     for m in [k for k in sys.modules if k == "jcvi" or k.startswith("jcvi.")]:
         monkeypatch.delitem(sys.modules, m)
+
+
+def test_result_views_keep_the_library_result_alive():
+    """_cabi.view_np: numpy views of a library-owned array free the result exactly when the last view (or slice
+    of one) is unreachable -- LiftoverResult hands out such views instead of copies."""
+    import ctypes
+    import gc
+    import numpy as np
+    from jcvi_b200 import _cabi as C
+    libc = ctypes.CDLL("libc.so.6")
+    libc.malloc.restype = ctypes.c_void_p
+    libc.free.argtypes = [ctypes.c_void_p]
+
+    class S(ctypes.Structure):
+        _fields_ = [("p", ctypes.POINTER(ctypes.c_int32))]
+
+    freed = []
+
+    def free(ref):
+        libc.free(ctypes.cast(ref._obj.p, ctypes.c_void_p))
+        freed.append(1)
+
+    s = S()
+    s.p = ctypes.cast(libc.malloc(40), ctypes.POINTER(ctypes.c_int32))
+    for i in range(10):
+        s.p[i] = i * i
+    own = C._Owner(free, s)
+    a = C.view_np(s.p, 10, np.int32, own)
+    b = C.view_np(s.p, 4, np.int32, own)
+    del own, s
+    gc.collect()
+    assert a.tolist() == [i * i for i in range(10)] and not freed
+    c = a[2:5]
+    del a, b
+    gc.collect()
+    assert c.tolist() == [4, 9, 16] and not freed
+    del c
+    gc.collect()
+    assert freed == [1]
+    assert len(C.view_np(None, 0, np.int32, None)) == 0
