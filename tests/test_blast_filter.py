@@ -5,6 +5,7 @@ CPU: the oracle's restatement against golden vectors produced by the unmodified 
 same vectors and against the oracle on a larger synthetic table."""
 import os
 
+import numpy as np
 import pytest
 
 from conftest import read
@@ -191,3 +192,55 @@ def test_exact_strtod_greater_than_cutoff_on_the_host():
                     assert got == (1 if float(t) > c else 0), (t, c, got)
                 n += 1
     assert n > 50000
+
+
+@pytest.mark.gpu
+def test_gpu_filter_edge_inputs(tmp_path):
+    """Empty and comment-only tables, a table without a final newline, rows longer than the tokenizer's window,
+    rows cut by tile boundaries, an --ids file whose names are absent, a 128-byte name (refused loudly like the
+    rest of the path: the reference overflows its char[128])."""
+    import oracle
+    from jcvi_b200.engine import get_engine
+    from jcvi_b200.formats import blast as gblast
+    eng = get_engine()
+    d = str(tmp_path)
+    row = "Ag%06d.1\tAg%06d.1\t%.2f\t%d\t3\t1\t10\t%d\t20\t%d\t%s\t%.1f"
+
+    def table(n, tail=""):
+        out = []
+        for i in range(n):
+            out.append(row % (i % 977, (i * 7) % 977 if i % 13 else i % 977, 90 + (i % 100) / 10.0, 50 + i % 300,
+                              10 + i % 300, 20 + i % 300, "%.1e" % (10.0 ** -(i % 40)), 30 + (i % 2000) / 3.0) + tail)
+        return out
+
+    cases = {
+        "empty": b"",
+        "comments": b"# a\n# b\n",
+        "one_no_newline": (table(1)[0]).encode(),
+        "blank_only": b"\n\n\n",
+        "long_rows": ("\n".join(r + "\t" + "x" * (1500 + 37 * (i % 50)) for i, r in enumerate(table(400))) + "\n").encode(),
+        "many": ("\n".join(table(60000)) + "\n").encode(),           # ~4 MB: hundreds of tile boundaries
+        "trailing_ws": ("\n".join(table(3000, tail=" \t ")) + "\n").encode(),
+    }
+    for name, text in cases.items():
+        p = os.path.join(d, name + ".last")
+        open(p, "wb").write(text)
+        for tag, kw in (("dflt", {}), ("inv", dict(pctid=95.0, inverse=True, noself=True)), ("ev", dict(pctid=0.0, hitlen=0, evalue=1e-20))):
+            okw = dict(score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, inverse=False)
+            okw.update(kw)
+            oracle.blast_filter(p, p + ".orc", **okw)
+            got, st = eng.blast_filter(np.frombuffer(text, dtype=np.uint8), **okw)
+            assert got == read(p + ".orc"), (name, tag)
+            assert st["kept"] == got.count(b"\n")
+    # --ids whose names never occur: nothing is kept, everything with --inverse
+    p = os.path.join(d, "many.last")
+    ids = os.path.join(d, "none.ids")
+    open(ids, "w").write("nobody\nnothing,else\n")
+    out = gblast.filter([p, "-o", os.path.join(d, "x"), "--pctid=0", "--hitlen=0", "--evalue=10", "--ids=" + ids])
+    assert read(out) == b""
+    out = gblast.filter([p, "-o", os.path.join(d, "y"), "--pctid=0", "--hitlen=0", "--evalue=10", "--ids=" + ids, "--inverse"])
+    assert read(out) == cases["many"]
+    # a 128-byte name
+    bad = ("A" * 128 + "\tB\t99.0\t200\t0\t0\t1\t2\t3\t4\t1e-5\t50\n").encode()
+    with pytest.raises(NotImplementedError):
+        eng.blast_filter(np.frombuffer(bad, dtype=np.uint8))
