@@ -262,6 +262,19 @@ int jx_blast_cscore(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_d
 int jx_blast_filter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, double score,
                     double pctid, int64_t hitlen, double evalue, int noself, int inverse, int use_ids,
                     char** out, int64_t* out_len, int64_t stats[4]);
+/* `jcvi.compara.synteny mcscan` (src/jcvi/compara/synteny.py:1538-1652): the chains of the block ranges
+ * (range_chain, src/jcvi/utils/range.py:412-463, repeated on the blocks that are left until max_iter chains,
+ * synteny.py:1601-1620) and the gene x track table of synteny.py:1622-1637.
+ *   start / end / score / block_id [n_ranges]: AnchorFile.make_ranges' Range list (compara/base.py:29-50), in its order
+ *   pair_gene / pair_partner / pair_block [n_pairs]: the block_pairs dictionaries flattened, one entry per
+ *       (block, gene): gene = caller's dense id (< n_genes) of the reference-BED accn, partner = caller's id of its partner
+ *   -> n_tracks; track_len[n_tracks] and track_blocks (block ids of every chain, in chain order, concatenated);
+ *      track_score[n_tracks] (the chain scores the reference logs); table[n_genes * n_tracks] = partner id of the
+ *      first block of the track that holds the gene, -1 for ".".  All four arrays: jx_free. */
+int jx_mcscan(jx_ctx* ctx, const double* start, const double* end, const int64_t* score, const int32_t* block_id,
+              int64_t n_ranges, int32_t max_iter, const int32_t* pair_gene, const int32_t* pair_partner,
+              const int32_t* pair_block, int64_t n_pairs, int32_t n_genes, int32_t n_blocks, int32_t* n_tracks,
+              int32_t** track_len, int32_t** track_blocks, int64_t** track_score, int32_t** table);
 /* float32 best score per name id of the open jx_cscore_begin session (first n entries) */
 int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
 /* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */

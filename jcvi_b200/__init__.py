@@ -21,7 +21,7 @@ def install():
     jsyn = importlib.import_module("jcvi.compara.synteny")
     jbf.main = bf.main
     jbf.blastfilter_main = bf.blastfilter_main
-    for name in ("scan", "liftover", "batch_scan", "synteny_scan", "synteny_liftover"):
+    for name in ("scan", "liftover", "batch_scan", "synteny_scan", "synteny_liftover", "mcscan"):
         setattr(jsyn, name, getattr(syn, name))
     try:                                   # formats.blast cscore
         from .formats import blast as gblast
@@ -34,7 +34,7 @@ def install():
         jcat = importlib.import_module("jcvi.compara.catalog")
         if hasattr(jcat, "blastfilter_main"):
             jcat.blastfilter_main = bf.main
-        for name in ("scan", "liftover"):
+        for name in ("scan", "liftover", "mcscan"):
             if hasattr(jcat, name):
                 setattr(jcat, name, getattr(syn, name))
         if hasattr(jcat, "cscore"):            # `from jcvi.formats.blast import cscore` (catalog.py:20)

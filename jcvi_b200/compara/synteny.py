@@ -264,10 +264,135 @@ def liftover(args):
     return newanchorfile
 
 
+def _best_pairs(qs, ss, ts):
+    """compara/base.py:139-150 get_best_pair: per gene the partner with the largest score, the first one on ties."""
+    pairs = {}
+    for q, s, t in zip(qs, ss, ts):
+        t = int(t[:-1]) if t[-1] == "L" else int(t)
+        if q not in pairs or pairs[q][1] < t:
+            pairs[q] = (s, t)
+    return dict((q, s) for q, (s, t) in pairs.items())
+
+
+def make_ranges(ac, order, clip=10):
+    """AnchorFile.make_ranges / make_range (compara/base.py:29-50,152-164) -> (ranges as (start, end, score, block id)
+    in the reference's order, block_pairs: one dict per block)."""
+    ranges = []
+    block_pairs = [dict() for _ in ac.blocks]
+
+    def one(q, s, t, i):
+        pairs = _best_pairs(q, s, t)
+        block_pairs[i].update(pairs)
+        ranks = sorted(order[x][0] for x in q)
+        qmin, qmax = ranks[0], ranks[-1]
+        if qmax - qmin >= 2 * clip:
+            qmin += clip / 2
+            qmax -= clip / 2
+        ranges.append((qmin, qmax, len(pairs), i))
+
+    for i, ib in enumerate(ac.blocks):
+        q, s, t = zip(*ib)
+        if q[0] not in order:
+            q, s = s, q
+        one(q, s, t, i)
+        assert q[0] in order
+        if s[0] not in order:
+            continue
+        one(s, q, t, i)                 # self comparison: the block seen from the other side
+    return ranges, block_pairs
+
+
+def mcscan(args):
+    """
+    %prog mcscan bedfile anchorfile [options]
+
+    Stack synteny blocks on a reference bed, MCSCAN style. The first column in
+    the output is the reference order, given in the bedfile. Then each column
+    next to it are separate 'tracks'.
+
+    If --mergetandem=tandem_file is specified, tandem_file should have each
+    tandem cluster as one line, tab separated.
+    """
+    p = OptionParser(mcscan.__doc__)
+    p.add_argument("--iter", default=100, type=int, help="Max number of chains to output")
+    p.add_argument("--ascii", default=False, action="store_true", help="Output symbols rather than gene names")
+    p.add_argument("--Nm", default=10, type=int, help="Clip block ends to allow slight overlaps")
+    p.add_argument("--trackids", action="store_true", help="Track block IDs in separate file")
+    p.add_argument("--mergetandem", default=None,
+                   help="merge tandems genes in output acoording to PATH-TO-TANDEM_FILE, cannot be used with --ascii")
+    p.set_outfile()
+    opts, args = p.parse_args(args)
+    if len(args) != 2:
+        sys.exit(not p.print_help())
+    bedfile, anchorfile = args
+    ascii_ = opts.ascii
+    ofile = opts.outfile
+    bed = Bed(bedfile)
+    order = bed.order
+    tandems = {}
+    if opts.mergetandem:
+        assert not ascii_
+        for row in open(opts.mergetandem):
+            row = row.split()
+            s = ";".join(row)
+            for atom in row:
+                tandems[atom] = s
+    ac = AnchorFile(anchorfile)
+    ranges, block_pairs = make_ranges(ac, order, clip=opts.Nm)
+    # dense ids: reference-BED accns (rows of the table) and partner names
+    gid = {}
+    for b in bed:
+        gid.setdefault(b.accn, len(gid))
+    names, nid = [], {}
+    pg, pp, pb = [], [], []
+    for i, pairs in enumerate(block_pairs):
+        for q, s in pairs.items():
+            if q not in gid:            # a key of a block dictionary that no BED row carries: never looked up
+                continue
+            if s not in nid:
+                nid[s] = len(names)
+                names.append(s)
+            pg.append(gid[q]); pp.append(nid[s]); pb.append(i)
+    print("Chain started: {0} blocks".format(len(ranges)), file=sys.stderr)
+    r = np.array(ranges, dtype=np.float64).reshape(-1, 4)
+    tracks, scores, table = get_engine().mcscan(r[:, 0], r[:, 1], r[:, 2].astype(np.int64), r[:, 3].astype(np.int32), opts.iter,
+                                                pg, pp, pb, len(gid), len(ac.blocks))
+    left = len(ranges)
+    rid = r[:, 3].astype(np.int64)
+    for it, (track, score) in enumerate(zip(tracks, scores)):
+        left -= int(np.isin(rid, list(set(track))).sum())
+        rid = rid[~np.isin(rid, list(set(track)))]
+        msg = "Chain {0}: score={1}".format(it, score)
+        msg += " {0} blocks remained..".format(left) if left else " done!"
+        print(msg, file=sys.stderr)
+    if opts.trackids:
+        with open(ofile + ".tracks", "w") as fwlog:
+            for track in tracks:
+                print(",".join(str(x) for x in sorted(set(track))), file=fwlog)
+    # partner id -> text (-1 = "."), --ascii / --mergetandem applied per name once
+    text = np.empty(len(names) + 1, dtype=object)
+    for k, nm in enumerate(names):
+        text[k] = "x" if ascii_ else (tandems.get(nm, nm) if tandems else nm)
+    text[len(names)] = tandems.get(".", ".") if tandems else "."
+    cells = text[table]                                   # -1 indexes the last entry
+    sep = "" if ascii_ else "\t"
+    close = ofile not in ("stdout", "-")
+    fw = open(ofile, "w") if close else sys.stdout
+    try:
+        for b in bed:
+            fw.write(b.accn + "\t" + sep.join(cells[gid[b.accn]]) + "\n")
+    finally:
+        if close:
+            fw.close()
+    logger.debug("MCscan blocks written to `{0}`.".format(ofile))
+    if opts.trackids:
+        logger.debug("Block IDs written to `{0}`.".format(ofile + ".tracks"))
+
+
 def main():
-    actions = {"scan": scan, "liftover": liftover, "summary": summary}
+    actions = {"scan": scan, "liftover": liftover, "summary": summary, "mcscan": mcscan}
     if len(sys.argv) < 2 or sys.argv[1] not in actions:
-        print("usage: python -m jcvi_b200.compara.synteny {scan,liftover,summary} ...", file=sys.stderr)
+        print("usage: python -m jcvi_b200.compara.synteny {scan,liftover,summary,mcscan} ...", file=sys.stderr)
         sys.exit(1)
     actions[sys.argv[1]](sys.argv[2:])
 

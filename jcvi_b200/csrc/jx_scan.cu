@@ -7,6 +7,7 @@
 //   214-219  _score        min(#distinct qi, #distinct si) >= N        -> per-component counters
 //   utils/grouper.py:73-81 iteration order (dict insertion)            -> "birth" = smallest sorted index that has an
 //                                                                        earlier neighbour; components ordered by birth
+#include <algorithm>
 #include "jx_internal.cuh"
 
 namespace {
@@ -487,3 +488,148 @@ int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const floa
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// synteny mcscan (src/jcvi/compara/synteny.py:1538-1652): stack the anchor blocks on a
+// reference BED.  Chaining = range_chain (src/jcvi/utils/range.py:412-463: end points sorted by
+// (position, LEFT before RIGHT, index, score), one DP cell per end point, strict `>`), repeated on the blocks
+// that are left (synteny.py:1601-1620) -- sequential by nature and O(blocks) per chain: host.  The
+// per-gene track table (synteny.py:1622-1637: for every gene and track the partner in the FIRST block of
+// the track, in chain order, that holds the gene) is one atomicMin per (block, gene) entry on the device.
+// =====================================================================================================
+namespace {
+__global__ void k_track_fill(const int32_t* __restrict__ pair_gene, const int32_t* __restrict__ pair_block, uint32_t n_pairs,
+                             const int32_t* __restrict__ track_of, const uint32_t* __restrict__ pos_of, uint32_t n_tracks,
+                             unsigned long long* cell) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int32_t t = track_of[pair_block[p]];
+  if (t < 0) return;
+  const unsigned long long key = ((unsigned long long)pos_of[pair_block[p]] << 32) | p;   // first block of the track wins
+  atomicMin(cell + (size_t)pair_gene[p] * n_tracks + (uint32_t)t, key);
+}
+__global__ void k_track_partner(const unsigned long long* __restrict__ cell, size_t n, const int32_t* __restrict__ pair_partner,
+                                int32_t* table) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long c = cell[i];
+  table[i] = c == ~0ull ? -1 : pair_partner[(uint32_t)c];
+}
+
+struct McEnd { double pos; int lr; int i; long long score; };
+// range_chain on `cur` (indices into the caller's ranges); chain = positions in `cur`, in chain order
+long long mc_chain(const std::vector<int>& cur, const double* start, const double* end, const int64_t* score, std::vector<int>& chain) {
+  std::vector<McEnd> ends;
+  ends.reserve(2 * cur.size());
+  for (size_t i = 0; i < cur.size(); ++i) {
+    ends.push_back({start[cur[i]], 0, (int)i, (long long)score[cur[i]]});
+    ends.push_back({end[cur[i]], 1, (int)i, (long long)score[cur[i]]});
+  }
+  std::sort(ends.begin(), ends.end(), [](const McEnd& a, const McEnd& b) {
+    if (a.pos != b.pos) return a.pos < b.pos;
+    if (a.lr != b.lr) return a.lr < b.lr;
+    if (a.i != b.i) return a.i < b.i;
+    return a.score < b.score;
+  });
+  struct Cell { long long score; int from, which; };
+  std::vector<Cell> sc;
+  sc.reserve(ends.size());
+  std::vector<int> left(cur.size(), -1);
+  for (size_t i = 0; i < ends.size(); ++i) {
+    Cell c = i == 0 ? Cell{0, -1, -1} : sc.back();
+    const McEnd& e = ends[i];
+    if (e.lr == 0) left[(size_t)e.i] = (int)i;
+    else {
+      const int lj = left[(size_t)e.i];
+      const long long cs = sc[(size_t)lj].score + e.score;
+      if (cs > c.score) c = Cell{cs, lj, e.i};
+    }
+    sc.push_back(c);
+  }
+  chain.clear();
+  int last = sc.back().from, which = sc.back().which;
+  while (last != -1) {
+    if (which != -1) chain.push_back(which);
+    which = sc[(size_t)last].which;
+    last = sc[(size_t)last].from;
+  }
+  std::reverse(chain.begin(), chain.end());
+  return sc.back().score;
+}
+}  // namespace
+
+extern "C" int jx_mcscan(jx_ctx* ctx, const double* start, const double* end, const int64_t* score, const int32_t* block_id,
+                         int64_t n_ranges, int32_t max_iter, const int32_t* pair_gene, const int32_t* pair_partner,
+                         const int32_t* pair_block, int64_t n_pairs, int32_t n_genes, int32_t n_blocks, int32_t* n_tracks,
+                         int32_t** track_len, int32_t** track_blocks, int64_t** track_score, int32_t** table) {
+  if (!ctx || !n_tracks || !track_len || !track_blocks || !track_score || !table || n_ranges < 0 || n_pairs < 0 ||
+      n_pairs >= (1ll << 32) || n_genes < 0 || n_blocks < 0) return JX_EARG;
+  *n_tracks = 0; *track_len = nullptr; *track_blocks = nullptr; *track_score = nullptr; *table = nullptr;
+  for (int64_t i = 0; i < n_ranges; ++i)
+    if (block_id[i] < 0 || block_id[i] >= n_blocks) { ctx->err = "jx_mcscan: block id out of range"; return JX_EARG; }
+  for (int64_t i = 0; i < n_pairs; ++i)
+    if (pair_gene[i] < 0 || pair_gene[i] >= n_genes || pair_block[i] < 0 || pair_block[i] >= n_blocks) {
+      ctx->err = "jx_mcscan: pair entry out of range"; return JX_EARG;
+    }
+  cudaSetDevice(ctx->device);
+  // ---- chains (host) -----------------------------------------------------------------------------------------
+  std::vector<int> cur((size_t)n_ranges);
+  for (int64_t i = 0; i < n_ranges; ++i) cur[(size_t)i] = (int)i;
+  std::vector<int32_t> tlen, tblocks;
+  std::vector<int64_t> tscore;
+  std::vector<int32_t> track_of((size_t)std::max(n_blocks, 1), -1);
+  std::vector<uint32_t> pos_of((size_t)std::max(n_blocks, 1), 0u);
+  std::vector<char> taken((size_t)std::max(n_blocks, 1), 0);
+  int iteration = 0;
+  while (!cur.empty() && iteration < max_iter) {
+    std::vector<int> chain;
+    const long long sc = mc_chain(cur, start, end, score, chain);
+    uint32_t pos = 0;
+    for (int x : chain) {
+      const int32_t b = block_id[cur[(size_t)x]];
+      tblocks.push_back(b);
+      if (!taken[(size_t)b]) { taken[(size_t)b] = 1; track_of[(size_t)b] = iteration; pos_of[(size_t)b] = pos; }
+      ++pos;
+    }
+    tlen.push_back((int32_t)chain.size());
+    tscore.push_back(sc);
+    std::vector<int> rest;
+    rest.reserve(cur.size());
+    for (int r : cur) if (!taken[(size_t)block_id[r]]) rest.push_back(r);
+    cur.swap(rest);
+    ++iteration;
+  }
+  const uint32_t T = (uint32_t)iteration;
+  *n_tracks = (int32_t)T;
+  auto dup = [](const void* src, size_t bytes) { void* p = malloc(bytes ? bytes : 1); if (p && bytes) memcpy(p, src, bytes); return p; };
+  *track_len = (int32_t*)dup(tlen.data(), tlen.size() * 4);
+  *track_blocks = (int32_t*)dup(tblocks.data(), tblocks.size() * 4);
+  *track_score = (int64_t*)dup(tscore.data(), tscore.size() * 8);
+  const size_t cells = (size_t)n_genes * T;
+  *table = (int32_t*)malloc(cells ? cells * 4 : 4);
+  if (!*track_len || !*track_blocks || !*track_score || !*table) { ctx->err = "out of host memory"; return JX_EINTERNAL; }
+  if (!cells) return JX_OK;
+  // ---- track table (device) ------------------------------------------------------------------------------------
+  Arena arena(ctx);
+  JX_ALLOC(d_cell, unsigned long long, cells, false);
+  JX_CK(cudaMemsetAsync(d_cell, 0xFF, cells * 8, ctx->stream));
+  JX_ALLOC(d_table, int32_t, cells, false);
+  JX_ALLOC(d_pg, int32_t, (size_t)std::max<int64_t>(n_pairs, 1), false);
+  JX_ALLOC(d_pp, int32_t, (size_t)std::max<int64_t>(n_pairs, 1), false);
+  JX_ALLOC(d_pb, int32_t, (size_t)std::max<int64_t>(n_pairs, 1), false);
+  JX_ALLOC(d_to, int32_t, track_of.size(), false);
+  JX_ALLOC(d_po, uint32_t, pos_of.size(), false);
+  if (n_pairs) {
+    JX_CK(cudaMemcpyAsync(d_pg, pair_gene, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(d_pp, pair_partner, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(d_pb, pair_block, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  JX_CK(cudaMemcpyAsync(d_to, track_of.data(), track_of.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_CK(cudaMemcpyAsync(d_po, pos_of.data(), pos_of.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_pairs) JX_LAUNCH(k_track_fill, nblk((size_t)n_pairs), 256, 0, d_pg, d_pb, (uint32_t)n_pairs, d_to, d_po, T, d_cell);
+  JX_LAUNCH(k_track_partner, nblk(cells), 256, 0, d_cell, cells, d_pp, d_table);
+  JX_CK(cudaMemcpyAsync(*table, d_table, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  return JX_OK;
+}
+

@@ -437,6 +437,30 @@ class Engine(object):
                                            len(a_qi), ctypes.byref(buf), ctypes.byref(ln), ctypes.byref(cnt)))
         return self._take_lines(buf, ln), cnt.value
 
+    def mcscan(self, start, end, score, block_id, max_iter, pair_gene, pair_partner, pair_block, n_genes, n_blocks):
+        """jx_mcscan -> (tracks: list of block-id lists in chain order, chain scores, table[n_genes, n_tracks] of partner ids, -1 = '.')."""
+        start = np.ascontiguousarray(start, dtype=np.float64); end = np.ascontiguousarray(end, dtype=np.float64)
+        score = np.ascontiguousarray(score, dtype=np.int64); block_id = np.ascontiguousarray(block_id, dtype=np.int32)
+        pg = np.ascontiguousarray(pair_gene, dtype=np.int32); pp = np.ascontiguousarray(pair_partner, dtype=np.int32)
+        pb = np.ascontiguousarray(pair_block, dtype=np.int32)
+        nt = ctypes.c_int32()
+        tl = ctypes.c_void_p(); tb = ctypes.c_void_p(); ts = ctypes.c_void_p(); tab = ctypes.c_void_p()
+        rc = self.lib.jx_mcscan(self.ctx, C.ptr(start), C.ptr(end), C.ptr(score), C.ptr(block_id), len(start), int(max_iter),
+                                C.ptr(pg), C.ptr(pp), C.ptr(pb), len(pg), int(n_genes), int(n_blocks), ctypes.byref(nt),
+                                ctypes.byref(tl), ctypes.byref(tb), ctypes.byref(ts), ctypes.byref(tab))
+        try:
+            self._check(rc)
+            T = nt.value
+            lens = C.as_np(ctypes.cast(tl, C.c_i32p), T, np.int32)
+            blocks = C.as_np(ctypes.cast(tb, C.c_i32p), int(lens.sum()), np.int32)
+            scores = C.as_np(ctypes.cast(ts, C.c_i64p), T, np.int64)
+            table = C.as_np(ctypes.cast(tab, C.c_i32p), int(n_genes) * T, np.int32).reshape(int(n_genes), T)
+        finally:
+            for p in (tl, tb, ts, tab):
+                self.lib.jx_free(p)
+        tracks = np.split(blocks, np.cumsum(lens)[:-1]) if T else []
+        return [t.tolist() for t in tracks], scores.tolist(), table
+
     # ---- instrumentation ----------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.jx_launch_count(self.ctx))

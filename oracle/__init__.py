@@ -10,6 +10,7 @@ from .oracle import (  # noqa: F401
     liftover,
     cscore,
     blast_filter,
+    mcscan,
     kdtree,
     gene_name,
     natcmp,

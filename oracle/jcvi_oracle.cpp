@@ -25,6 +25,7 @@
 //     -- build (balanced, compact, leafsize=16) and k=1, p=1 query; validated
 //     black-box against the installed scipy in tests/test_oracle_kdtree.py.
 #include <algorithm>
+#include <set>
 #include <cctype>
 #include <cmath>
 #include <cstdint>
@@ -1058,6 +1059,170 @@ int orc_blast_filter(const char* blast_file, const char* out_path, const char* i
   });
   fclose(fw);
   return ok ? 0 : -2;
+}
+
+
+// ---------------------------------------------------------------------------------
+// synteny mcscan  (src/jcvi/compara/synteny.py:1538-1652): stack the anchor blocks on a reference BED.
+//   AnchorFile.make_ranges / make_range / get_best_pair   src/jcvi/compara/base.py:29-50,139-164
+//   range_chain / _make_endpoints                           src/jcvi/utils/range.py:347-355,412-463
+// tracks_path: --trackids log (NULL: none); tandem_path: --mergetandem file (NULL: none).
+// returns 0, -1 I/O, -4 KeyError (gene of a block not in the BED), -5 ValueError (score not an integer, empty block)
+// ---------------------------------------------------------------------------------
+struct McRange { double start, end; long score; int id; };
+
+static bool mc_int(const std::string& t0, long& v) {          // int(t[:-1]) if t[-1] == "L" else int(t)
+  std::string t = t0;
+  if (!t.empty() && t.back() == 'L') t.pop_back();
+  if (t.empty()) return false;
+  char* endp = nullptr;
+  v = strtol(t.c_str(), &endp, 10);
+  return endp && *endp == 0 && (isdigit((unsigned char)t[0]) || ((t[0] == '-' || t[0] == '+') && t.size() > 1));
+}
+
+// range_chain on the current list; fills `chain` with indices into `ranges` in chain order
+static long mc_range_chain(const std::vector<McRange>& ranges, std::vector<int>& chain) {
+  struct End { double pos; int lr; int i; long score; };
+  std::vector<End> ends;
+  ends.reserve(2 * ranges.size());
+  for (size_t i = 0; i < ranges.size(); ++i) {
+    ends.push_back({ranges[i].start, 0, (int)i, ranges[i].score});
+    ends.push_back({ranges[i].end, 1, (int)i, ranges[i].score});
+  }
+  std::sort(ends.begin(), ends.end(), [](const End& a, const End& b) {       // sorted(tuples); seqid is "0" throughout
+    if (a.pos != b.pos) return a.pos < b.pos;
+    if (a.lr != b.lr) return a.lr < b.lr;
+    if (a.i != b.i) return a.i < b.i;
+    return a.score < b.score;
+  });
+  struct Cell { long score; int from; int which; };
+  std::vector<Cell> sc;
+  sc.reserve(ends.size());
+  std::vector<int> left_index(ranges.size(), -1);
+  for (size_t i = 0; i < ends.size(); ++i) {
+    Cell cur = i == 0 ? Cell{0, -1, -1} : sc.back();
+    const End& e = ends[i];
+    if (e.lr == 0) left_index[(size_t)e.i] = (int)i;
+    else {
+      const int lj = left_index[(size_t)e.i];
+      const long cs = sc[(size_t)lj].score + e.score;
+      if (cs > cur.score) cur = Cell{cs, lj, e.i};
+    }
+    sc.push_back(cur);
+  }
+  chain.clear();
+  long score = sc.back().score;
+  int last = sc.back().from, which = sc.back().which;
+  while (last != -1) {
+    if (which != -1) chain.push_back(which);
+    which = sc[(size_t)last].which;
+    last = sc[(size_t)last].from;
+  }
+  std::reverse(chain.begin(), chain.end());
+  return score;
+}
+
+int orc_mcscan(const char* bed_path, const char* anchor_path, const char* out_path, int max_iter, int ascii, int clip,
+               const char* tracks_path, const char* tandem_path) {
+  Bed bed;
+  if (!load_bed(bed_path, bed)) return -1;
+  AnchorBlocks ac;
+  if (!load_anchors(anchor_path, ac)) return -1;
+  std::unordered_map<std::string, std::string> tandems;
+  if (tandem_path && *tandem_path) {
+    std::string txt;
+    if (!read_file(tandem_path, txt)) return -1;
+    for_each_line(txt.data(), txt.size(), [&](const char* b, const char* e) {
+      std::vector<std::string> row = split_ws(std::string(b, e));
+      std::string j;
+      for (size_t k = 0; k < row.size(); ++k) { if (k) j += ";"; j += row[k]; }
+      for (const std::string& a : row) tandems[a] = j;
+    });
+  }
+  // make_ranges
+  std::vector<McRange> ranges;
+  std::vector<std::unordered_map<std::string, std::string>> block_pairs(ac.blocks.size());
+  int rc = 0;
+  auto make_range = [&](const std::vector<const std::string*>& q, const std::vector<const std::string*>& sv,
+                        const std::vector<const std::string*>& t, int i) -> bool {
+    std::unordered_map<std::string, std::pair<std::string, long>> pairs;      // get_best_pair: larger score wins, first on ties
+    for (size_t k = 0; k < q.size(); ++k) {
+      long tv;
+      if (!mc_int(*t[k], tv)) { rc = -5; return false; }
+      auto it = pairs.find(*q[k]);
+      if (it == pairs.end()) pairs.emplace(*q[k], std::make_pair(*sv[k], tv));
+      else if (it->second.second < tv) it->second = std::make_pair(*sv[k], tv);
+    }
+    for (auto& kv : pairs) block_pairs[(size_t)i][kv.first] = kv.second.first;   // dict.update
+    std::vector<long> ranks;
+    for (const std::string* x : q) {
+      auto it = bed.order.find(*x);
+      if (it == bed.order.end()) { rc = -4; return false; }
+      ranks.push_back(it->second);
+    }
+    std::sort(ranks.begin(), ranks.end());
+    double qmin = (double)ranks.front(), qmax = (double)ranks.back();
+    if (ranks.back() - ranks.front() >= 2L * clip) { qmin += clip / 2.0; qmax -= clip / 2.0; }
+    ranges.push_back({qmin, qmax, (long)pairs.size(), i});
+    return true;
+  };
+  for (size_t i = 0; i < ac.blocks.size(); ++i) {
+    const auto& ib = ac.blocks[i];
+    if (ib.empty()) { g_err = "empty block (zip(*ib) fails in the reference)"; return -5; }
+    std::vector<const std::string*> q, sv, t;
+    for (const auto& row : ib) {
+      if (row.size() != 3) { g_err = "anchor line without three columns"; return -5; }
+      q.push_back(&row[0]); sv.push_back(&row[1]); t.push_back(&row[2]);
+    }
+    if (!bed.order.count(*q[0])) std::swap(q, sv);
+    if (!make_range(q, sv, t, (int)i)) return rc;
+    if (!bed.order.count(*sv[0])) continue;
+    if (!make_range(sv, q, t, (int)i)) return rc;            // self comparison: the block seen from the other side
+  }
+  FILE* fl = nullptr;
+  if (tracks_path && *tracks_path) { fl = fopen(tracks_path, "w"); if (!fl) return -1; }
+  std::vector<std::vector<int>> tracks;                      // block ids in chain order
+  int iteration = 0;
+  while (!ranges.empty()) {
+    if (iteration >= max_iter) break;
+    std::vector<int> chain;
+    mc_range_chain(ranges, chain);
+    std::vector<int> ids;
+    std::set<int> sel;
+    for (int x : chain) { ids.push_back(ranges[(size_t)x].id); sel.insert(ranges[(size_t)x].id); }
+    tracks.push_back(ids);
+    if (fl) {
+      bool first = true;
+      for (int x : sel) { fprintf(fl, first ? "%d" : ",%d", x); first = false; }
+      fputc('\n', fl);
+    }
+    std::vector<McRange> rest;
+    for (const McRange& r : ranges) if (!sel.count(r.id)) rest.push_back(r);
+    ranges.swap(rest);
+    ++iteration;
+  }
+  if (fl) fclose(fl);
+  FILE* fw = fopen(out_path, "w");
+  if (!fw) return -1;
+  for (const BedLine& b : bed.rows) {
+    std::string line = b.accn + "\t";
+    for (size_t t = 0; t < tracks.size(); ++t) {
+      std::string anchor = ".";
+      for (int tid : tracks[t]) {
+        auto it = block_pairs[(size_t)tid].find(b.accn);
+        if (it != block_pairs[(size_t)tid].end()) { anchor = it->second; }
+        if (anchor != ".") break;
+      }
+      if (ascii && anchor != ".") anchor = "x";
+      if (tandem_path && *tandem_path) { auto it = tandems.find(anchor); if (it != tandems.end()) anchor = it->second; }
+      if (t && !ascii) line += "\t";
+      line += anchor;
+    }
+    line += "\n";
+    fwrite(line.data(), 1, line.size(), fw);
+  }
+  fclose(fw);
+  return 0;
 }
 
 }  // extern "C"

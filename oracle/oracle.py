@@ -101,6 +101,17 @@ def blast_filter(blast_file, out_path, score=0, pctid=95.0, hitlen=100, evalue=0
                                    ctypes.c_long(int(hitlen)), ctypes.c_double(evalue), int(bool(noself)), int(bool(inverse))))
 
 
+def mcscan(bedfile, anchorfile, out_path, iter=100, ascii=False, Nm=10, trackids=False, mergetandem=None):
+    """compara/synteny.py:1538-1652 (`jcvi.compara.synteny mcscan`); writes out_path (+ out_path + ".tracks")."""
+    rc = _lib().orc_mcscan(_b(bedfile), _b(anchorfile), _b(out_path), int(iter), int(bool(ascii)), int(Nm),
+                           _b(out_path + ".tracks") if trackids else _b(None), _b(mergetandem))
+    if rc == -4:
+        raise KeyError(_lib().orc_last_error().decode())
+    if rc == -5:
+        raise ValueError(_lib().orc_last_error().decode())
+    _check(rc)
+
+
 def kdtree(anchors, queries, bound):
     """Restated cKDTree(anchors, leafsize=16).query(queries, p=1, distance_upper_bound=bound)."""
     a = np.ascontiguousarray(anchors, dtype=np.int64).reshape(-1, 2)
