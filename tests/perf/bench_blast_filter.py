@@ -3,7 +3,7 @@
 one B200 (host buffer in, kept rows out; and with the table already resident), next to the CPU oracle on a
 500 k-line sample of the same table (tuning / reporting aid, not bench.py)."""
 import os, sys, time, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from jcvi_b200.engine import get_engine

@@ -2,7 +2,7 @@
 """`formats.blast cscore` on the C2 table: the drop-in's phases on one B200 and
 the CPU oracle on a 500 k-line sample of the same table (tuning / reporting aid, not bench.py)."""
 import os, sys, time, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from jcvi_b200.engine import get_engine

@@ -4,10 +4,10 @@ three homeologous copies), 200 M hits (~14 GB of text, > 4 GiB offsets), C-score
 liftover with the table resident, checks the size-independent properties of tests/test_gpu_fullsize.py, compares
 the first 500 k lines with the CPU oracle byte for byte, and prints ms per step.  Reporting aid, not bench.py.
 
-    python tools/run_c3.py [hits] [chunk]
+    python tests/perf/run_c3.py [hits] [chunk]
 """
 import os, sys, time, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from jcvi_b200 import synth
