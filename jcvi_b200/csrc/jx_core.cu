@@ -330,12 +330,17 @@ int jx_d2h_big(jx_ctx* ctx, char* host, const uint8_t* dev, size_t bytes) {
     if (nt == 1 || len < (4u << 20)) { memcpy(host + o, src, len); return; }
     std::vector<std::thread> th;
     const size_t part = ((len + nt - 1) / nt + 4095) & ~(size_t)4095;
-    for (unsigned t = 0; t < nt; ++t) {
-      const size_t a = (size_t)t * part;
-      if (a >= len) break;
-      const size_t l = std::min(part, len - a);
-      th.emplace_back([=]() { memcpy(host + o + a, src + a, l); });
-    }
+    size_t done = 0;                                 // bytes handed to a thread so far
+    try {
+      for (unsigned t = 0; t < nt; ++t) {
+        const size_t a = (size_t)t * part;
+        if (a >= len) break;
+        const size_t l = std::min(part, len - a);
+        th.emplace_back([=]() { memcpy(host + o + a, src + a, l); });
+        done = a + l;
+      }
+    } catch (...) {}                                 // no more threads: this one copies the rest
+    if (done < len) memcpy(host + o + done, src + done, len - done);
     for (auto& x : th) x.join();
   };
   cudaError_t err = cudaSuccess;

@@ -709,9 +709,17 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
     if (nlift < (1u << 18)) {
       for (int k = 0; k < 4; ++k) memcpy(dst[k], stage + (size_t)nlift * 4 * k, (size_t)nlift * 4);
     } else {                                       // fresh pages: fault and fill the four arrays side by side
-      std::thread th[4];
-      for (int k = 0; k < 4; ++k) th[k] = std::thread([=]() { memcpy(dst[k], stage + (size_t)nlift * 4 * k, (size_t)nlift * 4); });
-      for (int k = 0; k < 4; ++k) th[k].join();
+      std::vector<std::thread> th;
+      int started = 0;
+      try {
+        for (; started < 3; ++started) {
+          const int k = started + 1;
+          th.emplace_back([=]() { memcpy(dst[k], stage + (size_t)nlift * 4 * k, (size_t)nlift * 4); });
+        }
+      } catch (...) {}                               // no more threads: this one copies the rest
+      memcpy(dst[0], stage, (size_t)nlift * 4);
+      for (int k = started + 1; k < 4; ++k) memcpy(dst[k], stage + (size_t)nlift * 4 * k, (size_t)nlift * 4);
+      for (auto& x : th) x.join();
     }
   }
   JX_CK(cudaStreamSynchronize(ctx->stream));
