@@ -3,6 +3,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -14,6 +15,29 @@ struct HostReader {
   const unsigned char* p;
   __host__ __device__ inline uint32_t operator()(int i) const { return p[i]; }
 };
+// Host tables of the last jx_bed_load (perfect hash, displacements, overflow lists, word blob): the same name
+// list is often loaded on both sides (self comparisons; formats.blast cscore / filter --ids), and building the
+// tables is O(names) hashing and sorting on one host thread.
+struct BuiltSide {
+  bool valid = false;
+  std::vector<char> names; std::vector<uint32_t> off, name_id; std::vector<uint8_t> indexable; bool has_indexable = false;
+  std::vector<uint32_t> tab; std::vector<uint16_t> disp; std::vector<uint32_t> ovf_hash, ovf_rank, words, meta;
+  uint32_t bshift = 31, cshift = 28;
+  bool matches(const jx_bed* bed) const {
+    const size_t G = (size_t)bed->n_genes;
+    if (!valid || off.size() != G + 1) return false;
+    if (memcmp(off.data(), bed->name_off, (G + 1) * 4) != 0) return false;
+    const size_t blob = G ? bed->name_off[G] : 0;
+    if (names.size() != blob || (blob && memcmp(names.data(), bed->names, blob) != 0)) return false;
+    if (G && memcmp(name_id.data(), bed->name_id, G * 4) != 0) return false;
+    if (has_indexable != (bed->indexable != nullptr)) return false;
+    if (has_indexable && G && memcmp(indexable.data(), bed->indexable, G) != 0) return false;
+    return true;
+  }
+};
+BuiltSide g_built;          // guarded by g_built_mu: contexts of different threads may load concurrently
+std::mutex g_built_mu;
+
 template <class T>
 int upload(jx_ctx* ctx, T** dst, const T* src, size_t n) {
   if (*dst) { cudaFree(*dst); *dst = nullptr; }
@@ -115,7 +139,11 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
   // perfect hash table of 32-byte slots at load factor <= 0.5 (hash-and-displace), built on the host
   // with the same hash the kernels use (jx_fast5.cuh slot_hash_* / slot_index)
   int rc;
-  {
+  std::lock_guard<std::mutex> built_lock(g_built_mu);
+  BuiltSide& B = g_built;
+  const bool hit = B.matches(bed);
+  if (!hit) {
+    B.valid = false;
     HostReader rd{(const unsigned char*)bed->names};
     std::vector<std::pair<uint32_t, int64_t>> keys;     // (hash, rank); the last rank of a repeated name wins
     {
@@ -148,8 +176,8 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
     const size_t n = keys.size();
     uint32_t cbits = 4;
     while ((1ull << cbits) < 2 * (uint64_t)n + 2) ++cbits;
-    std::vector<uint32_t> tab;
-    std::vector<uint16_t> disp;
+    std::vector<uint32_t>& tab = B.tab;
+    std::vector<uint16_t>& disp = B.disp;
     uint32_t bbits = 1;
     for (;; ++cbits) {
       if (cbits > 30) { ctx->err = "BED name table does not fit"; return JX_EARG; }
@@ -196,19 +224,15 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
         for (uint32_t i = 0; i < 4 * JX_SLOT_WORDS && a + i < b; ++i)
           slot[2 + (i >> 2)] |= (uint32_t)(unsigned char)bed->names[a + i] << (8 * (i & 3));
       }
-      d.bshift = bshift; d.cshift = cshift;
+      B.bshift = bshift; B.cshift = cshift;
       break;
     }
-    if ((rc = upload(ctx, &d.table, reinterpret_cast<const uint4*>(tab.data()), tab.size() / 4))) return rc;
-    if ((rc = upload(ctx, &d.disp, disp.data(), disp.size()))) return rc;
-    d.n_ovf = (uint32_t)ovf_hash.size();
-    if ((rc = upload(ctx, &d.ovf_hash, ovf_hash.data(), ovf_hash.size()))) return rc;
-    if ((rc = upload(ctx, &d.ovf_rank, ovf_rank.data(), ovf_rank.size()))) return rc;
-  }
-  {
+    B.ovf_hash.swap(ovf_hash); B.ovf_rank.swap(ovf_rank);
+
     // word-aligned, zero-padded copy of the names so that the kernel verifies a probe with
     // 32-bit compares against shared-memory words
-    std::vector<uint32_t> meta((size_t)G), words;
+    std::vector<uint32_t>& meta = B.meta; std::vector<uint32_t>& words = B.words;
+    meta.assign((size_t)G, 0u); words.clear();
     words.reserve(blob / 4 + (size_t)G + 4);
     for (int64_t r = 0; r < G; ++r) {
       uint32_t a = bed->name_off[r], b = bed->name_off[r + 1], len = b - a;
@@ -222,9 +246,21 @@ int jx_bed_load(jx_ctx* ctx, int side, const jx_bed* bed) {
       }
     }
     words.push_back(0);
-    if ((rc = upload(ctx, &d.blobw, words.data(), words.size()))) return rc;
-    if ((rc = upload(ctx, &d.name_meta, meta.data(), meta.size()))) return rc;
+    B.names.assign(bed->names, bed->names + blob);
+    B.off.assign(bed->name_off, bed->name_off + G + 1);
+    B.name_id.assign(bed->name_id, bed->name_id + G);
+    B.has_indexable = bed->indexable != nullptr;
+    if (B.has_indexable) B.indexable.assign(bed->indexable, bed->indexable + G); else B.indexable.clear();
+    B.valid = true;
   }
+  d.bshift = B.bshift; d.cshift = B.cshift;
+  if ((rc = upload(ctx, &d.table, reinterpret_cast<const uint4*>(B.tab.data()), B.tab.size() / 4))) return rc;
+  if ((rc = upload(ctx, &d.disp, B.disp.data(), B.disp.size()))) return rc;
+  d.n_ovf = (uint32_t)B.ovf_hash.size();
+  if ((rc = upload(ctx, &d.ovf_hash, B.ovf_hash.data(), B.ovf_hash.size()))) return rc;
+  if ((rc = upload(ctx, &d.ovf_rank, B.ovf_rank.data(), B.ovf_rank.size()))) return rc;
+  if ((rc = upload(ctx, &d.blobw, B.words.data(), B.words.size()))) return rc;
+  if ((rc = upload(ctx, &d.name_meta, B.meta.data(), B.meta.size()))) return rc;
   if ((rc = upload(ctx, &d.chr_lex, bed->chr_lex, (size_t)G))) return rc;
   if ((rc = upload(ctx, &d.chr_begin, bed->chr_begin, (size_t)G))) return rc;
   if ((rc = upload(ctx, &d.chr_end, bed->chr_end, (size_t)G))) return rc;
