@@ -244,3 +244,91 @@ def test_gpu_filter_edge_inputs(tmp_path):
     bad = ("A" * 128 + "\tB\t99.0\t200\t0\t0\t1\t2\t3\t4\t1e-5\t50\n").encode()
     with pytest.raises(NotImplementedError):
         eng.blast_filter(np.frombuffer(bad, dtype=np.uint8))
+
+
+def test_kernel_row_decision_fuzz_against_glibc():
+    """Randomly perturbed rows (number formats, signs, leading zeros, exponents, separators, missing and extra
+    fields, cut-off-exact values): the kernel's row code on both routes must agree with glibc sscanf + C compares
+    for several cut-off sets, or refuse (-1) only where the path documents a refusal (20+ significant digits,
+    10+ digit integers, dangling exponents, inf / nan / hex)."""
+    import ctypes
+    import random
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = ctypes.CDLL(os.path.join(root, "jcvi_b200", "libjx_hostprobe.so"))
+    rng = random.Random(5)
+
+    def num(kind):
+        r = rng.random()
+        if kind == "int":
+            v = rng.choice([0, 1, 99, 100, 101, 150, rng.randint(0, 5000), rng.randint(0, 10 ** 8)])
+            s = str(v)
+            if r < 0.05:
+                s = "0" * rng.randint(1, 3) + s
+            elif r < 0.08:
+                s = "+" + s
+            elif r < 0.11:
+                s = "-" + s
+            return s
+        if kind == "pct":
+            v = rng.choice([95.0, 94.99, 95.01, 60.0, 100.0, rng.uniform(0, 100)])
+            return rng.choice(["%.2f", "%.1f", "%.0f", "%.3f", "%g"]) % v
+        if kind == "ev":
+            if r < 0.15:
+                return rng.choice(["0", "0.0", "0.01", "1e-2", "1e-30", "1.0e-30", "0.010000000000000002", "9.999999999999999e-31", "1e-400", "1e5"])
+            return rng.choice(["%.1e", "%.2e", "%g", "%.0e"]) % (10.0 ** rng.uniform(-60, 2))
+        if kind == "score":
+            v = rng.choice([400.0, 399.99, 400.01, rng.uniform(20, 3000)])
+            return rng.choice(["%.1f", "%.0f", "%g", "%.2e", "%.3g"]) % v
+        raise ValueError(kind)
+
+    def row():
+        q = "g%05d.%d" % (rng.randint(0, 300), rng.randint(1, 3))
+        s = q if rng.random() < 0.05 else "h%05d" % rng.randint(0, 300)
+        f = [q, s, num("pct")] + [num("int") for _ in range(7)] + [num("ev"), num("score")]
+        r = rng.random()
+        sep = "\t"
+        if r < 0.04:
+            f = f[:rng.randint(0, 11)]
+        elif r < 0.07:
+            f += ["extra", "cols"]
+        elif r < 0.10:
+            sep = rng.choice([" ", "  ", " \t"])
+        elif r < 0.12:
+            f[rng.randint(2, 11)] = rng.choice(["abc", "", "1e", ".", "-", "1.2.3", "12abc"])
+        line = sep.join(f)
+        if rng.random() < 0.03:
+            line = " " + line
+        if rng.random() < 0.03:
+            line += rng.choice([" ", "\t", " \t "])
+        return line
+
+    rows = [row() for _ in range(20000)]
+    text = ("\n".join(rows) + "\n").encode()
+    spans = _rows(text)
+    rs = np.array([s for s, _ in spans], dtype=np.int32)
+    re_ = np.array([e for _, e in spans], dtype=np.int32)
+    n_refused = 0
+    for kw in (dict(score=0, pctid=95.0, hitlen=100, evalue=0.01, noself=False, inverse=False),
+               dict(score=400, pctid=60.0, hitlen=150, evalue=1e-30, noself=True, inverse=False),
+               dict(score=-5, pctid=0.0, hitlen=0, evalue=0.0, noself=True, inverse=True)):
+        out = np.zeros(3 * len(spans), dtype=np.int8)
+        route = np.zeros(len(spans), dtype=np.int8)
+        L.probe_filter_rows(text, len(text), rs.ctypes.data_as(ctypes.c_void_p), re_.ctypes.data_as(ctypes.c_void_p),
+                            ctypes.c_long(len(spans)), ctypes.c_double(kw["score"]), ctypes.c_double(kw["pctid"]),
+                            ctypes.c_longlong(kw["hitlen"]), ctypes.c_double(kw["evalue"]), int(kw["noself"]),
+                            int(kw["inverse"]), out.ctypes.data_as(ctypes.c_void_p), route.ctypes.data_as(ctypes.c_void_p))
+        out = out.reshape(-1, 3)
+        for col in (0, 1):
+            decided = out[:, col] >= 0
+            bad = np.nonzero(decided & (out[:, col] != out[:, 2]))[0]
+            assert len(bad) == 0, (kw, col, [(rows[i], out[i].tolist(), int(route[i])) for i in bad[:5]])
+        refused = np.nonzero(out[:, 0] < 0)[0]
+        n_refused += len(refused)
+        for i in refused[:50]:                      # refusals must be explicable
+            toks = rows[i].split()
+            assert (any(len(t.lstrip("+-").lstrip("0")) >= 10 for t in toks[3:10])
+                    or any(len(t.split("e")[0].replace(".", "").lstrip("+-0")) > 19 for t in toks[2:])
+                    or any(t[-1:] in "eE" or t[-2:] in ("e+", "e-", "E+", "E-") for t in toks[2:])), rows[i]     # dangling exponent
+        assert route.mean() > 0.3            # both routes get their share of the rows
+    assert n_refused < 0.02 * 3 * len(rows)
