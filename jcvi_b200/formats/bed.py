@@ -66,7 +66,15 @@ class Bed(list):
     def __init__(self, filename=None, key=None, sorted=True):
         super().__init__()
         self.filename = filename
-        self.nullkey = lambda x: (natsort_key(x.seqid), x.start, x.accn)
+        seqid_keys = {}                    # a BED has few distinct seqids: one natural-sort key per seqid, not per row
+
+        def nullkey(x):
+            k = seqid_keys.get(x.seqid)
+            if k is None:
+                k = seqid_keys[x.seqid] = natsort_key(x.seqid)
+            return (k, x.start, x.accn)
+
+        self.nullkey = nullkey
         self.key = key or self.nullkey
         self._tables = None
         if not filename:
