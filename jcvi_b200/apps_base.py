@@ -39,6 +39,13 @@ class OptionParser(ArgumentParser):
         self.add_argument("-o", "--outfile", default=outfile, help="Outfile name")
 
 
+def file_key(path):
+    """Identity of a file's current contents for in-process caches: (absolute path, mtime in ns, size)."""
+    import os
+    st = os.stat(path)
+    return (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+
+
 def read_text_file(path):
     """Whole file as a uint8 array (gz/bz2 transparently, like must_open formats/base.py:473-550)."""
     import numpy as np

@@ -62,6 +62,15 @@ class AnchorFile(object):
         self.filename = filename
         self.blocks = list(self.iter_blocks(minsize=minsize))
 
+    @classmethod
+    def from_blocks(cls, filename, blocks):
+        """The AnchorFile of a file whose blocks the caller already holds (rows = [a, b, score]); what parsing
+        `filename` would give, without reading it again."""
+        self = cls.__new__(cls)
+        self.filename = filename
+        self.blocks = [list(b) for b in blocks] if blocks else [[]]
+        return self
+
     def _raw_blocks(self):
         with open(self.filename) as fp:
             return split_blocks(fp.readlines())

@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-from ..apps_base import OptionParser, logger, read_text_file
+from ..apps_base import OptionParser, logger, read_text_file, file_key
 from ..engine import get_engine
 
 
@@ -71,8 +71,13 @@ def blastfilter_main(blast_file, p, opts):
     excl = _exclude_keys(opts.exclude, qorder, sorder) if opts.exclude else None
     if excl is not None:
         logger.debug("running excluded pairs (--exclude `{}`) ..".format(opts.exclude))
-    res = eng.blastfilter(text, strip_names=opts.strip_names, cscore=opts.cscore, tandem_Nmax=opts.tandem_Nmax,
+    # one upload: the table stays resident, and `synteny liftover` of the same (unchanged) file in this process --
+    # catalog.ortholog's next step -- neither reads nor copies it again
+    key = file_key(blast_file)
+    dev = eng.upload(text)
+    res = eng.blastfilter(dev, strip_names=opts.strip_names, cscore=opts.cscore, tandem_Nmax=opts.tandem_Nmax,
                           exclude_keys=excl, want_text=True, want_mothers=bool(opts.tandems_only))
+    eng.remember_text(key, dev)
     st = res.stats
     logger.debug("Load BLAST file `{}` (total {} lines)".format(blast_file, st["lines"]))
     if st["unmapped"]:

@@ -10,7 +10,7 @@ from collections.abc import Iterable
 
 import numpy as np
 
-from ..apps_base import OptionParser, logger, read_text_file
+from ..apps_base import OptionParser, file_key, logger, read_text_file
 from ..engine import get_engine
 from ..formats.bed import Bed
 from .base import AnchorFile
@@ -135,15 +135,8 @@ def _describe(values):
         v.min(), v.max(), v.size, np.mean(v), np.std(v), np.median(v), v.sum())
 
 
-def summary(args):
-    """Block statistics on stderr; ValueError when the file holds no anchor (synteny.py:1445-1484)."""
-    p = OptionParser(summary.__doc__)
-    p.add_argument("--prefix", help="Generate per block stats")
-    opts, args = p.parse_args(args)
-    if len(args) != 1:
-        sys.exit(not p.print_help())
-    blocks = AnchorFile(args[0]).blocks
-    if blocks == [[]]:
+def _summary_blocks(blocks, prefix=None):
+    if not blocks or blocks == [[]]:
         logger.debug("A total of 0 anchor was found. Aborted.")
         raise ValueError("A total of 0 anchor was found. Aborted.")
     sizes = [len(b) for b in blocks]
@@ -152,10 +145,20 @@ def summary(args):
     print("A total of {0} (NR:{1}) anchors found in {2} clusters.".format(sum(sizes), sum(nr_sizes), len(blocks)), file=err)
     print("Stats:", _describe(sizes), file=err)
     print("NR stats:", _describe(nr_sizes), file=err)
-    if opts.prefix:
+    if prefix:
         width = len(str(len(blocks)))
         for i, n in enumerate(sizes, 1):
-            print("{0}{1:0{2}d}\t{3}".format(opts.prefix, i, width, n))
+            print("{0}{1:0{2}d}\t{3}".format(prefix, i, width, n))
+
+
+def summary(args):
+    """Block statistics on stderr; ValueError when the file holds no anchor (synteny.py:1445-1484)."""
+    p = OptionParser(summary.__doc__)
+    p.add_argument("--prefix", help="Generate per block stats")
+    opts, args = p.parse_args(args)
+    if len(args) != 1:
+        sys.exit(not p.print_help())
+    _summary_blocks(AnchorFile(args[0]).blocks, opts.prefix)
 
 
 def _int_str(x):
@@ -163,18 +166,21 @@ def _int_str(x):
 
 
 def write_anchors(res, qbed, sbed, anchor_file):
-    """scan's writer (synteny.py:1897-1903)."""
+    """scan's writer (synteny.py:1897-1903).  Returns the blocks as AnchorFile would parse them back."""
     qa = qbed.tables()["accns"]
     sa = sbed.tables()["accns"]
     out = []
+    blocks = []
     bs = res.block_start
     q, s, sc = res.q_rank.tolist(), res.s_rank.tolist(), res.score.astype(np.float64).tolist()
     for b in range(res.n_blocks):
         out.append("###\n")
-        for t in range(bs[b], bs[b + 1]):
-            out.append("%s\t%s\t%s\n" % (qa[q[t]], sa[s[t]], _int_str(sc[t])))
+        rows = [[qa[q[t]], sa[s[t]], _int_str(sc[t])] for t in range(bs[b], bs[b + 1])]
+        out.extend("%s\t%s\t%s\n" % (r[0], r[1], r[2]) for r in rows)
+        blocks.append(rows)
     with open(anchor_file, "w") as fw:
         fw.write("".join(out))
+    return blocks
 
 
 def scan(args):
@@ -199,8 +205,8 @@ def scan(args):
     res = eng.scan_text(read_text_file(blast_file), strip_names=False, xdist=dist, ydist=dist, N=opts.n,
                         intrabound=opts.intrabound)
     logger.debug("A total of %d BLAST imported from `%s`.", res.stats["hits"], blast_file)
-    write_anchors(res, qbed, sbed, anchor_file)
-    summary([anchor_file])
+    blocks = write_anchors(res, qbed, sbed, anchor_file)
+    _summary_blocks(blocks)                        # of the file just written (the reference re-reads it)
 
     lo = opts.liftover
     if not lo:
@@ -210,10 +216,10 @@ def scan(args):
         dargs += ["--no_strip_names"]
     liftover_dist = opts.liftover_dist or dist // 2
     dargs += ["--dist={}".format(liftover_dist)]
-    return liftover([lo, anchor_file] + dargs)
+    return liftover([lo, anchor_file] + dargs, _blocks=blocks)
 
 
-def liftover(args):
+def liftover(args, _blocks=None):
     """
     %prog liftover blastfile anchorfile [options]
 
@@ -229,7 +235,8 @@ def liftover(args):
     eng = get_engine()
     eng.load_pair(qbed, sbed, is_self)
 
-    ac = AnchorFile(anchor_file)
+    # _blocks: scan() hands over the blocks of the anchors file it has just written
+    ac = AnchorFile.from_blocks(anchor_file, _blocks) if _blocks is not None else AnchorFile(anchor_file)
     lines = [(row, bi) for bi, block in enumerate(ac.blocks) for row in block]
     a_qi = np.fromiter((qorder[r[0]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
                        dtype=np.int32, count=len(lines))
@@ -238,7 +245,11 @@ def liftover(args):
     a_block = np.fromiter((bi for _, bi in lines), dtype=np.int32, count=len(lines))
     logger.debug("A total of {0} anchors imported.".format(int((a_qi >= 0).sum())))
 
-    res = eng.liftover_text(read_text_file(blast_file), a_qi, a_si, a_block, strip_names=opts.strip_names, dist=dist)
+    # the raw table blastfilter uploaded in this process, if it is still resident and the file is unchanged
+    text = eng.recall_text(file_key(blast_file))
+    if text is None:
+        text = read_text_file(blast_file)
+    res = eng.liftover_text(text, a_qi, a_si, a_block, strip_names=opts.strip_names, dist=dist)
     logger.debug("A total of %d BLAST imported from `%s`.", res.stats["hits"], blast_file)
 
     qa = qbed.tables()["accns"]
@@ -260,7 +271,7 @@ def liftover(args):
             accepted[(qa[q], sa[s])] = _int_str(sc)
         ac.filter_blocks(accepted)
     ac.print_to_file(filename=newanchorfile)
-    summary([newanchorfile])
+    _summary_blocks(ac.blocks)                     # of the file just written
     return newanchorfile
 
 

@@ -186,6 +186,7 @@ class Engine(object):
 
     def distinct_names(self, text, strip_names=True, seed=0):
         """-> (list of representative raw lines (bytes, no terminator), uint8 side per line, stats dict)"""
+        self._held_key = None
         p, n, dev, keep = _text_ptr(text)
         buf = ctypes.c_void_p(); ln = ctypes.c_int64(); side = ctypes.c_void_p(); cnt = ctypes.c_int64()
         st = (ctypes.c_int64 * 4)()
@@ -201,6 +202,7 @@ class Engine(object):
 
     def blast_cscore(self, text, cutoff=0.9999, strip_names=True, pct=False, writeblast=False):
         """`jcvi.formats.blast cscore` in one call -> (cscore file bytes, --writeblast file bytes or None, stats)."""
+        self._held_key = None
         p, n, dev, keep = _text_ptr(text)
         out = ctypes.c_void_p(); ln = ctypes.c_int64(); bout = ctypes.c_void_p(); bln = ctypes.c_int64()
         st = (ctypes.c_int64 * 4)()
@@ -222,6 +224,7 @@ class Engine(object):
         """`jcvi.formats.blast filter` -> (bytes of the kept rows, stats).  ids: iterable of names (bytes) or None.
         sink: a binary file object; the rows are then written to it straight from the library's buffer (no Python
         copy of a multi-GB result) and b"" is returned in their place."""
+        self._held_key = None
         use_ids = bool(ids)
         if use_ids:
             self.load_names(sorted(set(ids)))
@@ -265,11 +268,23 @@ class Engine(object):
         if dev:
             raise ValueError("text is already on the device")
         out = ctypes.c_uint64()
+        self._held_key = None
         self._check(self.lib.jx_text_upload(self.ctx, p, n, ctypes.byref(out)))
         return DeviceText(out.value, n, keep)
 
     def release_text(self):
+        self._held_key = None
         self._check(self.lib.jx_text_release(self.ctx))
+
+    def remember_text(self, key, dev):
+        """Name the text Engine.upload returned last (e.g. apps_base.file_key of the file it came from)."""
+        self._held_key = (key, dev)
+
+    def recall_text(self, key):
+        """The resident DeviceText remembered under `key`, or None.  Every call that may replace the library's held
+        text (upload, release_text, cscore_begin, blast_cscore, blast_filter, distinct_names, near_lines) forgets it."""
+        hk = getattr(self, "_held_key", None)
+        return hk[1] if hk is not None and hk[0] == key else None
 
     def set_record_reuse(self, on=True):
         """liftover re-uses the records blastfilter tokenized from the same resident text (default);
@@ -371,6 +386,7 @@ class Engine(object):
     def cscore_begin(self, text, strip_names=True, exclude_keys=None):
         """Tokenize this rank's slice, accumulate the local per-name best scores.  Returns
         (device pointer of the table, number of entries): int32-orderable float bits."""
+        self._held_key = None
         p, n, dev, keep = _text_ptr(text)
         ek = None
         if exclude_keys is not None and len(exclude_keys):
@@ -423,6 +439,7 @@ class Engine(object):
     def near_lines(self, text, a_qi, a_si, strip_names=True, dist=10, device=False):
         """-> (uint8 array of the raw lines whose hit lies within `dist` of an anchor; count).
         device=True: a torch CUDA tensor viewing the library's device buffer instead."""
+        self._held_key = None
         p, n, dev, keep = _text_ptr(text)
         a_qi = np.ascontiguousarray(a_qi, dtype=np.int32)
         a_si = np.ascontiguousarray(a_si, dtype=np.int32)

@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""The drop-in CLI functions file to file on the C2 table (20 M hits, 1.43 GB): what a user of
+`python -m jcvi_b200.compara.blastfilter` / `... synteny scan --liftover` waits for, BED loading, file reads,
+Python and output writing included.  Reporting aid."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import bench
+from jcvi_b200.compara import blastfilter, synteny
+
+hits = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
+w = bench.make_workload(100, hits)
+d = w["dir"]
+last = os.path.join(d, "A.B.last")
+w["text"].tofile(last)
+for rep in range(2):
+    t0 = time.perf_counter()
+    blastfilter.main([last, "--cscore=0.7"])
+    t1 = time.perf_counter()
+    out = synteny.scan([last + ".filtered", os.path.join(d, "A.B.anchors"), "--liftover=" + last])
+    t2 = time.perf_counter()
+    print("rep %d: blastfilter.main %.2f s, synteny.scan --liftover %.2f s, total %.2f s = %.3g hits/s file to file (%s: %d bytes)" % (
+        rep, t1 - t0, t2 - t1, t2 - t0, w["n_hits"] / (t2 - t0), os.path.basename(out), os.path.getsize(out)), flush=True)
