@@ -57,4 +57,11 @@ def read_text_file(path):
         import bz2
         with bz2.open(path, "rb") as fh:
             return np.frombuffer(fh.read(), dtype=np.uint8)
+    import os
+    if os.path.getsize(path) >= (64 << 20):
+        # a large table is mapped, not copied: the upload reads the page cache directly (read-only view)
+        try:
+            return np.memmap(path, dtype=np.uint8, mode="r")
+        except (OSError, ValueError):
+            pass
     return np.fromfile(path, dtype=np.uint8)

@@ -20,3 +20,11 @@ for rep in range(2):
     t2 = time.perf_counter()
     print("rep %d: blastfilter.main %.2f s, synteny.scan --liftover %.2f s, total %.2f s = %.3g hits/s file to file (%s: %d bytes)" % (
         rep, t1 - t0, t2 - t1, t2 - t0, w["n_hits"] / (t2 - t0), os.path.basename(out), os.path.getsize(out)), flush=True)
+# the files against the C-ABI path on the in-memory table (the CLI maps large files instead of reading them)
+from jcvi_b200.engine import get_engine
+eng = get_engine()
+f = eng.blastfilter(w["text"], cscore=0.7, want_text=True)
+same = bytes(memoryview(f.text)) == open(last + ".filtered", "rb").read()
+print(".filtered written by the CLI == C-ABI result on the in-memory table:", same, flush=True)
+assert same
+
