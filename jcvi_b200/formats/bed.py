@@ -84,11 +84,19 @@ class Bed(list):
         if sorted:
             self.sort(key=self.key)
 
+    def sort(self, *args, **kwargs):
+        self._order = None                 # ranks change: drop what was derived from the old order
+        self._tables = None
+        super().sort(*args, **kwargs)
+
     @property
     def order(self):
         """accn -> (rank, BedLine); for duplicated accns the later rank wins, like the reference's
         dict comprehension."""
-        return {f.accn: (i, f) for i, f in enumerate(self)}
+        cached = getattr(self, "_order", None)
+        if cached is None or cached[0] != len(self):           # built once per (unchanged) list, not per access
+            cached = self._order = (len(self), {f.accn: (i, f) for i, f in enumerate(self)})
+        return cached[1]
 
     @property
     def seqids(self):
