@@ -233,3 +233,62 @@ def test_result_views_keep_the_library_result_alive():
     gc.collect()
     assert freed == [1]
     assert len(C.view_np(None, 0, np.int32, None)) == 0
+
+
+def test_in_memory_hand_over_equals_reading_the_files_back(tmp_path, capsys):
+    """scan() hands its freshly written blocks to summary / liftover instead of parsing the file again:
+    AnchorFile.from_blocks must equal AnchorFile(file) for what write_anchors / print_to_file emit, and the
+    in-memory summary must print what summary([file]) prints (and raise the same ValueError on nothing)."""
+    import pytest
+    from jcvi_b200.compara.base import AnchorFile
+    from jcvi_b200.compara import synteny as gsyn
+    blocks = [[["a1", "b1", "120"], ["a2", "b2", "98"], ["a2", "b3", "55L"]], [["a9", "b7", "300"]]]
+    ac = AnchorFile.from_blocks(str(tmp_path / "x.anchors"), blocks)
+    ac.print_to_file(str(tmp_path / "x.anchors"))
+    back = AnchorFile(str(tmp_path / "x.anchors"))
+    assert [[list(r) for r in b] for b in back.blocks] == blocks == [[list(r) for r in b] for b in ac.blocks]
+    gsyn._summary_blocks(ac.blocks)
+    mem = capsys.readouterr().err
+    gsyn.summary([str(tmp_path / "x.anchors")])
+    assert capsys.readouterr().err == mem and "A total of 4 (NR:3) anchors found in 2 clusters." in mem
+    (tmp_path / "empty.anchors").write_text("")
+    assert AnchorFile(str(tmp_path / "empty.anchors")).blocks == AnchorFile.from_blocks("e", []).blocks == [[]]
+    for call in (lambda: gsyn._summary_blocks([]), lambda: gsyn._summary_blocks([[]]), lambda: gsyn.summary([str(tmp_path / "empty.anchors")])):
+        with pytest.raises(ValueError, match="A total of 0 anchor was found. Aborted."):
+            call()
+
+
+def test_read_text_file_maps_large_tables_and_file_key_tracks_changes(tmp_path):
+    import os
+    import numpy as np
+    from jcvi_b200.apps_base import file_key, read_text_file
+    small = tmp_path / "s.last"
+    small.write_bytes(b"a\tb\n" * 10)
+    assert isinstance(read_text_file(str(small)), np.ndarray) and not isinstance(read_text_file(str(small)), np.memmap)
+    big = tmp_path / "b.last"
+    line = b"Ag000001.1\tBg000002.1\t99.0\t100\t0\t0\t1\t100\t1\t100\t1e-50\t200.0\n"
+    with open(big, "wb") as fw:
+        for _ in range(70):
+            fw.write(line * 16384)
+    m = read_text_file(str(big))
+    assert isinstance(m, np.memmap) and len(m) == os.path.getsize(big) and m[:len(line)].tobytes() == line
+    k0 = file_key(str(big))
+    assert k0 == file_key(str(big))
+    with open(big, "ab") as fw:
+        fw.write(line)
+    assert file_key(str(big)) != k0
+    import gzip
+    gz = tmp_path / "g.last.gz"
+    with gzip.open(gz, "wb") as fw:
+        fw.write(line * 3)
+    assert read_text_file(str(gz)).tobytes() == line * 3
+
+
+def test_bed_order_cache_follows_a_resort(tmp_path):
+    from jcvi_b200.formats.bed import Bed
+    p = tmp_path / "x.bed"
+    p.write_text("chr2\t10\t20\tg3\nchr1\t30\t40\tg2\nchr1\t5\t9\tg1\n")
+    b = Bed(str(p))
+    assert [f.accn for f in b] == ["g1", "g2", "g3"] and b.order["g3"][0] == 2 and b.order is b.order
+    b.sort(key=lambda f: -f.start)
+    assert b.order["g2"][0] == 0 and b.order["g1"][0] == 2
