@@ -1,0 +1,18 @@
+"""The oracle against the live reference on randomized inputs -- only where the reference tree exists (the build
+container); skipped on the GPU box.  See tests/live_reference_check.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(os.environ.get("JCVI_REFERENCE", "/root/reference"), "src", "jcvi")),
+                    reason="reference tree not present")
+def test_oracle_equals_live_reference_on_randomized_inputs():
+    out = subprocess.run([sys.executable, os.path.join(HERE, "live_reference_check.py")], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "LIVE_REFERENCE_OK" in out.stdout
