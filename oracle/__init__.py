@@ -11,6 +11,7 @@ from .oracle import (  # noqa: F401
     cscore,
     blast_filter,
     mcscan,
+    simple,
     kdtree,
     gene_name,
     natcmp,

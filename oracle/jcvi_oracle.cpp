@@ -1225,4 +1225,118 @@ int orc_mcscan(const char* bed_path, const char* anchor_path, const char* out_pa
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------
+// synteny simple  (src/jcvi/compara/synteny.py:1137-1316): the block ends of every block of an anchors file.
+//   get_orientation 222-236 (np.polyfit slope: restated as the sign of the exact integer covariance
+//   n*sum(xy) - sum(x)*sum(y); a covariance of exactly 0 gives a slope of +-rounding noise in the reference --
+//   "+" here, parity unpinned for such flat blocks), get_boundary_bases 1124-1134, range_minmax utils/range.py:157-168.
+// mode bits: 1 --rich, 2 --coords, 4 --noheader, 8 --bed (implies --coords; bed_path receives <simple>.bed)
+// returns 0, 1 (no blocks: the reference logs an error and returns), -1 I/O, -4 KeyError, -5 ValueError,
+// -7 AssertionError (a block end on two seqids)
+// ---------------------------------------------------------------------------------
+int orc_simple(const char* anchor_file, const char* qbed_path, const char* sbed_path, const char* out_path, int mode,
+               const char* bed_path) {
+  const bool rich = mode & 1, noheader = mode & 4, bedout = mode & 8, coords = (mode & 2) || bedout;
+  Beds beds;
+  if (!load_beds(qbed_path, sbed_path, beds)) return -1;
+  AnchorBlocks ac;
+  if (!load_anchors(anchor_file, ac)) return -1;
+  if (ac.blocks.empty() || ac.blocks[0].empty()) return 1;          // AnchorFile.is_empty
+  std::string af(anchor_file);
+  std::string pf;                                                   // "-".join(anchorfile.split(".", 2)[:2])
+  {
+    size_t d1 = af.find('.');
+    if (d1 == std::string::npos) pf = af;
+    else {
+      size_t d2 = af.find('.', d1 + 1);
+      pf = af.substr(0, d1) + "-" + af.substr(d1 + 1, d2 == std::string::npos ? std::string::npos : d2 - d1 - 1);
+    }
+  }
+  FILE* fw = fopen(out_path, "w");
+  if (!fw) return -1;
+  if (!noheader) {
+    if (coords) fputs("Block\tChr\tStart\tEnd\tSpan\tStartGene\tEndGene\tGeneSpan\tOrientation\n", fw);
+    else {
+      fputs("StartGeneA\tEndGeneA\tStartGeneB\tEndGeneB\tOrientation\tScore", fw);
+      if (rich) fputs("\tStartOrderA\tEndOrderA\tStartOrderB\tEndOrderB\tSizeA\tSizeB\tSize\tBlock", fw);
+      fputc('\n', fw);
+    }
+  }
+  struct BB { std::string seqid; long start, end; std::string accn; long size; char orient; };
+  std::vector<BB> bbed;
+  int rc = 0;
+  for (size_t i = 0; i < ac.blocks.size() && !rc; ++i) {
+    const auto& block = ac.blocks[i];
+    if (block.empty()) { rc = -5; break; }                           // zip(*block) of nothing
+    std::vector<long> ia, ib;
+    for (const auto& row : block) {
+      if (row.size() != 3) { rc = -5; break; }
+      auto qa = beds.q.order.find(row[0]);
+      auto sa = beds.s.order.find(row[1]);
+      if (qa == beds.q.order.end() || sa == beds.s.order.end()) { rc = -4; break; }
+      ia.push_back(qa->second); ib.push_back(sa->second);
+    }
+    if (rc) break;
+    const long astarti = *std::min_element(ia.begin(), ia.end()), aendi = *std::max_element(ia.begin(), ia.end());
+    const long bstarti = *std::min_element(ib.begin(), ib.end()), bendi = *std::max_element(ib.begin(), ib.end());
+    const BedLine &as = beds.q.rows[(size_t)astarti], &ae = beds.q.rows[(size_t)aendi];
+    const BedLine &bs = beds.s.rows[(size_t)bstarti], &be = beds.s.rows[(size_t)bendi];
+    const size_t sizeA = std::set<long>(ia.begin(), ia.end()).size(), sizeB = std::set<long>(ib.begin(), ib.end()).size();
+    const size_t size = block.size();
+    char orient = '+';
+    if (ia.size() >= 2) {
+      __int128 n = (long long)ia.size(), sx = 0, sy = 0, sxy = 0;
+      for (size_t k = 0; k < ia.size(); ++k) { sx += ia[k]; sy += ib[k]; sxy += (__int128)ia[k] * ib[k]; }
+      const __int128 cov = n * sxy - sx * sy;
+      orient = cov >= 0 ? '+' : '-';
+    }
+    const long aspan = aendi - astarti + 1, bspan = bendi - bstarti + 1;
+    const long score = (long)std::pow((double)(aspan * bspan), 0.5);   // int((aspan * bspan) ** 0.5)
+    const std::string block_id = pf + "-block-" + std::to_string(i);
+    if (coords) {
+      if (as.seqid != ae.seqid || bs.seqid != be.seqid) { rc = -7; break; }
+      auto minmax = [](const BedLine& s, const BedLine& e, long& lo, long& hi) {   // range_minmax of the two genes
+        lo = std::min(std::make_pair(s.start, s.end), std::make_pair(e.start, e.end)).first;
+        hi = e.end > s.end ? e.end : s.end;            // max(..., key=end): the first of equal ends, same value
+      };
+      long alo, ahi, blo, bhi;
+      minmax(as, ae, alo, ahi); minmax(bs, be, blo, bhi);
+      fprintf(fw, "%s\t%s\t%ld\t%ld\t%ld\t%s\t%s\t%ld\t+\n", block_id.c_str(), as.seqid.c_str(), alo, ahi, ahi - alo + 1,
+              as.accn.c_str(), ae.accn.c_str(), aspan);
+      fprintf(fw, "%s\t%s\t%ld\t%ld\t%ld\t%s\t%s\t%ld\t%c\n", block_id.c_str(), bs.seqid.c_str(), blo, bhi, bhi - blo + 1,
+              bs.accn.c_str(), be.accn.c_str(), bspan, orient);
+      if (bedout) {
+        char nm[512];
+        snprintf(nm, sizeof nm, "%s:%ld-%ld", as.seqid.c_str(), alo, ahi);
+        bbed.push_back({bs.seqid, blo, bhi, nm, (long)size, orient});   // BedLine: start = (blo - 1) + 1
+      }
+      continue;
+    }
+    fprintf(fw, "%s\t%s\t%s\t%s\t%ld\t%c", as.accn.c_str(), ae.accn.c_str(), bs.accn.c_str(), be.accn.c_str(), score, orient);
+    if (rich) fprintf(fw, "\t%ld\t%ld\t%ld\t%ld\t%zu\t%zu\t%zu\t%s", astarti, aendi, bstarti, bendi, sizeA, sizeB, size, block_id.c_str());
+    fputc('\n', fw);
+  }
+  fclose(fw);
+  if (rc) return rc;
+  if (bedout) {
+    if (!bed_path || !*bed_path) return -1;
+    // Bed.print_to_file(sorted=True): key (natsort_key(seqid), start, accn); BedLine.__str__ = seqid, start-1, end, accn, score, strand
+    std::stable_sort(bbed.begin(), bbed.end(), [](const BB& a, const BB& b) {
+      int c = natcmp(a.seqid, b.seqid);
+      if (c) return c < 0;
+      if (a.start != b.start) return a.start < b.start;
+      return a.accn < b.accn;
+    });
+    FILE* fb = fopen(bed_path, "w");
+    if (!fb) return -1;
+    for (const BB& b : bbed) {
+      long start = b.start < 1 ? 1 : b.start;                        // "Start < 1. Reset start"
+      fprintf(fb, "%s\t%ld\t%ld\t%s\t%ld\t%c\n", b.seqid.c_str(), start - 1, b.end, b.accn.c_str(), b.size, b.orient);
+    }
+    fclose(fb);
+  }
+  return 0;
+}
+
 }  // extern "C"

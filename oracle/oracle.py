@@ -112,6 +112,21 @@ def mcscan(bedfile, anchorfile, out_path, iter=100, ascii=False, Nm=10, trackids
     _check(rc)
 
 
+def simple(anchorfile, qbed, sbed, out_path, rich=False, coords=False, noheader=False, bed=False):
+    """compara/synteny.py:1137-1316 (`jcvi.compara.synteny simple`); writes out_path (+ out_path + ".bed" with bed=True).
+    Returns False when the anchors file holds no block (the reference logs an error and returns)."""
+    mode = (1 if rich else 0) | (2 if coords else 0) | (4 if noheader else 0) | (8 if bed else 0)
+    rc = _lib().orc_simple(_b(anchorfile), _b(qbed), _b(sbed), _b(out_path), mode, _b(out_path + ".bed") if bed else _b(None))
+    if rc == -4:
+        raise KeyError(_lib().orc_last_error().decode())
+    if rc == -5:
+        raise ValueError(_lib().orc_last_error().decode())
+    if rc == -7:
+        raise AssertionError("block end genes on different seqids")
+    _check(rc)
+    return rc == 0
+
+
 def kdtree(anchors, queries, bound):
     """Restated cKDTree(anchors, leafsize=16).query(queries, p=1, distance_upper_bound=bound)."""
     a = np.ascontiguousarray(anchors, dtype=np.int64).reshape(-1, 2)

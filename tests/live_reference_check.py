@@ -93,6 +93,50 @@ def main():
             if kw.get("trackids"):
                 assert rd(out + ".tracks") == rd(out + ".orc.tracks"), ("mcscan tracks", seed)
             n_checked += 1
+    # ---- simple: random small blocks; rows of blocks whose rank covariance is exactly 0 are compared without the
+    # orientation column (np.polyfit returns rounding noise of either sign there; the oracle says "+")
+    os.chdir(d)
+    flat_total = flat_diff = 0
+    for seed in range(6):
+        rng = random.Random(100 + seed)
+        G = 60
+        for nm in ("x", "y"):
+            with open("%s%d.bed" % (nm, seed), "w") as fw:
+                for i in range(G):
+                    fw.write("%schr%d\t%d\t%d\t%s%02d\n" % (nm, 1 + i // 30, 100 * i, 100 * i + 50 + 7 * (i % 3), nm, i))
+        flat = []
+        with open("x%d.y%d.anchors" % (seed, seed), "w") as fw:
+            for b in range(25):
+                fw.write("###\n")
+                lo = rng.choice([0, 30])
+                n = rng.randint(1, 6)
+                xs = [lo + rng.randint(0, 29) for _ in range(n)]
+                ys = [lo + rng.randint(0, 29) for _ in range(n)]
+                if rng.random() < 0.3:
+                    ys = [ys[0]] * n                                 # a flat block
+                for x, y in zip(xs, ys):
+                    fw.write("x%02d\ty%02d\t%d\n" % (x, y, rng.randint(10, 500)))
+                flat.append(n * sum(a * b for a, b in zip(xs, ys)) - sum(xs) * sum(ys) == 0 and n >= 2)
+        anchors = "x%d.y%d.anchors" % (seed, seed)
+        for tag, argv, kw in (("r", ["--rich"], dict(rich=True)), ("c", ["--coords"], dict(coords=True))):
+            ref_syn.simple([anchors, "--qbed=x%d.bed" % seed, "--sbed=y%d.bed" % seed] + argv)
+            ref_out = anchors.rsplit(".", 1)[0] + ".simple"
+            oracle.simple(anchors, "x%d.bed" % seed, "y%d.bed" % seed, ref_out + ".orc", **kw)
+            rl, ol = rd(ref_out).decode().split("\n"), rd(ref_out + ".orc").decode().split("\n")
+            assert len(rl) == len(ol), ("simple", seed, tag)
+            per = 2 if kw.get("coords") else 1
+            for k, (a, b) in enumerate(zip(rl[1:], ol[1:])):
+                blk = k // per
+                if a == b or blk >= len(flat):
+                    continue
+                assert flat[blk], ("simple", seed, tag, a, b)
+                col = 8 if kw.get("coords") else 5
+                fa, fb = a.split("\t"), b.split("\t")
+                assert fa[:col] + fa[col + 1:] == fb[:col] + fb[col + 1:], ("simple flat", a, b)
+                flat_diff += 1
+            flat_total += sum(flat)
+            n_checked += 1
+    print("simple: %d flat blocks compared without orientation, %d of them differ in it" % (flat_total, flat_diff))
     # ---- the path itself on fresh seeds (the committed goldens pin fixed ones) ----------------------------------
     from jcvi.compara import blastfilter as ref_bf
     from jcvi_b200 import synth
