@@ -275,6 +275,14 @@ int jx_mcscan(jx_ctx* ctx, const double* start, const double* end, const int64_t
               int64_t n_ranges, int32_t max_iter, const int32_t* pair_gene, const int32_t* pair_partner,
               const int32_t* pair_block, int64_t n_pairs, int32_t n_genes, int32_t n_blocks, int32_t* n_tracks,
               int32_t** track_len, int32_t** track_blocks, int64_t** track_score, int32_t** table);
+/* `jcvi.compara.synteny simple` (src/jcvi/compara/synteny.py:1137-1316), the per-block reductions of its loop body
+ * (1206-1228): for the anchors (block, query rank, subject rank) [n] of an anchors file with n_blocks blocks ->
+ * per block: min / max rank on both sides (astarti, aendi, bstarti, bendi), size (= len(block)), the number of
+ * distinct ranks per side (sizeA, sizeB), and sum(x'), sum(y'), sum(x'y') of the ranks centred at the block minima --
+ * get_orientation's slope (222-236) has the sign of  size * sum_qs - sum_q * sum_s.  Caller-owned arrays of n_blocks. */
+int jx_block_stats(jx_ctx* ctx, const int32_t* block, const int32_t* qrank, const int32_t* srank, int64_t n,
+                   int32_t n_blocks, int32_t* qmin, int32_t* qmax, int32_t* smin, int32_t* smax, uint32_t* size,
+                   uint32_t* distinct_q, uint32_t* distinct_s, uint64_t* sum_q, uint64_t* sum_s, uint64_t* sum_qs);
 /* float32 best score per name id of the open jx_cscore_begin session (first n entries) */
 int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
 /* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */

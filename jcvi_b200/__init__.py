@@ -21,7 +21,7 @@ def install():
     jsyn = importlib.import_module("jcvi.compara.synteny")
     jbf.main = bf.main
     jbf.blastfilter_main = bf.blastfilter_main
-    for name in ("scan", "liftover", "batch_scan", "synteny_scan", "synteny_liftover", "mcscan"):
+    for name in ("scan", "liftover", "batch_scan", "synteny_scan", "synteny_liftover", "mcscan", "simple"):
         setattr(jsyn, name, getattr(syn, name))
     try:                                   # formats.blast cscore
         from .formats import blast as gblast

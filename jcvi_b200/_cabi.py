@@ -61,7 +61,7 @@ EXPORTS = [
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
     "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse", "jx_distinct_names", "jx_best_table_copy", "jx_session_counts",
-    "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter", "jx_mcscan",
+    "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter", "jx_mcscan", "jx_block_stats",
     "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
 ]
 
@@ -137,6 +137,7 @@ def lib():
                                 ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                 ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_void_p),
                                 ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+        L.jx_block_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32] + [ctypes.c_void_p] * 10
         L.jx_free.argtypes = [ctypes.c_void_p]
         L.jx_free.restype = None
         sizes = (ctypes.c_int32 * 6)()

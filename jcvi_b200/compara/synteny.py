@@ -400,10 +400,127 @@ def mcscan(args):
         logger.debug("Block IDs written to `{0}`.".format(ofile + ".tracks"))
 
 
+def get_orientation(ia, ib):
+    """synteny.py:222-236 (the reference's own numpy call; used here only for blocks whose covariance is exactly 0,
+    where its sign is rounding noise that no restatement can reproduce)."""
+    if len(ia) != len(ib) or len(ia) < 2:
+        return "+"
+    slope, _ = np.polyfit(ia, ib, 1)
+    return "+" if slope >= 0 else "-"
+
+
+def simple(args):
+    """
+    %prog simple anchorfile --qbed=qbedfile --sbed=sbedfile [options]
+
+    Write the block ends for each block in the anchorfile.
+    GeneA1    GeneA2    GeneB1    GeneB2   +/-      score
+
+    Optional additional columns:
+    orderA1   orderA2   orderB1   orderB2  sizeA    sizeB   size    block_id
+
+    With base coordinates (--coords):
+    block_id  seqidA    startA    endA     bpSpanA  GeneA1   GeneA2  geneSpanA
+    block_id  seqidB    startB    endB     bpSpanB  GeneB1   GeneB2  geneSpanB
+    """
+    p = OptionParser(simple.__doc__)
+    p.add_argument("--rich", default=False, action="store_true", help="Output additional columns")
+    p.add_argument("--coords", default=False, action="store_true", help="Output columns with base coordinates")
+    p.add_argument("--bed", default=False, action="store_true", help="Generate BED file for the blocks")
+    p.add_argument("--noheader", default=False, action="store_true", help="Don't output header")
+    p.set_beds()
+    opts, args = p.parse_args(args)
+    if len(args) != 1:
+        sys.exit(not p.print_help())
+    (anchorfile,) = args
+    additional, coords, header, bed = opts.rich, opts.coords or opts.bed, not opts.noheader, opts.bed
+    ac = AnchorFile(anchorfile)
+    simplefile = anchorfile.rsplit(".", 1)[0] + ".simple"
+    qbed, sbed, qorder, sorder, is_self = check_beds(anchorfile, p, opts)
+    pf = "-".join(anchorfile.split(".", 2)[:2])
+    if ac.is_empty:
+        logger.error("No blocks found in `%s`. Aborting ..", anchorfile)
+        return
+    if coords:
+        h = "Block|Chr|Start|End|Span|StartGene|EndGene|GeneSpan|Orientation"
+    else:
+        h = "StartGeneA|EndGeneA|StartGeneB|EndGeneB|Orientation|Score"
+        if additional:
+            h += "|StartOrderA|EndOrderA|StartOrderB|EndOrderB|SizeA|SizeB|Size|Block"
+    blocks = ac.blocks
+    blk, ia, ib = [], [], []
+    for i, block in enumerate(blocks):
+        a, b, scores = zip(*block)
+        ia.extend(qorder[x][0] for x in a)          # KeyError like the reference for genes outside the BEDs
+        ib.extend(sorder[x][0] for x in b)
+        blk.extend([i] * len(block))
+    st = get_engine().block_stats(blk, ia, ib, len(blocks))      # the per-block reductions, on the device
+    n = st["size"].astype(object)
+    cov = n * st["sum_qs"].astype(object) - st["sum_q"].astype(object) * st["sum_s"].astype(object)   # exact Python ints
+    starts = np.concatenate(([0], np.cumsum(st["size"].astype(np.int64))))
+    out = ["\t".join(h.split("|"))] if header else []
+    bbed = []
+    atotalbase = btotalbase = 0
+    for i in range(len(blocks)):
+        astarti, aendi, bstarti, bendi = int(st["qmin"][i]), int(st["qmax"][i]), int(st["smin"][i]), int(st["smax"][i])
+        astart, aend, bstart, bend = qbed[astarti].accn, qbed[aendi].accn, sbed[bstarti].accn, sbed[bendi].accn
+        sizeA, sizeB, size = int(st["distinct_q"][i]), int(st["distinct_s"][i]), int(st["size"][i])
+        if size < 2:
+            orientation = "+"
+        elif size * (aendi - astarti + 1) * (bendi - bstarti + 1) >= (1 << 62):     # the device's 64-bit sums could wrap: exact on the host
+            lo, hi = int(starts[i]), int(starts[i + 1])
+            c = size * sum(x * y for x, y in zip(ia[lo:hi], ib[lo:hi])) - sum(ia[lo:hi]) * sum(ib[lo:hi])
+            orientation = ("+" if c > 0 else "-") if c else get_orientation(ia[lo:hi], ib[lo:hi])
+        elif cov[i] != 0:
+            orientation = "+" if cov[i] > 0 else "-"
+        else:                                       # exactly flat: the reference's answer is polyfit's rounding noise
+            lo, hi = int(starts[i]), int(starts[i + 1])
+            orientation = get_orientation(ia[lo:hi], ib[lo:hi])
+        aspan = aendi - astarti + 1
+        bspan = bendi - bstarti + 1
+        score = str(int((aspan * bspan) ** 0.5))
+        block_id = pf + "-block-{0}".format(i)
+        if coords:
+            (s, e) = qbed[astarti], qbed[aendi]
+            assert s.seqid == e.seqid
+            aseqid, astartbase, aendbase = s.seqid, min((s.start, s.end), (e.start, e.end))[0], max(s.end, e.end)
+            (s, e) = sbed[bstarti], sbed[bendi]
+            assert s.seqid == e.seqid
+            bseqid, bstartbase, bendbase = s.seqid, min((s.start, s.end), (e.start, e.end))[0], max(s.end, e.end)
+            abase = aendbase - astartbase + 1
+            bbase = bendbase - bstartbase + 1
+            atotalbase += abase
+            btotalbase += bbase
+            out.append("\t".join(str(x) for x in (block_id, aseqid, astartbase, aendbase, abase, astart, aend, aspan, "+")))
+            out.append("\t".join(str(x) for x in (block_id, bseqid, bstartbase, bendbase, bbase, bstart, bend, bspan, orientation)))
+            if bed:
+                bbed.append((bseqid, bstartbase, bendbase, "{}:{}-{}".format(aseqid, astartbase, aendbase), size, orientation))
+            continue
+        row = [astart, aend, bstart, bend, score, orientation]
+        if additional:
+            row += [astarti, aendi, bstarti, bendi, sizeA, sizeB, size, block_id]
+        out.append("\t".join(str(x) for x in row))
+    with open(simplefile, "w") as fws:
+        fws.write("\n".join(out) + "\n")
+    logger.debug("A total of {0} blocks written to `{1}`.".format(len(blocks), simplefile))
+    if coords:
+        print("Total block span in {0}: {1}".format(qbed.filename, atotalbase), file=sys.stderr)
+        print("Total block span in {0}: {1}".format(sbed.filename, btotalbase), file=sys.stderr)
+        print("Ratio: {0:.1f}x".format(max(atotalbase, btotalbase) * 1.0 / min(atotalbase, btotalbase)), file=sys.stderr)
+    if bed:
+        from ..formats.bed import natsort_key
+        bedfile = simplefile + ".bed"
+        bbed.sort(key=lambda r: (natsort_key(r[0]), r[1], r[3]))       # Bed.print_to_file(sorted=True)
+        with open(bedfile, "w") as fw:
+            for seqid, start, end, accn, size, orientation in bbed:
+                fw.write("\t".join(str(x) for x in (seqid, max(start, 1) - 1, end, accn, size, orientation)) + "\n")
+        logger.debug("Bed file written to `{}`".format(bedfile))
+
+
 def main():
-    actions = {"scan": scan, "liftover": liftover, "summary": summary, "mcscan": mcscan}
+    actions = {"scan": scan, "liftover": liftover, "summary": summary, "mcscan": mcscan, "simple": simple}
     if len(sys.argv) < 2 or sys.argv[1] not in actions:
-        print("usage: python -m jcvi_b200.compara.synteny {scan,liftover,summary,mcscan} ...", file=sys.stderr)
+        print("usage: python -m jcvi_b200.compara.synteny {scan,liftover,summary,mcscan,simple} ...", file=sys.stderr)
         sys.exit(1)
     actions[sys.argv[1]](sys.argv[2:])
 

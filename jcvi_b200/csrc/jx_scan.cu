@@ -633,3 +633,93 @@ extern "C" int jx_mcscan(jx_ctx* ctx, const double* start, const double* end, co
   return JX_OK;
 }
 
+// =====================================================================================================
+// synteny simple (src/jcvi/compara/synteny.py:1137-1316): per block of an anchors file the
+// first / last gene rank on both sides, the number of distinct genes, the size, and the sums the
+// orientation needs (get_orientation, synteny.py:222-236: the sign of the least-squares slope = the sign
+// of the covariance n*sum(xy) - sum(x)*sum(y), accumulated exactly on ranks centred at the block minimum).
+// One segmented reduction over the anchors: atomics for min / max / count / sums, and a sort of
+// (block, rank) keys per side for the distinct counts.
+// =====================================================================================================
+namespace {
+__global__ void k_block_minmax(const int32_t* __restrict__ blk, const int32_t* __restrict__ x, const int32_t* __restrict__ y,
+                               uint32_t n, int32_t* xmin, int32_t* xmax, int32_t* ymin, int32_t* ymax, uint32_t* size) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t b = blk[i];
+  atomicMin(xmin + b, x[i]); atomicMax(xmax + b, x[i]);
+  atomicMin(ymin + b, y[i]); atomicMax(ymax + b, y[i]);
+  atomicAdd(size + b, 1u);
+}
+__global__ void k_block_sums(const int32_t* __restrict__ blk, const int32_t* __restrict__ x, const int32_t* __restrict__ y,
+                             uint32_t n, const int32_t* __restrict__ xmin, const int32_t* __restrict__ ymin,
+                             unsigned long long* sx, unsigned long long* sy, unsigned long long* sxy) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t b = blk[i];
+  const unsigned long long cx = (unsigned long long)(x[i] - xmin[b]), cy = (unsigned long long)(y[i] - ymin[b]);
+  atomicAdd(sx + b, cx); atomicAdd(sy + b, cy); atomicAdd(sxy + b, cx * cy);
+}
+__global__ void k_block_rank_keys(const int32_t* __restrict__ blk, const int32_t* __restrict__ r, uint32_t n, uint64_t* keys) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = ((uint64_t)(uint32_t)blk[i] << 32) | (uint32_t)r[i];
+}
+__global__ void k_block_distinct(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* distinct) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 || keys[i - 1] != keys[i]) atomicAdd(distinct + (uint32_t)(keys[i] >> 32), 1u);
+}
+}  // namespace
+
+extern "C" int jx_block_stats(jx_ctx* ctx, const int32_t* block, const int32_t* qrank, const int32_t* srank, int64_t n,
+                              int32_t n_blocks, int32_t* qmin, int32_t* qmax, int32_t* smin, int32_t* smax, uint32_t* size,
+                              uint32_t* distinct_q, uint32_t* distinct_s, uint64_t* sum_q, uint64_t* sum_s, uint64_t* sum_qs) {
+  if (!ctx || n < 0 || n >= (1ll << 31) || n_blocks < 0 || (n && (!block || !qrank || !srank)) || !qmin || !qmax || !smin ||
+      !smax || !size || !distinct_q || !distinct_s || !sum_q || !sum_s || !sum_qs) return JX_EARG;
+  for (int64_t i = 0; i < n; ++i)
+    if (block[i] < 0 || block[i] >= n_blocks || qrank[i] < 0 || srank[i] < 0) { ctx->err = "jx_block_stats: entry out of range"; return JX_EARG; }
+  if (!n_blocks) return JX_OK;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  int rc;
+  const size_t nb = (size_t)n_blocks, nn = (size_t)std::max<int64_t>(n, 1);
+  JX_ALLOC(d_b, int32_t, nn, false);
+  JX_ALLOC(d_x, int32_t, nn, false);
+  JX_ALLOC(d_y, int32_t, nn, false);
+  JX_ALLOC(d_i32, int32_t, 4 * nb, false);          // xmin xmax ymin ymax
+  JX_ALLOC(d_u32, uint32_t, 3 * nb, true);          // size distinct_q distinct_s
+  JX_ALLOC(d_u64, unsigned long long, 3 * nb, true);
+  int32_t *xmin = d_i32, *xmax = d_i32 + nb, *ymin = d_i32 + 2 * nb, *ymax = d_i32 + 3 * nb;
+  JX_CK(cudaMemsetAsync(xmin, 0x7F, nb * 4, ctx->stream));     // 0x7F7F7F7F: above every rank (< 2^31 - 2 genes per BED)
+  JX_CK(cudaMemsetAsync(ymin, 0x7F, nb * 4, ctx->stream));
+  JX_CK(cudaMemsetAsync(xmax, 0xFF, nb * 4, ctx->stream));     // -1
+  JX_CK(cudaMemsetAsync(ymax, 0xFF, nb * 4, ctx->stream));
+  if (n) {
+    JX_CK(cudaMemcpyAsync(d_b, block, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(d_x, qrank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(d_y, srank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t un = (uint32_t)n;
+    JX_LAUNCH(k_block_minmax, nblk(un), 256, 0, d_b, d_x, d_y, un, xmin, xmax, ymin, ymax, d_u32);
+    JX_LAUNCH(k_block_sums, nblk(un), 256, 0, d_b, d_x, d_y, un, xmin, ymin, d_u64, d_u64 + nb, d_u64 + 2 * nb);
+    for (int side = 0; side < 2; ++side) {
+      JX_ALLOC(keys, uint64_t, nn, false);
+      JX_LAUNCH(k_block_rank_keys, nblk(un), 256, 0, d_b, side ? d_y : d_x, un, keys);
+      uint64_t* ks = keys;
+      if ((rc = jx_sort_keys(ctx, arena, ks, (size_t)n, 0, 64))) return rc;
+      JX_LAUNCH(k_block_distinct, nblk(un), 256, 0, ks, un, d_u32 + (size_t)(1 + side) * nb);
+    }
+  }
+  JX_CK(cudaMemcpyAsync(qmin, xmin, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(qmax, xmax, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(smin, ymin, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(smax, ymax, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(size, d_u32, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(distinct_q, d_u32 + nb, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(distinct_s, d_u32 + 2 * nb, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(sum_q, d_u64, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(sum_s, d_u64 + nb, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(sum_qs, d_u64 + 2 * nb, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  return JX_OK;
+}
+

@@ -478,6 +478,19 @@ class Engine(object):
         tracks = np.split(blocks, np.cumsum(lens)[:-1]) if T else []
         return [t.tolist() for t in tracks], scores.tolist(), table
 
+    def block_stats(self, block, qrank, srank, n_blocks):
+        """jx_block_stats -> dict of per-block arrays: qmin qmax smin smax size distinct_q distinct_s sum_q sum_s sum_qs."""
+        b = np.ascontiguousarray(block, dtype=np.int32); x = np.ascontiguousarray(qrank, dtype=np.int32)
+        y = np.ascontiguousarray(srank, dtype=np.int32)
+        nb = int(n_blocks)
+        out = dict(qmin=np.zeros(nb, np.int32), qmax=np.zeros(nb, np.int32), smin=np.zeros(nb, np.int32), smax=np.zeros(nb, np.int32),
+                   size=np.zeros(nb, np.uint32), distinct_q=np.zeros(nb, np.uint32), distinct_s=np.zeros(nb, np.uint32),
+                   sum_q=np.zeros(nb, np.uint64), sum_s=np.zeros(nb, np.uint64), sum_qs=np.zeros(nb, np.uint64))
+        self._check(self.lib.jx_block_stats(self.ctx, C.ptr(b), C.ptr(x), C.ptr(y), len(b), nb,
+                                            *[C.ptr(out[k]) for k in ("qmin", "qmax", "smin", "smax", "size", "distinct_q",
+                                                                      "distinct_s", "sum_q", "sum_s", "sum_qs")]))
+        return out
+
     # ---- instrumentation ----------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.jx_launch_count(self.ctx))

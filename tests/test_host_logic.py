@@ -170,7 +170,7 @@ def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
     (pkg / "blastfilter.py").write_text("def main(args):\n    return 'ref'\ndef blastfilter_main(a, b, c):\n    return 'ref'\n")
     (pkg / "synteny.py").write_text("def scan(a):\n    return 'ref'\ndef liftover(a):\n    return 'ref'\ndef mcscan(a):\n    return 'ref'\n"
                                     "def batch_scan(*a, **k):\n    return 'ref'\ndef synteny_scan(*a, **k):\n    return 'ref'\n"
-                                    "def synteny_liftover(*a, **k):\n    return 'ref'\n")
+                                    "def synteny_liftover(*a, **k):\n    return 'ref'\ndef simple(a):\n    return 'ref'\n")
     fm = tmp_path / "jcvi" / "formats"
     fm.mkdir()
     (fm / "__init__.py").write_text("")
