@@ -12,6 +12,7 @@ from .oracle import (  # noqa: F401
     blast_filter,
     mcscan,
     simple,
+    synfind,
     kdtree,
     gene_name,
     natcmp,

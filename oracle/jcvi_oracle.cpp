@@ -1339,4 +1339,154 @@ int orc_simple(const char* anchor_file, const char* qbed_path, const char* sbed_
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------
+// compara.synfind  (src/jcvi/compara/synfind.py:45-240; LIS: src/jcvi/algorithms/lis.py:20-116)
+// For every gene of the query BED: the hits of the +-window//2 genes around it on the same seqid, single-linked
+// along the subject when consecutive (subject order) hits are < window//2 ranks apart on one seqid; per linked
+// group the closest flanker, the longer of LIS / LDS over the subject ranks ("collinear" scoring), the score
+// min(#distinct x, #distinct y) (- 1 without a syntelog), kept when >= int(cutoff * window); then the mirror pass.
+// `--scoring=density` leaves `orientation` unbound in the reference (UnboundLocalError): not restated.
+// returns 0, -1 I/O, -5 ValueError (no hit maps onto the BEDs: `transposed([])` in the mirror pass)
+// ---------------------------------------------------------------------------------
+namespace {
+typedef std::pair<long, long> SfPt;                         // (x, y) = (query rank, subject rank)
+
+// lis.py:81-107 on (y, i) pairs; returns the chosen elements
+std::vector<SfPt> sf_lis(const std::vector<SfPt>& xs) {
+  std::vector<SfPt> tops;                                   // patience_sort: bisect_left on the pile tops
+  std::vector<std::vector<std::pair<SfPt, long>>> piles(1); // dummy pile 0; entries (x, index into the previous pile)
+  for (const SfPt& x : xs) {
+    const size_t p = (size_t)(std::lower_bound(tops.begin(), tops.end(), x) - tops.begin());
+    if (p == tops.size()) tops.push_back(x); else tops[p] = x;
+    if (p + 1 == piles.size()) piles.emplace_back();
+    piles[p + 1].push_back({x, (long)piles[p].size() - 1});
+  }
+  std::vector<SfPt> lis;
+  long prev = 0;
+  for (size_t pile = piles.size() - 1; pile >= 1; --pile) {
+    const auto& e = piles[pile][(size_t)prev];
+    lis.push_back(e.first);
+    prev = e.second;
+  }
+  std::reverse(lis.begin(), lis.end());
+  return lis;
+}
+std::vector<SfPt> sf_lds(const std::vector<SfPt>& xs) {     // list(reversed(LIS(reversed(xs))))
+  std::vector<SfPt> r(xs.rbegin(), xs.rend());
+  std::vector<SfPt> l = sf_lis(r);
+  std::reverse(l.begin(), l.end());
+  return l;
+}
+struct SfRegion { long syntelog, far_syntelog, left, right; char gray, orient; long score; };
+
+void sf_regions(long query, const Bed& sbed, const std::vector<SfPt>& data, long window, long cutoff, std::vector<SfRegion>& regions) {
+  regions.clear();
+  std::vector<SfPt> ys(data);
+  std::stable_sort(ys.begin(), ys.end(), [](const SfPt& a, const SfPt& b) { return a.second < b.second; });
+  // consecutive links -> runs; a point without any link is in no group
+  std::vector<std::vector<SfPt>> groups;
+  size_t i = 0;
+  while (i + 1 < ys.size()) {
+    auto linked = [&](size_t k) {
+      return ys[k + 1].second - ys[k].second < window && sbed.rows[(size_t)ys[k].second].seqid == sbed.rows[(size_t)ys[k + 1].second].seqid;
+    };
+    if (!linked(i)) { ++i; continue; }
+    size_t j = i;
+    while (j + 1 < ys.size() && linked(j)) ++j;
+    groups.emplace_back(ys.begin() + (long)i, ys.begin() + (long)j + 1);
+    i = j + 1;
+  }
+  std::sort(groups.begin(), groups.end());                  // sorted(g): lists of tuples, lexicographic
+  for (auto& group : groups) {
+    std::sort(group.begin(), group.end());                  // get_flanker: group.sort()
+    const size_t pos = (size_t)(std::lower_bound(group.begin(), group.end(), SfPt(query, 0)) - group.begin());
+    const SfPt left = pos == 0 ? group.front() : group[pos - 1];
+    const SfPt right = pos == group.size() ? group.back() : group[pos];
+    SfPt flanker, other;
+    if (std::labs(query - left.first) < std::labs(query - right.first)) { flanker = left; other = right; }
+    else { flanker = right; other = left; }
+    const bool flanked = !(pos == 0 || pos == group.size());   // `flanker == query` compares a tuple with an int: never true
+    // collinear scoring: the longer of LIS / LDS over (y, i)
+    std::vector<SfPt> yi;
+    for (size_t k = 0; k < group.size(); ++k) yi.push_back(SfPt(group[k].second, (long)k));
+    const std::vector<SfPt> lis = sf_lis(yi), lds = sf_lds(yi);
+    const bool plus = lis.size() >= lds.size();
+    const std::vector<SfPt>& track = plus ? lis : lds;
+    std::vector<SfPt> g2;
+    for (const SfPt& t : track) g2.push_back(group[(size_t)t.second]);
+    std::set<long> xs, ysset;
+    for (const SfPt& q : g2) { xs.insert(q.first); ysset.insert(q.second); }
+    long score = (long)std::min(xs.size(), ysset.size());
+    char gray;
+    if (flanker.first == query) gray = 'S';
+    else { gray = flanked ? 'F' : 'G'; score -= 1; }
+    if (score < cutoff) continue;
+    regions.push_back({flanker.second, other.second, g2.front().second, g2.back().second, gray, plus ? '+' : '-', score});
+  }
+  std::stable_sort(regions.begin(), regions.end(), [](const SfRegion& a, const SfRegion& b) { return a.score > b.score; });
+}
+
+std::string sf_note(const std::string& filename) {          // op.basename(filename).split(".")[0]
+  size_t sl = filename.rfind('/');
+  std::string b = sl == std::string::npos ? filename : filename.substr(sl + 1);
+  return b.substr(0, b.find('.'));
+}
+
+void sf_batch(const Bed& qbed, const Bed& sbed, std::vector<SfPt> all, long window_opt, double cutoff_opt, const std::string& qnote,
+              const std::string& snote, FILE* fw) {
+  const long cutoff = (long)(cutoff_opt * (double)window_opt);   // int(opts.cutoff * opts.window)
+  const long window = window_opt / 2;
+  std::sort(all.begin(), all.end());
+  std::vector<SfRegion> regions;
+  size_t a = 0;
+  const size_t G = qbed.rows.size();
+  while (a < G) {                                           // groupby(qsimplebed, seqid): consecutive equal seqids
+    size_t b = a;
+    while (b < G && qbed.rows[b].seqid == qbed.rows[a].seqid) ++b;
+    const long first = (long)a, last = (long)b - 1;
+    for (long r = first; r <= last; ++r) {
+      const long rmin = std::max(r - window, first), rmax = std::min(r + window + 1, last);
+      const auto lo = std::lower_bound(all.begin(), all.end(), SfPt(rmin, 0));
+      const auto hi = std::lower_bound(all.begin(), all.end(), SfPt(rmax, 0));
+      std::vector<SfPt> data;
+      if (lo < hi) data.assign(lo, hi);
+      sf_regions(r, sbed, data, window, cutoff, regions);
+      for (const SfRegion& g : regions) {
+        const BedLine& L = sbed.rows[(size_t)g.left]; const BedLine& R = sbed.rows[(size_t)g.right];
+        const BedLine& A = sbed.rows[(size_t)g.syntelog];
+        const long left_dist = A.seqid == L.seqid ? std::labs(A.start - L.start) : 0;
+        const long right_dist = A.seqid == R.seqid ? std::labs(A.start - R.start) : 0;
+        const long flank = (std::max(left_dist, right_dist) / 10000 + 1) * 10000;
+        fprintf(fw, "%s\t%s\t%c\t%ld\t%ld\t%c\t%s\t%s\n", qbed.rows[(size_t)r].accn.c_str(), A.accn.c_str(), g.gray, g.score, flank,
+                g.orient, qnote.c_str(), snote.c_str());
+      }
+    }
+    a = b;
+  }
+}
+}  // namespace
+
+int orc_synfind(const char* blast_file, const char* qbed_path, const char* sbed_path, const char* out_path, int strip_names,
+                int window, double cutoff) {
+  Beds beds;
+  if (!load_beds(qbed_path, sbed_path, beds)) return -1;
+  std::vector<Hit> hits;
+  if (!read_blast_ordered(blast_file, beds, strip_names != 0, hits, nullptr)) return -1;
+  std::vector<SfPt> all;
+  for (const Hit& h : hits) all.push_back(SfPt(h.qi, h.si));
+  FILE* fw = fopen(out_path, "w");
+  if (!fw) return -1;
+  const std::string qnote = sf_note(beds.q.filename), snote = sf_note(beds.s.filename);
+  sf_batch(beds.q, beds.s, all, window, cutoff, qnote, snote, fw);
+  if (!beds.is_self && all.empty()) { fclose(fw); g_err = "not enough values to unpack (expected 2, got 0)"; return -5; }   // transposed([])
+  if (!beds.is_self) {                                      // the mirror pass: transposed data, BEDs and notes swapped
+    std::vector<SfPt> tr;
+    for (const SfPt& p : all) tr.push_back(SfPt(p.second, p.first));
+    sf_batch(beds.s, beds.q, tr, window, cutoff, snote, qnote, fw);
+  }
+  fclose(fw);
+  return 0;
+}
+
 }  // extern "C"

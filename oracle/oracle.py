@@ -127,6 +127,15 @@ def simple(anchorfile, qbed, sbed, out_path, rich=False, coords=False, noheader=
     return rc == 0
 
 
+def synfind(blast_file, qbed, sbed, out_path, strip_names=True, window=40, cutoff=0.1):
+    """compara/synfind.py:205-240 (`jcvi.compara.synfind`, --scoring=collinear, text output); writes out_path."""
+    rc = _lib().orc_synfind(_b(blast_file), _b(qbed), _b(sbed), _b(out_path), int(bool(strip_names)), int(window),
+                            ctypes.c_double(cutoff))
+    if rc == -5:
+        raise ValueError(_lib().orc_last_error().decode())
+    _check(rc)
+
+
 def kdtree(anchors, queries, bound):
     """Restated cKDTree(anchors, leafsize=16).query(queries, p=1, distance_upper_bound=bound)."""
     a = np.ascontiguousarray(anchors, dtype=np.int64).reshape(-1, 2)

@@ -159,6 +159,29 @@ def main():
         oracle.liftover(last, "orc.anchors", os.path.basename(qbed), os.path.basename(sbed), out_path="orc.lifted", dist=7)
         assert rd(ref_out) == rd("orc.lifted"), ("liftover", seed)
         n_checked += 3
+    # ---- synfind (oracle first) on small pairs, a self comparison, two window sizes ----------------
+    from jcvi.compara import synfind as ref_sf
+    for seed, self_mode, argv, kw in ((301, False, [], {}), (302, False, ["--window=20", "--cutoff=0.2"], dict(window=20, cutoff=0.2)),
+                                      (303, True, [], {}), (304, False, ["--window=60", "--cutoff=0.05"], dict(window=60, cutoff=0.05))):
+        sub = os.path.join(d, "s%d" % seed)
+        os.makedirs(sub)
+        os.chdir(sub)
+        names = ("S", "S") if self_mode else ("A", "B")
+        qbed, sbed, last = synth.write_dataset(sub, names[0], names[1], seed, 900, 700, 14000, Kq=3, Ks=3, self_mode=self_mode)
+        last, qbed, sbed = os.path.basename(last), os.path.basename(qbed), os.path.basename(sbed)
+        ref_sf.main([last, "--qbed=" + qbed, "--sbed=" + sbed, "-o", "ref.synfind"] + argv)
+        oracle.synfind(last, qbed, sbed, "orc.synfind", **kw)
+        assert rd("ref.synfind") == rd("orc.synfind"), ("synfind", seed)
+        assert len(rd("ref.synfind")) > 1000, ("synfind output suspiciously small", seed)
+        n_checked += 1
+        if seed == 301:                       # nothing maps onto the BEDs: the reference dies in transposed([])
+            for fn in (lambda: ref_sf.main([last, "--qbed=" + qbed, "--sbed=" + sbed, "-o", "x", "--no_strip_names"]),
+                       lambda: oracle.synfind(last, qbed, sbed, "y", strip_names=False)):
+                try:
+                    fn()
+                    raise AssertionError("expected ValueError")
+                except ValueError:
+                    pass
     print("LIVE_REFERENCE_OK %d comparisons" % n_checked)
 
 
