@@ -18,12 +18,18 @@
 // running the unmodified reference (Cython cblast build) in this container
 // (tests/golden/make_golden.py).
 //
+// Also restated, each with its own golden vectors from the unmodified reference (tests/golden/make_golden_*.py) and
+// cross-checked against the live reference on randomized inputs (tests/live_reference_check.py): formats.blast cscore
+// and filter, synteny mcscan and simple, compara.synfind.
+//
 // Third-party arithmetic restated here because it is not under /root/reference:
 //   * glibc sscanf/sprintf  -- called directly, exactly like cblast.pyx does.
 //   * natsort (unpinned dep, pyproject.toml:49) -- default natural-sort key.
 //   * scipy.spatial.cKDTree (scipy 1.18.1 installed here; pyproject.toml:61 unpinned)
 //     -- build (balanced, compact, leafsize=16) and k=1, p=1 query; validated
 //     black-box against the installed scipy in tests/test_oracle_kdtree.py.
+//   * numpy.polyfit (synteny simple's orientation) -- the sign of the exact integer covariance; a covariance of
+//     exactly 0 is rounding noise in the reference and "+" here (parity unpinned for such flat blocks).
 #include <algorithm>
 #include <set>
 #include <cctype>
