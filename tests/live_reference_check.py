@@ -21,7 +21,11 @@ def rd(p):
 
 
 def main():
-    refenv.activate()
+    try:
+        refenv.activate()
+    except Exception as e:                       # no Cython / compiler here: nothing to compare with
+        print("LIVE_REFERENCE_UNAVAILABLE %s" % e)
+        sys.exit(77)
     from jcvi.formats import blast as ref_blast
     from jcvi.compara import synteny as ref_syn
     import oracle

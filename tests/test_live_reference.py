@@ -14,5 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def test_oracle_equals_live_reference_on_randomized_inputs():
     out = subprocess.run([sys.executable, os.path.join(HERE, "live_reference_check.py")], capture_output=True, text=True,
                          timeout=600)
+    if out.returncode == 77:
+        pytest.skip("the reference could not be set up here: " + out.stdout[-300:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert "LIVE_REFERENCE_OK" in out.stdout
