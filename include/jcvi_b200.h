@@ -117,18 +117,20 @@ typedef struct {
   int32_t* s_rank;
   float* score;                 /* float32 as parsed (cblast.pyx:88)                            */
   uint64_t* line_off;           /* byte offset of the hit's line in the input text              */
-  char* text;                   /* `.filtered` bytes when want_text; when text_pinned != 0 they
-                                   live in the context's pinned staging buffer and stay valid
-                                   until the next jx_blastfilter call on the same context       */
+  char* text;                   /* `.filtered` bytes when want_text; owned by this result and valid
+                                   until jx_filter_result_free (text_pinned = 2: a pinned buffer
+                                   borrowed from the context's pool and returned to it by the free;
+                                   the context must outlive the result)                         */
   int64_t text_len;
   int32_t* q_mother;            /* [n_genes(q)] when want_mothers: mother rank of every gene    */
   int32_t* s_mother;            /* [n_genes(s)]                                                 */
   /* counters: 0 lines (non-'#'), 1 mapped records, 2 unmapped names ("not in bed" warnings),
    * 3 after exclude, 4 after cscore (pre-dedupe), 5 after dedupe, 6 after tandem, 7 '#' lines */
   int64_t stats[8];
-  int32_t text_pinned;          /* 0: malloc'ed, owned by the result; 2: context-owned (see text) */
+  int32_t text_pinned;          /* 0: malloc'ed; 2: pinned, borrowed from the context's pool (see text) */
   int64_t device_token;         /* identifies the device-resident copy of the survivors kept by the
                                    context (valid until the next jx_blastfilter on it)               */
+  void* owner;                  /* the context whose pinned pool `text` came from (text_pinned = 2)  */
 } jx_filter_result;
 
 int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device,

@@ -38,7 +38,7 @@ class JxFilterResult(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int64), ("q_rank", c_i32p), ("s_rank", c_i32p), ("score", c_f32p),
                 ("line_off", c_u64p), ("text", ctypes.c_void_p), ("text_len", ctypes.c_int64),
                 ("q_mother", c_i32p), ("s_mother", c_i32p), ("stats", ctypes.c_int64 * 8),
-                ("text_pinned", ctypes.c_int32), ("device_token", ctypes.c_int64)]
+                ("text_pinned", ctypes.c_int32), ("device_token", ctypes.c_int64), ("owner", ctypes.c_void_p)]
 
 
 class JxScanOpts(ctypes.Structure):

@@ -96,7 +96,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   for (cudaEvent_t ev : ctx->held_events) cudaEventDestroy(ev);
   cudaFree(ctx->held_text);
   cudaFree(ctx->lines_dev);
-  if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+  for (auto& b : ctx->pin_pool) cudaFreeHost(b.p);
   if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
   if (ctx->ws) cudaFree(ctx->ws);
   cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);

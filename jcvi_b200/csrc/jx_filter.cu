@@ -219,7 +219,7 @@ __global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, 
   len[t] = (uint32_t)(e - p) + 1;      // + '\n'
 }
 __global__ void k_copy_lines(const uint8_t* text, const uint64_t* off, const uint32_t* idx, const uint32_t* len,
-                             const uint32_t* pos, uint32_t cnt, uint8_t* out) {
+                             const uint64_t* pos, uint32_t cnt, uint8_t* out) {
   uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= cnt) return;
   const uint8_t* src = text + off[idx ? idx[w] : w];
@@ -258,7 +258,7 @@ __global__ void k_format_len(const uint8_t* text, int64_t n, const uint64_t* off
 
 __global__ void k_format_write(const uint8_t* text, int64_t n, const uint64_t* off, const int32_t* q, const int32_t* s,
                                const uint32_t* qmeta, const uint32_t* qblob, const uint32_t* smeta, const uint32_t* sblob,
-                               uint32_t cnt, const uint32_t* pos, char* out) {
+                               uint32_t cnt, const uint64_t* pos, char* out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt) return;
   char tail[160];
@@ -314,7 +314,7 @@ int dedupe(jx_ctx* ctx, Arena& arena, uint64_t* keys, uint32_t* vals, size_t n, 
 
 // the reference's own formatting of one survivor: sscanf with cblast.pyx:15, start/stop
 // normalisation (cblast.pyx:115-120), sprintf with cblast.pyx:17 and the substituted names
-void format_range(const char* lines, const uint32_t* pos, const uint32_t* len, const int32_t* q_all, const int32_t* s_all,
+void format_range(const char* lines, const uint64_t* pos, const uint32_t* len, const int32_t* q_all, const int32_t* s_all,
                   const uint32_t* idx, size_t lo, size_t hi, const SideDev& Q, const SideDev& S, std::string& out) {
   char qn[160], sn[160], buf[1024];
   std::string line;
@@ -384,16 +384,16 @@ int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nb
   int rc;
   JX_ALLOC(off, uint64_t, cnt, false);
   JX_ALLOC(len, uint32_t, cnt, false);
-  JX_ALLOC(pos, uint32_t, cnt, false);
+  JX_ALLOC(pos, uint64_t, cnt, false);
   JX_LAUNCH(k_line_off, nblk(cnt), 256, 0, rec_idx, cnt, recs, desc, ntiles, off);
   JX_LAUNCH(k_line_len, nblk(cnt), 256, 0, d_text, nbytes, off, (const uint32_t*)nullptr, cnt, len, rstrip);
-  if ((rc = jx_exclusive_sum(ctx, arena, len, pos, cnt))) return rc;
-  uint32_t h[2];
-  JX_CK(cudaMemcpyAsync(&h[0], pos + cnt - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaMemcpyAsync(&h[1], len + cnt - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // byte positions are 64-bit: the packed lines of a big slice may exceed 4 GiB (C-score filter off)
+  if ((rc = jx_exclusive_sum64(ctx, arena, len, pos, cnt))) return rc;
+  uint64_t hpos = 0; uint32_t hlen = 0;
+  JX_CK(cudaMemcpyAsync(&hpos, pos + cnt - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(&hlen, len + cnt - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
   JX_CK(cudaStreamSynchronize(ctx->stream));
-  const uint64_t total = (uint64_t)h[0] + h[1];
-  if (total >= 0xFFFFFFF0ull) { ctx->err = "gathered lines exceed 4 GiB; use more ranks"; return JX_EUNSUPPORTED; }
+  const uint64_t total = hpos + hlen;
   if (dev_out) {                                   // context-owned device result (valid until the next one)
     if (ctx->lines_dev_cap < total + 16) {
       JX_CK(cudaStreamSynchronize(ctx->stream));
@@ -507,7 +507,8 @@ static int cscore_finish_impl(jx_ctx* ctx, double cscore, char** lines, int64_t*
 void jx_filter_result_free(jx_filter_result* r) {
   if (!r) return;
   free(r->q_rank); free(r->s_rank); free(r->score); free(r->line_off); free(r->q_mother); free(r->s_mother);
-  if (!r->text_pinned) free(r->text);   // pinned text belongs to the context
+  if (!r->text_pinned) free(r->text);
+  else if (r->owner && r->text) jx_pin_release((jx_ctx*)r->owner, r->text);   // back to the context's pool
   memset(r, 0, sizeof *r);
 }
 
@@ -705,42 +706,40 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
       // anything it declines (inf/nan, >int32 integers, decimal rounding ties in the evalue ...)
       // sends the whole output through the host's glibc instead.
       JX_ALLOC(flen, uint32_t, nF, false);
-      JX_ALLOC(fpos, uint32_t, nF, false);
+      JX_ALLOC(fpos, uint64_t, nF, false);
       JX_ALLOC(ffb, uint32_t, 1, true);
       JX_LAUNCH(k_format_len, nblk(nF, 128), 128, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, S.name_meta, nF, flen, ffb);
-      if ((rc = jx_exclusive_sum(ctx, arena, flen, fpos, nF))) return rc;
-      uint32_t h[3] = {0, 0, 0};
+      // 64-bit byte positions: with the C-score filter off the `.filtered` text of a big table exceeds 4 GiB
+      if ((rc = jx_exclusive_sum64(ctx, arena, flen, fpos, nF))) return rc;
+      uint32_t h[2] = {0, 0};
+      uint64_t hlast = 0;
       JX_CK(cudaMemcpyAsync(&h[0], ffb, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      JX_CK(cudaMemcpyAsync(&h[1], fpos + nF - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      JX_CK(cudaMemcpyAsync(&h[2], flen + nF - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(&hlast, fpos + nF - 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(&h[1], flen + nF - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
       JX_CK(cudaStreamSynchronize(ctx->stream));
       const uint32_t ndecl = h[0];
-      const uint64_t total = (uint64_t)h[1] + h[2];
-      if (total >= 0xFFFFFFF0ull) { ctx->err = "`.filtered` text exceeds 4 GiB"; return JX_EUNSUPPORTED; }
+      const uint64_t total = hlast + h[1];
       JX_ALLOC(dtext, char, (size_t)total + 1, false);
       JX_LAUNCH(k_format_write, nblk(nF, 128), 128, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, Q.blobw,
                 S.name_meta, S.blobw, nF, fpos, dtext);
-      if (ctx->pin_cap < total + 1) {               // grow-only pinned staging owned by the context
-        if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
-        ctx->pin_buf = nullptr; ctx->pin_cap = 0;
-        const size_t cap = (size_t)(total + 1) + (size_t)(total >> 2) + (1u << 20);
-        JX_CK(cudaMallocHost((void**)&ctx->pin_buf, cap));
-        ctx->pin_cap = cap;
-      }
-      char* host = ctx->pin_buf;
+      char* host = jx_pin_acquire(ctx, (size_t)total + 1);   // borrowed from the pool until the result is freed
+      if (!host) { ctx->err = "cudaMallocHost failed"; return JX_ECUDA; }
+      struct PinGuard { jx_ctx* c; char* p; ~PinGuard() { if (p) jx_pin_release(c, p); } } guard{ctx, host};
       JX_CK(cudaMemcpyAsync(host, dtext, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
       if (!ndecl) {
         JX_CK(cudaStreamSynchronize(ctx->stream));
         host[total] = 0;
         out->text = host;
-        out->text_pinned = 2;                        // context-owned: valid until the next jx_blastfilter on ctx
+        out->text_pinned = 2;
+        out->owner = ctx;
         out->text_len = (int64_t)total;
+        guard.p = nullptr;                           // now owned by the result
       } else {
         // a few lines were declined by the device writer: format exactly those with the host's
         // glibc (the reference's own sscanf/sprintf pair, cblast.pyx:15,17) and splice them in
-        std::vector<uint32_t> hlen_all(nF), hpos_all(nF);
+        std::vector<uint32_t> hlen_all(nF); std::vector<uint64_t> hpos_all(nF);
         JX_CK(cudaMemcpyAsync(hlen_all.data(), flen, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        JX_CK(cudaMemcpyAsync(hpos_all.data(), fpos, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaMemcpyAsync(hpos_all.data(), fpos, (size_t)nF * 8, cudaMemcpyDeviceToHost, ctx->stream));
         JX_CK(cudaStreamSynchronize(ctx->stream));
         std::vector<int32_t> tmpq, tmps;
         const int32_t* hq = out->q_rank; const int32_t* hs = out->s_rank;
@@ -757,16 +756,15 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
         const uint32_t nd = (uint32_t)didx.size();
         JX_ALLOC(d_idx, uint32_t, nd, false);
         JX_ALLOC(len, uint32_t, nd, false);
-        JX_ALLOC(pos, uint32_t, nd, false);
+        JX_ALLOC(pos, uint64_t, nd, false);
         JX_CK(cudaMemcpyAsync(d_idx, didx.data(), (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->stream));
         JX_LAUNCH(k_line_len, nblk(nd), 256, 0, tok.d_text, tok.nbytes, ooff, d_idx, nd, len);
-        if ((rc = jx_exclusive_sum(ctx, arena, len, pos, nd))) return rc;
-        std::vector<uint32_t> hlen(nd), hpos(nd);
+        if ((rc = jx_exclusive_sum64(ctx, arena, len, pos, nd))) return rc;
+        std::vector<uint32_t> hlen(nd); std::vector<uint64_t> hpos(nd);
         JX_CK(cudaMemcpyAsync(hlen.data(), len, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        JX_CK(cudaMemcpyAsync(hpos.data(), pos, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        JX_CK(cudaMemcpyAsync(hpos.data(), pos, (size_t)nd * 8, cudaMemcpyDeviceToHost, ctx->stream));
         JX_CK(cudaStreamSynchronize(ctx->stream));
-        const uint64_t ltotal = (uint64_t)hpos[nd - 1] + hlen[nd - 1];
-        if (ltotal >= 0xFFFFFFFFull) { ctx->err = "declined lines exceed 4 GiB"; return JX_EUNSUPPORTED; }
+        const uint64_t ltotal = hpos[nd - 1] + hlen[nd - 1];
         JX_ALLOC(packed, uint8_t, (size_t)ltotal, false);
         JX_LAUNCH(k_copy_lines, nblk((size_t)nd * 32), 256, 0, tok.d_text, ooff, d_idx, len, pos, nd, packed);
         std::vector<char> hl((size_t)ltotal);

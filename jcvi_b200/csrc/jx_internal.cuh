@@ -106,8 +106,10 @@ struct jx_ctx {
   bool sess_open = false;
   uint8_t* lines_dev = nullptr;  // grow-only device buffer of the last jx_*_device result (packed raw lines)
   size_t lines_dev_cap = 0;
-  char* pin_buf = nullptr;       // grow-only pinned staging for the `.filtered` text
-  size_t pin_cap = 0;
+  // pinned buffers for `.filtered` texts: a result borrows one and gives it back in jx_filter_result_free, so
+  // every result owns its text (no staleness when a later call runs) and steady state allocates nothing
+  struct PinBuf { char* p; size_t cap; bool busy; };
+  std::vector<PinBuf> pin_pool;
   char* pin_small = nullptr;     // grow-only pinned staging for small result arrays (one D2H instead of several pageable ones)
   size_t pin_small_cap = 0;
   uint8_t* held_text = nullptr;
@@ -147,6 +149,29 @@ inline void jx_harvest_tok_events(jx_ctx* ctx) {
     cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
   }
   ctx->tok_events.clear();
+}
+
+inline char* jx_pin_acquire(jx_ctx* ctx, size_t bytes) {
+  int best = -1, spare = -1;
+  for (int i = 0; i < (int)ctx->pin_pool.size(); ++i) {
+    auto& b = ctx->pin_pool[(size_t)i];
+    if (b.busy) continue;
+    if (b.cap >= bytes) { if (best < 0 || b.cap < ctx->pin_pool[(size_t)best].cap) best = i; }
+    else spare = i;
+  }
+  if (best >= 0) { ctx->pin_pool[(size_t)best].busy = true; return ctx->pin_pool[(size_t)best].p; }
+  const size_t cap = bytes + (bytes >> 2) + (1u << 20);
+  char* p = nullptr;
+  if (spare >= 0) {                                 // a free buffer that is too small: replace it
+    cudaFreeHost(ctx->pin_pool[(size_t)spare].p);
+    ctx->pin_pool.erase(ctx->pin_pool.begin() + spare);
+  }
+  if (cudaMallocHost((void**)&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ctx->pin_pool.push_back({p, cap, true});
+  return p;
+}
+inline void jx_pin_release(jx_ctx* ctx, char* p) {
+  for (auto& b : ctx->pin_pool) if (b.p == p) { b.busy = false; return; }
 }
 
 // pinned staging of at least `bytes` (valid until the next call of this function on the context)

@@ -557,7 +557,10 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
   const size_t nwords = (size_t)(((uint64_t)nqc * nsc + 31) >> 5);
   JX_ALLOC(bitmap, uint32_t, nwords, true);
-  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist, cshift, nsc, nqc, bitmap);
+  // the prefilter keeps records at distance 0 from an anchor even when dist == 0 (`scan --dist=1 --liftover`
+  // gives liftover_dist 0): AnchorFile.filter_blocks needs the anchors' own raw pairs; lifting stays `< dist`
+  const int dist_pre = std::max(dist, 1);
+  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist_pre, cshift, nsc, nqc, bitmap);
   const size_t capC = (size_t)tstats[2] + 1;
   JX_ALLOC(C0, uint4, capC, false);
   JX_ALLOC(C0idx, uint32_t, capC, false);
@@ -574,7 +577,7 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
   JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
   JX_TRACE("lo: select_cell");
-  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist, C, Cidx,
+  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist_pre, C, Cidx,
                      d_cnt + 1);
   uint32_t nC = 0;
   JX_CK(cudaMemcpyAsync(&nC, d_cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -798,7 +801,8 @@ static int near_lines_impl(jx_ctx* ctx, const char* text, int64_t nbytes, int te
   while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
   const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
   JX_ALLOC(bitmap, uint32_t, (size_t)(((uint64_t)nqc * nsc + 31) >> 5), true);
-  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist, cshift, nsc, nqc, bitmap);
+  const int dist_pre = std::max(dist, 1);        // records AT an anchor are kept even when dist == 0 (see jx_liftover_text)
+  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist_pre, cshift, nsc, nqc, bitmap);
   const size_t capC = (size_t)tok.stats[2] + 1;
   JX_ALLOC(C0, uint4, capC, false);
   JX_ALLOC(C0idx, uint32_t, capC, false);
@@ -810,7 +814,7 @@ static int near_lines_impl(jx_ctx* ctx, const char* text, int64_t nbytes, int te
   JX_CK(cudaStreamSynchronize(ctx->stream));
   JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
   JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
-  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist, C, Cidx,
+  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist_pre, C, Cidx,
                      d_cnt + 1);
   uint32_t nC = 0;
   JX_CK(cudaMemcpyAsync(&nC, d_cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -41,14 +41,16 @@ def _text_ptr(text):
 
 
 class FilterResult(object):
-    def __init__(self, r, lib, Gq, Gs, want_mothers):
+    def __init__(self, r, lib, Gq, Gs, want_mothers, engine=None):
+        self._engine = engine          # the text may be borrowed from the context's pinned pool: keep the context alive
         n = r.n
         self.n = n
         self.q_rank = C.as_np(r.q_rank, n, np.int32) if r.q_rank else None
         self.s_rank = C.as_np(r.s_rank, n, np.int32) if r.s_rank else None
         self.score = C.as_np(r.score, n, np.float32) if r.score else None
         self.line_off = C.as_np(r.line_off, n, np.uint64) if r.line_off else None
-        # zero-copy view of the library-owned `.filtered` bytes; freed with this object
+        # zero-copy view of the `.filtered` bytes; they belong to this result (jx_filter_result_free returns a pinned
+        # buffer to the context's pool) and stay valid however many calls follow on the same engine
         self._raw, self._lib = r, lib
         self.text = (np.ctypeslib.as_array(ctypes.cast(r.text, C.c_u8p), shape=(max(r.text_len, 1),))[: r.text_len]
                      if r.text else None)
@@ -314,7 +316,7 @@ class Engine(object):
             self._check(rc)
         if raw:
             return r          # caller frees with free_filter()
-        return FilterResult(r, self.lib, self.Gq, self.Gs, want_mothers)   # owns and frees `r`
+        return FilterResult(r, self.lib, self.Gq, self.Gs, want_mothers, engine=self)   # owns and frees `r`
 
     def free_filter(self, r):
         self.lib.jx_filter_result_free(ctypes.byref(r))

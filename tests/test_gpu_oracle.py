@@ -75,6 +75,13 @@ def test_tie_heavy_liftover(tmp_path, mods):
               scan_args=["--min_size=2", "--dist=2"], lift_args=["--dist=14"])
 
 
+@pytest.mark.parametrize("dist", [0, 1])
+def test_liftover_dist_zero_and_one(tmp_path, mods, dist):
+    """`scan --dist=1 --liftover` gives liftover_dist 0: nothing is lifted, but every anchor whose pair occurs in the raw
+    table stays accepted (AnchorFile.filter_blocks); the oracle was checked against the live reference for dist 0 / 1 / 2."""
+    _pipeline(tmp_path, mods, seed=41, Gq=3000, Gs=3000, n=60000, Kq=4, Ks=4, lift_args=["--dist=%d" % dist])
+
+
 def test_writer_declined_lines_are_spliced(tmp_path, mods):
     """Lines the device writer declines (decimal rounding ties in the evalue, integers beyond
     int32, 17-digit percent identities) are formatted by the host's glibc and spliced in place."""
