@@ -404,14 +404,18 @@ JX_HD int strip5(const BR& B, int a, int b, int bar) {
 JX_HD uint32_t slot_index(uint32_t h, uint32_t d, uint32_t cshift) {
   return ((h ^ (d * 0x85EBCA6Bu)) * 0x9E3779B1u) >> cshift;
 }
+// Name hash (host table build in jx_core.cu and every kernel): h = init; h = h * C + w over the ceil(len / 4)
+// zero-padded little-endian words of the name (at least one); finish = (h ^ len) * K.  A chain of integer
+// multiply-adds -- they issue on the FMA pipe, the ALU pipe being the tokenizer's limiter -- whose TOP bits are
+// well mixed; bucket (h >> bshift) and slot (slot_index) use the top bits only.
 JX_HD uint32_t slot_hash_init() { return 0x2F0B4A87u; }
-JX_HD uint32_t slot_hash_step(uint32_t h, uint32_t w) { return rotl32(h ^ w, 13) * 0x9E3779B1u; }   // the rotation keeps equal hashes at the birthday rate
-JX_HD uint32_t slot_hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ (len * 0x85EBCA77u)); }
+JX_HD uint32_t slot_hash_step(uint32_t h, uint32_t w) { return h * 0x9E3779B1u + w; }
+JX_HD uint32_t slot_hash_finish(uint32_t h, uint32_t len) { return (h ^ len) * 0x85EBCA77u; }
 template <class R>
 JX_HD uint32_t slot_hash_bytes(R& rd, int a, int b) {            // generic (byte reader) form
   uint32_t h = slot_hash_init();
   const int nw = (b - a + 3) >> 2;
-  for (int k = 0; k < (nw > JX_SLOT_WORDS ? nw : JX_SLOT_WORDS); ++k) {
+  for (int k = 0; k < (nw > 1 ? nw : 1); ++k) {
     uint32_t w = 0;
     for (int j = 0; j < 4; ++j) { const int p = a + 4 * k + j; if (p < b) w |= rd(p) << (8 * j); }
     h = slot_hash_step(h, w);
@@ -437,12 +441,13 @@ JX_HD void name_words6(const TW& wr, int a, int len, uint32_t* w) {
     w[k] = funnel_r(x[k], x[k + 1], sh) & m;
   }
 }
-JX_HD uint32_t slot_hash6(const uint32_t* w, int len) {
-  uint32_t h = slot_hash_init();
+JX_HD uint32_t slot_hash6(const uint32_t* w, int len) {          // 1 <= len <= 24, w = the six zero-padded words
+  uint32_t h = slot_hash_step(slot_hash_init(), w[0]);
+  const int nw = (len + 3) >> 2;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int k = 0; k < JX_SLOT_WORDS; ++k) h = slot_hash_step(h, w[k]);
+  for (int k = 1; k < JX_SLOT_WORDS; ++k) if (k < nw) h = slot_hash_step(h, w[k]);
   return slot_hash_finish(h, (uint32_t)len);
 }
 

@@ -290,3 +290,72 @@ extern "C" int probe_gt_double(const char* s, double c) {
   if (!d.ok) return -2;
   return jx::dec_gt_double(d, c);
 }
+
+// v6: the kernel's first-level route (jx_fast6.cuh) on one line of a padded buffer, masks from the kernel's classifier.
+// Returns 1 when accepted: spans (raw names), score, eflag, stripped ends (no '|' handling: the kernel uses this route
+// only for tiles without one) and the version-2 slot hashes of the stripped names; 0 when refused.
+#include "jx_fast6.cuh"
+extern "C" int probe_fast_line6(const char* buf, int buflen, int s, int e, int* spans, float* score, int* eflag, int* strip_ends,
+                                unsigned* hashes) {
+  const int padded = ((buflen + 31) / 32) * 32 + 256;
+  std::vector<unsigned char> text((size_t)padded, (unsigned char)'\n');
+  memcpy(text.data(), buf, (size_t)buflen);
+  std::vector<uint32_t> mw((size_t)padded / 32 + 2), mn((size_t)padded / 32 + 2);
+  uint32_t hi = 0;
+  for (int seg = 0; seg < padded / 32; ++seg) {
+    uint32_t w[8];
+    memcpy(w, text.data() + 32 * seg, 32);
+    jx::classify32(w, mw[(size_t)seg], mn[(size_t)seg], hi);
+  }
+  struct MaskRd { const uint32_t* p; inline uint32_t operator()(int i) const { return p[i]; } };
+  WordRd wr{text.data()};
+  MaskRd rw{mw.data()}, rn{mn.data()};
+  jx::WordBytes<WordRd> B(wr);
+  jx::Line6 o;
+  if (!jx::fast_line6(B, wr, rw, rn, s, e - s, o)) return 0;
+  spans[0] = s; spans[1] = s + o.t0; spans[2] = s + o.t0 + 1; spans[3] = s + o.t1;
+  *score = o.score; *eflag = o.eflag;
+  PtrReader rd{text.data()};
+  for (int k = 0; k < 2; ++k) {
+    const int a = spans[2 * k], len = spans[2 * k + 1] - a;
+    const int sl = jx::strip6(B, a, len, B.load32(a));
+    strip_ends[k] = a + sl;
+    hashes[k] = jx::slot_hash_bytes(rd, a, a + sl);
+  }
+  return 1;
+}
+
+// the name table jx_bed_load builds for n names (blob + offsets): out = {slot bits, bucket bits, overflow names,
+// table words}; every name must then be found by the lookup the kernels do.  Returns the number of names NOT found.
+#include "jx_nametable.h"
+extern "C" long probe_build_table(const char* blob, const unsigned* off, long n, long* out) {
+  std::vector<uint32_t> nid((size_t)n);
+  for (long i = 0; i < n; ++i) nid[(size_t)i] = (uint32_t)i;
+  jx_bed bed; memset(&bed, 0, sizeof bed);
+  bed.n_genes = n; bed.names = blob; bed.name_off = off; bed.name_id = nid.data();
+  jxnt::BuiltSide B;
+  const std::string e = jxnt::build_side(&bed, B);
+  if (!e.empty()) return -1;
+  out[0] = 32 - (long)B.cshift; out[1] = 32 - (long)B.bshift; out[2] = (long)B.ovf_hash.size(); out[3] = (long)B.tab.size();
+  PtrReader rd{(const unsigned char*)blob};
+  long missing = 0;
+  for (long i = 0; i < n; ++i) {
+    const int a = (int)off[i], b = (int)off[i + 1];
+    const uint32_t h = jx::slot_hash_bytes(rd, a, b);
+    const uint32_t idx = jx::slot_index(h, B.disp[h >> B.bshift], B.cshift);
+    const uint32_t* slot = &B.tab[(size_t)idx * 8];
+    bool ok = slot[0] != 0;
+    if (ok) {                                   // compare the first 24 bytes like the kernel
+      for (int k = 0; k < 24 && ok; ++k) {
+        const unsigned char want = a + k < b ? (unsigned char)blob[a + k] : 0;
+        ok = (unsigned char)((slot[2 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu) == want;
+      }
+    }
+    if (!ok) {                                  // parked in the overflow list?
+      bool found = false;
+      for (size_t k = 0; k < B.ovf_hash.size(); ++k) if (B.ovf_hash[k] == h) found = true;
+      if (!found) ++missing;
+    }
+  }
+  return missing;
+}

@@ -18,34 +18,18 @@
 //   x = query rank  (0xFFFFFFFF: no record -- '#' line, unmapped name, dropped self hit ...)
 //   y = subject rank
 //   z = float32 score bits (cblast.pyx:88)
-//   w = (byte offset of the line inside its 8 KiB tile << 1) | (evalue < 1e-10)
+//   w = (byte offset of the line inside its tile (JX_TILE bytes) << 1) | (evalue < 1e-10)
 #define JX_NOREC 0xFFFFFFFFu
 
-#ifndef JX_TOK_MINBLOCKS
-#define JX_TOK_MINBLOCKS 8
-#endif
-#ifndef JX_TOK_THREADS_DEF
-#define JX_TOK_THREADS_DEF 128
-#endif
-constexpr int JX_TOK_THREADS = JX_TOK_THREADS_DEF;       // threads per CTA of the tokenizer
-// JX_GROUP threads cooperate on one tile.  128: one 8 KiB tile per CTA (phases separated by CTA
-// barriers).  32: every warp owns its own 1920-byte tiles (+128 bytes of look-ahead = 64 mask words,
-// two per lane) and never waits for another warp.
-#ifndef JX_GROUP
+constexpr int JX_TOK_THREADS = 128;                      // threads per CTA of the tokenizer; they cooperate on one tile
 #define JX_GROUP 128
-#endif
-constexpr int JX_SEG = 64;                               // bytes of the tile owned by one thread
-#if JX_GROUP == 32
-constexpr int JX_TILE = 30 * JX_SEG;                     // 1920
-constexpr int JX_OVER = 128;                             // look-ahead staged in shared memory
-#else
-#ifndef JX_OVER_DEF
-#define JX_OVER_DEF 1024
-#endif
-constexpr int JX_TILE = JX_GROUP * JX_SEG;               // 8192
-constexpr int JX_OVER = JX_OVER_DEF;
-#endif
-constexpr int JX_WIN = JX_TILE + JX_OVER;
+constexpr int JX_SEG = 64;                               // bytes of the staged window classified by one thread
+// A CTA stages a WINDOW of 8 KiB = 128 threads x 64 bytes: the tile (the lines that START in it are the CTA's)
+// plus 256 bytes of look-ahead, so that every thread classifies exactly one segment and a line that starts near
+// the end of the tile is still inside the window (longer lines fall back to reading global memory).
+constexpr int JX_OVER = 256;
+constexpr int JX_TILE = JX_TOK_THREADS * JX_SEG - JX_OVER;   // 7936 (a multiple of 16: bulk-copy source alignment)
+constexpr int JX_WIN = JX_TILE + JX_OVER;                // 8192
 
 struct SideDev {
   int64_t G = 0;
@@ -87,6 +71,7 @@ struct jx_ctx {
   size_t ws_cap = 0, ws_used = 0, ws_virtual = 0, ws_need = 0;
   int ws_depth = 0;
   int64_t tok_resident = 0;      // persistent tokenizer CTAs that fit on this device at once
+  bool tok_v5 = false;           // JX_TOK_V5=1: run the path through the version-5 kernel (A/B measurements)
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
   // records of the last jx_blastfilter pass over the held text, for jx_liftover_text

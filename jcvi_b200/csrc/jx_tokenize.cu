@@ -20,6 +20,7 @@
 // sscanf-faithful scanner.  HBM traffic per line: the line's bytes once + 16 bytes of record.
 #include "jx_internal.cuh"
 #include "jx_fast5.cuh"
+#include "jx_fast6.cuh"
 
 namespace {
 
@@ -127,7 +128,7 @@ struct MaskWords {             // one of the bit-per-byte class masks of the win
 };
 
 #ifndef JX_TOK_MINBLK
-#define JX_TOK_MINBLK 7
+#define JX_TOK_MINBLK 8
 #endif
 constexpr int STAGE_BYTES = JX_WIN + 32;          // one staged window (+ slack for unaligned word reads)
 
@@ -641,6 +642,476 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   }
 }
 
+
+// =====================================================================================================================
+// Version 6 of the path's kernel (MODE 0).  Same machinery as above -- persistent CTAs, bulk-copy double buffer,
+// software-pipelined tiles, decoupled look-back -- with the instruction stream cut for the ALU pipe, which is
+// what bounds this kernel:
+//   * window = 128 x 64 bytes: every thread classifies exactly one 64-byte segment, straight-line;
+//   * classification assumes 7-bit text (no per-byte masking, 7 instead of 11 logic ops per word); a tile with a
+//     byte >= 0x80 is re-classified with the exact classifier (CTA-uniform branch);
+//   * the '|' test moved from every byte of the tile to the name words of each line;
+//   * per line: jx_fast6.cuh (32-bit mask windows, evalue decided instead of converted, byte-permute digit groups,
+//     3-word names, multiply-add name hash); every line it refuses goes through `slow_line`, the version-5 route
+//     followed by the generic sscanf-faithful scanner, kept out of line so that it costs the fast path no registers.
+// Results are identical to the version-5 kernel by construction: the fast route accepts a subset of lines and is
+// checked against the generic scanner and glibc on the host (tests/test_parse_host.py).
+enum { WH_MAPPED = 0, WH_COMMENT, WH_UNMAPPED, WH_HARD, WH_LONG, WH_EXCL, WH_SELF, WH_NONE };
+struct SlowOut { uint4 rec; int what; };
+
+// 64 bytes of 7-bit text -> W / N mask words (two each); `any` accumulates the bytes (bit 7 = not 7-bit text)
+__device__ __forceinline__ void classify64_ascii(const uint4& v0, const uint4& v1, const uint4& v2, const uint4& v3, uint32_t* wm,
+                                                 uint32_t* nm, uint32_t& any) {
+  const uint32_t x[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pw[4], pn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a = x[8 * h + 2 * k], b = x[8 * h + 2 * k + 1];
+      any |= a | b;
+      // bit 7 of each byte: tw clear <=> byte <= 0x20; un set <=> neither digit nor tab (no carries between 7-bit bytes)
+      const uint32_t twa = a + 0x5F5F5F5Fu, twb = b + 0x5F5F5F5Fu;
+      const uint32_t una = ((a ^ 0x30303030u) + 0x76767676u) & ((a ^ 0x09090909u) + 0x7F7F7F7Fu);
+      const uint32_t unb = ((b ^ 0x30303030u) + 0x76767676u) & ((b ^ 0x09090909u) + 0x7F7F7F7Fu);
+      // eight flags -> eight mask bits (text order) in the top byte
+      const uint32_t gw = ((~twa >> 4) & 0x08080808u) | (~twb & 0x80808080u);
+      const uint32_t gn = ((una >> 4) & 0x08080808u) | (unb & 0x80808080u);
+      pw[k] = gw * 0x00204081u;
+      pn[k] = gn * 0x00204081u;
+    }
+    wm[h] = jx::top_bytes(pw[0], pw[1], pw[2], pw[3]);
+    nm[h] = jx::top_bytes(pn[0], pn[1], pn[2], pn[3]);
+  }
+}
+
+// does the word hold a '|' (0x7C) byte?  (exact "any zero byte" test on w ^ 0x7C7C7C7C)
+__device__ __forceinline__ uint32_t bar_in(uint32_t w) {
+  const uint32_t v = w ^ 0x7C7C7C7Cu;
+  return (v - 0x01010101u) & ~v & 0x80808080u;
+}
+
+// The version-5 route for ONE line of a staged tile: fast_line5 on the masks, else the generic scanner; names through
+// the byte-reader table lookup when they are long.  Mirrors the per-line body of k_tokenize<0> above.
+__device__ __noinline__ SlowOut slow_line(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
+                                          const int64_t base, const int s, const int e) {
+  SlowOut o;
+  o.rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+  o.what = WH_NONE;
+  const uint32_t* smw = reinterpret_cast<const uint32_t*>(sm);
+  if (s >= e) {
+    // an empty segment between the '\r' and the '\n' of a CR LF pair is not a line (universal newlines);
+    // a real blank line is a BlastLine with empty names, never in the BED
+    const uint32_t prev = s > 0 ? sm[s - 1] : (base > 0 ? a.text[base - 1] : 0u);
+    if (!(prev == '\r' && sm[s] == '\n')) o.what = WH_UNMAPPED;
+    return o;
+  }
+  WinReader rd{sm, a.text, base, a.n};
+  const SmemWords wr{smw};
+  const MaskWords mwr{s_w}, mnr{s_n};
+  const SmemText B{sm, smw};
+  const SideTab TQ{a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob, a.qovh, a.qovr, a.qnov};
+  const SideTab TS{a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob, a.sovh, a.sovr, a.snov};
+  jx::LineTok t;
+  const bool fast = (e + 8 <= JX_WIN) && jx::fast_line5(B, mwr, mnr, s, e, t);
+  if (!fast) jx::tokenize_line(rd, s, e, t);
+  bool bad = false, selfhit = false;
+  int qi = -1, si = -1;
+  if (t.nconv >= 2) {
+    if (t.longname) bad = true;
+    int qa = t.qa, qb = t.qb, sa = t.sa, sb = t.sb;
+    if (a.is_self && (qb - qa) == (sb - sa)) {      // `is_self and query == subject` on raw names
+      selfhit = true;
+      for (int i = 0; i < qb - qa; ++i) if (rd(qa + i) != rd(sa + i)) { selfhit = false; break; }
+    }
+    if (!selfhit && !bad) {
+      if (a.strip) { jx::strip_isoform(rd, qa, qb); jx::strip_isoform(rd, sa, sb); }
+      qi = table_lookup_bytes(rd, qa, qb, TQ);
+      if (qi >= 0) si = table_lookup_bytes(rd, sa, sb, TS);
+    }
+  }
+  if (bad) { o.what = WH_LONG; return o; }
+  if (selfhit) { o.what = WH_SELF; return o; }
+  if (qi < 0 || si < 0) { o.what = WH_UNMAPPED; return o; }
+  if (t.hard) { o.what = WH_HARD; return o; }
+  if (a.is_self && qi > si) { int tmp = qi; qi = si; si = tmp; }
+  if (a.neardiag && a.qchr[qi] == a.schr[si] && si - qi < 40) { o.what = WH_SELF; return o; }
+  o.rec = make_uint4((uint32_t)qi, (uint32_t)si, __float_as_uint(t.score), ((uint32_t)s << 1) | (uint32_t)t.eflag);
+  o.what = WH_MAPPED;             // (the exclusion list and the best-score table are the caller's business)
+  return o;
+}
+
+__global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize6(const __grid_constant__ TokArgs a) {
+  __shared__ __align__(128) uint8_t s_text[2][STAGE_BYTES];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_term[JX_WIN / 32 + 2];      // terminator bit per byte of the window (+2: 64-bit windows read past it)
+  __shared__ uint32_t s_w[JX_WIN / 32 + 2];         // byte <= 0x20
+  __shared__ uint32_t s_n[JX_WIN / 32 + 2];         // byte is neither a digit nor a tab
+  __shared__ uint32_t s_pref[JX_TOK_THREADS];       // exclusive prefix of line starts per 64-byte segment
+  __shared__ unsigned long long s_start[JX_TOK_THREADS];
+  __shared__ uint16_t s_lpos[LCAP];                 // start offset of every line of the tile
+  __shared__ uint32_t s_warp[JX_TOK_THREADS / 32], s_wbit[JX_TOK_THREADS / 32];
+  __shared__ uint32_t s_next[2];
+  __shared__ unsigned long long s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0, c_lines = 0;
+  unsigned long long first_bad = 0;
+  bool overflow = false;
+  // tiles whose whole stage lies inside the text need no length arithmetic
+  const uint32_t n_full = a.n >= (int64_t)STAGE_BYTES ? (uint32_t)((a.n - STAGE_BYTES) / JX_TILE) + 1u : 0u;
+
+  auto avail_of = [&](uint32_t t) -> uint32_t {    // bytes of tile t's stage that exist in the text
+    if (t < n_full) return (uint32_t)STAGE_BYTES;
+    const int64_t left = a.n - (int64_t)t * JX_TILE;
+    return (uint32_t)(left < (int64_t)STAGE_BYTES ? (left < 0 ? 0 : left) : STAGE_BYTES);
+  };
+  auto issue = [&](uint32_t t, int stage) {        // one thread
+    const uint32_t bytes = avail_of(t) & ~15u;
+    if (bytes) {
+      mbar_expect_tx(&s_bar[stage], bytes);
+      bulk_g2s(s_text[stage], a.text + (int64_t)t * JX_TILE, bytes, &s_bar[stage]);
+    }
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t t0 = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[0] = t0;
+    if (t0 < a.tile_end) issue(t0, 0);
+    const uint32_t t1 = a.tile_begin + atomicAdd(a.ticket, 1u);
+    s_next[1] = t1;
+    if (t1 < a.tile_end) issue(t1, 1);
+  }
+  __syncthreads();
+
+  // ---- prepare(tile): wait for its bytes, classify them, count and locate its line starts, PUBLISH the count ----
+  auto prepare = [&](const uint32_t tile, const int stage, const uint32_t parity, uint32_t& nlines_out) {
+    const uint8_t* sm = s_text[stage];
+    const int64_t base = (int64_t)tile * JX_TILE;
+    const bool full = tile < n_full;
+    {
+      const uint32_t avail = avail_of(tile), bulk = avail & ~15u;
+      if (bulk) {
+        while (!mbar_try_wait(&s_bar[stage], parity)) {}
+      }
+      if (!full) {                                  // last tiles of the text only: '\n' beyond its end
+        uint8_t* wsm = s_text[stage];
+        for (uint32_t i = bulk + tid; i < (uint32_t)STAGE_BYTES; i += JX_TOK_THREADS)
+          wsm[i] = i < avail ? a.text[base + i] : (uint8_t)'\n';
+        __syncthreads();
+      }
+    }
+    // ---- byte classes of this thread's 64-byte segment ------------------------------------------------------------
+    const uint4* seg4 = reinterpret_cast<const uint4*>(sm + tid * JX_SEG);
+    const uint4 v0 = seg4[0], v1 = seg4[1], v2 = seg4[2], v3 = seg4[3];
+    uint32_t wm[2], nm[2], term[2], any = 0;
+    classify64_ascii(v0, v1, v2, v3, wm, nm, any);
+    auto finish_masks = [&]() {
+      // a terminator is a byte <= 0x20 that is not a tab: usually the only such bytes, checked by value
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t c = wm[h] & nm[h], tm = 0;
+        while (c) {
+          const int b = __ffs((int)c) - 1;
+          c &= c - 1u;
+          const uint32_t ch = sm[tid * JX_SEG + h * 32 + b];
+          if (ch == '\n' || ch == '\r') tm |= 1u << b;
+        }
+        term[h] = tm;
+      }
+      reinterpret_cast<uint2*>(s_w)[tid] = make_uint2(wm[0], wm[1]);
+      reinterpret_cast<uint2*>(s_n)[tid] = make_uint2(nm[0], nm[1]);
+      reinterpret_cast<uint2*>(s_term)[tid] = make_uint2(term[0], term[1]);
+      if (lane == 31) s_wbit[warp] = term[1] >> 31;     // the bit before the next warp's first segment
+    };
+    finish_masks();
+    if (__syncthreads_or((any & 0x80808080u) != 0u)) {   // a byte >= 0x80 somewhere in the window: exact classifier
+      uint32_t hiacc = 0;
+      const uint32_t w8a[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}, w8b[8] = {v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+      jx::classify32(w8a, wm[0], nm[0], hiacc);
+      jx::classify32(w8b, wm[1], nm[1], hiacc);
+      finish_masks();
+      __syncthreads();
+    }
+    // ---- line starts inside the tile + block scan ---------------------------------------------------------------------
+    // the bit before this segment: the previous thread's last terminator bit (the byte before the tile for thread 0)
+    uint32_t prevbit = __shfl_up_sync(0xFFFFFFFFu, term[1] >> 31, 1);
+    if (lane == 0) prevbit = tid ? s_wbit[warp - 1] : ((base == 0) ? 1u : (uint32_t)jx::is_term(a.text[base - 1]));
+    unsigned long long starts = 0;
+    if (tid < JX_TILE / JX_SEG) {
+      const unsigned long long tm = (unsigned long long)term[0] | ((unsigned long long)term[1] << 32);
+      starts = (tm << 1) | prevbit;
+      if (!full) {                                  // only positions that exist can start a line
+        const int64_t remain = a.n - (base + (int64_t)tid * JX_SEG);
+        if (remain <= 0) starts = 0;
+        else if (remain < 64) starts &= (1ull << remain) - 1ull;
+      }
+    }
+    const uint32_t slo = (uint32_t)starts, shi = (uint32_t)(starts >> 32);
+    const uint32_t cnt = __popc(slo) + __popc(shi);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, nlines = 0;
+#pragma unroll
+    for (int w = 0; w < JX_TOK_THREADS / 32; ++w) { const uint32_t v = s_warp[w]; if (w < warp) wbase += v; nlines += v; }
+    uint32_t o = wbase + inc - cnt;
+    if (nlines > (uint32_t)LCAP) { s_pref[tid] = o; s_start[tid] = starts; }   // overfull tile: the search path needs them
+    {
+      uint32_t m = slo;
+      const uint32_t p0 = (uint32_t)(tid * JX_SEG);
+      while (m && o < (uint32_t)LCAP) { s_lpos[o++] = (uint16_t)(p0 + __ffs((int)m) - 1); m &= m - 1u; }
+      m = shi;
+      while (m && o < (uint32_t)LCAP) { s_lpos[o++] = (uint16_t)(p0 + 32u + __ffs((int)m) - 1); m &= m - 1u; }
+    }
+    if (tid == 0) {
+      const uint64_t d = (tile == 0 ? FLAG_INC : FLAG_AGG) | (uint64_t)nlines;
+      atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)d);
+    }
+    nlines_out = nlines;
+  };
+
+  // ---- decoupled look-back (warp 0): global ordinal of the tile's first line ------------------------------------
+  auto look_back = [&](const uint32_t tile, const uint32_t nlines) {
+#ifdef JX_EXP_NOLB
+    if (lane == 0) s_base = (unsigned long long)tile * 128ull;     // EXPERIMENT: sparse slots, no chain (timing only)
+    return;
+#endif
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      int64_t j = (int64_t)tile - 1;
+      uint32_t spins = 0;
+      bool done = false;
+      while (!done) {
+        const int64_t idx = j - lane;
+        const uint64_t d = idx >= 0 ? *((volatile uint64_t*)(a.desc + idx)) : FLAG_INC;
+        const uint32_t flag = (uint32_t)(d >> 62);
+        const unsigned notready = __ballot_sync(0xFFFFFFFFu, flag == 0);
+        const unsigned isinc = __ballot_sync(0xFFFFFFFFu, flag == 2);
+        const int first = isinc ? __ffs(isinc) - 1 : 32;
+        const unsigned upto = first < 31 ? ((2u << first) - 1u) : 0xFFFFFFFFu;
+        if (notready & upto) {
+          if (++spins > (1u << 22)) { if (lane == 0) atomicExch(a.stats + 10, 1ull); done = true; }   // never hang the GPU
+          else __nanosleep(64);
+        } else {
+          const uint32_t agg = ((int)lane < first) ? (uint32_t)d : 0u;
+          excl += __reduce_add_sync(0xFFFFFFFFu, agg);
+          if (first < 32) {
+            excl += __shfl_sync(0xFFFFFFFFu, (unsigned long long)(d & VAL_MASK), first);
+            done = true;
+          } else {
+            j -= 32;
+          }
+        }
+      }
+      if (lane == 0) atomicExch((unsigned long long*)(a.desc + tile), (unsigned long long)(FLAG_INC | (excl + nlines)));
+    }
+    if (lane == 0) s_base = excl;
+  };
+
+  const bool v6 = !a.is_self;                        // self comparisons compare and swap raw names: version-5 route
+  uint32_t tile = a.tile_end, nlines = 0;
+  for (int it = -1;; ++it) {
+    const bool have_cur = it >= 0;
+    const int stage = it & 1;
+    const uint8_t* sm = s_text[stage];
+    const uint32_t* smw = reinterpret_cast<const uint32_t*>(sm);
+    const int64_t base = (int64_t)tile * JX_TILE;
+    const bool defer = nlines <= (uint32_t)JX_TOK_THREADS;
+    uint4 held = make_uint4(JX_NOREC, 0u, 0u, 0u);
+    bool have_held = false;
+    if (have_cur) {
+      if (!defer) {
+        __syncthreads();                             // nobody still reads the previous tile's s_base
+        if (warp == 0) look_back(tile, nlines);
+        __syncthreads();
+      }
+      const SmemWords wr{smw};
+      const MaskWords mwr{s_w}, mnr{s_n};
+      const SmemText B{sm, smw};
+      for (uint32_t k0 = 0; k0 < nlines; k0 += JX_TOK_THREADS) {
+        const uint32_t k = k0 + tid;
+        if (k >= nlines) break;
+        int s, e;
+        if (k < (uint32_t)LCAP) s = s_lpos[k];
+        else {   // overfull tile (average line < 8 bytes): locate the line through the prefix array
+          int lo = 0, hi = JX_TOK_THREADS - 1;
+          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= k) lo = mid; else hi = mid - 1; }
+          unsigned long long m = s_start[lo];
+          for (uint32_t r = k - s_pref[lo]; r; --r) m &= m - 1;
+          s = lo * JX_SEG + __ffsll((long long)m) - 1;
+        }
+        if (k + 1 < nlines && k + 1 < (uint32_t)LCAP) e = (int)s_lpos[k + 1] - 1;
+        else {   // the tile's last line: next terminator at or after s
+          int w = s >> 5;
+          uint32_t m = s_term[w] & (0xFFFFFFFFu << (s & 31));
+          while (!m && ++w < JX_WIN / 32) m = s_term[w];
+          if (m) e = w * 32 + __ffs(m) - 1;
+          else { e = JX_WIN; while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e; }
+        }
+        uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+        int what = WH_NONE;
+        bool fastdone = false;
+        const int len = e - s;
+#ifdef JX_EXP_NOPARSE
+        if (true) { what = WH_COMMENT; fastdone = true; rec.x = (uint32_t)len; } else
+#endif
+        if (len > 0 && sm[s] == '#') {
+          what = WH_COMMENT; fastdone = true;
+        } else if (v6 && e + 8 <= JX_WIN) {
+          jx::Line6 L;
+          if (jx::fast_line6_names(mwr, mnr, s, len, L)) {
+            // ---- names: three zero-padded words each, gene_name, perfect-hash probe --------------------------------
+            const int qa = s, sa = s + L.t0 + 1;
+            int lq = L.t0, lsn = L.t1 - L.t0 - 1;
+            const int iq = qa >> 2, is = sa >> 2;
+            const uint32_t shq = (uint32_t)(qa & 3) * 8u, shs = (uint32_t)(sa & 3) * 8u;
+            const uint32_t xq0 = smw[iq], xq1 = smw[iq + 1], xq2 = smw[iq + 2], xq3 = smw[iq + 3];
+            const uint32_t xs0 = smw[is], xs1 = smw[is + 1], xs2 = smw[is + 2], xs3 = smw[is + 3];
+            uint32_t q0 = __funnelshift_r(xq0, xq1, shq), q1 = __funnelshift_r(xq1, xq2, shq), q2 = __funnelshift_r(xq2, xq3, shq);
+            uint32_t s0 = __funnelshift_r(xs0, xs1, shs), s1 = __funnelshift_r(xs1, xs2, shs), s2 = __funnelshift_r(xs2, xs3, shs);
+            if (a.strip) { lq = jx::strip6(B, qa, lq, q0); lsn = jx::strip6(B, sa, lsn, s0); }
+            if (lq <= 12 && lsn <= 12 && lq >= 1 && lsn >= 1) {
+              q0 &= jx::name_mask(lq, 0); q1 &= jx::name_mask(lq, 1); q2 &= jx::name_mask(lq, 2);
+              s0 &= jx::name_mask(lsn, 0); s1 &= jx::name_mask(lsn, 1); s2 &= jx::name_mask(lsn, 2);
+              const uint32_t bar = a.strip ? (bar_in(q0) | bar_in(q1) | bar_in(q2) | bar_in(s0) | bar_in(s1) | bar_in(s2)) : 0u;
+              if (bar == 0u) {
+                uint32_t hq = jx::slot_hash_step(jx::slot_hash_init(), q0), hs = jx::slot_hash_step(jx::slot_hash_init(), s0);
+                if (lq > 4) hq = jx::slot_hash_step(hq, q1);
+                if (lsn > 4) hs = jx::slot_hash_step(hs, s1);
+                if (lq > 8) hq = jx::slot_hash_step(hq, q2);
+                if (lsn > 8) hs = jx::slot_hash_step(hs, s2);
+                hq = jx::slot_hash_finish(hq, (uint32_t)lq); hs = jx::slot_hash_finish(hs, (uint32_t)lsn);
+                // the table loads are issued HERE; the rest of the line is parsed while they are in flight
+#ifdef JX_EXP_NOLOOKUP
+                const uint4 tq0 = make_uint4((hq & 1023u) + 1u, hq & 1023u, q0, q1), tq1 = make_uint4(q2, 0u, 0u, 0u), ts0 = make_uint4((hs & 1023u) + 1u, hs & 1023u, s0, s1), ts1 = make_uint4(s2, 0u, 0u, 0u);
+#else
+                const uint32_t dq = __ldg(a.qdisp + (hq >> a.qbshift)), ds = __ldg(a.sdisp + (hs >> a.sbshift));
+                const uint4* pq = a.qtab + 2 * jx::slot_index(hq, dq, a.qcshift);
+                const uint4* ps = a.stab + 2 * jx::slot_index(hs, ds, a.scshift);
+                const uint4 tq0 = __ldg(pq), tq1 = __ldg(pq + 1), ts0 = __ldg(ps), ts1 = __ldg(ps + 1);
+#endif
+                if (jx::fast_line6_rest(B, wr, mwr, mnr, s, len, L)) {
+                  const uint32_t dfq = (tq0.z ^ q0) | (tq0.w ^ q1) | (tq1.x ^ q2) | tq1.y | tq1.z | tq1.w;
+                  const uint32_t dfs = (ts0.z ^ s0) | (ts0.w ^ s1) | (ts1.x ^ s2) | ts1.y | ts1.z | ts1.w;
+                  const bool okq = tq0.x != 0u && dfq == 0u, oks = ts0.x != 0u && dfs == 0u;
+                  // a miss may be a name parked in an overflow list (names with equal 32-bit hashes): rare route
+                  if ((okq && oks) || (a.qnov | a.snov) == 0u) {
+                    fastdone = true;
+                    if (!(okq && oks)) what = WH_UNMAPPED;
+                    else {
+                      const uint32_t qi = tq0.x - 1u, si = ts0.x - 1u;
+                      bool keep = true;
+                      if (a.n_excl) {
+                        const uint64_t key = ((uint64_t)qi << 32) | si;
+                        int64_t l = 0, h = a.n_excl;
+                        while (l < h) { const int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+                        if (l < a.n_excl && a.excl[l] == key) { keep = false; what = WH_EXCL; }
+                      }
+                      if (keep) {
+                        what = WH_MAPPED;
+                        const uint32_t sbits = __float_as_uint(L.score);
+                        rec = make_uint4(qi, si, sbits, ((uint32_t)s << 1) | (uint32_t)L.eflag);
+#ifndef JX_EXP_NOLOOKUP
+                        if (a.best && L.score > 0.f) {        // best_score[name] = max(score), starting at 0.0:
+                          atomicMax(a.best + tq0.y, sbits);   // two reductions (no return value, nothing to wait for)
+                          atomicMax(a.best + ts0.y, sbits);
+                        }
+#endif
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (!fastdone) {
+          const SlowOut so = slow_line(a, sm, s_w, s_n, base, s, e);
+          rec = so.rec; what = so.what;
+          if (what == WH_MAPPED) {
+            if (a.n_excl) {
+              const uint64_t key = ((uint64_t)rec.x << 32) | rec.y;
+              int64_t l = 0, h = a.n_excl;
+              while (l < h) { const int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+              if (l < a.n_excl && a.excl[l] == key) { what = WH_EXCL; rec.x = JX_NOREC; }
+            }
+            if (what == WH_MAPPED && a.best && __uint_as_float(rec.z) > 0.f) {
+              atomicMax(a.best + a.qnid[rec.x], rec.z);
+              atomicMax(a.best + a.snid[rec.y], rec.z);
+            }
+          }
+        }
+        switch (what) {
+          case WH_MAPPED: ++c_mapped; break;
+          case WH_COMMENT: ++c_comment; break;
+          case WH_UNMAPPED: ++c_unmapped; break;
+          case WH_HARD: ++c_hard; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; break;
+          case WH_LONG: ++c_long; if (!first_bad) first_bad = (unsigned long long)(base + s) + 1; break;
+          case WH_EXCL: ++c_excl; break;
+          case WH_SELF: ++c_self; break;
+          default: break;
+        }
+        if (defer) { held = rec; have_held = true; }
+        else {
+          const unsigned long long ord = s_base + k;
+          if (ord < a.rec_cap) a.recs[ord] = rec;
+        }
+      }
+      __syncthreads();                               // this stage and the mask / line-start arrays are free again
+      if (tid == 0) {                                // T[it + 2] goes into the stage just released
+        const uint32_t t = a.tile_begin + atomicAdd(a.ticket, 1u);
+        s_next[stage] = t;
+        if (t < a.tile_end) issue(t, stage);
+      }
+    }
+
+    // ---- the next tile: classified, counted and published before this CTA waits for anybody -------------------------
+    const uint32_t nxt = s_next[(it + 1) & 1];
+    uint32_t nxt_lines = 0;
+    if (nxt < a.tile_end) prepare(nxt, (it + 1) & 1, (uint32_t)((it + 1) >> 1) & 1u, nxt_lines);
+
+    if (have_cur && defer) {
+      if (warp == 0) look_back(tile, nlines);
+    }
+    __syncthreads();                                 // s_base; the next tile's arrays; s_next
+    if (have_cur) {
+      if (defer) {
+        const unsigned long long ord = s_base + tid;
+        if (have_held && ord < a.rec_cap) a.recs[ord] = held;
+      }
+      if (tid == 0) {
+        c_lines += nlines;
+        if (s_base + nlines > a.rec_cap) overflow = true;
+      }
+    }
+    if (nxt >= a.tile_end) break;
+    tile = nxt; nlines = nxt_lines;
+  }
+
+  uint32_t vals[7] = {c_comment, c_mapped, c_unmapped, c_hard, c_long, c_excl, c_self};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) vals[i] = __reduce_add_sync(0xFFFFFFFFu, vals[i]);
+  if (lane == 0) {
+    if (vals[0]) atomicAdd(a.stats + 1, (unsigned long long)vals[0]);
+    if (vals[1]) atomicAdd(a.stats + 2, (unsigned long long)vals[1]);
+    if (vals[2]) atomicAdd(a.stats + 3, (unsigned long long)vals[2]);
+    if (vals[3]) atomicAdd(a.stats + 4, (unsigned long long)vals[3]);
+    if (vals[4]) atomicAdd(a.stats + 5, (unsigned long long)vals[4]);
+    if (vals[5]) atomicAdd(a.stats + 8, (unsigned long long)vals[5]);
+    if (vals[6]) atomicAdd(a.stats + 9, (unsigned long long)vals[6]);
+  }
+  if (first_bad) atomicMin(a.stats + 7, first_bad);
+  if (tid == 0) {
+    if (c_lines) atomicAdd(a.stats + 0, (unsigned long long)c_lines);
+    if (overflow) atomicExch(a.stats + 6, 1ull);
+  }
+}
+
 }  // namespace
 
 int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
@@ -735,6 +1206,9 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       unsigned long long init = ~0ull;
       JX_CK(cudaMemcpyAsync(d_stats + 7, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     }
+#ifdef JX_EXP_NOLB
+    JX_CK(cudaMemsetAsync(recs, 0xFF, (size_t)cap64 * sizeof(uint4), ctx->stream));
+#endif
     JX_TRACE("tok: allocs");
     TokArgs a;
     a.text = d_text; a.n = nbytes; a.desc = d_desc; a.ticket = d_ticket; a.tile_begin = 0; a.tile_end = 0; a.recs = recs; a.rec_cap = (uint32_t)cap64;
@@ -752,7 +1226,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     // persistent CTAs: as many as are resident at once
     if (!ctx->tok_resident) {
       int per_sm = 0, n_sm = 0;
-      JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<0>, JX_TOK_THREADS, 0));
+      if (ctx->tok_v5) JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<0>, JX_TOK_THREADS, 0));
+      else JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize6, JX_TOK_THREADS, 0));
       JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->tok_resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
     }
@@ -780,7 +1255,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       a.ticket = d_ticket + c; a.tile_begin = (uint32_t)t0; a.tile_end = (uint32_t)t1;
       if (mode.filter) JX_LAUNCH(k_tokenize<2>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       else if (mode.names) JX_LAUNCH(k_tokenize<1>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
-      else JX_LAUNCH(k_tokenize<0>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else if (ctx->tok_v5) JX_LAUNCH(k_tokenize<0>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else JX_LAUNCH(k_tokenize6, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
     }

@@ -169,20 +169,38 @@ def test_name_table_boundaries(tmp_path, mods):
 
 def test_names_with_equal_hashes(tmp_path, mods):
     """Two BED names with the same 32-bit table hash cannot both live in the perfect-hash table: the
-    second goes to the overflow list that lookups consult after a miss.  Colliding names are found
-    by a birthday search with the library's own hash."""
+    second goes to the overflow list that lookups consult after a miss.  Colliding names are constructed
+    from the hash's definition and confirmed with the library's own hash."""
     import ctypes
     probe = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jcvi_b200",
                                      "libjx_hostprobe.so"))
-    n = 700000
-    names = ["Ag%06d" % (7 * i + 3) for i in range(n)]      # ~n^2 / 2^33 = 57 pairs of equal hashes expected
+    # the name hash is a multiply-add chain over the name's 32-bit words (jx_fast5.cuh slot_hash_*): two 8-byte names
+    # collide iff  w0 * C + w1  agree mod 2^32 -- solve for the second word and keep the solutions that are printable
+    C = 0x9E3779B1
+    ok = np.zeros(256, dtype=bool)
+    ok[[ord(c) for c in "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789_-+:=@~^"]] = True
+    srng = np.random.default_rng(77)
+    alpha = np.flatnonzero(ok).astype(np.uint8)
+    pairs = []
+    while len(pairs) < 12:
+        a8 = srng.choice(alpha, size=(200000, 8))
+        b4 = srng.choice(alpha, size=(200000, 4))
+        w0a = a8[:, :4].copy().view("<u4")[:, 0].astype(np.uint64); w1a = a8[:, 4:].copy().view("<u4")[:, 0].astype(np.uint64)
+        w0b = b4.copy().view("<u4")[:, 0].astype(np.uint64)
+        w1b = ((w0a * C + w1a - w0b * C) & 0xFFFFFFFF).astype("<u4")
+        byt = w1b.view(np.uint8).reshape(-1, 4)
+        good = ok[byt].all(axis=1) & (w0a != w0b)
+        for i in np.flatnonzero(good)[:16]:
+            pairs.append((bytes(a8[i]).decode(), (bytes(b4[i]) + bytes(byt[i])).decode()))
+    names = ["Ag%06d" % (7 * i + 3) for i in range(3000)] + [x for pr in pairs for x in pr]
+    n = len(names)
     blob = "".join(names).encode()
     off = np.concatenate([[0], np.cumsum([len(x) for x in names])]).astype(np.uint32)
     out = np.zeros(n, dtype=np.uint32)
     probe.probe_slot_hash_many(blob, off.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(n), out.ctypes.data_as(ctypes.c_void_p))
     order = np.argsort(out, kind="stable")
     same = np.nonzero(out[order][1:] == out[order][:-1])[0]
-    assert len(same) >= 5, "birthday search found too few collisions"
+    assert len(same) >= 12, "the constructed names do not collide"
     coll = sorted(set(order[same].tolist()) | set(order[same + 1].tolist()))
     rng = np.random.default_rng(5)
     others = rng.choice(n, 1500, replace=False).tolist()

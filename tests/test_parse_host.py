@@ -318,3 +318,123 @@ def test_slot_hash_word_route_equals_byte_route(probe):
         probe.probe_slot_hash_many(name, off.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(1), out.ctypes.data_as(ctypes.c_void_p))
         assert (h6 & 0xFFFFFFFF) == int(out[0]), (name, pad)
         assert np.array(list(words), dtype="<u4").tobytes() == name + b"\0" * (24 - L), (name, pad)
+
+
+def test_fast_line6_agrees_with_generic_scanner(probe):
+    """v6 (jx_fast6.cuh, the kernel's first-level route): whatever it ACCEPTS must equal the sscanf-faithful generic
+    scanner field for field -- every alignment, short and long names, the number formats the aligners write, and
+    near-regular lines with one defect (those must be refused or still parse identically)."""
+    rng = np.random.default_rng(606)
+    alphabet = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789_.-"
+
+    def name():
+        n = int(rng.integers(1, 17)) if rng.random() < 0.9 else int(rng.integers(17, 40))
+        return "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), n))
+
+    def evalue():
+        r = rng.random()
+        if r < 0.5:
+            x = float(10 ** rng.uniform(-300, 3))
+            return ["%.1e", "%.2e", "%.0e", "%.3g", "%g", "%.2g"][int(rng.integers(0, 6))] % x
+        if r < 0.6:
+            return ["0.0", "0", "0.000", "1e-10", "9.99e-11", "1.0e-10", "1e-11", "0.5e-9", "0.0e-12", "1e-9", "1e-100",
+                    "2e-05", "1E-20", "1.5e+02", "0.00000000001", "0.0000000001", "12.5e-12", "9e-011", "1e-0100"][int(rng.integers(0, 19))]
+        return ["%.3f", "%.1f", "%d", "%.5f", "%.9f"][int(rng.integers(0, 5))] % (
+            rng.uniform(0, 10) if rng.random() < 0.7 else 0)
+
+    def score():
+        r = rng.random()
+        if r < 0.6:
+            return ["%.1f", "%.0f", "%.2f", "%.3f", "%.4f"][int(rng.integers(0, 5))] % float(10 ** rng.uniform(0, 5))
+        if r < 0.8:
+            return str(int(10 ** rng.uniform(0, 8)))
+        return ["16777215", "16777216", "16777217", "1677721.5", "999.9999", "0.5", "0", "100.", "1e3", "3.2e+02", ".5", "1.23456",
+                "99999999", "8388608.5", "00012.5"][int(rng.integers(0, 15))]
+
+    naccept = ntotal = 0
+    for it in range(12000):
+        f = [name(), name(), "%.2f" % rng.uniform(0, 100) if rng.random() < 0.8 else str(int(rng.integers(0, 101)))]
+        f += [str(int(rng.integers(0, 10 ** int(rng.integers(1, 7))))) for _ in range(7)]
+        f += [evalue(), score()]
+        if it % 7 == 0:                                  # one defect
+            k = int(rng.integers(0, 8))
+            j = int(rng.integers(0, 12))
+            if k == 0: f[j] = ""
+            elif k == 1: f[j] = f[j] + " "
+            elif k == 2: f[j] = f[j][:1] + "x" + f[j][1:]
+            elif k == 3: f[j] = "-" + f[j]
+            elif k == 4: f = f[:j] + f[j + 1:]
+            elif k == 5: f[j] = f[j] + "\t"
+            elif k == 6: f[2] = f[2].replace(".", "..") if "." in f[2] else "."
+            else: f[j] = f[j].replace("e", "e+") if "e" in f[j] else f[j] + ".7."
+        ln = "\t".join(f)
+        pad = it % 41
+        raw = (b"#" * pad) + ln.encode()
+        buf = raw + b"\n" + b"Zq9\tnext\t1.0\t" * 3
+        s, n = pad, len(raw)
+        spans = (ctypes.c_int * 4)(); sc = ctypes.c_float(); eflag = ctypes.c_int()
+        ends = (ctypes.c_int * 2)(); hs = (ctypes.c_uint * 2)()
+        ok = probe.probe_fast_line6(buf, len(buf), s, n, spans, ctypes.byref(sc), ctypes.byref(eflag), ends, hs)
+        ntotal += 1
+        if not ok:
+            continue
+        naccept += 1
+        gsp = (ctypes.c_int * 4)(); gsc = ctypes.c_float(); gnc = ctypes.c_int(); gef = ctypes.c_int()
+        fl = probe.probe_line(ln.encode(), len(ln), gsp, ctypes.byref(gsc), ctypes.byref(gnc), ctypes.byref(gef))
+        assert fl == 0 and gnc.value == 12, ln
+        assert [x - pad for x in spans] == list(gsp), ln
+        assert f32bits(sc.value) == f32bits(gsc.value), ln
+        assert eflag.value == gef.value, ln
+        # and against glibc itself
+        q = ctypes.create_string_buffer(256); sb = ctypes.create_string_buffer(256)
+        gs = ctypes.c_float(); ge = ctypes.c_double(); ints = (ctypes.c_int * 7)()
+        assert probe.probe_line_glibc(ln.encode(), q, sb, ctypes.byref(gs), ctypes.byref(ge), ints) == 12, ln
+        assert f32bits(gs.value) == f32bits(sc.value) and (1 if ge.value < 1e-10 else 0) == eflag.value, ln
+        for k in (0, 1):
+            nm = ln[gsp[2 * k]:gsp[2 * k + 1]]
+            if "|" in nm:
+                continue
+            b = probe.probe_strip(nm.encode(), len(nm))
+            assert ends[k] - pad - gsp[2 * k] == b, (ln, k)
+            off = np.array([0, b], dtype=np.uint32); out = np.zeros(1, dtype=np.uint32)
+            probe.probe_slot_hash_many(nm[:b].encode() or b"\0", off.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(1),
+                                       out.ctypes.data_as(ctypes.c_void_p))
+            assert hs[k] == int(out[0]), (ln, k)
+    assert naccept > 0.35 * ntotal, (naccept, ntotal)
+    # the shapes the aligners write must ALL take this route (LAST / BLAST+ tab12: %.2f pctid, %.1e / %.0e / 0.0 evalues,
+    # integer or one-decimal scores)
+    for it in range(3000):
+        x = float(10 ** rng.uniform(-250, -1))
+        ev = ["%.1e" % x, "%.0e" % x, "0.0", "%.2e" % x][it % 4]
+        scv = float(10 ** rng.uniform(1, 4.5))
+        f = ["Ag%06d.%d" % (rng.integers(0, 10 ** 6), rng.integers(1, 4)), "Bg%06d" % rng.integers(0, 10 ** 6), "%.2f" % rng.uniform(20, 100)]
+        f += [str(int(rng.integers(1, 5000))) for _ in range(7)] + [ev, ["%.1f" % scv, "%d" % scv][it % 2]]
+        ln = "\t".join(f)
+        pad = it % 37
+        raw = (b"x" * pad) + ln.encode()
+        buf = raw + b"\n" + b"Zq9\tnext\t1.0\t" * 3
+        spans = (ctypes.c_int * 4)(); sc = ctypes.c_float(); eflag = ctypes.c_int()
+        ends = (ctypes.c_int * 2)(); hs = (ctypes.c_uint * 2)()
+        assert probe.probe_fast_line6(buf, len(buf), pad, len(raw), spans, ctypes.byref(sc), ctypes.byref(eflag), ends, hs) == 1, ln
+        assert f32bits(sc.value) == f32bits(np.float32(f[11])), ln
+        assert eflag.value == (1 if float(ev) < 1e-10 else 0), ln
+
+
+def test_name_table_build_is_perfect_and_compact(probe):
+    """jx_bed_load's host build (jx_nametable.h) with the multiply-add name hash: every name is found by the lookup the
+    kernels do, the table has the minimum power-of-two size for load <= 0.5, equal 32-bit hashes stay at the birthday rate."""
+    import math
+    rng = np.random.default_rng(5)
+    sets = [[b"Ag%06d" % i for i in range(40000)], [b"AT%dG%05d" % (c, i * 10) for c in range(1, 6) for i in range(7000)],
+            [b"evm.model.scaffold_%d.%d" % (c, i) for c in range(1, 200) for i in range(150)],
+            list({bytes(rng.integers(97, 123, size=rng.integers(1, 40)).astype(np.uint8)) for _ in range(60000)})]
+    probe.probe_build_table.restype = ctypes.c_long
+    for names in sets:
+        blob = b"".join(names)
+        off = np.zeros(len(names) + 1, dtype=np.uint32)
+        np.cumsum([len(x) for x in names], out=off[1:])
+        out = (ctypes.c_long * 4)()
+        missing = probe.probe_build_table(blob, off.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(names)), out)
+        assert missing == 0
+        assert out[0] == math.ceil(math.log2(2 * len(names) + 2)), list(out)
+        assert out[2] <= 3 + len(names) ** 2 // 2 ** 31, list(out)

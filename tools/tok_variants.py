@@ -29,8 +29,11 @@ def child(hits):
     for it in range(8):
         if it == 3:
             eng.tokenizer_timing(reset=True)
-        r = eng.blastfilter(dev, want_text=False, raw=True, skip_arrays=True)
-        eng.free_filter(r)
+        try:
+            r = eng.blastfilter(dev, want_text=False, raw=True, skip_arrays=True)
+            eng.free_filter(r)
+        except ZeroDivisionError:          # experiment builds that skip the best-score table
+            pass
     ms, launches, nbytes, lines = eng.tokenizer_timing(reset=True)
     full = nbytes / 5 // (64 << 20)          # launches over a full 64 MiB chunk per pass
     print("RESULT lib=%s ms_total_per_pass=%.4f launches_per_pass=%d MBps=%.1f ms_per_64MiB=%.4f" % (
