@@ -46,6 +46,7 @@ int jx_ctx_create(int device, jx_ctx** out) {
   ctx->device = device;
   ctx->trace = getenv("JX_TRACE") ? atoi(getenv("JX_TRACE")) : 0;
   ctx->tok_v5 = getenv("JX_TOK_V5") && atoi(getenv("JX_TOK_V5")) != 0;
+  ctx->tok_v6 = getenv("JX_TOK_V6") && atoi(getenv("JX_TOK_V6")) != 0;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;

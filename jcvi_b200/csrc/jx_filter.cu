@@ -189,7 +189,7 @@ __global__ void k_order_keys(const uint32_t* Fj, const uint4* C, const uint32_t*
 }
 
 __global__ void k_gather_out(const uint32_t* Fj, uint32_t n, const uint4* C, const uint32_t* Cidx, const int32_t* mq,
-                             const int32_t* ms, const uint64_t* desc, int64_t ntiles, int32_t* oq, int32_t* os,
+                             const int32_t* ms, const LineIndex li, int32_t* oq, int32_t* os,
                              float* oscore, uint64_t* ooff) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -198,14 +198,7 @@ __global__ void k_gather_out(const uint32_t* Fj, uint32_t n, const uint4* C, con
   oq[t] = mq ? mq[r.x] : (int32_t)r.x;
   os[t] = ms ? ms[r.y] : (int32_t)r.y;
   oscore[t] = __uint_as_float(r.z);
-  // tile of line i: first tile whose inclusive line count exceeds i
-  const uint64_t i = Cidx[j];
-  int64_t lo = 0, hi = ntiles - 1;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((desc[mid] & ((1ull << 62) - 1)) > i) hi = mid; else lo = mid + 1;
-  }
-  ooff[t] = (uint64_t)lo * JX_TILE + (r.w >> 1);
+  ooff[t] = jx_line_offset(li, Cidx[j], r.w);
 }
 
 __global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, const uint32_t* idx, uint32_t cnt, uint32_t* len,
@@ -362,20 +355,15 @@ __global__ void k_compact_idx(const uint32_t* flags, const uint32_t* pos, uint32
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && flags[i]) idx[pos[i]] = i;
 }
-__global__ void k_line_off(const uint32_t* idx, uint32_t cnt, const uint4* recs, const uint64_t* desc, int64_t ntiles, uint64_t* off) {
+__global__ void k_line_off(const uint32_t* idx, uint32_t cnt, const uint4* recs, const LineIndex li, uint64_t* off) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt) return;
   const uint64_t i = idx[t];
-  int64_t lo = 0, hi = ntiles - 1;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((desc[mid] & ((1ull << 62) - 1)) > i) hi = mid; else lo = mid + 1;
-  }
-  off[t] = (uint64_t)lo * JX_TILE + (recs[i].w >> 1);
+  off[t] = jx_line_offset(li, i, recs[i].w);
 }
 }  // namespace
 
-int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
+int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const LineIndex& li,
                     const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip, uint64_t* dev_out) {
   if (out) *out = nullptr;
   *out_len = 0;
@@ -385,7 +373,7 @@ int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nb
   JX_ALLOC(off, uint64_t, cnt, false);
   JX_ALLOC(len, uint32_t, cnt, false);
   JX_ALLOC(pos, uint64_t, cnt, false);
-  JX_LAUNCH(k_line_off, nblk(cnt), 256, 0, rec_idx, cnt, recs, desc, ntiles, off);
+  JX_LAUNCH(k_line_off, nblk(cnt), 256, 0, rec_idx, cnt, recs, li, off);
   JX_LAUNCH(k_line_len, nblk(cnt), 256, 0, d_text, nbytes, off, (const uint32_t*)nullptr, cnt, len, rstrip);
   // byte positions are 64-bit: the packed lines of a big slice may exceed 4 GiB (C-score filter off)
   if ((rc = jx_exclusive_sum64(ctx, arena, len, pos, cnt))) return rc;
@@ -496,7 +484,8 @@ static int cscore_finish_impl(jx_ctx* ctx, double cscore, char** lines, int64_t*
     if (cnt) JX_LAUNCH(k_compact_idx, nblk(n), 256, 0, flags, pos, n, ix);
     idx = ix;
   }
-  rc = jx_gather_lines(ctx, arena, c.text, c.nbytes, c.desc, c.ntiles, c.recs, idx, cnt, lines, lines_len, 0, dev_out);
+  LineIndex li; li.desc = c.desc; li.ntiles = c.ntiles; li.cap = c.cap; li.sub_bytes = c.sub_bytes;
+  rc = jx_gather_lines(ctx, arena, c.text, c.nbytes, li, c.recs, idx, cnt, lines, lines_len, 0, dev_out);
   if (rc) return rc;
   *n_lines = cnt;
   ctx->sess_open = false;
@@ -677,7 +666,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
     JX_ALLOC(os, int32_t, nF, false);
     JX_ALLOC(osc, float, nF, false);
     JX_ALLOC(ooff, uint64_t, nF, false);
-    JX_LAUNCH(k_gather_out, nblk(nF), 256, 0, ov, nF, C, Cidx, d_mq, d_ms, tok.desc, tok.ntiles, oq, os, osc, ooff);
+    JX_LAUNCH(k_gather_out, nblk(nF), 256, 0, ov, nF, C, Cidx, d_mq, d_ms, tok.li, oq, os, osc, ooff);
     if (host_arrays) {
       JX_CK(cudaMemcpyAsync(out->q_rank, oq, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
       JX_CK(cudaMemcpyAsync(out->s_rank, os, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -71,13 +71,15 @@ struct jx_ctx {
   size_t ws_cap = 0, ws_used = 0, ws_virtual = 0, ws_need = 0;
   int ws_depth = 0;
   int64_t tok_resident = 0;      // persistent tokenizer CTAs that fit on this device at once
-  bool tok_v5 = false;           // JX_TOK_V5=1: run the path through the version-5 kernel (A/B measurements)
+  bool tok_v5 = false, tok_v6 = false;   // JX_TOK_V5=1 / JX_TOK_V6=1: run the path through an older kernel (A/B measurements)
+  uint32_t tok_cap = 64;         // version-7 kernel: record slots per sub-tile that fitted the last text (sticky guess)
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
   // records of the last jx_blastfilter pass over the held text, for jx_liftover_text
   struct RecCache {
     uint4* recs = nullptr; size_t recs_cap = 0;       // context-owned, grow-only
     uint64_t* desc = nullptr; size_t desc_cap = 0;
+    uint32_t cap = 0, sub_bytes = 0;                  // record slot layout (see LineIndex)
     bool valid = false;
     bool plain = false;       // records of a non-self pass without exclusions or the near-diagonal rule: any stage may reuse them
     const uint8_t* text = nullptr; int64_t nbytes = 0; int strip = 0;
@@ -258,8 +260,28 @@ struct TokMode {
   bool f_noself = false, f_inverse = false, f_ids = false;
   uint32_t seed = 0;           // of that hash
 };
+// How a record's index maps to its line's byte offset.  Version-7 records live in fixed slots (`cap` per sub-tile of
+// `sub_bytes` bytes): offset = index / cap * sub_bytes + (rec.w >> 1).  cap == 0: dense line ordinals, the per-tile
+// inclusive line counts (`desc`, tiles of JX_TILE bytes) are searched.
+struct LineIndex {
+  const uint64_t* desc = nullptr;
+  int64_t ntiles = 0;
+  uint32_t cap = 0, sub_bytes = 0;
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t jx_line_offset(const LineIndex& L, uint64_t i, uint32_t w) {
+  if (L.cap) return (i / L.cap) * (uint64_t)L.sub_bytes + (w >> 1);
+  int64_t lo = 0, hi = L.ntiles - 1;              // tile of line i: first tile whose inclusive line count exceeds i
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((L.desc[mid] & ((1ull << 62) - 1)) > i) hi = mid; else lo = mid + 1;
+  }
+  return (uint64_t)lo * JX_TILE + (w >> 1);
+}
+#endif
 struct TokOut {
-  uint4* recs = nullptr;       // [n_lines]
+  LineIndex li;
+  uint4* recs = nullptr;       // [n_lines] (n_lines = record SLOTS: lines, or sub-tiles x cap with "no record" fillers)
   uint4* hashes = nullptr;     // [n_lines] names mode: {hq.lo, hq.hi, hs.lo, hs.hi}, 0 = no name
   uint64_t* desc = nullptr;    // per tile: (2 << 62) | inclusive line count
   int64_t ntiles = 0;
@@ -274,7 +296,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
                      const TokMode& mode, TokOut& out);
 
 // raw text lines of the records rec_idx[0..cnt) (device array, file order) -> malloc'ed host buffer
-int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const uint64_t* desc, int64_t ntiles,
+int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const LineIndex& li,
                     const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip = 0,
                     uint64_t* dev_out = nullptr);   // dev_out: leave the packed lines in ctx->lines_dev instead (no host copy)
 

@@ -776,6 +776,7 @@ static int near_lines_impl(jx_ctx* ctx, const char* text, int64_t nbytes, int te
     if (c.valid && c.plain && text_on_device && (const uint8_t*)text == c.text && nbytes == c.nbytes &&
         (strip_names != 0) == (c.strip != 0) && !ctx->is_self) {
       tok.recs = c.recs; tok.desc = c.desc; tok.ntiles = c.ntiles; tok.n_lines = c.n_lines; tok.d_text = c.text; tok.nbytes = c.nbytes;
+      tok.li.desc = c.desc; tok.li.ntiles = c.ntiles; tok.li.cap = c.cap; tok.li.sub_bytes = c.sub_bytes;
       memcpy(tok.stats, c.stats, sizeof tok.stats);
       c.valid = false;
     } else {
@@ -828,7 +829,7 @@ static int near_lines_impl(jx_ctx* ctx, const char* text, int64_t nbytes, int te
     if ((rc = jx_sort_keys(ctx, arena, ks, nC, 0, 32))) return rc;
     JX_LAUNCH(k_narrow_idx, nblk(nC), 256, 0, ks, nC, idx);
   }
-  if ((rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, idx, nC, lines, lines_len, 0, dev_out))) return rc;
+  if ((rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.li, tok.recs, idx, nC, lines, lines_len, 0, dev_out))) return rc;
   *n_out = nC;
   return JX_OK;
 }

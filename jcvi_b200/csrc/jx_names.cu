@@ -156,7 +156,7 @@ int jx_distinct_names(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on
   JX_ALLOC(rep_side, uint8_t, g, false);
   JX_LAUNCH(k_take_reps, nblk(m), 256, 0, vs, flag, pos, m, rep_line, rep_side);
   JX_CK(cudaMemcpyAsync(*side, rep_side, g, cudaMemcpyDeviceToHost, ctx->stream));
-  rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.desc, tok.ntiles, tok.recs, rep_line, g, lines, lines_len);
+  rc = jx_gather_lines(ctx, arena, tok.d_text, tok.nbytes, tok.li, tok.recs, rep_line, g, lines, lines_len);
   JX_CK(cudaStreamSynchronize(ctx->stream));
   return rc;
 }

@@ -64,8 +64,9 @@ struct WinReader {             // byte view: shared-memory window, global memory
   const uint8_t* sm;
   const uint8_t* g;
   int64_t base, n;
+  int win = JX_WIN;            // bytes of the window
   __device__ __forceinline__ uint32_t operator()(int p) const {
-    if (p < JX_WIN) return sm[p];
+    if (p < win) return sm[p];
     int64_t gp = base + p;
     return gp < n ? g[gp] : (uint32_t)'\n';
   }
@@ -694,7 +695,7 @@ __device__ __forceinline__ uint32_t bar_in(uint32_t w) {
 // The version-5 route for ONE line of a staged tile: fast_line5 on the masks, else the generic scanner; names through
 // the byte-reader table lookup when they are long.  Mirrors the per-line body of k_tokenize<0> above.
 __device__ __noinline__ SlowOut slow_line(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
-                                          const int64_t base, const int s, const int e) {
+                                          const int64_t base, const int s, const int e, const int win) {
   SlowOut o;
   o.rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
   o.what = WH_NONE;
@@ -706,14 +707,14 @@ __device__ __noinline__ SlowOut slow_line(const TokArgs& a, const uint8_t* sm, c
     if (!(prev == '\r' && sm[s] == '\n')) o.what = WH_UNMAPPED;
     return o;
   }
-  WinReader rd{sm, a.text, base, a.n};
+  WinReader rd{sm, a.text, base, a.n, win};
   const SmemWords wr{smw};
   const MaskWords mwr{s_w}, mnr{s_n};
   const SmemText B{sm, smw};
   const SideTab TQ{a.qtab, a.qdisp, a.qbshift, a.qcshift, a.qmeta, a.qblob, a.qovh, a.qovr, a.qnov};
   const SideTab TS{a.stab, a.sdisp, a.sbshift, a.scshift, a.smeta, a.sblob, a.sovh, a.sovr, a.snov};
   jx::LineTok t;
-  const bool fast = (e + 8 <= JX_WIN) && jx::fast_line5(B, mwr, mnr, s, e, t);
+  const bool fast = (e + 8 <= win) && jx::fast_line5(B, mwr, mnr, s, e, t);
   if (!fast) jx::tokenize_line(rd, s, e, t);
   bool bad = false, selfhit = false;
   int qi = -1, si = -1;
@@ -1031,7 +1032,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize6(con
           }
         }
         if (!fastdone) {
-          const SlowOut so = slow_line(a, sm, s_w, s_n, base, s, e);
+          const SlowOut so = slow_line(a, sm, s_w, s_n, base, s, e, JX_WIN);
           rec = so.rec; what = so.what;
           if (what == WH_MAPPED) {
             if (a.n_excl) {
@@ -1112,6 +1113,398 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize6(con
   }
 }
 
+
+// =====================================================================================================================
+// Version 7 of the path's kernel: WARP-AUTONOMOUS sub-tiles, no CTA barrier and no cross-CTA chain.
+//
+// The version-6 profile (profiles/r2_k_tokenize6_*) showed the kernel bound by waiting, not by any pipe: 23 % of the
+// warp samples sat in CTA barriers (13 % of them behind warp 0's decoupled look-back), 25 % on the table loads.  Both
+// waits came from the tile organisation -- 128 threads share a tile, so every phase ends in a barrier, and records are
+// stored at dense line ordinals, so every tile needs the line counts of all its predecessors.  Here
+//   * one WARP owns a sub-tile: a 4 KiB window (32 lanes x 128 bytes) = 3840 bytes whose lines are the warp's + 256
+//     bytes of look-ahead; masks, line starts and the per-line parse only need __syncwarp;
+//   * records go to FIXED SLOTS: sub-tile t owns recs[t * cap, (t + 1) * cap) (cap >= its number of lines, the rest is
+//     filled with "no record"), so no warp ever needs another warp's count.  A record's index is still monotone in file
+//     order -- all the first-seen / stable-sort rules need -- and the line's byte offset follows from the index alone
+//     (index / cap * 3840 + offset inside the sub-tile): the per-tile descriptor chain is gone.  cap starts at 64
+//     (lines of >= 60 bytes on average) and grows by relaunch when a sub-tile overflows;
+//   * the windows arrive by bulk copy into a ring of W7_NBUF buffers per CTA: a warp that finishes a sub-tile re-arms
+//     its buffer for the CTA's position p + NBUF and takes the next position; there are always NBUF - 4 copies in flight.
+// Per-line work is version 6's (jx_fast6.cuh first, `slow_line` for everything it refuses).
+constexpr int W7_WIN = 4096;
+constexpr int W7_TILE = 3840;                       // = 30 lanes x 128 bytes = 16 x 240
+constexpr int W7_PRE = 16;                          // bytes staged in front of the window (the byte before it decides its first line start)
+constexpr int W7_STAGE = W7_PRE + W7_WIN + 32;      // + slack for unaligned word reads past the window
+#ifndef JX_W7_NBUF
+#define JX_W7_NBUF 5
+#endif
+constexpr int W7_NBUF = JX_W7_NBUF;
+constexpr int W7_LC = 126;                          // line starts of a window kept in shared memory (more: per-lane route)
+#ifndef JX_W7_MINBLK
+#define JX_W7_MINBLK 7     // 72 registers: 8 CTAs (64 registers) spill inside the per-line code and measure 7 % slower
+#endif
+
+// Per-warp counters live in shared memory: only lines that are NOT plain mapped records touch them (mapped = lines -
+// everything else), so the common case costs neither registers nor instructions.
+struct Counters7 {
+  uint32_t* cnt;                 // [WH_NONE + 1] of this warp
+  unsigned long long* stats;     // the launch's global statistics (first bad offset: atomicMin, rare)
+};
+
+// One line [s, e) of a staged window -> record (version 6's per-line body).  `tile_off` = offset stored in the record.
+__device__ __forceinline__ uint4 parse_line7(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
+                                             const int64_t base, const int s, const int e, const int win, const bool v6,
+                                             const Counters7& c) {
+  const uint32_t* smw = reinterpret_cast<const uint32_t*>(sm);
+  uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+  int what = WH_NONE;
+  bool fastdone = false;
+  const int len = e - s;
+  if (len > 0 && sm[s] == '#') {
+    what = WH_COMMENT; fastdone = true;
+  } else if (v6 && e + 8 <= win) {
+    const SmemWords wr{smw};
+    const MaskWords mwr{s_w}, mnr{s_n};
+    const SmemText B{sm, smw};
+    jx::Line6 L;
+    if (jx::fast_line6_names(mwr, mnr, s, len, L)) {
+      const int qa = s, sa = s + L.t0 + 1;
+      int lq = L.t0, lsn = L.t1 - L.t0 - 1;
+      const int iq = qa >> 2, is = sa >> 2;
+      const uint32_t shq = (uint32_t)(qa & 3) * 8u, shs = (uint32_t)(sa & 3) * 8u;
+      const uint32_t xq0 = smw[iq], xq1 = smw[iq + 1], xq2 = smw[iq + 2], xq3 = smw[iq + 3];
+      const uint32_t xs0 = smw[is], xs1 = smw[is + 1], xs2 = smw[is + 2], xs3 = smw[is + 3];
+      uint32_t q0 = __funnelshift_r(xq0, xq1, shq), q1 = __funnelshift_r(xq1, xq2, shq), q2 = __funnelshift_r(xq2, xq3, shq);
+      uint32_t s0 = __funnelshift_r(xs0, xs1, shs), s1 = __funnelshift_r(xs1, xs2, shs), s2 = __funnelshift_r(xs2, xs3, shs);
+      if (a.strip) { lq = jx::strip6(B, qa, lq, q0); lsn = jx::strip6(B, sa, lsn, s0); }
+      if (lq <= 12 && lsn <= 12 && lq >= 1 && lsn >= 1) {
+        q0 &= jx::name_mask(lq, 0); q1 &= jx::name_mask(lq, 1); q2 &= jx::name_mask(lq, 2);
+        s0 &= jx::name_mask(lsn, 0); s1 &= jx::name_mask(lsn, 1); s2 &= jx::name_mask(lsn, 2);
+        const uint32_t bar = a.strip ? (bar_in(q0) | bar_in(q1) | bar_in(q2) | bar_in(s0) | bar_in(s1) | bar_in(s2)) : 0u;
+        if (bar == 0u) {
+          uint32_t hq = jx::slot_hash_step(jx::slot_hash_init(), q0), hs = jx::slot_hash_step(jx::slot_hash_init(), s0);
+          if (lq > 4) hq = jx::slot_hash_step(hq, q1);
+          if (lsn > 4) hs = jx::slot_hash_step(hs, s1);
+          if (lq > 8) hq = jx::slot_hash_step(hq, q2);
+          if (lsn > 8) hs = jx::slot_hash_step(hs, s2);
+          hq = jx::slot_hash_finish(hq, (uint32_t)lq); hs = jx::slot_hash_finish(hs, (uint32_t)lsn);
+          // the table loads are issued HERE; the rest of the line is parsed while they are in flight
+          const uint32_t dq = __ldg(a.qdisp + (hq >> a.qbshift)), ds = __ldg(a.sdisp + (hs >> a.sbshift));
+          const uint4* pq = a.qtab + 2 * jx::slot_index(hq, dq, a.qcshift);
+          const uint4* ps = a.stab + 2 * jx::slot_index(hs, ds, a.scshift);
+          const uint4 tq0 = __ldg(pq), tq1 = __ldg(pq + 1), ts0 = __ldg(ps), ts1 = __ldg(ps + 1);
+          if (jx::fast_line6_rest(B, wr, mwr, mnr, s, len, L)) {
+            const uint32_t dfq = (tq0.z ^ q0) | (tq0.w ^ q1) | (tq1.x ^ q2) | tq1.y | tq1.z | tq1.w;
+            const uint32_t dfs = (ts0.z ^ s0) | (ts0.w ^ s1) | (ts1.x ^ s2) | ts1.y | ts1.z | ts1.w;
+            const bool okq = tq0.x != 0u && dfq == 0u, oks = ts0.x != 0u && dfs == 0u;
+            // a miss may be a name parked in an overflow list (names with equal 32-bit hashes): rare route
+            if ((okq && oks) || (a.qnov | a.snov) == 0u) {
+              fastdone = true;
+              if (!(okq && oks)) what = WH_UNMAPPED;
+              else {
+                const uint32_t qi = tq0.x - 1u, si = ts0.x - 1u;
+                bool keep = true;
+                if (a.n_excl) {
+                  const uint64_t key = ((uint64_t)qi << 32) | si;
+                  int64_t l = 0, h = a.n_excl;
+                  while (l < h) { const int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+                  if (l < a.n_excl && a.excl[l] == key) { keep = false; what = WH_EXCL; }
+                }
+                if (keep) {
+                  what = WH_MAPPED;
+                  const uint32_t sbits = __float_as_uint(L.score);
+                  rec = make_uint4(qi, si, sbits, ((uint32_t)s << 1) | (uint32_t)L.eflag);
+                  if (a.best && L.score > 0.f) {        // best_score[name] = max(score), starting at 0.0:
+                    atomicMax(a.best + tq0.y, sbits);   // two reductions (no return value, nothing to wait for)
+                    atomicMax(a.best + ts0.y, sbits);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!fastdone) {
+    const SlowOut so = slow_line(a, sm, s_w, s_n, base, s, e, win);
+    rec = so.rec; what = so.what;
+    if (what == WH_MAPPED) {
+      if (a.n_excl) {
+        const uint64_t key = ((uint64_t)rec.x << 32) | rec.y;
+        int64_t l = 0, h = a.n_excl;
+        while (l < h) { const int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+        if (l < a.n_excl && a.excl[l] == key) { what = WH_EXCL; rec.x = JX_NOREC; }
+      }
+      if (what == WH_MAPPED && a.best && __uint_as_float(rec.z) > 0.f) {
+        atomicMax(a.best + a.qnid[rec.x], rec.z);
+        atomicMax(a.best + a.snid[rec.y], rec.z);
+      }
+    }
+  }
+  if (what != WH_MAPPED) {
+    atomicAdd(c.cnt + what, 1u);
+    if (what == WH_HARD || what == WH_LONG) atomicMin(c.stats + 7, (unsigned long long)(base + s) + 1ull);
+  }
+  return rec;
+}
+
+// A window full of tiny lines (more line starts than the shared list holds): every lane walks the line starts of its
+// own 128-byte segment, ordinals from the warp prefix.  Rare; generic route only.
+__device__ __noinline__ void walk_tiny_lines(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
+                                             const int64_t base, const uint32_t st0, const uint32_t st1, const uint32_t st2,
+                                             const uint32_t st3, uint32_t k, const uint32_t cap, uint4* slots, Counters7 c) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t st[4] = {st0, st1, st2, st3};
+#pragma unroll 1
+  for (int h = 0; h < 4; ++h) {
+    uint32_t m = st[h];
+    while (m) {
+      const int s = lane * 128 + h * 32 + __ffs((int)m) - 1;
+      m &= m - 1u;
+      int e = s;
+      while (e < W7_WIN && !jx::is_term(sm[e])) ++e;
+      if (e >= W7_WIN) while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e;
+      SlowOut so;
+      if (e > s && sm[s] == '#') { so.rec = make_uint4(JX_NOREC, 0u, 0u, 0u); so.what = WH_COMMENT; }
+      else so = slow_line(a, sm, s_w, s_n, base, s, e, W7_WIN);
+      if (so.what == WH_MAPPED) {
+        if (a.n_excl) {
+          const uint64_t key = ((uint64_t)so.rec.x << 32) | so.rec.y;
+          int64_t l = 0, hh = a.n_excl;
+          while (l < hh) { const int64_t mm = (l + hh) >> 1; if (a.excl[mm] < key) l = mm + 1; else hh = mm; }
+          if (l < a.n_excl && a.excl[l] == key) { so.what = WH_EXCL; so.rec.x = JX_NOREC; }
+        }
+        if (so.what == WH_MAPPED && a.best && __uint_as_float(so.rec.z) > 0.f) {
+          atomicMax(a.best + a.qnid[so.rec.x], so.rec.z);
+          atomicMax(a.best + a.snid[so.rec.y], so.rec.z);
+        }
+      }
+      if (so.what != WH_MAPPED) {
+        atomicAdd(c.cnt + so.what, 1u);
+        if (so.what == WH_HARD || so.what == WH_LONG) atomicMin(c.stats + 7, (unsigned long long)(base + s) + 1ull);
+      }
+      if (k < cap) slots[k] = so.rec;
+      ++k;
+    }
+  }
+}
+
+// 32 bytes of 7-bit text -> one word of each mask (see classify64_ascii)
+__device__ __forceinline__ void classify32_ascii(const uint4& v0, const uint4& v1, uint32_t& wm, uint32_t& nm, uint32_t& any) {
+  const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  uint32_t pw[4], pn[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t a = x[2 * k], b = x[2 * k + 1];
+    any |= a | b;
+    const uint32_t twa = a + 0x5F5F5F5Fu, twb = b + 0x5F5F5F5Fu;
+    const uint32_t una = ((a ^ 0x30303030u) + 0x76767676u) & ((a ^ 0x09090909u) + 0x7F7F7F7Fu);
+    const uint32_t unb = ((b ^ 0x30303030u) + 0x76767676u) & ((b ^ 0x09090909u) + 0x7F7F7F7Fu);
+    pw[k] = (((~twa >> 4) & 0x08080808u) | (~twb & 0x80808080u)) * 0x00204081u;
+    pn[k] = (((una >> 4) & 0x08080808u) | (unb & 0x80808080u)) * 0x00204081u;
+  }
+  wm = jx::top_bytes(pw[0], pw[1], pw[2], pw[3]);
+  nm = jx::top_bytes(pn[0], pn[1], pn[2], pn[3]);
+}
+
+struct Tok7Args {
+  TokArgs t;
+  int64_t sub_begin, nsub; // this launch handles the sub-tiles [sub_begin, nsub)
+  uint32_t cap;            // record slots per sub-tile
+};
+
+__global__ void __launch_bounds__(JX_TOK_THREADS, JX_W7_MINBLK) k_tokenize7(const __grid_constant__ Tok7Args A) {
+  const TokArgs& a = A.t;
+  constexpr int NW = JX_TOK_THREADS / 32;
+  __shared__ __align__(128) uint8_t s_text[W7_NBUF][W7_STAGE];
+  __shared__ __align__(8) uint64_t s_bar[W7_NBUF];
+  __shared__ __align__(16) uint32_t s_wm[NW][W7_WIN / 32 + 4];   // byte <= 0x20 (+ slack: 64-bit windows read past the window)
+  __shared__ __align__(16) uint32_t s_nm[NW][W7_WIN / 32 + 4];   // byte is neither a digit nor a tab
+  __shared__ uint16_t s_lp[NW][W7_LC + 2];                       // start offset of every line of the window
+  __shared__ uint32_t s_cnt[NW][WH_NONE + 2];                    // per warp: lines that are not plain records, by kind; [WH_NONE + 1] = lines
+  __shared__ uint32_t s_head;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* const s_w = s_wm[warp];
+  uint32_t* const s_n = s_nm[warp];
+  uint16_t* const s_lpos = s_lp[warp];
+  const Counters7 c{s_cnt[warp], a.stats};
+  if (lane < WH_NONE + 2) s_cnt[warp][lane] = 0u;
+  bool overflow = false;
+  uint32_t maxlines = 0;
+  const bool v6 = !a.is_self;
+  const int64_t nsub = A.nsub;
+  const uint32_t cap = A.cap;
+
+  // sub-tile of the CTA's ring position p; the stage of a sub-tile: bytes [base - 16, base + WIN + 32) of the text
+  auto sub_of = [&](uint32_t p) -> int64_t { return A.sub_begin + (int64_t)blockIdx.x + (int64_t)p * gridDim.x; };
+  auto arm = [&](uint32_t p) {                      // one thread: start the copy of position p's window into its buffer
+    const int64_t sub = sub_of(p);
+    if (sub >= nsub) return;
+    const int b = (int)(p % W7_NBUF);
+    const int64_t base = sub * W7_TILE;
+    const int64_t src = base ? base - W7_PRE : 0;
+    const int64_t left = a.n - src;
+    const uint32_t want = base ? (uint32_t)W7_STAGE : (uint32_t)(W7_STAGE - W7_PRE);
+    const uint32_t bytes = (uint32_t)(left < (int64_t)want ? left : (int64_t)want) & ~15u;
+    if (bytes) {
+      mbar_expect_tx(&s_bar[b], bytes);
+      bulk_g2s(s_text[b] + (base ? 0 : W7_PRE), a.text + src, bytes, &s_bar[b]);
+    }
+  };
+  if (tid == 0) {
+    for (int b = 0; b < W7_NBUF; ++b) mbar_init(&s_bar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_head = 0;
+    for (uint32_t p = 0; p < (uint32_t)W7_NBUF; ++p) arm(p);
+  }
+  if (lane < 4) { s_w[W7_WIN / 32 + lane] = 0u; s_n[W7_WIN / 32 + lane] = 0u; }
+  __syncthreads();                                  // the only CTA barrier of the kernel
+
+  for (;;) {
+    uint32_t p = 0;
+    if (lane == 0) p = atomicAdd(&s_head, 1u);
+    p = __shfl_sync(0xFFFFFFFFu, p, 0);
+    const int64_t sub = sub_of(p);
+    if (sub >= nsub) break;
+    const int b = (int)(p % W7_NBUF);
+    const uint32_t parity = (p / W7_NBUF) & 1u;
+    const int64_t base = sub * W7_TILE;
+    uint8_t* const stage = s_text[b];
+    const uint8_t* const sm = stage + W7_PRE;
+    // ---- the window: wait for the bulk copy; '\n' beyond the end of the text -------------------------------------------
+    const int64_t src = base ? base - W7_PRE : 0;
+    const int64_t left = a.n - src;
+    const uint32_t want = base ? (uint32_t)W7_STAGE : (uint32_t)(W7_STAGE - W7_PRE);
+    const bool full = left >= (int64_t)want;
+    {
+      const uint32_t avail = (uint32_t)(full ? (int64_t)want : left), bulk = avail & ~15u;
+      if (bulk) {
+        while (!mbar_try_wait(&s_bar[b], parity)) {}
+      }
+      if (!full) {                                  // last windows of the text only
+        uint8_t* dst = stage + (base ? 0 : W7_PRE);
+        for (uint32_t i = bulk + lane; i < want; i += 32) dst[i] = i < avail ? a.text[src + i] : (uint8_t)'\n';
+        __syncwarp();
+      }
+    }
+    // ---- byte classes: lane handles the 32-byte pieces lane, lane + 32, lane + 64, lane + 96 --------------------------
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4* p4 = reinterpret_cast<const uint4*>(sm + 32 * (lane + 32 * j));
+      const uint4 v0 = p4[0], v1 = p4[1];
+      uint32_t wm, nm;
+      classify32_ascii(v0, v1, wm, nm, any);
+      s_w[lane + 32 * j] = wm;
+      s_n[lane + 32 * j] = nm;
+    }
+    if (__any_sync(0xFFFFFFFFu, (any & 0x80808080u) != 0u)) {   // a byte >= 0x80 in the window: exact classifier
+      uint32_t hiacc = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(sm + 32 * (lane + 32 * j));
+        const uint4 v0 = p4[0], v1 = p4[1];
+        const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t wm, nm;
+        jx::classify32(w8, wm, nm, hiacc);
+        s_w[lane + 32 * j] = wm;
+        s_n[lane + 32 * j] = nm;
+      }
+    }
+    __syncwarp();
+    // ---- terminators and line starts of this lane's 128-byte segment ----------------------------------------------------
+    const uint4 W4 = reinterpret_cast<const uint4*>(s_w)[lane], N4 = reinterpret_cast<const uint4*>(s_n)[lane];
+    const uint32_t wv[4] = {W4.x, W4.y, W4.z, W4.w}, nv[4] = {N4.x, N4.y, N4.z, N4.w};
+    uint32_t term[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint32_t cnd = wv[h] & nv[h], tm = 0;       // a terminator is a byte <= 0x20 that is not a tab: checked by value
+      while (cnd) {
+        const int bit = __ffs((int)cnd) - 1;
+        cnd &= cnd - 1u;
+        const uint32_t ch = sm[lane * 128 + h * 32 + bit];
+        if (ch == '\n' || ch == '\r') tm |= 1u << bit;
+      }
+      term[h] = tm;
+    }
+    uint32_t prevbit = __shfl_up_sync(0xFFFFFFFFu, term[3] >> 31, 1);
+    if (lane == 0) prevbit = base == 0 ? 1u : (uint32_t)jx::is_term(sm[-1]);
+    uint32_t st[4];
+    st[0] = (term[0] << 1) | prevbit;
+    st[1] = (term[1] << 1) | (term[0] >> 31);
+    st[2] = (term[2] << 1) | (term[1] >> 31);
+    st[3] = (term[3] << 1) | (term[2] >> 31);
+    if (!full) {                                    // only positions that exist can start a line
+      const int64_t remain = a.n - (base + (int64_t)lane * 128);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int64_t r = remain - 32 * h;
+        if (r <= 0) st[h] = 0u; else if (r < 32) st[h] &= (1u << r) - 1u;
+      }
+    }
+    const uint32_t cnt = __popc(st[0]) + __popc(st[1]) + __popc(st[2]) + __popc(st[3]);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);                 // starts in the whole window
+    const uint32_t nlines = __shfl_sync(0xFFFFFFFFu, inc, W7_TILE / 128 - 1); // ... in the sub-tile: this warp's lines
+    const uint32_t pref = inc - cnt;
+    if (nlines > cap) overflow = true;
+    maxlines = max(maxlines, nlines);
+    uint4* const slots = a.recs + (uint64_t)sub * cap;
+    const bool listed = total <= (uint32_t)W7_LC;  // (else a window full of tiny lines: every lane walks its own line starts)
+    if (listed) {
+      uint32_t o = pref;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t m = st[h];
+        const uint32_t p0 = (uint32_t)(lane * 128 + h * 32);
+        while (m) { s_lpos[o++] = (uint16_t)(p0 + __ffs((int)m) - 1); m &= m - 1u; }
+      }
+    }
+    __syncwarp();
+    if (listed) {
+      for (uint32_t k = lane; k < nlines; k += 32) {
+        const int s = s_lpos[k];
+        int e;
+        if (k + 1 < total) e = (int)s_lpos[k + 1] - 1;
+        else {                                        // no line start after this one inside the window: find the terminator
+          e = s;
+          while (e < W7_WIN && !jx::is_term(sm[e])) ++e;
+          if (e >= W7_WIN) while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e;
+        }
+        const uint4 rec = parse_line7(a, sm, s_w, s_n, base, s, e, W7_WIN, v6, c);
+        if (k < cap) slots[k] = rec;
+      }
+    } else if (lane < W7_TILE / 128) {
+      walk_tiny_lines(a, sm, s_w, s_n, base, st[0], st[1], st[2], st[3], pref, cap, slots, c);
+    }
+    for (uint32_t k = nlines + lane; k < cap; k += 32) slots[k] = make_uint4(JX_NOREC, 0u, 0u, 0u);
+    if (lane == 0) s_cnt[warp][WH_NONE + 1] += nlines;
+    __syncwarp();                                     // every lane is done with the window
+    if (lane == 0) arm(p + W7_NBUF);
+  }
+
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t* cw = s_cnt[warp];
+    const uint32_t lines = cw[WH_NONE + 1];
+    const uint32_t other = cw[WH_COMMENT] + cw[WH_UNMAPPED] + cw[WH_HARD] + cw[WH_LONG] + cw[WH_EXCL] + cw[WH_SELF] + cw[WH_NONE];
+    if (cw[WH_COMMENT]) atomicAdd(a.stats + 1, (unsigned long long)cw[WH_COMMENT]);
+    if (lines - other) atomicAdd(a.stats + 2, (unsigned long long)(lines - other));       // mapped = everything else
+    if (cw[WH_UNMAPPED]) atomicAdd(a.stats + 3, (unsigned long long)cw[WH_UNMAPPED]);
+    if (cw[WH_HARD]) atomicAdd(a.stats + 4, (unsigned long long)cw[WH_HARD]);
+    if (cw[WH_LONG]) atomicAdd(a.stats + 5, (unsigned long long)cw[WH_LONG]);
+    if (cw[WH_EXCL]) atomicAdd(a.stats + 8, (unsigned long long)cw[WH_EXCL]);
+    if (cw[WH_SELF]) atomicAdd(a.stats + 9, (unsigned long long)cw[WH_SELF]);
+    if (lines) atomicAdd(a.stats + 0, (unsigned long long)lines);
+  }
+  if (__any_sync(0xFFFFFFFFu, overflow) && lane == 0) atomicExch(a.stats + 6, 1ull);
+  if (lane == 0 && maxlines) atomicMax(a.stats + 11, (unsigned long long)maxlines);
+}
+
 }  // namespace
 
 int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes, int on_device,
@@ -1159,8 +1552,12 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
   JX_ALLOC(d_ticket, uint32_t, (size_t)nchunks + 2, true);   // one ticket counter per launch
   const bool to_cache = held && ((mode.fill_cache && !ctx->is_self && mode.n_excl == 0 && !mode.neardiag) || mode.persist);
   if (to_cache) ctx->cache.valid = false;    // about to overwrite the retained records
+  const bool use7 = !mode.names && !mode.filter && !ctx->tok_v5 && !ctx->tok_v6;   // the path's kernel: version 7 (fixed slots)
+  const int64_t nsub = (nbytes + W7_TILE - 1) / W7_TILE;
   uint64_t* d_desc = nullptr;
-  if (to_cache) {
+  if (use7) {
+    // no descriptor chain
+  } else if (to_cache) {
     if (ctx->cache.desc_cap < (size_t)ntiles + 1) {
       if (ctx->cache.desc) cudaFree(ctx->cache.desc);
       ctx->cache.desc = nullptr; ctx->cache.desc_cap = 0;
@@ -1174,11 +1571,14 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     d_desc = dd;
   }
   out.desc = d_desc;
+  out.li.desc = d_desc; out.li.ntiles = ntiles; out.li.cap = 0; out.li.sub_bytes = 0;
   const SideDev& Q = ctx->side[0];
   const SideDev& S = ctx->side[1];
+  uint32_t slot_cap = std::max<uint32_t>(ctx->tok_cap, 8u);     // version 7: record slots per sub-tile
   for (int attempt = 0; attempt < 2; ++attempt) {
     uint64_t cap64 = attempt == 0 ? (uint64_t)(nbytes / 20 + 1024) : (uint64_t)nbytes + 1;
-    if (cap64 > 0xFFFFFFF0ull) { ctx->err = "more than 2^32 lines in one text"; return JX_EARG; }
+    if (use7) cap64 = (uint64_t)std::max<int64_t>(nsub, 1) * slot_cap;
+    if (cap64 > 0xFFFFFFF0ull) { ctx->err = use7 ? "more than 2^32 record slots in one text" : "more than 2^32 lines in one text"; return JX_EARG; }
     uint4* recs = nullptr;
     if (to_cache) {
       if (ctx->cache.recs_cap < (size_t)cap64) {
@@ -1199,7 +1599,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     if (attempt) {
       JX_CK(cudaMemsetAsync(d_stats, 0, 12 * sizeof(unsigned long long), ctx->stream));
       JX_CK(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t) * ((size_t)nchunks + 2), ctx->stream));
-      JX_CK(cudaMemsetAsync(d_desc, 0, (size_t)ntiles * sizeof(uint64_t), ctx->stream));
+      if (d_desc) JX_CK(cudaMemsetAsync(d_desc, 0, (size_t)ntiles * sizeof(uint64_t), ctx->stream));
       if (mode.best) JX_CK(cudaMemsetAsync(mode.best, 0, (size_t)ctx->n_name_ids * sizeof(uint32_t), ctx->stream));
     }
     {
@@ -1227,7 +1627,8 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     if (!ctx->tok_resident) {
       int per_sm = 0, n_sm = 0;
       if (ctx->tok_v5) JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<0>, JX_TOK_THREADS, 0));
-      else JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize6, JX_TOK_THREADS, 0));
+      else if (ctx->tok_v6) JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize6, JX_TOK_THREADS, 0));
+      else JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize7, JX_TOK_THREADS, 0));
       JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->tok_resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
     }
@@ -1241,12 +1642,19 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
 #else
     const int64_t launch_tiles = pending ? tiles_per_chunk : std::max<int64_t>(ntiles, 1);
 #endif
-    const int64_t nlaunch = (ntiles + launch_tiles - 1) / launch_tiles;
+    // (version 7 counts in sub-tiles; 64 MiB is not a multiple of 3840 bytes, so a launch's last window may start in the
+    //  next chunk's first bytes: the launch waits for that copy as well, see below)
+    const int64_t units = use7 ? nsub : ntiles;
+    const int64_t units_per_chunk = use7 ? (CHUNK + W7_TILE - 1) / W7_TILE : tiles_per_chunk;
+    const int64_t launch_units = pending ? units_per_chunk : std::max<int64_t>(units, 1);
+    const int64_t nlaunch = use7 ? (units + launch_units - 1) / launch_units : (ntiles + launch_tiles - 1) / launch_tiles;
     for (int64_t c = 0; c < nlaunch; ++c) {
-      int64_t t0 = c * launch_tiles, t1 = std::min(ntiles, t0 + launch_tiles);
+      int64_t t0 = c * (use7 ? launch_units : launch_tiles), t1 = std::min(use7 ? nsub : ntiles, t0 + (use7 ? launch_units : launch_tiles));
       if (pending) {
         // a tile's look-ahead may reach into the next chunk: wait for that copy too
-        JX_CK(cudaStreamWaitEvent(ctx->stream, copied[(size_t)std::min(c + 1, nchunks - 1)], 0));
+        int64_t last_chunk = c + 1;
+        if (use7) last_chunk = (std::min<int64_t>(t1 * W7_TILE + W7_WIN + 64, nbytes) - 1) / CHUNK;
+        JX_CK(cudaStreamWaitEvent(ctx->stream, copied[(size_t)std::min(last_chunk, nchunks - 1)], 0));
       }
       cudaEvent_t e0, e1;
       JX_CK(cudaEventCreate(&e0));
@@ -1256,7 +1664,11 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       if (mode.filter) JX_LAUNCH(k_tokenize<2>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       else if (mode.names) JX_LAUNCH(k_tokenize<1>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       else if (ctx->tok_v5) JX_LAUNCH(k_tokenize<0>, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
-      else JX_LAUNCH(k_tokenize6, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else if (ctx->tok_v6) JX_LAUNCH(k_tokenize6, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
+      else {
+        Tok7Args a7; a7.t = a; a7.nsub = t1; a7.sub_begin = t0; a7.cap = slot_cap;
+        JX_LAUNCH(k_tokenize7, (unsigned)std::min<int64_t>((t1 - t0 + 3) / 4, resident), JX_TOK_THREADS, 0, a7);
+      }
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
     }
@@ -1266,23 +1678,32 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     JX_CK(cudaMemcpyAsync(out.stats, d_stats, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaStreamSynchronize(ctx->stream));
     jx_harvest_tok_events(ctx);
+    if (use7) {
+      // stats[11] = the largest number of lines of any sub-tile: the next text (and the retry, when this one did
+      // not fit) gets that many slots plus an eighth
+      const uint32_t maxl = (uint32_t)out.stats[11];
+      const uint32_t want = std::min<uint32_t>(std::max<uint32_t>(((maxl + maxl / 8 + 2 + 7) / 8) * 8, 16u), (uint32_t)W7_TILE);
+      if (!out.stats[6]) {
+        out.li.desc = nullptr; out.li.ntiles = 0; out.li.cap = slot_cap; out.li.sub_bytes = (uint32_t)W7_TILE;
+        ctx->tok_cap = want;
+        break;
+      }
+      if (attempt == 1) { ctx->err = "record slots overflow"; return JX_EINTERNAL; }
+      slot_cap = std::max(want, maxl);
+      continue;
+    }
     if (!out.stats[6]) break;
     if (attempt == 1) { ctx->err = "record buffer overflow"; return JX_EINTERNAL; }
   }
   if (!held) for (cudaEvent_t ev : copied) cudaEventDestroy(ev);
-  out.n_lines = (uint32_t)out.stats[0];
+  out.n_lines = use7 ? (uint32_t)((uint64_t)std::max<int64_t>(nsub, 0) * slot_cap) : (uint32_t)out.stats[0];
   ctx->tok_lines += (int64_t)out.stats[0];
-  if (to_cache && !out.stats[4] && !out.stats[5] && !out.stats[10] && !out.stats[11]) {
+  if (to_cache && !out.stats[4] && !out.stats[5] && !out.stats[10]) {
     auto& c = ctx->cache;
-    c.valid = true; c.plain = !ctx->is_self && mode.n_excl == 0 && !mode.neardiag; c.text = d_text; c.nbytes = nbytes; c.strip = mode.strip; c.ntiles = ntiles; c.n_lines = out.n_lines;
+    c.valid = true; c.plain = !ctx->is_self && mode.n_excl == 0 && !mode.neardiag; c.text = d_text; c.nbytes = nbytes; c.strip = mode.strip; c.ntiles = ntiles; c.n_lines = out.n_lines; c.cap = out.li.cap; c.sub_bytes = out.li.sub_bytes;
     memcpy(c.stats, out.stats, sizeof c.stats);
   }
   if (out.stats[10]) { ctx->err = "tokenizer look-back timed out"; return JX_EINTERNAL; }
-  if (out.stats[11]) {
-    ctx->err = "the text contains '\\r' line terminators that are not followed by '\\n' (classic Mac line endings); "
-               "not supported";
-    return JX_EUNSUPPORTED;
-  }
   if (out.stats[5]) {
     ctx->err = "BLAST name of 128+ bytes near byte offset " + std::to_string(out.stats[7] - 1) +
                " (overflows cblast.pyx's char[128]; undefined behaviour in the reference)";
