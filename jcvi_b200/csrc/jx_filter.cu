@@ -35,7 +35,7 @@ __global__ void k_gene_best(const uint32_t* __restrict__ best, const uint32_t* _
 #endif
 __global__ void __launch_bounds__(256, JX_SEL_MINB) k_select(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bestq,
                          const uint32_t* __restrict__ bests, double cscore,
-                         int use_cscore, uint4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* counter,
+                         int use_cscore, uint32_t ord_base, uint4* __restrict__ out, uint32_t* counter,
                          uint32_t* errflag) {
 #ifndef JX_SEL_U
 #define JX_SEL_U 4
@@ -80,69 +80,151 @@ __global__ void __launch_bounds__(256, JX_SEL_MINB) k_select(const uint4* __rest
     block_append_multi<U>(keep, counter, slot, s_cnt);
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (keep[u]) { out[slot[u]] = r[u]; out_idx[slot[u]] = i0 + u * 32u + lane; }
+      if (keep[u]) {     // candidate: ranks, score, (order << 1) | (evalue < 1e-10); order = record index = file order
+        uint4 c = r[u];
+        c.w = ((ord_base + i0 + u * 32u + lane) << 1) | (c.w & 1u);
+        out[slot[u]] = c;
+      }
   }
 }
 
-__global__ void k_make_keys(const uint4* __restrict__ C, uint32_t n, int sb, uint64_t* keys, uint32_t* vals) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uint4 r = C[j];
-  keys[j] = ((uint64_t)r.x << sb) | r.y;
-  vals[j] = j;
+// ---- K3 / K7: per-pair best record through a hash table --------------------------------------------------------
+// The reference keeps, per (query, subject), the first record of a stable score-descending sort (blastfilter.py:49,
+// 86-89; again at 250-258 after the tandem substitution) = the record with the highest score and, among equals, the
+// lowest line.  That is one 64-bit atomicMax per candidate -- value = (ordered score bits << 32) | ~order -- into an
+// open-addressing table keyed by (qi << 32 | si): no sort, no run walk, and the table doubles as the pair SET the
+// tandem pass probes.  `order` = the candidate's record index (file order); candidates come in any order.
+#define JX_HEMPTY 0xFFFFFFFFFFFFFFFFull
+__device__ __forceinline__ uint32_t pair_hash(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ b * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+  return h;
 }
-
-// per run of equal keys: pick the preferred record. mode 0: (score desc, line asc); mode 1: line asc
-__global__ void k_run_best(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                           const uint4* __restrict__ C, const uint32_t* __restrict__ Cidx, uint32_t n, int mode,
-                           uint32_t* flag, uint32_t* pick) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const uint64_t k = keys[t];
-  const bool head = (t == 0) || keys[t - 1] != k;
-  flag[t] = head;
-  if (!head) return;
-  uint32_t bj = vals[t];
-  uint32_t bs = mode == 0 ? score_ord(C[bj].z) : 0u, bi = Cidx[bj];
-  for (uint32_t u = t + 1; u < n && keys[u] == k; ++u) {
-    uint32_t j = vals[u];
-    uint32_t s = mode == 0 ? score_ord(C[j].z) : 0u, i = Cidx[j];
-    if (s > bs || (s == bs && i < bi)) { bj = j; bs = s; bi = i; }
+__device__ __forceinline__ unsigned long long cand_value(const uint4& c) {   // higher = better: score, then earlier line
+  return ((unsigned long long)score_ord(c.z) << 32) | (0xFFFFFFFFu - (c.w >> 1));
+}
+// find-or-insert; returns the slot
+__device__ __forceinline__ uint32_t hash_slot_insert(unsigned long long* K, uint32_t mask, uint32_t a, uint32_t b) {
+  const unsigned long long key = ((unsigned long long)a << 32) | b;
+  uint32_t slot = pair_hash(a, b) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(K + slot, JX_HEMPTY, key);
+    if (prev == JX_HEMPTY || prev == key) return slot;
+    slot = (slot + 1u) & mask;
   }
-  pick[t] = bj;
 }
-
-__global__ void k_scatter_pairs(const uint64_t* keys, const uint32_t* vals, const uint32_t* flag, const uint32_t* pos,
-                                uint32_t n, uint64_t* okeys, uint32_t* ovals) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n || !flag[t]) return;
-  okeys[pos[t]] = keys[t];
-  if (ovals) ovals[pos[t]] = vals[t];
+__device__ __forceinline__ int64_t hash_slot_find(const unsigned long long* K, uint32_t mask, uint32_t a, uint32_t b) {
+  const unsigned long long key = ((unsigned long long)a << 32) | b;
+  uint32_t slot = pair_hash(a, b) & mask;
+  for (;;) {
+    const unsigned long long k = K[slot];
+    if (k == key) return slot;
+    if (k == JX_HEMPTY) return -1;
+    slot = (slot + 1u) & mask;
+  }
 }
-
-__global__ void k_eflags(const uint32_t* Kj, const uint4* C, uint32_t n, uint32_t* flag) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) flag[t] = C[Kj[t]].w & 1u;
+// candidates C[0 .. *n): insert (max value per pair); Cslot[j] = the pair's slot
+__global__ void k_pair_insert(const uint4* __restrict__ C, const uint32_t* __restrict__ n, const uint8_t* __restrict__ live,
+                              unsigned long long* K, unsigned long long* V, uint32_t mask, uint32_t* Cslot) {
+  const uint32_t N = *n;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    if (live && !live[j]) continue;
+    const uint4 c = C[j];
+    const uint32_t slot = hash_slot_insert(K, mask, c.x, c.y);
+    atomicMax(V + slot, cand_value(c));
+    Cslot[j] = slot;
+  }
 }
-
-__global__ void k_swap_keys(const uint64_t* in, uint32_t n, int sb, int qb, uint64_t* out) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  uint64_t k = in[t];
-  uint64_t qi = k >> sb, si = k & ((1ull << sb) - 1);
-  out[t] = (si << qb) | qi;
+// win[j] = 1 iff candidate j is its pair's record; W[slot] = j for the winner
+__global__ void k_pair_winner(const uint4* __restrict__ C, const uint32_t* __restrict__ n, const uint8_t* __restrict__ live,
+                              const uint32_t* __restrict__ Cslot, const unsigned long long* __restrict__ V, uint32_t* W, uint8_t* win,
+                              uint32_t* nwin) {
+  const uint32_t N = *n;
+  const uint32_t nround = (N + 31u) & ~31u;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+    bool w = false;
+    if (j < N && (!live || live[j])) {
+      const uint32_t slot = Cslot[j];
+      w = V[slot] == cand_value(C[j]);
+      if (w && W) W[slot] = j;
+    }
+    if (j < N) win[j] = w;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, w);       // distinct pairs (a statistic only)
+    if (nwin && m && (threadIdx.x & 31) == 0) atomicAdd(nwin, (uint32_t)__popc(m));
+  }
 }
-
-// tandem_grouper: consecutive hits of one gene (sorted by partner rank) on the same seqid and
-// within Nmax ranks are joined
-__global__ void k_tandem_adj(const uint64_t* __restrict__ keys, uint32_t n, int lowbits, const int32_t* __restrict__ chr,
-                             int nmax, uint32_t* parent) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0 || t >= n) return;
-  uint64_t a = keys[t - 1], b = keys[t];
-  if ((a >> lowbits) != (b >> lowbits)) return;
-  uint32_t ra = (uint32_t)(a & ((1ull << lowbits) - 1)), rb = (uint32_t)(b & ((1ull << lowbits) - 1));
-  if (chr[ra] == chr[rb] && (int64_t)rb - (int64_t)ra <= nmax) uf_union(parent, ra, rb);
+// tandem_grouper (blastfilter.py:262-284) without its sorts: among the winners with evalue < 1e-10, the hits of one
+// gene sorted by partner rank are joined when consecutive ones lie on one seqid within Nmax ranks.  For the winner
+// (q, s): its successor in q's list is the first (q, s + d), d = 1 .. Nmax, that is a flagged winner -- found by probing
+// the pair table -- and symmetrically (q + d, s) for s's list.  One edge per side at most; the union-find then gives the
+// same families (joining consecutive members or all members within Nmax has the same closure).
+__global__ void k_tandem_edges(const uint4* __restrict__ C, const uint32_t* __restrict__ n, const uint8_t* __restrict__ win,
+                               const unsigned long long* __restrict__ K, const uint32_t* __restrict__ W, uint32_t mask, int nmax,
+                               uint32_t Gq, uint32_t Gs, const int32_t* __restrict__ qchr, const int32_t* __restrict__ schr,
+                               uint2* qedges, uint2* sedges, uint32_t* nedges /* [0] q side, [1] s side */) {
+  const uint32_t N = *n;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    if (!win[j]) continue;
+    const uint4 c = C[j];
+    if (!(c.w & 1u)) continue;
+    const uint32_t q = c.x, s = c.y;
+    const int32_t cs = schr[s], cq = qchr[q];
+    for (int d = 1; d <= nmax; ++d) {                 // flip=False: per query, subject ranks ascending -> subject families
+      const uint32_t s2 = s + (uint32_t)d;
+      if (s2 >= Gs || schr[s2] != cs) break;
+      const int64_t slot = hash_slot_find(K, mask, q, s2);
+      if (slot >= 0 && (C[W[slot]].w & 1u)) { sedges[atomicAdd(nedges + 1, 1u)] = make_uint2(s, s2); break; }
+    }
+    for (int d = 1; d <= nmax; ++d) {                 // flip=True: per subject, query ranks ascending -> query families
+      const uint32_t q2 = q + (uint32_t)d;
+      if (q2 >= Gq || qchr[q2] != cq) break;
+      const int64_t slot = hash_slot_find(K, mask, q2, s);
+      if (slot >= 0 && (C[W[slot]].w & 1u)) { qedges[atomicAdd(nedges, 1u)] = make_uint2(q, q2); break; }
+    }
+  }
+}
+__global__ void k_apply_edges(const uint2* __restrict__ edges, const uint32_t* __restrict__ n, uint32_t* parent) {
+  const uint32_t N = *n;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) uf_union(parent, edges[t].x, edges[t].y);
+}
+// filter_tandem (blastfilter.py:240-259): winners -> (mother_q[q], mother_s[s]); `query == subject` pairs dropped; the
+// substituted candidate D[j] enters the second pair table
+__global__ void k_collapse_insert(const uint4* __restrict__ C, const uint32_t* __restrict__ n, const uint8_t* __restrict__ win,
+                                  const int32_t* __restrict__ mq, const int32_t* __restrict__ ms, const int32_t* __restrict__ q_same_s,
+                                  unsigned long long* K, unsigned long long* V, uint32_t mask, uint4* D, uint32_t* Dslot, uint8_t* live) {
+  const uint32_t N = *n;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    bool l = false;
+    if (win[j]) {
+      uint4 c = C[j];
+      const int32_t a = mq[c.x], b = ms[c.y];
+      if (q_same_s[a] != b) {                        // filter_tandem: `if b.query == b.subject: continue`
+        c.x = (uint32_t)a; c.y = (uint32_t)b;
+        D[j] = c;
+        const uint32_t slot = hash_slot_insert(K, mask, c.x, c.y);
+        atomicMax(V + slot, cand_value(c));
+        Dslot[j] = slot;
+        l = true;
+      }
+    }
+    live[j] = l;
+  }
+}
+// the survivors, in any order, with their output-order key (score desc, line asc)
+__global__ void k_final_emit(const uint4* __restrict__ D, const uint32_t* __restrict__ n, const uint8_t* __restrict__ fin,
+                             uint4* F, unsigned long long* keys, uint32_t* vals, uint32_t* nF) {
+  const uint32_t N = *n;
+  const uint32_t nround = (N + 31u) & ~31u;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+    const bool keep = j < N && fin[j];
+    const uint32_t pos = warp_append(keep, nF);
+    if (keep) {
+      const uint4 c = D[j];
+      F[pos] = c;
+      keys[pos] = ((unsigned long long)(~score_ord(c.z)) << 32) | (c.w >> 1);
+      vals[pos] = pos;
+    }
+  }
 }
 
 __global__ void k_iota(uint32_t* p, uint32_t n) {
@@ -170,35 +252,17 @@ __global__ void k_mother3(const uint32_t* root, const uint32_t* mroot, uint32_t 
   if (g < n) mother[g] = (int32_t)mroot[root[g]];
 }
 
-__global__ void k_collapse(const uint64_t* Kkey, uint32_t n, int sb, const int32_t* mq, const int32_t* ms,
-                           const int32_t* q_same_s, uint64_t* key2, uint32_t* flag) {
+// survivors in output order -> result columns + the byte offset of each survivor's line (from its record)
+__global__ void k_gather_out(const uint32_t* __restrict__ order, uint32_t n, const uint4* __restrict__ F, const uint4* __restrict__ recs,
+                             uint32_t ord_base, const LineIndex li, int32_t* oq, int32_t* os, float* oscore, uint64_t* ooff) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  uint64_t k = Kkey[t];
-  uint32_t qi = (uint32_t)(k >> sb), si = (uint32_t)(k & ((1ull << sb) - 1));
-  int32_t a = mq[qi], b = ms[si];
-  key2[t] = ((uint64_t)(uint32_t)a << sb) | (uint32_t)b;
-  flag[t] = q_same_s[a] != b;          // filter_tandem: `if b.query == b.subject: continue`
-}
-
-__global__ void k_order_keys(const uint32_t* Fj, const uint4* C, const uint32_t* Cidx, uint32_t n, uint64_t* keys) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  uint32_t j = Fj[t];
-  keys[t] = ((uint64_t)(~score_ord(C[j].z)) << 32) | Cidx[j];
-}
-
-__global__ void k_gather_out(const uint32_t* Fj, uint32_t n, const uint4* C, const uint32_t* Cidx, const int32_t* mq,
-                             const int32_t* ms, const LineIndex li, int32_t* oq, int32_t* os,
-                             float* oscore, uint64_t* ooff) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  uint32_t j = Fj[t];
-  uint4 r = C[j];
-  oq[t] = mq ? mq[r.x] : (int32_t)r.x;
-  os[t] = ms ? ms[r.y] : (int32_t)r.y;
-  oscore[t] = __uint_as_float(r.z);
-  ooff[t] = jx_line_offset(li, Cidx[j], r.w);
+  const uint4 c = F[order[t]];
+  oq[t] = (int32_t)c.x;
+  os[t] = (int32_t)c.y;
+  oscore[t] = __uint_as_float(c.z);
+  const uint32_t idx = (c.w >> 1) - ord_base;
+  ooff[t] = jx_line_offset(li, idx, recs[idx].w);
 }
 
 __global__ void k_line_len(const uint8_t* text, int64_t n, const uint64_t* off, const uint32_t* idx, uint32_t cnt, uint32_t* len,
@@ -268,42 +332,6 @@ __global__ void k_format_write(const uint8_t* text, int64_t n, const uint64_t* o
 }
 
 inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
-
-// flags -> exclusive positions + count (one small D2H)
-int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n, uint32_t*& pos, uint32_t& count) {
-  count = 0;
-  pos = nullptr;
-  if (!n) return JX_OK;
-  JX_ALLOC(p, uint32_t, n, false);
-  int rc = jx_exclusive_sum(ctx, arena, flag, p, n);
-  if (rc) return rc;
-  uint32_t last[2];
-  JX_CK(cudaMemcpyAsync(&last[0], p + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaMemcpyAsync(&last[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
-  count = last[0] + last[1];
-  pos = p;
-  return JX_OK;
-}
-
-// sort (key, j) and keep one record per key; output stays sorted by key
-int dedupe(jx_ctx* ctx, Arena& arena, uint64_t* keys, uint32_t* vals, size_t n, int keybits, const uint4* C,
-           const uint32_t* Cidx, int mode, uint64_t*& Kkey, uint32_t*& Kj, uint32_t& nK) {
-  Kkey = nullptr; Kj = nullptr; nK = 0;
-  if (!n) return JX_OK;
-  int rc = jx_sort_pairs(ctx, arena, keys, vals, n, 0, keybits);
-  if (rc) return rc;
-  JX_ALLOC(flag, uint32_t, n, false);
-  JX_ALLOC(pick, uint32_t, n, false);
-  JX_LAUNCH(k_run_best, nblk(n), 256, 0, keys, vals, C, Cidx, (uint32_t)n, mode, flag, pick);
-  uint32_t* pos;
-  if ((rc = compact_positions(ctx, arena, flag, n, pos, nK))) return rc;
-  JX_ALLOC(ok, uint64_t, nK, false);
-  JX_ALLOC(oj, uint32_t, nK, false);
-  JX_LAUNCH(k_scatter_pairs, nblk(n), 256, 0, keys, pick, flag, pos, (uint32_t)n, ok, oj);
-  Kkey = ok; Kj = oj;
-  return JX_OK;
-}
 
 // the reference's own formatting of one survivor: sscanf with cblast.pyx:15, start/stop
 // normalisation (cblast.pyx:115-120), sprintf with cblast.pyx:17 and the substituted names
@@ -539,10 +567,10 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   JX_TRACE("bf: tokenized");
 
   // ---- K5: C-score predicate fused with compaction -------------------------------------------------
+  if ((uint64_t)nrec >= (1ull << 31)) { ctx->err = "more than 2^31 record slots"; return JX_EUNSUPPORTED; }
   const size_t capC = (size_t)tok.stats[2] + 1;
   JX_ALLOC(C, uint4, capC, false);
-  JX_ALLOC(Cidx, uint32_t, capC, false);
-  JX_ALLOC(d_cnt, uint32_t, 2, true);
+  JX_ALLOC(d_cnt, uint32_t, 8, true);          // 0 candidates, 1 zero-division flag, 2 q edges, 3 s edges, 4 survivors
   if (nrec) {
     unsigned grid = std::min<unsigned>(nblk((nrec + 3) / 4), 148u * JX_SEL_GRID);
     JX_ALLOC(bestq, uint32_t, (size_t)Q.G + 1, false);
@@ -551,8 +579,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
       JX_LAUNCH(k_gene_best, nblk((size_t)Q.G), 256, 0, d_best, Q.name_id, (uint32_t)Q.G, bestq);
       JX_LAUNCH(k_gene_best, nblk((size_t)S.G), 256, 0, d_best, S.name_id, (uint32_t)S.G, bests);
     }
-    JX_LAUNCH(k_select, grid, 256, 0, tok.recs, nrec, bestq, bests, opts->cscore, use_cscore ? 1 : 0, C,
-              Cidx, d_cnt, d_cnt + 1);
+    JX_LAUNCH(k_select, grid, 256, 0, tok.recs, nrec, bestq, bests, opts->cscore, use_cscore ? 1 : 0, 0u, C, d_cnt, d_cnt + 1);
   }
   uint32_t h_cnt[2] = {0, 0};
   JX_CK(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -562,87 +589,92 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   out->stats[4] = nC;
   JX_TRACE("bf: k_select");
 
-  // ---- K3: per-pair best record (sorted by (qi, si)) ----------------------------------------------------
-  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
-  uint64_t* Kkey = nullptr; uint32_t* Kj = nullptr; uint32_t nK = 0;
-  {
-    JX_ALLOC(keys, uint64_t, nC, false);
-    JX_ALLOC(vals, uint32_t, nC, false);
-    if (nC) JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
-    if ((rc = dedupe(ctx, arena, keys, vals, nC, sb + qb, C, Cidx, 0, Kkey, Kj, nK))) return rc;
-  }
-  out->stats[5] = nK;
-  JX_TRACE("bf: dedupe1");
-
-  // ---- K6: tandem families + mothers -----------------------------------------------------------------------
+  // ---- K3, K6, K7 on the candidates; everything below is sized by nC and runs without a host round trip ------------
+  uint32_t nF = 0;
+  uint4* F = nullptr; uint32_t* Forder = nullptr;
   int32_t *d_mq = nullptr, *d_ms = nullptr;
-  uint32_t* Fj = Kj; uint32_t nF = nK;
-  if (use_tandem) {
+  if (use_tandem) {                                 // (the maps are also a result: want_mothers)
     const uint32_t Gq = (uint32_t)Q.G, Gs = (uint32_t)S.G;
-    JX_ALLOC(parent_q, uint32_t, Gq, false);
-    uint32_t* parent_s = parent_q;
-    JX_LAUNCH(k_iota, nblk(std::max(Gq, 1u)), 256, 0, parent_q, Gq);
-    if (!ctx->is_self) {
-      JX_ALLOC(ps, uint32_t, Gs, false);
-      parent_s = ps;
-      JX_LAUNCH(k_iota, nblk(std::max(Gs, 1u)), 256, 0, parent_s, Gs);
-    }
-    if (nK) {
-      JX_ALLOC(ef, uint32_t, nK, false);
-      JX_LAUNCH(k_eflags, nblk(nK), 256, 0, Kj, C, nK, ef);
-      uint32_t* pos; uint32_t nT;
-      if ((rc = compact_positions(ctx, arena, ef, nK, pos, nT))) return rc;
-      if (nT) {
-        JX_ALLOC(Tk, uint64_t, nT, false);
-        JX_LAUNCH(k_scatter_pairs, nblk(nK), 256, 0, Kkey, (const uint32_t*)nullptr, ef, pos, nK, Tk, (uint32_t*)nullptr);
-        // flip=False: per query, subject ranks ascending -> subject families
-        JX_LAUNCH(k_tandem_adj, nblk(nT), 256, 0, Tk, nT, sb, S.chr_lex, opts->tandem_nmax, parent_s);
-        // flip=True: per subject, query ranks ascending -> query families
-        JX_ALLOC(Tk2, uint64_t, nT, false);
-        JX_LAUNCH(k_swap_keys, nblk(nT), 256, 0, Tk, nT, sb, qb, Tk2);
-        uint64_t* Tk2s = Tk2;
-        if ((rc = jx_sort_keys(ctx, arena, Tk2s, nT, 0, sb + qb))) return rc;
-        JX_LAUNCH(k_tandem_adj, nblk(nT), 256, 0, Tk2s, nT, qb, Q.chr_lex, opts->tandem_nmax, parent_q);
-      }
-    }
-    auto mothers = [&](uint32_t* parent, const SideDev& D, int32_t*& d_m) -> int {
-      const uint32_t G = (uint32_t)D.G;
-      JX_ALLOC(root, uint32_t, G, false);
-      JX_ALLOC(bk, unsigned long long, G, true);
-      JX_ALLOC(mroot, uint32_t, G, false);
-      JX_ALLOC(m, int32_t, G, false);
-      if (G) {
-        JX_LAUNCH(k_flatten, nblk(G), 256, 0, parent, G, root);
-        JX_LAUNCH(k_mother1, nblk(G), 256, 0, root, D.length, D.lexrank, G, bk);
-        JX_LAUNCH(k_mother2, nblk(G), 256, 0, root, D.length, D.lexrank, G, bk, mroot);
-        JX_LAUNCH(k_mother3, nblk(G), 256, 0, root, mroot, G, m);
-      }
-      d_m = m;
-      return JX_OK;
-    };
-    if ((rc = mothers(parent_q, Q, d_mq))) return rc;
+    JX_ALLOC(mq0, int32_t, (size_t)Gq + 1, false);
+    d_mq = mq0;
     if (ctx->is_self) d_ms = d_mq;
-    else if ((rc = mothers(parent_s, S, d_ms))) return rc;
-
-    // ---- K7: substitute mothers, drop q == s, second per-pair best --------------------------------------
-    nF = 0; Fj = nullptr;
-    if (nK) {
-      JX_ALLOC(key2, uint64_t, nK, false);
-      JX_ALLOC(fl, uint32_t, nK, false);
-      JX_LAUNCH(k_collapse, nblk(nK), 256, 0, Kkey, nK, sb, d_mq, d_ms, ctx->q_same_s, key2, fl);
-      uint32_t* pos; uint32_t nM;
-      if ((rc = compact_positions(ctx, arena, fl, nK, pos, nM))) return rc;
-      JX_ALLOC(k3, uint64_t, nM, false);
-      JX_ALLOC(v3, uint32_t, nM, false);
-      if (nM) JX_LAUNCH(k_scatter_pairs, nblk(nK), 256, 0, key2, Kj, fl, pos, nK, k3, v3);
-      uint64_t* Fkey;
-      if ((rc = dedupe(ctx, arena, k3, v3, nM, sb + qb, C, Cidx, 0, Fkey, Fj, nF))) return rc;
+    else { JX_ALLOC(ms0, int32_t, (size_t)Gs + 1, false); d_ms = ms0; }
+  }
+  if (nC || use_tandem) {
+    uint32_t hcap = 1024;
+    while (hcap < 2u * nC + 16u && hcap < (1u << 31)) hcap <<= 1;
+    const uint32_t hmask = hcap - 1u;
+    const unsigned g1 = std::max(1u, std::min<unsigned>(nblk(std::max<uint32_t>(nC, 1u)), 148u * 8u));
+    JX_ALLOC(K1, unsigned long long, hcap, false);
+    JX_ALLOC(V1, unsigned long long, hcap, true);
+    JX_ALLOC(W1, uint32_t, hcap, false);
+    JX_ALLOC(Cslot, uint32_t, (size_t)nC + 1, false);
+    JX_ALLOC(win, uint8_t, (size_t)nC + 1, false);
+    JX_CK(cudaMemsetAsync(K1, 0xFF, (size_t)hcap * 8, ctx->stream));
+    JX_LAUNCH(k_pair_insert, g1, 256, 0, C, d_cnt, (const uint8_t*)nullptr, K1, V1, hmask, Cslot);
+    JX_LAUNCH(k_pair_winner, g1, 256, 0, C, d_cnt, (const uint8_t*)nullptr, Cslot, V1, W1, win, d_cnt + 5);
+    const uint4* D = C; const uint8_t* fin = win;
+    if (use_tandem) {
+      const uint32_t Gq = (uint32_t)Q.G, Gs = (uint32_t)S.G;
+      JX_ALLOC(parent_q, uint32_t, (size_t)Gq + 1, false);
+      uint32_t* parent_s = parent_q;
+      JX_LAUNCH(k_iota, nblk(std::max(Gq, 1u)), 256, 0, parent_q, Gq);
+      if (!ctx->is_self) {
+        JX_ALLOC(ps, uint32_t, (size_t)Gs + 1, false);
+        parent_s = ps;
+        JX_LAUNCH(k_iota, nblk(std::max(Gs, 1u)), 256, 0, parent_s, Gs);
+      }
+      JX_ALLOC(qedges, uint2, (size_t)nC + 1, false);
+      JX_ALLOC(sedges, uint2, (size_t)nC + 1, false);
+      JX_LAUNCH(k_tandem_edges, g1, 256, 0, C, d_cnt, win, K1, W1, hmask, opts->tandem_nmax, Gq, Gs, Q.chr_lex, S.chr_lex,
+                qedges, sedges, d_cnt + 2);
+      JX_LAUNCH(k_apply_edges, g1, 256, 0, qedges, d_cnt + 2, parent_q);
+      JX_LAUNCH(k_apply_edges, g1, 256, 0, sedges, d_cnt + 3, parent_s);
+      auto mothers = [&](uint32_t* parent, const SideDev& Dv, int32_t* m) -> int {
+        const uint32_t G = (uint32_t)Dv.G;
+        JX_ALLOC(root, uint32_t, (size_t)G + 1, false);
+        JX_ALLOC(bk, unsigned long long, (size_t)G + 1, true);
+        JX_ALLOC(mroot, uint32_t, (size_t)G + 1, false);
+        if (G) {
+          JX_LAUNCH(k_flatten, nblk(G), 256, 0, parent, G, root);
+          JX_LAUNCH(k_mother1, nblk(G), 256, 0, root, Dv.length, Dv.lexrank, G, bk);
+          JX_LAUNCH(k_mother2, nblk(G), 256, 0, root, Dv.length, Dv.lexrank, G, bk, mroot);
+          JX_LAUNCH(k_mother3, nblk(G), 256, 0, root, mroot, G, m);
+        }
+        return JX_OK;
+      };
+      if ((rc = mothers(parent_q, Q, d_mq))) return rc;
+      if (!ctx->is_self && (rc = mothers(parent_s, S, d_ms))) return rc;
+      // ---- K7: substitute mothers, drop q == s, second per-pair best ---------------------------------------------------
+      JX_ALLOC(K2, unsigned long long, hcap, false);
+      JX_ALLOC(V2, unsigned long long, hcap, true);
+      JX_ALLOC(D2, uint4, (size_t)nC + 1, false);
+      JX_ALLOC(Dslot, uint32_t, (size_t)nC + 1, false);
+      JX_ALLOC(live, uint8_t, (size_t)nC + 1, false);
+      JX_ALLOC(fin2, uint8_t, (size_t)nC + 1, false);
+      JX_CK(cudaMemsetAsync(K2, 0xFF, (size_t)hcap * 8, ctx->stream));
+      JX_LAUNCH(k_collapse_insert, g1, 256, 0, C, d_cnt, win, d_mq, d_ms, ctx->q_same_s, K2, V2, hmask, D2, Dslot, live);
+      JX_LAUNCH(k_pair_winner, g1, 256, 0, D2, d_cnt, live, Dslot, V2, (uint32_t*)nullptr, fin2, (uint32_t*)nullptr);
+      D = D2; fin = fin2;
     }
+    // ---- K8: the survivors and their output order (score desc, line asc) ----------------------------------------------------
+    JX_ALLOC(F0, uint4, (size_t)nC + 1, false);
+    JX_ALLOC(okeys, uint64_t, (size_t)nC + 1, false);
+    JX_ALLOC(ovals, uint32_t, (size_t)nC + 1, false);
+    JX_LAUNCH(k_final_emit, g1, 256, 0, D, d_cnt, fin, F0, (unsigned long long*)okeys, ovals, d_cnt + 4);
+    uint32_t h5[6] = {0, 0, 0, 0, 0, 0};
+    JX_CK(cudaMemcpyAsync(h5, d_cnt, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    nF = h5[4];
+    out->stats[5] = h5[5];
+    F = F0;
+    uint64_t* ok = okeys; uint32_t* ov = ovals;
+    if (nF && (rc = jx_sort_pairs(ctx, arena, ok, ov, nF, 0, 64))) return rc;
+    Forder = ov;
   }
   out->stats[6] = nF;
-  JX_TRACE("bf: tandem+dedupe2");
+  JX_TRACE("bf: pairs+tandem+order");
 
-  // ---- K8: output order (score desc, line asc) and gather ----------------------------------------------------
   out->n = nF;
   const bool host_arrays = !opts->skip_arrays;
   if (host_arrays) {
@@ -653,20 +685,11 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   }
   ctx->lastf.n = 0; ctx->lastf.token = 0;
   if (nF) {
-    JX_ALLOC(okeys, uint64_t, nF, false);
-    JX_LAUNCH(k_order_keys, nblk(nF), 256, 0, Fj, C, Cidx, nF, okeys);
-    uint64_t* ok = okeys; uint32_t* ov = Fj;
-    {  // sort needs a private copy of the values
-      JX_ALLOC(vcopy, uint32_t, nF, false);
-      JX_CK(cudaMemcpyAsync(vcopy, Fj, nF * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-      ov = vcopy;
-    }
-    if ((rc = jx_sort_pairs(ctx, arena, ok, ov, nF, 0, 64))) return rc;
     JX_ALLOC(oq, int32_t, nF, false);
     JX_ALLOC(os, int32_t, nF, false);
     JX_ALLOC(osc, float, nF, false);
     JX_ALLOC(ooff, uint64_t, nF, false);
-    JX_LAUNCH(k_gather_out, nblk(nF), 256, 0, ov, nF, C, Cidx, d_mq, d_ms, tok.li, oq, os, osc, ooff);
+    JX_LAUNCH(k_gather_out, nblk(nF), 256, 0, Forder, nF, F, tok.recs, 0u, tok.li, oq, os, osc, ooff);
     if (host_arrays) {
       JX_CK(cudaMemcpyAsync(out->q_rank, oq, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
       JX_CK(cudaMemcpyAsync(out->s_rank, os, nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
