@@ -248,13 +248,9 @@ def impl_ours(args):
         return s.q_rank, s.s_rank, blk
 
     def step_device():
-        r = eng.blastfilter(dev_text, want_text=False, raw=True, skip_arrays=True)   # survivors stay on the device
-        try:
-            s = eng.scan_filtered(r)
-        finally:
-            eng.free_filter(r)
-        aq, as_, ab = anchors_of(s)
-        l = eng.liftover_text(dev_text, aq, as_, ab, dist=10)
+        # one library call (jx_pipeline): survivors and anchors stay on the device between the stages; the anchors and the
+        # lifted pairs come back to the host inside the step, the `.filtered` text is not formatted (`e2e` includes it)
+        f, s, l = eng.pipeline(dev_text, want_text=False, skip_arrays=True, liftover_dist=10)
         return s, l
 
     e2e_log = []

@@ -193,6 +193,16 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
                      const int32_t* a_block, int64_t n_anchor_lines, jx_liftover_result* out);
 void jx_liftover_result_free(jx_liftover_result* r);
 
+/* ---- the three stages as one call (what catalog.ortholog runs back to back, src/jcvi/compara/catalog.py:720-750) ----
+ * jx_blastfilter -> jx_scan_filtered -> jx_liftover_text(same raw text, the anchors just found, dist = liftover_dist)
+ * with everything that flows between the stages left on the device: the survivors go to scan as device arrays ("%.3g"
+ * score round trip applied there), the anchors go to liftover as device arrays while their copy to the host is in
+ * flight, liftover re-uses the records blastfilter tokenized.  Host text is uploaded (jx_text_upload) first; device text
+ * must come from jx_text_upload.  The three results are exactly those of the three separate calls. */
+int jx_pipeline(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, const jx_filter_opts* fopts,
+                const jx_scan_opts* sopts, int liftover_dist, jx_filter_result* fout, jx_scan_result* sout,
+                jx_liftover_result* lout);
+
 /* synteny_liftover (synteny.py:455-473) on caller-supplied integer points: nearest[i] = index
  * of the anchor cKDTree(anchors, leafsize=16).query(p=1, distance_upper_bound=dist) returns for
  * point i, or n_anchors when none is strictly closer than dist; dist_out[i] its L1 distance. */

@@ -99,6 +99,8 @@ struct jx_ctx {
   std::vector<PinBuf> pin_pool;
   char* pin_small = nullptr;     // grow-only pinned staging for small result arrays (one D2H instead of several pageable ones)
   size_t pin_small_cap = 0;
+  char* pin_scan = nullptr;      // the same for scan results (their copy may still be in flight while liftover stages its own)
+  size_t pin_scan_cap = 0;
   uint8_t* held_text = nullptr;
   int64_t held_n = 0;
   int64_t held_cap = 0;
@@ -171,6 +173,18 @@ inline int jx_pin_small(jx_ctx* ctx, size_t bytes, char** out) {
     ctx->pin_small_cap = cap;
   }
   *out = ctx->pin_small;
+  return JX_OK;
+}
+
+inline int jx_pin_scan(jx_ctx* ctx, size_t bytes, char** out) {
+  if (ctx->pin_scan_cap < bytes) {
+    if (ctx->pin_scan) { cudaStreamSynchronize(ctx->copy_stream); cudaFreeHost(ctx->pin_scan); }
+    ctx->pin_scan = nullptr; ctx->pin_scan_cap = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    if (cudaMallocHost((void**)&ctx->pin_scan, cap) != cudaSuccess) { ctx->err = "cudaMallocHost failed"; return JX_ECUDA; }
+    ctx->pin_scan_cap = cap;
+  }
+  *out = ctx->pin_scan;
   return JX_OK;
 }
 
@@ -299,6 +313,21 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
 int jx_gather_lines(jx_ctx* ctx, Arena& arena, const uint8_t* d_text, int64_t nbytes, const LineIndex& li,
                     const uint4* recs, const uint32_t* rec_idx, uint32_t cnt, char** out, int64_t* out_len, int rstrip = 0,
                     uint64_t* dev_out = nullptr);   // dev_out: leave the packed lines in ctx->lines_dev instead (no host copy)
+
+// ---- stage cores shared by the C-ABI entry points (jx_filter.cu / jx_scan.cu / jx_liftover.cu / jx_pipeline.cu) ----
+// device-side anchors of a scan (arena memory of the caller): members cluster by cluster, block id per member
+struct ScanDev {
+  int32_t* q = nullptr; int32_t* s = nullptr; float* score = nullptr; uint32_t* block = nullptr;
+  uint32_t* count = nullptr;     // device: [0] = anchors
+  uint32_t n = 0, nb = 0;        // host copies (nb only when the host half has run)
+  bool defer_copy = false;       // in: leave the result copy in flight (`stage`), the caller finishes with scan_finish_host
+  char* stage = nullptr;
+};
+void scan_finish_host(jx_scan_result* out, const char* stage, uint32_t m);
+int jx_scan_survivors(jx_ctx* ctx, Arena& arena, const jx_scan_opts* opts, jx_scan_result* out, ScanDev* dev);   // of the last jx_blastfilter
+int jx_liftover_core(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t n_slots, const unsigned long long* tstats, int dist,
+                     const int32_t* d_aq, const int32_t* d_as, const uint32_t* d_ablock, uint32_t nal,
+                     const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out);
 
 // ---- shared device helpers ---------------------------------------------------------------------
 #if defined(__CUDACC__)

@@ -477,14 +477,9 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   memset(out, 0, sizeof *out);
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
-  const SideDev& Q = ctx->side[0];
-  const SideDev& S = ctx->side[1];
   const uint32_t nal = (uint32_t)n_lines64;
   int rc;
-
-  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
   JX_TRACE("lo: enter");
-
   // ---- raw records: reuse the ones jx_blastfilter just produced from the same held text (the
   // reference parses the raw table twice: blastfilter.py:48 and synteny.py:1939), else tokenize
   const uint4* recs = nullptr; uint32_t n_lines = 0;
@@ -506,50 +501,259 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
       memcpy(tstats, tok.stats, sizeof tstats);
     }
   }
+  JX_ALLOC(daq, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(das, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(dab, uint32_t, (size_t)nal + 1, false);
+  if (nal) {
+    JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dab, a_block, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  JX_TRACE("lo: records ready");
+  return jx_liftover_core(ctx, arena, recs, n_lines, tstats, dist, daq, das, dab, nal, a_qi, a_si, a_block, out);
+}
+
+}  // extern "C"
+
+namespace {
+// anchor lines -> sort keys: (qi << sb | si) for anchors in the BED, one key above all others for the rest
+__global__ void k_anchor_keys(const int32_t* __restrict__ aq, const int32_t* __restrict__ as_, uint32_t nal, int sb, int kb,
+                              uint32_t Gq, uint32_t Gs, uint64_t* keys, uint32_t* order, uint32_t* counts /* 0 valid, 1 out of range */) {
+  const uint32_t nround = (nal + 31u) & ~31u;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nround) return;
+  bool valid = false;
+  if (t < nal) {
+    const int32_t q = aq[t], s = as_[t];
+    valid = q >= 0 && s >= 0;
+    if (valid && ((uint32_t)q >= Gq || (uint32_t)s >= Gs)) { atomicExch(counts + 1, 1u); valid = false; }
+    keys[t] = valid ? (((uint64_t)(uint32_t)q << sb) | (uint32_t)s) : (1ull << kb);
+    order[t] = t;
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+  if (m && (threadIdx.x & 31) == 0) atomicAdd(counts, (uint32_t)__popc(m));
+}
+__global__ void k_anchor_blocks2(const uint64_t* keys, const uint32_t* order, const uint32_t* block_in, const uint32_t* na,
+                                 uint32_t* block_out, uint32_t* dup) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *na) return;
+  block_out[i] = block_in[order[i]];
+  if (i && keys[i] == keys[i - 1]) atomicExch(dup, 1u);
+}
+__global__ void k_rowptr2(const uint64_t* akey, const uint32_t* na_p, int sb, uint32_t G, uint32_t* rowptr) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  const uint32_t na = *na_p;
+  uint64_t key = (uint64_t)g << sb;
+  uint32_t lo = 0, hi = na;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (akey[mid] < key) lo = mid + 1; else hi = mid; }
+  rowptr[g] = lo;
+}
+__global__ void k_mark_cells2(const uint64_t* akey, const uint32_t* na, int sb, int dist, int cshift, uint32_t nsc, uint32_t nqc,
+                              uint32_t* bitmap) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *na) return;
+  const uint64_t a = akey[t];
+  const int32_t x = (int32_t)(a >> sb), y = (int32_t)(a & ((1ull << sb) - 1));
+  const int32_t x0 = max(x - dist, 0) >> cshift, x1 = min((uint32_t)((x + dist) >> cshift), nqc - 1);
+  const int32_t y0 = max(y - dist, 0) >> cshift, y1 = min((uint32_t)((y + dist) >> cshift), nsc - 1);
+  for (int32_t cx = x0; cx <= x1; ++cx)
+    for (int32_t cy = y0; cy <= y1; ++cy) {
+      const uint64_t bit = (uint64_t)cx * nsc + (uint64_t)cy;
+      atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+    }
+}
+// pass 1 as k_select_cell, candidates in the compact form {qi, si, score bits, record index}
+__global__ void __launch_bounds__(256) k_select_cell2(const uint4* __restrict__ recs, uint32_t n, const uint32_t* __restrict__ bitmap,
+                                                      int cshift, uint32_t nsc, uint4* out, uint32_t* counter) {
+  constexpr int U = 4;
+  __shared__ uint32_t s_cnt[256 / 32 + 1];
+  const uint32_t stride = gridDim.x * blockDim.x * U;
+  const uint32_t lane = threadIdx.x & 31u, woff = (threadIdx.x & ~31u) * U;
+  for (uint64_t c0 = (uint64_t)blockIdx.x * blockDim.x * U; c0 < n; c0 += stride) {
+    const uint32_t i0 = (uint32_t)c0 + woff;
+    uint4 r[U]; bool keep[U]; uint32_t w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      r[u] = i < n ? __ldcs(recs + i) : make_uint4(JX_NOREC, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      keep[u] = r[u].x != JX_NOREC;
+      const uint64_t bit = (uint64_t)(r[u].x >> cshift) * nsc + (uint64_t)(r[u].y >> cshift);
+      w[u] = keep[u] ? __ldg(bitmap + (bit >> 5)) >> (bit & 31) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) keep[u] = keep[u] && (w[u] & 1u);
+    uint32_t slot[U];
+    block_append_multi<U>(keep, counter, slot, s_cnt);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (keep[u]) { r[u].w = i0 + u * 32u + lane; out[slot[u]] = r[u]; }
+  }
+}
+__device__ __forceinline__ uint32_t pair_hash2(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ b * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+  return h;
+}
+// pass 2: exact window test; the candidates that are near an anchor enter the pair table, which keeps the FIRST
+// occurrence in file order per (qi, si) (process_blast_for_liftover's `seen`, synteny.py:339-360): value = index << 32 | j
+__global__ void k_near_insert(const uint4* __restrict__ cand, const uint32_t* __restrict__ n_p, int sb, const uint64_t* __restrict__ akey,
+                              const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
+                              const int32_t* __restrict__ schr, int dist, unsigned long long* K, unsigned long long* V, uint32_t mask,
+                              uint32_t* Cslot) {
+  const uint32_t n = *n_p;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const uint4 r = cand[t];
+    uint32_t slot = 0xFFFFFFFFu;
+    if (anchor_within((int32_t)r.x, (int32_t)r.y, sb, akey, rowptr, qbeg, qend, schr, dist)) {
+      const unsigned long long key = ((unsigned long long)r.x << 32) | r.y;
+      slot = pair_hash2(r.x, r.y) & mask;
+      for (;;) {
+        const unsigned long long prev = atomicCAS(K + slot, 0xFFFFFFFFFFFFFFFFull, key);
+        if (prev == 0xFFFFFFFFFFFFFFFFull || prev == key) break;
+        slot = (slot + 1u) & mask;
+      }
+      atomicMin(V + slot, ((unsigned long long)r.w << 32) | t);
+    }
+    Cslot[t] = slot;
+  }
+}
+// the unique hits (first occurrences), in any order
+__global__ void k_hits_emit(const uint4* __restrict__ cand, const uint32_t* __restrict__ n_p, const uint32_t* __restrict__ Cslot,
+                            const unsigned long long* __restrict__ V, int sb, uint64_t* hkey, float* hsc, uint32_t* hline, uint32_t* nh) {
+  const uint32_t n = *n_p;
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+    bool w = false;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (t < n) {
+      const uint32_t slot = Cslot[t];
+      if (slot != 0xFFFFFFFFu) { w = (uint32_t)V[slot] == t; r = cand[t]; }
+    }
+    const uint32_t pos = warp_append(w, nh);
+    if (w) { hkey[pos] = ((uint64_t)r.x << sb) | r.y; hsc[pos] = __uint_as_float(r.z); hline[pos] = r.w; }
+  }
+}
+// accepted[(query, subject)] lookup for every anchor line: a probe of the pair table
+__global__ void k_lookup2(const unsigned long long* __restrict__ K, const unsigned long long* __restrict__ V, uint32_t mask,
+                          const uint4* __restrict__ cand, const int32_t* aq, const int32_t* as_, uint32_t na, uint8_t* acc, float* raw) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= na) return;
+  acc[t] = 0; raw[t] = 0.f;
+  if (aq[t] < 0 || as_[t] < 0) return;
+  const uint32_t a = (uint32_t)aq[t], b = (uint32_t)as_[t];
+  const unsigned long long key = ((unsigned long long)a << 32) | b;
+  uint32_t slot = pair_hash2(a, b) & mask;
+  for (;;) {
+    const unsigned long long k = K[slot];
+    if (k == key) { acc[t] = 1; raw[t] = __uint_as_float(cand[(uint32_t)V[slot]].z); return; }
+    if (k == 0xFFFFFFFFFFFFFFFFull) return;
+    slot = (slot + 1u) & mask;
+  }
+}
+__global__ void k_nearest2(const uint64_t* __restrict__ hkey, const uint32_t* __restrict__ nh_p, int sb, const uint64_t* __restrict__ akey,
+                           const uint32_t* __restrict__ ablock, const uint32_t* __restrict__ rowptr,
+                           const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
+                           const int32_t* __restrict__ schr, int dist, uint32_t* hit_block, uint8_t* state, uint32_t* counts /* 0 lifted, 1 ambiguous */) {
+  const uint32_t nh = *nh_p;
+  const uint32_t nround = (nh + 31u) & ~31u;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+    uint8_t st = 0;
+    if (t < nh) {
+      const uint64_t k = hkey[t];
+      const uint64_t smask = (1ull << sb) - 1;
+      const int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & smask);
+      const int32_t lo = max(x - (dist - 1), qbeg[x]), hi = min(x + dist - 1, qend[x] - 1);
+      uint32_t bt = 0xFFFFFFFFu, bblk = 0; bool amb = false;
+      int best = dist;
+      if (hi >= lo) {
+        const uint32_t t0 = rowptr[lo], t1 = rowptr[hi + 1];
+        const int32_t cy = schr[y];
+        for (uint32_t u = t0; u < t1; ++u) {
+          const uint64_t a = akey[u];
+          const int32_t ax = (int32_t)(a >> sb), ay = (int32_t)(a & smask);
+          const int d = abs(ax - x) + abs(ay - y);
+          if (d > best) continue;
+          if (schr[ay] != cy) continue;
+          if (d < best) { best = d; bt = u; bblk = ablock[u]; amb = false; }
+          else if (bt != 0xFFFFFFFFu && ablock[u] != bblk) amb = true;
+        }
+      }
+      // state: 0 none within dist / is an anchor itself, 1 lifted (unambiguous), 2 needs the tree walk
+      if (bt != 0xFFFFFFFFu && best > 0) st = amb ? 2 : 1;
+      state[t] = st;
+      hit_block[t] = st == 1 ? bblk : 0u;
+    }
+    const unsigned ml = __ballot_sync(0xFFFFFFFFu, st != 0), ma = __ballot_sync(0xFFFFFFFFu, st == 2);
+    if ((threadIdx.x & 31) == 0) {
+      if (ml) atomicAdd(counts, (uint32_t)__popc(ml));
+      if (ma) atomicAdd(counts + 1, (uint32_t)__popc(ma));
+    }
+  }
+}
+__global__ void k_gather_amb2(const uint8_t* state, const uint32_t* nh_p, uint32_t* amb_hit, uint32_t* namb) {
+  const uint32_t nh = *nh_p;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nh && state[t] == 2) amb_hit[atomicAdd(namb, 1u)] = t;
+}
+// lifted hits (any order) with the key of the reference's append order: (block, sorted chromosome pair, file order)
+__global__ void k_lift_emit(const uint8_t* state, const uint32_t* nh_p, const uint64_t* hkey, const uint32_t* hline, const uint32_t* hit_block,
+                            int sb, const int32_t* qchr, const int32_t* schr, uint64_t nschr, int ob, int cb, uint64_t* keys,
+                            uint32_t* vals, uint32_t* npos) {
+  const uint32_t nh = *nh_p;
+  const uint32_t nround = (nh + 31u) & ~31u;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+    const bool w = t < nh && state[t] != 0;
+    const uint32_t pos = warp_append(w, npos);
+    if (w) {
+      const uint64_t k = hkey[t];
+      const int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & ((1ull << sb) - 1));
+      const uint64_t cp = (uint64_t)qchr[x] * nschr + (uint64_t)schr[y];
+      keys[pos] = ((uint64_t)hit_block[t] << (ob + cb)) | (cp << ob) | hline[t];
+      vals[pos] = t;
+    }
+  }
+}
+}  // namespace
+
+// liftover on device-resident records and anchors.  d_aq / d_as / d_ablock: per anchor LINE (file order; -1 = name not
+// in the BED).  h_*: the same on the host when the caller has them (only the rare tie walk needs them; null: copied back).
+int jx_liftover_core(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t n_lines, const unsigned long long* tstats, int dist,
+                     const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
+                     const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out) {
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  int rc;
+  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
   out->stats[0] = (int64_t)(tstats[0] - tstats[1]);
   out->stats[5] = (int64_t)tstats[1];
   out->stats[1] = (int64_t)tstats[2];        // mapped raw records (before pair de-duplication)
-
-  // ---- anchors ------------------------------------------------------------------------------------------
   out->accepted = (uint8_t*)calloc((size_t)nal + 1, 1);
   out->raw_score = (float*)calloc((size_t)nal + 1, sizeof(float));
-  std::vector<uint64_t> akeys_h; std::vector<uint32_t> aline_h;
-  akeys_h.reserve(nal); aline_h.reserve(nal);
-  for (uint32_t t = 0; t < nal; ++t) {
-    if (a_qi[t] < 0 || a_si[t] < 0) continue;
-    if (a_qi[t] >= Q.G || a_si[t] >= S.G) { ctx->err = "anchor rank out of range"; return JX_EARG; }
-    akeys_h.push_back(((uint64_t)(uint32_t)a_qi[t] << sb) | (uint32_t)a_si[t]);
-    aline_h.push_back(t);
-  }
-  const uint32_t na = (uint32_t)akeys_h.size();
-  out->stats[2] = na;
   auto alloc_out = [&](uint32_t n) {
     out->q_rank = (int32_t*)malloc(4 * ((size_t)n + 1)); out->s_rank = (int32_t*)malloc(4 * ((size_t)n + 1));
     out->score = (float*)malloc(4 * ((size_t)n + 1)); out->block = (int32_t*)malloc(4 * ((size_t)n + 1));
     out->n_lifted = n;
   };
-  if (!na || !tstats[2]) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
+  if (!nal || !tstats[2]) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
 
-  // sort anchors by (qi, si) on the device; detect duplicates (read_anchors' assert)
-  JX_ALLOC(akey, uint64_t, na, false);
-  JX_ALLOC(aord, uint32_t, na, false);
-  std::vector<uint32_t> ablock_h(na);
-  for (uint32_t i = 0; i < na; ++i) ablock_h[i] = (uint32_t)a_block[aline_h[i]];
-  JX_TRACE("lo: records ready");
-  JX_CK(cudaMemcpyAsync(akey, akeys_h.data(), (size_t)na * 8, cudaMemcpyHostToDevice, ctx->stream));
-  JX_ALLOC(dablock0, uint32_t, na, false);
-  JX_CK(cudaMemcpyAsync(dablock0, ablock_h.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
-  JX_LAUNCH(k_iota_u32, nblk(na), 256, 0, aord, na);
+  // ---- anchors sorted by (qi, si); duplicates = read_anchors' assert ------------------------------------------------------
+  // counters: 0 anchors in the BED, 1 rank out of range, 2 duplicate, 3 candidates (cells), 4 unique hits, 5 lifted, 6 ambiguous, 7 emitted
+  JX_ALLOC(d_cnt, uint32_t, 12, true);
+  const int kb = sb + qb;
+  JX_ALLOC(akey, uint64_t, nal, false);
+  JX_ALLOC(aord, uint32_t, nal, false);
+  JX_LAUNCH(k_anchor_keys, nblk(nal), 256, 0, daq, das, nal, sb, kb, (uint32_t)Q.G, (uint32_t)S.G, akey, aord, d_cnt);
   uint64_t* aks = akey; uint32_t* aos = aord;
-  if ((rc = jx_sort_pairs(ctx, arena, aks, aos, na, 0, sb + qb))) return rc;
-  // block of every sorted anchor and the duplicate check stay on the device; the flag comes back with
-  // the first count read below
-  JX_ALLOC(dablock, uint32_t, na, false);
-  JX_ALLOC(d_dup, uint32_t, 1, true);
-  JX_LAUNCH(k_anchor_blocks, nblk(na), 256, 0, aks, aos, dablock0, na, dablock, d_dup);
+  if ((rc = jx_sort_pairs(ctx, arena, aks, aos, nal, 0, kb + 1))) return rc;
+  JX_ALLOC(dablock, uint32_t, nal, false);
+  JX_LAUNCH(k_anchor_blocks2, nblk(nal), 256, 0, aks, aos, dab, d_cnt, dablock, d_cnt + 2);
   JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
-  JX_TRACE("lo: anchors sorted (host round trip)");
-  JX_LAUNCH(k_rowptr, nblk((size_t)Q.G + 1), 256, 0, aks, na, sb, (uint32_t)Q.G, rowptr);
+  JX_LAUNCH(k_rowptr2, nblk((size_t)Q.G + 1), 256, 0, aks, d_cnt, sb, (uint32_t)Q.G, rowptr);
+  JX_TRACE("lo: anchors sorted");
 
   // ---- raw records -> candidates near an anchor -> unique (qi,si), first occurrence ------------------------
   int cshift = 4;                                          // 16 x 16 rank cells, coarser for huge genomes
@@ -560,89 +764,82 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   // the prefilter keeps records at distance 0 from an anchor even when dist == 0 (`scan --dist=1 --liftover`
   // gives liftover_dist 0): AnchorFile.filter_blocks needs the anchors' own raw pairs; lifting stays `< dist`
   const int dist_pre = std::max(dist, 1);
-  JX_LAUNCH(k_mark_cells, nblk(na), 256, 0, aks, na, sb, dist_pre, cshift, nsc, nqc, bitmap);
+  JX_LAUNCH(k_mark_cells2, nblk(nal), 256, 0, aks, d_cnt, sb, dist_pre, cshift, nsc, nqc, bitmap);
   const size_t capC = (size_t)tstats[2] + 1;
   JX_ALLOC(C0, uint4, capC, false);
-  JX_ALLOC(C0idx, uint32_t, capC, false);
-  JX_ALLOC(d_cnt, uint32_t, 2, true);
   if (n_lines) {
     unsigned grid = std::min<unsigned>(nblk((n_lines + 3) / 4), 148u * 8u);
-    JX_LAUNCH(k_select_cell, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, C0, C0idx, d_cnt);
+    JX_LAUNCH(k_select_cell2, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, C0, d_cnt + 3);
   }
-  uint32_t nC0 = 0, h_dup = 0;
-  JX_CK(cudaMemcpyAsync(&nC0, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaMemcpyAsync(&h_dup, d_dup, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t h4[4] = {0, 0, 0, 0};
+  JX_CK(cudaMemcpyAsync(h4, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
   JX_CK(cudaStreamSynchronize(ctx->stream));
-  if (h_dup) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
-  JX_ALLOC(C, uint4, (size_t)nC0 + 1, false);
-  JX_ALLOC(Cidx, uint32_t, (size_t)nC0 + 1, false);
+  if (h4[1]) { ctx->err = "anchor rank out of range"; return JX_EARG; }
+  if (h4[2]) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
+  const uint32_t na = h4[0], nC0 = h4[3];
+  out->stats[2] = na;
   JX_TRACE("lo: select_cell");
-  if (nC0) JX_LAUNCH(k_keep_near, nblk(nC0), 256, 0, C0, C0idx, nC0, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist_pre, C, Cidx,
-                     d_cnt + 1);
-  uint32_t nC = 0;
-  JX_CK(cudaMemcpyAsync(&nC, d_cnt + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
-  uint32_t nh = 0;
-  uint64_t* hkey = nullptr; float* hsc = nullptr; uint32_t* hline = nullptr;
-  if (nC) {
-    JX_ALLOC(keys, uint64_t, nC, false);
-    JX_ALLOC(vals, uint32_t, nC, false);
-  JX_TRACE("lo: keep_near");
-    JX_LAUNCH(k_make_keys, nblk(nC), 256, 0, C, nC, sb, keys, vals);
-    uint64_t* ks = keys; uint32_t* vs = vals;
-    if ((rc = jx_sort_pairs(ctx, arena, ks, vs, nC, 0, sb + qb))) return rc;
-    JX_ALLOC(flag, uint32_t, nC, false);
-    JX_ALLOC(pick, uint32_t, nC, false);
-    JX_LAUNCH(k_run_first, nblk(nC), 256, 0, ks, vs, Cidx, nC, flag, pick);
-    uint32_t* pos;
-    if ((rc = compact_positions(ctx, arena, flag, nC, pos, nh))) return rc;
-    JX_ALLOC(hk, uint64_t, nh, false);
-    JX_ALLOC(hs, float, nh, false);
-    JX_ALLOC(hl, uint32_t, nh, false);
-    JX_LAUNCH(k_scatter_hits, nblk(nC), 256, 0, ks, pick, flag, pos, nC, C, Cidx, hk, hs, hl);
-    hkey = hk; hsc = hs; hline = hl;
-  }
+  if (!na || !nC0) { alloc_out(0); return JX_OK; }
 
+  uint32_t hcap = 1024;
+  while (hcap < 2u * nC0 + 16u && hcap < (1u << 31)) hcap <<= 1;
+  const uint32_t hmask = hcap - 1u;
+  const unsigned g1 = std::max(1u, std::min<unsigned>(nblk(nC0), 148u * 8u));
+  JX_ALLOC(HK, unsigned long long, hcap, false);
+  JX_ALLOC(HV, unsigned long long, hcap, false);
+  JX_ALLOC(Cslot, uint32_t, (size_t)nC0 + 1, false);
+  JX_CK(cudaMemsetAsync(HK, 0xFF, (size_t)hcap * 8, ctx->stream));
+  JX_CK(cudaMemsetAsync(HV, 0xFF, (size_t)hcap * 8, ctx->stream));
+  JX_LAUNCH(k_near_insert, g1, 256, 0, C0, d_cnt + 3, sb, aks, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist_pre, HK, HV, hmask, Cslot);
+  JX_ALLOC(hkey, uint64_t, (size_t)nC0 + 1, false);
+  JX_ALLOC(hsc, float, (size_t)nC0 + 1, false);
+  JX_ALLOC(hline, uint32_t, (size_t)nC0 + 1, false);
+  JX_LAUNCH(k_hits_emit, g1, 256, 0, C0, d_cnt + 3, Cslot, HV, sb, hkey, hsc, hline, d_cnt + 4);
   // accepted[(query, subject)] for every anchor line
-  JX_ALLOC(daq, int32_t, nal, false);
-  JX_ALLOC(das, int32_t, nal, false);
-  JX_ALLOC(dacc, uint8_t, nal, false);
-  JX_ALLOC(draw, float, nal, false);
-  if (nal) {
-    JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-    JX_LAUNCH(k_lookup, nblk(nal), 256, 0, hkey, hsc, nh, daq, das, nal, sb, dacc, draw);
-    JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  if (!nh) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
+  JX_ALLOC(dacc, uint8_t, (size_t)nal + 1, false);
+  JX_ALLOC(draw, float, (size_t)nal + 1, false);
+  JX_LAUNCH(k_lookup2, nblk(nal), 256, 0, HK, HV, hmask, C0, daq, das, nal, dacc, draw);
+  JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_TRACE("lo: near+dedupe+lookup");
 
   // ---- nearest anchor per hit -------------------------------------------------------------------------------
-  JX_ALLOC(best_a, uint32_t, nh, false);
-  JX_ALLOC(state, uint8_t, nh, false);
-  JX_TRACE("lo: dedupe+lookup");
-  JX_LAUNCH(k_nearest, nblk(nh, 128), 128, 0, hkey, nh, sb, aks, dablock, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist,
-            best_a, state);
-  JX_ALLOC(f1, uint32_t, nh, false);
-  JX_ALLOC(f2, uint32_t, nh, false);
-  JX_LAUNCH(k_lift_flags, nblk(nh), 256, 0, state, nh, f1, f2);
-  uint32_t *pos1, *pos2; uint32_t nlift, namb;
-  if ((rc = compact_positions(ctx, arena, f1, nh, pos1, nlift))) return rc;
-  if ((rc = compact_positions(ctx, arena, f2, nh, pos2, namb))) return rc;
+  JX_ALLOC(hit_block, uint32_t, (size_t)nC0 + 1, false);
+  JX_ALLOC(state, uint8_t, (size_t)nC0 + 1, false);
+  JX_LAUNCH(k_nearest2, g1, 128, 0, hkey, d_cnt + 4, sb, aks, dablock, rowptr, Q.chr_begin, Q.chr_end, S.chr_lex, dist, hit_block, state,
+            d_cnt + 5);
+  uint32_t h3[3] = {0, 0, 0};
+  JX_CK(cudaMemcpyAsync(h3, d_cnt + 4, 12, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t nh = h3[0], nlift = h3[1], namb = h3[2];
   out->stats[3] = nlift;
   out->stats[4] = namb;
-  JX_ALLOC(hit_block, uint32_t, nh, false);
-  JX_LAUNCH(k_hit_block, nblk(nh), 256, 0, state, best_a, dablock, nh, hit_block);
 
   // ---- cross-block ties: exact cKDTree emulation ---------------------------------------------------------------
   if (namb) {
     JX_ALLOC(amb_hit, uint32_t, namb, false);
-    JX_LAUNCH(k_gather_amb, nblk(nh), 256, 0, state, pos2, nh, amb_hit);
+    JX_LAUNCH(k_gather_amb2, nblk(nh), 256, 0, state, d_cnt + 4, amb_hit, d_cnt + 8);
     std::vector<uint32_t> amb_h(namb);
     std::vector<uint64_t> hk_h(nh);
+    std::vector<int32_t> caq, cas, cab;
+    if (!h_aq) {                                   // anchors that never left the device (fused scan + liftover)
+      caq.resize(nal); cas.resize(nal); cab.resize(nal);
+      JX_CK(cudaMemcpyAsync(caq.data(), daq, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(cas.data(), das, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaMemcpyAsync(cab.data(), dab, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      h_aq = caq.data(); h_as = cas.data(); h_ablock = cab.data();
+    }
     JX_CK(cudaMemcpyAsync(amb_h.data(), amb_hit, (size_t)namb * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaMemcpyAsync(hk_h.data(), hkey, (size_t)nh * 8, cudaMemcpyDeviceToHost, ctx->stream));
     JX_CK(cudaStreamSynchronize(ctx->stream));
+    // anchors in the BED, in file order (all_anchors[chr_pair], synteny.py:392)
+    std::vector<uint64_t> akeys_h; std::vector<uint32_t> ablock_h;
+    akeys_h.reserve(nal); ablock_h.reserve(nal);
+    for (uint32_t t = 0; t < nal; ++t) {
+      if (h_aq[t] < 0 || h_as[t] < 0) continue;
+      akeys_h.push_back(((uint64_t)(uint32_t)h_aq[t] << sb) | (uint32_t)h_as[t]);
+      ablock_h.push_back((uint32_t)h_ablock[t]);
+    }
     const uint64_t smask = (1ull << sb) - 1;
     auto cp_of = [&](uint64_t key) {
       return (uint64_t)Q.h_chr_lex[(size_t)(key >> sb)] * (uint64_t)S.n_chr + (uint64_t)S.h_chr_lex[(size_t)(key & smask)];
@@ -654,9 +851,8 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
       qx[i] = (long long)(key >> sb); qy[i] = (long long)(key & smask);
       tree_of.emplace(cp_of(key), -1);
     }
-    // anchors of those chromosome pairs, in file order (all_anchors[chr_pair], synteny.py:392)
     std::map<uint64_t, std::vector<uint32_t>> members;
-    for (uint32_t i = 0; i < na; ++i) {
+    for (uint32_t i = 0; i < (uint32_t)akeys_h.size(); ++i) {
       uint64_t cp = cp_of(akeys_h[i]);
       if (tree_of.count(cp)) members[cp].push_back(i);
     }
@@ -683,27 +879,25 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
     JX_LAUNCH(k_patch_amb, nblk(namb), 256, 0, amb_hit, d_ab, namb, hit_block);
     JX_CK(cudaStreamSynchronize(ctx->stream));
   }
+  JX_TRACE("lo: nearest+ambiguous");
 
-  // ---- order: (block, sorted chromosome pair, file order) ------------------------------------------------------------
+  // ---- order: (block, sorted chromosome pair, file order) in ONE key ------------------------------------------------------------
   alloc_out(nlift);
   if (nlift) {
+    const uint64_t maxcp = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
+    const int ob = jx_bits((uint64_t)std::max<uint32_t>(n_lines, 1u)), cb = jx_bits(maxcp), bb = jx_bits((uint64_t)nal + 1);
+    if (ob + cb + bb > 64) { ctx->err = "too many chromosome pairs / blocks / lines for one liftover sort key"; return JX_EUNSUPPORTED; }
     JX_ALLOC(k1, uint64_t, nlift, false);
     JX_ALLOC(v1, uint32_t, nlift, false);
-  JX_TRACE("lo: nearest+ambiguous");
-    JX_LAUNCH(k_lift_keys, nblk(nh), 256, 0, state, pos1, hkey, hline, sb, Q.chr_lex, S.chr_lex, (uint64_t)S.n_chr, nh, k1, v1);
+    JX_LAUNCH(k_lift_emit, std::max(1u, std::min<unsigned>(nblk(nh), 148u * 8u)), 256, 0, state, d_cnt + 4, hkey, hline, hit_block, sb,
+              Q.chr_lex, S.chr_lex, (uint64_t)S.n_chr, ob, cb, k1, v1, d_cnt + 7);
     uint64_t* k1s = k1; uint32_t* v1s = v1;
-    const uint64_t maxcp = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
-    if (maxcp >= (1ull << 32)) { ctx->err = "too many chromosome pairs"; return JX_EUNSUPPORTED; }
-    if ((rc = jx_sort_pairs(ctx, arena, k1s, v1s, nlift, 0, 32 + jx_bits(maxcp)))) return rc;
-    JX_ALLOC(k2, uint64_t, nlift, false);
-    JX_LAUNCH(k_block_keys, nblk(nlift), 256, 0, v1s, hit_block, nlift, k2);
-    uint64_t* k2s = k2;
-    if ((rc = jx_sort_pairs(ctx, arena, k2s, v1s, nlift, 0, 32))) return rc;
+    if ((rc = jx_sort_pairs(ctx, arena, k1s, v1s, nlift, 0, ob + cb + bb))) return rc;
     // one device block, one copy into pinned staging (instead of four synchronous pageable copies)
     JX_ALLOC(oblk, uint32_t, (size_t)nlift * 4, false);
     int32_t* oq = (int32_t*)oblk; int32_t* os = (int32_t*)(oblk + nlift); float* osc = (float*)(oblk + 2 * (size_t)nlift);
-    int32_t* ob = (int32_t*)(oblk + 3 * (size_t)nlift);
-    JX_LAUNCH(k_emit_lifted, nblk(nlift), 256, 0, v1s, nlift, hkey, hsc, hit_block, sb, oq, os, osc, ob);
+    int32_t* ob_ = (int32_t*)(oblk + 3 * (size_t)nlift);
+    JX_LAUNCH(k_emit_lifted, nblk(nlift), 256, 0, v1s, nlift, hkey, hsc, hit_block, sb, oq, os, osc, ob_);
     char* stage = nullptr;
     if ((rc = jx_pin_small(ctx, (size_t)nlift * 16, &stage))) return rc;
     JX_CK(cudaMemcpyAsync(stage, oblk, (size_t)nlift * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -730,6 +924,8 @@ int jx_liftover_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_
   JX_CK(cudaGetLastError());
   return JX_OK;
 }
+
+extern "C" {
 
 namespace {
 __global__ void k_widen_idx(const uint32_t* in, uint32_t n, uint64_t* out) {

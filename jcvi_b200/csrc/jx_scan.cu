@@ -10,6 +10,26 @@
 #include <algorithm>
 #include "jx_internal.cuh"
 
+// host half of a scan result: the pinned block {q, s, score, index, head flags} x m -> result arrays + block starts
+void scan_finish_host(jx_scan_result* out, const char* stage, uint32_t m) {
+  memcpy(out->q_rank, stage, (size_t)m * 4);
+  memcpy(out->s_rank, stage + (size_t)m * 4, (size_t)m * 4);
+  memcpy(out->score, stage + (size_t)m * 8, (size_t)m * 4);
+  const uint32_t* hidx = (const uint32_t*)(stage + (size_t)m * 12);
+  const uint32_t* hhead = (const uint32_t*)(stage + (size_t)m * 16);
+  int64_t nb = 0;
+  for (uint32_t t = 0; t < m; ++t) nb += hhead[t];
+  free(out->block_start);
+  out->block_start = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nb + 1));
+  int64_t b = 0;
+  for (uint32_t t = 0; t < m; ++t) {
+    if (hhead[t]) out->block_start[b++] = t;
+    out->index[t] = hidx[t];
+  }
+  out->block_start[nb] = m;
+  out->n_blocks = nb;
+}
+
 namespace {
 
 inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
@@ -142,42 +162,157 @@ __global__ void k_count_x(const int32_t* px, const uint64_t* cp, const uint32_t*
     if (label[j] == l) return;
   atomicAdd(nx + l, 1u);
 }
-__global__ void k_label_y_keys(const uint32_t* label, const int32_t* py, uint32_t n, uint64_t* keys) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = ((uint64_t)label[i] << 32) | (uint32_t)py[i];
-}
-__global__ void k_count_unique(const uint64_t* keys, uint32_t n, uint32_t* ny) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  if (t == 0 || keys[t] != keys[t - 1]) atomicAdd(ny + (uint32_t)(keys[t] >> 32), 1u);
-}
-
-__global__ void k_pass_flags(const uint32_t* label, const uint32_t* birth, const uint32_t* nx, const uint32_t* ny,
-                             uint32_t n, int N, uint32_t* flag, uint32_t* inclus) {
+// #distinct si per component: (label, y) pairs through a hash set; the thread that inserts a new pair counts it
+__global__ void k_count_y(const uint32_t* __restrict__ label, const int32_t* __restrict__ py, uint32_t n, unsigned long long* K,
+                          uint32_t mask, uint32_t* ny) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t l = label[i];
-  bool clustered = birth[l] != 0xFFFFFFFFu;        // isolated points never enter the Grouper
-  uint32_t s = nx[l] < ny[l] ? nx[l] : ny[l];
-  flag[i] = clustered && (int)s >= N;
-  if (clustered) atomicAdd(inclus, 1u);
+  const uint32_t l = label[i], y = (uint32_t)py[i];
+  const unsigned long long key = ((unsigned long long)l << 32) | y;
+  uint32_t h = l * 0x9E3779B1u ^ y * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+  uint32_t slot = h & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(K + slot, 0xFFFFFFFFFFFFFFFFull, key);
+    if (prev == 0xFFFFFFFFFFFFFFFFull) { atomicAdd(ny + l, 1u); return; }
+    if (prev == key) return;
+    slot = (slot + 1u) & mask;
+  }
 }
-__global__ void k_out_keys(const uint32_t* flag, const uint32_t* pos, const uint32_t* label, const uint32_t* birth,
-                           uint32_t n, uint64_t* keys, uint32_t* vals) {
+
+// flag = the point's cluster passes min(#distinct qi, #distinct si) >= N; output key = (birth of the cluster, index):
+// clusters in Grouper's iteration order, members ascending.  Points that do not pass get a key above all others.
+__global__ void k_pass_keys(const uint32_t* label, const uint32_t* birth, const uint32_t* nx, const uint32_t* ny,
+                            uint32_t n, int N, int ib, uint64_t* keys, uint32_t* vals, uint32_t* counts /* 0 passing, 1 clustered */) {
+  const uint32_t nround = (n + 31u) & ~31u;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
-  keys[pos[i]] = ((uint64_t)birth[label[i]] << 32) | i;
-  vals[pos[i]] = i;
+  if (i >= nround) return;
+  bool pass = false, clustered = false;
+  if (i < n) {
+    const uint32_t l = label[i];
+    clustered = birth[l] != 0xFFFFFFFFu;            // isolated points never enter the Grouper
+    const uint32_t s = nx[l] < ny[l] ? nx[l] : ny[l];
+    pass = clustered && (int)s >= N;
+    keys[i] = pass ? (((uint64_t)birth[l] << ib) | i) : (1ull << (2 * ib));
+    vals[i] = i;
+  }
+  const unsigned mp = __ballot_sync(0xFFFFFFFFu, pass), mc = __ballot_sync(0xFFFFFFFFu, clustered);
+  if ((threadIdx.x & 31) == 0) {
+    if (mp) atomicAdd(counts, (uint32_t)__popc(mp));
+    if (mc) atomicAdd(counts + 1, (uint32_t)__popc(mc));
+  }
 }
-__global__ void k_emit(const uint64_t* keys, const uint32_t* vals, uint32_t n, const int32_t* px, const int32_t* py,
+// the first *m sorted entries are the anchors
+__global__ void k_emit(const uint64_t* keys, const uint32_t* vals, const uint32_t* m, int ib, const int32_t* px, const int32_t* py,
                        const float* psc, const uint32_t* pidx, int32_t* oq, int32_t* os, float* osc, uint32_t* oidx,
                        uint32_t* head) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
+  if (t >= *m) return;
   uint32_t i = vals[t];
   oq[t] = px[i]; os[t] = py[i]; osc[t] = psc[i];
   if (oidx) oidx[t] = pidx ? pidx[i] : i;
-  head[t] = (t == 0) || (keys[t] >> 32) != (keys[t - 1] >> 32);
+  head[t] = (t == 0) || (keys[t] >> ib) != (keys[t - 1] >> ib);
+}
+__global__ void k_block_ids(const uint32_t* head, const uint32_t* excl, const uint32_t* m, uint32_t* block) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < *m) block[t] = excl[t] + head[t] - 1u;
+}
+
+// Core: points already sorted by (chromosome pair, qi, si) on the device.  One host round trip (the result copy).
+// `dev` (optional) receives the anchors as device arrays, valid as long as the caller's Arena.
+int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32_t* py, const float* psc,
+                       const uint64_t* cp, const uint32_t* pidx, uint32_t n, int is_self, const jx_scan_opts* o,
+                       jx_scan_result* out, ScanDev* dev, const uint32_t* extra_flag) {
+  out->n_anchors = 0; out->n_blocks = 0;
+  out->block_start = (int64_t*)calloc(1, sizeof(int64_t));
+  if (dev) { const bool defer = dev->defer_copy; *dev = ScanDev(); dev->defer_copy = defer; }
+  if (!n) {
+    out->q_rank = (int32_t*)malloc(4); out->s_rank = (int32_t*)malloc(4); out->score = (float*)malloc(4);
+    out->index = (int64_t*)malloc(8);
+    if (extra_flag) {
+      uint32_t hb = 0;
+      JX_CK(cudaMemcpyAsync(&hb, extra_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      JX_CK(cudaStreamSynchronize(ctx->stream));
+      if (hb) { ctx->err = "score outside the exactly handled %.3g range"; return JX_EUNSUPPORTED; }
+    }
+    return JX_OK;
+  }
+  JX_ALLOC(parent, uint32_t, n, false);
+  JX_ALLOC(hasprev, uint8_t, n, false);
+  JX_ALLOC(label, uint32_t, n, false);
+  JX_ALLOC(birth, uint32_t, n, false);
+  JX_ALLOC(nx, uint32_t, n, true);
+  JX_ALLOC(ny, uint32_t, n, true);
+  JX_ALLOC(d_cnt, uint32_t, 4, true);
+  JX_CK(cudaMemsetAsync(birth, 0xFF, (size_t)n * 4, ctx->stream));
+  JX_TRACE("scan: points ready");
+  JX_LAUNCH(k_iota, nblk(n), 256, 0, parent, n);
+  JX_LAUNCH(k_link, nblk(n, 128), 128, 0, px, py, cp, n, o->xdist, o->ydist, is_self, o->intrabound, parent, hasprev);
+  JX_LAUNCH(k_label, nblk(n), 256, 0, parent, hasprev, n, label, birth);
+  JX_TRACE("scan: link+label");
+  JX_LAUNCH(k_count_x, nblk(n), 256, 0, px, cp, label, n, nx);
+  {
+    uint32_t hcap = 1024;
+    while (hcap < 2u * n + 16u && hcap < (1u << 31)) hcap <<= 1;
+    JX_ALLOC(HK, unsigned long long, hcap, false);
+    JX_CK(cudaMemsetAsync(HK, 0xFF, (size_t)hcap * 8, ctx->stream));
+    JX_LAUNCH(k_count_y, nblk(n), 256, 0, label, py, n, HK, hcap - 1u, ny);
+  }
+  JX_TRACE("scan: counts");
+  const int ib = jx_bits((uint64_t)n);
+  JX_ALLOC(okeys, uint64_t, n, false);
+  JX_ALLOC(ovals, uint32_t, n, false);
+  JX_LAUNCH(k_pass_keys, nblk(n), 256, 0, label, birth, nx, ny, n, o->min_size, ib, okeys, ovals, d_cnt);
+  uint64_t* ok = okeys; uint32_t* ov = ovals;
+  int rc;
+  if ((rc = jx_sort_pairs(ctx, arena, ok, ov, n, 0, 2 * ib + 1))) return rc;
+  JX_TRACE("scan: out sort");
+  // the five result arrays are one device block: ONE copy into pinned staging
+  JX_ALLOC(oblk, uint32_t, (size_t)n * 5 + 4, false);
+  int32_t* oq = (int32_t*)oblk; int32_t* os = (int32_t*)(oblk + n); float* osc = (float*)(oblk + 2 * (size_t)n);
+  uint32_t* oidx = oblk + 3 * (size_t)n; uint32_t* head = oblk + 4 * (size_t)n;
+  JX_LAUNCH(k_emit, nblk(n), 256, 0, ok, ov, d_cnt, ib, px, py, psc, pidx, oq, os, osc, oidx, head);
+  if (dev) {                                      // block id of every anchor, for liftover on the device
+    JX_ALLOC(excl, uint32_t, n, false);
+    JX_ALLOC(blk, uint32_t, n, false);
+    if ((rc = jx_exclusive_sum(ctx, arena, head, excl, n))) return rc;     // (entries beyond *m are never read)
+    JX_LAUNCH(k_block_ids, nblk(n), 256, 0, head, excl, d_cnt, blk);
+    dev->q = oq; dev->s = os; dev->score = osc; dev->block = blk; dev->count = d_cnt;
+  }
+  // counts first (8 bytes), then exactly the anchors
+  uint32_t hc[2] = {0, 0}, hbad = 0;
+  JX_CK(cudaMemcpyAsync(hc, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (extra_flag) JX_CK(cudaMemcpyAsync(&hbad, extra_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (hbad) { ctx->err = "score outside the exactly handled %.3g range"; return JX_EUNSUPPORTED; }
+  const uint32_t m = hc[0];
+  if (dev) dev->n = m;
+  out->stats[2] = hc[1];
+  out->q_rank = (int32_t*)malloc(4 * ((size_t)m + 1));
+  out->s_rank = (int32_t*)malloc(4 * ((size_t)m + 1));
+  out->score = (float*)malloc(4 * ((size_t)m + 1));
+  out->index = (int64_t*)malloc(8 * ((size_t)m + 1));
+  out->n_anchors = m;
+  if (m) {
+    char* stage = nullptr;
+    if ((rc = jx_pin_scan(ctx, (size_t)m * 20, &stage))) return rc;
+    if (dev && dev->defer_copy) {
+      // the caller overlaps this copy with its next stage (copy stream; everything above has completed: the
+      // count read-back synchronised) and finishes the result itself
+      for (int k = 0; k < 5; ++k)
+        JX_CK(cudaMemcpyAsync(stage + (size_t)m * 4 * k, oblk + (size_t)n * k, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      dev->stage = stage;
+      return JX_OK;
+    }
+    for (int k = 0; k < 5; ++k)
+      JX_CK(cudaMemcpyAsync(stage + (size_t)m * 4 * k, oblk + (size_t)n * k, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    scan_finish_host(out, stage, m);
+    JX_TRACE("scan: emit + D2H");
+  }
+  if (dev) dev->nb = (uint32_t)out->n_blocks;
+  JX_CK(cudaGetLastError());
+  return JX_OK;
 }
 
 int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n, uint32_t*& pos, uint32_t& count) {
@@ -195,97 +330,9 @@ int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n,
   return JX_OK;
 }
 
-// Core: points already sorted by (chromosome pair, qi, si) on the device.
-int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32_t* py, const float* psc,
-                       const uint64_t* cp, const uint32_t* pidx, uint32_t n, int is_self, const jx_scan_opts* o,
-                       jx_scan_result* out) {
-  out->n_anchors = 0; out->n_blocks = 0;
-  out->block_start = (int64_t*)calloc(1, sizeof(int64_t));
-  if (!n) {
-    out->q_rank = (int32_t*)malloc(4); out->s_rank = (int32_t*)malloc(4); out->score = (float*)malloc(4);
-    out->index = (int64_t*)malloc(8);
-    return JX_OK;
-  }
-  JX_ALLOC(parent, uint32_t, n, false);
-  JX_ALLOC(hasprev, uint8_t, n, false);
-  JX_ALLOC(label, uint32_t, n, false);
-  JX_ALLOC(birth, uint32_t, n, false);
-  JX_ALLOC(nx, uint32_t, n, true);
-  JX_ALLOC(ny, uint32_t, n, true);
-  JX_ALLOC(d_in, uint32_t, 1, true);
-  JX_CK(cudaMemsetAsync(birth, 0xFF, (size_t)n * 4, ctx->stream));
-  JX_TRACE("scan: points ready");
-  JX_LAUNCH(k_iota, nblk(n), 256, 0, parent, n);
-  JX_LAUNCH(k_link, nblk(n, 128), 128, 0, px, py, cp, n, o->xdist, o->ydist, is_self, o->intrabound, parent, hasprev);
-  JX_LAUNCH(k_label, nblk(n), 256, 0, parent, hasprev, n, label, birth);
-  JX_TRACE("scan: link+label");
-  JX_LAUNCH(k_count_x, nblk(n), 256, 0, px, cp, label, n, nx);
-  {
-    JX_ALLOC(yk, uint64_t, n, false);
-    JX_LAUNCH(k_label_y_keys, nblk(n), 256, 0, label, py, n, yk);
-    uint64_t* yks = yk;
-    int rc = jx_sort_keys(ctx, arena, yks, n, 0, 64);
-    if (rc) return rc;
-    JX_LAUNCH(k_count_unique, nblk(n), 256, 0, yks, n, ny);
-  }
-  JX_ALLOC(flag, uint32_t, n, false);
-  JX_TRACE("scan: counts");
-  JX_LAUNCH(k_pass_flags, nblk(n), 256, 0, label, birth, nx, ny, n, o->min_size, flag, d_in);
-  uint32_t* pos; uint32_t m;
-  int rc = compact_positions(ctx, arena, flag, n, pos, m);
-  if (rc) return rc;
-  uint32_t h_in = 0;
-  JX_CK(cudaMemcpyAsync(&h_in, d_in, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  out->q_rank = (int32_t*)malloc(4 * ((size_t)m + 1));
-  out->s_rank = (int32_t*)malloc(4 * ((size_t)m + 1));
-  out->score = (float*)malloc(4 * ((size_t)m + 1));
-  out->index = (int64_t*)malloc(8 * ((size_t)m + 1));
-  out->n_anchors = m;
-  if (m) {
-    JX_ALLOC(okeys, uint64_t, m, false);
-    JX_ALLOC(ovals, uint32_t, m, false);
-  JX_TRACE("scan: flags+compact");
-    JX_LAUNCH(k_out_keys, nblk(n), 256, 0, flag, pos, label, birth, n, okeys, ovals);
-    uint64_t* ok = okeys; uint32_t* ov = ovals;
-    if ((rc = jx_sort_pairs(ctx, arena, ok, ov, m, 0, 64))) return rc;
-    // the five result arrays are one device block: ONE copy into pinned staging instead of five
-    // synchronous pageable copies
-    JX_ALLOC(oblk, uint32_t, (size_t)m * 5, false);
-    int32_t* oq = (int32_t*)oblk; int32_t* os = (int32_t*)(oblk + m); float* osc = (float*)(oblk + 2 * (size_t)m);
-    uint32_t* oidx = oblk + 3 * (size_t)m; uint32_t* head = oblk + 4 * (size_t)m;
-    JX_TRACE("scan: out sort");
-    JX_LAUNCH(k_emit, nblk(m), 256, 0, ok, ov, m, px, py, psc, pidx, oq, os, osc, oidx, head);
-    char* stage = nullptr;
-    if ((rc = jx_pin_small(ctx, (size_t)m * 20, &stage))) return rc;
-    JX_CK(cudaMemcpyAsync(stage, oblk, (size_t)m * 20, cudaMemcpyDeviceToHost, ctx->stream));
-    JX_CK(cudaStreamSynchronize(ctx->stream));
-    memcpy(out->q_rank, stage, (size_t)m * 4);
-    memcpy(out->s_rank, stage + (size_t)m * 4, (size_t)m * 4);
-    memcpy(out->score, stage + (size_t)m * 8, (size_t)m * 4);
-    const uint32_t* hidx = (const uint32_t*)(stage + (size_t)m * 12);
-    const uint32_t* hhead = (const uint32_t*)(stage + (size_t)m * 16);
-    JX_TRACE("scan: emit + D2H");
-    int64_t nb = 0;
-    for (uint32_t t = 0; t < m; ++t) nb += hhead[t];
-    free(out->block_start);
-    out->block_start = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nb + 1));
-    int64_t b = 0;
-    for (uint32_t t = 0; t < m; ++t) {
-      if (hhead[t]) out->block_start[b++] = t;
-      out->index[t] = hidx[t];
-    }
-    out->block_start[nb] = m;
-    out->n_blocks = nb;
-  }
-  JX_CK(cudaStreamSynchronize(ctx->stream));
-  out->stats[2] = h_in;
-  JX_CK(cudaGetLastError());
-  return JX_OK;
-}
-
 // records (file order, holes marked JX_NOREC) -> scan
 int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, size_t nvalid_hint, const jx_scan_opts* o,
-                 jx_scan_result* out, bool valid_unique = false) {
+                 jx_scan_result* out, bool valid_unique = false, ScanDev* dev = nullptr, const uint32_t* extra_flag = nullptr) {
   const SideDev& Q = ctx->side[0];
   const SideDev& S = ctx->side[1];
   int rc;
@@ -306,7 +353,7 @@ int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, si
       JX_LAUNCH(k_points_from_keys, nblk(n), 256, 0, ks, vs, recs, n, sb0, qb0, x1, y1, s1, c1);
       JX_TRACE("scan: single sort (valid, unique input)");
       out->stats[1] = n;
-      return scan_sorted_points(ctx, arena, x1, y1, s1, c1, nullptr, n, ctx->is_self ? 1 : 0, o, out);
+      return scan_sorted_points(ctx, arena, x1, y1, s1, c1, nullptr, n, ctx->is_self ? 1 : 0, o, out, dev, extra_flag);
     }
   }
   JX_ALLOC(C, uint4, nvalid_hint + 1, false);
@@ -355,7 +402,7 @@ int scan_records(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t nrec, si
     px = x1; py = y1; psc = s1; cp = cs;
   }
   out->stats[1] = n;
-  return scan_sorted_points(ctx, arena, px, py, psc, cp, nullptr, n, ctx->is_self ? 1 : 0, o, out);
+  return scan_sorted_points(ctx, arena, px, py, psc, cp, nullptr, n, ctx->is_self ? 1 : 0, o, out, dev, extra_flag);
 }
 
 __global__ void k_filtered_to_recs(const int32_t* q, const int32_t* s, const float* score, uint32_t n, int is_self,
@@ -407,34 +454,24 @@ int jx_scan_filtered(jx_ctx* ctx, const jx_filter_result* f, const jx_scan_opts*
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
   const uint32_t n = (uint32_t)f->n;
+  if (n && f->device_token && f->device_token == ctx->lastf.token && (int64_t)n == ctx->lastf.n)
+    return jx_scan_survivors(ctx, arena, opts, out, nullptr);          // still resident: no round trip
   JX_ALLOC(dq, int32_t, n, false);
   JX_ALLOC(ds, int32_t, n, false);
   JX_ALLOC(dsc, float, n, false);
   JX_ALLOC(recs, uint4, n, false);
   JX_ALLOC(bad, uint32_t, 1, true);
-  bool resident_survivors = false;
   if (n) {
-    const int32_t* srcq = dq; const int32_t* srcs = ds; const float* srcsc = dsc;
-    if (f->device_token && f->device_token == ctx->lastf.token && (int64_t)n == ctx->lastf.n) {
-      srcq = ctx->lastf.q; srcs = ctx->lastf.s; srcsc = ctx->lastf.score;      // still resident: no round trip
-      resident_survivors = true;
-    } else {
-      if (!f->q_rank || !f->s_rank || !f->score) { ctx->err = "filter result has no host arrays and is no longer resident"; return JX_EARG; }
-      JX_CK(cudaMemcpyAsync(dq, f->q_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-      JX_CK(cudaMemcpyAsync(ds, f->s_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-      JX_CK(cudaMemcpyAsync(dsc, f->score, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    JX_LAUNCH(k_filtered_to_recs, nblk(n), 256, 0, srcq, srcs, srcsc, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
+    if (!f->q_rank || !f->s_rank || !f->score) { ctx->err = "filter result has no host arrays and is no longer resident"; return JX_EARG; }
+    JX_CK(cudaMemcpyAsync(dq, f->q_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(ds, f->s_rank, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dsc, f->score, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_LAUNCH(k_filtered_to_recs, nblk(n), 256, 0, dq, ds, dsc, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
               ctx->side[1].chr_lex, recs, bad);
   }
-  uint32_t hbad = 0;
-  JX_CK(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
-  if (hbad) { ctx->err = "score outside the exactly handled %.3g range"; return JX_EUNSUPPORTED; }
   out->stats[0] = n;
-  // the library's own survivors are valid and pair-unique (blastfilter de-duplicates twice); a self
-  // comparison re-orients pairs (qi <= si) and can make duplicates, and host arrays may be anything
-  return scan_records(ctx, arena, recs, n, n, opts, out, resident_survivors && !ctx->is_self);
+  // host arrays may be anything: the general route (select valid, pair de-duplication, stable pair sort)
+  return scan_records(ctx, arena, recs, n, n, opts, out, false, nullptr, bad);
 }
 
 int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const float* score, const int64_t* group,
@@ -484,10 +521,24 @@ int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const floa
     px = x1; py = y1; psc = s1; cp = gs; pidx = perm;
   }
   out->stats[1] = n;
-  return scan_sorted_points(ctx, arena, px, py, psc, cp, pidx, n, is_self, opts, out);
+  return scan_sorted_points(ctx, arena, px, py, psc, cp, pidx, n, is_self, opts, out, nullptr, nullptr);
 }
 
 }  // extern "C"
+
+// the in-memory hand-over of the LAST jx_blastfilter's survivors (still on the device) to scan: equivalent to writing
+// `.filtered` with "%.3g" scores (cblast.pyx:17) and reading it back with read_blast
+int jx_scan_survivors(jx_ctx* ctx, Arena& arena, const jx_scan_opts* opts, jx_scan_result* out, ScanDev* dev) {
+  const uint32_t n = (uint32_t)ctx->lastf.n;
+  JX_ALLOC(recs, uint4, (size_t)n + 1, false);
+  JX_ALLOC(bad, uint32_t, 1, true);
+  if (n) JX_LAUNCH(k_filtered_to_recs, nblk(n), 256, 0, ctx->lastf.q, ctx->lastf.s, ctx->lastf.score, n, ctx->is_self ? 1 : 0,
+                   ctx->side[0].chr_lex, ctx->side[1].chr_lex, recs, bad);
+  out->stats[0] = n;
+  // the library's own survivors are valid and pair-unique (blastfilter de-duplicates twice); a self comparison
+  // re-orients pairs (qi <= si) and can make duplicates
+  return scan_records(ctx, arena, recs, n, n, opts, out, !ctx->is_self, dev, bad);
+}
 
 // =====================================================================================================
 // synteny mcscan (src/jcvi/compara/synteny.py:1538-1652): stack the anchor blocks on a

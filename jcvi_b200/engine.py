@@ -318,6 +318,40 @@ class Engine(object):
             return r          # caller frees with free_filter()
         return FilterResult(r, self.lib, self.Gq, self.Gs, want_mothers, engine=self)   # owns and frees `r`
 
+    def pipeline(self, text, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None, want_text=True,
+                 skip_arrays=True, xdist=20, ydist=20, N=4, intrabound=300, liftover_dist=10):
+        """blastfilter -> scan -> liftover in ONE library call (jx_pipeline): the survivors and the anchors stay on the
+        device between the stages.  -> (FilterResult, ScanResult, LiftoverResult), identical to the three separate calls."""
+        p, n, dev, keep = _text_ptr(text)
+        o = C.JxFilterOpts()
+        o.strip_names = int(bool(strip_names))
+        o.cscore = float(cscore or 0.0)
+        o.tandem_nmax = int(tandem_Nmax or 0)
+        ek = None
+        if exclude_keys is not None and len(exclude_keys):
+            ek = np.unique(np.asarray(exclude_keys, dtype=np.uint64))
+            o.exclude_keys = C.ptr(ek)
+            o.n_exclude = len(ek)
+        o.want_text = int(bool(want_text))
+        o.skip_arrays = int(bool(skip_arrays))
+        so = self._scan_opts(xdist, ydist, N, intrabound)
+        fr = C.JxFilterResult(); sr = C.JxScanResult(); lr = C.JxLiftoverResult()
+        if not dev:
+            self._held_key = None                      # the library uploads (and holds) the text
+        rc = self.lib.jx_pipeline(self.ctx, p, n, dev, ctypes.byref(o), ctypes.byref(so), int(liftover_dist), ctypes.byref(fr),
+                                  ctypes.byref(sr), ctypes.byref(lr))
+        if rc != 0:
+            self.lib.jx_filter_result_free(ctypes.byref(fr))
+            self.lib.jx_scan_result_free(ctypes.byref(sr))
+            self.lib.jx_liftover_result_free(ctypes.byref(lr))
+            self._check(rc)
+        f = FilterResult(fr, self.lib, self.Gq, self.Gs, False, engine=self)
+        try:
+            s = ScanResult(sr)
+        finally:
+            self.lib.jx_scan_result_free(ctypes.byref(sr))
+        return f, s, LiftoverResult(lr, s.n_anchors, self.lib)
+
     def free_filter(self, r):
         self.lib.jx_filter_result_free(ctypes.byref(r))
 

@@ -19,6 +19,13 @@ N = 8
 for it in range(N + 3):
     if it == N + 2:
         print("---- last step ----", file=sys.stderr, flush=True)
+    if os.environ.get("PROBE_PIPELINE"):
+        t0 = time.perf_counter()
+        f, s, l = eng.pipeline(dt, want_text=bool(int(os.environ.get("PROBE_TEXT", "0"))), skip_arrays=True, liftover_dist=10)
+        t3 = time.perf_counter()
+        if it >= 3:
+            acc += [t3 - t0, 0, 0]
+        continue
     t0 = time.perf_counter()
     r = eng.blastfilter(dt, want_text=False, raw=True, skip_arrays=True)
     t1 = time.perf_counter()
