@@ -242,6 +242,48 @@ int jx_near_lines_device(jx_ctx* ctx, const char* text, int64_t nbytes, int text
                          int64_t* lines_len, int64_t* n_out);
 void jx_free(void* p);
 
+/* ---- one genome pair sharded over ranks BY CHROMOSOME PAIR (SURVEY.md 8e stages B / C) ----------------------------
+ * From the pair de-duplication on, the reference's loops are independent per (qseqid, sseqid): (qi, si) determines the
+ * pair of seqids, tandem families never leave a seqid (blastfilter.py:262-284), synteny_scan and synteny_liftover run per
+ * chromosome pair (synteny.py:444-450, 1946-1956).  Global: the per-name best score (all-reduce max, as above) and the
+ * tandem families (each owner finds the edges of its pairs, the edge lists are all-gathered, every rank runs the same
+ * union-find).  The caller moves 16-byte CANDIDATES {qi, si, float32 score bits, (global order << 1) | (evalue < 1e-10)}
+ * GPU to GPU; global order = ord_base + record index, monotone in file order over the ranks' slices, < 2^31.
+ *   jx_cscore_begin -> [all-reduce max] -> jx_shard_candidates -> [all-reduce the histogram, choose owners]
+ *   -> jx_shard_partition -> [all-to-all] -> jx_shard_pairs -> [all-gather edges] -> jx_shard_survivors
+ *   -> jx_scan_cands (per owner) ... jx_shard_near -> jx_shard_partition -> [all-to-all] -> jx_shard_lift (per owner)
+ * Device arrays returned by these calls belong to the context's session and live until jx_shard_reset. */
+int jx_shard_reset(jx_ctx* ctx);
+/* record slots of the slice jx_cscore_begin retained: ord_base of rank r = sum of the slots of the ranks before it */
+int jx_shard_slots(jx_ctx* ctx, int64_t* n_slots);
+/* candidates of this rank's slice that pass the C-score filter + their count per chromosome pair
+ * (cp = chr_lex(q) * n_chr(s) + chr_lex(s); cp_hist[n_cp] is caller-owned host memory) */
+int jx_shard_candidates(jx_ctx* ctx, double cscore, uint32_t ord_base, uint64_t* cand_dev, int64_t* n, uint32_t* cp_hist, int64_t n_cp);
+/* candidates grouped by destination rank owner[cp]: device array + counts[world] */
+int jx_shard_partition(jx_ctx* ctx, uint64_t cand_dev, int64_t n, const int32_t* owner, int64_t n_cp, int world, uint64_t* out_dev,
+                       int64_t* counts);
+/* owner: per-pair best record of the received candidates (blastfilter.py:86-89) + the tandem edges of its pairs as
+ * device arrays of (rank a, rank b) uint32 pairs, query side and subject side */
+int jx_shard_pairs(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int tandem_nmax, uint64_t* qedges_dev, int64_t* nq, uint64_t* sedges_dev,
+                   int64_t* ns);
+/* owner: ALL ranks' edges -> families, mothers (identical on every rank; copied to q_mother / s_mother when given),
+ * mother substitution and second per-pair best (blastfilter.py:240-259) -> this rank's survivors (device candidates) */
+int jx_shard_survivors(jx_ctx* ctx, uint64_t qedges_dev, int64_t nq, uint64_t sedges_dev, int64_t ns, int tandem_nmax,
+                       uint64_t* surv_dev, int64_t* n_surv, int32_t* q_mother, int32_t* s_mother);
+/* `.filtered` order (score descending, global order ascending) of a set of survivors -> host columns of `out`
+ * (line_off receives the global order) */
+int jx_shard_order(jx_ctx* ctx, uint64_t surv_dev, int64_t n, jx_filter_result* out);
+/* scan of survivors given as device candidates (the hand-over of jx_scan_filtered) */
+int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n, const jx_scan_opts* opts, jx_scan_result* out);
+/* this rank's raw records within dist of any anchor (records retained by jx_cscore_begin, or `text`):
+ * device array of {qi, si, score bits, ord_base + record index} */
+int jx_shard_near(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist, const int32_t* a_qi,
+                  const int32_t* a_si, int64_t n_anchor_lines, uint32_t ord_base, uint64_t* cand_dev, int64_t* n);
+/* owner: the near candidates received + all anchor lines (global block ids) -> jx_liftover_result for this rank's
+ * chromosome pairs (lifted pairs ordered by (block, chromosome pair, global order)) */
+int jx_shard_lift(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int64_t n_slots_total, int dist, const int32_t* a_qi, const int32_t* a_si,
+                  const int32_t* a_block, int64_t n_anchor_lines, jx_liftover_result* out);
+
 /* ---- jcvi.formats.blast cscore (src/jcvi/formats/blast.py:1098-1189) ------------
  * `cscore` has no BED: its dictionaries are keyed by whatever (gene_name-stripped) names the table
  * holds.  jx_distinct_names returns one representative raw line per distinct name of the table

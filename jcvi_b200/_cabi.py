@@ -62,7 +62,8 @@ EXPORTS = [
     "jx_scan_text", "jx_scan_points", "jx_scan_filtered", "jx_scan_result_free", "jx_liftover_text",
     "jx_liftover_result_free", "jx_nearest_anchor", "jx_text_upload", "jx_text_release", "jx_set_record_reuse", "jx_distinct_names", "jx_best_table_copy", "jx_session_counts",
     "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter", "jx_mcscan", "jx_block_stats",
-    "jx_pipeline", "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
+    "jx_pipeline", "jx_shard_reset", "jx_shard_slots", "jx_shard_candidates", "jx_shard_partition", "jx_shard_pairs",
+    "jx_shard_survivors", "jx_shard_order", "jx_scan_cands", "jx_shard_near", "jx_shard_lift", "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
 ]
 
 _lib = None
@@ -107,6 +108,20 @@ def lib():
         L.jx_pipeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(JxFilterOpts),
                                   ctypes.POINTER(JxScanOpts), ctypes.c_int, ctypes.POINTER(JxFilterResult),
                                   ctypes.POINTER(JxScanResult), ctypes.POINTER(JxLiftoverResult)]
+        L.jx_shard_reset.argtypes = [ctypes.c_void_p]
+        L.jx_shard_slots.argtypes = [ctypes.c_void_p, c_i64p]
+        L.jx_shard_candidates.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_uint32, c_u64p, c_i64p, ctypes.c_void_p, ctypes.c_int64]
+        L.jx_shard_partition.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                         c_u64p, ctypes.c_void_p]
+        L.jx_shard_pairs.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, c_u64p, c_i64p, c_u64p, c_i64p]
+        L.jx_shard_survivors.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int,
+                                         c_u64p, c_i64p, ctypes.c_void_p, ctypes.c_void_p]
+        L.jx_shard_order.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(JxFilterResult)]
+        L.jx_scan_cands.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(JxScanOpts), ctypes.POINTER(JxScanResult)]
+        L.jx_shard_near.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, c_u64p, c_i64p]
+        L.jx_shard_lift.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(JxLiftoverResult)]
         L.jx_liftover_result_free.argtypes = [ctypes.POINTER(JxLiftoverResult)]
         L.jx_liftover_result_free.restype = None
         L.jx_nearest_anchor.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,

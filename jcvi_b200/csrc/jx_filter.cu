@@ -843,4 +843,285 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
   return JX_OK;
 }
 
+
+}  // extern "C"
+
+// =====================================================================================================================
+// One genome pair sharded over ranks by CHROMOSOME PAIR (SURVEY.md 8(e) stages B / C).
+//
+// The reference's loops are independent per chromosome pair from the pair de-duplication on: (qi, si) determines the
+// pair of seqids, tandem families never leave a seqid (blastfilter.py:262-284), `synteny_scan` and `synteny_liftover`
+// run per (qseqid, sseqid) (synteny.py:444-450, 1946-1956).  What is global: the per-name best score (reduced with
+// ncclAllReduce(max) before these calls) and the tandem families (a subject gene collects evidence from every query
+// chromosome): each owner finds the tandem edges of its pairs, the edge lists are all-gathered and every rank runs the
+// same small union-find.  The caller (jcvi_b200/sharded.py) moves the 16-byte candidates GPU to GPU (all-to-all) and the
+// edge lists (all-gather); these entry points are the device work in between.
+//   jx_cscore_begin -> [all-reduce max] -> jx_shard_candidates -> [hist all-reduce, owners] -> jx_shard_partition
+//   -> [all-to-all] -> jx_shard_pairs -> [all-gather edges] -> jx_shard_survivors -> jx_shard_scan ...
+// Candidate = {qi, si, float32 score bits, (global order << 1) | (evalue < 1e-10)}; global order = ord_base + record
+// index, monotone in file order across the ranks' slices, < 2^31.
+// =====================================================================================================================
+namespace {
+__global__ void k_cp_hist(const uint4* __restrict__ C, uint32_t n, const int32_t* __restrict__ qchr, const int32_t* __restrict__ schr,
+                          uint32_t nschr, uint32_t* hist) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint4 c = C[j];
+    atomicAdd(hist + (uint32_t)qchr[c.x] * nschr + (uint32_t)schr[c.y], 1u);
+  }
+}
+__global__ void k_dest_scatter(const uint4* __restrict__ C, uint32_t n, const int32_t* __restrict__ qchr, const int32_t* __restrict__ schr,
+                               uint32_t nschr, const int32_t* __restrict__ owner, uint32_t* cursor, uint4* out) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint4 c = C[j];
+    const int32_t d = owner[(uint32_t)qchr[c.x] * nschr + (uint32_t)schr[c.y]];
+    out[atomicAdd(cursor + d, 1u)] = c;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int jx_shard_reset(jx_ctx* ctx) {
+  if (!ctx) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  for (void* p : ctx->sh.allocs) cudaFreeAsync(p, ctx->stream);
+  ctx->sh = jx_ctx::Shard();
+  return JX_OK;
+}
+
+/* record slots of the slice jx_cscore_begin retained (this rank's share of the global order range) */
+int jx_shard_slots(jx_ctx* ctx, int64_t* n_slots) {
+  if (!ctx || !n_slots) return JX_EARG;
+  if (!ctx->cache.valid) { ctx->err = "jx_shard_slots without retained records"; return JX_EARG; }
+  *n_slots = ctx->cache.n_lines;
+  return JX_OK;
+}
+
+int jx_shard_candidates(jx_ctx* ctx, double cscore, uint32_t ord_base, uint64_t* cand_dev, int64_t* n_out, uint32_t* cp_hist,
+                        int64_t n_cp) {
+  if (!ctx || !cand_dev || !n_out || !cp_hist) return JX_EARG;
+  if (!ctx->sess_open || !ctx->cache.valid) { ctx->err = "jx_shard_candidates without jx_cscore_begin"; return JX_EARG; }
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  if (n_cp != (int64_t)Q.n_chr * S.n_chr) { ctx->err = "n_cp must be n_chr(q) * n_chr(s)"; return JX_EARG; }
+  auto& c = ctx->cache;
+  const uint32_t nrec = c.n_lines;
+  if ((uint64_t)ord_base + nrec >= (1ull << 31)) { ctx->err = "more than 2^31 record slots over all ranks"; return JX_EUNSUPPORTED; }
+  const bool use_cscore = cscore != 0.0;
+  const size_t capC = (size_t)c.stats[2] + 1;
+  JX_SALLOC(C, uint4, capC, false);
+  JX_ALLOC(d_cnt, uint32_t, 2, true);
+  JX_ALLOC(d_hist, uint32_t, (size_t)n_cp + 1, true);
+  if (nrec) {
+    unsigned grid = std::min<unsigned>(nblk((nrec + 3) / 4), 148u * JX_SEL_GRID);
+    JX_ALLOC(bestq, uint32_t, (size_t)Q.G + 1, false);
+    JX_ALLOC(bests, uint32_t, (size_t)S.G + 1, false);
+    if (use_cscore) {
+      JX_LAUNCH(k_gene_best, nblk((size_t)Q.G), 256, 0, ctx->sess_best, Q.name_id, (uint32_t)Q.G, bestq);
+      JX_LAUNCH(k_gene_best, nblk((size_t)S.G), 256, 0, ctx->sess_best, S.name_id, (uint32_t)S.G, bests);
+    }
+    JX_LAUNCH(k_select, grid, 256, 0, c.recs, nrec, bestq, bests, cscore, use_cscore ? 1 : 0, ord_base, C, d_cnt, d_cnt + 1);
+  }
+  uint32_t h[2] = {0, 0};
+  JX_CK(cudaMemcpyAsync(h, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (h[1]) { ctx->err = "float division by zero"; return JX_EZERODIV; }
+  if (h[0]) JX_LAUNCH(k_cp_hist, std::min<unsigned>(nblk(h[0]), 148u * 8u), 256, 0, C, h[0], Q.chr_lex, S.chr_lex, (uint32_t)S.n_chr, d_hist);
+  JX_CK(cudaMemcpyAsync(cp_hist, d_hist, (size_t)n_cp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  ctx->sess_open = false;
+  c.valid = c.plain;          // plain records stay for the liftover stage on the same held slice
+  *cand_dev = (uint64_t)(uintptr_t)C; *n_out = h[0];
+  return JX_OK;
+}
+
+int jx_shard_partition(jx_ctx* ctx, uint64_t cand_dev, int64_t n, const int32_t* owner, int64_t n_cp, int world,
+                       uint64_t* out_dev, int64_t* counts) {
+  if (!ctx || !owner || !out_dev || !counts || world < 1 || n < 0 || n >= (1ll << 31)) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  if (n_cp != (int64_t)Q.n_chr * S.n_chr) { ctx->err = "n_cp must be n_chr(q) * n_chr(s)"; return JX_EARG; }
+  // per-destination counts from the chromosome-pair histogram (host: n_cp is small)
+  JX_ALLOC(d_hist, uint32_t, (size_t)n_cp + 1, true);
+  const uint4* C = (const uint4*)(uintptr_t)cand_dev;
+  const unsigned grid = std::max(1u, std::min<unsigned>(nblk((size_t)std::max<int64_t>(n, 1)), 148u * 8u));
+  if (n) JX_LAUNCH(k_cp_hist, grid, 256, 0, C, (uint32_t)n, Q.chr_lex, S.chr_lex, (uint32_t)S.n_chr, d_hist);
+  std::vector<uint32_t> hist((size_t)n_cp);
+  JX_CK(cudaMemcpyAsync(hist.data(), d_hist, (size_t)n_cp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> cursor((size_t)world, 0);
+  for (int64_t k = 0; k < n_cp; ++k) {
+    if (owner[k] < 0 || owner[k] >= world) { ctx->err = "owner out of range"; return JX_EARG; }
+    cursor[(size_t)owner[k]] += hist[(size_t)k];
+  }
+  uint32_t run = 0;
+  for (int d = 0; d < world; ++d) { counts[d] = cursor[(size_t)d]; const uint32_t t = cursor[(size_t)d]; cursor[(size_t)d] = run; run += t; }
+  JX_SALLOC(out, uint4, (size_t)n + 1, false);
+  JX_ALLOC(d_owner, int32_t, (size_t)n_cp + 1, false);
+  JX_ALLOC(d_cursor, uint32_t, (size_t)world, false);
+  JX_CK(cudaMemcpyAsync(d_owner, owner, (size_t)n_cp * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_CK(cudaMemcpyAsync(d_cursor, cursor.data(), (size_t)world * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n) JX_LAUNCH(k_dest_scatter, grid, 256, 0, C, (uint32_t)n, Q.chr_lex, S.chr_lex, (uint32_t)S.n_chr, d_owner, d_cursor, out);
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  *out_dev = (uint64_t)(uintptr_t)out;
+  return JX_OK;
+}
+
+// owner side, first half: per-pair best record of the received candidates + the tandem edges of this rank's pairs
+int jx_shard_pairs(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int tandem_nmax, uint64_t* qedges_dev, int64_t* nq,
+                   uint64_t* sedges_dev, int64_t* ns) {
+  if (!ctx || !qedges_dev || !nq || !sedges_dev || !ns || n < 0 || n >= (1ll << 31)) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  auto& sh = ctx->sh;
+  const uint32_t nC = (uint32_t)n;
+  sh.C = (const uint4*)(uintptr_t)recv_dev; sh.nC = nC;
+  uint32_t hcap = 1024;
+  while (hcap < 2u * nC + 16u && hcap < (1u << 31)) hcap <<= 1;
+  sh.hmask = hcap - 1u;
+  JX_SALLOC(cnt, uint32_t, 8, true);
+  JX_SALLOC(K1, unsigned long long, hcap, false);
+  JX_SALLOC(V1, unsigned long long, hcap, true);
+  JX_SALLOC(W1, uint32_t, hcap, false);
+  JX_SALLOC(Cslot, uint32_t, (size_t)nC + 1, false);
+  JX_SALLOC(win, uint8_t, (size_t)nC + 1, false);
+  JX_SALLOC(qe, uint2, (size_t)nC + 1, false);
+  JX_SALLOC(se, uint2, (size_t)nC + 1, false);
+  sh.cnt = cnt; sh.K1 = K1; sh.V1 = V1; sh.W1 = W1; sh.Cslot = Cslot; sh.win = win;
+  JX_CK(cudaMemcpyAsync(cnt, &nC, 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_CK(cudaMemsetAsync(K1, 0xFF, (size_t)hcap * 8, ctx->stream));
+  const unsigned g1 = std::max(1u, std::min<unsigned>(nblk(std::max<uint32_t>(nC, 1u)), 148u * 8u));
+  JX_LAUNCH(k_pair_insert, g1, 256, 0, sh.C, cnt, (const uint8_t*)nullptr, K1, V1, sh.hmask, Cslot);
+  JX_LAUNCH(k_pair_winner, g1, 256, 0, sh.C, cnt, (const uint8_t*)nullptr, Cslot, V1, W1, win, cnt + 5);
+  if (tandem_nmax)
+    JX_LAUNCH(k_tandem_edges, g1, 256, 0, sh.C, cnt, win, K1, W1, sh.hmask, tandem_nmax, (uint32_t)Q.G, (uint32_t)S.G, Q.chr_lex, S.chr_lex,
+              qe, se, cnt + 2);
+  uint32_t h[4] = {0, 0, 0, 0};
+  JX_CK(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  *qedges_dev = (uint64_t)(uintptr_t)qe; *nq = h[2];
+  *sedges_dev = (uint64_t)(uintptr_t)se; *ns = h[3];
+  return JX_OK;
+}
+
+// owner side, second half: ALL ranks' edges (device arrays of (a, b) rank pairs) -> the same families and mothers on
+// every rank -> mother substitution, second per-pair best -> this rank's survivors (candidates with substituted ranks)
+int jx_shard_survivors(jx_ctx* ctx, uint64_t qedges_dev, int64_t nq, uint64_t sedges_dev, int64_t ns, int tandem_nmax,
+                       uint64_t* surv_dev, int64_t* n_surv, int32_t* q_mother, int32_t* s_mother) {
+  if (!ctx || !surv_dev || !n_surv || nq < 0 || ns < 0) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  auto& sh = ctx->sh;
+  if (!sh.cnt) { ctx->err = "jx_shard_survivors without jx_shard_pairs"; return JX_EARG; }
+  int rc;
+  const uint32_t nC = sh.nC;
+  const unsigned g1 = std::max(1u, std::min<unsigned>(nblk(std::max<uint32_t>(nC, 1u)), 148u * 8u));
+  const uint4* D = sh.C; const uint8_t* fin = sh.win;
+  if (tandem_nmax) {
+    const uint32_t Gq = (uint32_t)Q.G, Gs = (uint32_t)S.G;
+    JX_SALLOC(mq0, int32_t, (size_t)Gq + 1, false);
+    sh.mq = mq0;
+    if (ctx->is_self) sh.ms = sh.mq;
+    else { JX_SALLOC(ms0, int32_t, (size_t)Gs + 1, false); sh.ms = ms0; }
+    JX_ALLOC(parent_q, uint32_t, (size_t)Gq + 1, false);
+    uint32_t* parent_s = parent_q;
+    JX_LAUNCH(k_iota, nblk(std::max(Gq, 1u)), 256, 0, parent_q, Gq);
+    if (!ctx->is_self) {
+      JX_ALLOC(ps, uint32_t, (size_t)Gs + 1, false);
+      parent_s = ps;
+      JX_LAUNCH(k_iota, nblk(std::max(Gs, 1u)), 256, 0, parent_s, Gs);
+    }
+    JX_ALLOC(d_ne, uint32_t, 2, false);
+    const uint32_t hne[2] = {(uint32_t)nq, (uint32_t)ns};
+    JX_CK(cudaMemcpyAsync(d_ne, hne, 8, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned gq = std::max(1u, std::min<unsigned>(nblk((size_t)std::max<int64_t>(nq, 1)), 148u * 8u));
+    const unsigned gs = std::max(1u, std::min<unsigned>(nblk((size_t)std::max<int64_t>(ns, 1)), 148u * 8u));
+    if (nq) JX_LAUNCH(k_apply_edges, gq, 256, 0, (const uint2*)(uintptr_t)qedges_dev, d_ne, parent_q);
+    if (ns) JX_LAUNCH(k_apply_edges, gs, 256, 0, (const uint2*)(uintptr_t)sedges_dev, d_ne + 1, parent_s);
+    auto mothers = [&](uint32_t* parent, const SideDev& Dv, int32_t* m) -> int {
+      const uint32_t G = (uint32_t)Dv.G;
+      JX_ALLOC(root, uint32_t, (size_t)G + 1, false);
+      JX_ALLOC(bk, unsigned long long, (size_t)G + 1, true);
+      JX_ALLOC(mroot, uint32_t, (size_t)G + 1, false);
+      if (G) {
+        JX_LAUNCH(k_flatten, nblk(G), 256, 0, parent, G, root);
+        JX_LAUNCH(k_mother1, nblk(G), 256, 0, root, Dv.length, Dv.lexrank, G, bk);
+        JX_LAUNCH(k_mother2, nblk(G), 256, 0, root, Dv.length, Dv.lexrank, G, bk, mroot);
+        JX_LAUNCH(k_mother3, nblk(G), 256, 0, root, mroot, G, m);
+      }
+      return JX_OK;
+    };
+    if ((rc = mothers(parent_q, Q, sh.mq))) return rc;
+    if (!ctx->is_self && (rc = mothers(parent_s, S, sh.ms))) return rc;
+    const uint32_t hcap = sh.hmask + 1u;
+    JX_ALLOC(K2, unsigned long long, hcap, false);
+    JX_ALLOC(V2, unsigned long long, hcap, true);
+    JX_SALLOC(D2, uint4, (size_t)nC + 1, false);
+    JX_ALLOC(Dslot, uint32_t, (size_t)nC + 1, false);
+    JX_ALLOC(live, uint8_t, (size_t)nC + 1, false);
+    JX_SALLOC(fin2, uint8_t, (size_t)nC + 1, false);
+    JX_CK(cudaMemsetAsync(K2, 0xFF, (size_t)hcap * 8, ctx->stream));
+    JX_LAUNCH(k_collapse_insert, g1, 256, 0, sh.C, sh.cnt, sh.win, sh.mq, sh.ms, ctx->q_same_s, K2, V2, sh.hmask, D2, Dslot, live);
+    JX_LAUNCH(k_pair_winner, g1, 256, 0, D2, sh.cnt, live, Dslot, V2, (uint32_t*)nullptr, fin2, (uint32_t*)nullptr);
+    D = D2; fin = fin2;
+    if (q_mother && Gq) JX_CK(cudaMemcpyAsync(q_mother, sh.mq, (size_t)Gq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (s_mother && Gs) JX_CK(cudaMemcpyAsync(s_mother, sh.ms, (size_t)Gs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  JX_SALLOC(F, uint4, (size_t)nC + 1, false);
+  JX_ALLOC(okeys, unsigned long long, (size_t)nC + 1, false);
+  JX_ALLOC(ovals, uint32_t, (size_t)nC + 1, false);
+  JX_LAUNCH(k_final_emit, g1, 256, 0, D, sh.cnt, fin, F, okeys, ovals, sh.cnt + 4);
+  uint32_t h5[5] = {0, 0, 0, 0, 0};
+  JX_CK(cudaMemcpyAsync(h5, sh.cnt, 20, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  *surv_dev = (uint64_t)(uintptr_t)F; *n_surv = h5[4];
+  return JX_OK;
+}
+
+// `.filtered` order of a set of survivors (any rank's, or the concatenation of all): score descending, order ascending
+// -> host columns; line_off receives the global order of each survivor (the byte offset lives on its source rank)
+int jx_shard_order(jx_ctx* ctx, uint64_t surv_dev, int64_t n, jx_filter_result* out) {
+  if (!ctx || !out || n < 0 || n >= (1ll << 31)) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const uint32_t nF = (uint32_t)n;
+  out->n = nF;
+  out->q_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
+  out->s_rank = (int32_t*)malloc(sizeof(int32_t) * (nF + 1));
+  out->score = (float*)malloc(sizeof(float) * (nF + 1));
+  out->line_off = (uint64_t*)malloc(sizeof(uint64_t) * (nF + 1));
+  if (!nF) return JX_OK;
+  const uint4* F = (const uint4*)(uintptr_t)surv_dev;
+  JX_ALLOC(cnt, uint32_t, 2, true);
+  JX_ALLOC(all, uint8_t, nF, false);
+  JX_CK(cudaMemsetAsync(all, 1, nF, ctx->stream));
+  JX_CK(cudaMemcpyAsync(cnt, &nF, 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_ALLOC(F2, uint4, nF, false);
+  JX_ALLOC(okeys, uint64_t, nF, false);
+  JX_ALLOC(ovals, uint32_t, nF, false);
+  JX_LAUNCH(k_final_emit, std::min<unsigned>(nblk(nF), 148u * 8u), 256, 0, F, cnt, all, F2, (unsigned long long*)okeys, ovals, cnt + 1);
+  uint64_t* ok = okeys; uint32_t* ov = ovals;
+  int rc;
+  if ((rc = jx_sort_pairs(ctx, arena, ok, ov, nF, 0, 64))) return rc;
+  std::vector<uint4> h(nF); std::vector<uint32_t> ord(nF);
+  JX_CK(cudaMemcpyAsync(h.data(), F2, (size_t)nF * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(ord.data(), ov, (size_t)nF * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t t = 0; t < nF; ++t) {
+    const uint4 c = h[ord[t]];
+    out->q_rank[t] = (int32_t)c.x; out->s_rank[t] = (int32_t)c.y;
+    memcpy(&out->score[t], &c.z, 4);
+    out->line_off[t] = c.w >> 1;
+  }
+  return JX_OK;
+}
+
 }  // extern "C"

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -90,6 +91,15 @@ struct jx_ctx {
   struct LastFilter { int32_t* q = nullptr; int32_t* s = nullptr; float* score = nullptr; size_t cap = 0; int64_t n = 0; int64_t token = 0; } lastf;
   int64_t token_counter = 0;
   uint32_t* sess_best = nullptr; size_t sess_best_cap = 0;   // jx_cscore_begin/finish session
+  // one genome pair sharded over ranks (jx_shard_*): device state that lives from one stage call to the next
+  struct Shard {
+    std::vector<void*> allocs;                         // stream-ordered allocations of this session
+    const uint4* C = nullptr; uint32_t nC = 0;         // owner side: the candidates received for this rank's chromosome pairs
+    uint32_t* cnt = nullptr;                           // device counters
+    unsigned long long *K1 = nullptr, *V1 = nullptr; uint32_t* W1 = nullptr; uint32_t hmask = 0;
+    uint32_t* Cslot = nullptr; uint8_t* win = nullptr;
+    int32_t *mq = nullptr, *ms = nullptr;              // mother maps (identical on every rank)
+  } sh;
   bool sess_open = false;
   uint8_t* lines_dev = nullptr;  // grow-only device buffer of the last jx_*_device result (packed raw lines)
   size_t lines_dev_cap = 0;
@@ -187,6 +197,23 @@ inline int jx_pin_scan(jx_ctx* ctx, size_t bytes, char** out) {
   *out = ctx->pin_scan;
   return JX_OK;
 }
+
+// session memory of the sharded stages: stream-ordered, released by jx_shard_reset / the next session
+template <class T>
+inline T* jx_shard_alloc(jx_ctx* ctx, size_t n, bool zero = false) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  if (cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ctx->sh.allocs.push_back(p);
+  if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+  return (T*)p;
+}
+#define JX_SALLOC(var, T, n, zero)                                                          \
+  T* var = jx_shard_alloc<T>(ctx, (n), (zero));                                             \
+  if (!var) {                                                                               \
+    ctx->err = "device allocation failed: " #var;                                           \
+    return JX_ECUDA;                                                                        \
+  }
 
 #define JX_LAUNCH(kernel, grid, block, smem, ...)                                           \
   do {                                                                                      \

@@ -719,15 +719,54 @@ __global__ void k_lift_emit(const uint8_t* state, const uint32_t* nh_p, const ui
 }
 }  // namespace
 
+// the anchor side of a liftover: anchors sorted by (qi, si) with a row pointer per query rank, the occupancy bitmap of
+// the cells within `dist` of an anchor, device counters (0 anchors in the BED, 1 rank out of range, 2 duplicate,
+// 3 candidates, 4 unique hits, 5 lifted, 6 ambiguous, 7 emitted)
+struct LoAnchors {
+  int sb = 0, qb = 0, cshift = 4, dist_pre = 1;
+  uint32_t nqc = 0, nsc = 0, na = 0;
+  uint64_t* aks = nullptr; uint32_t* dablock = nullptr; uint32_t* rowptr = nullptr; uint32_t* bitmap = nullptr; uint32_t* d_cnt = nullptr;
+};
+static int lo_anchors(jx_ctx* ctx, Arena& arena, int dist, const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
+                      LoAnchors& L) {
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  int rc;
+  L.sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)); L.qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
+  const int sb = L.sb, kb = L.sb + L.qb;
+  JX_ALLOC(d_cnt, uint32_t, 12, true);
+  JX_ALLOC(akey, uint64_t, (size_t)nal + 1, false);
+  JX_ALLOC(aord, uint32_t, (size_t)nal + 1, false);
+  JX_LAUNCH(k_anchor_keys, nblk(std::max(nal, 1u)), 256, 0, daq, das, nal, sb, kb, (uint32_t)Q.G, (uint32_t)S.G, akey, aord, d_cnt);
+  uint64_t* aks = akey; uint32_t* aos = aord;
+  if (nal && (rc = jx_sort_pairs(ctx, arena, aks, aos, nal, 0, kb + 1))) return rc;
+  JX_ALLOC(dablock, uint32_t, (size_t)nal + 1, false);
+  JX_LAUNCH(k_anchor_blocks2, nblk(std::max(nal, 1u)), 256, 0, aks, aos, dab, d_cnt, dablock, d_cnt + 2);
+  JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
+  JX_LAUNCH(k_rowptr2, nblk((size_t)Q.G + 1), 256, 0, aks, d_cnt, sb, (uint32_t)Q.G, rowptr);
+  int cshift = 4;                                          // 16 x 16 rank cells, coarser for huge genomes
+  while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
+  L.cshift = cshift;
+  L.nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1; L.nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
+  const size_t nwords = (size_t)(((uint64_t)L.nqc * L.nsc + 31) >> 5);
+  JX_ALLOC(bitmap, uint32_t, nwords, true);
+  // the prefilter keeps records at distance 0 from an anchor even when dist == 0 (`scan --dist=1 --liftover`
+  // gives liftover_dist 0): AnchorFile.filter_blocks needs the anchors' own raw pairs; lifting stays `< dist`
+  L.dist_pre = std::max(dist, 1);
+  JX_LAUNCH(k_mark_cells2, nblk(std::max(nal, 1u)), 256, 0, aks, d_cnt, sb, L.dist_pre, cshift, L.nsc, L.nqc, bitmap);
+  L.aks = aks; L.dablock = dablock; L.rowptr = rowptr; L.bitmap = bitmap; L.d_cnt = d_cnt;
+  return JX_OK;
+}
+static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uint32_t nC0, uint32_t n_lines, int dist,
+                   const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
+                   const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out);
+
 // liftover on device-resident records and anchors.  d_aq / d_as / d_ablock: per anchor LINE (file order; -1 = name not
 // in the BED).  h_*: the same on the host when the caller has them (only the rare tie walk needs them; null: copied back).
 int jx_liftover_core(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t n_lines, const unsigned long long* tstats, int dist,
                      const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
                      const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out) {
-  const SideDev& Q = ctx->side[0];
-  const SideDev& S = ctx->side[1];
   int rc;
-  const int sb = jx_bits((uint64_t)std::max<int64_t>(S.G, 1)), qb = jx_bits((uint64_t)std::max<int64_t>(Q.G, 1));
   out->stats[0] = (int64_t)(tstats[0] - tstats[1]);
   out->stats[5] = (int64_t)tstats[1];
   out->stats[1] = (int64_t)tstats[2];        // mapped raw records (before pair de-duplication)
@@ -739,48 +778,44 @@ int jx_liftover_core(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t n_li
     out->n_lifted = n;
   };
   if (!nal || !tstats[2]) { alloc_out(0); JX_CK(cudaStreamSynchronize(ctx->stream)); return JX_OK; }
-
-  // ---- anchors sorted by (qi, si); duplicates = read_anchors' assert ------------------------------------------------------
-  // counters: 0 anchors in the BED, 1 rank out of range, 2 duplicate, 3 candidates (cells), 4 unique hits, 5 lifted, 6 ambiguous, 7 emitted
-  JX_ALLOC(d_cnt, uint32_t, 12, true);
-  const int kb = sb + qb;
-  JX_ALLOC(akey, uint64_t, nal, false);
-  JX_ALLOC(aord, uint32_t, nal, false);
-  JX_LAUNCH(k_anchor_keys, nblk(nal), 256, 0, daq, das, nal, sb, kb, (uint32_t)Q.G, (uint32_t)S.G, akey, aord, d_cnt);
-  uint64_t* aks = akey; uint32_t* aos = aord;
-  if ((rc = jx_sort_pairs(ctx, arena, aks, aos, nal, 0, kb + 1))) return rc;
-  JX_ALLOC(dablock, uint32_t, nal, false);
-  JX_LAUNCH(k_anchor_blocks2, nblk(nal), 256, 0, aks, aos, dab, d_cnt, dablock, d_cnt + 2);
-  JX_ALLOC(rowptr, uint32_t, (size_t)Q.G + 2, false);
-  JX_LAUNCH(k_rowptr2, nblk((size_t)Q.G + 1), 256, 0, aks, d_cnt, sb, (uint32_t)Q.G, rowptr);
+  LoAnchors L;
+  if ((rc = lo_anchors(ctx, arena, dist, daq, das, dab, nal, L))) return rc;
   JX_TRACE("lo: anchors sorted");
-
   // ---- raw records -> candidates near an anchor -> unique (qi,si), first occurrence ------------------------
-  int cshift = 4;                                          // 16 x 16 rank cells, coarser for huge genomes
-  while ((((uint64_t)Q.G >> cshift) + 1) * (((uint64_t)S.G >> cshift) + 1) > (1ull << 31)) ++cshift;
-  const uint32_t nqc = (uint32_t)((uint64_t)Q.G >> cshift) + 1, nsc = (uint32_t)((uint64_t)S.G >> cshift) + 1;
-  const size_t nwords = (size_t)(((uint64_t)nqc * nsc + 31) >> 5);
-  JX_ALLOC(bitmap, uint32_t, nwords, true);
-  // the prefilter keeps records at distance 0 from an anchor even when dist == 0 (`scan --dist=1 --liftover`
-  // gives liftover_dist 0): AnchorFile.filter_blocks needs the anchors' own raw pairs; lifting stays `< dist`
-  const int dist_pre = std::max(dist, 1);
-  JX_LAUNCH(k_mark_cells2, nblk(nal), 256, 0, aks, d_cnt, sb, dist_pre, cshift, nsc, nqc, bitmap);
   const size_t capC = (size_t)tstats[2] + 1;
   JX_ALLOC(C0, uint4, capC, false);
   if (n_lines) {
     unsigned grid = std::min<unsigned>(nblk((n_lines + 3) / 4), 148u * 8u);
-    JX_LAUNCH(k_select_cell2, grid, 256, 0, recs, n_lines, bitmap, cshift, nsc, C0, d_cnt + 3);
+    JX_LAUNCH(k_select_cell2, grid, 256, 0, recs, n_lines, L.bitmap, L.cshift, L.nsc, C0, L.d_cnt + 3);
   }
   uint32_t h4[4] = {0, 0, 0, 0};
-  JX_CK(cudaMemcpyAsync(h4, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaMemcpyAsync(h4, L.d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
   JX_CK(cudaStreamSynchronize(ctx->stream));
   if (h4[1]) { ctx->err = "anchor rank out of range"; return JX_EARG; }
   if (h4[2]) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
-  const uint32_t na = h4[0], nC0 = h4[3];
-  out->stats[2] = na;
+  L.na = h4[0];
+  out->stats[2] = L.na;
   JX_TRACE("lo: select_cell");
-  if (!na || !nC0) { alloc_out(0); return JX_OK; }
+  if (!L.na || !h4[3]) { alloc_out(0); return JX_OK; }
+  return lo_back(ctx, arena, L, C0, h4[3], n_lines, dist, daq, das, dab, nal, h_aq, h_as, h_ablock, out);
+}
 
+// candidates C0[0 .. nC0) = {qi, si, score bits, order} (order: file-order key, < n_lines) -> the liftover result
+static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uint32_t nC0, uint32_t n_lines, int dist,
+                   const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
+                   const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out) {
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  int rc;
+  const int sb = L.sb;
+  uint64_t* const aks = L.aks; uint32_t* const dablock = L.dablock; uint32_t* const rowptr = L.rowptr; uint32_t* const d_cnt = L.d_cnt;
+  const int dist_pre = L.dist_pre;
+  auto alloc_out = [&](uint32_t n) {
+    out->q_rank = (int32_t*)malloc(4 * ((size_t)n + 1)); out->s_rank = (int32_t*)malloc(4 * ((size_t)n + 1));
+    out->score = (float*)malloc(4 * ((size_t)n + 1)); out->block = (int32_t*)malloc(4 * ((size_t)n + 1));
+    out->n_lifted = n;
+  };
+  JX_CK(cudaMemcpyAsync(d_cnt + 3, &nC0, 4, cudaMemcpyHostToDevice, ctx->stream));
   uint32_t hcap = 1024;
   while (hcap < 2u * nC0 + 16u && hcap < (1u << 31)) hcap <<= 1;
   const uint32_t hmask = hcap - 1u;
@@ -1050,6 +1085,135 @@ int jx_nearest_anchor(jx_ctx* ctx, const int64_t* points_xy, int64_t n_points, c
     if (dist_out) dist_out[i] = dd[(size_t)i];
   }
   return JX_OK;
+}
+
+}  // extern "C"
+
+// ---- liftover of one genome pair sharded over ranks (see jx_filter.cu: jx_shard_*) -------------------------------------
+// Every rank tests ITS raw records against ALL anchors (the anchors are small and every rank has them), keeps the ones
+// within `dist` of an anchor and sends them to the owner of their chromosome pair (jx_shard_partition + all-to-all); the
+// owner runs the rest of liftover on what it receives.
+namespace {
+__global__ void k_near_emit(const uint4* __restrict__ cand, const uint32_t* __restrict__ n_p, int sb, const uint64_t* __restrict__ akey,
+                            const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
+                            const int32_t* __restrict__ schr, int dist, uint32_t ord_base, uint4* out, uint32_t* counter) {
+  const uint32_t n = *n_p;
+  const uint32_t nround = (n + 31u) & ~31u;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+    uint4 r = make_uint4(0, 0, 0, 0);
+    bool keep = false;
+    if (t < n) {
+      r = cand[t];
+      keep = anchor_within((int32_t)r.x, (int32_t)r.y, sb, akey, rowptr, qbeg, qend, schr, dist);
+    }
+    const uint32_t slot = warp_append(keep, counter);
+    if (keep) { r.w += ord_base; out[slot] = r; }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// this rank's raw records (of the slice jx_cscore_begin tokenized, or `text` when given) within dist of an anchor:
+// device array of {qi, si, score bits, ord_base + record index} + count
+int jx_shard_near(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist, const int32_t* a_qi,
+                  const int32_t* a_si, int64_t nal64, uint32_t ord_base, uint64_t* cand_dev, int64_t* n_out) {
+  if (!ctx || !cand_dev || !n_out || nal64 < 0 || nal64 >= (1ll << 31) || dist < 0) return JX_EARG;
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const SideDev& Q = ctx->side[0];
+  const SideDev& S = ctx->side[1];
+  const uint32_t nal = (uint32_t)nal64;
+  int rc;
+  *cand_dev = 0; *n_out = 0;
+  const uint4* recs = nullptr; uint32_t n_lines = 0;
+  unsigned long long tstats[12];
+  {
+    auto& c = ctx->cache;                   // records of the same held slice (jx_cscore_begin), one-shot
+    if (c.valid && c.plain && (!text || (text_on_device && (const uint8_t*)text == c.text && nbytes == c.nbytes)) &&
+        (strip_names != 0) == (c.strip != 0) && !ctx->is_self) {
+      recs = c.recs; n_lines = c.n_lines;
+      memcpy(tstats, c.stats, sizeof tstats);
+      c.valid = false;
+    } else {
+      if (!text) { ctx->err = "jx_shard_near: no retained records and no text"; return JX_EARG; }
+      TokMode mode;
+      mode.strip = strip_names;
+      mode.neardiag = ctx->is_self ? 1 : 0;
+      TokOut tok;
+      if ((rc = jx_run_tokenizer(ctx, arena, text, nbytes, text_on_device, mode, tok))) return rc;
+      recs = tok.recs; n_lines = tok.n_lines;
+      memcpy(tstats, tok.stats, sizeof tstats);
+    }
+  }
+  if ((uint64_t)ord_base + n_lines >= (1ull << 31)) { ctx->err = "more than 2^31 record slots over all ranks"; return JX_EUNSUPPORTED; }
+  if (!nal || !tstats[2]) return JX_OK;
+  JX_ALLOC(daq, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(das, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(dab, uint32_t, (size_t)nal + 1, true);
+  JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LoAnchors L;
+  if ((rc = lo_anchors(ctx, arena, dist, daq, das, dab, nal, L))) return rc;
+  const size_t capC = (size_t)tstats[2] + 1;
+  JX_ALLOC(C0, uint4, capC, false);
+  if (n_lines) {
+    unsigned grid = std::min<unsigned>(nblk((n_lines + 3) / 4), 148u * 8u);
+    JX_LAUNCH(k_select_cell2, grid, 256, 0, recs, n_lines, L.bitmap, L.cshift, L.nsc, C0, L.d_cnt + 3);
+  }
+  uint32_t h4[4] = {0, 0, 0, 0};
+  JX_CK(cudaMemcpyAsync(h4, L.d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (h4[1]) { ctx->err = "anchor rank out of range"; return JX_EARG; }
+  if (!h4[0] || !h4[3]) return JX_OK;
+  JX_SALLOC(out, uint4, (size_t)h4[3] + 1, false);
+  JX_LAUNCH(k_near_emit, std::max(1u, std::min<unsigned>(nblk(h4[3]), 148u * 8u)), 256, 0, C0, L.d_cnt + 3, L.sb, L.aks, L.rowptr,
+            Q.chr_begin, Q.chr_end, S.chr_lex, L.dist_pre, ord_base, out, L.d_cnt + 7);
+  uint32_t nn = 0;
+  JX_CK(cudaMemcpyAsync(&nn, L.d_cnt + 7, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  *cand_dev = (uint64_t)(uintptr_t)out; *n_out = nn;
+  return JX_OK;
+}
+
+// owner side: the near candidates received for this rank's chromosome pairs + all anchor lines (ranks and GLOBAL block
+// ids) -> lifted pairs ordered by (block, chromosome pair, global order), accepted / raw score for the anchor lines whose
+// pair this rank received.  n_slots_total = upper bound of the global order values.
+int jx_shard_lift(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int64_t n_slots_total, int dist, const int32_t* a_qi, const int32_t* a_si,
+                  const int32_t* a_block, int64_t nal64, jx_liftover_result* out) {
+  if (!ctx || !out || n < 0 || n >= (1ll << 31) || nal64 < 0 || nal64 >= (1ll << 31) || n_slots_total < 0 || n_slots_total >= (1ll << 31))
+    return JX_EARG;
+  memset(out, 0, sizeof *out);
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const uint32_t nal = (uint32_t)nal64;
+  int rc;
+  out->accepted = (uint8_t*)calloc((size_t)nal + 1, 1);
+  out->raw_score = (float*)calloc((size_t)nal + 1, sizeof(float));
+  auto alloc_out = [&](uint32_t k) {
+    out->q_rank = (int32_t*)malloc(4 * ((size_t)k + 1)); out->s_rank = (int32_t*)malloc(4 * ((size_t)k + 1));
+    out->score = (float*)malloc(4 * ((size_t)k + 1)); out->block = (int32_t*)malloc(4 * ((size_t)k + 1));
+    out->n_lifted = k;
+  };
+  if (!nal || !n) { alloc_out(0); return JX_OK; }
+  JX_ALLOC(daq, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(das, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(dab, uint32_t, (size_t)nal + 1, false);
+  JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  JX_CK(cudaMemcpyAsync(dab, a_block, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LoAnchors L;
+  if ((rc = lo_anchors(ctx, arena, dist, daq, das, dab, nal, L))) return rc;
+  uint32_t h3[3] = {0, 0, 0};
+  JX_CK(cudaMemcpyAsync(h3, L.d_cnt, 12, cudaMemcpyDeviceToHost, ctx->stream));
+  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (h3[1]) { ctx->err = "anchor rank out of range"; return JX_EARG; }
+  if (h3[2]) { ctx->err = "duplicate anchors"; return JX_EDUPANCHOR; }
+  L.na = h3[0];
+  out->stats[2] = L.na;
+  if (!L.na) { alloc_out(0); return JX_OK; }
+  return lo_back(ctx, arena, L, (const uint4*)(uintptr_t)recv_dev, (uint32_t)n, (uint32_t)n_slots_total, dist, daq, das, dab, nal, a_qi,
+                 a_si, a_block, out);
 }
 
 }  // extern "C"

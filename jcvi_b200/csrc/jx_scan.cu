@@ -526,6 +526,41 @@ int jx_scan_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, const floa
 
 }  // extern "C"
 
+namespace {
+__global__ void k_cands_to_recs(const uint4* __restrict__ F, uint32_t n, int is_self, const int32_t* qchr, const int32_t* schr,
+                                uint4* recs, uint32_t* bad) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint4 c = F[t];
+  int32_t qi = (int32_t)c.x, si = (int32_t)c.y;
+  float r;
+  if (!jx::round3g_f32(__uint_as_float(c.z), r)) { atomicExch(bad, 1u); r = __uint_as_float(c.z); }   // "%.3g" text round trip
+  uint4 rec = make_uint4((uint32_t)qi, (uint32_t)si, __float_as_uint(r), 0u);
+  if (is_self) {                                   // read_blast, synteny.py:274-283
+    if (qi > si) { rec.x = (uint32_t)si; rec.y = (uint32_t)qi; int32_t tmp = qi; qi = si; si = tmp; }
+    if (qchr[qi] == schr[si] && si - qi < 40) rec.x = JX_NOREC;
+  }
+  recs[t] = rec;
+}
+}  // namespace
+
+// scan of a set of survivors given as device candidates {qi, si, score bits, ..} (a rank's share of a sharded pair, or
+// all of them): the same hand-over as jx_scan_filtered
+extern "C" int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n64, const jx_scan_opts* opts, jx_scan_result* out) {
+  if (!ctx || !opts || !out || n64 < 0 || n64 >= (1ll << 31)) return JX_EARG;
+  memset(out, 0, sizeof *out);
+  if (!ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
+  cudaSetDevice(ctx->device);
+  Arena arena(ctx);
+  const uint32_t n = (uint32_t)n64;
+  JX_ALLOC(recs, uint4, (size_t)n + 1, false);
+  JX_ALLOC(bad, uint32_t, 1, true);
+  if (n) JX_LAUNCH(k_cands_to_recs, nblk(n), 256, 0, (const uint4*)(uintptr_t)surv_dev, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
+                   ctx->side[1].chr_lex, recs, bad);
+  out->stats[0] = n;
+  return scan_records(ctx, arena, recs, n, n, opts, out, !ctx->is_self, nullptr, bad);
+}
+
 // the in-memory hand-over of the LAST jx_blastfilter's survivors (still on the device) to scan: equivalent to writing
 // `.filtered` with "%.3g" scores (cblast.pyx:17) and reading it back with read_blast
 int jx_scan_survivors(jx_ctx* ctx, Arena& arena, const jx_scan_opts* opts, jx_scan_result* out, ScanDev* dev) {

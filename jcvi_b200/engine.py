@@ -490,6 +490,111 @@ class Engine(object):
                                            len(a_qi), ctypes.byref(buf), ctypes.byref(ln), ctypes.byref(cnt)))
         return self._take_lines(buf, ln), cnt.value
 
+    # ---- one genome pair sharded by chromosome pair (jcvi_b200/sharded.py drives these) -----------------------------
+    def _dev_records(self, ptr, n):
+        """torch int32 [n, 4] view of n 16-byte device records of the context's session (valid until shard_reset)."""
+        import torch
+
+        class _Dev(object):
+            pass
+        if not n:
+            return torch.empty((0, 4), dtype=torch.int32, device="cuda:%d" % self.device)
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (int(n), 4), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(d, device="cuda:%d" % self.device)
+
+    def shard_reset(self):
+        self._check(self.lib.jx_shard_reset(self.ctx))
+
+    def shard_slots(self):
+        n = ctypes.c_int64()
+        self._check(self.lib.jx_shard_slots(self.ctx, ctypes.byref(n)))
+        return n.value
+
+    def shard_candidates(self, cscore, ord_base, n_cp):
+        """-> (int32 [n, 4] device candidates, uint32 histogram per chromosome pair)"""
+        hist = np.zeros(max(int(n_cp), 1), dtype=np.uint32)
+        ptr = ctypes.c_uint64(); n = ctypes.c_int64()
+        self._check(self.lib.jx_shard_candidates(self.ctx, float(cscore or 0.0), int(ord_base), ctypes.byref(ptr), ctypes.byref(n),
+                                                 C.ptr(hist), int(n_cp)))
+        return self._dev_records(ptr.value, n.value), hist[:n_cp]
+
+    def shard_partition(self, cand, owner, world):
+        """candidates grouped by destination rank -> (int32 [n, 4] device array, int64 counts[world])"""
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        counts = np.zeros(int(world), dtype=np.int64)
+        out = ctypes.c_uint64()
+        self._check(self.lib.jx_shard_partition(self.ctx, int(cand.data_ptr()) if cand.numel() else 0, int(cand.shape[0]), C.ptr(owner),
+                                                len(owner), int(world), ctypes.byref(out), C.ptr(counts)))
+        return self._dev_records(out.value, cand.shape[0]), counts
+
+    def _dev_pairs(self, ptr, n):
+        import torch
+
+        class _Dev(object):
+            pass
+        if not n:
+            return torch.empty((0, 2), dtype=torch.int32, device="cuda:%d" % self.device)
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (int(n), 2), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(d, device="cuda:%d" % self.device)
+
+    def shard_pairs(self, recv, tandem_Nmax):
+        """-> (query-side edges, subject-side edges): int32 [n, 2] device arrays of gene ranks"""
+        q = ctypes.c_uint64(); nq = ctypes.c_int64(); s = ctypes.c_uint64(); ns = ctypes.c_int64()
+        self._keep_recv = recv
+        self._check(self.lib.jx_shard_pairs(self.ctx, int(recv.data_ptr()) if recv.numel() else 0, int(recv.shape[0]), int(tandem_Nmax or 0),
+                                            ctypes.byref(q), ctypes.byref(nq), ctypes.byref(s), ctypes.byref(ns)))
+        return self._dev_pairs(q.value, nq.value), self._dev_pairs(s.value, ns.value)
+
+    def shard_survivors(self, qedges, sedges, tandem_Nmax, want_mothers=False):
+        """all ranks' edges -> (this rank's survivors: int32 [n, 4] device candidates, q_mother, s_mother)"""
+        out = ctypes.c_uint64(); n = ctypes.c_int64()
+        mq = np.zeros(max(self.Gq, 1), dtype=np.int32) if want_mothers else None
+        ms = np.zeros(max(self.Gs, 1), dtype=np.int32) if want_mothers else None
+        self._check(self.lib.jx_shard_survivors(self.ctx, int(qedges.data_ptr()) if qedges.numel() else 0, int(qedges.shape[0]),
+                                                int(sedges.data_ptr()) if sedges.numel() else 0, int(sedges.shape[0]), int(tandem_Nmax or 0),
+                                                ctypes.byref(out), ctypes.byref(n), C.ptr(mq), C.ptr(ms)))
+        return self._dev_records(out.value, n.value), mq, ms
+
+    def shard_order(self, surv):
+        r = C.JxFilterResult()
+        rc = self.lib.jx_shard_order(self.ctx, int(surv.data_ptr()) if surv.numel() else 0, int(surv.shape[0]), ctypes.byref(r))
+        if rc != 0:
+            self.lib.jx_filter_result_free(ctypes.byref(r))
+            self._check(rc)
+        return FilterResult(r, self.lib, self.Gq, self.Gs, False, engine=self)
+
+    def scan_cands(self, surv, xdist=20, ydist=20, N=4, intrabound=300):
+        o = self._scan_opts(xdist, ydist, N, intrabound)
+        r = C.JxScanResult()
+        rc = self.lib.jx_scan_cands(self.ctx, int(surv.data_ptr()) if surv.numel() else 0, int(surv.shape[0]), ctypes.byref(o), ctypes.byref(r))
+        try:
+            self._check(rc)
+            return ScanResult(r)
+        finally:
+            self.lib.jx_scan_result_free(ctypes.byref(r))
+
+    def shard_near(self, a_qi, a_si, ord_base, strip_names=True, dist=10, text=None):
+        """this rank's raw records within dist of an anchor -> int32 [n, 4] device candidates"""
+        a_qi = np.ascontiguousarray(a_qi, dtype=np.int32); a_si = np.ascontiguousarray(a_si, dtype=np.int32)
+        p, nb, dev, keep = _text_ptr(text) if text is not None else (None, 0, 1, None)
+        ptr = ctypes.c_uint64(); n = ctypes.c_int64()
+        self._check(self.lib.jx_shard_near(self.ctx, p, nb, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si), len(a_qi),
+                                           int(ord_base), ctypes.byref(ptr), ctypes.byref(n)))
+        return self._dev_records(ptr.value, n.value)
+
+    def shard_lift(self, recv, n_slots_total, a_qi, a_si, a_block, dist=10):
+        a_qi = np.ascontiguousarray(a_qi, dtype=np.int32); a_si = np.ascontiguousarray(a_si, dtype=np.int32)
+        a_block = np.ascontiguousarray(a_block, dtype=np.int32)
+        r = C.JxLiftoverResult()
+        rc = self.lib.jx_shard_lift(self.ctx, int(recv.data_ptr()) if recv.numel() else 0, int(recv.shape[0]), int(n_slots_total), int(dist),
+                                    C.ptr(a_qi), C.ptr(a_si), C.ptr(a_block), len(a_qi), ctypes.byref(r))
+        if rc != 0:
+            self.lib.jx_liftover_result_free(ctypes.byref(r))
+            self._check(rc)
+        return LiftoverResult(r, len(a_qi), self.lib)
+
     def mcscan(self, start, end, score, block_id, max_iter, pair_gene, pair_partner, pair_block, n_genes, n_blocks):
         """jx_mcscan -> (tracks: list of block-id lists in chain order, chain scores, table[n_genes, n_tracks] of partner ids, -1 = '.')."""
         start = np.ascontiguousarray(start, dtype=np.float64); end = np.ascontiguousarray(end, dtype=np.float64)

@@ -1,0 +1,44 @@
+"""Chromosome-pair sharding of one genome pair (jcvi_b200.sharded.run_sharded): all ranks emulated in one process on one
+GPU (LocalComm: the collectives are tensor copies), every exchange and owner-side stage exercised; results must equal
+the single-GPU jx_pipeline arrays."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case,world", [("pair", 3), ("polyploid", 4), ("pair", 1), ("no_tandem", 2)])
+def test_sharded_equals_single_gpu(tmp_path, case, world):
+    from jcvi_b200 import sharded, synth
+    from jcvi_b200.engine import Engine, get_engine
+    from jcvi_b200.formats.bed import Bed
+    kw = dict(pair=dict(Gq=8000, Gs=7500, n=300000, Kq=13, Ks=12), polyploid=dict(Gq=9000, Gs=3000, n=250000, Kq=21, Ks=7),
+              no_tandem=dict(Gq=5000, Gs=5000, n=150000, Kq=7, Ks=9))[case]
+    qbed, sbed, last = synth.write_dataset(str(tmp_path), "A", "B", 91, kw["Gq"], kw["Gs"], kw["n"], Kq=kw["Kq"], Ks=kw["Ks"])
+    qb, sb = Bed(qbed), Bed(sbed)
+    text = np.fromfile(last, dtype=np.uint8)
+    opts = dict(cscore=0.5 if case == "polyploid" else 0.7, tandem_Nmax=0 if case == "no_tandem" else 10)
+    scan_kw = dict(N=3 if case == "polyploid" else 4, xdist=10 if case == "polyploid" else 20, ydist=10 if case == "polyploid" else 20)
+    dist = 15 if case == "polyploid" else 10
+    e0 = get_engine()
+    e0.load_pair(qb, sb, False)
+    f0, s0, l0 = e0.pipeline(text, want_text=False, skip_arrays=False, liftover_dist=dist, **opts, **scan_kw)
+    assert s0.n_anchors > 100 and l0.n_lifted > 10
+    engines = [Engine(0) for _ in range(world)]
+    slices = []
+    for r in range(world):
+        lo, hi = sharded.slice_bounds(text, r, world)
+        slices.append(text[lo:hi])
+    res = sharded.run_sharded(slices, qb, sb, comm=sharded.LocalComm(world), engines=engines, liftover_dist=dist, **opts, **scan_kw)
+    f = res.filtered
+    assert f.n == f0.n
+    assert np.array_equal(f.q_rank, f0.q_rank) and np.array_equal(f.s_rank, f0.s_rank) and np.array_equal(f.score, f0.score)
+    s = res.scan
+    assert np.array_equal(s.q_rank, s0.q_rank) and np.array_equal(s.s_rank, s0.s_rank) and np.array_equal(s.score, s0.score)
+    assert np.array_equal(s.block_start, s0.block_start)
+    l = res.lifted
+    for name in ("q_rank", "s_rank", "score", "block", "accepted", "raw_score"):
+        assert np.array_equal(getattr(l, name), getattr(l0, name)), name
+    for e in engines:
+        e.shard_reset()
+        e.close()
