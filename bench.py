@@ -132,6 +132,132 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+# ---- strong scaling: ONE genome pair sharded by chromosome pair over the ranks (BASELINE configs[2] and [4]) -----------
+SS_CHUNKS = 8
+SS_CONFIGS = {
+    # name: (genes q, chromosomes q, genes s, chromosomes s, options)
+    "c3": dict(Gq=110_000, Kq=21, Gs=35_000, Ks=7, seed=3, cscore=0.7, tandem_Nmax=10, dist=20, N=4, liftover_dist=10,
+               label="C3: synthetic hexaploid-vs-diploid (110k vs 35k genes, three homeologous copies), C-score 0.7"),
+    "c5": dict(Gq=60_000, Kq=16, Gs=60_000, Ks=16, seed=5, cscore=0.7, tandem_Nmax=10, dist=20, N=4, liftover_dist=20,
+               label="C5: liftover-heavy -- sparse anchors (min_size=4), raw hits rescued within dist=20"),
+}
+
+
+def ss_workload(cfg, hits, world, rank, outdir):
+    """This rank's slice of the table (chunks [8 r / N, 8 (r + 1) / N) of 8 seeded chunks: the same table for every N)
+    + the two BEDs.  -> (text uint8, n_hits of the slice, qbed, sbed)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from jcvi_b200 import synth
+    from jcvi_b200.formats.bed import Bed
+    c = SS_CONFIGS[cfg]
+    rng = np.random.default_rng(c["seed"])
+    gq = synth.Genome("W", c["Gq"], c["Kq"], rng)
+    gs = synth.Genome("H", c["Gs"], c["Ks"], rng)
+    per = hits // SS_CHUNKS
+    mine = list(range(SS_CHUNKS * rank // world, SS_CHUNKS * (rank + 1) // world))
+
+    def one(ch):
+        arrays = synth.make_hits_chunk(gq, gs, per, ch, SS_CHUNKS, 1000 + c["seed"])
+        return synth.format_hits(gq, gs, arrays, header=(ch == 0), nthreads=max(2, host_threads() // max(1, min(4, len(mine)) * max(1, min(world, 4)))))
+
+    with ThreadPoolExecutor(max_workers=min(4, len(mine))) as ex:
+        parts = list(ex.map(one, mine))
+    text = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    qp, sp = os.path.join(outdir, "W.bed"), os.path.join(outdir, "H.bed")
+    gq.write_bed(qp, np.random.default_rng(10)); gs.write_bed(sp, np.random.default_rng(11))
+    return text, per * len(mine), Bed(qp), Bed(sp)
+
+
+def _digest(*arrays):
+    import hashlib
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, trace=False):
+    """ms per step of blastfilter -> scan -> liftover on ONE genome pair of `hits` raw hits whose table is spread over the
+    `world` ranks (slices resident in HBM; N = 1: the single-GPU jx_pipeline).  Collective over the ranks; the dict is
+    complete on rank 0.  `checksum` digests the anchors and the lifted pairs: identical for every N."""
+    import torch
+    import torch.distributed as dist
+    from jcvi_b200 import sharded
+    from jcvi_b200.engine import get_engine
+    c = SS_CONFIGS[cfg]
+    d = tempfile.mkdtemp(prefix="jcvi_b200_ss_")
+    t0 = time.time()
+    text, n_mine, qbed, sbed = ss_workload(cfg, hits, world, rank, d)
+    gen_s = time.time() - t0
+    eng = get_engine(local)
+    eng.load_pair(qbed, sbed, False)
+    dev = eng.upload(text)
+    torch.cuda.synchronize()
+    log("[rank %d] %s slice: %d hits, %.2f GB, generated in %.1fs" % (rank, cfg, n_mine, len(text) / 1e9, gen_s))
+    comm = sharded.DistComm()
+    kw = dict(cscore=c["cscore"], tandem_Nmax=c["tandem_Nmax"], xdist=c["dist"], ydist=c["dist"], N=c["N"], liftover_dist=c["liftover_dist"])
+    marks = []
+
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    def step():
+        if world == 1:
+            f, s, l = eng.pipeline(dev, want_text=False, skip_arrays=True, cscore=kw["cscore"], tandem_Nmax=kw["tandem_Nmax"], xdist=kw["xdist"],
+                                   ydist=kw["ydist"], N=kw["N"], liftover_dist=kw["liftover_dist"])
+            return f.n, s, l
+        del marks[:]
+        mark("start")
+        r = sharded.run_sharded([dev], qbed, sbed, comm=comm, engines=[eng], want_filtered=False, mark=mark, **kw)
+        return None, r.scan, r.lifted
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 1)):
+        nf, s, l = step()
+    times = []
+    for _ in range(steps):
+        barrier()
+        t0 = time.perf_counter()
+        nf, s, l = step()
+        barrier()
+        times.append(time.perf_counter() - t0)
+    t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) * 1e3
+    out = {"workload": c["label"], "hits": int(hits), "n_gpus": world, "ms_per_step": ms, "value": hits / (ms / 1e3), "unit": "hits/s",
+           "steps": steps, "scaling": "strong",
+           "sharding": "single GPU: jx_pipeline" if world == 1 else
+                       "text slices per rank; ncclAllReduce(max) of the best-score table; all-to-all of 16-byte candidates to the owner of "
+                       "their chromosome pair (blastfilter, liftover); all-gather of tandem edges and anchors",
+           "options": "cscore=%g tandem_Nmax=%d dist=%d min_size=%d liftover_dist=%d" % (c["cscore"], c["tandem_Nmax"], c["dist"], c["N"], c["liftover_dist"])}
+    if rank == 0:
+        out["outputs"] = {"anchors": int(s.n_anchors), "blocks": int(s.n_blocks), "lifted": int(l.n_lifted)}
+        out["checksum"] = _digest(s.q_rank, s.s_rank, s.score, s.block_start, l.q_rank, l.s_rank, l.score, l.block, l.accepted, l.raw_score)
+        if trace and marks:
+            out["phases_ms"] = {marks[i][0]: round((marks[i][1] - marks[i - 1][1]) * 1e3, 3) for i in range(1, len(marks))}
+    if verify and world > 1:
+        # rank 0 builds the whole table and runs the single-GPU pipeline on it
+        if rank == 0:
+            eng.shard_reset()
+            whole, _, _, _ = ss_workload(cfg, hits, 1, 0, d)
+            f0, s0, l0 = eng.pipeline(whole, want_text=False, skip_arrays=True, cscore=kw["cscore"], tandem_Nmax=kw["tandem_Nmax"],
+                                      xdist=kw["xdist"], ydist=kw["ydist"], N=kw["N"], liftover_dist=kw["liftover_dist"])
+            out["verified_against_single_gpu"] = bool(
+                _digest(s0.q_rank, s0.s_rank, s0.score, s0.block_start, l0.q_rank, l0.s_rank, l0.score, l0.block, l0.accepted, l0.raw_score)
+                == out["checksum"])
+        dist.barrier()
+    eng.shard_reset()
+    eng.release_text()
+    return out
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -184,6 +310,47 @@ def run_cpu_oracle(w, sample_text, steps, warmup, threads=1):
     return n, times
 
 
+REF_SAMPLE_LINES = 150_000
+
+
+def reference_built():
+    return os.path.exists(os.path.join(ROOT, "baseline", "_ref", ".built"))
+
+
+def run_cpu_reference(w, sample_text, steps, warmup, threads=1):
+    """hits/s of the UNMODIFIED reference (baseline/_ref: jcvi's own blastfilter.main -> synteny.scan --liftover with the
+    compiled cblast, one Python process per table -- the reference is single-threaded) on the sample; threads > 1: that
+    many independent copies side by side, one process per host thread.  -> (lines per copy, [wall seconds per step], outputs dir)"""
+    d = w["dir"]
+    n = int((sample_text == 10).sum())
+    lasts = []
+    for t in range(threads):
+        last = os.path.join(d, "A.B.ref%d.last" % t)
+        sample_text.tofile(last)
+        lasts.append(last)
+    script = os.path.join(ROOT, "baseline", "time_ref.py")
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([sys.executable, script, l, w["qbed_path"], w["sbed_path"], "10"], stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL) for l in lasts]
+        outs = [p.communicate()[0] for p in procs]
+        dt = time.perf_counter() - t0
+        if any(p.returncode != 0 for p in procs):
+            raise RuntimeError("the reference failed on the sample")
+        inner = max(json.loads(o.decode().strip().splitlines()[-1])["total"] for o in outs)     # without interpreter start-up
+        if it >= warmup:
+            times.append(inner)
+    for last in lasts[1:]:
+        stem = last[:-len(".last")]
+        for f in (last, last + ".filtered", stem + ".ref.anchors", stem + ".ref.lifted.anchors"):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+    return n, times
+
+
 def impl_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -192,9 +359,32 @@ def impl_reference(args):
     sample = min(CPU_SAMPLE_LINES, hits)
     # the sample is the head of the rank-0 workload (same seed, same table as the GPU arm)
     w = make_workload(100, hits)
-    st = head_lines(w["text"], sample + 3)
     warm = min(args.warmup, 1)
     T = host_threads()
+    if reference_built():
+        # the reference's own implementation (Python + compiled cblast), one process per host thread
+        st = head_lines(w["text"], min(REF_SAMPLE_LINES, hits) + 3)
+        n1, t1 = run_cpu_reference(w, st, 1, 0, threads=1)
+        n, times = run_cpu_reference(w, st, args.steps, warm, threads=T)
+        ms = 1000.0 * sum(times) / len(times)
+        val = T * n / (ms / 1000.0)
+        out = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "hits/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 text / int32 ranks / f32 scores / f64 C-score", "data": "synthetic",
+            "config": {"workload": "C2: synthetic diploid pair, 40k genes each, 20M hits with tandem arrays",
+                       "sample": "%d independent copies of the first %d lines per step, one Python process per host thread" % (T, n)},
+            "cpu_baseline": {"value": val, "unit": "hits/s", "cores": T, "kind": "reference",
+                             "sample": "first %d lines of the C2 table through the UNMODIFIED reference (baseline/_ref: "
+                                       "jcvi.compara.blastfilter.main -> jcvi.compara.synteny.scan --liftover, compiled cblast), file to "
+                                       "file; %d independent copies side by side, one process per host thread (the reference is "
+                                       "single-threaded: a many-core host works on one pair file per core); one copy on one core: "
+                                       "%.4g hits/s" % (n, T, n1 / t1[0])},
+            "e2e": {"value": val, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        emit(out)
+        return
+    st = head_lines(w["text"], sample + 3)
     n1, t1 = run_cpu_oracle(w, st, 1, 0, threads=1)                 # one table on one core, for the record
     n, times = run_cpu_oracle(w, st, args.steps, warm, threads=T)   # every core busy with its own table
     ms = 1000.0 * sum(times) / len(times)
@@ -227,7 +417,8 @@ def impl_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's own log (communicator size, transports) goes to stderr: stdout is claimed for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("BENCH_NCCL_DEBUG", "INFO"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hits = args.hits or HITS
     t0 = time.time()
@@ -313,9 +504,18 @@ def impl_ours(args):
     tok_ms, tok_launches, tok_bytes, tok_lines = eng.tokenizer_timing(reset=True)
     # ---- the same with record reuse off: liftover tokenizes the table again (two passes per step, like the
     # reference's two parses of the raw file); reported next to `value`, not instead of it
+    def step_separate():        # the three C-ABI calls one by one, every stage tokenizing for itself
+        r = eng.blastfilter(dev_text, want_text=False, raw=True, skip_arrays=True)
+        try:
+            s = eng.scan_filtered(r)
+        finally:
+            eng.free_filter(r)
+        aq, as_, ab = anchors_of(s)
+        return s, eng.liftover_text(dev_text, aq, as_, ab, dist=10)
+
     eng.set_record_reuse(False)
-    step_device()
-    noreuse_ms, _ = timed(step_device, args.steps)
+    step_separate()
+    noreuse_ms, _ = timed(step_separate, args.steps)
     eng.set_record_reuse(True)
     eng.tokenizer_timing(reset=True)
     # ---- timed: end to end with host buffers --------------------------------------------------------------
@@ -331,6 +531,18 @@ def impl_ours(args):
     ms_per_step = dev_ms / args.steps
     value = world * n_hits / (ms_per_step / 1000.0)
     e2e_value = world * n_hits / (e2e_ms / args.steps / 1000.0)
+
+    # ---- strong scaling: ONE genome pair (BASELINE configs[2], 200 M hits) over the `world` GPUs ------------------------
+    strong = None
+    ss_hits = args.ss_hits if args.ss_hits >= 0 else int(os.environ.get("BENCH_SS_HITS", "200000000"))
+    if ss_hits > 0:
+        try:
+            eng.release_text()
+            del pin_text, dev_text
+            strong = strong_scaling("c3", ss_hits, max(3, min(args.steps, 5)), 2, world, rank, local)
+        except Exception as e:                       # the weak-scaling line above stands on its own
+            strong = {"error": "%s: %s" % (type(e).__name__, e)}
+            log("[rank %d] strong-scaling section failed: %s" % (rank, strong["error"]))
 
     if rank == 0:
         peaks = {}
@@ -373,6 +585,30 @@ def impl_ours(args):
         parity = parity and rd(os.path.join(d, "g.anchors")) == rd(os.path.join(d, "A.B.sample.anchors"))
         t_cli = time.perf_counter() - t_cli
         parity = parity and rd(out_l) == rd(os.path.join(d, "A.B.sample.lifted.anchors"))
+        cpu = {"value": cpu_val, "unit": "hits/s", "cores": T, "kind": "port",
+               "sample": "first %d lines of this table, blastfilter+scan+liftover file to file, "
+                         "oracle/jcvi_oracle.cpp: %d independent copies side by side, one per host thread "
+                         "(%.2f s; one copy on one thread %.2f s = %.4g hits/s); the drop-in CLI functions on the "
+                         "same files, file to file incl. BED load and Python: %.2f s; GPU output on the sample "
+                         "byte-identical: %s" % (ncpu, T, times_all[0], times[0], ncpu / times[0], t_cli, parity)}
+        if reference_built():
+            # the reference itself (Python + compiled cblast) on a smaller head of the same table, and the GPU drop-in
+            # against ITS output files
+            rs = head_lines(text, REF_SAMPLE_LINES + 3)
+            nr, tr1 = run_cpu_reference(w, rs, 1, 0, threads=1)
+            _, trT = run_cpu_reference(w, rs, 1, 0, threads=T) if T > 1 else (nr, tr1)
+            rlast = os.path.join(d, "A.B.ref0.last")
+            ref_f, ref_a, ref_l = rd(rlast + ".filtered"), rd(os.path.join(d, "A.B.ref0.ref.anchors")), rd(os.path.join(d, "A.B.ref0.ref.lifted.anchors"))
+            gbf.main([rlast, "--qbed=" + w["qbed_path"], "--sbed=" + w["sbed_path"]])
+            out_r = gsyn.scan([rlast + ".filtered", os.path.join(d, "gr.anchors"), "--qbed=" + w["qbed_path"], "--sbed=" + w["sbed_path"],
+                               "--liftover=" + rlast, "--liftover_dist=10"])
+            rpar = rd(rlast + ".filtered") == ref_f and rd(os.path.join(d, "gr.anchors")) == ref_a and rd(out_r) == ref_l
+            cpu = {"value": T * nr / trT[0], "unit": "hits/s", "cores": T, "kind": "reference",
+                   "sample": "first %d lines of this table through the UNMODIFIED reference (baseline/_ref: jcvi.compara.blastfilter.main "
+                             "-> synteny.scan --liftover, compiled cblast), file to file: %d independent copies side by side, one "
+                             "Python process per host thread (%.2f s; one copy on one core %.2f s = %.4g hits/s); GPU drop-in output "
+                             "on the same files byte-identical to the reference's: %s" % (nr, T, trT[0], tr1[0], nr / tr1[0], rpar),
+                   "port": cpu}
         out = {
             "metric": METRIC, "value": value, "unit": "hits/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -382,9 +618,12 @@ def impl_ours(args):
                        "options": "cscore=0.7 tandem_Nmax=10 dist=20 min_size=4 liftover_dist=10",
                        "parallelism": "one genome pair per GPU (no data-path collective)",
                        "tokenizer_passes_per_step": 1,
+                       "value_is": "one jx_pipeline call per step on the table resident in HBM: blastfilter -> scan -> liftover with "
+                                   "survivors and anchors left on the device, anchors and lifted pairs copied to the host, `.filtered` "
+                                   "text not formatted (`e2e` includes the host->device copy of the table and the text)",
                        "record_reuse": "liftover re-uses the records blastfilter tokenized from the same resident "
-                                       "table in the same step (outputs identical); with reuse off (two passes, "
-                                       "jx_set_record_reuse(0)): %.3f ms/step = %.4g hits/s" % (
+                                       "table in the same step (outputs identical); as three separate C-ABI calls with reuse off "
+                                       "(two tokenizer passes, jx_set_record_reuse(0)): %.3f ms/step = %.4g hits/s" % (
                                            noreuse_ms / args.steps, world * n_hits / (noreuse_ms / args.steps / 1000.0)),
                        "l2": "inputs (%.0f MB text per pass) are larger than the 126 MB L2" % (len(text) / 1e6),
                        "outputs": {"filtered": int(f1.n), "anchors": int(s0.n_anchors), "blocks": int(s0.n_blocks),
@@ -394,13 +633,9 @@ def impl_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "cpu_baseline": {"value": cpu_val, "unit": "hits/s", "cores": T, "kind": "port",
-                             "sample": "first %d lines of this table, blastfilter+scan+liftover file to file, "
-                                       "oracle/jcvi_oracle.cpp: %d independent copies side by side, one per host thread "
-                                       "(%.2f s; one copy on one thread %.2f s = %.4g hits/s); the drop-in CLI functions on the "
-                                       "same files, file to file incl. BED load and Python: %.2f s; GPU output on the sample "
-                                       "byte-identical: %s" % (ncpu, T, times_all[0], times[0], ncpu / times[0], t_cli, parity)},
+            "cpu_baseline": cpu,
             "wall_ms_per_step": wall_ms / args.steps,
+            "strong_scaling": strong,
         }
         emit(out)
     if world > 1:
@@ -437,6 +672,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hits", type=int, default=0, help="override hits per GPU (debugging only)")
+    ap.add_argument("--ss-hits", type=int, default=-1, dest="ss_hits",
+                    help="raw hits of the strong-scaling table (one genome pair over all GPUs); 0 skips the section; default 200 M")
     args = ap.parse_args()
     if args.impl == "reference":
         impl_reference(args)

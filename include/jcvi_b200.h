@@ -261,7 +261,8 @@ int jx_shard_slots(jx_ctx* ctx, int64_t* n_slots);
 int jx_shard_candidates(jx_ctx* ctx, double cscore, uint32_t ord_base, uint64_t* cand_dev, int64_t* n, uint32_t* cp_hist, int64_t n_cp);
 /* candidates grouped by destination rank owner[cp]: device array + counts[world] */
 int jx_shard_partition(jx_ctx* ctx, uint64_t cand_dev, int64_t n, const int32_t* owner, int64_t n_cp, int world, uint64_t* out_dev,
-                       int64_t* counts);
+                       int64_t* counts, const uint32_t* cp_hist_in /* [n_cp] as jx_shard_candidates returned it, or NULL: counted here */,
+                       uint32_t* cp_hist_out /* [n_cp] or NULL: the candidates' count per chromosome pair */);
 /* owner: per-pair best record of the received candidates (blastfilter.py:86-89) + the tandem edges of its pairs as
  * device arrays of (rank a, rank b) uint32 pairs, query side and subject side */
 int jx_shard_pairs(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int tandem_nmax, uint64_t* qedges_dev, int64_t* nq, uint64_t* sedges_dev,
@@ -273,16 +274,21 @@ int jx_shard_survivors(jx_ctx* ctx, uint64_t qedges_dev, int64_t nq, uint64_t se
 /* `.filtered` order (score descending, global order ascending) of a set of survivors -> host columns of `out`
  * (line_off receives the global order) */
 int jx_shard_order(jx_ctx* ctx, uint64_t surv_dev, int64_t n, jx_filter_result* out);
-/* scan of survivors given as device candidates (the hand-over of jx_scan_filtered) */
-int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n, const jx_scan_opts* opts, jx_scan_result* out);
+/* scan of survivors given as device candidates (the hand-over of jx_scan_filtered).  dev_rows != NULL: the anchors are
+ * also left on the device as int32 rows {qi, si, score bits, block}; host_result = 0 then skips the host arrays of `out` */
+int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n, const jx_scan_opts* opts, jx_scan_result* out, uint64_t* dev_rows,
+                  int host_result);
 /* this rank's raw records within dist of any anchor (records retained by jx_cscore_begin, or `text`):
  * device array of {qi, si, score bits, ord_base + record index} */
 int jx_shard_near(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist, const int32_t* a_qi,
-                  const int32_t* a_si, int64_t n_anchor_lines, uint32_t ord_base, uint64_t* cand_dev, int64_t* n);
+                  const int32_t* a_si, int64_t n_anchor_lines, int anchors_on_device, uint32_t ord_base, uint64_t* cand_dev, int64_t* n);
 /* owner: the near candidates received + all anchor lines (global block ids) -> jx_liftover_result for this rank's
  * chromosome pairs (lifted pairs ordered by (block, chromosome pair, global order)) */
 int jx_shard_lift(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int64_t n_slots_total, int dist, const int32_t* a_qi, const int32_t* a_si,
-                  const int32_t* a_block, int64_t n_anchor_lines, jx_liftover_result* out);
+                  const int32_t* a_block, int64_t n_anchor_lines, int anchors_on_device, jx_liftover_result* out,
+                  uint64_t* dev_out /* NULL, or [2]: the result stays on the device (session memory): [0] int32 columns
+                                       {q | s | score bits | block} x n_lifted, [1] int64 per anchor line accepted << 32 | raw score bits;
+                                       the host arrays of `out` are then not filled */);
 
 /* ---- jcvi.formats.blast cscore (src/jcvi/formats/blast.py:1098-1189) ------------
  * `cscore` has no BED: its dictionaries are keyed by whatever (gene_name-stripped) names the table

@@ -112,16 +112,17 @@ def lib():
         L.jx_shard_slots.argtypes = [ctypes.c_void_p, c_i64p]
         L.jx_shard_candidates.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_uint32, c_u64p, c_i64p, ctypes.c_void_p, ctypes.c_int64]
         L.jx_shard_partition.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
-                                         c_u64p, ctypes.c_void_p]
+                                         c_u64p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.jx_shard_pairs.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, c_u64p, c_i64p, c_u64p, c_i64p]
         L.jx_shard_survivors.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int,
                                          c_u64p, c_i64p, ctypes.c_void_p, ctypes.c_void_p]
         L.jx_shard_order.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(JxFilterResult)]
-        L.jx_scan_cands.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(JxScanOpts), ctypes.POINTER(JxScanResult)]
+        L.jx_scan_cands.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(JxScanOpts), ctypes.POINTER(JxScanResult),
+                                    c_u64p, ctypes.c_int]
         L.jx_shard_near.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, c_u64p, c_i64p]
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, c_u64p, c_i64p]
         L.jx_shard_lift.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
-                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(JxLiftoverResult)]
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(JxLiftoverResult), c_u64p]
         L.jx_liftover_result_free.argtypes = [ctypes.POINTER(JxLiftoverResult)]
         L.jx_liftover_result_free.restype = None
         L.jx_nearest_anchor.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,

@@ -938,7 +938,7 @@ int jx_shard_candidates(jx_ctx* ctx, double cscore, uint32_t ord_base, uint64_t*
 }
 
 int jx_shard_partition(jx_ctx* ctx, uint64_t cand_dev, int64_t n, const int32_t* owner, int64_t n_cp, int world,
-                       uint64_t* out_dev, int64_t* counts) {
+                       uint64_t* out_dev, int64_t* counts, const uint32_t* cp_hist_in, uint32_t* cp_hist_out) {
   if (!ctx || !owner || !out_dev || !counts || world < 1 || n < 0 || n >= (1ll << 31)) return JX_EARG;
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
@@ -949,10 +949,14 @@ int jx_shard_partition(jx_ctx* ctx, uint64_t cand_dev, int64_t n, const int32_t*
   JX_ALLOC(d_hist, uint32_t, (size_t)n_cp + 1, true);
   const uint4* C = (const uint4*)(uintptr_t)cand_dev;
   const unsigned grid = std::max(1u, std::min<unsigned>(nblk((size_t)std::max<int64_t>(n, 1)), 148u * 8u));
-  if (n) JX_LAUNCH(k_cp_hist, grid, 256, 0, C, (uint32_t)n, Q.chr_lex, S.chr_lex, (uint32_t)S.n_chr, d_hist);
   std::vector<uint32_t> hist((size_t)n_cp);
-  JX_CK(cudaMemcpyAsync(hist.data(), d_hist, (size_t)n_cp * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
+  if (cp_hist_in) memcpy(hist.data(), cp_hist_in, (size_t)n_cp * 4);        // (what jx_shard_candidates returned)
+  else {
+    if (n) JX_LAUNCH(k_cp_hist, grid, 256, 0, C, (uint32_t)n, Q.chr_lex, S.chr_lex, (uint32_t)S.n_chr, d_hist);
+    JX_CK(cudaMemcpyAsync(hist.data(), d_hist, (size_t)n_cp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (cp_hist_out) memcpy(cp_hist_out, hist.data(), (size_t)n_cp * 4);
   std::vector<uint32_t> cursor((size_t)world, 0);
   for (int64_t k = 0; k < n_cp; ++k) {
     if (owner[k] < 0 || owner[k] >= world) { ctx->err = "owner out of range"; return JX_EARG; }

@@ -348,6 +348,7 @@ struct ScanDev {
   uint32_t* count = nullptr;     // device: [0] = anchors
   uint32_t n = 0, nb = 0;        // host copies (nb only when the host half has run)
   bool defer_copy = false;       // in: leave the result copy in flight (`stage`), the caller finishes with scan_finish_host
+  bool no_host = false;          // in: the anchors stay on the device only (no result copy; counts are still returned)
   char* stage = nullptr;
 };
 void scan_finish_host(jx_scan_result* out, const char* stage, uint32_t m);

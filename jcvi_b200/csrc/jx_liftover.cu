@@ -719,6 +719,10 @@ __global__ void k_lift_emit(const uint8_t* state, const uint32_t* nh_p, const ui
 }
 }  // namespace
 
+__global__ void k_pack_accepted(const uint8_t* acc, const float* raw, uint32_t n, long long* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = ((long long)acc[t] << 32) | (long long)__float_as_uint(raw[t]);
+}
 // the anchor side of a liftover: anchors sorted by (qi, si) with a row pointer per query rank, the occupancy bitmap of
 // the cells within `dist` of an anchor, device counters (0 anchors in the BED, 1 rank out of range, 2 duplicate,
 // 3 candidates, 4 unique hits, 5 lifted, 6 ambiguous, 7 emitted)
@@ -759,7 +763,7 @@ static int lo_anchors(jx_ctx* ctx, Arena& arena, int dist, const int32_t* daq, c
 }
 static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uint32_t nC0, uint32_t n_lines, int dist,
                    const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
-                   const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out);
+                   const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out, uint64_t* dev_out = nullptr);
 
 // liftover on device-resident records and anchors.  d_aq / d_as / d_ablock: per anchor LINE (file order; -1 = name not
 // in the BED).  h_*: the same on the host when the caller has them (only the rare tie walk needs them; null: copied back).
@@ -801,9 +805,12 @@ int jx_liftover_core(jx_ctx* ctx, Arena& arena, const uint4* recs, uint32_t n_li
 }
 
 // candidates C0[0 .. nC0) = {qi, si, score bits, order} (order: file-order key, < n_lines) -> the liftover result
+// dev_out != NULL (sharded run): the result stays on the device in session memory -- dev_out[0] = int32 columns
+// {q | s | score bits | block} x n_lifted, dev_out[1] = int64 per anchor line: accepted << 32 | raw score bits -- and the
+// host arrays of `out` are not filled (counts and stats are)
 static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uint32_t nC0, uint32_t n_lines, int dist,
                    const int32_t* daq, const int32_t* das, const uint32_t* dab, uint32_t nal,
-                   const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out) {
+                   const int32_t* h_aq, const int32_t* h_as, const int32_t* h_ablock, jx_liftover_result* out, uint64_t* dev_out) {
   const SideDev& Q = ctx->side[0];
   const SideDev& S = ctx->side[1];
   int rc;
@@ -834,8 +841,14 @@ static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uin
   JX_ALLOC(dacc, uint8_t, (size_t)nal + 1, false);
   JX_ALLOC(draw, float, (size_t)nal + 1, false);
   JX_LAUNCH(k_lookup2, nblk(nal), 256, 0, HK, HV, hmask, C0, daq, das, nal, dacc, draw);
-  JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dev_out) {
+    JX_SALLOC(packed, long long, (size_t)nal + 1, false);
+    JX_LAUNCH(k_pack_accepted, nblk(nal), 256, 0, dacc, draw, nal, packed);
+    dev_out[1] = (uint64_t)(uintptr_t)packed;
+  } else {
+    JX_CK(cudaMemcpyAsync(out->accepted, dacc, nal, cudaMemcpyDeviceToHost, ctx->stream));
+    JX_CK(cudaMemcpyAsync(out->raw_score, draw, (size_t)nal * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   JX_TRACE("lo: near+dedupe+lookup");
 
   // ---- nearest anchor per hit -------------------------------------------------------------------------------
@@ -917,7 +930,7 @@ static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uin
   JX_TRACE("lo: nearest+ambiguous");
 
   // ---- order: (block, sorted chromosome pair, file order) in ONE key ------------------------------------------------------------
-  alloc_out(nlift);
+  if (dev_out) { alloc_out(0); out->n_lifted = nlift; } else alloc_out(nlift);
   if (nlift) {
     const uint64_t maxcp = (uint64_t)std::max<int64_t>(Q.n_chr, 1) * (uint64_t)std::max<int64_t>(S.n_chr, 1);
     const int ob = jx_bits((uint64_t)std::max<uint32_t>(n_lines, 1u)), cb = jx_bits(maxcp), bb = jx_bits((uint64_t)nal + 1);
@@ -933,6 +946,13 @@ static int lo_back(jx_ctx* ctx, Arena& arena, LoAnchors& L, const uint4* C0, uin
     int32_t* oq = (int32_t*)oblk; int32_t* os = (int32_t*)(oblk + nlift); float* osc = (float*)(oblk + 2 * (size_t)nlift);
     int32_t* ob_ = (int32_t*)(oblk + 3 * (size_t)nlift);
     JX_LAUNCH(k_emit_lifted, nblk(nlift), 256, 0, v1s, nlift, hkey, hsc, hit_block, sb, oq, os, osc, ob_);
+    if (dev_out) {
+      JX_SALLOC(keep, uint32_t, (size_t)nlift * 4, false);
+      JX_CK(cudaMemcpyAsync(keep, oblk, (size_t)nlift * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+      JX_CK(cudaStreamSynchronize(ctx->stream));
+      dev_out[0] = (uint64_t)(uintptr_t)keep;
+      return JX_OK;
+    }
     char* stage = nullptr;
     if ((rc = jx_pin_small(ctx, (size_t)nlift * 16, &stage))) return rc;
     JX_CK(cudaMemcpyAsync(stage, oblk, (size_t)nlift * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1117,7 +1137,7 @@ extern "C" {
 // this rank's raw records (of the slice jx_cscore_begin tokenized, or `text` when given) within dist of an anchor:
 // device array of {qi, si, score bits, ord_base + record index} + count
 int jx_shard_near(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int dist, const int32_t* a_qi,
-                  const int32_t* a_si, int64_t nal64, uint32_t ord_base, uint64_t* cand_dev, int64_t* n_out) {
+                  const int32_t* a_si, int64_t nal64, int anchors_on_device, uint32_t ord_base, uint64_t* cand_dev, int64_t* n_out) {
   if (!ctx || !cand_dev || !n_out || nal64 < 0 || nal64 >= (1ll << 31) || dist < 0) return JX_EARG;
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
@@ -1148,11 +1168,15 @@ int jx_shard_near(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_dev
   }
   if ((uint64_t)ord_base + n_lines >= (1ull << 31)) { ctx->err = "more than 2^31 record slots over all ranks"; return JX_EUNSUPPORTED; }
   if (!nal || !tstats[2]) return JX_OK;
-  JX_ALLOC(daq, int32_t, (size_t)nal + 1, false);
-  JX_ALLOC(das, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(daq0, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(das0, int32_t, (size_t)nal + 1, false);
   JX_ALLOC(dab, uint32_t, (size_t)nal + 1, true);
-  JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-  JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const int32_t* daq = daq0; const int32_t* das = das0;
+  if (anchors_on_device) { daq = a_qi; das = a_si; }
+  else {
+    JX_CK(cudaMemcpyAsync(daq0, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(das0, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
   LoAnchors L;
   if ((rc = lo_anchors(ctx, arena, dist, daq, das, dab, nal, L))) return rc;
   const size_t capC = (size_t)tstats[2] + 1;
@@ -1180,7 +1204,7 @@ int jx_shard_near(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_dev
 // ids) -> lifted pairs ordered by (block, chromosome pair, global order), accepted / raw score for the anchor lines whose
 // pair this rank received.  n_slots_total = upper bound of the global order values.
 int jx_shard_lift(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int64_t n_slots_total, int dist, const int32_t* a_qi, const int32_t* a_si,
-                  const int32_t* a_block, int64_t nal64, jx_liftover_result* out) {
+                  const int32_t* a_block, int64_t nal64, int anchors_on_device, jx_liftover_result* out, uint64_t* dev_out) {
   if (!ctx || !out || n < 0 || n >= (1ll << 31) || nal64 < 0 || nal64 >= (1ll << 31) || n_slots_total < 0 || n_slots_total >= (1ll << 31))
     return JX_EARG;
   memset(out, 0, sizeof *out);
@@ -1195,13 +1219,27 @@ int jx_shard_lift(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int64_t n_slots_tot
     out->score = (float*)malloc(4 * ((size_t)k + 1)); out->block = (int32_t*)malloc(4 * ((size_t)k + 1));
     out->n_lifted = k;
   };
-  if (!nal || !n) { alloc_out(0); return JX_OK; }
-  JX_ALLOC(daq, int32_t, (size_t)nal + 1, false);
-  JX_ALLOC(das, int32_t, (size_t)nal + 1, false);
-  JX_ALLOC(dab, uint32_t, (size_t)nal + 1, false);
-  JX_CK(cudaMemcpyAsync(daq, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-  JX_CK(cudaMemcpyAsync(das, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
-  JX_CK(cudaMemcpyAsync(dab, a_block, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (dev_out) { dev_out[0] = 0; dev_out[1] = 0; }
+  if (!nal) { alloc_out(0); return JX_OK; }
+  if (!n) {
+    alloc_out(0);
+    if (dev_out) {                                 // nothing received: every anchor line "not accepted" here
+      JX_SALLOC(packed, long long, (size_t)nal + 1, true);
+      JX_CK(cudaStreamSynchronize(ctx->stream));
+      dev_out[1] = (uint64_t)(uintptr_t)packed;
+    }
+    return JX_OK;
+  }
+  JX_ALLOC(daq0, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(das0, int32_t, (size_t)nal + 1, false);
+  JX_ALLOC(dab0, uint32_t, (size_t)nal + 1, false);
+  const int32_t* daq = daq0; const int32_t* das = das0; const uint32_t* dab = dab0;
+  if (anchors_on_device) { daq = a_qi; das = a_si; dab = (const uint32_t*)a_block; }
+  else {
+    JX_CK(cudaMemcpyAsync(daq0, a_qi, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(das0, a_si, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JX_CK(cudaMemcpyAsync(dab0, a_block, (size_t)nal * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
   LoAnchors L;
   if ((rc = lo_anchors(ctx, arena, dist, daq, das, dab, nal, L))) return rc;
   uint32_t h3[3] = {0, 0, 0};
@@ -1212,8 +1250,14 @@ int jx_shard_lift(jx_ctx* ctx, uint64_t recv_dev, int64_t n, int64_t n_slots_tot
   L.na = h3[0];
   out->stats[2] = L.na;
   if (!L.na) { alloc_out(0); return JX_OK; }
-  return lo_back(ctx, arena, L, (const uint4*)(uintptr_t)recv_dev, (uint32_t)n, (uint32_t)n_slots_total, dist, daq, das, dab, nal, a_qi,
-                 a_si, a_block, out);
+  rc = lo_back(ctx, arena, L, (const uint4*)(uintptr_t)recv_dev, (uint32_t)n, (uint32_t)n_slots_total, dist, daq, das, dab, nal,
+               anchors_on_device ? nullptr : a_qi, anchors_on_device ? nullptr : a_si, anchors_on_device ? nullptr : a_block, out, dev_out);
+  if (!rc && dev_out && !dev_out[1]) {             // (early exits of the core: no candidate survived)
+    JX_SALLOC(packed, long long, (size_t)nal + 1, true);
+    dev_out[1] = (uint64_t)(uintptr_t)packed;
+  }
+  if (!rc) JX_CK(cudaStreamSynchronize(ctx->stream));
+  return rc;
 }
 
 }  // extern "C"

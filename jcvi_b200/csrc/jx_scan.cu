@@ -225,7 +225,7 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
                        jx_scan_result* out, ScanDev* dev, const uint32_t* extra_flag) {
   out->n_anchors = 0; out->n_blocks = 0;
   out->block_start = (int64_t*)calloc(1, sizeof(int64_t));
-  if (dev) { const bool defer = dev->defer_copy; *dev = ScanDev(); dev->defer_copy = defer; }
+  if (dev) { const bool defer = dev->defer_copy, nh = dev->no_host; *dev = ScanDev(); dev->defer_copy = defer; dev->no_host = nh; }
   if (!n) {
     out->q_rank = (int32_t*)malloc(4); out->s_rank = (int32_t*)malloc(4); out->score = (float*)malloc(4);
     out->index = (int64_t*)malloc(8);
@@ -293,6 +293,7 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
   out->score = (float*)malloc(4 * ((size_t)m + 1));
   out->index = (int64_t*)malloc(8 * ((size_t)m + 1));
   out->n_anchors = m;
+  if (dev && dev->no_host) return JX_OK;
   if (m) {
     char* stage = nullptr;
     if ((rc = jx_pin_scan(ctx, (size_t)m * 20, &stage))) return rc;
@@ -546,9 +547,20 @@ __global__ void k_cands_to_recs(const uint4* __restrict__ F, uint32_t n, int is_
 
 // scan of a set of survivors given as device candidates {qi, si, score bits, ..} (a rank's share of a sharded pair, or
 // all of them): the same hand-over as jx_scan_filtered
-extern "C" int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n64, const jx_scan_opts* opts, jx_scan_result* out) {
+namespace {
+__global__ void k_pack_anchor_cols(const int32_t* q, const int32_t* s, const float* sc, const uint32_t* blk, uint32_t m, int32_t* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  out[4 * (size_t)t] = q[t]; out[4 * (size_t)t + 1] = s[t]; out[4 * (size_t)t + 2] = __float_as_int(sc[t]); out[4 * (size_t)t + 3] = (int32_t)blk[t];
+}
+}  // namespace
+// dev_rows != NULL: the anchors are ALSO left on the device as int32 rows {qi, si, score bits, block} (session memory,
+// see jx_shard_reset); host_result = 0 then skips the host arrays of `out` (n_anchors is still set).
+extern "C" int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n64, const jx_scan_opts* opts, jx_scan_result* out, uint64_t* dev_rows,
+                             int host_result) {
   if (!ctx || !opts || !out || n64 < 0 || n64 >= (1ll << 31)) return JX_EARG;
   memset(out, 0, sizeof *out);
+  if (dev_rows) *dev_rows = 0;
   if (!ctx->pair_ready) { ctx->err = "jx_bed_load / jx_pair_setup first"; return JX_EARG; }
   cudaSetDevice(ctx->device);
   Arena arena(ctx);
@@ -558,7 +570,17 @@ extern "C" int jx_scan_cands(jx_ctx* ctx, uint64_t surv_dev, int64_t n64, const 
   if (n) JX_LAUNCH(k_cands_to_recs, nblk(n), 256, 0, (const uint4*)(uintptr_t)surv_dev, n, ctx->is_self ? 1 : 0, ctx->side[0].chr_lex,
                    ctx->side[1].chr_lex, recs, bad);
   out->stats[0] = n;
-  return scan_records(ctx, arena, recs, n, n, opts, out, !ctx->is_self, nullptr, bad);
+  ScanDev dev;
+  dev.no_host = dev_rows && !host_result;
+  int rc = scan_records(ctx, arena, recs, n, n, opts, out, !ctx->is_self, dev_rows ? &dev : nullptr, bad);
+  if (rc) return rc;
+  if (dev_rows && dev.n) {
+    JX_SALLOC(rows, int32_t, (size_t)dev.n * 4, false);
+    JX_LAUNCH(k_pack_anchor_cols, nblk(dev.n), 256, 0, dev.q, dev.s, dev.score, dev.block, dev.n, rows);
+    JX_CK(cudaStreamSynchronize(ctx->stream));
+    *dev_rows = (uint64_t)(uintptr_t)rows;
+  }
+  return JX_OK;
 }
 
 // the in-memory hand-over of the LAST jx_blastfilter's survivors (still on the device) to scan: equivalent to writing

@@ -519,14 +519,18 @@ class Engine(object):
                                                  C.ptr(hist), int(n_cp)))
         return self._dev_records(ptr.value, n.value), hist[:n_cp]
 
-    def shard_partition(self, cand, owner, world):
-        """candidates grouped by destination rank -> (int32 [n, 4] device array, int64 counts[world])"""
+    def shard_partition(self, cand, owner, world, want_hist=False, hist_in=None):
+        """candidates grouped by destination rank -> (int32 [n, 4] device array, int64 counts[world][, uint32 hist per pair]);
+        hist_in: the candidates' histogram when the caller already has it (shard_candidates) -- saves a pass and a round trip"""
         owner = np.ascontiguousarray(owner, dtype=np.int32)
         counts = np.zeros(int(world), dtype=np.int64)
+        hist = np.zeros(len(owner), dtype=np.uint32) if want_hist else None
+        hin = None if hist_in is None else np.ascontiguousarray(hist_in, dtype=np.uint32)
         out = ctypes.c_uint64()
         self._check(self.lib.jx_shard_partition(self.ctx, int(cand.data_ptr()) if cand.numel() else 0, int(cand.shape[0]), C.ptr(owner),
-                                                len(owner), int(world), ctypes.byref(out), C.ptr(counts)))
-        return self._dev_records(out.value, cand.shape[0]), counts
+                                                len(owner), int(world), ctypes.byref(out), C.ptr(counts), C.ptr(hin), C.ptr(hist)))
+        part = self._dev_records(out.value, cand.shape[0])
+        return (part, counts, hist) if want_hist else (part, counts)
 
     def _dev_pairs(self, ptr, n):
         import torch
@@ -565,35 +569,76 @@ class Engine(object):
             self._check(rc)
         return FilterResult(r, self.lib, self.Gq, self.Gs, False, engine=self)
 
-    def scan_cands(self, surv, xdist=20, ydist=20, N=4, intrabound=300):
+    def scan_cands(self, surv, xdist=20, ydist=20, N=4, intrabound=300, device=False):
+        """scan of device survivors.  device=True: -> int32 [m, 4] CUDA tensor of {qi, si, score bits, block} (the anchors
+        never visit the host); else a ScanResult"""
         o = self._scan_opts(xdist, ydist, N, intrabound)
         r = C.JxScanResult()
-        rc = self.lib.jx_scan_cands(self.ctx, int(surv.data_ptr()) if surv.numel() else 0, int(surv.shape[0]), ctypes.byref(o), ctypes.byref(r))
+        rows = ctypes.c_uint64()
+        rc = self.lib.jx_scan_cands(self.ctx, int(surv.data_ptr()) if surv.numel() else 0, int(surv.shape[0]), ctypes.byref(o), ctypes.byref(r),
+                                    ctypes.byref(rows) if device else None, 0 if device else 1)
         try:
             self._check(rc)
+            if device:
+                return self._dev_records(rows.value, r.n_anchors)
             return ScanResult(r)
         finally:
             self.lib.jx_scan_result_free(ctypes.byref(r))
 
+    @staticmethod
+    def _anchor_ptr(a):
+        """-> (pointer, on_device, keepalive) of an int32 anchor column (numpy array or CUDA tensor)"""
+        if hasattr(a, "is_cuda"):
+            t = a.contiguous()
+            return ctypes.c_void_p(t.data_ptr() if t.numel() else 0), 1, t
+        h = np.ascontiguousarray(a, dtype=np.int32)
+        return C.ptr(h), 0, h
+
     def shard_near(self, a_qi, a_si, ord_base, strip_names=True, dist=10, text=None):
-        """this rank's raw records within dist of an anchor -> int32 [n, 4] device candidates"""
-        a_qi = np.ascontiguousarray(a_qi, dtype=np.int32); a_si = np.ascontiguousarray(a_si, dtype=np.int32)
+        """this rank's raw records within dist of an anchor -> int32 [n, 4] device candidates (anchors: host arrays or
+        int32 CUDA tensors)"""
+        pq, dq, kq = self._anchor_ptr(a_qi); ps, ds, ks = self._anchor_ptr(a_si)
+        assert dq == ds
         p, nb, dev, keep = _text_ptr(text) if text is not None else (None, 0, 1, None)
         ptr = ctypes.c_uint64(); n = ctypes.c_int64()
-        self._check(self.lib.jx_shard_near(self.ctx, p, nb, dev, int(bool(strip_names)), int(dist), C.ptr(a_qi), C.ptr(a_si), len(a_qi),
+        self._check(self.lib.jx_shard_near(self.ctx, p, nb, dev, int(bool(strip_names)), int(dist), pq, ps, len(kq), dq,
                                            int(ord_base), ctypes.byref(ptr), ctypes.byref(n)))
         return self._dev_records(ptr.value, n.value)
 
-    def shard_lift(self, recv, n_slots_total, a_qi, a_si, a_block, dist=10):
-        a_qi = np.ascontiguousarray(a_qi, dtype=np.int32); a_si = np.ascontiguousarray(a_si, dtype=np.int32)
-        a_block = np.ascontiguousarray(a_block, dtype=np.int32)
+    def shard_lift(self, recv, n_slots_total, a_qi, a_si, a_block, dist=10, device=False):
+        """device=True: -> (int32 [4, n_lifted] CUDA tensor of the columns q / s / score bits / block, int64 [n_anchor_lines]
+        CUDA tensor accepted << 32 | raw score bits); else a LiftoverResult"""
+        import torch
+        pq, dq, kq = self._anchor_ptr(a_qi); ps, ds, ks = self._anchor_ptr(a_si); pb, db, kb = self._anchor_ptr(a_block)
+        assert dq == ds == db
         r = C.JxLiftoverResult()
+        dv = (ctypes.c_uint64 * 2)()
         rc = self.lib.jx_shard_lift(self.ctx, int(recv.data_ptr()) if recv.numel() else 0, int(recv.shape[0]), int(n_slots_total), int(dist),
-                                    C.ptr(a_qi), C.ptr(a_si), C.ptr(a_block), len(a_qi), ctypes.byref(r))
+                                    pq, ps, pb, len(kq), dq, ctypes.byref(r), dv if device else None)
         if rc != 0:
             self.lib.jx_liftover_result_free(ctypes.byref(r))
             self._check(rc)
-        return LiftoverResult(r, len(a_qi), self.lib)
+        if not device:
+            return LiftoverResult(r, len(kq), self.lib)
+        nl, nal = int(r.n_lifted), len(kq)
+        self.lib.jx_liftover_result_free(ctypes.byref(r))
+        dname = "cuda:%d" % self.device
+
+        class _Dev(object):
+            pass
+        if nl and dv[0]:
+            d = _Dev()
+            d.__cuda_array_interface__ = {"shape": (4, nl), "typestr": "<i4", "data": (int(dv[0]), False), "version": 2}
+            cols = torch.as_tensor(d, device=dname)
+        else:
+            cols = torch.zeros((4, 0), dtype=torch.int32, device=dname)
+        if nal and dv[1]:
+            d = _Dev()
+            d.__cuda_array_interface__ = {"shape": (nal,), "typestr": "<i8", "data": (int(dv[1]), False), "version": 2}
+            acc = torch.as_tensor(d, device=dname)
+        else:
+            acc = torch.zeros((nal,), dtype=torch.int64, device=dname)
+        return cols, acc
 
     def mcscan(self, start, end, score, block_id, max_iter, pair_gene, pair_partner, pair_block, n_genes, n_blocks):
         """jx_mcscan -> (tracks: list of block-id lists in chain order, chain scores, table[n_genes, n_tracks] of partner ids, -1 = '.')."""

@@ -181,61 +181,52 @@ class DistComm(object):
         self.local = [self.rank]
         self.dist = dist if self.world > 1 and dist.is_initialized() else None
 
-    def allreduce_max_(self, tensors):
-        if self.dist:
-            self.dist.all_reduce(tensors[0], op=self.dist.ReduceOp.MAX)
-
-    def allreduce_sum_np(self, arrays):
-        import torch
-        if not self.dist:
-            return [arrays[0].copy()]
-        t = torch.from_numpy(arrays[0].astype(np.int64)).to(self._dev())
-        self.dist.all_reduce(t)
-        return [t.cpu().numpy()]
-
-    def allgather_np(self, arrays):
-        """small host arrays: -> [list over all ranks] per local rank"""
-        if not self.dist:
-            return [[arrays[0]]]
-        out = [None] * self.world
-        self.dist.all_gather_object(out, arrays[0])
-        return [out]
-
     def _dev(self):
         import torch
         return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 
-    def alltoallv(self, sends, counts):
-        """sends[0]: [n, W] tensor grouped by destination, counts[0]: int64[world] -> (received [m, W] tensor, recv counts)"""
+    def allreduce_max_(self, tensors):
+        if self.dist:
+            self.dist.all_reduce(tensors[0], op=self.dist.ReduceOp.MAX)
+
+    def allgather_fixed(self, arrays):
+        """equal-shape small host arrays -> [world, ...] int64 numpy (the same on every rank), per local rank"""
+        import torch
+        a = np.ascontiguousarray(arrays[0], dtype=np.int64)
+        if not self.dist:
+            return [a[None]]
+        t = torch.from_numpy(a).to(self._dev())
+        out = torch.empty((self.world,) + tuple(a.shape), dtype=torch.int64, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.unsqueeze(0) if a.ndim == 0 else t)
+        return [out.cpu().numpy().reshape((self.world,) + tuple(a.shape))]
+
+    def alltoallv(self, sends, matrix):
+        """sends[0]: [n, W] device tensor grouped by destination; matrix[r][d] = rows rank r sends to rank d (known to
+        every rank) -> the rows received, grouped by source"""
         import torch
         if not self.dist:
-            return [sends[0]], [counts[0].copy()]
-        c = torch.from_numpy(np.ascontiguousarray(counts[0], dtype=np.int64)).to(sends[0].device)
-        rc = torch.empty_like(c)
-        self.dist.all_to_all_single(rc, c)
-        rcounts = rc.cpu().numpy()
-        recv = torch.empty((int(rcounts.sum()), sends[0].shape[1]), dtype=sends[0].dtype, device=sends[0].device)
-        self.dist.all_to_all_single(recv, sends[0].contiguous(), output_split_sizes=[int(x) for x in rcounts],
-                                    input_split_sizes=[int(x) for x in counts[0]])
-        return [recv], [rcounts]
+            return [sends[0]]
+        r = self.rank
+        recv = torch.empty((int(matrix[:, r].sum()), sends[0].shape[1]), dtype=sends[0].dtype, device=sends[0].device)
+        self.dist.all_to_all_single(recv, sends[0].contiguous(), output_split_sizes=[int(x) for x in matrix[:, r]],
+                                    input_split_sizes=[int(x) for x in matrix[r, :]])
+        return [recv]
 
     def allgatherv(self, tensors):
-        """[n_r, W] device tensors -> the concatenation over all ranks (rank order) on every rank, + sizes"""
+        """[n_r, W] device tensors -> (their concatenation over all ranks in rank order, sizes[world]) on every rank"""
         import torch
         t = tensors[0]
         if not self.dist:
-            return [t], [np.array([t.shape[0]], dtype=np.int64)]
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        sizes = torch.empty(self.world, dtype=torch.int64, device=t.device)
-        self.dist.all_gather_into_tensor(sizes, n)
-        sizes = sizes.cpu().numpy()
+            return [t], np.array([t.shape[0]], dtype=np.int64)
+        sizes = self.allgather_fixed([np.array([t.shape[0]])])[0][:, 0]
         pad = int(max(sizes.max(), 1))
         mine = torch.zeros((pad, t.shape[1]), dtype=t.dtype, device=t.device)
         mine[: t.shape[0]] = t
         allp = torch.empty((self.world * pad, t.shape[1]), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(allp, mine)
-        parts = [allp[r * pad: r * pad + int(sizes[r])] for r in range(self.world)]
-        return [torch.cat(parts, 0) if parts else t], [sizes]
+        if (sizes == pad).all():
+            return [allp], sizes
+        return [torch.cat([allp[r * pad: r * pad + int(sizes[r])] for r in range(self.world)], 0)], sizes
 
     def barrier(self):
         if self.dist:
@@ -259,29 +250,20 @@ class LocalComm(object):
         for t in tensors:
             t.copy_(m)
 
-    def allreduce_sum_np(self, arrays):
-        s = np.sum([a.astype(np.int64) for a in arrays], axis=0)
-        return [s.copy() for _ in arrays]
+    def allgather_fixed(self, arrays):
+        m = np.stack([np.ascontiguousarray(a, dtype=np.int64) for a in arrays])
+        return [m.copy() for _ in arrays]
 
-    def allgather_np(self, arrays):
-        return [list(arrays) for _ in arrays]
-
-    def alltoallv(self, sends, counts):
+    def alltoallv(self, sends, matrix):
         import torch
         W = self.world
-        offs = [np.concatenate([[0], np.cumsum(c)]) for c in counts]
-        recv, rcounts = [], []
-        for d in range(W):
-            parts = [sends[r][int(offs[r][d]): int(offs[r][d + 1])] for r in range(W)]
-            recv.append(torch.cat(parts, 0).clone())
-            rcounts.append(np.array([int(counts[r][d]) for r in range(W)], dtype=np.int64))
-        return recv, rcounts
+        offs = np.concatenate([np.zeros((W, 1), np.int64), np.cumsum(matrix, axis=1)], axis=1)
+        return [torch.cat([sends[r][int(offs[r][d]): int(offs[r][d + 1])] for r in range(W)], 0).clone() for d in range(W)]
 
     def allgatherv(self, tensors):
         import torch
         cat = torch.cat(list(tensors), 0)
-        sizes = np.array([t.shape[0] for t in tensors], dtype=np.int64)
-        return [cat.clone() for _ in tensors], [sizes.copy() for _ in tensors]
+        return [cat.clone() for _ in tensors], np.array([t.shape[0] for t in tensors], dtype=np.int64)
 
     def barrier(self):
         pass
@@ -300,6 +282,14 @@ def assign_owners(hist, world):
     return owner
 
 
+def _send_matrix(H, owner, world):
+    """H[r][cp] = candidates of rank r per chromosome pair -> matrix[r][d] = rows rank r sends to rank d"""
+    M = np.zeros((H.shape[0], world), dtype=np.int64)
+    for d in range(world):
+        M[:, d] = H[:, owner == d].sum(axis=1)
+    return M
+
+
 class ShardedResult(object):
     """What rank 0 holds after a sharded run: the `.filtered` columns (output order), the anchors block by block in the
     reference's order, the lifted pairs with `accepted` / `raw_score` per anchor line -- the same arrays as the
@@ -309,7 +299,6 @@ class ShardedResult(object):
         self.filtered = None
         self.scan = None
         self.lifted = None
-        self.timing = {}
 
 
 class _Scan(object):
@@ -338,58 +327,56 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
     ts = sbed.tables()
     n_chr_s = int(ts["n_chr"])
     n_cp = int(tq["n_chr"]) * n_chr_s
-    qchr = np.asarray(tq["chr_lex"]); schr = np.asarray(ts["chr_lex"])
+    devs = ["cuda:%d" % e.device for e in engines]
     for i in L:
         engines[i].load_pair(qbed, sbed, False)
         engines[i].shard_reset()
+    # every rank owns a fixed stride of the global order (no exchange of slice sizes)
+    stride = (1 << 31) // W
+    base = [comm.local[i] * stride for i in L]
+    total_slots = (1 << 31) - 1
     # ---- stage A: tokenize the slice, best-score table, all-reduce(max) -------------------------------------------------
     bests = []
     for i in L:
         ptr, n_ids = engines[i].cscore_begin(slices[i], strip_names=strip_names)
         bests.append(engines[i].best_table_tensor(ptr, n_ids))
+        if engines[i].shard_slots() >= stride:
+            raise NotImplementedError("a slice with more than 2^31 / world record slots")
     mark("tokenize")
-    torch.cuda.synchronize()
     comm.allreduce_max_(bests)
     torch.cuda.synchronize()
-    slots = [np.array([engines[i].shard_slots()], dtype=np.int64) for i in L]
-    all_slots = comm.allgather_np(slots)
-    base = []
-    for k, i in enumerate(L):
-        sizes = [int(x[0]) for x in all_slots[k]]
-        r = comm.local[k]
-        base.append(int(sum(sizes[:r])))
-        total_slots = int(sum(sizes))
     mark("allreduce")
     # ---- stage B: candidates -> owners of their chromosome pair ------------------------------------------------------------
     cands, hists = [], []
     for i in L:
         c, h = engines[i].shard_candidates(cscore, base[i], n_cp)
         cands.append(c); hists.append(h)
-    ghist = comm.allreduce_sum_np(hists)
-    owner = assign_owners(ghist[0], W)
-    parts, counts = [], []
-    for i in L:
-        p, c = engines[i].shard_partition(cands[i], owner, W)
-        parts.append(p); counts.append(c)
-    torch.cuda.synchronize()
-    recv, _ = comm.alltoallv(parts, counts)
+    H = comm.allgather_fixed(hists)[0]                      # [world, n_cp]: also every rank's send counts
+    owner = assign_owners(H.sum(axis=0), W)
+    M = _send_matrix(H, owner, W)
+    parts = [engines[i].shard_partition(cands[i], owner, W, hist_in=hists[i])[0] for i in L]
+    recv = comm.alltoallv(parts, M)
     torch.cuda.synchronize()
     mark("select+exchange")
     # ---- stage C: per owner -- pair best, tandem edges; all-gather the edges; mothers; survivors ------------------------------
-    qe, se = [], []
+    edges, nq = [], []
     for i in L:
         a, b = engines[i].shard_pairs(recv[i], tandem_Nmax)
-        qe.append(a); se.append(b)
-    if tandem_Nmax:
-        qall, _ = comm.allgatherv(qe)
-        sall, _ = comm.allgatherv(se)
-    else:
-        qall, sall = qe, se
-    torch.cuda.synchronize()
+        edges.append(torch.cat([a, b], 0) if tandem_Nmax else a[:0]); nq.append(np.array([a.shape[0], b.shape[0]]))
     surv = []
-    for i in L:
-        s_, mq, ms = engines[i].shard_survivors(qall[i].contiguous(), sall[i].contiguous(), tandem_Nmax)
-        surv.append(s_)
+    if tandem_Nmax:
+        E = comm.allgather_fixed(nq)[0]                     # [world, 2]
+        eall, esz = comm.allgatherv(edges)
+        torch.cuda.synchronize()
+        offs = np.concatenate([[0], np.cumsum(esz)])
+        for i in L:
+            qs = torch.cat([eall[i][int(offs[r]): int(offs[r]) + int(E[r, 0])] for r in range(W)], 0).contiguous()
+            ss = torch.cat([eall[i][int(offs[r]) + int(E[r, 0]): int(offs[r + 1])] for r in range(W)], 0).contiguous()
+            surv.append(engines[i].shard_survivors(qs, ss, tandem_Nmax)[0])
+    else:
+        for i in L:
+            z = edges[i]
+            surv.append(engines[i].shard_survivors(z, z, 0)[0])
     mark("pairs+tandem")
     res = ShardedResult()
     if want_filtered:
@@ -398,78 +385,79 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
         if comm.rank == 0:
             res.filtered = engines[0].shard_order(allsurv[0].contiguous())
         mark("filtered order")
-    # ---- scan per owner; the blocks of all owners in sorted chromosome-pair order --------------------------------------------
-    scans = [engines[i].scan_cands(surv[i], xdist=xdist, ydist=ydist, N=N, intrabound=intrabound) for i in L]
-    mark("scan")
-    anchors_dev, meta = [], []
+    # ---- scan per owner; the blocks of all owners in sorted chromosome-pair order (assembled on the device) -----------------
+    per = []
     for i in L:
-        s_ = scans[i]
-        first = s_.block_start[:-1]
-        bcp = (qchr[s_.q_rank[first]].astype(np.int64) * n_chr_s + schr[s_.s_rank[first]]) if s_.n_blocks else np.zeros(0, np.int64)
-        meta.append(np.stack([bcp, np.diff(s_.block_start)]) if s_.n_blocks else np.zeros((2, 0), np.int64))
-        a = np.stack([s_.q_rank, s_.s_rank, s_.score.view(np.int32)], axis=1) if s_.n_anchors else np.zeros((0, 3), np.int32)
-        anchors_dev.append(torch.from_numpy(np.ascontiguousarray(a)).to("cuda:%d" % engines[i].device))
-    all_meta = comm.allgather_np(meta)
-    all_anchors, _ = comm.allgatherv(anchors_dev)
-    torch.cuda.synchronize()
-    # global block order: sorted chromosome pair (each pair lives on one rank), then the rank's own cluster order
-    m = all_meta[0]
-    cps = np.concatenate([x[0] for x in m]) if m else np.zeros(0, np.int64)
-    sizes = np.concatenate([x[1] for x in m]) if m else np.zeros(0, np.int64)
-    order = np.argsort(cps, kind="stable")
-    starts = np.concatenate([[0], np.cumsum(sizes)])[:-1]
-    A = all_anchors[0].cpu().numpy()
-    nb = len(order)
-    new_sizes = sizes[order]
-    new_start = np.concatenate([[0], np.cumsum(new_sizes)]).astype(np.int64)
-    if nb:
-        idx = np.concatenate([np.arange(starts[b], starts[b] + sizes[b]) for b in order]) if A.shape[0] else np.zeros(0, np.int64)
-    else:
-        idx = np.zeros(0, np.int64)
-    G = A[idx] if len(idx) else np.zeros((0, 3), np.int32)
-    sc = _Scan()
-    sc.q_rank = np.ascontiguousarray(G[:, 0]); sc.s_rank = np.ascontiguousarray(G[:, 1])
-    sc.score = np.ascontiguousarray(G[:, 2]).view(np.float32)
-    sc.block_start = new_start; sc.n_blocks = nb; sc.n_anchors = int(G.shape[0])
-    res.scan = sc
-    a_block = np.repeat(np.arange(nb, dtype=np.int32), new_sizes) if nb else np.zeros(0, np.int32)
+        d = devs[i]
+        rows = engines[i].scan_cands(surv[i], xdist=xdist, ydist=ydist, N=N, intrabound=intrabound, device=True)   # {q, s, score, block}
+        if not hasattr(engines[i], "_chr_t") or engines[i]._chr_t[0] is not qbed:
+            engines[i]._chr_t = (qbed, torch.from_numpy(np.asarray(tq["chr_lex"], dtype=np.int32)).to(d),
+                                 torch.from_numpy(np.asarray(ts["chr_lex"], dtype=np.int32)).to(d))
+        _, qc, sc_ = engines[i]._chr_t
+        if rows.shape[0]:
+            cp = qc[rows[:, 0].long()] * n_chr_s + sc_[rows[:, 1].long()]
+            per.append(torch.cat([rows[:, :3], cp.unsqueeze(1), rows[:, 3:4]], dim=1))
+        else:
+            per.append(torch.zeros((0, 5), dtype=torch.int32, device=d))
+    mark("scan")
+    allA, _ = comm.allgatherv(per)
+    anchors = []
+    for i in L:
+        A = allA[i]
+        if A.shape[0]:
+            # every chromosome pair lives on one rank and a rank's anchors are ordered (pair, cluster, member): a stable
+            # sort by (pair, cluster) of the concatenation is the reference's block order
+            key = A[:, 3].long() * (int(A[:, 4].max()) + 1) + A[:, 4].long()
+            ks, o = torch.sort(key, stable=True)
+            A = A[o]
+            head = torch.ones(A.shape[0], dtype=torch.int32, device=A.device)
+            head[1:] = (ks[1:] != ks[:-1]).to(torch.int32)
+            blk = (torch.cumsum(head, 0) - 1).to(torch.int32)
+        else:
+            head = blk = A[:, 0]
+        anchors.append((A[:, 0].contiguous(), A[:, 1].contiguous(), blk.contiguous(), A[:, 2].contiguous(), head))
+    if comm.rank == 0:
+        aq, as_, ab, asb, head = anchors[0]
+        sc = _Scan()
+        sc.q_rank = aq.cpu().numpy(); sc.s_rank = as_.cpu().numpy(); sc.score = asb.cpu().numpy().view(np.float32)
+        hs = np.flatnonzero(head.cpu().numpy()) if aq.shape[0] else np.zeros(0, np.int64)
+        sc.block_start = np.concatenate([hs, [aq.shape[0]]]).astype(np.int64)
+        sc.n_blocks = len(hs); sc.n_anchors = int(aq.shape[0])
+        res.scan = sc
     mark("anchors gathered")
     # ---- liftover: every rank tests its raw records against all anchors, near hits go to the owners ---------------------------
-    near = [engines[i].shard_near(sc.q_rank, sc.s_rank, base[i], strip_names=strip_names, dist=liftover_dist) for i in L]
-    parts, counts = [], []
+    parts, cnts = [], []
     for i in L:
-        p, c = engines[i].shard_partition(near[i], owner, W)
-        parts.append(p); counts.append(c)
-    torch.cuda.synchronize()
-    recv2, _ = comm.alltoallv(parts, counts)
+        near = engines[i].shard_near(anchors[i][0], anchors[i][1], base[i], strip_names=strip_names, dist=liftover_dist)
+        p, c = engines[i].shard_partition(near, owner, W)
+        parts.append(p); cnts.append(c)
+    M2 = comm.allgather_fixed(cnts)[0]
+    recv2 = comm.alltoallv(parts, M2)
     torch.cuda.synchronize()
     mark("near+exchange")
-    lifts = [engines[i].shard_lift(recv2[i].contiguous(), total_slots, sc.q_rank, sc.s_rank, a_block, dist=liftover_dist) for i in L]
-    mark("lift")
-    # lifted pairs and the per-anchor columns to rank 0: a block's lifted pairs all come from its owner
-    lt = []
+    lt, accs = [], []
     for i in L:
-        l = lifts[i]
-        t = np.stack([l.q_rank, l.s_rank, l.score.view(np.int32), l.block], axis=1) if l.n_lifted else np.zeros((0, 4), np.int32)
-        acc = np.stack([l.accepted.astype(np.int32), l.raw_score.view(np.int32)], axis=1) if len(l.accepted) else np.zeros((0, 2), np.int32)
-        lt.append((torch.from_numpy(np.ascontiguousarray(t)).to("cuda:%d" % engines[i].device),
-                   torch.from_numpy(np.ascontiguousarray(acc)).to("cuda:%d" % engines[i].device)))
-    all_l, _ = comm.allgatherv([x[0] for x in lt])
-    all_a, asz = comm.allgatherv([x[1] for x in lt])
+        cols, acc = engines[i].shard_lift(recv2[i].contiguous(), total_slots, anchors[i][0], anchors[i][1], anchors[i][2],
+                                          dist=liftover_dist, device=True)
+        lt.append(cols.t().contiguous())
+        # accepted / raw score of an anchor line come from the one rank that owns its pair: max over ranks of (flag, bits)
+        accs.append(acc.clone())
+    mark("lift")
+    all_l, _ = comm.allgatherv(lt)
+    comm.allreduce_max_(accs)
     torch.cuda.synchronize()
-    Lh = all_l[0].cpu().numpy()
-    o = np.argsort(Lh[:, 3], kind="stable") if Lh.shape[0] else np.zeros(0, np.int64)
-    Lh = Lh[o]
-    li = _Lift()
-    li.q_rank = np.ascontiguousarray(Lh[:, 0]); li.s_rank = np.ascontiguousarray(Lh[:, 1])
-    li.score = np.ascontiguousarray(Lh[:, 2]).view(np.float32); li.block = np.ascontiguousarray(Lh[:, 3])
-    li.n_lifted = int(Lh.shape[0])
-    Ah = all_a[0].cpu().numpy().reshape(W, -1, 2) if sc.n_anchors else np.zeros((W, 0, 2), np.int32)
-    accm = Ah[:, :, 0]
-    li.accepted = (accm.max(axis=0) if accm.size else np.zeros(0, np.int32)).astype(np.uint8)
-    who = accm.argmax(axis=0) if accm.size else np.zeros(0, np.int64)
-    raw = Ah[who, np.arange(Ah.shape[1]), 1] if accm.size else np.zeros(0, np.int32)
-    li.raw_score = np.ascontiguousarray(raw).view(np.float32)
-    res.lifted = li
+    if comm.rank == 0:
+        Lt = all_l[0]
+        if Lt.shape[0]:                                    # a block's lifted pairs all come from its owner, already in order
+            Lt = Lt[torch.sort(Lt[:, 3], stable=True)[1]]
+        Lh = Lt.cpu().numpy()
+        li = _Lift()
+        li.q_rank = np.ascontiguousarray(Lh[:, 0]); li.s_rank = np.ascontiguousarray(Lh[:, 1])
+        li.score = np.ascontiguousarray(Lh[:, 2]).view(np.float32); li.block = np.ascontiguousarray(Lh[:, 3])
+        li.n_lifted = int(Lh.shape[0])
+        ah = accs[0].cpu().numpy()
+        li.accepted = (ah >> 32).astype(np.uint8)
+        li.raw_score = (ah & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+        res.lifted = li
     mark("lifted gathered")
     return res

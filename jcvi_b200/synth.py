@@ -171,6 +171,68 @@ def make_hits(gq, gs, n_lines, rng, self_mode=False, p_loss=0.25, p_hsp2=0.30, p
     return (Q.astype(np.int32), S.astype(np.int32), qiso, siso, SC.astype(np.int32), pct.astype(np.int32), ints7)
 
 
+def make_hits_chunk(gq, gs, n_lines, chunk, nchunks, seed, p_loss=0.25, p_hsp2=0.30, p_tandem=0.05, frac_mid=0.35,
+                    p_dup=0.2, p_absent=0.001, p_iso=0.05):
+    """Chunk `chunk` of a table that is generated in `nchunks` independent pieces (ranks of a sharded run generate
+    only their own slice): the structured hits (orthologs, second HSPs, tandem copies) come from ONE seeded map shared by
+    all chunks and are dealt round-robin over them; the random hits are the chunk's own.  Same columns as make_hits."""
+    rs = np.random.default_rng(seed)
+    Gq, Gs = gq.G, gs.G
+    copies = max(1, int(round(Gq / Gs)))
+    per = -(-Gq // copies)
+    ortho = np.empty(Gq, dtype=np.int64)
+    for c in range(copies):
+        a, b = c * per, min(Gq, (c + 1) * per)
+        ortho[a:b] = _block_map(b - a, Gs, rs)
+    keep = rs.random(Gq) > p_loss
+    q0 = np.nonzero(keep)[0]
+    s0 = ortho[q0]
+    sc0 = rs.integers(3000, 25000, size=len(q0))
+    Q, S, SC = [q0], [s0], [sc0]
+    m = rs.random(len(q0)) < p_hsp2
+    Q.append(q0[m]); S.append(s0[m]); SC.append((sc0[m] * rs.uniform(0.2, 0.9, m.sum())).astype(np.int64))
+    t = np.nonzero(rs.random(len(q0)) < p_tandem)[0]
+    for k in (1, 2, 3):
+        tk = t[rs.random(len(t)) < (1.0 / k)]
+        Q.append(q0[tk]); S.append(np.minimum(s0[tk] + k, Gs - 1)); SC.append((sc0[tk] * rs.uniform(0.75, 0.98, len(tk))).astype(np.int64))
+    t2 = np.nonzero(rs.random(len(q0)) < p_tandem)[0]
+    for k in (1, 2):
+        tk = t2[rs.random(len(t2)) < (1.0 / k)]
+        Q.append(np.minimum(q0[tk] + k, Gq - 1)); S.append(s0[tk]); SC.append((sc0[tk] * rs.uniform(0.75, 0.98, len(tk))).astype(np.int64))
+    Q = np.concatenate(Q)[chunk::nchunks]; S = np.concatenate(S)[chunk::nchunks]; SC = np.concatenate(SC)[chunk::nchunks]
+    rng = np.random.default_rng(seed * 1000003 + 17 * chunk + 1)
+    n_rand = max(0, n_lines - len(Q))
+    n_mid = int(n_rand * frac_mid)
+    rq = rng.integers(0, Gq, size=n_rand)
+    rsb = rng.integers(0, Gs, size=n_rand)
+    rsc = np.concatenate((rng.integers(600, 9000, size=n_mid), rng.integers(300, 3000, size=n_rand - n_mid)))
+    rng.shuffle(rsc)
+    if n_rand:
+        d = np.nonzero(rng.random(n_rand) < p_dup)[0]
+        src = rng.integers(0, n_rand, size=len(d))
+        rq[d] = rq[src]; rsb[d] = rsb[src]
+    Q = np.concatenate((Q, rq))[:n_lines]; S = np.concatenate((S, rsb))[:n_lines]; SC = np.concatenate((SC, rsc))[:n_lines]
+    n = len(Q)
+    perm = rng.permutation(n)
+    Q, S, SC = Q[perm], S[perm], SC[perm]
+    qiso = np.ones(n, dtype=np.uint8); siso = np.ones(n, dtype=np.uint8)
+    m = rng.random(n) < p_iso; qiso[m] = rng.integers(2, 4, size=m.sum())
+    m = rng.random(n) < p_iso; siso[m] = rng.integers(2, 4, size=m.sum())
+    m = rng.random(n) < p_absent; Q = Q.copy(); Q[m] = Gq + rng.integers(1, 1000, size=m.sum())
+    m = rng.random(n) < p_absent; S = S.copy(); S[m] = Gs + rng.integers(1, 1000, size=m.sum())
+    pct = rng.integers(2500, 10001, size=n)
+    ints7 = np.empty((n, 7), dtype=np.int32)
+    ints7[:, 0] = rng.integers(30, 1500, size=n)
+    ints7[:, 1] = rng.integers(0, 300, size=n)
+    ints7[:, 2] = rng.integers(0, 20, size=n)
+    qa = rng.integers(1, 3000, size=n); qb = qa + ints7[:, 0]
+    sa = rng.integers(1, 3000, size=n); sb = sa + ints7[:, 0]
+    rev = rng.random(n) < 0.3
+    ints7[:, 3] = qa; ints7[:, 4] = qb
+    ints7[:, 5] = np.where(rev, sb, sa); ints7[:, 6] = np.where(rev, sa, sb)
+    return (Q.astype(np.int32), S.astype(np.int32), qiso, siso, SC.astype(np.int32), pct.astype(np.int32), ints7)
+
+
 def format_hits(gq, gs, arrays, ediv=8.0, score_style=0, nthreads=None, header=True):
     """-> bytes of the .last text (with '#' header lines)."""
     Q, S, qiso, siso, SC, pct, ints7 = [np.ascontiguousarray(a) for a in arrays]

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""One genome pair sharded by chromosome pair over the ranks of a torchrun launch (BASELINE configs[2] / [4] shapes):
+
+    torchrun --nproc-per-node N --master-addr 127.0.0.1 tools/run_shard_cp.py [--hits H] [--config c3|c5] [--verify] [--steps K]
+
+The table is the concatenation of 8 seeded chunks; rank r of N generates (only) chunks [8 r / N, 8 (r + 1) / N), so the
+table is the same for every N.  A step = jcvi_b200.sharded.run_sharded over the resident slices; time = max over ranks
+between barriers.  --verify: rank 0 also builds the whole table, runs the single-GPU pipeline and compares every array.
+Prints one JSON line on rank 0.  Reporting aid (bench.py carries the same measurement as `strong_scaling`)."""
+import argparse, hashlib, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import bench
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--hits", type=int, default=200_000_000)
+ap.add_argument("--config", default="c3")
+ap.add_argument("--verify", action="store_true")
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--trace", action="store_true")
+args = ap.parse_args()
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+out = bench.strong_scaling(args.config, args.hits, args.steps, 2, world, rank, local, verify=args.verify, trace=args.trace)
+if rank == 0:
+    print(json.dumps(out), flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
