@@ -113,3 +113,71 @@ def test_prefix_against_oracle(big, tmp_path):
     oracle.blastfilter(last, w["qbed_path"], w["sbed_path"], out_path=last + ".orc")
     bf.main([last, "--qbed=" + w["qbed_path"], "--sbed=" + w["sbed_path"]])
     assert open(last + ".filtered", "rb").read() == open(last + ".orc", "rb").read()
+
+
+def _whole_table_vs_oracle(tmp_path, text, qbed_path, sbed_path, bf_args, scan_args, lift_dist):
+    """`.filtered`, `.anchors`, `.lifted.anchors` of the drop-in CLI functions against the CPU oracle, byte for byte.  The
+    oracle's two long stages (blastfilter and liftover both parse the whole raw table) run side by side: liftover is given
+    the GPU's `.anchors`, which is legitimate only because those are asserted identical to the oracle's own afterwards."""
+    import threading
+    import oracle
+    from jcvi_b200.compara import blastfilter as bf, synteny as syn
+    last = str(tmp_path / "A.B.last")
+    text.tofile(last)
+    beds = ["--qbed=" + qbed_path, "--sbed=" + sbed_path]
+    bf.main([last] + beds + bf_args)
+    ganch = str(tmp_path / "g.anchors")
+    glift = syn.scan([last + ".filtered", ganch] + beds + scan_args + ["--liftover=" + last, "--liftover_dist=%d" % lift_dist])
+    kw = {a.split("=")[0].lstrip("-"): a.split("=")[1] for a in bf_args + scan_args}
+    err = []
+
+    def run_bf():
+        try:
+            oracle.blastfilter(last, qbed_path, sbed_path, out_path=last + ".orc", cscore=float(kw.get("cscore", 0.7)),
+                               tandem_Nmax=int(kw.get("tandem_Nmax", 10)))
+        except Exception as e:      # pragma: no cover
+            err.append(e)
+
+    def run_lift():
+        try:
+            oracle.liftover(last, ganch, qbed_path, sbed_path, out_path=str(tmp_path / "o.lifted"), dist=lift_dist)
+        except Exception as e:      # pragma: no cover
+            err.append(e)
+    th = [threading.Thread(target=run_bf), threading.Thread(target=run_lift)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not err, err
+    rd = lambda p: open(p, "rb").read()
+    assert rd(last + ".filtered") == rd(last + ".orc")
+    oracle.scan(last + ".orc", str(tmp_path / "o.anchors"), qbed_path, sbed_path, dist=int(kw.get("dist", 20)),
+                min_size=int(kw.get("min_size", 4)))
+    assert rd(ganch) == rd(str(tmp_path / "o.anchors"))
+    assert rd(glift) == rd(str(tmp_path / "o.lifted"))
+    return rd(ganch).count(b"\n"), rd(glift).count(b"L\n")
+
+
+@pytest.mark.skipif(os.environ.get("JCVI_B200_SKIP_WHOLE_C2") == "1", reason="whole-table oracle run switched off")
+def test_whole_c2_table_against_oracle(big, tmp_path):
+    """BASELINE configs[1] -- ALL 20 M lines, every stage, byte for byte against the oracle (a few minutes of CPU time)."""
+    w, _ = big
+    na, nl = _whole_table_vs_oracle(tmp_path, w["text"], w["qbed_path"], w["sbed_path"], [], [], 10)
+    assert na > 50_000 and nl > 50_000
+
+
+def test_c3_shape_8m_against_oracle(tmp_path):
+    """BASELINE configs[2] shape (hexaploid vs diploid, 110 k vs 35 k genes, C-score 0.7) at 8 M hits, every stage."""
+    import bench
+    text, n, qbed, sbed = bench.ss_workload("c3", 8_000_000, 1, 0, str(tmp_path))
+    na, nl = _whole_table_vs_oracle(tmp_path, text, str(tmp_path / "W.bed"), str(tmp_path / "H.bed"), ["--cscore=0.7"], [], 10)
+    assert na > 1000 and nl > 100
+
+
+def test_c5_shape_6m_against_oracle(tmp_path):
+    """BASELINE configs[4] shape: sparse anchors (min_size=4), liftover-heavy with dist=20, at 6 M raw hits."""
+    import bench
+    text, n, qbed, sbed = bench.ss_workload("c5", 6_000_000, 1, 0, str(tmp_path))
+    na, nl = _whole_table_vs_oracle(tmp_path, text, str(tmp_path / "W.bed"), str(tmp_path / "H.bed"), [],
+                                    ["--min_size=4", "--dist=20"], 20)
+    assert na > 1000 and nl > 1000
