@@ -220,6 +220,8 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
 
     for _ in range(max(warmup, 1)):
         nf, s, l = step()
+    sampler = ClockSampler(local)
+    sampler.start()
     times = []
     for _ in range(steps):
         barrier()
@@ -227,12 +229,13 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
         nf, s, l = step()
         barrier()
         times.append(time.perf_counter() - t0)
+    clocks = sampler.summary()
     t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) * 1e3
     out = {"workload": c["label"], "hits": int(hits), "n_gpus": world, "ms_per_step": ms, "value": hits / (ms / 1e3), "unit": "hits/s",
-           "steps": steps, "scaling": "strong",
+           "steps": steps, "scaling": "strong", "clocks": clocks,
            "sharding": "single GPU: jx_pipeline" if world == 1 else
                        "text slices per rank; ncclAllReduce(max) of the best-score table; all-to-all of 16-byte candidates to the owner of "
                        "their chromosome pair (blastfilter, liftover); all-gather of tandem edges and anchors",
@@ -418,7 +421,8 @@ def impl_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL's own log (communicator size, transports) goes to stderr: stdout is claimed for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("BENCH_NCCL_DEBUG", "INFO"))
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hits = args.hits or HITS
     t0 = time.time()

@@ -49,6 +49,7 @@ def run_pairs(jobs, cscore=0.7, tandem_Nmax=10, dist=20, min_size=4, liftover_di
             args.append("--liftover_dist=%d" % liftover_dist)
         outs[i] = synteny.scan(args)
     dt = time.perf_counter() - t0
+    run_pairs.last_busy = dt                     # this rank's own busy time (the return value is the max over ranks)
     return mine, outs, max_over_ranks(dt)
 
 
