@@ -343,6 +343,36 @@ int jx_mcscan(jx_ctx* ctx, const double* start, const double* end, const int64_t
 int jx_block_stats(jx_ctx* ctx, const int32_t* block, const int32_t* qrank, const int32_t* srank, int64_t n,
                    int32_t n_blocks, int32_t* qmin, int32_t* qmax, int32_t* smin, int32_t* smax, uint32_t* size,
                    uint32_t* distinct_q, uint32_t* distinct_s, uint64_t* sum_q, uint64_t* sum_s, uint64_t* sum_qs);
+/* ---- jcvi.compara.synfind (src/jcvi/compara/synfind.py:68-240) ---------------------------------
+ * For every gene of the query BED: the syntenic regions find_synteny_region (68-127, "collinear" scoring) returns for
+ * the hits of the window // 2 genes around it, in batch_query's order (130-202: genes in BED order, regions by
+ * decreasing score, equal scores in the order of `sorted(Grouper)`), then the same from the subject side ("mirror",
+ * synfind.py:229-232; not for a self comparison).  Rows [0, n_forward) are the forward pass, [n_forward, n_forward +
+ * n_mirror) the mirror pass, where `query` is a rank of the SUBJECT BED and syntelog / left / right are ranks of the
+ * query BED.  The caller prints accn(query), accn(syntelog), gray, score, the flank distance from left / right
+ * (181-185), orientation and the notes. */
+typedef struct {
+  int64_t n_forward, n_mirror;
+  int64_t n_points;             /* distinct (qi, si) pairs imported (read_blast, synteny.py:255-297)  */
+  int32_t* query;               /* rank of the gene the region was found for                          */
+  int32_t* syntelog;            /* rank of the closest flanker's partner (the anchor column)          */
+  int32_t* left;                /* subject rank of the first / last point of the chosen track         */
+  int32_t* right;
+  int32_t* score;
+  uint8_t* gray;                /* 0 "S" syntelog, 1 "G" gray (query outside the group's x range), 2 "F" flanked */
+  uint8_t* minus;               /* 1: orientation "-" (the LDS was strictly longer)                   */
+  /* 0 lines, 1 distinct pairs, 2 '#' lines */
+  int64_t stats[8];
+} jx_synfind_result;
+/* window_half = opts.window // 2, cutoff = int(opts.cutoff * opts.window) (synfind.py:132-133) */
+int jx_synfind_text(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, int strip_names, int window_half,
+                    int cutoff, jx_synfind_result* out);
+/* batch_query (synfind.py:130-202) on caller-supplied DISTINCT (qi, si) pairs; passes: 1 = as given, 2 = transposed
+ * (transpose=True: BEDs swapped), 3 = both */
+int jx_synfind_points(jx_ctx* ctx, const int32_t* qi, const int32_t* si, int64_t n, int window_half, int cutoff, int passes,
+                      jx_synfind_result* out);
+void jx_synfind_result_free(jx_synfind_result* r);
+
 /* float32 best score per name id of the open jx_cscore_begin session (first n entries) */
 int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
 /* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */

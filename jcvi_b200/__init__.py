@@ -30,6 +30,13 @@ def install():
         jblast.filter = gblast.filter
     except ImportError:
         pass
+    try:                                   # compara.synfind
+        from .compara import synfind as gsf
+        jsf = importlib.import_module("jcvi.compara.synfind")
+        for name in ("main", "synfind", "batch_query"):
+            setattr(jsf, name, getattr(gsf, name))
+    except ImportError:
+        pass
     try:
         jcat = importlib.import_module("jcvi.compara.catalog")
         if hasattr(jcat, "blastfilter_main"):

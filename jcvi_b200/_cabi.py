@@ -56,6 +56,12 @@ class JxLiftoverResult(ctypes.Structure):
                 ("block", c_i32p), ("accepted", c_u8p), ("raw_score", c_f32p), ("stats", ctypes.c_int64 * 8)]
 
 
+class JxSynfindResult(ctypes.Structure):
+    _fields_ = [("n_forward", ctypes.c_int64), ("n_mirror", ctypes.c_int64), ("n_points", ctypes.c_int64), ("query", c_i32p),
+                ("syntelog", c_i32p), ("left", c_i32p), ("right", c_i32p), ("score", c_i32p), ("gray", c_u8p), ("minus", c_u8p),
+                ("stats", ctypes.c_int64 * 8)]
+
+
 EXPORTS = [
     "jx_ctx_create", "jx_ctx_destroy", "jx_last_error", "jx_version", "jx_launch_count", "jx_stream_handle",
     "jx_tokenizer_timing", "jx_bed_load", "jx_pair_setup", "jx_blastfilter", "jx_filter_result_free",
@@ -64,6 +70,7 @@ EXPORTS = [
     "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter", "jx_mcscan", "jx_block_stats",
     "jx_pipeline", "jx_shard_reset", "jx_shard_slots", "jx_shard_candidates", "jx_shard_partition", "jx_shard_pairs",
     "jx_shard_survivors", "jx_shard_order", "jx_scan_cands", "jx_shard_near", "jx_shard_lift", "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
+    "jx_synfind_text", "jx_synfind_points", "jx_synfind_result_free",
 ]
 
 _lib = None
@@ -159,6 +166,12 @@ def lib():
         L.jx_block_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32] + [ctypes.c_void_p] * 10
         L.jx_free.argtypes = [ctypes.c_void_p]
         L.jx_free.restype = None
+        L.jx_synfind_text.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.POINTER(JxSynfindResult)]
+        L.jx_synfind_points.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.POINTER(JxSynfindResult)]
+        L.jx_synfind_result_free.argtypes = [ctypes.POINTER(JxSynfindResult)]
+        L.jx_synfind_result_free.restype = None
         sizes = (ctypes.c_int32 * 6)()
         L.jx_abi_sizes(sizes)
         mine = [ctypes.sizeof(x) for x in (JxBed, JxFilterOpts, JxFilterResult, JxScanOpts, JxScanResult, JxLiftoverResult)]

@@ -97,6 +97,22 @@ class LiftoverResult(object):
         self.stats = dict(zip(("lines", "hits", "anchors", "lifted", "tree_walked", "comments"), list(r.stats)[:6]))
 
 
+class SynfindResult(object):
+    """Rows of jx_synfind_*: [0, n_forward) the forward pass, the rest the mirror pass (ranks of the other BED)."""
+
+    def __init__(self, r):
+        n = r.n_forward + r.n_mirror
+        self.n_forward, self.n_mirror, self.n_points = r.n_forward, r.n_mirror, r.n_points
+        self.query = C.as_np(r.query, n, np.int32)
+        self.syntelog = C.as_np(r.syntelog, n, np.int32)
+        self.left = C.as_np(r.left, n, np.int32)
+        self.right = C.as_np(r.right, n, np.int32)
+        self.score = C.as_np(r.score, n, np.int32)
+        self.gray = C.as_np(r.gray, n, np.uint8)
+        self.minus = C.as_np(r.minus, n, np.uint8)
+        self.stats = dict(zip(("lines", "hits", "comments"), list(r.stats)[:3]))
+
+
 class Engine(object):
     """One per GPU.  Not thread-safe (like a jx_ctx)."""
 
@@ -676,6 +692,30 @@ class Engine(object):
                                             *[C.ptr(out[k]) for k in ("qmin", "qmax", "smin", "smax", "size", "distinct_q",
                                                                       "distinct_s", "sum_q", "sum_s", "sum_qs")]))
         return out
+
+    def synfind_text(self, text, strip_names=True, window=40, cutoff=0.1):
+        """jx_synfind_text (compara/synfind.py:130-133 derive the two integers)."""
+        p, n, dev, keep = _text_ptr(text)
+        r = C.JxSynfindResult()
+        rc = self.lib.jx_synfind_text(self.ctx, p, n, dev, int(bool(strip_names)), int(window) // 2, int(cutoff * window),
+                                      ctypes.byref(r))
+        try:
+            self._check(rc)
+            return SynfindResult(r)
+        finally:
+            self.lib.jx_synfind_result_free(ctypes.byref(r))
+
+    def synfind_points(self, qi, si, window_half, cutoff, passes=1):
+        qi = np.ascontiguousarray(qi, dtype=np.int32)
+        si = np.ascontiguousarray(si, dtype=np.int32)
+        r = C.JxSynfindResult()
+        rc = self.lib.jx_synfind_points(self.ctx, C.ptr(qi), C.ptr(si), len(qi), int(window_half), int(cutoff), int(passes),
+                                        ctypes.byref(r))
+        try:
+            self._check(rc)
+            return SynfindResult(r)
+        finally:
+            self.lib.jx_synfind_result_free(ctypes.byref(r))
 
     # ---- instrumentation ----------------------------------------------------------------------------
     def launch_count(self):
