@@ -67,6 +67,12 @@ int jx_tokenizer_timing(jx_ctx* ctx, int reset, double* ms, int64_t* launches, i
  * jx_text_release or jx_ctx_destroy.  Pinned host memory gives full PCIe speed. */
 int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t* device_ptr);
 int jx_text_release(jx_ctx* ctx);
+/* The same from a FILE (replaces must_open, src/jcvi/formats/base.py:473-550, for the path's input
+ * table): plain files are read by several threads straight into pinned pieces and copied as they complete; blocked gzip
+ * (BGZF, as bgzip writes) is inflated block-parallel by the same threads; any other gzip is streamed through one
+ * inflating thread with the copies running behind it.  *kind: 0 plain, 1 gzip stream, 2 BGZF.  JX_EUNSUPPORTED for
+ * bzip2 (the caller keeps its own reader).  The result is the context's held text, exactly as after jx_text_upload. */
+int jx_file_upload(jx_ctx* ctx, const char* path, uint64_t* device_ptr, int64_t* nbytes, int32_t* kind);
 /* jx_liftover_text on the SAME resident text re-uses the records jx_blastfilter just tokenized (the
  * reference parses the raw table twice: blastfilter.py:48 and synteny.py:1939).  on = 0 turns that
  * off (every call tokenizes); default 1.  Results are identical either way. */

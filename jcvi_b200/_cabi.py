@@ -70,7 +70,7 @@ EXPORTS = [
     "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter", "jx_mcscan", "jx_block_stats",
     "jx_pipeline", "jx_shard_reset", "jx_shard_slots", "jx_shard_candidates", "jx_shard_partition", "jx_shard_pairs",
     "jx_shard_survivors", "jx_shard_order", "jx_scan_cands", "jx_shard_near", "jx_shard_lift", "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
-    "jx_synfind_text", "jx_synfind_points", "jx_synfind_result_free",
+    "jx_synfind_text", "jx_synfind_points", "jx_synfind_result_free", "jx_file_upload",
 ]
 
 _lib = None
@@ -136,6 +136,8 @@ def lib():
                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.jx_text_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64)]
         L.jx_text_release.argtypes = [ctypes.c_void_p]
+        L.jx_file_upload.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), c_i64p,
+                                     ctypes.POINTER(ctypes.c_int32)]
         L.jx_set_record_reuse.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.jx_distinct_names.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),

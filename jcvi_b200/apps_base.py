@@ -39,6 +39,22 @@ class OptionParser(ArgumentParser):
         self.add_argument("-o", "--outfile", default=outfile, help="Outfile name")
 
 
+class no_gc(object):
+    """The writers build hundreds of thousands of small row objects next to BEDs of 10^5 objects; every young-generation
+    overflow would make the cyclic collector walk all of them (measured: 0.3 s of a 0.5 s C2 run).  Nothing here creates
+    reference cycles, so collection is paused for the duration of an action."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+
+
 def file_key(path):
     """Identity of a file's current contents for in-process caches: (absolute path, mtime in ns, size)."""
     import os

@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-from ..apps_base import OptionParser, logger, read_text_file, file_key
+from ..apps_base import OptionParser, logger, file_key, no_gc
 from ..engine import get_engine
 
 
@@ -67,14 +67,13 @@ def blastfilter_main(blast_file, p, opts):
     qbed, sbed, qorder, sorder, is_self = check_beds(blast_file, p, opts)
     eng = get_engine()
     eng.load_pair(qbed, sbed, is_self)
-    text = read_text_file(blast_file)
     excl = _exclude_keys(opts.exclude, qorder, sorder) if opts.exclude else None
     if excl is not None:
         logger.debug("running excluded pairs (--exclude `{}`) ..".format(opts.exclude))
     # one upload: the table stays resident, and `synteny liftover` of the same (unchanged) file in this process --
     # catalog.ortholog's next step -- neither reads nor copies it again
     key = file_key(blast_file)
-    dev = eng.upload(text)
+    dev = eng.upload_file(blast_file)
     res = eng.blastfilter(dev, strip_names=opts.strip_names, cscore=opts.cscore, tandem_Nmax=opts.tandem_Nmax,
                           exclude_keys=excl, want_text=True, want_mothers=bool(opts.tandems_only))
     eng.remember_text(key, dev)
@@ -116,7 +115,8 @@ def main(args):
     opts, args = p.parse_args(args)
     if len(args) != 1:
         sys.exit(not p.print_help())
-    blastfilter_main(args[0], p, opts)
+    with no_gc():
+        blastfilter_main(args[0], p, opts)
 
 
 if __name__ == "__main__":

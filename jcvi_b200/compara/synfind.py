@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-from ..apps_base import OptionParser, logger, read_text_file
+from ..apps_base import OptionParser, logger
 from ..engine import get_engine
 from .synteny import check_beds
 
@@ -88,7 +88,7 @@ def synfind(blastfile, p, opts):
     qbed, sbed, qorder, sorder, is_self = check_beds(blastfile, p, opts)
     eng = get_engine()
     eng.load_pair(qbed, sbed, is_self)
-    res = eng.synfind_text(read_text_file(blastfile), strip_names=opts.strip_names, window=opts.window, cutoff=opts.cutoff)
+    res = eng.synfind_text(eng.upload_file(blastfile), strip_names=opts.strip_names, window=opts.window, cutoff=opts.cutoff)
     logger.debug("A total of %d BLAST imported from `%s`.", res.stats["hits"], blastfile)
 
     c = conn = None

@@ -10,7 +10,7 @@ from collections.abc import Iterable
 
 import numpy as np
 
-from ..apps_base import OptionParser, file_key, logger, read_text_file
+from ..apps_base import OptionParser, file_key, logger, no_gc, read_text_file
 from ..engine import get_engine
 from ..formats.bed import Bed
 from .base import AnchorFile
@@ -184,12 +184,17 @@ def write_anchors(res, qbed, sbed, anchor_file):
 
 
 def scan(args):
+    with no_gc():
+        return _scan(args)
+
+
+def _scan(args):
     """
     %prog scan blastfile anchor_file [options]
 
     pull out syntenic anchors from blastfile based on single-linkage algorithm
     """
-    p = OptionParser(scan.__doc__)
+    p = OptionParser(_scan.__doc__)
     p.add_argument("-n", "--min_size", dest="n", type=int, default=4, help="minimum number of anchors in a cluster")
     p.add_argument("--intrabound", default=300, type=int,
                    help="Lower bound of intra-chromosomal blocks (only for self comparison)")
@@ -216,17 +221,33 @@ def scan(args):
         dargs += ["--no_strip_names"]
     liftover_dist = opts.liftover_dist or dist // 2
     dargs += ["--dist={}".format(liftover_dist)]
-    return liftover([lo, anchor_file] + dargs, _blocks=blocks)
+    block_of = np.repeat(np.arange(res.n_blocks, dtype=np.int32), np.diff(res.block_start))
+    return liftover([lo, anchor_file] + dargs, _blocks=blocks, _ranks=(res.q_rank, res.s_rank, block_of))
 
 
-def liftover(args, _blocks=None):
+def _anchor_ranks(lines, qorder, sorder):
+    """ranks of every anchor line (-1 when a name is not in its BED) + its block index"""
+    a_qi = np.fromiter((qorder[r[0]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
+                       dtype=np.int32, count=len(lines))
+    a_si = np.fromiter((sorder[r[1]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
+                       dtype=np.int32, count=len(lines))
+    a_block = np.fromiter((bi for _, bi in lines), dtype=np.int32, count=len(lines))
+    return a_qi, a_si, a_block
+
+
+def liftover(args, _blocks=None, _ranks=None):
+    with no_gc():
+        return _liftover(args, _blocks, _ranks)
+
+
+def _liftover(args, _blocks=None, _ranks=None):
     """
     %prog liftover blastfile anchorfile [options]
 
     Typical use for this program is given a list of anchors (syntennic
     genes), choose from the blastfile the pairs that are close to the anchors.
     """
-    p = OptionParser(liftover.__doc__)
+    p = OptionParser(_liftover.__doc__)
     p.set_stripnames()
     p.set_outfile(outfile=None)
 
@@ -238,41 +259,62 @@ def liftover(args, _blocks=None):
     # _blocks: scan() hands over the blocks of the anchors file it has just written
     ac = AnchorFile.from_blocks(anchor_file, _blocks) if _blocks is not None else AnchorFile(anchor_file)
     lines = [(row, bi) for bi, block in enumerate(ac.blocks) for row in block]
-    a_qi = np.fromiter((qorder[r[0]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
-                       dtype=np.int32, count=len(lines))
-    a_si = np.fromiter((sorder[r[1]][0] if (len(r) > 1 and r[0] in qorder and r[1] in sorder) else -1 for r, _ in lines),
-                       dtype=np.int32, count=len(lines))
-    a_block = np.fromiter((bi for _, bi in lines), dtype=np.int32, count=len(lines))
+    if _ranks is not None and len(_ranks[0]) == len(lines):
+        # scan() also hands over the ranks of the rows it wrote (the names came from these ranks)
+        a_qi, a_si, a_block = (np.ascontiguousarray(x, dtype=np.int32) for x in _ranks)
+    else:
+        a_qi, a_si, a_block = _anchor_ranks(lines, qorder, sorder)
     logger.debug("A total of {0} anchors imported.".format(int((a_qi >= 0).sum())))
 
     # the raw table blastfilter uploaded in this process, if it is still resident and the file is unchanged
-    text = eng.recall_text(file_key(blast_file))
+    key = file_key(blast_file)
+    text = eng.recall_text(key)
     if text is None:
-        text = read_text_file(blast_file)
+        text = eng.upload_file(blast_file)
+        eng.remember_text(key, text)
     res = eng.liftover_text(text, a_qi, a_si, a_block, strip_names=opts.strip_names, dist=dist)
     logger.debug("A total of %d BLAST imported from `%s`.", res.stats["hits"], blast_file)
 
     qa = qbed.tables()["accns"]
     sa = sbed.tables()["accns"]
-    for q, s, sc, b in zip(res.q_rank.tolist(), res.s_rank.tolist(), res.score.astype(np.float64).tolist(),
-                           res.block.tolist()):
-        ac.blocks[b].append((qa[q], sa[s], _int_str(sc) + "L"))
     logger.debug("%d new pairs found (dist=%d).", res.n_lifted, dist)
     newanchorfile = opts.outfile or anchor_file.rsplit(".", 1)[0] + ".lifted.anchors"
+    # The lifted pairs join their blocks, then AnchorFile.filter_blocks (compara/base.py:52-83).  `accepted` maps a pair to
+    # the raw score of the pair, so the dictionary is not needed: the device already looked every anchor line up
+    # (res.accepted / res.raw_score, index-aligned with `lines`), and a lifted pair carries its own raw score + "L".
+    lifted_sc = res.score.astype(np.int64).astype(str).tolist()          # str(int(score)), synteny.py:1961
     if res.stats["hits"]:
-        # AnchorFile.filter_blocks (compara/base.py:52-83) with `accepted` restricted to the
-        # pairs the anchors file mentions (the device did the lookups)
-        accepted = {}
-        acc, raw = res.accepted.tolist(), res.raw_score.astype(np.float64).tolist()
-        for (row, _), ok, sc in zip(lines, acc, raw):
-            if ok:
-                accepted[(row[0], row[1])] = _int_str(sc)
-        for q, s, sc in zip(res.q_rank.tolist(), res.s_rank.tolist(), res.score.astype(np.float64).tolist()):
-            accepted[(qa[q], sa[s])] = _int_str(sc)
-        ac.filter_blocks(accepted)
+        raw = res.raw_score.astype(np.int64).astype(str).tolist()
+        blocks = [[] for _ in ac.blocks]
+        dropped = fixed = 0
+        for (row, bi), ok, rs in zip(lines, res.accepted.tolist(), raw):
+            if not ok:
+                dropped += 1
+                continue
+            sc = row[2]
+            if sc != rs and sc != rs + "L":
+                sc, fixed = rs, fixed + 1
+            blocks[bi].append((row[0], row[1], sc))
+    else:
+        blocks = [list(b) for b in ac.blocks]
+        dropped = fixed = None
+    for q, s, sc, b in zip(res.q_rank.tolist(), res.s_rank.tolist(), lifted_sc, res.block.tolist()):
+        blocks[b].append((qa[q], sa[s], sc + "L"))
+    if dropped is not None:
+        kept = [b for b in blocks if b]
+        logger.debug("Removed %d existing anchors", dropped)
+        if len(kept) != len(blocks):
+            logger.debug("Removed %d empty blocks", len(blocks) - len(kept))
+        logger.debug("Corrected scores for %d anchors", fixed)
+        blocks = kept
+    ac.blocks = blocks
     ac.print_to_file(filename=newanchorfile)
     _summary_blocks(ac.blocks)                     # of the file just written
     return newanchorfile
+
+
+scan.__doc__ = _scan.__doc__
+liftover.__doc__ = _liftover.__doc__
 
 
 def _best_pairs(qs, ss, ts):

@@ -78,6 +78,7 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   cudaFree(ctx->lines_dev);
   for (auto& b : ctx->pin_pool) cudaFreeHost(b.p);
   if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
+  if (ctx->io_pin) cudaFreeHost(ctx->io_pin);
   if (ctx->pin_scan) cudaFreeHost(ctx->pin_scan);
   if (ctx->ws) cudaFree(ctx->ws);
   cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);

@@ -111,6 +111,7 @@ struct jx_ctx {
   size_t pin_small_cap = 0;
   char* pin_scan = nullptr;      // the same for scan results (their copy may still be in flight while liftover stages its own)
   size_t pin_scan_cap = 0;
+  void* io_pin = nullptr;        // jx_file_upload: ring of pinned pieces (jx_io.cu), grow-never, freed with the context
   uint8_t* held_text = nullptr;
   int64_t held_n = 0;
   int64_t held_cap = 0;

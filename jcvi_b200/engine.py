@@ -290,6 +290,25 @@ class Engine(object):
         self._check(self.lib.jx_text_upload(self.ctx, p, n, ctypes.byref(out)))
         return DeviceText(out.value, n, keep)
 
+    def upload_file(self, path):
+        """jx_file_upload: the table of `path` resident on the device -- plain files through reader threads and pinned
+        pieces, `.gz` inflated by the library (block-parallel for BGZF); bzip2 falls back to Python's reader."""
+        import os
+        out = ctypes.c_uint64()
+        n = ctypes.c_int64()
+        kind = ctypes.c_int32()
+        self._held_key = None
+        rc = self.lib.jx_file_upload(self.ctx, os.fsencode(path), ctypes.byref(out), ctypes.byref(n), ctypes.byref(kind))
+        if rc == C.JX_EUNSUPPORTED:
+            from .apps_base import read_text_file
+            return self.upload(read_text_file(path))
+        if rc == C.JX_EARG and not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self._check(rc)
+        dev = DeviceText(out.value, n.value, None)
+        dev.kind = ("plain", "gzip", "bgzf")[kind.value]
+        return dev
+
     def release_text(self):
         self._held_key = None
         self._check(self.lib.jx_text_release(self.ctx))
