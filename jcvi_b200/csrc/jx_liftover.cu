@@ -24,75 +24,8 @@ namespace {
 
 inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
 
-__global__ void k_select_valid(const uint4* __restrict__ recs, uint32_t n, uint4* out, uint32_t* out_idx, uint32_t* counter) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t nround = (n + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-    uint4 r = make_uint4(JX_NOREC, 0, 0, 0);
-    if (i < n) r = __ldcs(recs + i);
-    bool keep = r.x != JX_NOREC;
-    uint32_t slot = warp_append(keep, counter);
-    if (keep) { out[slot] = r; out_idx[slot] = i; }
-  }
-}
-__global__ void k_make_keys(const uint4* __restrict__ C, uint32_t n, int sb, uint64_t* keys, uint32_t* vals) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uint4 r = C[j];
-  keys[j] = ((uint64_t)r.x << sb) | r.y;
-  vals[j] = j;
-}
-__global__ void k_run_first(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                            const uint32_t* __restrict__ Cidx, uint32_t n, uint32_t* flag, uint32_t* pick) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const uint64_t k = keys[t];
-  const bool head = (t == 0) || keys[t - 1] != k;
-  flag[t] = head;
-  if (!head) return;
-  uint32_t bj = vals[t], bi = Cidx[bj];
-  for (uint32_t u = t + 1; u < n && keys[u] == k; ++u) {
-    uint32_t j = vals[u], i = Cidx[j];
-    if (i < bi) { bj = j; bi = i; }
-  }
-  pick[t] = bj;
-}
-// unique hits sorted by (qi, si): key, score, line ordinal
-__global__ void k_scatter_hits(const uint64_t* keys, const uint32_t* pick, const uint32_t* flag, const uint32_t* pos,
-                               uint32_t n, const uint4* C, const uint32_t* Cidx, uint64_t* hkey, float* hsc, uint32_t* hline) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n || !flag[t]) return;
-  uint32_t o = pos[t], j = pick[t];
-  hkey[o] = keys[t];
-  hsc[o] = __uint_as_float(C[j].z);
-  hline[o] = Cidx[j];
-}
 
-// accepted[(query, subject)] lookup for every anchor line
-__global__ void k_lookup(const uint64_t* hkey, const float* hsc, uint32_t nh, const int32_t* aq, const int32_t* as_,
-                         uint32_t na, int sb, uint8_t* acc, float* raw) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= na) return;
-  acc[t] = 0; raw[t] = 0.f;
-  if (aq[t] < 0 || as_[t] < 0) return;
-  uint64_t key = ((uint64_t)(uint32_t)aq[t] << sb) | (uint32_t)as_[t];
-  uint32_t lo = 0, hi = nh;
-  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (hkey[mid] < key) lo = mid + 1; else hi = mid; }
-  if (lo < nh && hkey[lo] == key) { acc[t] = 1; raw[t] = hsc[lo]; }
-}
 
-__global__ void k_iota_u32(uint32_t* p, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = i;
-}
-// block id of every anchor in sorted order; two equal neighbours = duplicate anchors (read_anchors' assert)
-__global__ void k_anchor_blocks(const uint64_t* keys, const uint32_t* order, const uint32_t* block_in, uint32_t n,
-                                uint32_t* block_out, uint32_t* dup) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  block_out[i] = block_in[order[i]];
-  if (i && keys[i] == keys[i - 1]) atomicExch(dup, 1u);
-}
 __global__ void k_rowptr(const uint64_t* akey, uint32_t na, int sb, uint32_t G, uint32_t* rowptr) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g > G) return;
@@ -190,35 +123,6 @@ __global__ void k_keep_near(const uint4* __restrict__ cand, const uint32_t* __re
   if (keep) { out[slot] = r; out_idx[slot] = cand_idx[t]; }
 }
 
-// exact minimum L1 distance (< dist) to the anchors of the same chromosome pair
-__global__ void k_nearest(const uint64_t* __restrict__ hkey, uint32_t nh, int sb, const uint64_t* __restrict__ akey,
-                          const uint32_t* __restrict__ ablock, const uint32_t* __restrict__ rowptr,
-                          const int32_t* __restrict__ qbeg, const int32_t* __restrict__ qend,
-                          const int32_t* __restrict__ schr, int dist, uint32_t* best_a, uint8_t* state) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nh) return;
-  const uint64_t k = hkey[t];
-  const uint64_t smask = (1ull << sb) - 1;
-  const int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & smask);
-  const int32_t lo = max(x - (dist - 1), qbeg[x]), hi = min(x + dist - 1, qend[x] - 1);
-  const uint32_t t0 = rowptr[lo], t1 = rowptr[hi + 1];
-  const int32_t cy = schr[y];
-  int best = dist; uint32_t bt = 0xFFFFFFFFu, bblk = 0; bool amb = false;
-  for (uint32_t u = t0; u < t1; ++u) {
-    const uint64_t a = akey[u];
-    const int32_t ax = (int32_t)(a >> sb), ay = (int32_t)(a & smask);
-    const int d = abs(ax - x) + abs(ay - y);
-    if (d > best) continue;
-    if (schr[ay] != cy) continue;
-    if (d < best) { best = d; bt = u; bblk = ablock[u]; amb = false; }
-    else if (bt != 0xFFFFFFFFu && ablock[u] != bblk) amb = true;
-  }
-  // state: 0 none within dist / is an anchor itself, 1 lifted (unambiguous), 2 needs the tree walk
-  uint8_t st = 0;
-  if (bt != 0xFFFFFFFFu && best > 0) st = amb ? 2 : 1;
-  state[t] = st;
-  best_a[t] = bt;
-}
 
 // ---- scipy cKDTree emulation ------------------------------------------------------------------
 struct KNode { long long split; int split_dim, lesser, greater, start, end, pad; };
@@ -402,38 +306,9 @@ int run_walk(jx_ctx* ctx, Arena& arena, const HostTrees& T, const std::vector<lo
   return JX_OK;
 }
 
-__global__ void k_lift_flags(const uint8_t* state, uint32_t n, uint32_t* f1, uint32_t* f2) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  f1[t] = state[t] != 0;
-  f2[t] = state[t] == 2;
-}
-__global__ void k_gather_amb(const uint8_t* state, const uint32_t* pos2, uint32_t n, uint32_t* amb_hit) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n && state[t] == 2) amb_hit[pos2[t]] = t;
-}
 __global__ void k_patch_amb(const uint32_t* amb_hit, const uint32_t* amb_block, uint32_t n, uint32_t* hit_block) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) hit_block[amb_hit[t]] = amb_block[t];
-}
-__global__ void k_hit_block(const uint8_t* state, const uint32_t* best_a, const uint32_t* ablock, uint32_t n, uint32_t* hit_block) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) hit_block[t] = state[t] == 1 ? ablock[best_a[t]] : 0u;
-}
-// sort keys of the lifted hits: pass 1 (cp << 32 | line), pass 2 block
-__global__ void k_lift_keys(const uint8_t* state, const uint32_t* pos1, const uint64_t* hkey, const uint32_t* hline, int sb,
-                            const int32_t* qchr, const int32_t* schr, uint64_t nschr, uint32_t n, uint64_t* k1, uint32_t* v1) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n || state[t] == 0) return;
-  uint64_t k = hkey[t];
-  int32_t x = (int32_t)(k >> sb), y = (int32_t)(k & ((1ull << sb) - 1));
-  uint64_t cp = (uint64_t)qchr[x] * nschr + (uint64_t)schr[y];
-  k1[pos1[t]] = (cp << 32) | hline[t];
-  v1[pos1[t]] = t;
-}
-__global__ void k_block_keys(const uint32_t* v, const uint32_t* hit_block, uint32_t n, uint64_t* k2) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) k2[t] = hit_block[v[t]];
 }
 __global__ void k_emit_lifted(const uint32_t* v, uint32_t n, const uint64_t* hkey, const float* hsc, const uint32_t* hit_block,
                               int sb, int32_t* oq, int32_t* os, float* osc, int32_t* ob) {
@@ -445,20 +320,6 @@ __global__ void k_emit_lifted(const uint32_t* v, uint32_t n, const uint64_t* hke
   osc[t] = hsc[h]; ob[t] = (int32_t)hit_block[h];
 }
 
-int compact_positions(jx_ctx* ctx, Arena& arena, const uint32_t* flag, size_t n, uint32_t*& pos, uint32_t& count) {
-  count = 0; pos = nullptr;
-  if (!n) return JX_OK;
-  JX_ALLOC(p, uint32_t, n, false);
-  int rc = jx_exclusive_sum(ctx, arena, flag, p, n);
-  if (rc) return rc;
-  uint32_t last[2];
-  JX_CK(cudaMemcpyAsync(&last[0], p + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaMemcpyAsync(&last[1], flag + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  JX_CK(cudaStreamSynchronize(ctx->stream));
-  count = last[0] + last[1];
-  pos = p;
-  return JX_OK;
-}
 
 }  // namespace
 

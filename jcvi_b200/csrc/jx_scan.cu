@@ -119,7 +119,32 @@ __global__ void k_points_from_keys(const uint64_t* __restrict__ keys, const uint
   psc[t] = __uint_as_float(recs[vals[t]].z);
 }
 
-// synteny_scan inner loops: for point i walk back while x_i - x_j <= xdist (same chromosome pair)
+// synteny_scan inner loops (synteny.py:402-434): point i is joined with every earlier point j of its chromosome pair with
+// 0 <= x_i - x_j <= xdist and |y_i - y_j| <= ydist.  Points are sorted by (chromosome pair, x, y), so the candidates of a
+// row (one x) are a y-interval of that row: the walk goes back point by point while it is inside the interval and SEEKS
+// (galloping + binary search over the global order) past the parts of a row that lie above y_i + ydist or below
+// y_i - ydist.  In the usual sparse case a row holds one or two points and the seek's first probe already lands in the
+// previous row -- the cost of a plain walk; in dense tables (--cscore=0 on a polyploid: hundreds of points per row) a
+// row costs O(log) + its matches instead of its length.
+__device__ __forceinline__ bool key_gt(const uint64_t c, const int32_t x, const int32_t y, const uint64_t tc, const int32_t tx,
+                                       const int32_t ty) {
+  return c != tc ? c > tc : (x != tx ? x > tx : y > ty);
+}
+// largest index < j whose (cp, x, y) <= (tc, tx, ty), or -1; precondition: the key at j is greater than the target
+__device__ __forceinline__ int64_t seek_le(const int32_t* __restrict__ px, const int32_t* __restrict__ py,
+                                           const uint64_t* __restrict__ cp, int64_t j, const uint64_t tc, const int32_t tx,
+                                           const int32_t ty) {
+  int64_t hi = j, lo = j - 1, step = 1;
+  while (lo >= 0 && key_gt(cp[lo], px[lo], py[lo], tc, tx, ty)) {
+    hi = lo; step <<= 1; lo = hi - step;
+    if (lo < 0) { lo = -1; break; }
+  }
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (key_gt(cp[mid], px[mid], py[mid], tc, tx, ty)) hi = mid; else lo = mid;
+  }
+  return lo;
+}
 __global__ void k_link(const int32_t* __restrict__ px, const int32_t* __restrict__ py, const uint64_t* __restrict__ cp,
                        uint32_t n, int xdist, int ydist, int is_self, int intrabound, uint32_t* parent, uint8_t* hasprev) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,19 +152,23 @@ __global__ void k_link(const int32_t* __restrict__ px, const int32_t* __restrict
   const int32_t xi = px[i], yi = py[i];
   const uint64_t ci = cp[i];
   const int di = abs(xi - yi);
+  const int32_t ylo = yi - ydist, yhi = yi + ydist;
   bool any = false;
-  for (int64_t j = (int64_t)i - 1; j >= 0; --j) {
+  int64_t j = (int64_t)i - 1;
+  while (j >= 0) {
     if (cp[j] != ci) break;
     const int32_t xj = px[j];
     if (xi - xj > xdist) break;
     const int32_t yj = py[j];
-    if (abs(yi - yj) > ydist) continue;
+    if (yj > yhi) { j = seek_le(px, py, cp, j, ci, xj, yhi); continue; }                 // down to the interval (or the row before)
+    if (yj < ylo) { j = seek_le(px, py, cp, j, ci, xj - 1, 0x7FFFFFFF); continue; }      // the rest of the row is below it
+    bool ok = true;
     if (is_self) {
-      int dj = abs(xj - yj);
-      if ((di < dj ? di : dj) < intrabound) continue;
+      const int dj = abs(xj - yj);
+      ok = (di < dj ? di : dj) >= intrabound;
     }
-    uf_union(parent, i, (uint32_t)j);
-    any = true;
+    if (ok) { uf_union(parent, i, (uint32_t)j); any = true; }
+    --j;
   }
   hasprev[i] = any;
 }
@@ -152,32 +181,27 @@ __global__ void k_label(uint32_t* parent, const uint8_t* hasprev, uint32_t n, ui
   if (hasprev[i]) atomicMin(birth + r, i);
 }
 
-// #distinct qi per component: point i counts iff no earlier point of its row (same cp, same x)
-// carries the same label
-__global__ void k_count_x(const int32_t* px, const uint64_t* cp, const uint32_t* label, uint32_t n, uint32_t* nx) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t l = label[i];
-  for (int64_t j = (int64_t)i - 1; j >= 0 && cp[j] == cp[i] && px[j] == px[i]; --j)
-    if (label[j] == l) return;
-  atomicAdd(nx + l, 1u);
-}
-// #distinct si per component: (label, y) pairs through a hash set; the thread that inserts a new pair counts it
-__global__ void k_count_y(const uint32_t* __restrict__ label, const int32_t* __restrict__ py, uint32_t n, unsigned long long* K,
-                          uint32_t mask, uint32_t* ny) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t l = label[i], y = (uint32_t)py[i];
-  const unsigned long long key = ((unsigned long long)l << 32) | y;
-  uint32_t h = l * 0x9E3779B1u ^ y * 0x85EBCA77u;
+// #distinct qi and #distinct si per component: (label, x) and (label, y) pairs through ONE hash set (x entries carry
+// bit 31); the thread that inserts a new pair counts it
+__device__ __forceinline__ void count_distinct(unsigned long long* K, uint32_t mask, uint32_t l, uint32_t v, uint32_t* cnt) {
+  const unsigned long long key = ((unsigned long long)l << 32) | v;
+  uint32_t h = l * 0x9E3779B1u ^ v * 0x85EBCA77u;
   h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
   uint32_t slot = h & mask;
   for (;;) {
     const unsigned long long prev = atomicCAS(K + slot, 0xFFFFFFFFFFFFFFFFull, key);
-    if (prev == 0xFFFFFFFFFFFFFFFFull) { atomicAdd(ny + l, 1u); return; }
+    if (prev == 0xFFFFFFFFFFFFFFFFull) { atomicAdd(cnt + l, 1u); return; }
     if (prev == key) return;
     slot = (slot + 1u) & mask;
   }
+}
+__global__ void k_count_xy(const uint32_t* __restrict__ label, const int32_t* __restrict__ px, const int32_t* __restrict__ py,
+                           uint32_t n, unsigned long long* K, uint32_t mask, uint32_t* nx, uint32_t* ny) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t l = label[i];
+  count_distinct(K, mask, l, (uint32_t)px[i] | 0x80000000u, nx);
+  count_distinct(K, mask, l, (uint32_t)py[i], ny);
 }
 
 // flag = the point's cluster passes min(#distinct qi, #distinct si) >= N; output key = (birth of the cluster, index):
@@ -250,13 +274,12 @@ int scan_sorted_points(jx_ctx* ctx, Arena& arena, const int32_t* px, const int32
   JX_LAUNCH(k_link, nblk(n, 128), 128, 0, px, py, cp, n, o->xdist, o->ydist, is_self, o->intrabound, parent, hasprev);
   JX_LAUNCH(k_label, nblk(n), 256, 0, parent, hasprev, n, label, birth);
   JX_TRACE("scan: link+label");
-  JX_LAUNCH(k_count_x, nblk(n), 256, 0, px, cp, label, n, nx);
   {
     uint32_t hcap = 1024;
-    while (hcap < 2u * n + 16u && hcap < (1u << 31)) hcap <<= 1;
+    while ((uint64_t)hcap < 4ull * n + 16u && hcap < (1u << 31)) hcap <<= 1;
     JX_ALLOC(HK, unsigned long long, hcap, false);
     JX_CK(cudaMemsetAsync(HK, 0xFF, (size_t)hcap * 8, ctx->stream));
-    JX_LAUNCH(k_count_y, nblk(n), 256, 0, label, py, n, HK, hcap - 1u, ny);
+    JX_LAUNCH(k_count_xy, nblk(n), 256, 0, label, px, py, n, HK, hcap - 1u, nx, ny);
   }
   JX_TRACE("scan: counts");
   const int ib = jx_bits((uint64_t)n);

@@ -127,6 +127,7 @@ class Engine(object):
         self.device = device
         self._pair = None
         self.Gq = self.Gs = 0
+        self.n_name_ids = 0
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -175,6 +176,7 @@ class Engine(object):
         self._pair = key
         self._beds = (qbed, sbed)          # keep alive: the cache key uses id()
         self.Gq, self.Gs = tq["G"], ts["G"]
+        self.n_name_ids = len(ids)
 
     def load_names(self, names):
         """No BED (formats.blast cscore): `names` (sorted, distinct byte strings) become the name table

@@ -114,6 +114,38 @@ def _slice_for_engine(text_np, owner, lo, hi):
     return text_np[lo:hi]
 
 
+_STATUS = ((NotImplementedError, 1), (ZeroDivisionError, 2), (MemoryError, 3))
+
+
+def _status_code(exc):
+    if exc is None:
+        return 0
+    for cls, code in _STATUS:
+        if isinstance(exc, cls):
+            return code
+    return 4
+
+
+def _agree(err, device=None):
+    """All ranks learn whether any rank failed (one tiny all-reduce) and stop together: without it a rank-local
+    NotImplementedError / ZeroDivisionError would leave the other ranks waiting in the next collective."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        if err is not None:
+            raise err
+        return
+    nccl = dist.get_backend() == "nccl"
+    t = torch.tensor([_status_code(err)], dtype=torch.int32, device=("cuda:%d" % device) if nccl else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    code = int(t.item())
+    if code:
+        if err is not None:
+            raise err
+        cls = {c: k for k, c in _STATUS}.get(code, RuntimeError)
+        raise cls("another rank failed in its slice of the table (see its log); all ranks stop together")
+
+
 def blastfilter_sharded(text, qbed, sbed, is_self, strip_names=True, cscore=0.7, tandem_Nmax=10, exclude_keys=None,
                         want_text=True, engine=None):
     """Collective over all ranks; returns the FilterResult on rank 0 (None elsewhere)."""
@@ -124,18 +156,27 @@ def blastfilter_sharded(text, qbed, sbed, is_self, strip_names=True, cscore=0.7,
     eng.load_pair(qbed, sbed, is_self)
     text, owner = _as_u8(text)
     lo, hi = slice_bounds(text, rank, world)
-    ptr, n = eng.cscore_begin(_slice_for_engine(text, owner, lo, hi), strip_names=strip_names, exclude_keys=exclude_keys)
+    err = None
+    try:
+        ptr, n = eng.cscore_begin(_slice_for_engine(text, owner, lo, hi), strip_names=strip_names, exclude_keys=exclude_keys)
+    except Exception as e:                                   # noqa: BLE001 -- agreed on below
+        err = e
+    _agree(err, eng.device)
     if world > 1 and dist.is_initialized():
         best = eng.best_table_tensor(ptr, n)
         dist.all_reduce(best, op=dist.ReduceOp.MAX)          # ncclAllReduce(max) over NVLink, in place
         torch.cuda.synchronize(eng.device)
-    if _use_device_exchange():                               # survivors go GPU to GPU over NVLink
-        lines, cnt = eng.cscore_finish(cscore, device=True)
+    dev_x = _use_device_exchange()
+    try:
+        lines, cnt = eng.cscore_finish(cscore, device=True) if dev_x else eng.cscore_finish(cscore)
+    except Exception as e:                                   # noqa: BLE001 -- ZeroDivisionError on one rank only
+        err = e
+    _agree(err, eng.device)
+    if dev_x:                                                # survivors go GPU to GPU over NVLink
         merged = _gather_device(lines, device=eng.device)
         if rank != 0:
             return None
     else:
-        lines, cnt = eng.cscore_finish(cscore)
         parts = _gather_bytes(lines, device=eng.device)
         if rank != 0:
             return None
@@ -151,13 +192,19 @@ def liftover_sharded(text, a_qi, a_si, a_block, qbed, sbed, is_self, strip_names
     eng.load_pair(qbed, sbed, is_self)
     text, owner = _as_u8(text)
     lo, hi = slice_bounds(text, rank, world)
-    if _use_device_exchange():
-        lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist, device=True)
+    dev_x = _use_device_exchange()
+    err = None
+    try:
+        lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist,
+                                    device=dev_x)
+    except Exception as e:                                   # noqa: BLE001 -- agreed on below
+        err = e
+    _agree(err, eng.device)
+    if dev_x:
         merged = _gather_device(lines, device=eng.device)
         if rank != 0:
             return None
     else:
-        lines, cnt = eng.near_lines(_slice_for_engine(text, owner, lo, hi), a_qi, a_si, strip_names=strip_names, dist=dist)
         parts = _gather_bytes(lines, device=eng.device)
         if rank != 0:
             return None
@@ -309,6 +356,20 @@ class _Lift(object):
     pass
 
 
+def _raise_agreed(codes, failed):
+    """codes: one status per rank (0 = fine).  Every rank raises the exception class of the lowest failing rank; a rank
+    that failed itself re-raises its own exception (it carries the message)."""
+    codes = [int(c) for c in np.asarray(codes).reshape(-1)]
+    bad = [r for r, c in enumerate(codes) if c]
+    if not bad:
+        return
+    for e in failed:
+        if e is not None:
+            raise e
+    cls = {code: c for c, code in _STATUS}.get(codes[bad[0]], RuntimeError)
+    raise cls("rank %d failed in its slice of the table (see its log); all ranks stop together" % bad[0])
+
+
 def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7, tandem_Nmax=10, xdist=20, ydist=20, N=4,
                 intrabound=300, liftover_dist=10, comm=None, engines=None, want_filtered=True, mark=None):
     """blastfilter -> scan -> liftover of ONE genome pair whose raw table is cut into `slices` (one per LOCAL rank: a list
@@ -336,12 +397,20 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
     base = [comm.local[i] * stride for i in L]
     total_slots = (1 << 31) - 1
     # ---- stage A: tokenize the slice, best-score table, all-reduce(max) -------------------------------------------------
+    # A failure that only one rank sees (an unsupported line in its slice, ZeroDivisionError from a score <= 0, an
+    # allocation) must not leave the others waiting in a collective: the rank keeps taking part with empty data, its
+    # status travels with the histogram all-gather below, and every rank raises the same exception after it.
     bests = []
+    failed = [None] * len(engines)
     for i in L:
-        ptr, n_ids = engines[i].cscore_begin(slices[i], strip_names=strip_names)
-        bests.append(engines[i].best_table_tensor(ptr, n_ids))
-        if engines[i].shard_slots() >= stride:
-            raise NotImplementedError("a slice with more than 2^31 / world record slots")
+        try:
+            ptr, n_ids = engines[i].cscore_begin(slices[i], strip_names=strip_names)
+            bests.append(engines[i].best_table_tensor(ptr, n_ids))
+            if engines[i].shard_slots() >= stride:
+                raise NotImplementedError("a slice with more than 2^31 / world record slots")
+        except Exception as e:                               # noqa: BLE001 -- re-raised on every rank below
+            failed[i] = e
+            bests.append(torch.zeros(max(engines[i].n_name_ids, 1), dtype=torch.int32, device=devs[i]))
     mark("tokenize")
     comm.allreduce_max_(bests)
     torch.cuda.synchronize()
@@ -349,9 +418,20 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
     # ---- stage B: candidates -> owners of their chromosome pair ------------------------------------------------------------
     cands, hists = [], []
     for i in L:
-        c, h = engines[i].shard_candidates(cscore, base[i], n_cp)
-        cands.append(c); hists.append(h)
-    H = comm.allgather_fixed(hists)[0]                      # [world, n_cp]: also every rank's send counts
+        c = h = None
+        if failed[i] is None:
+            try:
+                c, h = engines[i].shard_candidates(cscore, base[i], n_cp)
+            except Exception as e:                           # noqa: BLE001
+                failed[i] = e
+        if failed[i] is not None:
+            c, h = torch.zeros((0, 4), dtype=torch.int32, device=devs[i]), np.zeros(n_cp, dtype=np.uint32)
+        cands.append(c)
+        hists.append(np.concatenate([np.asarray(h, dtype=np.uint32), [_status_code(failed[i])]]).astype(np.uint32))
+    H = comm.allgather_fixed(hists)[0]                      # [world, n_cp + 1]: every rank's send counts + its status
+    _raise_agreed(H[:, n_cp], failed)
+    H = np.ascontiguousarray(H[:, :n_cp])
+    hists = [h[:n_cp] for h in hists]
     owner = assign_owners(H.sum(axis=0), W)
     M = _send_matrix(H, owner, W)
     parts = [engines[i].shard_partition(cands[i], owner, W, hist_in=hists[i])[0] for i in L]

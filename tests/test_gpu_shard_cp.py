@@ -42,3 +42,32 @@ def test_sharded_equals_single_gpu(tmp_path, case, world):
     for e in engines:
         e.shard_reset()
         e.close()
+
+
+@pytest.mark.parametrize("what", ["unsupported", "zerodiv"])
+def test_rank_local_failure_stops_every_rank(tmp_path, what):
+    """An unsupported line / a score <= 0 in ONE slice: the failing rank keeps taking part with empty data, its status
+    rides on the histogram all-gather, and the driver raises the reference's exception instead of hanging."""
+    from jcvi_b200 import sharded, synth
+    from jcvi_b200.engine import Engine
+    from jcvi_b200.formats.bed import Bed
+    qbed, sbed, last = synth.write_dataset(str(tmp_path), "A", "B", 33, 3000, 3000, 60000, Kq=5, Ks=5)
+    qb, sb = Bed(qbed), Bed(sbed)
+    text = np.fromfile(last, dtype=np.uint8)
+    world = 3
+    slices = []
+    for r in range(world):
+        lo, hi = sharded.slice_bounds(text, r, world)
+        slices.append(text[lo:hi].copy())
+    line = bytes(slices[1][: int(np.flatnonzero(slices[1] == 10)[0])]).split(b"\t")
+    line[11] = b"inf" if what == "unsupported" else b"0"
+    bad = np.frombuffer(b"\t".join(line) + b"\n", dtype=np.uint8)
+    slices[1] = np.concatenate([bad, slices[1]])
+    engines = [Engine(0) for _ in range(world)]
+    try:
+        with pytest.raises(NotImplementedError if what == "unsupported" else ZeroDivisionError):
+            sharded.run_sharded(slices, qb, sb, comm=sharded.LocalComm(world), engines=engines)
+    finally:
+        for e in engines:
+            e.shard_reset()
+            e.close()

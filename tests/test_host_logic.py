@@ -140,9 +140,20 @@ mine = assign_pairs(sizes, world)[rank]
 t = max_over_ranks(1.0 + rank)
 got = [None] * world
 dist.all_gather_object(got, mine)
+# a failure only one rank sees stops every rank with the same exception class instead of leaving the rest in a collective
+from jcvi_b200.sharded import _agree, _raise_agreed
+_agree(None)
+try:
+    _agree(ZeroDivisionError("float division by zero") if rank == 1 else None)
+    agreed = "no exception"
+except ZeroDivisionError as e:
+    agreed = "ZeroDivisionError"
+flags = [None] * world
+dist.all_gather_object(flags, agreed)
 if rank == 0:
     assert sorted(i for p in got for i in p) == list(range(len(sizes))), got
     assert t == float(world), t
+    assert flags == ["ZeroDivisionError"] * world, flags
     print("GLOO_OK", got)
 dist.destroy_process_group()
 '''
@@ -156,6 +167,22 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_sharded_status_agreement_picks_one_exception_class():
+    import numpy as np
+    import pytest
+    from jcvi_b200.sharded import _raise_agreed, _status_code
+    _raise_agreed(np.zeros(4, dtype=np.uint32), [None])
+    mine = NotImplementedError("unsupported line 17")
+    with pytest.raises(NotImplementedError, match="line 17"):
+        _raise_agreed([0, _status_code(mine), 0, 2], [mine])           # the failing rank re-raises its own exception
+    with pytest.raises(NotImplementedError, match="rank 1"):
+        _raise_agreed([0, _status_code(mine), 0, 2], [None])           # the others raise the class of the lowest failing rank
+    with pytest.raises(ZeroDivisionError):
+        _raise_agreed([0, 0, 0, _status_code(ZeroDivisionError())], [None])
+    with pytest.raises(RuntimeError):
+        _raise_agreed([_status_code(KeyError("x"))], [None])
 
 
 def test_install_rebinds_the_reference_names(tmp_path, monkeypatch):
