@@ -119,32 +119,11 @@ __global__ void k_points_from_keys(const uint64_t* __restrict__ keys, const uint
   psc[t] = __uint_as_float(recs[vals[t]].z);
 }
 
-// synteny_scan inner loops (synteny.py:402-434): point i is joined with every earlier point j of its chromosome pair with
-// 0 <= x_i - x_j <= xdist and |y_i - y_j| <= ydist.  Points are sorted by (chromosome pair, x, y), so the candidates of a
-// row (one x) are a y-interval of that row: the walk goes back point by point while it is inside the interval and SEEKS
-// (galloping + binary search over the global order) past the parts of a row that lie above y_i + ydist or below
-// y_i - ydist.  In the usual sparse case a row holds one or two points and the seek's first probe already lands in the
-// previous row -- the cost of a plain walk; in dense tables (--cscore=0 on a polyploid: hundreds of points per row) a
-// row costs O(log) + its matches instead of its length.
-__device__ __forceinline__ bool key_gt(const uint64_t c, const int32_t x, const int32_t y, const uint64_t tc, const int32_t tx,
-                                       const int32_t ty) {
-  return c != tc ? c > tc : (x != tx ? x > tx : y > ty);
-}
-// largest index < j whose (cp, x, y) <= (tc, tx, ty), or -1; precondition: the key at j is greater than the target
-__device__ __forceinline__ int64_t seek_le(const int32_t* __restrict__ px, const int32_t* __restrict__ py,
-                                           const uint64_t* __restrict__ cp, int64_t j, const uint64_t tc, const int32_t tx,
-                                           const int32_t ty) {
-  int64_t hi = j, lo = j - 1, step = 1;
-  while (lo >= 0 && key_gt(cp[lo], px[lo], py[lo], tc, tx, ty)) {
-    hi = lo; step <<= 1; lo = hi - step;
-    if (lo < 0) { lo = -1; break; }
-  }
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (key_gt(cp[mid], px[mid], py[mid], tc, tx, ty)) hi = mid; else lo = mid;
-  }
-  return lo;
-}
+// synteny_scan inner loops (synteny.py:402-434): for point i walk back while x_i - x_j <= xdist (same chromosome pair).
+// Measured on a dense set (9.2 M points, dist 40, ~800 earlier points per window, tests/perf/scan_dense.py): a variant
+// that seeks past the parts of a row outside [y_i - ydist, y_i + ydist] (galloping + binary search) took 56 ms against
+// 61 ms for this walk and was 1.7x slower on the usual sparse set -- the dense case is bound by the ~20 unions per point
+// into a few giant components, not by the walk -- so the plain walk stays.
 __global__ void k_link(const int32_t* __restrict__ px, const int32_t* __restrict__ py, const uint64_t* __restrict__ cp,
                        uint32_t n, int xdist, int ydist, int is_self, int intrabound, uint32_t* parent, uint8_t* hasprev) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,26 +131,23 @@ __global__ void k_link(const int32_t* __restrict__ px, const int32_t* __restrict
   const int32_t xi = px[i], yi = py[i];
   const uint64_t ci = cp[i];
   const int di = abs(xi - yi);
-  const int32_t ylo = yi - ydist, yhi = yi + ydist;
   bool any = false;
-  int64_t j = (int64_t)i - 1;
-  while (j >= 0) {
+  for (int64_t j = (int64_t)i - 1; j >= 0; --j) {
     if (cp[j] != ci) break;
     const int32_t xj = px[j];
     if (xi - xj > xdist) break;
     const int32_t yj = py[j];
-    if (yj > yhi) { j = seek_le(px, py, cp, j, ci, xj, yhi); continue; }                 // down to the interval (or the row before)
-    if (yj < ylo) { j = seek_le(px, py, cp, j, ci, xj - 1, 0x7FFFFFFF); continue; }      // the rest of the row is below it
-    bool ok = true;
+    if (abs(yi - yj) > ydist) continue;
     if (is_self) {
-      const int dj = abs(xj - yj);
-      ok = (di < dj ? di : dj) >= intrabound;
+      int dj = abs(xj - yj);
+      if ((di < dj ? di : dj) < intrabound) continue;
     }
-    if (ok) { uf_union(parent, i, (uint32_t)j); any = true; }
-    --j;
+    uf_union(parent, i, (uint32_t)j);
+    any = true;
   }
   hasprev[i] = any;
 }
+
 
 __global__ void k_label(uint32_t* parent, const uint8_t* hasprev, uint32_t n, uint32_t* label, uint32_t* birth) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -60,7 +60,15 @@ def test_rank_local_failure_stops_every_rank(tmp_path, what):
         lo, hi = sharded.slice_bounds(text, r, world)
         slices.append(text[lo:hi].copy())
     line = bytes(slices[1][: int(np.flatnonzero(slices[1] == 10)[0])]).split(b"\t")
-    line[11] = b"inf" if what == "unsupported" else b"0"
+    if what == "unsupported":
+        line[11] = b"inf"
+    else:
+        # blastfilter.py:235 divides by max(best score of the two genes): 0 only when neither gene scores anywhere else
+        qn, sn = line[0].split(b".")[0], line[1].split(b".")[0]
+        for r in range(world):
+            rows = [x for x in bytes(slices[r]).split(b"\n") if x and qn not in x and sn not in x]
+            slices[r] = np.frombuffer(b"\n".join(rows) + b"\n", dtype=np.uint8)
+        line[11] = b"0"
     bad = np.frombuffer(b"\t".join(line) + b"\n", dtype=np.uint8)
     slices[1] = np.concatenate([bad, slices[1]])
     engines = [Engine(0) for _ in range(world)]
