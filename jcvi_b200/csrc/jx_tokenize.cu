@@ -686,6 +686,13 @@ __device__ __forceinline__ void classify64_ascii(const uint4& v0, const uint4& v
   }
 }
 
+// one 256-bit load of a 32-byte table slot (LDG.E.256 on sm_100: half the LSU work of two LDG.128)
+__device__ __forceinline__ void ldg256(const uint4* p, uint4& lo, uint4& hi) {       // p: 32-byte aligned, read-only data
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+
 // does the word hold a '|' (0x7C) byte?  (exact "any zero byte" test on w ^ 0x7C7C7C7C)
 __device__ __forceinline__ uint32_t bar_in(uint32_t w) {
   const uint32_t v = w ^ 0x7C7C7C7Cu;
@@ -994,7 +1001,9 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize6(con
                 const uint32_t dq = __ldg(a.qdisp + (hq >> a.qbshift)), ds = __ldg(a.sdisp + (hs >> a.sbshift));
                 const uint4* pq = a.qtab + 2 * jx::slot_index(hq, dq, a.qcshift);
                 const uint4* ps = a.stab + 2 * jx::slot_index(hs, ds, a.scshift);
-                const uint4 tq0 = __ldg(pq), tq1 = __ldg(pq + 1), ts0 = __ldg(ps), ts1 = __ldg(ps + 1);
+                uint4 tq0, tq1, ts0, ts1;                // one 256-bit load per 32-byte slot (LDG.E.256: half the LSU work of two LDG.128)
+          ldg256(pq, tq0, tq1);
+          ldg256(ps, ts0, ts1);
 #endif
                 if (jx::fast_line6_rest(B, wr, mwr, mnr, s, len, L)) {
                   const uint32_t dfq = (tq0.z ^ q0) | (tq0.w ^ q1) | (tq1.x ^ q2) | tq1.y | tq1.z | tq1.w;
@@ -1151,16 +1160,26 @@ struct Counters7 {
   unsigned long long* stats;     // the launch's global statistics (first bad offset: atomicMin, rare)
 };
 
-// One line [s, e) of a staged window -> record (version 6's per-line body).  `tile_off` = offset stored in the record.
-__device__ __forceinline__ uint4 parse_line7(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
-                                             const int64_t base, const int s, const int e, const int win, const bool v6,
-                                             const Counters7& c) {
+// One line [s, e) of a staged window -> record (version 6's per-line body); false = the line needs `parse_slow7`.
+// The slow route is NOT called from here: a call inside the hot loop makes the compiler keep the loop's state (line
+// index, slot pointer, mask pointers) in local memory around it -- the reloads were the kernel's largest long-scoreboard
+// stall (profiles/r2_v7b_*: 11 % of the samples).  The kernel lists the refused lines and handles them after the loop.
+__device__ __forceinline__ bool parse_fast7(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
+                                            const int s, const int e, const int win, const bool v6, const Counters7& c,
+                                            uint4& rec) {
   const uint32_t* smw = reinterpret_cast<const uint32_t*>(sm);
-  uint4 rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
+  rec = make_uint4(JX_NOREC, 0u, 0u, (uint32_t)s << 1);
   int what = WH_NONE;
   bool fastdone = false;
   const int len = e - s;
-  if (len > 0 && sm[s] == '#') {
+  // the first twelve bytes of the line (the query name of a regular line); also answer "is it a '#' line?" -- the text
+  // bytes the per-line code needs come from these words, not from byte loads (shared-memory wavefronts are what the
+  // kernel has least of: 32 lanes read 32 different lines, every load is a 2-3-way bank conflict)
+  const int qa = s, iq = qa >> 2;
+  const uint32_t shq = (uint32_t)(qa & 3) * 8u;
+  const uint32_t xq0 = smw[iq], xq1 = smw[iq + 1], xq2 = smw[iq + 2], xq3 = smw[iq + 3];
+  uint32_t q0 = __funnelshift_r(xq0, xq1, shq), q1 = __funnelshift_r(xq1, xq2, shq), q2 = __funnelshift_r(xq2, xq3, shq);
+  if (len > 0 && (q0 & 0xFFu) == (uint32_t)'#') {
     what = WH_COMMENT; fastdone = true;
   } else if (v6 && e + 8 <= win) {
     const SmemWords wr{smw};
@@ -1168,14 +1187,14 @@ __device__ __forceinline__ uint4 parse_line7(const TokArgs& a, const uint8_t* sm
     const SmemText B{sm, smw};
     jx::Line6 L;
     if (jx::fast_line6_names(mwr, mnr, s, len, L)) {
-      const int qa = s, sa = s + L.t0 + 1;
+      const int sa = s + L.t0 + 1;
       int lq = L.t0, lsn = L.t1 - L.t0 - 1;
-      const int iq = qa >> 2, is = sa >> 2;
-      const uint32_t shq = (uint32_t)(qa & 3) * 8u, shs = (uint32_t)(sa & 3) * 8u;
-      const uint32_t xq0 = smw[iq], xq1 = smw[iq + 1], xq2 = smw[iq + 2], xq3 = smw[iq + 3];
+      const int is = sa >> 2;
+      const uint32_t shs = (uint32_t)(sa & 3) * 8u;
       const uint32_t xs0 = smw[is], xs1 = smw[is + 1], xs2 = smw[is + 2], xs3 = smw[is + 3];
-      uint32_t q0 = __funnelshift_r(xq0, xq1, shq), q1 = __funnelshift_r(xq1, xq2, shq), q2 = __funnelshift_r(xq2, xq3, shq);
       uint32_t s0 = __funnelshift_r(xs0, xs1, shs), s1 = __funnelshift_r(xs1, xs2, shs), s2 = __funnelshift_r(xs2, xs3, shs);
+      // (taking the names' last two bytes from q0..q2 / s0..s2 instead of two byte loads each was measured 3.6 % slower:
+      //  the selects and shifts cost more issue slots than the loads cost wavefronts)
       if (a.strip) { lq = jx::strip6(B, qa, lq, q0); lsn = jx::strip6(B, sa, lsn, s0); }
       if (lq <= 12 && lsn <= 12 && lq >= 1 && lsn >= 1) {
         q0 &= jx::name_mask(lq, 0); q1 &= jx::name_mask(lq, 1); q2 &= jx::name_mask(lq, 2);
@@ -1192,7 +1211,9 @@ __device__ __forceinline__ uint4 parse_line7(const TokArgs& a, const uint8_t* sm
           const uint32_t dq = __ldg(a.qdisp + (hq >> a.qbshift)), ds = __ldg(a.sdisp + (hs >> a.sbshift));
           const uint4* pq = a.qtab + 2 * jx::slot_index(hq, dq, a.qcshift);
           const uint4* ps = a.stab + 2 * jx::slot_index(hs, ds, a.scshift);
-          const uint4 tq0 = __ldg(pq), tq1 = __ldg(pq + 1), ts0 = __ldg(ps), ts1 = __ldg(ps + 1);
+          uint4 tq0, tq1, ts0, ts1;                // one 256-bit load per 32-byte slot (LDG.E.256: half the LSU work of two LDG.128)
+          ldg256(pq, tq0, tq1);
+          ldg256(ps, ts0, ts1);
           if (jx::fast_line6_rest(B, wr, mwr, mnr, s, len, L)) {
             const uint32_t dfq = (tq0.z ^ q0) | (tq0.w ^ q1) | (tq1.x ^ q2) | tq1.y | tq1.z | tq1.w;
             const uint32_t dfs = (ts0.z ^ s0) | (ts0.w ^ s1) | (ts1.x ^ s2) | ts1.y | ts1.z | ts1.w;
@@ -1226,20 +1247,25 @@ __device__ __forceinline__ uint4 parse_line7(const TokArgs& a, const uint8_t* sm
       }
     }
   }
-  if (!fastdone) {
-    const SlowOut so = slow_line(a, sm, s_w, s_n, base, s, e, win);
-    rec = so.rec; what = so.what;
-    if (what == WH_MAPPED) {
-      if (a.n_excl) {
-        const uint64_t key = ((uint64_t)rec.x << 32) | rec.y;
-        int64_t l = 0, h = a.n_excl;
-        while (l < h) { const int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
-        if (l < a.n_excl && a.excl[l] == key) { what = WH_EXCL; rec.x = JX_NOREC; }
-      }
-      if (what == WH_MAPPED && a.best && __uint_as_float(rec.z) > 0.f) {
-        atomicMax(a.best + a.qnid[rec.x], rec.z);
-        atomicMax(a.best + a.snid[rec.y], rec.z);
-      }
+  if (fastdone && what != WH_MAPPED) atomicAdd(c.cnt + what, 1u);   // comment / unmapped / excluded
+  return fastdone;
+}
+// the lines parse_fast7 refused: version-5 route, then the generic scanner
+__device__ __noinline__ uint4 parse_slow7(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
+                                          const int64_t base, const int s, const int e, const int win, const Counters7 c) {
+  const SlowOut so = slow_line(a, sm, s_w, s_n, base, s, e, win);
+  uint4 rec = so.rec;
+  int what = so.what;
+  if (what == WH_MAPPED) {
+    if (a.n_excl) {
+      const uint64_t key = ((uint64_t)rec.x << 32) | rec.y;
+      int64_t l = 0, h = a.n_excl;
+      while (l < h) { const int64_t m = (l + h) >> 1; if (a.excl[m] < key) l = m + 1; else h = m; }
+      if (l < a.n_excl && a.excl[l] == key) { what = WH_EXCL; rec.x = JX_NOREC; }
+    }
+    if (what == WH_MAPPED && a.best && __uint_as_float(rec.z) > 0.f) {
+      atomicMax(a.best + a.qnid[rec.x], rec.z);
+      atomicMax(a.best + a.snid[rec.y], rec.z);
     }
   }
   if (what != WH_MAPPED) {
@@ -1308,6 +1334,24 @@ __device__ __forceinline__ void classify32_ascii(const uint4& v0, const uint4& v
   nm = jx::top_bytes(pn[0], pn[1], pn[2], pn[3]);
 }
 
+// 16 bytes -> 16 bits of each mask (low half-word of the results)
+__device__ __forceinline__ void classify16_ascii(const uint4& v, uint32_t& wm, uint32_t& nm, uint32_t& any) {
+  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+  uint32_t pw[2], pn[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t a = x[2 * k], b = x[2 * k + 1];
+    any |= a | b;
+    const uint32_t twa = a + 0x5F5F5F5Fu, twb = b + 0x5F5F5F5Fu;
+    const uint32_t una = ((a ^ 0x30303030u) + 0x76767676u) & ((a ^ 0x09090909u) + 0x7F7F7F7Fu);
+    const uint32_t unb = ((b ^ 0x30303030u) + 0x76767676u) & ((b ^ 0x09090909u) + 0x7F7F7F7Fu);
+    pw[k] = (((~twa >> 4) & 0x08080808u) | (~twb & 0x80808080u)) * 0x00204081u;
+    pn[k] = (((una >> 4) & 0x08080808u) | (unb & 0x80808080u)) * 0x00204081u;
+  }
+  wm = __byte_perm(pw[0], pw[1], 0x0073);          // byte 3 of each product; the upper half is not stored
+  nm = __byte_perm(pn[0], pn[1], 0x0073);
+}
+
 struct Tok7Args {
   TokArgs t;
   int64_t sub_begin, nsub; // this launch handles the sub-tiles [sub_begin, nsub)
@@ -1319,18 +1363,25 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_W7_MINBLK) k_tokenize7(cons
   constexpr int NW = JX_TOK_THREADS / 32;
   __shared__ __align__(128) uint8_t s_text[W7_NBUF][W7_STAGE];
   __shared__ __align__(8) uint64_t s_bar[W7_NBUF];
-  __shared__ __align__(16) uint32_t s_wm[NW][W7_WIN / 32 + 4];   // byte <= 0x20 (+ slack: 64-bit windows read past the window)
-  __shared__ __align__(16) uint32_t s_nm[NW][W7_WIN / 32 + 4];   // byte is neither a digit nor a tab
-  __shared__ uint16_t s_lp[NW][W7_LC + 2];                       // start offset of every line of the window
-  __shared__ uint32_t s_cnt[NW][WH_NONE + 2];                    // per warp: lines that are not plain records, by kind; [WH_NONE + 1] = lines
+  // everything a warp owns sits in ONE struct: the masks, the line list, the to-do list and the counters are constant
+  // offsets from a single base register (five separate arrays cost five address registers in the per-line code)
+  struct __align__(16) Warp7 {
+    uint32_t w[W7_WIN / 32 + 4];   // byte <= 0x20 (+ slack: 64-bit windows read past the window)
+    uint32_t n[W7_WIN / 32 + 4];   // byte is neither a digit nor a tab
+    uint16_t lp[W7_LC + 2];        // start offset of every line of the window
+    uint8_t todo[W7_LC + 2];       // lines of the window left to the slow route
+    uint32_t cnt[WH_NONE + 2];     // lines that are not plain records, by kind; [WH_NONE + 1] = lines
+  };
+  __shared__ Warp7 s_warp[NW];
   __shared__ uint32_t s_head;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* const s_w = s_wm[warp];
-  uint32_t* const s_n = s_nm[warp];
-  uint16_t* const s_lpos = s_lp[warp];
-  const Counters7 c{s_cnt[warp], a.stats};
-  if (lane < WH_NONE + 2) s_cnt[warp][lane] = 0u;
+  Warp7& SW = s_warp[warp];
+  uint32_t* const s_w = SW.w;
+  uint32_t* const s_n = SW.n;
+  uint16_t* const s_lpos = SW.lp;
+  const Counters7 c{SW.cnt, a.stats};
+  if (lane < WH_NONE + 2) SW.cnt[lane] = 0u;
   bool overflow = false;
   uint32_t maxlines = 0;
   const bool v6 = !a.is_self;
@@ -1390,15 +1441,21 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_W7_MINBLK) k_tokenize7(cons
       }
     }
     // ---- byte classes: lane handles the 32-byte pieces lane, lane + 32, lane + 64, lane + 96 --------------------------
+    // (16-byte chunks lane, lane + 32, ...: a quarter-warp reads 128 contiguous bytes per LDS.128 -- 32-byte pieces per
+    //  lane cost twice the shared-memory wavefronts; the two 16-bit halves of a mask word come from neighbouring lanes)
     uint32_t any = 0;
+    {
+      uint16_t* const w16 = reinterpret_cast<uint16_t*>(s_w);
+      uint16_t* const n16 = reinterpret_cast<uint16_t*>(s_n);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4* p4 = reinterpret_cast<const uint4*>(sm + 32 * (lane + 32 * j));
-      const uint4 v0 = p4[0], v1 = p4[1];
-      uint32_t wm, nm;
-      classify32_ascii(v0, v1, wm, nm, any);
-      s_w[lane + 32 * j] = wm;
-      s_n[lane + 32 * j] = nm;
+      for (int j = 0; j < W7_WIN / 512; ++j) {
+        const int cidx = lane + 32 * j;
+        const uint4 v = reinterpret_cast<const uint4*>(sm)[cidx];
+        uint32_t wm, nm;
+        classify16_ascii(v, wm, nm, any);
+        w16[cidx] = (uint16_t)wm;
+        n16[cidx] = (uint16_t)nm;
+      }
     }
     if (__any_sync(0xFFFFFFFFu, (any & 0x80808080u) != 0u)) {   // a byte >= 0x80 in the window: exact classifier
       uint32_t hiacc = 0;
@@ -1466,30 +1523,49 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_W7_MINBLK) k_tokenize7(cons
     }
     __syncwarp();
     if (listed) {
-      for (uint32_t k = lane; k < nlines; k += 32) {
-        const int s = s_lpos[k];
-        int e;
-        if (k + 1 < total) e = (int)s_lpos[k + 1] - 1;
-        else {                                        // no line start after this one inside the window: find the terminator
-          e = s;
-          while (e < W7_WIN && !jx::is_term(sm[e])) ++e;
-          if (e >= W7_WIN) while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e;
+      auto line_end = [&](uint32_t k, int s) -> int {
+        if (k + 1 < total) return (int)s_lpos[k + 1] - 1;
+        int e = s;                                    // no line start after this one inside the window: find the terminator
+        while (e < W7_WIN && !jx::is_term(sm[e])) ++e;
+        if (e >= W7_WIN) while (base + e < a.n && !jx::is_term(a.text[base + e])) ++e;
+        return e;
+      };
+      uint32_t ntodo = 0;                             // lines the fast route refused (warp-uniform count)
+      for (uint32_t k0 = 0; k0 < nlines; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        bool later = false;
+        if (k < nlines) {
+          const int s = s_lpos[k];
+          const int e = line_end(k, s);
+          uint4 rec;
+          later = !parse_fast7(a, sm, s_w, s_n, s, e, W7_WIN, v6, c, rec);
+          if (!later && k < cap) slots[k] = rec;
         }
-        const uint4 rec = parse_line7(a, sm, s_w, s_n, base, s, e, W7_WIN, v6, c);
-        if (k < cap) slots[k] = rec;
+        const unsigned lm = __ballot_sync(0xFFFFFFFFu, later);
+        if (later) SW.todo[ntodo + __popc(lm & ((1u << lane) - 1u))] = (uint8_t)k;
+        ntodo += __popc(lm);
+      }
+      if (ntodo) {
+        __syncwarp();
+        for (uint32_t t = lane; t < ntodo; t += 32) {
+          const uint32_t k = SW.todo[t];
+          const int s = s_lpos[k];
+          const uint4 rec = parse_slow7(a, sm, s_w, s_n, base, s, line_end(k, s), W7_WIN, c);
+          if (k < cap) slots[k] = rec;
+        }
       }
     } else if (lane < W7_TILE / 128) {
       walk_tiny_lines(a, sm, s_w, s_n, base, st[0], st[1], st[2], st[3], pref, cap, slots, c);
     }
     for (uint32_t k = nlines + lane; k < cap; k += 32) slots[k] = make_uint4(JX_NOREC, 0u, 0u, 0u);
-    if (lane == 0) s_cnt[warp][WH_NONE + 1] += nlines;
+    if (lane == 0) SW.cnt[WH_NONE + 1] += nlines;
     __syncwarp();                                     // every lane is done with the window
     if (lane == 0) arm(p + W7_NBUF);
   }
 
   __syncwarp();
   if (lane == 0) {
-    const uint32_t* cw = s_cnt[warp];
+    const uint32_t* cw = SW.cnt;
     const uint32_t lines = cw[WH_NONE + 1];
     const uint32_t other = cw[WH_COMMENT] + cw[WH_UNMAPPED] + cw[WH_HARD] + cw[WH_LONG] + cw[WH_EXCL] + cw[WH_SELF] + cw[WH_NONE];
     if (cw[WH_COMMENT]) atomicAdd(a.stats + 1, (unsigned long long)cw[WH_COMMENT]);
