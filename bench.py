@@ -557,7 +557,7 @@ def impl_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:   # DRAM bytes per 64 MiB launch from the committed `ncu --set full` capture (profiles/)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_tokenize_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_tokenize_traffic.json")))
             traffic = float(tj["dram_bytes_per_launch"])
         except Exception:
             pass
@@ -566,7 +566,7 @@ def impl_ours(args):
         roof = {"bound": "hbm", "kernel": "k_tokenize (K1 tokenizer + K2 hash join, fused K4 best-score)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback",
-                "traffic": traffic, "traffic_note": "dram__bytes_read+write of one launch over the whole resident table (1426.7 MB text + 320.0 MB records algorithmic), ncu capture in profiles/r1_tokenize_traffic.json",
+                "traffic": traffic, "traffic_note": "dram__bytes_read+write of one launch over the whole resident table (algorithmic: 1426.7 MB text + 320.0 MB records; the measured write side also holds the 'no record' fillers of the fixed slots, 72 slots per 3840-byte sub-tile), ncu capture in profiles/r2_tokenize_traffic.json",
                 "launches": tok_launches, "avg_launch_ms": tok_ms / max(tok_launches, 1),
                 "algorithmic_bytes_per_launch": alg_bytes / max(tok_launches, 1),
                 "share_of_step": tok_ms / dev_ms if dev_ms else None}

@@ -18,12 +18,22 @@ ap.add_argument("--config", default="c3")
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--trace", action="store_true")
+ap.add_argument("--profile", action="store_true", help="cProfile of rank 0 around the timed steps (host-side cost of the driver)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if args.profile and rank == 0:
+    import cProfile, pstats, io
+    pr = cProfile.Profile()
+    pr.enable()
 out = bench.strong_scaling(args.config, args.hits, args.steps, 2, world, rank, local, verify=args.verify, trace=args.trace)
+if args.profile and rank == 0:
+    pr.disable()
+    sio = io.StringIO()
+    pstats.Stats(pr, stream=sio).sort_stats("tottime").print_stats(45)
+    print(sio.getvalue()[:9000], file=sys.stderr, flush=True)
 if rank == 0:
     print(json.dumps(out), flush=True)
 if world > 1:
