@@ -198,9 +198,12 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
     kw = dict(cscore=c["cscore"], tandem_Nmax=c["tandem_Nmax"], xdist=c["dist"], ydist=c["dist"], N=c["N"], liftover_dist=c["liftover_dist"])
     marks = []
 
+    nosync = bool(os.environ.get("SS_MARK_NOSYNC"))       # host-side phase times only (no added synchronisation)
+
     def mark(name):
         if trace:
-            torch.cuda.synchronize()
+            if not nosync:
+                torch.cuda.synchronize()
             marks.append((name, time.perf_counter()))
 
     def step():

@@ -24,16 +24,40 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-if args.profile and rank == 0:
-    import cProfile, pstats, io
-    pr = cProfile.Profile()
-    pr.enable()
+acc = {}
+seen = [0]
+if args.profile:
+    # wall time spent inside every driver-level call (engine stage calls, collectives, synchronisations): where the host
+    # of rank 0 blocks.  No extra synchronisation is added.
+    from jcvi_b200 import sharded as _sh
+    from jcvi_b200.engine import Engine as _Eng
+
+    def _wrap(obj, name, label):
+        f = getattr(obj, name)
+
+        def g(*a, **k):
+            if label.startswith("run_sharded"):
+                seen[0] += 1
+                if seen[0] == 4:                      # warm-up steps (allocations, NCCL set-up) are not counted
+                    acc.clear()
+            t0 = time.perf_counter()
+            try:
+                return f(*a, **k)
+            finally:
+                e = acc.setdefault(label, [0, 0.0]); e[0] += 1; e[1] += time.perf_counter() - t0
+        setattr(obj, name, g)
+    for n in ("allreduce_max_", "allgather_fixed", "alltoallv", "allgatherv"):
+        _wrap(_sh.DistComm, n, "comm." + n)
+    for n in ("cscore_begin", "shard_candidates", "shard_partition", "shard_pairs", "shard_survivors", "scan_cands", "shard_near",
+              "shard_lift", "shard_reset", "best_table_tensor", "load_pair", "shard_slots"):
+        _wrap(_Eng, n, "engine." + n)
+    _wrap(torch.cuda, "synchronize", "torch.cuda.synchronize")
+    _wrap(_sh, "run_sharded", "run_sharded (total)")
 out = bench.strong_scaling(args.config, args.hits, args.steps, 2, world, rank, local, verify=args.verify, trace=args.trace)
 if args.profile and rank == 0:
-    pr.disable()
-    sio = io.StringIO()
-    pstats.Stats(pr, stream=sio).sort_stats("tottime").print_stats(45)
-    print(sio.getvalue()[:9000], file=sys.stderr, flush=True)
+    calls = max(acc.get("run_sharded (total)", [1])[0], 1)
+    for k, (n, t) in sorted(acc.items(), key=lambda x: -x[1][1]):
+        print("%-32s %5.1f calls/step %8.3f ms/step" % (k, n / calls, t / calls * 1e3), file=sys.stderr, flush=True)
 if rank == 0:
     print(json.dumps(out), flush=True)
 if world > 1:
