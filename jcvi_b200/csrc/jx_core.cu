@@ -79,6 +79,8 @@ void jx_ctx_destroy(jx_ctx* ctx) {
   for (auto& b : ctx->pin_pool) cudaFreeHost(b.p);
   if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
   if (ctx->io_pin) cudaFreeHost(ctx->io_pin);
+  cudaFree(ctx->ftext_dev);
+  if (ctx->ev_text) cudaEventDestroy(ctx->ev_text);
   if (ctx->pin_scan) cudaFreeHost(ctx->pin_scan);
   if (ctx->ws) cudaFree(ctx->ws);
   cudaFree(ctx->cache.recs); cudaFree(ctx->cache.desc); cudaFree(ctx->sess_best);

@@ -287,15 +287,30 @@ __global__ void k_copy_lines(const uint8_t* text, const uint64_t* off, const uin
 }
 
 // ---- K12: exact `.filtered` writer on the device ------------------------------------------------
-struct TextReader {            // bytes of one line in global memory, relative to its start
-  const uint8_t* t;
+// Pass 1 (k_format_len): the block stages the first 208 bytes of its 128 lines in shared memory with coalesced 16-byte
+// loads (a thread that reads its line byte by byte from global memory waits ~70 dependent round trips), every thread
+// scans and formats the numeric tail of its line ONCE, keeps the tail (<= FMT_TAIL bytes) in a scratch row and returns
+// the line's length.  Pass 2 (k_format_write), after the 64-bit prefix sum: names + kept tail into a shared staging
+// area at the line's position inside the block's (contiguous) output range, then one coalesced copy to global memory.
+constexpr int FMT_THREADS = 128;
+constexpr int FMT_STAGE = 208;          // bytes staged per line (13 x 16); longer lines continue in global memory
+constexpr int FMT_TAIL = 96;            // kept tail bytes per line; a longer tail is declined (host glibc formats the line)
+constexpr int FMT_OUT = FMT_THREADS * 136;   // output staging per block; a block that needs more writes directly
+
+struct StagedReader {          // bytes of one line: staged part in shared memory, the rest in global memory
+  const uint8_t* s;            // shared copy of text[off ..]
+  int avail;
+  const uint8_t* g;            // text + off
   int64_t remain;
-  __device__ __forceinline__ uint32_t operator()(int p) const { return p < remain ? t[p] : (uint32_t)'\n'; }
+  __device__ __forceinline__ uint32_t operator()(int p) const {
+    if ((int64_t)p >= remain) return (uint32_t)'\n';
+    return p < avail ? s[p] : g[p];
+  }
 };
 
-// formats the numeric tail of survivor t into `tail` (<= 160 bytes); returns false -> glibc
-__device__ bool format_tail(const uint8_t* text, int64_t n, uint64_t off, char* tail, int& tail_len) {
-  TextReader rd{text + off, n - (int64_t)off};
+// formats the numeric tail of the line in `rd` into `tail` (<= 160 bytes); returns false -> glibc
+template <class R>
+__device__ bool format_tail(R& rd, char* tail, int& tail_len) {
   int e = 0;
   while (!jx::is_term(rd(e))) ++e;
   jx::LineFields f;
@@ -303,32 +318,67 @@ __device__ bool format_tail(const uint8_t* text, int64_t n, uint64_t off, char* 
   return jx::fmt_numeric_tail(tail, tail_len, f);
 }
 
-__global__ void k_format_len(const uint8_t* text, int64_t n, const uint64_t* off, const int32_t* q, const int32_t* s,
-                             const uint32_t* qmeta, const uint32_t* smeta, uint32_t cnt, uint32_t* len, uint32_t* fallback) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(FMT_THREADS) k_format_len(const uint8_t* text, int64_t n, const uint64_t* off, const int32_t* q,
+                                                            const int32_t* s, const uint32_t* qmeta, const uint32_t* smeta, uint32_t cnt,
+                                                            uint32_t* len, uint8_t* tails, uint32_t* fallback) {
+  __shared__ __align__(16) uint8_t s_in[FMT_THREADS * FMT_STAGE];
+  const uint32_t t0 = blockIdx.x * FMT_THREADS;
+  for (int j = threadIdx.x; j < FMT_THREADS * (FMT_STAGE / 16); j += FMT_THREADS) {
+    const int line = j / (FMT_STAGE / 16), part = j - line * (FMT_STAGE / 16);
+    const uint32_t t = t0 + (uint32_t)line;
+    uint4 v = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+    if (t < cnt) {
+      const uint64_t a = (off[t] & ~15ull) + (uint64_t)part * 16u;      // the text buffer is 16-byte aligned
+      if ((int64_t)a + 16 <= n) v = __ldg(reinterpret_cast<const uint4*>(text + a));
+      else if ((int64_t)a < n) {                                        // the last, partial piece of the text
+        uint32_t w[4] = {0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au};
+        for (int i = 0; i < 16 && (int64_t)a + i < n; ++i) w[i >> 2] = (w[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)text[a + i] << (8 * (i & 3)));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    reinterpret_cast<uint4*>(s_in)[j] = v;
+  }
+  __syncthreads();
+  const uint32_t t = t0 + threadIdx.x;
   if (t >= cnt) return;
+  const uint64_t o = off[t];
+  const int sh = (int)(o & 15u);
+  StagedReader rd{s_in + threadIdx.x * FMT_STAGE + sh, FMT_STAGE - sh, text + o, n - (int64_t)o};
   char tail[160];
   int tl = 0;
-  if (!format_tail(text, n, off[t], tail, tl)) { atomicAdd(fallback, 1u); len[t] = 0; return; }   // declined: host formats it
+  if (!format_tail(rd, tail, tl) || tl > FMT_TAIL) { atomicAdd(fallback, 1u); len[t] = 0; return; }   // declined: host formats it
+  uint8_t* row = tails + (size_t)t * FMT_TAIL;
+  for (int i = 0; i < tl; ++i) row[i] = (uint8_t)tail[i];
   len[t] = (qmeta[q[t]] & 127u) + 1u + (smeta[s[t]] & 127u) + (uint32_t)tl;
 }
 
-__global__ void k_format_write(const uint8_t* text, int64_t n, const uint64_t* off, const int32_t* q, const int32_t* s,
-                               const uint32_t* qmeta, const uint32_t* qblob, const uint32_t* smeta, const uint32_t* sblob,
-                               uint32_t cnt, const uint64_t* pos, char* out) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cnt) return;
-  char tail[160];
-  int tl = 0;
-  if (!format_tail(text, n, off[t], tail, tl)) return;
-  char* o = out + pos[t];
-  uint32_t m = qmeta[q[t]], l = m & 127u;
-  const uint32_t* w = qblob + (m >> 7);
-  for (uint32_t i = 0; i < l; ++i) *o++ = (char)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-  *o++ = '\t';
-  m = smeta[s[t]]; l = m & 127u; w = sblob + (m >> 7);
-  for (uint32_t i = 0; i < l; ++i) *o++ = (char)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-  for (int i = 0; i < tl; ++i) *o++ = tail[i];
+__global__ void __launch_bounds__(FMT_THREADS) k_format_write(const int32_t* q, const int32_t* s, const uint32_t* qmeta, const uint32_t* qblob,
+                                                              const uint32_t* smeta, const uint32_t* sblob, uint32_t cnt, const uint32_t* len,
+                                                              const uint64_t* pos, const uint8_t* tails, char* out) {
+  __shared__ uint8_t s_out[FMT_OUT];
+  const uint32_t t0 = blockIdx.x * FMT_THREADS, t1 = min(cnt, t0 + FMT_THREADS);
+  const uint64_t base = pos[t0];
+  const uint64_t total = pos[t1 - 1] + len[t1 - 1] - base;        // the block's lines are one contiguous output range
+  const bool staged = total <= (uint64_t)FMT_OUT;
+  const uint32_t t = t0 + threadIdx.x;
+  if (t < cnt && len[t]) {
+    uint8_t* o = staged ? s_out + (pos[t] - base) : reinterpret_cast<uint8_t*>(out) + pos[t];
+    uint32_t m = qmeta[q[t]], l = m & 127u;
+    const uint32_t* w = qblob + (m >> 7);
+    for (uint32_t i = 0; i < l; ++i) *o++ = (uint8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+    *o++ = (uint8_t)'\t';
+    m = smeta[s[t]];
+    const uint32_t l2 = m & 127u;
+    w = sblob + (m >> 7);
+    for (uint32_t i = 0; i < l2; ++i) *o++ = (uint8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+    const uint32_t tl = len[t] - l - 1u - l2;
+    const uint8_t* row = tails + (size_t)t * FMT_TAIL;
+    for (uint32_t i = 0; i < tl; ++i) *o++ = row[i];
+  }
+  if (!staged) return;
+  __syncthreads();
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + base;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)total; i += FMT_THREADS) dst[i] = s_out[i];
 }
 
 inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
@@ -720,7 +770,9 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
       JX_ALLOC(flen, uint32_t, nF, false);
       JX_ALLOC(fpos, uint64_t, nF, false);
       JX_ALLOC(ffb, uint32_t, 1, true);
-      JX_LAUNCH(k_format_len, nblk(nF, 128), 128, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, S.name_meta, nF, flen, ffb);
+      JX_ALLOC(ftails, uint8_t, (size_t)nF * FMT_TAIL, false);
+      JX_LAUNCH(k_format_len, nblk(nF, FMT_THREADS), FMT_THREADS, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, S.name_meta, nF,
+                flen, ftails, ffb);
       // 64-bit byte positions: with the C-score filter off the `.filtered` text of a big table exceeds 4 GiB
       if ((rc = jx_exclusive_sum64(ctx, arena, flen, fpos, nF))) return rc;
       uint32_t h[2] = {0, 0};
@@ -731,12 +783,41 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
       JX_CK(cudaStreamSynchronize(ctx->stream));
       const uint32_t ndecl = h[0];
       const uint64_t total = hlast + h[1];
-      JX_ALLOC(dtext, char, (size_t)total + 1, false);
-      JX_LAUNCH(k_format_write, nblk(nF, 128), 128, 0, tok.d_text, tok.nbytes, ooff, oq, os, Q.name_meta, Q.blobw,
-                S.name_meta, S.blobw, nF, fpos, dtext);
+      // jx_pipeline (ctx->defer_text): the text goes to a context-owned buffer and crosses PCIe on the copy stream while
+      // the next stages run; the caller waits for the copy stream before it returns
+      const bool defer = ctx->defer_text && !ndecl;
+      char* dtext = nullptr;
+      if (defer) {
+        if (ctx->ftext_dev_cap < (size_t)total + 1) {
+          cudaFree(ctx->ftext_dev);
+          ctx->ftext_dev = nullptr; ctx->ftext_dev_cap = 0;
+          const size_t cap = (size_t)total + (size_t)(total >> 2) + 4096;
+          JX_CK(cudaMalloc((void**)&ctx->ftext_dev, cap));
+          ctx->ftext_dev_cap = cap;
+        }
+        dtext = (char*)ctx->ftext_dev;
+      } else {
+        JX_ALLOC(dt0, char, (size_t)total + 1, false);
+        dtext = dt0;
+      }
+      JX_LAUNCH(k_format_write, nblk(nF, FMT_THREADS), FMT_THREADS, 0, oq, os, Q.name_meta, Q.blobw, S.name_meta, S.blobw, nF, flen, fpos,
+                ftails, dtext);
       char* host = jx_pin_acquire(ctx, (size_t)total + 1);   // borrowed from the pool until the result is freed
       if (!host) { ctx->err = "cudaMallocHost failed"; return JX_ECUDA; }
       struct PinGuard { jx_ctx* c; char* p; ~PinGuard() { if (p) jx_pin_release(c, p); } } guard{ctx, host};
+      if (defer) {
+        if (!ctx->ev_text) JX_CK(cudaEventCreateWithFlags(&ctx->ev_text, cudaEventDisableTiming));
+        JX_CK(cudaEventRecord(ctx->ev_text, ctx->stream));
+        JX_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_text, 0));
+        JX_CK(cudaMemcpyAsync(host, dtext, (size_t)total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->text_in_flight = true;
+        host[total] = 0;                               // (the copy writes [0, total) only)
+        out->text = host;
+        out->text_pinned = 2;
+        out->owner = ctx;
+        out->text_len = (int64_t)total;
+        guard.p = nullptr;                             // owned by the result
+      } else {
       JX_CK(cudaMemcpyAsync(host, dtext, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
       if (!ndecl) {
         JX_CK(cudaStreamSynchronize(ctx->stream));
@@ -820,6 +901,7 @@ int jx_blastfilter(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_de
         out->text[merged.size()] = 0;
         out->text_len = (int64_t)merged.size();
         out->text_pinned = 0;
+      }
       }
     }
   } else if (opts->want_text) {

@@ -111,6 +111,10 @@ struct jx_ctx {
   size_t pin_small_cap = 0;
   char* pin_scan = nullptr;      // the same for scan results (their copy may still be in flight while liftover stages its own)
   size_t pin_scan_cap = 0;
+  // jx_pipeline: the `.filtered` text is formatted into a context-owned device buffer and copied to the host on the copy
+  // stream while scan and liftover run (the stage's own scratch is recycled by then)
+  uint8_t* ftext_dev = nullptr; size_t ftext_dev_cap = 0; bool defer_text = false, text_in_flight = false;
+  cudaEvent_t ev_text = nullptr;
   void* io_pin = nullptr;        // jx_file_upload: ring of pinned pieces (jx_io.cu), grow-never, freed with the context
   uint8_t* held_text = nullptr;
   int64_t held_n = 0;

@@ -24,7 +24,15 @@ extern "C" int jx_pipeline(jx_ctx* ctx, const char* text, int64_t nbytes, int te
   else if (!held) { ctx->err = "jx_pipeline: device text must come from jx_text_upload"; return JX_EARG; }
   const bool reuse0 = ctx->record_reuse;
   ctx->record_reuse = true;
+  // the `.filtered` text crosses PCIe on the copy stream while scan and liftover run; whatever path leaves this
+  // function waits for it first (the result's host buffer must be complete -- and quiet -- when the caller sees it)
+  struct TextWait {
+    jx_ctx* c;
+    ~TextWait() { if (c->text_in_flight) { cudaStreamSynchronize(c->copy_stream); c->text_in_flight = false; } c->defer_text = false; }
+  } text_wait{ctx};
+  ctx->defer_text = true;
   rc = jx_blastfilter(ctx, (const char*)(uintptr_t)dptr, nbytes, 1, fopts, fout);
+  ctx->defer_text = false;
   ctx->record_reuse = reuse0;
   if (rc) return rc;
   Arena arena(ctx);
