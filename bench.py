@@ -197,6 +197,7 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
     comm = sharded.DistComm()
     kw = dict(cscore=c["cscore"], tandem_Nmax=c["tandem_Nmax"], xdist=c["dist"], ydist=c["dist"], N=c["N"], liftover_dist=c["liftover_dist"])
     marks = []
+    ss_mode = ["single GPU"]
 
     nosync = bool(os.environ.get("SS_MARK_NOSYNC"))       # host-side phase times only (no added synchronisation)
 
@@ -213,7 +214,9 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
             return f.n, s, l
         del marks[:]
         mark("start")
-        r = sharded.run_sharded([dev], qbed, sbed, comm=comm, engines=[eng], want_filtered=False, mark=mark, **kw)
+        r = sharded.run_sharded([dev], qbed, sbed, comm=comm, engines=[eng], want_filtered=False, mark=mark,
+                                mode=os.environ.get("SS_MODE", "auto"), **kw)
+        ss_mode[0] = r.mode
         return None, r.scan, r.lifted
 
     def barrier():
@@ -239,9 +242,13 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
     ms = float(t[0]) * 1e3
     out = {"workload": c["label"], "hits": int(hits), "n_gpus": world, "ms_per_step": ms, "value": hits / (ms / 1e3), "unit": "hits/s",
            "steps": steps, "scaling": "strong", "clocks": clocks,
-           "sharding": "single GPU: jx_pipeline" if world == 1 else
+           "sharding": "single GPU: jx_pipeline" if world == 1 else (
                        "text slices per rank; ncclAllReduce(max) of the best-score table; all-to-all of 16-byte candidates to the owner of "
-                       "their chromosome pair (blastfilter, liftover); all-gather of tandem edges and anchors",
+                       "their chromosome pair (blastfilter, liftover); all-gather of tandem edges and anchors" if ss_mode[0] == "owners" else
+                       "text slices per rank (tokenizer, C-score predicate and liftover prefilter are sharded); ncclAllReduce(max) of the "
+                       "best-score table; all-gather of the 16-byte candidates, every rank runs pair de-duplication / tandem / scan on "
+                       "all of them; the raw records near an anchor are gathered and lifted on rank 0"),
+           "mode": ss_mode[0],
            "options": "cscore=%g tandem_Nmax=%d dist=%d min_size=%d liftover_dist=%d" % (c["cscore"], c["tandem_Nmax"], c["dist"], c["N"], c["liftover_dist"])}
     if rank == 0:
         out["outputs"] = {"anchors": int(s.n_anchors), "blocks": int(s.n_blocks), "lifted": int(l.n_lifted)}

@@ -259,6 +259,22 @@ class DistComm(object):
                                     input_split_sizes=[int(x) for x in matrix[r, :]])
         return [recv]
 
+    def allgatherv_known(self, tensors, sizes):
+        """allgatherv when every rank already knows every rank's row count (no size exchange)"""
+        import torch
+        t = tensors[0]
+        if not self.dist:
+            return [t]
+        sizes = np.asarray(sizes, dtype=np.int64)
+        pad = int(max(sizes.max(), 1))
+        mine = torch.zeros((pad, t.shape[1]), dtype=t.dtype, device=t.device)
+        mine[: t.shape[0]] = t
+        allp = torch.empty((self.world * pad, t.shape[1]), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(allp, mine)
+        if (sizes == pad).all():
+            return [allp]
+        return [torch.cat([allp[r * pad: r * pad + int(sizes[r])] for r in range(self.world)], 0)]
+
     def allgatherv(self, tensors):
         """[n_r, W] device tensors -> (their concatenation over all ranks in rank order, sizes[world]) on every rank"""
         import torch
@@ -312,6 +328,9 @@ class LocalComm(object):
         cat = torch.cat(list(tensors), 0)
         return [cat.clone() for _ in tensors], np.array([t.shape[0] for t in tensors], dtype=np.int64)
 
+    def allgatherv_known(self, tensors, sizes):
+        return self.allgatherv(tensors)[0]
+
     def barrier(self):
         pass
 
@@ -346,6 +365,7 @@ class ShardedResult(object):
         self.filtered = None
         self.scan = None
         self.lifted = None
+        self.mode = "owners"           # how the stages behind the C-score predicate were run (run_sharded's `mode`)
 
 
 class _Scan(object):
@@ -370,11 +390,66 @@ def _raise_agreed(codes, failed):
     raise cls("rank %d failed in its slice of the table (see its log); all ranks stop together" % bad[0])
 
 
+GATHER_MAX = 16_000_000        # candidates in total up to which every rank takes all of them ("auto" mode of run_sharded)
+
+
+def _run_gathered(comm, engines, L, W, cands, sizes, base, total_slots, strip_names, tandem_Nmax, xdist, ydist, N, intrabound,
+                  liftover_dist, want_filtered, mark):
+    """run_sharded, mode "gather" (from stage B on; `sizes`: candidates per rank, known from the histogram all-gather)."""
+    import torch
+    allc = comm.allgatherv_known(cands, sizes)              # every rank: all candidates, in rank order
+    torch.cuda.synchronize()
+    mark("select+exchange")
+    rows, survs = [], []
+    for i in L:
+        a, b = engines[i].shard_pairs(allc[i], tandem_Nmax)
+        surv = engines[i].shard_survivors(a, b, tandem_Nmax)[0]
+        survs.append(surv)
+        rows.append(engines[i].scan_cands(surv, xdist=xdist, ydist=ydist, N=N, intrabound=intrabound, device=True))   # {q, s, score, block}
+    mark("pairs+tandem+scan")
+    res = ShardedResult()
+    res.mode = "gather"
+    anchors = []
+    for i in L:
+        r = rows[i]
+        anchors.append((r[:, 0].contiguous(), r[:, 1].contiguous(), r[:, 3].contiguous()))
+    # ---- liftover: every rank tests its raw records against the anchors; the near hits are gathered ---------------------------
+    near = [engines[i].shard_near(anchors[i][0], anchors[i][1], base[i], strip_names=strip_names, dist=liftover_dist) for i in L]
+    alln, _ = comm.allgatherv(near)
+    torch.cuda.synchronize()
+    mark("near+exchange")
+    if comm.rank == 0:
+        if want_filtered:
+            res.filtered = engines[0].shard_order(survs[0])
+        R = rows[0].cpu().numpy()
+        sc = _Scan()
+        sc.q_rank = np.ascontiguousarray(R[:, 0]); sc.s_rank = np.ascontiguousarray(R[:, 1])
+        sc.score = np.ascontiguousarray(R[:, 2]).view(np.float32)
+        blk = R[:, 3]
+        hs = np.flatnonzero(np.concatenate([[1], blk[1:] != blk[:-1]])) if len(blk) else np.zeros(0, np.int64)
+        sc.block_start = np.concatenate([hs, [len(blk)]]).astype(np.int64)
+        sc.n_blocks = len(hs); sc.n_anchors = int(len(blk))
+        res.scan = sc
+        res.lifted = engines[0].shard_lift(alln[0].contiguous(), total_slots, anchors[0][0], anchors[0][1], anchors[0][2],
+                                           dist=liftover_dist, device=False)
+    mark("lift")
+    return res
+
+
 def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7, tandem_Nmax=10, xdist=20, ydist=20, N=4,
-                intrabound=300, liftover_dist=10, comm=None, engines=None, want_filtered=True, mark=None):
+                intrabound=300, liftover_dist=10, comm=None, engines=None, want_filtered=True, mark=None, mode="auto"):
     """blastfilter -> scan -> liftover of ONE genome pair whose raw table is cut into `slices` (one per LOCAL rank: a list
     of length 1 under torch.distributed, of length world under LocalComm; each slice ends at a line boundary; host arrays,
-    pinned tensors or DeviceText).  Returns a ShardedResult (complete on rank 0)."""
+    pinned tensors or DeviceText).  Returns a ShardedResult (complete on rank 0).
+
+    mode: what happens after the C-score predicate (the part that is O(raw hits) -- tokenizing, the predicate, the
+    liftover prefilter -- is sharded either way):
+      "owners"  every chromosome pair has an owner rank; all-to-all of the candidates, every later stage per owner;
+      "gather"  the candidates (a few % of the raw hits) are all-gathered and EVERY rank runs pair de-duplication, tandem
+                collapse and scan on all of them (identical results, nothing to exchange afterwards); the raw records near
+                an anchor are gathered and lifted on rank 0.  The stages behind the predicate are latency-sized on such a
+                set (2 - 3 ms on one GPU whatever the split), so splitting them buys nothing and every exchange costs;
+      "auto"    "gather" up to GATHER_MAX candidates in total, "owners" beyond (e.g. with the C-score filter off)."""
     import torch
     comm = comm or DistComm()
     W = comm.world
@@ -432,6 +507,9 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
     _raise_agreed(H[:, n_cp], failed)
     H = np.ascontiguousarray(H[:, :n_cp])
     hists = [h[:n_cp] for h in hists]
+    if mode == "gather" or (mode == "auto" and int(H.sum()) <= GATHER_MAX):
+        return _run_gathered(comm, engines, L, W, cands, H.sum(axis=1), base, total_slots, strip_names, tandem_Nmax, xdist, ydist, N,
+                             intrabound, liftover_dist, want_filtered, mark)
     owner = assign_owners(H.sum(axis=0), W)
     M = _send_matrix(H, owner, W)
     parts = [engines[i].shard_partition(cands[i], owner, W, hist_in=hists[i])[0] for i in L]

@@ -7,8 +7,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("mode", ["owners", "gather"])
 @pytest.mark.parametrize("case,world", [("pair", 3), ("polyploid", 4), ("pair", 1), ("no_tandem", 2)])
-def test_sharded_equals_single_gpu(tmp_path, case, world):
+def test_sharded_equals_single_gpu(tmp_path, case, world, mode):
     from jcvi_b200 import sharded, synth
     from jcvi_b200.engine import Engine, get_engine
     from jcvi_b200.formats.bed import Bed
@@ -29,7 +30,9 @@ def test_sharded_equals_single_gpu(tmp_path, case, world):
     for r in range(world):
         lo, hi = sharded.slice_bounds(text, r, world)
         slices.append(text[lo:hi])
-    res = sharded.run_sharded(slices, qb, sb, comm=sharded.LocalComm(world), engines=engines, liftover_dist=dist, **opts, **scan_kw)
+    res = sharded.run_sharded(slices, qb, sb, comm=sharded.LocalComm(world), engines=engines, liftover_dist=dist, mode=mode, **opts,
+                              **scan_kw)
+    assert res.mode == mode
     f = res.filtered
     assert f.n == f0.n
     assert np.array_equal(f.q_rank, f0.q_rank) and np.array_equal(f.s_rank, f0.s_rank) and np.array_equal(f.score, f0.score)
