@@ -217,6 +217,7 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
         r = sharded.run_sharded([dev], qbed, sbed, comm=comm, engines=[eng], want_filtered=False, mark=mark,
                                 mode=os.environ.get("SS_MODE", "auto"), **kw)
         ss_mode[0] = r.mode
+        ss_mode[1:] = [r.n_candidates]
         return None, r.scan, r.lifted
 
     def barrier():
@@ -248,7 +249,7 @@ def strong_scaling(cfg, hits, steps, warmup, world, rank, local, verify=False, t
                        "text slices per rank (tokenizer, C-score predicate and liftover prefilter are sharded); ncclAllReduce(max) of the "
                        "best-score table; all-gather of the 16-byte candidates, every rank runs pair de-duplication / tandem / scan on "
                        "all of them; the raw records near an anchor are gathered and lifted on rank 0"),
-           "mode": ss_mode[0],
+           "mode": ss_mode[0], "candidates": (ss_mode[1] if len(ss_mode) > 1 else None),
            "options": "cscore=%g tandem_Nmax=%d dist=%d min_size=%d liftover_dist=%d" % (c["cscore"], c["tandem_Nmax"], c["dist"], c["N"], c["liftover_dist"])}
     if rank == 0:
         out["outputs"] = {"anchors": int(s.n_anchors), "blocks": int(s.n_blocks), "lifted": int(l.n_lifted)}

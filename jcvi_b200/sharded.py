@@ -366,6 +366,7 @@ class ShardedResult(object):
         self.scan = None
         self.lifted = None
         self.mode = "owners"           # how the stages behind the C-score predicate were run (run_sharded's `mode`)
+        self.n_candidates = 0          # records that passed the C-score predicate, over all ranks
 
 
 class _Scan(object):
@@ -390,10 +391,13 @@ def _raise_agreed(codes, failed):
     raise cls("rank %d failed in its slice of the table (see its log); all ranks stop together" % bad[0])
 
 
-GATHER_MAX = 16_000_000        # candidates in total up to which every rank takes all of them ("auto" mode of run_sharded)
+# candidates in total up to which every rank takes all of them ("auto" mode of run_sharded).  Measured on 8 B200s: C3
+# (200 M hits, <= 1.6 M candidates) gather 6.1 ms vs owners 7.8 ms; C5 (500 M hits, ~14 M candidates) owners 13.9 ms vs gather
+# 18.0 ms -- the stages behind the predicate cost ~0.65 ms per million candidates on one GPU, the owners' extra exchanges ~3 ms
+GATHER_MAX = 4_000_000
 
 
-def _run_gathered(comm, engines, L, W, cands, sizes, base, total_slots, strip_names, tandem_Nmax, xdist, ydist, N, intrabound,
+def _run_gathered(n_candidates, comm, engines, L, W, cands, sizes, base, total_slots, strip_names, tandem_Nmax, xdist, ydist, N, intrabound,
                   liftover_dist, want_filtered, mark):
     """run_sharded, mode "gather" (from stage B on; `sizes`: candidates per rank, known from the histogram all-gather)."""
     import torch
@@ -409,6 +413,7 @@ def _run_gathered(comm, engines, L, W, cands, sizes, base, total_slots, strip_na
     mark("pairs+tandem+scan")
     res = ShardedResult()
     res.mode = "gather"
+    res.n_candidates = n_candidates
     anchors = []
     for i in L:
         r = rows[i]
@@ -449,7 +454,7 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
                 collapse and scan on all of them (identical results, nothing to exchange afterwards); the raw records near
                 an anchor are gathered and lifted on rank 0.  The stages behind the predicate are latency-sized on such a
                 set (2 - 3 ms on one GPU whatever the split), so splitting them buys nothing and every exchange costs;
-      "auto"    "gather" up to GATHER_MAX candidates in total, "owners" beyond (e.g. with the C-score filter off)."""
+      "auto"    "gather" up to GATHER_MAX candidates in total, "owners" beyond (large or unfiltered tables)."""
     import torch
     comm = comm or DistComm()
     W = comm.world
@@ -508,7 +513,7 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
     H = np.ascontiguousarray(H[:, :n_cp])
     hists = [h[:n_cp] for h in hists]
     if mode == "gather" or (mode == "auto" and int(H.sum()) <= GATHER_MAX):
-        return _run_gathered(comm, engines, L, W, cands, H.sum(axis=1), base, total_slots, strip_names, tandem_Nmax, xdist, ydist, N,
+        return _run_gathered(int(H.sum()), comm, engines, L, W, cands, H.sum(axis=1), base, total_slots, strip_names, tandem_Nmax, xdist, ydist, N,
                              intrabound, liftover_dist, want_filtered, mark)
     owner = assign_owners(H.sum(axis=0), W)
     M = _send_matrix(H, owner, W)
@@ -537,6 +542,7 @@ def run_sharded(slices, qbed, sbed, is_self=False, strip_names=True, cscore=0.7,
             surv.append(engines[i].shard_survivors(z, z, 0)[0])
     mark("pairs+tandem")
     res = ShardedResult()
+    res.n_candidates = int(H.sum())
     if want_filtered:
         allsurv, _ = comm.allgatherv(surv)
         torch.cuda.synchronize()
