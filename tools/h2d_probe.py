@@ -24,3 +24,23 @@ print("H2D %d bytes: single copy %.2f ms (%.1f GB/s); 64 MiB pieces %.2f ms (%.1
 d2 = torch.empty(40 << 20, dtype=torch.uint8, device="cuda"); h2 = torch.empty(40 << 20, dtype=torch.uint8).pin_memory()
 t = timed(lambda: h2.copy_(d2, non_blocking=True))
 print("D2H 40 MiB: %.3f ms (%.1f GB/s)" % (t, (40 << 20) / t / 1e6))
+# two streams, alternating 32 MiB pieces: does a second DMA engine add anything on this link?
+s2 = torch.cuda.Stream()
+def two_streams(piece):
+    def f():
+        k = 0
+        for o in range(0, n, piece):
+            with torch.cuda.stream(s if k % 2 == 0 else s2):
+                d[o:o + piece].copy_(h[o:o + piece], non_blocking=True)
+            k += 1
+    return f
+def timed2(fn, reps=5):
+    best = 1e9
+    for _ in range(reps):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); best = min(best, (time.perf_counter() - t0) * 1e3)
+    return best
+for piece in (16 << 20, 32 << 20, 64 << 20):
+    t2 = timed2(two_streams(piece))
+    print("H2D two streams, %d MiB pieces: %.2f ms (%.1f GB/s, wall clock)" % (piece >> 20, t2, n / t2 / 1e6))
+t1 = timed2(chunks)
+print("H2D one stream, 64 MiB pieces, wall clock: %.2f ms (%.1f GB/s)" % (t1, n / t1 / 1e6))
