@@ -59,6 +59,11 @@ def make_workload(seed, hits, genes=GENES, outdir=None):
     gq = synth.Genome("A", genes, 12, rng)
     gs = synth.Genome("B", genes, 12, rng)
     arrays = synth.make_hits(gq, gs, hits, rng)
+    if os.environ.get("BENCH_QUERY_GROUPED"):
+        # measurement aid (not the bench workload): the same hits in the order lastal / BLAST write them, all alignments of
+        # a query together, instead of the generator's uniformly shuffled lines
+        o = np.argsort(arrays[0], kind="stable")
+        arrays = tuple(a[o] for a in arrays)
     text = synth.format_hits(gq, gs, arrays)
     qbed, sbed = os.path.join(outdir, "A.bed"), os.path.join(outdir, "B.bed")
     gq.write_bed(qbed, np.random.default_rng(seed + 7))

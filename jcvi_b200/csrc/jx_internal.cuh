@@ -74,6 +74,7 @@ struct jx_ctx {
   int64_t tok_resident = 0;      // persistent tokenizer CTAs that fit on this device at once
   bool tok_v5 = false, tok_v6 = false;   // JX_TOK_V5=1 / JX_TOK_V6=1: run the path through an older kernel (A/B measurements)
   uint32_t tok_cap = 64;         // version-7 kernel: record slots per sub-tile that fitted the last text (sticky guess)
+  int tok_grouped = 0;           // the held text's lines come in runs of equal queries (sampled at upload)
   int64_t tok_bytes = 0;
   // text uploaded with jx_text_upload (device copy + one event per 64 MiB chunk)
   // records of the last jx_blastfilter pass over the held text, for jx_liftover_text
@@ -143,6 +144,27 @@ inline void jx_trace_point(jx_ctx* ctx, const char* label) {
   ctx->trace_t0 = t;
 }
 #define JX_TRACE(label) jx_trace_point(ctx, label)
+
+// Do the lines of a table come in runs of equal queries (lastal / BLAST write all alignments of a query together)?
+// Looks at the first 256 KiB: 1 when at least half of the lines repeat the first field of the line before them.
+inline int jx_sample_query_runs(const uint8_t* p, size_t n) {
+  if (n > (256u << 10)) n = 256u << 10;
+  size_t lines = 0, same = 0, prev_a = 0, prev_len = 0, i = 0;
+  bool have_prev = false;
+  while (i < n) {
+    size_t a = i, e = i;
+    while (e < n && p[e] != '\t' && p[e] != '\n') ++e;
+    const size_t len = e - a;
+    if (len && p[a] != '#') {
+      ++lines;
+      if (have_prev && len == prev_len && memcmp(p + a, p + prev_a, len) == 0) ++same;
+      prev_a = a; prev_len = len; have_prev = true;
+    }
+    while (e < n && p[e] != '\n') ++e;
+    i = e + 1;
+  }
+  return lines >= 32 && same * 2 >= lines ? 1 : 0;
+}
 
 // fold finished tokenizer launch timings into the accumulators (call after a stream synchronise);
 // keeps the event list from growing when nobody asks for jx_tokenizer_timing

@@ -166,6 +166,7 @@ int upload_plain(jx_ctx* ctx, int fd, int64_t size) {
         if (r <= 0) { ring_filled(R, k, false, "short read (file changed while it was read?)"); return; }
         got += r;
       }
+      if (k == 0) ctx->tok_grouped = jx_sample_query_runs(dst, (size_t)p.len);
       ring_filled(R, k, true);
     }
   };
@@ -264,6 +265,7 @@ int upload_bgzf(jx_ctx* ctx, const uint8_t* z, const std::vector<GzBlock>& block
         ok = (r == Z_STREAM_END) && zs.avail_out == 0 && (uint32_t)crc32(0L, dst, (uInt)B.ulen) == B.crc;   // gzip.open checks it too
         dst += B.ulen;
       }
+      if (ok && k == 0) ctx->tok_grouped = jx_sample_query_runs(R.slot(k), (size_t)R.pieces[0].len);
       ring_filled(R, k, ok, "corrupt BGZF block");
       if (!ok) break;
     }
@@ -330,6 +332,7 @@ int upload_gzip_stream(jx_ctx* ctx, const uint8_t* z, int64_t n) {
       cudaFree(ctx->held_text);
       ctx->held_text = nb; ctx->held_cap = ncap;
     }
+    if (k == 0) ctx->tok_grouped = jx_sample_query_runs(dst, (size_t)got);
     if (got) {
       if (cudaMemcpyAsync(ctx->held_text + total, dst, (size_t)got, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess) {
         ctx->err = "host->device copy failed"; rc = JX_ECUDA; break;

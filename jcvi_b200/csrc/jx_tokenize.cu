@@ -44,6 +44,7 @@ struct TokArgs {
   uint32_t* best;
   const uint64_t* excl; int64_t n_excl;
   int strip, is_self, neardiag;
+  int merge_q;             // the lines come grouped by query (lastal / BLAST order): merge a warp's equal-query reductions
   unsigned long long* stats;
 };
 
@@ -1164,6 +1165,7 @@ struct Counters7 {
 // The slow route is NOT called from here: a call inside the hot loop makes the compiler keep the loop's state (line
 // index, slot pointer, mask pointers) in local memory around it -- the reloads were the kernel's largest long-scoreboard
 // stall (profiles/r2_v7b_*: 11 % of the samples).  The kernel lists the refused lines and handles them after the loop.
+template <bool MERGE_Q>
 __device__ __forceinline__ bool parse_fast7(const TokArgs& a, const uint8_t* sm, const uint32_t* s_w, const uint32_t* s_n,
                                             const int s, const int e, const int win, const bool v6, const Counters7& c,
                                             uint4& rec) {
@@ -1236,7 +1238,26 @@ __device__ __forceinline__ bool parse_fast7(const TokArgs& a, const uint8_t* sm,
                   const uint32_t sbits = __float_as_uint(L.score);
                   rec = make_uint4(qi, si, sbits, ((uint32_t)s << 1) | (uint32_t)L.eflag);
                   if (a.best && L.score > 0.f) {        // best_score[name] = max(score), starting at 0.0:
-                    atomicMax(a.best + tq0.y, sbits);   // two reductions (no return value, nothing to wait for)
+                    // two reductions (no return value, nothing to wait for).  lastal / BLAST write all alignments of a
+                    // query together, so the lanes of a warp usually carry the SAME query: when they all do, one lane sends
+                    // the warp's maximum (32 same-address reductions from one warp serialise in L2 -- measured 9 % of the
+                    // kernel on a query-grouped table; a general __match_any_sync costs 26 % on a shuffled one, so only the
+                    // all-equal case is merged, and only in the MERGE_Q instantiation of the kernel, which the host picks when
+                    // a sample of the text showed runs of equal queries: the test alone costs 2 % on a shuffled table);
+                    // subjects are spread, each lane sends its own
+                    if constexpr (MERGE_Q) {
+                      const unsigned act = __activemask();
+                      const int lead = __ffs((int)act) - 1;
+                      const uint32_t nid0 = __shfl_sync(act, tq0.y, lead);
+                      if (__all_sync(act, tq0.y == nid0)) {
+                        const uint32_t gmax = __reduce_max_sync(act, sbits);  // positive float32 bit patterns order like integers
+                        if ((int)(threadIdx.x & 31) == lead) atomicMax(a.best + nid0, gmax);
+                      } else {
+                        atomicMax(a.best + tq0.y, sbits);
+                      }
+                    } else {
+                      atomicMax(a.best + tq0.y, sbits);
+                    }
                     atomicMax(a.best + ts0.y, sbits);
                   }
                 }
@@ -1358,6 +1379,7 @@ struct Tok7Args {
   uint32_t cap;            // record slots per sub-tile
 };
 
+template <bool MERGE_Q>
 __global__ void __launch_bounds__(JX_TOK_THREADS, JX_W7_MINBLK) k_tokenize7(const __grid_constant__ Tok7Args A) {
   const TokArgs& a = A.t;
   constexpr int NW = JX_TOK_THREADS / 32;
@@ -1538,7 +1560,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_W7_MINBLK) k_tokenize7(cons
           const int s = s_lpos[k];
           const int e = line_end(k, s);
           uint4 rec;
-          later = !parse_fast7(a, sm, s_w, s_n, s, e, W7_WIN, v6, c, rec);
+          later = !parse_fast7<MERGE_Q>(a, sm, s_w, s_n, s, e, W7_WIN, v6, c, rec);
           if (!later && k < cap) slots[k] = rec;
         }
         const unsigned lm = __ballot_sync(0xFFFFFFFFu, later);
@@ -1697,6 +1719,7 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
     a.qchr = Q.chr_lex; a.schr = S.chr_lex; a.qnid = Q.name_id; a.snid = S.name_id;
     a.best = mode.best; a.excl = mode.excl; a.n_excl = mode.n_excl;
     a.strip = mode.strip; a.is_self = ctx->is_self ? 1 : 0; a.neardiag = mode.neardiag;
+    a.merge_q = (!on_device && nbytes > 0) ? jx_sample_query_runs((const uint8_t*)text, (size_t)nbytes) : (held ? ctx->tok_grouped : 0);
     a.stats = d_stats;
     const int64_t tiles_per_chunk = CHUNK / JX_TILE;
     // persistent CTAs: as many as are resident at once
@@ -1704,7 +1727,12 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       int per_sm = 0, n_sm = 0;
       if (ctx->tok_v5) JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<0>, JX_TOK_THREADS, 0));
       else if (ctx->tok_v6) JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize6, JX_TOK_THREADS, 0));
-      else JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize7, JX_TOK_THREADS, 0));
+      else {
+        int p0 = 0, p1 = 0;
+        JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p0, k_tokenize7<false>, JX_TOK_THREADS, 0));
+        JX_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, k_tokenize7<true>, JX_TOK_THREADS, 0));
+        per_sm = std::min(p0, p1);
+      }
       JX_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->tok_resident = (int64_t)std::max(per_sm, 1) * std::max(n_sm, 1);
     }
@@ -1743,7 +1771,9 @@ int jx_run_tokenizer(jx_ctx* ctx, Arena& arena, const char* text, int64_t nbytes
       else if (ctx->tok_v6) JX_LAUNCH(k_tokenize6, (unsigned)std::min<int64_t>(t1 - t0, resident), JX_TOK_THREADS, 0, a);
       else {
         Tok7Args a7; a7.t = a; a7.nsub = t1; a7.sub_begin = t0; a7.cap = slot_cap;
-        JX_LAUNCH(k_tokenize7, (unsigned)std::min<int64_t>((t1 - t0 + 3) / 4, resident), JX_TOK_THREADS, 0, a7);
+        const unsigned g7 = (unsigned)std::min<int64_t>((t1 - t0 + 3) / 4, resident);
+        if (a.merge_q) JX_LAUNCH(k_tokenize7<true>, g7, JX_TOK_THREADS, 0, a7);
+        else JX_LAUNCH(k_tokenize7<false>, g7, JX_TOK_THREADS, 0, a7);
       }
       JX_CK(cudaEventRecord(e1, ctx->stream));
       ctx->tok_events.emplace_back(e0, e1);
@@ -1838,6 +1868,7 @@ int jx_text_upload(jx_ctx* ctx, const char* host_text, int64_t nbytes, uint64_t*
     ctx->held_cap = nbytes + 16;
   }
   uint8_t* buf = ctx->held_text;
+  ctx->tok_grouped = jx_sample_query_runs((const uint8_t*)host_text, (size_t)nbytes);
   for (int64_t off = 0; off < nbytes; off += CHUNK) {
     const int64_t len = std::min(CHUNK, nbytes - off);
     JX_CK(cudaMemcpyAsync(buf + off, host_text + off, (size_t)len, cudaMemcpyHostToDevice, ctx->copy_stream));

@@ -16,7 +16,7 @@ def mods():
     return blastfilter, synteny
 
 
-def _pipeline(tmp, mods, seed, Gq, Gs, n, self_mode=False, bf_args=(), scan_args=(), lift_args=(), **kw):
+def _pipeline(tmp, mods, seed, Gq, Gs, n, self_mode=False, bf_args=(), scan_args=(), lift_args=(), group_by_query=False, **kw):
     import oracle
     from jcvi_b200 import synth
     bf, syn = mods
@@ -25,6 +25,14 @@ def _pipeline(tmp, mods, seed, Gq, Gs, n, self_mode=False, bf_args=(), scan_args
     qbed, sbed, last = synth.write_dataset(d, q, s, seed, Gq, Gs, n, self_mode=self_mode, **kw)
     if self_mode:
         sbed = qbed
+    if group_by_query:
+        # the order lastal / BLAST write: all alignments of a query together (the tokenizer then merges a warp's
+        # equal-query best-score reductions -- its MERGE_Q instantiation)
+        rows = read(last).split(b"\n")
+        body = [r for r in rows if r and not r.startswith(b"#")]
+        body.sort(key=lambda r: r.split(b"\t", 1)[0])                  # stable: file order inside a query
+        with open(last, "wb") as fw:
+            fw.write(b"\n".join([r for r in rows if r.startswith(b"#")] + body) + b"\n")
     beds = ["--qbed=" + qbed, "--sbed=" + sbed]
 
     def opt(args, name, default, cast):
@@ -51,6 +59,11 @@ def _pipeline(tmp, mods, seed, Gq, Gs, n, self_mode=False, bf_args=(), scan_args
 
 def test_pair_300k(tmp_path, mods):
     st = _pipeline(tmp_path, mods, seed=21, Gq=8000, Gs=7500, n=300000, Kq=13, Ks=12)
+    assert st["after_tandem"] > 1000
+
+
+def test_pair_query_grouped_lines(tmp_path, mods):
+    st = _pipeline(tmp_path, mods, seed=27, Gq=6000, Gs=6000, n=400000, Kq=9, Ks=9, group_by_query=True)
     assert st["after_tandem"] > 1000
 
 
