@@ -50,6 +50,8 @@ const char* jx_version(void);
 /* sizeof() of jx_bed, jx_filter_opts, jx_filter_result, jx_scan_opts, jx_scan_result,
  * jx_liftover_result as this library was compiled (binding self-check) */
 void jx_abi_sizes(int32_t out[6]);
+/* sizeof(jx_synfind_result) as compiled (the same check for the struct added with SURVEY 8(f) N3) */
+int32_t jx_abi_size_synfind(void);
 /* number of kernels this library launched on ctx since creation (bench.py "gpu_launches") */
 int64_t jx_launch_count(jx_ctx* ctx);
 /* the context's CUDA stream as an integer handle (for event timing on the launching stream) */

@@ -34,7 +34,9 @@ void jx_abi_sizes(int32_t out[6]) {
   out[3] = (int32_t)sizeof(jx_scan_opts); out[4] = (int32_t)sizeof(jx_scan_result); out[5] = (int32_t)sizeof(jx_liftover_result);
 }
 
-const char* jx_version(void) { return "jcvi_b200 0.1 (sm_100a)"; }
+int32_t jx_abi_size_synfind(void) { return (int32_t)sizeof(jx_synfind_result); }
+
+const char* jx_version(void) { return "jcvi_b200 0.2 (sm_100a)"; }
 
 int jx_ctx_create(int device, jx_ctx** out) {
   if (!out) return JX_EARG;
