@@ -205,8 +205,10 @@ void jx_liftover_result_free(jx_liftover_result* r);
  * jx_blastfilter -> jx_scan_filtered -> jx_liftover_text(same raw text, the anchors just found, dist = liftover_dist)
  * with everything that flows between the stages left on the device: the survivors go to scan as device arrays ("%.3g"
  * score round trip applied there), the anchors go to liftover as device arrays while their copy to the host is in
- * flight, liftover re-uses the records blastfilter tokenized.  Host text is uploaded (jx_text_upload) first; device text
- * must come from jx_text_upload.  The three results are exactly those of the three separate calls. */
+ * flight, liftover re-uses the records blastfilter tokenized, the `.filtered` text (want_text) crosses PCIe on the copy
+ * stream while scan and liftover run and is complete when the call returns.  Host text is uploaded (jx_text_upload: 64 MiB
+ * chunks, tokenized as they land) first; device text must come from jx_text_upload / jx_file_upload.  The three results
+ * are exactly those of the three separate calls. */
 int jx_pipeline(jx_ctx* ctx, const char* text, int64_t nbytes, int text_on_device, const jx_filter_opts* fopts,
                 const jx_scan_opts* sopts, int liftover_dist, jx_filter_result* fout, jx_scan_result* sout,
                 jx_liftover_result* lout);
