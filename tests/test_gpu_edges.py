@@ -241,3 +241,35 @@ def test_tiny_and_truncated_tables(tmp_path, mods):
         oracle.blastfilter(last, qbed, sbed, out_path=last + ".orc", cscore=0)
         bf.main([last] + beds + ["--cscore=0"])
         assert read(last + ".filtered") == read(last + ".orc"), n
+
+
+def test_writer_lines_longer_than_the_staged_window(tmp_path):
+    """Survivors whose lines exceed the 208 bytes the `.filtered` writer stages per line (names of ~100 bytes): the reader
+    continues in global memory; bytes identical to the oracle (and the tokenizer takes its generic route for such names)."""
+    import oracle
+    from jcvi_b200.compara import blastfilter
+    d = str(tmp_path)
+    rng = np.random.default_rng(4)
+    nq = ns = 60
+    qn = ["Q" + "q" * (70 + (i % 37)) + "%03d" % i for i in range(nq)]
+    sn = ["S" + "s" * (75 + (i % 41)) + "%03d" % i for i in range(ns)]
+    with open(os.path.join(d, "A.bed"), "w") as fw:
+        for i, n in enumerate(qn):
+            fw.write("chr%d\t%d\t%d\t%s\n" % (1 + i // 30, 1000 * i, 1000 * i + 500, n))
+    with open(os.path.join(d, "B.bed"), "w") as fw:
+        for i, n in enumerate(sn):
+            fw.write("chr%d\t%d\t%d\t%s\n" % (1 + i // 30, 1000 * i, 1000 * i + 500, n))
+    last = os.path.join(d, "A.B.last")
+    with open(last, "w") as fw:
+        for k in range(4000):
+            i, j = int(rng.integers(0, nq)), int(rng.integers(0, ns))
+            if k % 3 == 0:
+                j = i
+            fw.write("%s\t%s\t%.2f\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.1e\t%d\n" % (
+                qn[i], sn[j], 70 + 30 * rng.random(), rng.integers(50, 2000), rng.integers(0, 50), rng.integers(0, 9),
+                rng.integers(1, 900), rng.integers(900, 3000), rng.integers(1, 900), rng.integers(900, 3000),
+                10.0 ** -float(rng.integers(3, 150)), rng.integers(100, 9000)))
+    oracle.blastfilter(last, os.path.join(d, "A.bed"), os.path.join(d, "B.bed"), out_path=last + ".orc", cscore=0.5, tandem_Nmax=0)
+    blastfilter.main([last, "--cscore=0.5", "--tandem_Nmax=0"])
+    got, want = read(last + ".filtered"), read(last + ".orc")
+    assert got == want and want.count(b"\n") > 100 and max(len(x) for x in want.split(b"\n")) > 208
