@@ -94,6 +94,23 @@ def test_file_reader_variants_give_identical_outputs(tmp_path):
     open(bad, "wb").write(raw)
     with pytest.raises(ValueError):
         eng.upload_file(bad)
+    # a stream that inflates to far more than its size hint (last member small, ratio ~ 100): the device text grows while
+    # the pieces are copied
+    line = next(x for x in text.split(b"\n") if x and not x.startswith(b"#")) + b"\n"
+    rep = line * 600000                                       # ~ 40 MB of one line
+    sub = os.path.join(d, "grow"); os.makedirs(sub)
+    shutil.copy(qbed, sub); shutil.copy(sbed, sub)
+    fplain, fgz = os.path.join(sub, "A.B.last"), os.path.join(sub, "gz", "A.B.last.gz")
+    os.makedirs(os.path.dirname(fgz)); shutil.copy(qbed, os.path.dirname(fgz)); shutil.copy(sbed, os.path.dirname(fgz))
+    open(fplain, "wb").write(rep)
+    with open(fgz, "wb") as fh:
+        fh.write(gzip.compress(rep[: len(line) * 590000], 6)); fh.write(gzip.compress(rep[len(line) * 590000:], 6))
+    assert os.path.getsize(fgz) * 20 < len(rep)
+    dev = eng.upload_file(fgz)
+    assert dev.nbytes == len(rep) and dev.kind == "gzip"
+    blastfilter.main([fplain, "--cscore=0.7", "--qbed=" + qbed, "--sbed=" + sbed])
+    blastfilter.main([fgz, "--cscore=0.7", "--qbed=" + qbed, "--sbed=" + sbed])
+    assert read(fgz + ".filtered") == read(fplain + ".filtered") and len(read(fplain + ".filtered")) > 0
     # empty file
     open(os.path.join(d, "empty.last"), "wb").close()
     assert eng.upload_file(os.path.join(d, "empty.last")).nbytes == 0
