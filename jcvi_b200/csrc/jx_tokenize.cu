@@ -53,11 +53,7 @@ struct TokArgs {
 #define VAL_MASK ((1ull << 62) - 1)
 
 #ifndef JX_LCAP
-#if JX_GROUP == 32
-#define JX_LCAP 128
-#else
 #define JX_LCAP 1024
-#endif
 #endif
 constexpr int LCAP = JX_LCAP;     // line starts of a tile kept in shared memory (more -> search path)
 
@@ -188,10 +184,9 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
   uint32_t* s_pref = g_pref[grp]; unsigned long long* s_start = g_start[grp];
   uint16_t* s_lpos = g_lpos[grp]; uint32_t* s_warp = g_warp[grp]; uint32_t* s_next = g_next[grp];
   unsigned long long& s_base = g_base[grp];
-  // group-wide synchronisation: a CTA barrier for one group per CTA, a warp barrier for warp groups
-  auto gsync = [&]() { if (JX_GROUP == 32) __syncwarp(); else __syncthreads(); };
+  // group-wide synchronisation (one group per CTA: a CTA barrier)
+  auto gsync = [&]() { __syncthreads(); };
   auto gany = [&](bool p) -> bool {
-    if (JX_GROUP == 32) { __syncwarp(); return __any_sync(0xFFFFFFFFu, p) != 0; }
     return __syncthreads_or(p) != 0;
   };
   uint32_t c_comment = 0, c_mapped = 0, c_unmapped = 0, c_hard = 0, c_long = 0, c_excl = 0, c_self = 0, c_lines = 0;
@@ -284,9 +279,7 @@ __global__ void __launch_bounds__(JX_TOK_THREADS, JX_TOK_MINBLK) k_tokenize(cons
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
   uint32_t wbase = 0, nlines = 0;
-  if (JX_GROUP == 32) {
-    nlines = __shfl_sync(0xFFFFFFFFu, inc, 31);
-  } else {
+  {
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
 #pragma unroll
