@@ -387,6 +387,11 @@ void jx_synfind_result_free(jx_synfind_result* r);
 int jx_best_table_copy(jx_ctx* ctx, float* out, uint32_t n);
 /* counters of the records jx_cscore_begin retained: 0 non-'#' lines, 1 mapped, 2 unmapped */
 int jx_session_counts(jx_ctx* ctx, int64_t out[3]);
+/* HOST helper: do the lines of a table come in runs of equal queries (the order lastal / BLAST write)?  Looks at the
+ * first 256 KiB; 1 when at least half of the lines repeat the first field of the line before.  This is the test that
+ * picks the tokenizer instantiation which merges a warp's equal-query best-score reductions (results are the same
+ * either way). */
+int jx_host_query_runs(const char* text, int64_t nbytes);
 /* HOST helper for the few lines that survive a filter: BlastLine(line) and str(BlastLine) with the
  * very glibc calls cblast.pyx makes (sscanf format cblast.pyx:15, start<=stop swap 114-120, sprintf
  * format cblast.pyx:17).  query128 / subject128: char[128]; returns the number of converted fields. */

@@ -70,7 +70,7 @@ EXPORTS = [
     "jx_host_blastline", "jx_blast_cscore", "jx_blast_filter", "jx_mcscan", "jx_block_stats",
     "jx_pipeline", "jx_shard_reset", "jx_shard_slots", "jx_shard_candidates", "jx_shard_partition", "jx_shard_pairs",
     "jx_shard_survivors", "jx_shard_order", "jx_scan_cands", "jx_shard_near", "jx_shard_lift", "jx_cscore_begin", "jx_cscore_finish", "jx_near_lines", "jx_cscore_finish_device", "jx_near_lines_device", "jx_free", "jx_abi_sizes",
-    "jx_synfind_text", "jx_synfind_points", "jx_synfind_result_free", "jx_file_upload", "jx_abi_size_synfind",
+    "jx_synfind_text", "jx_synfind_points", "jx_synfind_result_free", "jx_file_upload", "jx_abi_size_synfind", "jx_host_query_runs",
 ]
 
 _lib = None
@@ -180,6 +180,7 @@ def lib():
         if list(sizes) != mine:
             raise ImportError("jcvi_b200: struct layout mismatch between _cabi.py %s and libjcvi_b200.so %s" % (mine, list(sizes)))
         L.jx_abi_size_synfind.restype = ctypes.c_int32
+        L.jx_host_query_runs.argtypes = [ctypes.c_char_p, ctypes.c_int64]
         if L.jx_abi_size_synfind() != ctypes.sizeof(JxSynfindResult):
             raise ImportError("jcvi_b200: jx_synfind_result layout mismatch between _cabi.py and libjcvi_b200.so")
         _lib = L

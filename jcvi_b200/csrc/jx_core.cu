@@ -34,6 +34,10 @@ void jx_abi_sizes(int32_t out[6]) {
   out[3] = (int32_t)sizeof(jx_scan_opts); out[4] = (int32_t)sizeof(jx_scan_result); out[5] = (int32_t)sizeof(jx_liftover_result);
 }
 
+int jx_host_query_runs(const char* text, int64_t nbytes) {
+  return (text && nbytes > 0) ? jx_sample_query_runs((const uint8_t*)text, (size_t)nbytes) : 0;
+}
+
 int32_t jx_abi_size_synfind(void) { return (int32_t)sizeof(jx_synfind_result); }
 
 const char* jx_version(void) { return "jcvi_b200 0.2 (sm_100a)"; }

@@ -169,6 +169,24 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     assert "GLOO_OK" in out.stdout
 
 
+def test_query_run_sample_tells_grouped_from_shuffled_tables(tmp_path):
+    """The host test that picks the tokenizer's MERGE_Q instantiation (jx_sample_query_runs)."""
+    import numpy as np
+    from jcvi_b200 import _cabi, synth
+    L = _cabi.lib()
+    qbed, sbed, last = synth.write_dataset(str(tmp_path), "A", "B", 5, 2000, 2000, 40000, Kq=3, Ks=3)
+    text = open(last, "rb").read()
+    assert L.jx_host_query_runs(text, len(text)) == 0                      # the generator shuffles the lines
+    rows = [r for r in text.split(b"\n") if r and not r.startswith(b"#")]
+    rows.sort(key=lambda r: r.split(b"\t", 1)[0])
+    grouped = b"# header\n" + b"\n".join(rows) + b"\n"
+    assert L.jx_host_query_runs(grouped, len(grouped)) == 1               # lastal / BLAST order
+    assert L.jx_host_query_runs(b"", 0) == 0
+    assert L.jx_host_query_runs(b"a\tb\n" * 8, 32) == 0                    # too few lines to tell
+    assert L.jx_host_query_runs(b"a\tb\n" * 64, 256) == 1
+    assert L.jx_host_query_runs(b"\n\n#x\n" * 100, 500) == 0              # blank and comment lines only
+
+
 def test_sharded_status_agreement_picks_one_exception_class():
     import numpy as np
     import pytest
